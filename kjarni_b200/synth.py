@@ -1,0 +1,155 @@
+"""Random-init model directories and synthetic inputs (no network, no checkpoints).
+
+Writes exactly what Kjarni's own loader accepts (`EncoderLoader::load_from_pretrained`,
+kjarni-transformers/src/pipeline/encoder/loader.rs:82-141): `model.safetensors`
+(F32, tensor names per the three layouts in SURVEY.md Appendix B), `config.json`
+and a minimal WordLevel `tokenizer.json` -- the same recipe as the reference's
+fixture test kjarni-models/src/models/sentence_encoder/tests.rs:16-176.
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+ARCHS = {
+    # name: (family, hidden, layers, heads, intermediate, vocab, max_pos, type_vocab, num_labels)
+    "minilm-l6": ("bert", 384, 6, 12, 1536, 30522, 512, 2, 0),
+    "minilm-l6-cross-encoder": ("bert_prefixed", 384, 6, 12, 1536, 30522, 512, 2, 1),
+    "distilbert-sst2": ("distilbert", 768, 6, 12, 3072, 30522, 512, 0, 2),
+    "bert-base": ("bert", 768, 12, 12, 3072, 30522, 512, 2, 0),
+    # tiny shapes for CPU-speed tests
+    "tiny-bert": ("bert", 64, 2, 4, 256, 1000, 64, 2, 0),
+    "tiny-cross-encoder": ("bert_prefixed", 64, 2, 4, 256, 1000, 64, 2, 1),
+    "tiny-distilbert": ("distilbert", 128, 2, 2, 512, 1000, 64, 0, 2),
+}
+
+
+def write_safetensors(path: str, tensors: Dict[str, np.ndarray]) -> None:
+    """Standard safetensors container: u64 LE header size, JSON header, raw LE data."""
+    header = {}
+    off = 0
+    order = sorted(tensors)
+    for name in order:
+        a = np.ascontiguousarray(tensors[name], dtype="<f4")
+        header[name] = {"dtype": "F32", "shape": list(a.shape), "data_offsets": [off, off + a.nbytes]}
+        off += a.nbytes
+    hj = json.dumps(header, separators=(",", ":")).encode()
+    hj += b" " * ((8 - len(hj) % 8) % 8)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<Q", len(hj)))
+        f.write(hj)
+        for name in order:
+            f.write(np.ascontiguousarray(tensors[name], dtype="<f4").tobytes())
+
+
+def make_weights(arch: str, seed: int = 1234) -> Tuple[Dict[str, np.ndarray], dict]:
+    family, H, L, heads, I, vocab, max_pos, type_vocab, num_labels = ARCHS[arch]
+    rng = np.random.default_rng(seed)
+    t: Dict[str, np.ndarray] = {}
+
+    def mat(*shape, std=0.02):
+        return (rng.standard_normal(shape) * std).astype(np.float32)
+
+    def bias(n):
+        return (rng.standard_normal(n) * 0.05).astype(np.float32)
+
+    def gamma(n):
+        return (1.0 + rng.standard_normal(n) * 0.05).astype(np.float32)
+
+    if family == "distilbert":
+        ep, lp = "distilbert.embeddings.", "distilbert.transformer.layer.{}."
+        n = dict(q="attention.q_lin", k="attention.k_lin", v="attention.v_lin", o="attention.out_lin",
+                 ln1="sa_layer_norm", f1="ffn.lin1", f2="ffn.lin2", ln2="output_layer_norm")
+    else:
+        pre = "bert." if family == "bert_prefixed" else ""
+        ep, lp = pre + "embeddings.", pre + "encoder.layer.{}."
+        n = dict(q="attention.self.query", k="attention.self.key", v="attention.self.value",
+                 o="attention.output.dense", ln1="attention.output.LayerNorm",
+                 f1="intermediate.dense", f2="output.dense", ln2="output.LayerNorm")
+    t[ep + "word_embeddings.weight"] = mat(vocab, H)
+    t[ep + "position_embeddings.weight"] = mat(max_pos, H)
+    if type_vocab:
+        t[ep + "token_type_embeddings.weight"] = mat(type_vocab, H)
+    t[ep + "LayerNorm.weight"] = gamma(H)
+    t[ep + "LayerNorm.bias"] = bias(H)
+    for i in range(L):
+        p = lp.format(i)
+        for key, (o, k) in dict(q=(H, H), k=(H, H), v=(H, H), o=(H, H), f1=(I, H), f2=(H, I)).items():
+            t[p + n[key] + ".weight"] = mat(o, k)
+            t[p + n[key] + ".bias"] = bias(o)
+        for key in ("ln1", "ln2"):
+            t[p + n[key] + ".weight"] = gamma(H)
+            t[p + n[key] + ".bias"] = bias(H)
+    if family == "distilbert":
+        t["pre_classifier.weight"] = mat(H, H, std=0.05)
+        t["pre_classifier.bias"] = bias(H)
+        t["classifier.weight"] = mat(num_labels, H, std=0.5)
+        t["classifier.bias"] = bias(num_labels)
+        cfg = dict(model_type="distilbert", activation="gelu", dim=H, hidden_dim=I, n_layers=L, n_heads=heads,
+                   max_position_embeddings=max_pos, vocab_size=vocab,
+                   id2label={"0": "NEGATIVE", "1": "POSITIVE"}, label2id={"NEGATIVE": 0, "POSITIVE": 1})
+    else:
+        cfg = dict(model_type="bert", hidden_size=H, num_hidden_layers=L, num_attention_heads=heads,
+                   intermediate_size=I, vocab_size=vocab, layer_norm_eps=1e-12, hidden_act="gelu",
+                   type_vocab_size=type_vocab, max_position_embeddings=max_pos)
+        if family == "bert_prefixed":
+            t["bert.pooler.dense.weight"] = mat(H, H, std=0.05)
+            t["bert.pooler.dense.bias"] = bias(H)
+            t["classifier.weight"] = mat(num_labels, H, std=0.5)
+            t["classifier.bias"] = bias(num_labels)
+            cfg["num_labels"] = num_labels
+            cfg["id2label"] = {str(i): f"LABEL_{i}" for i in range(num_labels)}
+            cfg["_name_or_path"] = "cross-encoder/ms-marco-MiniLM-L-6-v2"
+    return t, cfg
+
+
+def write_model_dir(path: str, arch: str, seed: int = 1234) -> str:
+    """Creates `path` with model.safetensors + config.json + tokenizer.json."""
+    os.makedirs(path, exist_ok=True)
+    t, cfg = make_weights(arch, seed)
+    write_safetensors(os.path.join(path, "model.safetensors"), t)
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(cfg, f, indent=1)
+    vocab = {"[PAD]": 0, "[UNK]": 100, "[CLS]": 101, "[SEP]": 102}
+    tok = {"version": "1.0", "truncation": None, "padding": None, "added_tokens": [], "normalizer": None,
+           "pre_tokenizer": {"type": "Whitespace"}, "post_processor": None, "decoder": None,
+           "model": {"type": "WordLevel", "vocab": vocab, "unk_token": "[UNK]"}}
+    with open(os.path.join(path, "tokenizer.json"), "w") as f:
+        json.dump(tok, f)
+    return path
+
+
+def synth_tokens(batch: int, seq: int, vocab: int = 30522, *, regime: str = "T", seed: int = 42,
+                 pair: bool = False) -> Tuple[np.ndarray, np.ndarray, Optional[np.ndarray]]:
+    """Synthetic token ids / mask / type ids.
+
+    regime 'T' (throughput): every row has length `seq`.  regime 'P' (parity):
+    lengths uniform in [seq/4, seq], plus one length-1 row.  [CLS]=101 first,
+    [SEP]=102 last, body uniform in [lo, vocab), pad id 0."""
+    rng = np.random.default_rng(seed)
+    lo = 1000 if vocab > 2000 else 200
+    ids = np.zeros((batch, seq), dtype=np.uint32)
+    mask = np.zeros((batch, seq), dtype=np.uint32)
+    types = np.zeros((batch, seq), dtype=np.uint32) if pair else None
+    if regime == "T":
+        lens = np.full(batch, seq)
+    else:
+        lens = rng.integers(max(seq // 4, 2), seq + 1, size=batch)
+        lens[batch // 2] = 1
+    for b in range(batch):
+        n = int(lens[b])
+        row = rng.integers(lo, vocab, size=n)
+        row[0] = 101
+        if n > 1:
+            row[n - 1] = 102
+        ids[b, :n] = row
+        mask[b, :n] = 1
+        if pair and n > 3:
+            cut = int(rng.integers(2, n - 1))
+            ids[b, cut - 1] = 102
+            types[b, cut:n] = 1
+    return ids, mask, types
