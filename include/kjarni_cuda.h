@@ -1,0 +1,196 @@
+/* kjarni_cuda.h -- C ABI of libkjarni_cuda.so, the B200 (sm_100a) backend for Kjarni's
+ * data-parallel hot path: the batched BERT-family encoder forward behind
+ * Embedder / Classifier / Reranker, and the brute-force cosine top-k scan behind
+ * Searcher.  This is the inner FFI a Rust `kjarni-cuda-sys` crate would bind
+ * (see INTEGRATION.md); it fills the slot that `Device::Wgpu` / `KJARNI_DEVICE_GPU`
+ * selects today.  Plain pointers and sizes only; caller-allocated outputs; opaque
+ * handles; no allocation crosses the boundary.
+ *
+ * All `file:line` citations are into the reference tree (olafurjohannsson/kjarni),
+ * KT = crates/kjarni-transformers/src, KM = crates/kjarni-models/src,
+ * KS = crates/kjarni-search/src, KR = crates/kjarni-rag/src, KF = crates/kjarni-ffi/src.
+ *
+ * Threading: handles may be used from several host threads; calls on one handle are
+ * serialised internally (the reference's wgpu path serialises on a pool mutex too,
+ * KT/cpu/encoder/traits.rs:108-112).  Every call returns after its stream has
+ * synchronised unless the name ends in `_async`.
+ */
+#ifndef KJARNI_CUDA_H
+#define KJARNI_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same numbering as KjarniErrorCode (KF/src/error.rs:14-40). */
+typedef enum KjcStatus {
+    KJC_OK = 0,
+    KJC_NULL_POINTER = 1,
+    KJC_INVALID_UTF8 = 2,
+    KJC_MODEL_NOT_FOUND = 3,
+    KJC_LOAD_FAILED = 4,
+    KJC_INFERENCE_FAILED = 5,
+    KJC_GPU_UNAVAILABLE = 6,
+    KJC_INVALID_CONFIG = 7,
+    KJC_CANCELLED = 8,
+    KJC_TIMEOUT = 9,
+    KJC_STREAM_ENDED = 10,
+    KJC_UNKNOWN = 255
+} KjcStatus;
+
+/* Thread-local message of the last failing call on this thread; valid until the next
+ * failure on the same thread (KF/src/error.rs:7-9,57-101). */
+const char* kjc_last_error_message(void);
+void kjc_clear_error(void);
+const char* kjc_error_name(int status);
+const char* kjc_version(void);
+/* Number of visible CUDA devices; a negative value means no usable driver. */
+int kjc_device_count(void);
+
+/* ------------------------------------------------------------------ encoder */
+
+typedef struct KjcEncoder KjcEncoder;
+
+/* Layout selected from config.json (KM/models/sentence_encoder/model.rs:41-54,
+ * KM/models/sentence_encoder/configs.rs:271-364,638-687). */
+typedef enum KjcArch { KJC_ARCH_BERT = 0, KJC_ARCH_BERT_PREFIXED = 1, KJC_ARCH_DISTILBERT = 2 } KjcArch;
+/* Head auto-detected from tensor names, first match wins (KT/cpu/encoder/classifier.rs:113-206). */
+typedef enum KjcHeadKind {
+    KJC_HEAD_ABSENT = 0,      /* sentence encoder: no classifier tensors */
+    KJC_HEAD_DENSE_TANH = 1,  /* classifier.dense + tanh + classifier.out_proj */
+    KJC_HEAD_PRE_RELU = 2,    /* pre_classifier + ReLU + classifier (DistilBERT) */
+    KJC_HEAD_POOLER_TANH = 3, /* bert.pooler.dense + tanh + classifier (cross-encoder) */
+    KJC_HEAD_LINEAR = 4       /* classifier only */
+} KjcHeadKind;
+
+typedef struct KjcEncoderInfo {
+    int32_t arch;         /* KjcArch */
+    int32_t hidden_size;
+    int32_t num_layers;
+    int32_t num_heads;
+    int32_t intermediate_size; /* read from the fc1 weight shape, never from metadata */
+    int32_t vocab_size;
+    int32_t max_position_embeddings;
+    int32_t type_vocab_size; /* 0: no token-type table (DistilBERT) */
+    int32_t position_offset; /* extra_pos_embeddings: 0 BERT/DistilBERT */
+    int32_t head_kind;       /* KjcHeadKind */
+    int32_t num_labels;      /* rows of the classifier weight; 0 without a head */
+    int32_t device;
+    float layer_norm_eps;
+} KjcEncoderInfo;
+
+/* Loads `<model_dir>/config.json` + `<model_dir>/model.safetensors` (F32/F16/BF16 tensors),
+ * resolves the tensor-name layout, pre-packs GEMM weights to bf16 (Q/K/V fused to [3H,H])
+ * and uploads everything to `device` once.  Mirrors EncoderLoader::load_from_pretrained
+ * (KT/pipeline/encoder/loader.rs:82-141) + CpuTransformerEncoder::new
+ * (KT/cpu/encoder/transformer_encoder.rs:30-235).  `tokenizer.json` is not read here
+ * (token ids come in through the API).
+ * Errors: KJC_MODEL_NOT_FOUND (missing dir/files), KJC_LOAD_FAILED (bad safetensors, missing
+ * tensor, shape mismatch), KJC_INVALID_CONFIG (bad config.json / unsupported sizes),
+ * KJC_GPU_UNAVAILABLE (no device / not sm_100). */
+int kjc_encoder_create(const char* model_dir, int device, KjcEncoder** out);
+void kjc_encoder_destroy(KjcEncoder* enc);
+int kjc_encoder_info(const KjcEncoder* enc, KjcEncoderInfo* out);
+/* Label `i` of config.json:id2label (sorted by numeric key), or NULL. Borrowed; valid until destroy.
+ * (KF/src/classifier.rs:253-300 labels / num_labels.) */
+const char* kjc_encoder_label(const KjcEncoder* enc, int i);
+
+typedef enum KjcOutput {
+    KJC_OUT_HIDDEN = 0,     /* out: f32 [B,S,H] last hidden state -- get_hidden_states_batch_from_ids, KT/cpu/encoder/traits.rs:66-139 */
+    KJC_OUT_POOLED = 1,     /* out: f32 [B,H]   pooled (+L2)      -- encode_batch, KT/cpu/encoder/traits.rs:204-225,529-536 */
+    KJC_OUT_LOGITS = 2      /* out: f32 [B,C]   head logits       -- predict_logits, KM/models/sequence_classifier/mod.rs:266-346;
+                                                                     predict_pairs, KM/models/cross_encoder/model.rs:170-240 */
+} KjcOutput;
+typedef enum KjcPooling { KJC_POOL_MEAN = 0, KJC_POOL_CLS = 1, KJC_POOL_MAX = 2, KJC_POOL_LAST = 3 } KjcPooling;
+/* Which reference CPU variant's padding convention to reproduce (they differ only for a fully
+ * padded sequence): ALLOC = masked score := -1e9 (KT/utils/masks.rs:4-36; Classifier/Reranker always),
+ * NOALLOC = -inf (KT/cpu/encoder/encoder_self_attention.rs:311-325; Embedder when B*S >= 1000 or <= 1),
+ * AUTO = ComputeStrategy::select (KT/cpu/strategy.rs:29-47) for POOLED/HIDDEN, ALLOC for LOGITS. */
+typedef enum KjcMaskConvention { KJC_MASK_AUTO = 0, KJC_MASK_ALLOC = 1, KJC_MASK_NOALLOC = 2 } KjcMaskConvention;
+
+typedef struct KjcForwardOptions {
+    int32_t output;          /* KjcOutput */
+    int32_t pooling;         /* KjcPooling (POOLED only) */
+    int32_t normalize;       /* L2-normalise pooled rows (POOLED only) */
+    int32_t mask_convention; /* KjcMaskConvention */
+} KjcForwardOptions;
+
+/* One encoder forward over a batch of token ids, HOST buffers in and out.
+ *   ids       u32 [B*S]  token ids (id >= vocab -> zero embedding row, KT/cpu/embeddings/mod.rs:227-246)
+ *   mask      f32 [B*S]  1 = token, 0 = padding; NULL = all ones
+ *   type_ids  u32 [B*S]  or NULL (row 0 of the type table is added to every token, KT/cpu/embeddings/mod.rs:216-223)
+ *   out       f32, caller-allocated, size per `opts->output`
+ * Host->device copies of ids/mask/type_ids and the device->host copy of `out` are part of the call.
+ * Errors: KJC_NULL_POINTER, KJC_INVALID_CONFIG (S > max positions is allowed as in the reference: positions
+ * beyond the table add nothing; S > 512 or B*S == 0 is rejected), KJC_INFERENCE_FAILED (CUDA error, or a
+ * token-type id out of range -- the reference panics there, KT/cpu/embeddings/mod.rs:312-317). */
+int kjc_encoder_forward(KjcEncoder* enc, const uint32_t* ids, const float* mask, const uint32_t* type_ids, int batch,
+                        int seq_len, const KjcForwardOptions* opts, float* out);
+
+/* Same forward with DEVICE pointers (all on the encoder's device), enqueued on `stream`
+ * (a cudaStream_t; NULL = the encoder's own stream) without synchronising. */
+int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_type_ids,
+                                     int batch, int seq_len, const KjcForwardOptions* opts, float* d_out, void* stream);
+/* Largest number of sequences processed per internal micro-batch for `seq_len` (activations are
+ * sized to stay L2-resident); larger batches are looped internally. */
+int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len);
+/* Number of kernel launches the last forward on this handle enqueued (for bench bookkeeping). */
+int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc);
+
+/* softmax over the label axis in place (SequenceClassifier::classify_scores_batch,
+ * KM/models/sequence_classifier/mod.rs:248-263 -> KT/activations.rs:223-242). Host-side helper. */
+void kjc_softmax_rows(float* logits, int rows, int cols);
+
+/* ---------------------------------------------------------------- index scan */
+
+typedef struct KjcIndex KjcIndex;
+typedef enum KjcScanMode {
+    KJC_SCAN_SEGMENT = 0,     /* Segment::search_vectors semantics, KR/segment.rs:307-337,355-370 */
+    KJC_SCAN_VECTORSTORE = 1  /* VectorStore::search semantics, KS/vector.rs:131-165 */
+} KjcScanMode;
+
+/* An index shard: `capacity_rows` x `dim` fp32 rows resident in HBM on `device`.
+ * `id_base` is the global id of local row 0 (IndexReader::local_to_global, KR/index_reader.rs:313-319). */
+int kjc_index_create(int dim, uint64_t capacity_rows, uint64_t id_base, int device, KjcIndex** out);
+void kjc_index_destroy(KjcIndex* idx);
+uint64_t kjc_index_len(const KjcIndex* idx);
+int kjc_index_dim(const KjcIndex* idx);
+/* Append `n` rows from host memory (raw little-endian f32, the `vectors.bin` layout, KR/segment.rs:87-123). */
+int kjc_index_add_rows(KjcIndex* idx, const float* rows, uint64_t n);
+/* Append the rows of one on-disk segment file `<segment_dir>/vectors.bin` (KR/segment.rs:195-262);
+ * the row count is file_size / (4*dim). */
+int kjc_index_load_vectors_bin(KjcIndex* idx, const char* path);
+/* Append `n` rows of the counter-based synthetic generator shared with the oracle
+ * (bench / test input only): x[r,c] = (hash32(seed, row0+r, c) >> 8) * 2^-24 - 0.5. */
+int kjc_index_append_synthetic(KjcIndex* idx, uint32_t seed, uint64_t row0, uint64_t n);
+/* Copy local rows [row, row+n) back to the host (Segment::get_embedding, KR/segment.rs:240-262). */
+int kjc_index_get_rows(const KjcIndex* idx, uint64_t row, uint64_t n, float* out);
+
+/* Top-k cosine search of `nq` HOST queries [nq, dim] against this shard.
+ *   out_ids    u64 [nq*k]  global ids, order (score desc, id asc); UINT64_MAX where fewer than k results
+ *   out_scores f32 [nq*k]  -inf where empty
+ *   out_counts i32 [nq] or NULL: number of valid results per query (0 for a zero-norm query in SEGMENT mode)
+ * Errors: KJC_NULL_POINTER, KJC_INVALID_CONFIG (k < 1 or k > 256, nq < 1), KJC_INFERENCE_FAILED. */
+int kjc_index_search(KjcIndex* idx, const float* queries, int nq, int k, int mode, uint64_t* out_ids, float* out_scores,
+                     int32_t* out_counts);
+/* Device-pointer variant, enqueued on `stream` (NULL = the index's stream), no synchronise.
+ * Produces this shard's sorted candidates -- the per-segment top-k of IndexReader::search_semantic. */
+int kjc_index_search_device_async(KjcIndex* idx, const float* d_queries, int nq, int k, int mode, uint64_t* d_out_ids,
+                                  float* d_out_scores, int32_t* d_out_counts, void* stream);
+/* Merge `n_lists` sorted candidate lists (e.g. one per shard/rank after the NVLink gather) into the final
+ * top-k per query: concat -> stable sort desc -> truncate of KR/index_reader.rs:212-224 with the canonical
+ * tie-break (score desc, global id asc).  Device pointers: cand_* are [n_lists, nq, k]. */
+int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const float* d_cand_scores, int n_lists, int nq, int k,
+                                uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, void* stream);
+int64_t kjc_index_last_launch_count(const KjcIndex* idx);
+
+/* cosine of two host vectors (kjarni_cosine_similarity, KF/src/lib.rs:177-188 -> KS/vector.rs:131-148). */
+float kjc_cosine_similarity(const float* a, const float* b, size_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KJARNI_CUDA_H */

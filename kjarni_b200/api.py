@@ -1,0 +1,249 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C ABI.
+
+Same names and argument meaning as the Rust API the CUDA backend sits behind
+(citations into /root/reference/crates; KT = kjarni-transformers/src, KM = kjarni-models/src,
+KS = kjarni-search/src, KR = kjarni-rag/src):
+
+  EncoderModel.get_hidden_states_batch_from_ids   KT/cpu/encoder/traits.rs:66-139
+  EncoderModel.encode_batch_from_ids              KT/cpu/encoder/traits.rs:204-225 (SentenceEncoder::encode_batch on ids)
+  EncoderModel.predict_logits                     KM/models/sequence_classifier/mod.rs:266-346
+  EncoderModel.classify_scores_batch              KM/models/sequence_classifier/mod.rs:248-263
+  EncoderModel.predict_pairs / rerank             KM/models/cross_encoder/model.rs:170-255
+  Segment.search_vectors / get_embedding          KR/segment.rs:240-262,307-337
+  VectorStore.search                              KS/vector.rs:150-165
+  IndexReader.search_semantic                     KR/index_reader.rs:207-228
+
+Everything numeric happens inside libkjarni_cuda.so; numpy is only the container for
+host buffers.  No torch import here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class EncoderModel:
+    """One encoder checkpoint resident on one GPU (KjcEncoder)."""
+
+    def __init__(self, model_dir: str, device: int = 0):
+        self._h = C.c_void_p()
+        N.check(N.lib().kjc_encoder_create(str(model_dir).encode(), int(device), C.byref(self._h)))
+        info = N.KjcEncoderInfo()
+        N.check(N.lib().kjc_encoder_info(self._h, C.byref(info)))
+        self.info = info
+        self.arch = N.ARCH_NAMES[info.arch]
+        self.head_kind = N.HEAD_NAMES[info.head_kind]
+        self.hidden_size = info.hidden_size
+        self.num_labels = info.num_labels
+        self.device = info.device
+        self.labels: List[str] = []
+        i = 0
+        while True:
+            s = N.lib().kjc_encoder_label(self._h, i)
+            if s is None:
+                break
+            self.labels.append(s.decode())
+            i += 1
+
+    @classmethod
+    def from_pretrained(cls, model_dir: str, device: int = 0) -> "EncoderModel":
+        return cls(model_dir, device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().kjc_encoder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ core
+    def _forward(self, ids, mask, type_ids, output, pooling=N.POOL_MEAN, normalize=True, mask_convention=N.MASK_AUTO) -> np.ndarray:
+        ids = _c(ids, np.uint32)
+        if ids.ndim != 2:
+            raise ValueError("input_ids must be [batch, seq]")
+        B, S = ids.shape
+        maskf = None if mask is None else _c(mask, np.float32)
+        types = None if type_ids is None else _c(type_ids, np.uint32)
+        if maskf is not None and maskf.shape != ids.shape:
+            raise ValueError("attention_mask shape mismatch")
+        if types is not None and types.shape != ids.shape:
+            raise ValueError("token_type_ids shape mismatch")
+        if output == N.OUT_HIDDEN:
+            out = np.empty((B, S, self.hidden_size), np.float32)
+        elif output == N.OUT_POOLED:
+            out = np.empty((B, self.hidden_size), np.float32)
+        else:
+            out = np.empty((B, max(self.num_labels, 0)), np.float32)
+        opts = N.KjcForwardOptions(output, pooling, 1 if normalize else 0, mask_convention)
+        N.check(N.lib().kjc_encoder_forward(self._h, _ptr(ids), _ptr(maskf), _ptr(types), B, S, C.byref(opts), _ptr(out)))
+        return out
+
+    def get_hidden_states_batch_from_ids(self, input_ids, attention_mask, mask_convention=N.MASK_AUTO) -> np.ndarray:
+        return self._forward(input_ids, attention_mask, None, N.OUT_HIDDEN, mask_convention=mask_convention)
+
+    def forward_tokens(self, input_ids, attention_mask, token_type_ids=None, mask_convention=N.MASK_ALLOC) -> np.ndarray:
+        """KT/cpu/encoder/traits.rs:295-313 (embed with type ids -> embed LN -> encoder.forward, alloc path)."""
+        return self._forward(input_ids, attention_mask, token_type_ids, N.OUT_HIDDEN, mask_convention=mask_convention)
+
+    def encode_batch_from_ids(self, input_ids, attention_mask, pooling: str = "mean", normalize: bool = True) -> np.ndarray:
+        pool = {"mean": N.POOL_MEAN, "cls": N.POOL_CLS, "max": N.POOL_MAX, "last": N.POOL_LAST}[pooling]
+        return self._forward(input_ids, attention_mask, None, N.OUT_POOLED, pool, normalize)
+
+    def predict_logits(self, input_ids, attention_mask, token_type_ids=None) -> np.ndarray:
+        if self.info.type_vocab_size > 0 and token_type_ids is None:
+            token_type_ids = np.zeros_like(_c(input_ids, np.uint32))
+        return self._forward(input_ids, attention_mask, token_type_ids, N.OUT_LOGITS)
+
+    def classify_scores_batch(self, input_ids, attention_mask, token_type_ids=None) -> np.ndarray:
+        logits = self.predict_logits(input_ids, attention_mask, token_type_ids)
+        N.lib().kjc_softmax_rows(_ptr(logits), logits.shape[0], logits.shape[1])
+        return logits
+
+    def predict_pairs(self, input_ids, attention_mask, token_type_ids) -> np.ndarray:
+        """Cross-encoder relevance scores = logits[:, 0] (raw) (KM/models/cross_encoder/model.rs:239)."""
+        return self.predict_logits(input_ids, attention_mask, token_type_ids)[:, 0].copy()
+
+    def rerank(self, input_ids, attention_mask, token_type_ids) -> List[Tuple[int, float]]:
+        """Stable sort by score descending (KM/models/cross_encoder/model.rs:243-255)."""
+        s = self.predict_pairs(input_ids, attention_mask, token_type_ids)
+        order = np.argsort(-s, kind="stable")
+        return [(int(i), float(s[i])) for i in order]
+
+    def micro_batch(self, seq_len: int) -> int:
+        return int(N.lib().kjc_encoder_micro_batch(self._h, int(seq_len)))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(N.lib().kjc_encoder_last_launch_count(self._h))
+
+
+def scores_to_top_k(probs: np.ndarray, labels: Sequence[str], k: int) -> List[Tuple[str, float]]:
+    """Stable sort descending => ties resolve to the lowest label index (KM/models/sequence_classifier/mod.rs:369-390)."""
+    order = np.argsort(-np.asarray(probs, np.float32), kind="stable")[:k]
+    return [(labels[i] if i < len(labels) else f"LABEL_{i}", float(probs[i])) for i in order]
+
+
+class IndexShard:
+    """A contiguous block of index rows resident in HBM on one GPU (KjcIndex)."""
+
+    def __init__(self, dim: int, capacity_rows: int, id_base: int = 0, device: int = 0, mode: int = N.SCAN_SEGMENT):
+        self._h = C.c_void_p()
+        self.mode = mode
+        self.dim = dim
+        self.id_base = id_base
+        self.device = device
+        N.check(N.lib().kjc_index_create(int(dim), int(capacity_rows), int(id_base), int(device), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().kjc_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(N.lib().kjc_index_len(self._h))
+
+    def add_rows(self, rows) -> None:
+        rows = _c(rows, np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError("rows must be [n, dim]")
+        N.check(N.lib().kjc_index_add_rows(self._h, _ptr(rows), rows.shape[0]))
+
+    def load_vectors_bin(self, path: str) -> None:
+        N.check(N.lib().kjc_index_load_vectors_bin(self._h, str(path).encode()))
+
+    def append_synthetic(self, seed: int, row0: int, n: int) -> None:
+        N.check(N.lib().kjc_index_append_synthetic(self._h, int(seed), int(row0), int(n)))
+
+    def get_embedding(self, doc_id: int) -> np.ndarray:
+        out = np.empty((self.dim,), np.float32)
+        N.check(N.lib().kjc_index_get_rows(self._h, int(doc_id), 1, _ptr(out)))
+        return out
+
+    def get_rows(self, row: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), np.float32)
+        N.check(N.lib().kjc_index_get_rows(self._h, int(row), int(n), _ptr(out)))
+        return out
+
+    def search_batch(self, queries, k: int, mode: Optional[int] = None):
+        """Top-k of every query: (ids u64 [Q,k], scores f32 [Q,k], counts i32 [Q]); order (score desc, id asc)."""
+        q = _c(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError("queries must be [nq, dim]")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.uint64)
+        sc = np.empty((nq, k), np.float32)
+        cnt = np.empty((nq,), np.int32)
+        N.check(N.lib().kjc_index_search(self._h, _ptr(q), nq, int(k), self.mode if mode is None else mode, _ptr(ids), _ptr(sc), _ptr(cnt)))
+        return ids, sc, cnt
+
+    def search_vectors(self, query, limit: int) -> List[Tuple[int, float]]:
+        """Segment::search_vectors: [] on a dimension mismatch or zero-norm query; local doc ids."""
+        q = np.asarray(query, np.float32)
+        if q.ndim != 1 or q.shape[0] != self.dim or limit <= 0:
+            return []
+        ids, sc, cnt = self.search_batch(q[None, :], min(int(limit), 256), N.SCAN_SEGMENT)
+        return [(int(ids[0, j] - self.id_base), float(sc[0, j])) for j in range(int(cnt[0]))]
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(N.lib().kjc_index_last_launch_count(self._h))
+
+
+class VectorStore(IndexShard):
+    """In-memory store semantics (KS/vector.rs): scores use max(|q||r|, 1e-9) as denominator."""
+
+    def __init__(self, dim: int, capacity_rows: int, device: int = 0):
+        super().__init__(dim, capacity_rows, 0, device, N.SCAN_VECTORSTORE)
+
+    def search(self, query_embedding, limit: int) -> List[Tuple[int, float]]:
+        q = np.asarray(query_embedding, np.float32)
+        if len(self) == 0 or q.ndim != 1 or q.shape[0] != self.dim or limit <= 0:
+            return []
+        ids, sc, cnt = self.search_batch(q[None, :], min(int(limit), 256), N.SCAN_VECTORSTORE)
+        return [(int(ids[0, j]), float(sc[0, j])) for j in range(int(cnt[0]))]
+
+
+class IndexReader:
+    """Several shards (segments) searched one after another on their GPUs and merged on the host the way
+    IndexReader::search_semantic does: per-shard top-`limit`, concat in shard order, stable sort desc, truncate;
+    global id = shard id_base + local id.  (The multi-process NCCL variant lives in kjarni_b200.distributed.)"""
+
+    def __init__(self, shards: Sequence[IndexShard]):
+        self.shards = list(shards)
+
+    def search_semantic(self, query, limit: int) -> List[Tuple[int, float]]:
+        allr: List[Tuple[int, float]] = []
+        for sh in self.shards:
+            allr.extend((i + sh.id_base, s) for i, s in sh.search_vectors(query, limit))
+        order = np.argsort(-np.array([r[1] for r in allr], np.float32), kind="stable") if allr else []
+        return [allr[i] for i in order[:limit]]
+
+
+def cosine_similarity(a, b) -> float:
+    a = _c(a, np.float32)
+    b = _c(b, np.float32)
+    if a.shape != b.shape:
+        return 0.0
+    return float(N.lib().kjc_cosine_similarity(_ptr(a), _ptr(b), a.size))

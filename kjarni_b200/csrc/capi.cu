@@ -1,0 +1,213 @@
+// extern "C" surface of libkjarni_cuda.so (include/kjarni_cuda.h): argument checks,
+// exception -> status-code translation and the thread-local error message
+// (same contract as kjarni-ffi/src/error.rs:7-101 in the reference).
+#include <cmath>
+
+#include "index.hpp"
+#include "../../include/kjarni_cuda_debug.h"
+
+namespace kj {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace kj
+
+struct KjcEncoder { kj::Encoder impl; KjcEncoder(const char* d, int dev) : impl(d, dev) {} };
+struct KjcIndex { kj::Index impl; KjcIndex(int dim, uint64_t cap, uint64_t base, int dev) : impl(dim, cap, base, dev) {} };
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return KJC_OK;
+    } catch (const kj::Error& e) {
+        kj::set_last_error(e.what());
+        return e.status;
+    } catch (const std::bad_alloc&) {
+        kj::set_last_error("out of host memory");
+        return KJC_INFERENCE_FAILED;
+    } catch (const std::exception& e) {
+        kj::set_last_error(e.what());
+        return KJC_UNKNOWN;
+    } catch (...) {
+        kj::set_last_error("unknown error");
+        return KJC_UNKNOWN;
+    }
+}
+#define KJC_REQUIRE(ptr)                                             \
+    do {                                                             \
+        if ((ptr) == nullptr) {                                      \
+            kj::set_last_error("null pointer argument: " #ptr);      \
+            return KJC_NULL_POINTER;                                 \
+        }                                                            \
+    } while (0)
+
+extern "C" {
+
+const char* kjc_last_error_message(void) { return kj::g_last_error.empty() ? nullptr : kj::g_last_error.c_str(); }
+void kjc_clear_error(void) { kj::g_last_error.clear(); }
+const char* kjc_error_name(int s) {
+    switch (s) {
+        case KJC_OK: return "Ok";
+        case KJC_NULL_POINTER: return "NullPointer";
+        case KJC_INVALID_UTF8: return "InvalidUtf8";
+        case KJC_MODEL_NOT_FOUND: return "ModelNotFound";
+        case KJC_LOAD_FAILED: return "LoadFailed";
+        case KJC_INFERENCE_FAILED: return "InferenceFailed";
+        case KJC_GPU_UNAVAILABLE: return "GpuUnavailable";
+        case KJC_INVALID_CONFIG: return "InvalidConfig";
+        case KJC_CANCELLED: return "Cancelled";
+        case KJC_TIMEOUT: return "Timeout";
+        case KJC_STREAM_ENDED: return "StreamEnded";
+        default: return "Unknown";
+    }
+}
+const char* kjc_version(void) { return "kjarni-b200 0.1.0 (sm_100a)"; }
+int kjc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
+}
+
+// ------------------------------------------------------------------ encoder
+int kjc_encoder_create(const char* model_dir, int device, KjcEncoder** out) {
+    KJC_REQUIRE(out);
+    *out = nullptr;
+    KJC_REQUIRE(model_dir);
+    return guarded([&] { *out = new KjcEncoder(model_dir, device); });
+}
+void kjc_encoder_destroy(KjcEncoder* enc) { delete enc; }
+int kjc_encoder_info(const KjcEncoder* enc, KjcEncoderInfo* out) {
+    KJC_REQUIRE(enc);
+    KJC_REQUIRE(out);
+    *out = enc->impl.info();
+    return KJC_OK;
+}
+const char* kjc_encoder_label(const KjcEncoder* enc, int i) {
+    if (!enc || i < 0 || i >= static_cast<int>(enc->impl.labels().size())) return nullptr;
+    return enc->impl.labels()[i].c_str();
+}
+static KjcForwardOptions default_opts() { return KjcForwardOptions{KJC_OUT_POOLED, KJC_POOL_MEAN, 1, KJC_MASK_AUTO}; }
+int kjc_encoder_forward(KjcEncoder* enc, const uint32_t* ids, const float* mask, const uint32_t* type_ids, int batch, int seq_len,
+                        const KjcForwardOptions* opts, float* out) {
+    KJC_REQUIRE(enc);
+    KJC_REQUIRE(ids);
+    KJC_REQUIRE(out);
+    const KjcForwardOptions o = opts ? *opts : default_opts();
+    return guarded([&] { enc->impl.forward_host(ids, mask, type_ids, batch, seq_len, o, out); });
+}
+int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_type_ids, int batch,
+                                     int seq_len, const KjcForwardOptions* opts, float* d_out, void* stream) {
+    KJC_REQUIRE(enc);
+    KJC_REQUIRE(d_ids);
+    KJC_REQUIRE(d_out);
+    const KjcForwardOptions o = opts ? *opts : default_opts();
+    return guarded([&] { enc->impl.forward_device(d_ids, d_mask, d_type_ids, batch, seq_len, o, d_out, static_cast<cudaStream_t>(stream)); });
+}
+int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len) { return enc ? enc->impl.micro_batch(seq_len) : 0; }
+int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc) { return enc ? enc->impl.last_launches() : 0; }
+
+void kjc_softmax_rows(float* x, int rows, int cols) {
+    // softmax_inplace, KT/activations.rs:223-242: max-subtract, exp, divide only if the sum is > 0
+    if (!x) return;
+    for (int r = 0; r < rows; ++r) {
+        float* p = x + static_cast<size_t>(r) * cols;
+        float m = -INFINITY;
+        for (int c = 0; c < cols; ++c) m = fmaxf(m, p[c]);
+        float s = 0.f;
+        for (int c = 0; c < cols; ++c) { p[c] = expf(p[c] - m); s += p[c]; }
+        if (s > 0.f) for (int c = 0; c < cols; ++c) p[c] /= s;
+    }
+}
+
+// -------------------------------------------------------------------- index
+int kjc_index_create(int dim, uint64_t capacity_rows, uint64_t id_base, int device, KjcIndex** out) {
+    KJC_REQUIRE(out);
+    *out = nullptr;
+    return guarded([&] { *out = new KjcIndex(dim, capacity_rows, id_base, device); });
+}
+void kjc_index_destroy(KjcIndex* idx) { delete idx; }
+uint64_t kjc_index_len(const KjcIndex* idx) { return idx ? idx->impl.len() : 0; }
+int kjc_index_dim(const KjcIndex* idx) { return idx ? idx->impl.dim() : 0; }
+int kjc_index_add_rows(KjcIndex* idx, const float* rows, uint64_t n) {
+    KJC_REQUIRE(idx);
+    if (n == 0) return KJC_OK;
+    KJC_REQUIRE(rows);
+    return guarded([&] { idx->impl.add_rows_host(rows, n); });
+}
+int kjc_index_load_vectors_bin(KjcIndex* idx, const char* path) {
+    KJC_REQUIRE(idx);
+    KJC_REQUIRE(path);
+    return guarded([&] { idx->impl.load_vectors_bin(path); });
+}
+int kjc_index_append_synthetic(KjcIndex* idx, uint32_t seed, uint64_t row0, uint64_t n) {
+    KJC_REQUIRE(idx);
+    return guarded([&] { idx->impl.append_synthetic(seed, row0, n); });
+}
+int kjc_index_get_rows(const KjcIndex* idx, uint64_t row, uint64_t n, float* out) {
+    KJC_REQUIRE(idx);
+    KJC_REQUIRE(out);
+    return guarded([&] { idx->impl.get_rows(row, n, out); });
+}
+int kjc_index_search(KjcIndex* idx, const float* queries, int nq, int k, int mode, uint64_t* out_ids, float* out_scores,
+                     int32_t* out_counts) {
+    KJC_REQUIRE(idx);
+    KJC_REQUIRE(queries);
+    KJC_REQUIRE(out_ids);
+    KJC_REQUIRE(out_scores);
+    return guarded([&] { idx->impl.search_host(queries, nq, k, mode, out_ids, out_scores, out_counts); });
+}
+int kjc_index_search_device_async(KjcIndex* idx, const float* d_queries, int nq, int k, int mode, uint64_t* d_out_ids, float* d_out_scores,
+                                  int32_t* d_out_counts, void* stream) {
+    KJC_REQUIRE(idx);
+    KJC_REQUIRE(d_queries);
+    KJC_REQUIRE(d_out_ids);
+    KJC_REQUIRE(d_out_scores);
+    return guarded([&] { idx->impl.search_device(d_queries, nq, k, mode, d_out_ids, d_out_scores, d_out_counts, static_cast<cudaStream_t>(stream)); });
+}
+int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const float* d_cand_scores, int n_lists, int nq, int k,
+                                uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, void* stream) {
+    KJC_REQUIRE(d_cand_ids);
+    KJC_REQUIRE(d_cand_scores);
+    KJC_REQUIRE(d_out_ids);
+    KJC_REQUIRE(d_out_scores);
+    return guarded([&] {
+        if (n_lists < 1 || nq < 1 || k < 1) throw kj::Error(KJC_INVALID_CONFIG, "n_lists, nq and k must be positive");
+        KJ_CUDA(cudaSetDevice(device));
+        kj::merge_lists_u64(d_cand_ids, d_cand_scores, n_lists, nq, k, d_out_ids, d_out_scores, d_out_counts, static_cast<cudaStream_t>(stream));
+    });
+}
+int64_t kjc_index_last_launch_count(const KjcIndex* idx) { return idx ? idx->impl.last_launches() : 0; }
+
+float kjc_cosine_similarity(const float* a, const float* b, size_t len) {
+    // kjarni_cosine_similarity (KF/src/lib.rs:177-188) -> VectorStore::cosine_similarity (KS/vector.rs:131-148)
+    if (!a || !b || len == 0) return 0.0f;
+    float dot = 0.f, na = 0.f, nb = 0.f;
+    for (size_t i = 0; i < len; ++i) { dot += a[i] * b[i]; na += a[i] * a[i]; nb += b[i] * b[i]; }
+    const float den = fmaxf(sqrtf(na) * sqrtf(nb), 1e-9f);
+    return dot / den;
+}
+
+// -------------------------------------------------------------- debug hooks
+// Single-kernel entry points used by tests/ to check each kernel in isolation (host buffers).
+int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* residual, int M, int N, int K, int epi,
+                 int act, int block_n, void* out) {
+    KJC_REQUIRE(a_bf16);
+    KJC_REQUIRE(w_bf16);
+    KJC_REQUIRE(out);
+    return guarded([&] { kj::dbg_gemm(a_bf16, w_bf16, bias, residual, M, N, K, epi, act, block_n, out); });
+}
+
+int kjc_dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16) {
+    KJC_REQUIRE(qkv_bf16);
+    KJC_REQUIRE(ctx_bf16);
+    return guarded([&] { kj::dbg_attention(qkv_bf16, mask, B, S, H, heads, nan_if_all_masked, ctx_bf16); });
+}
+
+int kjc_dbg_encoder_head(KjcEncoder* enc, const float* hidden, int batch, int seq_len, float* logits) {
+    KJC_REQUIRE(enc);
+    KJC_REQUIRE(hidden);
+    KJC_REQUIRE(logits);
+    return guarded([&] { enc->impl.head_only_host(hidden, batch, seq_len, logits); });
+}
+
+}  // extern "C"

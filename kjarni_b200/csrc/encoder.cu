@@ -1,0 +1,703 @@
+// Encoder handle: model-directory loader (config.json + model.safetensors ->
+// layout -> bf16 pre-packed weights in HBM) and the batched forward that strings
+// the sm_100a kernels together.  Host-side mirror of
+//   EncoderLoader::load_from_pretrained      KT/pipeline/encoder/loader.rs:82-141
+//   CpuTransformerEncoder::new / forward     KT/cpu/encoder/transformer_encoder.rs:30-368
+//   EncoderLayer::forward_postnorm(_noalloc) KT/cpu/encoder/encoder_layer.rs:113-232
+//   get_hidden_states_batch_from_ids         KT/cpu/encoder/traits.rs:66-139
+// (KT = kjarni-transformers/src, KM = kjarni-models/src in the reference tree).
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "attention.cuh"
+#include "encoder.hpp"
+#include "gemm_tcgen05.cuh"
+#include "rowwise.cuh"
+
+namespace kj {
+
+// ------------------------------------------------------------ TMA descriptors
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    if (!fn) throw Error(KJC_GPU_UNAVAILABLE, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    return fn;
+}
+
+// 2-D row-major [rows, cols] tensor, box = [box_rows, 64 elements (128 B)], 128-byte swizzle, zero OOB fill.
+CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * static_cast<uint64_t>(elem_bytes)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15))
+        throw Error(KJC_INVALID_CONFIG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    CUresult r = get_encode_fn()(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(KJC_INFERENCE_FAILED, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+// ----------------------------------------------------------------- GEMM launch
+int pick_block_n(int N) {
+    if (N % 256 == 0) return 256;
+    if (N % 192 == 0) return 192;
+    if (N % 128 == 0) return 128;
+    if (N <= 64) return 64;
+    if (N <= 128) return 128;
+    if (N <= 192) return 192;
+    return 256;
+}
+
+template <int BN, int EPI>
+static void launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static int configured[64] = {0};
+    auto kern = gemm_tcgen05_kernel<BN, EPI>;
+    ensure_smem_attr(kern, Cfg::kSmemBytes, configured);
+    const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int grid = std::min(m_tiles * n_tiles, num_sms);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    KJ_CUDA(cudaGetLastError());
+}
+
+template <int BN>
+static void launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
+    switch (epi) {
+        case EPI_BIAS_BF16: launch_gemm_inst<BN, EPI_BIAS_BF16>(ta, tb, p, num_sms, st); break;
+        case EPI_BIAS_ACT_BF16: launch_gemm_inst<BN, EPI_BIAS_ACT_BF16>(ta, tb, p, num_sms, st); break;
+        case EPI_BIAS_RES_F32: launch_gemm_inst<BN, EPI_BIAS_RES_F32>(ta, tb, p, num_sms, st); break;
+        case EPI_BIAS_F32: launch_gemm_inst<BN, EPI_BIAS_F32>(ta, tb, p, num_sms, st); break;
+        default: throw Error(KJC_INVALID_CONFIG, "unknown GEMM epilogue");
+    }
+}
+
+void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
+    if (p.N % 16 != 0 || p.K % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs N % 16 == 0 and K % 8 == 0");
+    switch (block_n) {
+        case 64: launch_gemm_bn<64>(epi, ta, tb, p, num_sms, st); break;
+        case 128: launch_gemm_bn<128>(epi, ta, tb, p, num_sms, st); break;
+        case 192: launch_gemm_bn<192>(epi, ta, tb, p, num_sms, st); break;
+        case 256: launch_gemm_bn<256>(epi, ta, tb, p, num_sms, st); break;
+        default: throw Error(KJC_INVALID_CONFIG, "unsupported GEMM block N");
+    }
+}
+
+// ------------------------------------------------------------ row-kernel launch
+template <typename F>
+static void dispatch_nv(int H, F&& f) {
+    const int nv = (H + 127) / 128;
+    switch (nv) {
+        case 1: f(std::integral_constant<int, 1>()); break;
+        case 2: f(std::integral_constant<int, 2>()); break;
+        case 3: f(std::integral_constant<int, 3>()); break;
+        case 4: f(std::integral_constant<int, 4>()); break;
+        case 5: case 6: f(std::integral_constant<int, 6>()); break;
+        case 7: case 8: f(std::integral_constant<int, 8>()); break;
+        default: throw Error(KJC_INVALID_CONFIG, "hidden size > 1024 is not supported");
+    }
+}
+
+void launch_layernorm(const float* y, const float* g, const float* b, float eps, float* x32, __nv_bfloat16* x16, int M, int H,
+                      cudaStream_t st) {
+    const int grid = (M + 7) / 8;
+    dispatch_nv(H, [&](auto nv) {
+        layernorm_kernel<decltype(nv)::value><<<grid, kRowThreads, 0, st>>>(y, g, b, eps, x32, x16, M, H);
+    });
+    KJ_CUDA(cudaGetLastError());
+}
+
+void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
+    const size_t smem = attention_smem_bytes(p.S, D);
+    const int grid = p.B * p.heads;
+    auto go = [&](auto kern) {
+        static int configured[64] = {0};
+        if (smem > 48 * 1024) ensure_smem_attr(kern, static_cast<int>(smem), configured);
+        kern<<<grid, kAttnThreads, smem, st>>>(p);
+    };
+    switch (D) {
+        case 16: go(attention_kernel<16>); break;
+        case 32: go(attention_kernel<32>); break;
+        case 64: go(attention_kernel<64>); break;
+        default: throw Error(KJC_INVALID_CONFIG, "head_dim must be 16, 32 or 64");
+    }
+    KJ_CUDA(cudaGetLastError());
+}
+
+// -------------------------------------------------------------------- loader
+static int json_int(const Json& cfg, const char* key, bool required = true, int dflt = 0) {
+    const Json* j = cfg.get(key);
+    if (!j || j->type != Json::Num) {
+        if (required) throw Error(KJC_INVALID_CONFIG, std::string("config.json: missing field '") + key + "'");
+        return dflt;
+    }
+    return static_cast<int>(j->num);
+}
+
+static int act_from_string(const std::string& s) {
+    // encoder configs map "gelu" -> erf GELU (KM/models/sentence_encoder/configs.rs:194-200; DistilBERT hard-codes it :621)
+    if (s == "gelu") return ACT_GELU_ERF;
+    if (s == "gelu_new" || s == "gelu_fast" || s == "gelu_pytorch_tanh") return ACT_GELU_TANH;
+    if (s == "relu") return ACT_RELU;
+    throw Error(KJC_INVALID_CONFIG, "unsupported activation '" + s + "'");
+}
+
+Encoder::Encoder(const std::string& dir, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) throw Error(KJC_GPU_UNAVAILABLE, "no CUDA device available");
+    if (device < 0 || device >= ndev) throw Error(KJC_GPU_UNAVAILABLE, "device index out of range");
+    cudaDeviceProp prop;
+    KJ_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw Error(KJC_GPU_UNAVAILABLE, std::string("kjarni-b200 needs an sm_100 GPU, found ") + prop.name);
+    num_sms_ = prop.multiProcessorCount;
+    info_.device = device;
+
+    struct stat sb;
+    if (stat(dir.c_str(), &sb) != 0 || !S_ISDIR(sb.st_mode)) throw Error(KJC_MODEL_NOT_FOUND, "model directory not found: " + dir);
+    // ModelWeights::new needs config.json + model.safetensors (KT/weights/model_weights.rs:45-66)
+    const std::string cfg_text = read_text_file(dir + "/config.json", KJC_MODEL_NOT_FOUND);
+    const Json cfg = JsonParser(cfg_text.data(), cfg_text.size()).parse();
+    if (cfg.type != Json::Obj) throw Error(KJC_INVALID_CONFIG, "config.json is not an object");
+    SafeTensors st(dir + "/model.safetensors");
+
+    const std::string model_type = cfg.string("model_type", "bert");
+    std::string ep, lp;  // embedding prefix, layer prefix (with "{}" for the index)
+    const char *nq, *nk, *nv, *no, *nln1, *nf1, *nf2, *nln2;
+    int H, L, heads, max_pos, vocab;
+    int act = ACT_GELU_ERF;
+    if (model_type == "distilbert") {
+        // DistilBertConfig, KM/models/sentence_encoder/configs.rs:473-512,611-687
+        info_.arch = KJC_ARCH_DISTILBERT;
+        H = json_int(cfg, "dim");
+        L = json_int(cfg, "n_layers");
+        heads = json_int(cfg, "n_heads");
+        max_pos = json_int(cfg, "max_position_embeddings");
+        vocab = json_int(cfg, "vocab_size");
+        info_.layer_norm_eps = 1e-12f;  // hard-coded, configs.rs:620
+        act = ACT_GELU_ERF;             // hard-coded Activation::Gelu, configs.rs:621
+        ep = "distilbert.embeddings.";
+        lp = "distilbert.transformer.layer.";
+        nq = "attention.q_lin"; nk = "attention.k_lin"; nv = "attention.v_lin"; no = "attention.out_lin";
+        nln1 = "sa_layer_norm"; nf1 = "ffn.lin1"; nf2 = "ffn.lin2"; nln2 = "output_layer_norm";
+    } else if (model_type == "roberta" || model_type == "distilroberta" || model_type == "mpnet" || model_type == "xlm-roberta") {
+        throw Error(KJC_INVALID_CONFIG, "model_type '" + model_type + "' (RoBERTa/MPNet layouts) is not supported by the CUDA backend yet");
+    } else {
+        // BertConfig, KM/models/sentence_encoder/configs.rs:15-65,174-366
+        const bool prefixed = cfg.has("id2label") || cfg.has("num_labels");  // is_hf_classification, configs.rs:92-95
+        info_.arch = prefixed ? KJC_ARCH_BERT_PREFIXED : KJC_ARCH_BERT;
+        H = json_int(cfg, "hidden_size");
+        L = json_int(cfg, "num_hidden_layers");
+        heads = json_int(cfg, "num_attention_heads");
+        max_pos = json_int(cfg, "max_position_embeddings");
+        vocab = json_int(cfg, "vocab_size");
+        info_.layer_norm_eps = static_cast<float>(cfg.number("layer_norm_eps", 1e-12));
+        act = act_from_string(cfg.string("hidden_act", "gelu"));
+        const std::string pre = prefixed ? "bert." : "";
+        ep = pre + "embeddings.";
+        lp = pre + "encoder.layer.";
+        nq = "attention.self.query"; nk = "attention.self.key"; nv = "attention.self.value"; no = "attention.output.dense";
+        nln1 = "attention.output.LayerNorm"; nf1 = "intermediate.dense"; nf2 = "output.dense"; nln2 = "output.LayerNorm";
+    }
+    if (H <= 0 || L <= 0 || heads <= 0 || H % heads != 0) throw Error(KJC_INVALID_CONFIG, "config.json: inconsistent hidden/heads/layers");
+    const int d = H / heads;
+    if (d != 16 && d != 32 && d != 64) throw Error(KJC_INVALID_CONFIG, "head_dim " + std::to_string(d) + " unsupported (16/32/64)");
+    if (H % 16 != 0 || H > 1024) throw Error(KJC_INVALID_CONFIG, "hidden size must be a multiple of 16 and <= 1024");
+    info_.hidden_size = H;
+    info_.num_layers = L;
+    info_.num_heads = heads;
+    info_.vocab_size = vocab;
+    info_.max_position_embeddings = max_pos;
+    info_.position_offset = 0;
+    act_ = act;
+
+    auto shape_is = [&](const std::string& name, std::initializer_list<int64_t> want) {
+        const StTensor& t = st.at(name);
+        if (t.shape != std::vector<int64_t>(want)) {
+            std::string got;
+            for (auto v : t.shape) got += std::to_string(v) + " ";
+            throw Error(KJC_LOAD_FAILED, "tensor '" + name + "' has shape [" + got + "] (unexpected)");
+        }
+    };
+
+    // ---- collect fp32 tensors on the host, then one arena upload
+    std::vector<float> f32;       // all fp32 parameters
+    std::vector<float> w_gemm;    // all GEMM weights (converted to bf16 on device)
+    auto push_f32 = [&](const std::vector<float>& v) {
+        const size_t off = f32.size();
+        f32.insert(f32.end(), v.begin(), v.end());
+        while (f32.size() % 64) f32.push_back(0.f);  // 256-byte alignment of every tensor
+        return off;
+    };
+    auto push_w = [&](const std::vector<float>& v) {
+        const size_t off = w_gemm.size();
+        w_gemm.insert(w_gemm.end(), v.begin(), v.end());
+        while (w_gemm.size() % 128) w_gemm.push_back(0.f);
+        return off;
+    };
+    auto opt_bias = [&](const std::string& name, int n, bool& present) {
+        present = st.contains(name);
+        if (!present) return std::vector<float>(static_cast<size_t>(n), 0.f);
+        shape_is(name, {n});
+        return st.as_f32(name);
+    };
+
+    const std::string word_name = ep + "word_embeddings.weight";
+    const StTensor& wt = st.at(word_name);
+    if (wt.shape.size() != 2 || wt.shape[1] != H) throw Error(KJC_LOAD_FAILED, "word embedding table has the wrong hidden size");
+    info_.vocab_size = static_cast<int>(wt.shape[0]);  // the table is the truth for the bounds check (embeddings/mod.rs:227-246)
+    const size_t off_word = push_f32(st.as_f32(word_name));
+    const std::string pos_name = ep + "position_embeddings.weight";
+    const StTensor& pt = st.at(pos_name);
+    if (pt.shape.size() != 2 || pt.shape[1] != H) throw Error(KJC_LOAD_FAILED, "position embedding table has the wrong hidden size");
+    info_.max_position_embeddings = static_cast<int>(pt.shape[0]);
+    const size_t off_pos = push_f32(st.as_f32(pos_name));
+    size_t off_type = 0;
+    info_.type_vocab_size = 0;
+    const std::string type_name = ep + "token_type_embeddings.weight";
+    if (st.contains(type_name)) {
+        const StTensor& tt = st.at(type_name);
+        if (tt.shape.size() != 2 || tt.shape[1] != H) throw Error(KJC_LOAD_FAILED, "token-type table has the wrong hidden size");
+        info_.type_vocab_size = static_cast<int>(tt.shape[0]);
+        off_type = push_f32(st.as_f32(type_name));
+    }
+    shape_is(ep + "LayerNorm.weight", {H});
+    shape_is(ep + "LayerNorm.bias", {H});
+    const size_t off_eg = push_f32(st.as_f32(ep + "LayerNorm.weight"));
+    const size_t off_eb = push_f32(st.as_f32(ep + "LayerNorm.bias"));
+
+    struct LayerOff { size_t wqkv, wo, w1, w2, bqkv, bo, b1, b2, g1, be1, g2, be2; };
+    std::vector<LayerOff> lo(L);
+    int I = -1;
+    for (int l = 0; l < L; ++l) {
+        const std::string p = lp + std::to_string(l) + ".";
+        auto W = [&](const char* n) { return p + n + ".weight"; };
+        auto Bn = [&](const char* n) { return p + n + ".bias"; };
+        shape_is(W(nq), {H, H}); shape_is(W(nk), {H, H}); shape_is(W(nv), {H, H}); shape_is(W(no), {H, H});
+        const StTensor& f1 = st.at(W(nf1));
+        if (f1.shape.size() != 2 || f1.shape[1] != H) throw Error(KJC_LOAD_FAILED, "fc1 weight has the wrong shape in layer " + std::to_string(l));
+        if (I < 0) I = static_cast<int>(f1.shape[0]);  // intermediate size from the weight, never from metadata
+        shape_is(W(nf1), {I, H});
+        shape_is(W(nf2), {H, I});
+        // fused [3H, H] QKV weight: rows = q | k | v (KT/cpu/encoder/qkv_projection.rs:109-136)
+        std::vector<float> wqkv = st.as_f32(W(nq));
+        { auto k = st.as_f32(W(nk)); wqkv.insert(wqkv.end(), k.begin(), k.end()); }
+        { auto v = st.as_f32(W(nv)); wqkv.insert(wqkv.end(), v.begin(), v.end()); }
+        lo[l].wqkv = push_w(wqkv);
+        lo[l].wo = push_w(st.as_f32(W(no)));
+        lo[l].w1 = push_w(st.as_f32(W(nf1)));
+        lo[l].w2 = push_w(st.as_f32(W(nf2)));
+        bool hq, hk, hv, hb;
+        std::vector<float> bq = opt_bias(Bn(nq), H, hq), bk = opt_bias(Bn(nk), H, hk), bv = opt_bias(Bn(nv), H, hv);
+        if (H <= 512 && !(hq && hk && hv)) {
+            // the reference's fused-QKV path drops every bias unless all three exist (qkv_projection.rs:235-238)
+            std::fill(bq.begin(), bq.end(), 0.f); std::fill(bk.begin(), bk.end(), 0.f); std::fill(bv.begin(), bv.end(), 0.f);
+        }
+        std::vector<float> bqkv = bq;
+        bqkv.insert(bqkv.end(), bk.begin(), bk.end());
+        bqkv.insert(bqkv.end(), bv.begin(), bv.end());
+        lo[l].bqkv = push_f32(bqkv);
+        lo[l].bo = push_f32(opt_bias(Bn(no), H, hb));
+        lo[l].b1 = push_f32(opt_bias(Bn(nf1), I, hb));
+        lo[l].b2 = push_f32(opt_bias(Bn(nf2), H, hb));
+        shape_is(W(nln1), {H}); shape_is(Bn(nln1), {H}); shape_is(W(nln2), {H}); shape_is(Bn(nln2), {H});
+        lo[l].g1 = push_f32(st.as_f32(W(nln1)));
+        lo[l].be1 = push_f32(st.as_f32(Bn(nln1)));
+        lo[l].g2 = push_f32(st.as_f32(W(nln2)));
+        lo[l].be2 = push_f32(st.as_f32(Bn(nln2)));
+    }
+    if (I % 16 != 0) throw Error(KJC_INVALID_CONFIG, "intermediate size must be a multiple of 16");
+    info_.intermediate_size = I;
+
+    // ---- classification head, first match wins (KT/cpu/encoder/classifier.rs:113-206)
+    size_t off_wpre = 0, off_bpre = 0, off_wcls = 0, off_bcls = 0;
+    bool has_bpre = false, has_bcls = false;
+    info_.head_kind = KJC_HEAD_ABSENT;
+    info_.num_labels = 0;
+    std::string pre_w, pre_b, cls_w, cls_b;
+    if (st.contains("classifier.dense.weight")) {
+        info_.head_kind = KJC_HEAD_DENSE_TANH;
+        pre_w = "classifier.dense.weight"; pre_b = "classifier.dense.bias"; cls_w = "classifier.out_proj.weight"; cls_b = "classifier.out_proj.bias";
+    } else if (st.contains("pre_classifier.weight")) {
+        info_.head_kind = KJC_HEAD_PRE_RELU;
+        pre_w = "pre_classifier.weight"; pre_b = "pre_classifier.bias"; cls_w = "classifier.weight"; cls_b = "classifier.bias";
+    } else if (st.contains("bert.pooler.dense.weight")) {
+        info_.head_kind = KJC_HEAD_POOLER_TANH;
+        pre_w = "bert.pooler.dense.weight"; pre_b = "bert.pooler.dense.bias"; cls_w = "classifier.weight"; cls_b = "classifier.bias";
+    } else if (st.contains("classifier.weight")) {
+        info_.head_kind = KJC_HEAD_LINEAR;
+        cls_w = "classifier.weight"; cls_b = "classifier.bias";
+    }
+    if (info_.head_kind != KJC_HEAD_ABSENT) {
+        if (!pre_w.empty()) {
+            shape_is(pre_w, {H, H});
+            off_wpre = push_f32(st.as_f32(pre_w));
+            off_bpre = push_f32(opt_bias(pre_b, H, has_bpre));
+        }
+        const StTensor& cw = st.at(cls_w);
+        if (cw.shape.size() != 2 || cw.shape[1] != H) throw Error(KJC_LOAD_FAILED, "classifier weight has the wrong shape");
+        info_.num_labels = static_cast<int>(cw.shape[0]);
+        off_wcls = push_f32(st.as_f32(cls_w));
+        off_bcls = push_f32(opt_bias(cls_b, info_.num_labels, has_bcls));
+    }
+    // labels from id2label sorted by numeric key (KF/src/classifier.rs:253-300)
+    if (const Json* id2 = cfg.get("id2label")) {
+        if (id2->type == Json::Obj) {
+            std::vector<std::pair<long, std::string>> items;
+            for (auto& kv : id2->obj)
+                if (kv.second.type == Json::Str) items.emplace_back(strtol(kv.first.c_str(), nullptr, 10), kv.second.str);
+            std::sort(items.begin(), items.end(), [](auto& a, auto& b) { return a.first < b.first; });
+            for (auto& it : items) labels_.push_back(it.second);
+        }
+    }
+
+    // ---- upload
+    KJ_CUDA(cudaSetDevice(device));
+    KJ_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    KJ_CUDA(cudaMalloc(&d_f32_, f32.size() * sizeof(float)));
+    KJ_CUDA(cudaMemcpy(d_f32_, f32.data(), f32.size() * sizeof(float), cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMalloc(&d_w16_, w_gemm.size() * sizeof(__nv_bfloat16)));
+    {
+        float* tmp = nullptr;
+        KJ_CUDA(cudaMalloc(&tmp, w_gemm.size() * sizeof(float)));
+        KJ_CUDA(cudaMemcpy(tmp, w_gemm.data(), w_gemm.size() * sizeof(float), cudaMemcpyHostToDevice));
+        const size_t n = w_gemm.size();
+        f32_to_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream_>>>(tmp, d_w16_, n);
+        KJ_CUDA(cudaGetLastError());
+        KJ_CUDA(cudaStreamSynchronize(stream_));
+        KJ_CUDA(cudaFree(tmp));
+    }
+    KJ_CUDA(cudaMalloc(&d_err_, sizeof(int)));
+    KJ_CUDA(cudaMemset(d_err_, 0, sizeof(int)));
+
+    word_ = d_f32_ + off_word;
+    pos_ = d_f32_ + off_pos;
+    type_ = info_.type_vocab_size ? d_f32_ + off_type : nullptr;
+    emb_g_ = d_f32_ + off_eg;
+    emb_b_ = d_f32_ + off_eb;
+    bn_qkv_ = pick_block_n(3 * H);
+    bn_h_ = pick_block_n(H);
+    bn_i_ = pick_block_n(I);
+    layers_.resize(L);
+    for (int l = 0; l < L; ++l) {
+        LayerDev& ld = layers_[l];
+        ld.wqkv = d_w16_ + lo[l].wqkv; ld.wo = d_w16_ + lo[l].wo; ld.w1 = d_w16_ + lo[l].w1; ld.w2 = d_w16_ + lo[l].w2;
+        ld.bqkv = d_f32_ + lo[l].bqkv; ld.bo = d_f32_ + lo[l].bo; ld.b1 = d_f32_ + lo[l].b1; ld.b2 = d_f32_ + lo[l].b2;
+        ld.g1 = d_f32_ + lo[l].g1; ld.be1 = d_f32_ + lo[l].be1; ld.g2 = d_f32_ + lo[l].g2; ld.be2 = d_f32_ + lo[l].be2;
+        ld.t_wqkv = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, bn_qkv_, kGemmBlockK);
+        ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK);
+        ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK);
+        ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK);
+    }
+    if (info_.head_kind != KJC_HEAD_ABSENT) {
+        w_pre_ = pre_w.empty() ? nullptr : d_f32_ + off_wpre;
+        b_pre_ = (pre_w.empty() || !has_bpre) ? nullptr : d_f32_ + off_bpre;
+        w_cls_ = d_f32_ + off_wcls;
+        b_cls_ = has_bcls ? d_f32_ + off_bcls : nullptr;
+    }
+    const char* env = getenv("KJC_MICRO_TOKENS");
+    micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
+}
+
+Encoder::~Encoder() {
+    cudaSetDevice(info_.device);
+    free_workspace();
+    if (d_f32_) cudaFree(d_f32_);
+    if (d_w16_) cudaFree(d_w16_);
+    if (d_err_) cudaFree(d_err_);
+    if (d_in_) cudaFree(d_in_);
+    if (d_out_) cudaFree(d_out_);
+    if (h_stage_in_) cudaFreeHost(h_stage_in_);
+    if (h_stage_out_) cudaFreeHost(h_stage_out_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Encoder::free_workspace() {
+    for (void* p : {(void*)x32_, (void*)y32_, (void*)x16_, (void*)qkv16_, (void*)ctx16_, (void*)h16_})
+        if (p) cudaFree(p);
+    x32_ = y32_ = nullptr; x16_ = qkv16_ = ctx16_ = h16_ = nullptr;
+    ws_tokens_ = 0;
+}
+
+int Encoder::micro_batch(int S) const { return std::max(1, micro_tokens_ / std::max(S, 1)); }
+
+// Activations for one micro-batch; sized once for the largest token count seen (>= 128 rows so TMA boxes fit).
+void Encoder::ensure_workspace(int tokens) {
+    if (tokens <= ws_tokens_) return;
+    free_workspace();
+    const size_t T = static_cast<size_t>(std::max(tokens, 128));
+    const int H = info_.hidden_size, I = info_.intermediate_size;
+    KJ_CUDA(cudaMalloc(&x32_, T * H * 4));
+    KJ_CUDA(cudaMalloc(&y32_, T * H * 4));
+    KJ_CUDA(cudaMalloc(&x16_, T * H * 2));
+    KJ_CUDA(cudaMalloc(&qkv16_, T * 3 * H * 2));
+    KJ_CUDA(cudaMalloc(&ctx16_, T * H * 2));
+    KJ_CUDA(cudaMalloc(&h16_, T * I * 2));
+    // stale rows beyond the live token count are read by TMA (results discarded): keep them finite
+    KJ_CUDA(cudaMemsetAsync(x16_, 0, T * H * 2, stream_));
+    KJ_CUDA(cudaMemsetAsync(ctx16_, 0, T * H * 2, stream_));
+    KJ_CUDA(cudaMemsetAsync(h16_, 0, T * I * 2, stream_));
+    KJ_CUDA(cudaStreamSynchronize(stream_));  // the forward may run on a caller stream
+    t_x16_ = make_tmap_2d(x16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK);
+    t_ctx16_ = make_tmap_2d(ctx16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK);
+    t_h16_ = make_tmap_2d(h16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK);
+    ws_tokens_ = static_cast<int>(T);
+}
+
+// One micro-batch: ids/mask/types are device pointers for `nb` sequences of length S.
+void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S,
+                            const KjcForwardOptions& o, bool noalloc_convention, float* d_out, cudaStream_t st) {
+    const int H = info_.hidden_size, I = info_.intermediate_size, M = nb * S, d = H / info_.num_heads;
+    const float eps = info_.layer_norm_eps;
+    {
+        EmbedParams e;
+        e.ids = d_ids; e.type_ids = d_types; e.word = word_; e.pos = pos_; e.type = type_; e.gamma = emb_g_; e.beta = emb_b_;
+        e.x32 = x32_; e.x16 = x16_; e.err_flag = d_err_;
+        e.M = M; e.S = S; e.H = H; e.vocab = info_.vocab_size; e.max_pos = info_.max_position_embeddings;
+        e.type_vocab = info_.type_vocab_size; e.pos_offset = info_.position_offset; e.eps = eps;
+        const int grid = (M + 7) / 8;
+        dispatch_nv(H, [&](auto nv) { embed_layernorm_kernel<decltype(nv)::value><<<grid, kRowThreads, 0, st>>>(e); });
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    for (const LayerDev& L : layers_) {
+        GemmParams g{};
+        // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
+        g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = qkv16_; g.ldo = 3 * H; g.act = ACT_NONE;
+        launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, g, num_sms_, st);
+        // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
+        AttnParams a;
+        a.qkv = qkv16_; a.mask = d_mask; a.ctx = ctx16_; a.B = nb; a.S = S; a.H = H; a.heads = info_.num_heads;
+        a.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
+        a.nan_if_all_masked = noalloc_convention ? 1 : 0;
+        launch_attention(a, d, st);
+        // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
+        g = GemmParams{};
+        g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = x32_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+        launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_ctx16_, L.t_wo, g, num_sms_, st);
+        launch_layernorm(y32_, L.g1, L.be1, eps, x32_, x16_, M, H, st);
+        // t = act(x W1^T + b1)                                     (standard_new.rs:47-73)
+        g = GemmParams{};
+        g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = h16_; g.ldo = I; g.act = act_;
+        launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, g, num_sms_, st);
+        // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
+        g = GemmParams{};
+        g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = x32_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+        launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_h16_, L.t_w2, g, num_sms_, st);
+        launch_layernorm(y32_, L.g2, L.be2, eps, x32_, x16_, M, H, st);
+        launches_ += 7;
+    }
+    if (o.output == KJC_OUT_HIDDEN) {
+        KJ_CUDA(cudaMemcpyAsync(d_out, x32_, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
+    } else if (o.output == KJC_OUT_POOLED) {
+        pool_l2_kernel<<<nb, 256, 0, st>>>(x32_, d_mask, d_out, S, H, o.pooling, o.normalize);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+    } else {
+        HeadParams hp;
+        hp.x = x32_; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
+        hp.B = nb; hp.S = S; hp.H = H; hp.C = info_.num_labels;
+        hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
+        const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
+        static int configured[64] = {0};
+        if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel, static_cast<int>(smem), configured);
+        cls_head_kernel<<<(nb + kHeadSeqs - 1) / kHeadSeqs, 256, smem, st>>>(hp);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+}
+
+size_t Encoder::out_row_elems(const KjcForwardOptions& o, int S) const {
+    if (o.output == KJC_OUT_HIDDEN) return static_cast<size_t>(S) * info_.hidden_size;
+    if (o.output == KJC_OUT_POOLED) return static_cast<size_t>(info_.hidden_size);
+    return static_cast<size_t>(info_.num_labels);
+}
+
+void Encoder::validate(int B, int S, const KjcForwardOptions& o) const {
+    if (B <= 0 || S <= 0) throw Error(KJC_INVALID_CONFIG, "batch and seq_len must be positive");
+    if (S > 512) throw Error(KJC_INVALID_CONFIG, "seq_len > 512 is not supported by the fused attention kernel");
+    if (o.output < KJC_OUT_HIDDEN || o.output > KJC_OUT_LOGITS) throw Error(KJC_INVALID_CONFIG, "unknown output mode");
+    if (o.output == KJC_OUT_LOGITS && info_.head_kind == KJC_HEAD_ABSENT)
+        throw Error(KJC_INVALID_CONFIG, "model has no classification head (no classifier tensors in the checkpoint)");
+    if (o.output == KJC_OUT_POOLED && (o.pooling < KJC_POOL_MEAN || o.pooling > KJC_POOL_LAST))
+        throw Error(KJC_INVALID_CONFIG, "unknown pooling strategy");
+}
+
+bool Encoder::resolve_noalloc(int B, int S, const KjcForwardOptions& o) const {
+    if (o.mask_convention == KJC_MASK_ALLOC) return false;
+    if (o.mask_convention == KJC_MASK_NOALLOC) return true;
+    if (o.output == KJC_OUT_LOGITS) return false;  // Classifier / Reranker always take the alloc path
+    const long tokens = static_cast<long>(B) * S;  // ComputeStrategy::select, KT/cpu/strategy.rs:29-47
+    return tokens <= 1 || tokens >= 1000;
+}
+
+void Encoder::forward_device(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S,
+                             const KjcForwardOptions& o, float* d_out, cudaStream_t st) {
+    validate(B, S, o);
+    std::lock_guard<std::mutex> lock(mu_);
+    KJ_CUDA(cudaSetDevice(info_.device));
+    if (!st) st = stream_;
+    launches_ = 0;
+    const int mb = micro_batch(S);
+    ensure_workspace(std::min(B, mb) * S);
+    const bool noalloc = resolve_noalloc(B, S, o);
+    const size_t row = out_row_elems(o, S);
+    for (int b0 = 0; b0 < B; b0 += mb) {
+        const int nb = std::min(mb, B - b0);
+        const size_t t0 = static_cast<size_t>(b0) * S;
+        forward_micro(d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, o, noalloc, d_out + b0 * row, st);
+    }
+}
+
+void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o,
+                           float* out) {
+    validate(B, S, o);
+    std::lock_guard<std::mutex> lock(mu_);
+    KJ_CUDA(cudaSetDevice(info_.device));
+    launches_ = 0;
+    const size_t T = static_cast<size_t>(B) * S;
+    const size_t row = out_row_elems(o, S);
+    const size_t in_words = T * 3, out_elems = static_cast<size_t>(B) * row;
+    if (in_words > in_cap_) {
+        if (d_in_) cudaFree(d_in_);
+        if (h_stage_in_) cudaFreeHost(h_stage_in_);
+        KJ_CUDA(cudaMalloc(&d_in_, in_words * 4));
+        KJ_CUDA(cudaMallocHost(&h_stage_in_, in_words * 4));
+        in_cap_ = in_words;
+    }
+    if (out_elems > out_cap_) {
+        if (d_out_) cudaFree(d_out_);
+        if (h_stage_out_) cudaFreeHost(h_stage_out_);
+        KJ_CUDA(cudaMalloc(&d_out_, out_elems * 4));
+        KJ_CUDA(cudaMallocHost(&h_stage_out_, out_elems * 4));
+        out_cap_ = out_elems;
+    }
+    // stage through pinned memory so the copies are true async DMA transfers
+    uint32_t* hs = h_stage_in_;
+    memcpy(hs, ids, T * 4);
+    if (mask) memcpy(hs + T, mask, T * 4);
+    if (types) memcpy(hs + 2 * T, types, T * 4);
+    KJ_CUDA(cudaMemcpyAsync(d_in_, hs, T * 4, cudaMemcpyHostToDevice, stream_));
+    if (mask) KJ_CUDA(cudaMemcpyAsync(d_in_ + T, hs + T, T * 4, cudaMemcpyHostToDevice, stream_));
+    if (types) KJ_CUDA(cudaMemcpyAsync(d_in_ + 2 * T, hs + 2 * T, T * 4, cudaMemcpyHostToDevice, stream_));
+    const uint32_t* d_ids = d_in_;
+    const float* d_mask = mask ? reinterpret_cast<const float*>(d_in_ + T) : nullptr;
+    const uint32_t* d_types = types ? d_in_ + 2 * T : nullptr;
+
+    const int mb = micro_batch(S);
+    ensure_workspace(std::min(B, mb) * S);
+    const bool noalloc = resolve_noalloc(B, S, o);
+    for (int b0 = 0; b0 < B; b0 += mb) {
+        const int nb = std::min(mb, B - b0);
+        const size_t t0 = static_cast<size_t>(b0) * S;
+        forward_micro(d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, o, noalloc,
+                      d_out_ + b0 * row, stream_);
+    }
+    KJ_CUDA(cudaMemcpyAsync(h_stage_out_, d_out_, out_elems * 4, cudaMemcpyDeviceToHost, stream_));
+    int err = 0;
+    KJ_CUDA(cudaMemcpyAsync(&err_host_, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    KJ_CUDA(cudaStreamSynchronize(stream_));
+    err = err_host_;
+    if (err) {
+        KJ_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), stream_));
+        throw Error(KJC_INFERENCE_FAILED, "Token type ID out of range");
+    }
+    memcpy(out, h_stage_out_, out_elems * 4);
+}
+
+// Head stage alone on caller-supplied fp32 hidden states (debug hook: the argmax stage must be
+// bit-exact against the oracle when both see the same fp32 input).
+void Encoder::head_only_host(const float* hidden, int B, int S, float* logits) {
+    if (info_.head_kind == KJC_HEAD_ABSENT) throw Error(KJC_INVALID_CONFIG, "model has no classification head");
+    std::lock_guard<std::mutex> lock(mu_);
+    KJ_CUDA(cudaSetDevice(info_.device));
+    const int H = info_.hidden_size, Cn = info_.num_labels;
+    float *dh, *dl;
+    KJ_CUDA(cudaMalloc(&dh, static_cast<size_t>(B) * S * H * 4));
+    KJ_CUDA(cudaMalloc(&dl, static_cast<size_t>(B) * Cn * 4));
+    KJ_CUDA(cudaMemcpy(dh, hidden, static_cast<size_t>(B) * S * H * 4, cudaMemcpyHostToDevice));
+    HeadParams hp;
+    hp.x = dh; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = dl;
+    hp.B = B; hp.S = S; hp.H = H; hp.C = Cn;
+    hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
+    const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
+    static int configured[64] = {0};
+    if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel, static_cast<int>(smem), configured);
+    cls_head_kernel<<<(B + kHeadSeqs - 1) / kHeadSeqs, 256, smem, stream_>>>(hp);
+    KJ_CUDA(cudaGetLastError());
+    KJ_CUDA(cudaStreamSynchronize(stream_));
+    KJ_CUDA(cudaMemcpy(logits, dl, static_cast<size_t>(B) * Cn * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dh);
+    cudaFree(dl);
+}
+
+// -------------------------------------------------------------- debug hooks
+// Single-kernel entry points (include/kjarni_cuda_debug.h): host buffers in, host buffers out.
+void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* residual, int M, int N, int K, int epi,
+              int act, int block_n, void* out) {
+                cudaDeviceProp prop;
+        int dev = 0;
+        KJ_CUDA(cudaGetDevice(&dev));
+        KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+        const int bn = block_n > 0 ? block_n : pick_block_n(N);
+        const size_t Mp = std::max(M, 128), Np = std::max(N, bn);
+        __nv_bfloat16 *dA, *dW;
+        float *dB = nullptr, *dR = nullptr;
+        void* dO;
+        const bool f32out = epi == EPI_BIAS_RES_F32 || epi == EPI_BIAS_F32;
+        KJ_CUDA(cudaMalloc(&dA, Mp * K * 2));
+        KJ_CUDA(cudaMalloc(&dW, Np * K * 2));
+        KJ_CUDA(cudaMemset(dA, 0, Mp * K * 2));
+        KJ_CUDA(cudaMemset(dW, 0, Np * K * 2));
+        KJ_CUDA(cudaMalloc(&dO, static_cast<size_t>(M) * N * (f32out ? 4 : 2)));
+        KJ_CUDA(cudaMemcpy(dA, a_bf16, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
+        KJ_CUDA(cudaMemcpy(dW, w_bf16, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
+        if (bias) { KJ_CUDA(cudaMalloc(&dB, static_cast<size_t>(N) * 4)); KJ_CUDA(cudaMemcpy(dB, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice)); }
+        if (residual) { KJ_CUDA(cudaMalloc(&dR, static_cast<size_t>(M) * N * 4)); KJ_CUDA(cudaMemcpy(dR, residual, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice)); }
+        CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK);
+        CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK);
+        GemmParams p{};
+        p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act;
+        launch_gemm(bn, epi, ta, tb, p, prop.multiProcessorCount, nullptr);
+        KJ_CUDA(cudaDeviceSynchronize());
+        KJ_CUDA(cudaMemcpy(out, dO, static_cast<size_t>(M) * N * (f32out ? 4 : 2), cudaMemcpyDeviceToHost));
+        cudaFree(dA); cudaFree(dW); cudaFree(dO);
+        if (dB) cudaFree(dB);
+        if (dR) cudaFree(dR);
+}
+
+void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16) {
+                const size_t T = static_cast<size_t>(B) * S;
+        __nv_bfloat16 *dq, *dc;
+        float* dm = nullptr;
+        KJ_CUDA(cudaMalloc(&dq, T * 3 * H * 2));
+        KJ_CUDA(cudaMalloc(&dc, T * H * 2));
+        KJ_CUDA(cudaMemcpy(dq, qkv_bf16, T * 3 * H * 2, cudaMemcpyHostToDevice));
+        if (mask) { KJ_CUDA(cudaMalloc(&dm, T * 4)); KJ_CUDA(cudaMemcpy(dm, mask, T * 4, cudaMemcpyHostToDevice)); }
+        AttnParams a;
+        const int d = H / heads;
+        a.qkv = dq; a.mask = dm; a.ctx = dc; a.B = B; a.S = S; a.H = H; a.heads = heads;
+        a.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
+        a.nan_if_all_masked = nan_if_all_masked;
+        launch_attention(a, d, nullptr);
+        KJ_CUDA(cudaDeviceSynchronize());
+        KJ_CUDA(cudaMemcpy(ctx_bf16, dc, T * H * 2, cudaMemcpyDeviceToHost));
+        cudaFree(dq); cudaFree(dc);
+        if (dm) cudaFree(dm);
+}
+
+}  // namespace kj

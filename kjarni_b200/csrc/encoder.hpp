@@ -1,0 +1,100 @@
+// Encoder handle behind KjcEncoder (see include/kjarni_cuda.h and encoder.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "host_util.hpp"
+
+namespace kj {
+
+struct GemmParams;
+struct AttnParams;
+
+CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols);
+int pick_block_n(int N);
+void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st);
+void launch_attention(const AttnParams& p, int head_dim, cudaStream_t st);
+void launch_layernorm(const float* y, const float* g, const float* b, float eps, float* x32, __nv_bfloat16* x16, int M, int H,
+                      cudaStream_t st);
+
+void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* residual, int M, int N, int K, int epi,
+              int act, int block_n, void* out);
+void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember what each device was configured with.
+template <typename K>
+inline void ensure_smem_attr(K kern, int bytes, int (&configured)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured[dev & 63] >= bytes) return;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+        throw Error(KJC_INFERENCE_FAILED, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+    configured[dev & 63] = bytes;
+}
+
+struct LayerDev {
+    const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
+    const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
+    CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
+};
+
+class Encoder {
+  public:
+    Encoder(const std::string& model_dir, int device);
+    ~Encoder();
+    Encoder(const Encoder&) = delete;
+    Encoder& operator=(const Encoder&) = delete;
+
+    const KjcEncoderInfo& info() const { return info_; }
+    const std::vector<std::string>& labels() const { return labels_; }
+    int micro_batch(int seq_len) const;
+    int64_t last_launches() const { return launches_; }
+
+    void forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o, float* out);
+    void head_only_host(const float* hidden, int B, int S, float* logits);
+    void forward_device(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S, const KjcForwardOptions& o,
+                        float* d_out, cudaStream_t st);
+
+  private:
+    void validate(int B, int S, const KjcForwardOptions& o) const;
+    bool resolve_noalloc(int B, int S, const KjcForwardOptions& o) const;
+    size_t out_row_elems(const KjcForwardOptions& o, int S) const;
+    void ensure_workspace(int tokens);
+    void free_workspace();
+    void forward_micro(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S, const KjcForwardOptions& o,
+                       bool noalloc_convention, float* d_out, cudaStream_t st);
+
+    KjcEncoderInfo info_{};
+    std::vector<std::string> labels_;
+    int num_sms_ = 0, act_ = 0, micro_tokens_ = 0;
+    int bn_qkv_ = 0, bn_h_ = 0, bn_i_ = 0;
+    std::mutex mu_;
+    cudaStream_t stream_ = nullptr;
+    // parameters
+    float* d_f32_ = nullptr;
+    __nv_bfloat16* d_w16_ = nullptr;
+    const float *word_ = nullptr, *pos_ = nullptr, *type_ = nullptr, *emb_g_ = nullptr, *emb_b_ = nullptr;
+    const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
+    std::vector<LayerDev> layers_;
+    // activations of one micro-batch
+    int ws_tokens_ = 0;
+    float *x32_ = nullptr, *y32_ = nullptr;
+    __nv_bfloat16 *x16_ = nullptr, *qkv16_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr;
+    CUtensorMap t_x16_, t_ctx16_, t_h16_;
+    // host-buffer entry point staging
+    uint32_t* d_in_ = nullptr;
+    float* d_out_ = nullptr;
+    uint32_t* h_stage_in_ = nullptr;
+    float* h_stage_out_ = nullptr;
+    size_t in_cap_ = 0, out_cap_ = 0;
+    int* d_err_ = nullptr;
+    int err_host_ = 0;
+    int64_t launches_ = 0;
+};
+
+}  // namespace kj

@@ -1,0 +1,272 @@
+// Persistent warp-specialised tcgen05 GEMM for the encoder projections:
+//     C[M,N] = epilogue( A[M,K] (bf16, K-major) x W[N,K]^T (bf16, K-major) )
+// This is the B200 replacement for LinearLayer::matmul / matmul_noalloc
+// (reference: kjarni-transformers/src/linear_layer/linear_layer.rs:160-282 ->
+// cpu/ops/matmul.rs:370-479 -> cpu/kernels/x86/f32.rs:9-124), with the bias,
+// activation (cpu/feedforward/standard_new.rs:65-73) and residual add
+// (cpu/encoder/encoder_layer.rs:129-136,156-163) fused into the epilogue.
+//
+// Structure (one CTA per SM, 384 threads):
+//   warp 0      TMA producer: A tile [128 x 64] + W tile [BN x 64] per stage, 128B swizzle
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma 128 x BN x 16, fp32 accum in TMEM
+//   warp 2      TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers -> bias/GELU/residual -> global
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace kj {
+
+enum GemmEpilogue : int {
+    EPI_BIAS_BF16 = 0,      // out bf16 = acc + bias
+    EPI_BIAS_ACT_BF16 = 1,  // out bf16 = act(acc + bias)
+    EPI_BIAS_RES_F32 = 2,   // out f32  = acc + bias + residual(f32)
+    EPI_BIAS_F32 = 3,       // out f32  = acc + bias
+};
+enum Activation : int { ACT_GELU_ERF = 0, ACT_GELU_TANH = 1, ACT_RELU = 2, ACT_NONE = 3 };
+
+struct GemmParams {
+    int M, N, K;
+    const float* bias;      // [N] or nullptr
+    const float* residual;  // [M, ldr] fp32 (EPI_BIAS_RES_F32)
+    void* out;              // [M, ldo] bf16 or f32
+    int ldo, ldr;
+    int act;
+};
+
+constexpr int kGemmBlockM = 128;
+constexpr int kGemmBlockK = 64;
+constexpr int kGemmThreads = 384;
+constexpr int kGemmEpiWarp0 = 4;
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+    static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
+    static constexpr int kBBytes = BN * kGemmBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// erf-GELU, 0.5*x*(1+erf(x/sqrt2)) (reference activations.rs:57-59), with
+// erf(t) = 1 - 2^-q(t), q a degree-6 polynomial fitted on [0, 4.2] (max |erf| error 7e-6,
+// max GELU error 8e-7 -- far below the bf16 rounding of the stored activation).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = fminf(ax * 0.70710678118654752f, 4.2f);
+    float q = -3.0826393e-04f;
+    q = fmaf(q, t, 4.6386556e-03f);
+    q = fmaf(q, t, -3.3037759e-02f);
+    q = fmaf(q, t, 1.5190166e-01f);
+    q = fmaf(q, t, 9.1710484e-01f);
+    q = fmaf(q, t, 1.6281176e+00f);
+    q = q * t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
+    return 0.5f * fmaf(ax, 1.0f - e, x);
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    // gelu_new_scalar, activations.rs:62-66
+    const float inner = 0.7978845608f * fmaf(0.044715f * x * x, x, x);
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));
+    return 0.5f * x * (1.0f + th);
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == ACT_GELU_ERF) return gelu_erf_fast(x);
+    if (act == ACT_GELU_TANH) return gelu_tanh_fast(x);
+    if (act == ACT_RELU) return fmaxf(x, 0.0f);
+    return x;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int kStages = Cfg::kStages;
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tmem_full = bars + 2 * kStages;
+    uint64_t* tmem_empty = bars + 2 * kStages + 2;
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM,
+                                kEvictFirst);
+                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_blk * BN, kEvictLast);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp >= kGemmEpiWarp0) {
+        // ---------------------------------------------------------- epilogue
+        const int ew = warp - kGemmEpiWarp0;  // 0..7
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int half = ew >> 2;             // column half handled by this warpgroup
+        constexpr int kColsPerHalf = BN / 2;
+        constexpr int kChunks = kColsPerHalf / 16;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * kGemmBlockM + quad * 32 + lane;
+            const bool row_ok = row < p.M;
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * kColsPerHalf;
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t v[16];
+                tmem_ld_32x16(taddr0 + c * 16, v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + half * kColsPerHalf + c * 16;
+                if (col0 >= p.N) continue;  // N tail (N is a multiple of 16)
+                float f[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                if (p.bias != nullptr) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        f[4 * j + 0] += b.x;
+                        f[4 * j + 1] += b.y;
+                        f[4 * j + 2] += b.z;
+                        f[4 * j + 3] += b.w;
+                    }
+                }
+                if (EPI == EPI_BIAS_ACT_BF16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act);
+                }
+                if (!row_ok) continue;
+                if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                    uint4 w0, w1;
+                    w0.x = pack_bf16(f[0], f[1]);
+                    w0.y = pack_bf16(f[2], f[3]);
+                    w0.z = pack_bf16(f[4], f[5]);
+                    w0.w = pack_bf16(f[6], f[7]);
+                    w1.x = pack_bf16(f[8], f[9]);
+                    w1.y = pack_bf16(f[10], f[11]);
+                    w1.z = pack_bf16(f[12], f[13]);
+                    w1.w = pack_bf16(f[14], f[15]);
+                    reinterpret_cast<uint4*>(o)[0] = w0;
+                    reinterpret_cast<uint4*>(o)[1] = w1;
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                    if (EPI == EPI_BIAS_RES_F32) {
+                        const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 r = __ldg(r4 + j);
+                            f[4 * j + 0] += r.x;
+                            f[4 * j + 1] += r.y;
+                            f[4 * j + 2] += r.z;
+                            f[4 * j + 3] += r.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                }
+            }
+            // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace kj

@@ -1,0 +1,49 @@
+// Index shard handle behind KjcIndex (see include/kjarni_cuda.h and index.cu).
+#pragma once
+#include <mutex>
+#include <string>
+
+#include "encoder.hpp"
+
+namespace kj {
+
+void merge_lists_u64(const uint64_t* d_ids, const float* d_scores, int n_lists, int nq, int k, uint64_t* d_out_ids, float* d_out_scores,
+                     int32_t* d_out_counts, cudaStream_t st);
+
+class Index {
+  public:
+    Index(int dim, uint64_t capacity_rows, uint64_t id_base, int device);
+    ~Index();
+    Index(const Index&) = delete;
+    Index& operator=(const Index&) = delete;
+
+    uint64_t len() const { return len_; }
+    int dim() const { return dim_; }
+    int device() const { return device_; }
+    int64_t last_launches() const { return launches_; }
+
+    void add_rows_host(const float* rows, uint64_t n);
+    void load_vectors_bin(const std::string& path);
+    void append_synthetic(uint32_t seed, uint64_t row0, uint64_t n);
+    void get_rows(uint64_t row, uint64_t n, float* out) const;
+    void search_host(const float* q, int nq, int k, int mode, uint64_t* ids, float* scores, int32_t* counts);
+    void search_device(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st);
+
+  private:
+    void compute_norms(uint64_t row0, uint64_t n, cudaStream_t st);
+    int dim_;
+    uint64_t cap_, id_base_, len_ = 0;
+    int device_, num_sms_ = 0;
+    std::mutex mu_;
+    cudaStream_t stream_ = nullptr;
+    float *rows_ = nullptr, *norms_ = nullptr;
+    float *d_q_ = nullptr, *d_qn_ = nullptr, *d_cand_s_ = nullptr, *d_out_s_ = nullptr;
+    uint32_t* d_cand_i_ = nullptr;
+    uint64_t* d_out_i_ = nullptr;
+    int32_t* d_out_c_ = nullptr;
+    float* h_stage_ = nullptr;
+    size_t q_cap_ = 0, qn_cap_ = 0, cand_cap_ = 0, out_cap_ = 0, outc_cap_ = 0;
+    int64_t launches_ = 0;
+};
+
+}  // namespace kj

@@ -1,0 +1,286 @@
+// Bandwidth-bound row kernels of the encoder path: fused embedding gather +
+// LayerNorm, LayerNorm, masked mean-pool + L2 normalise, CLS pooling and the
+// classification head.  fp32 statistics everywhere (layer_norm_eps = 1e-12 is
+// below bf16 resolution); one warp per token row, rows held in registers.
+#pragma once
+#include "ptx.cuh"
+
+namespace kj {
+
+constexpr int kRowThreads = 256;  // 8 rows per CTA
+
+// LayerNorm over H held as float4 chunks: biased variance, eps inside the sqrt
+// (reference: kjarni-transformers/src/cpu/normalization/layer_norm.rs:37-134).
+template <int NV>  // float4 chunks per lane
+__device__ __forceinline__ void warp_layernorm_store(float4 (&v)[NV], int H, int lane, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float eps, float* __restrict__ out32,
+                                                     __nv_bfloat16* __restrict__ out16) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if ((lane + 32 * i) * 4 < H) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / static_cast<float>(H);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if ((lane + 32 * i) * 4 < H) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    const float inv_std = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(H) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < H) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+            float4 y;
+            y.x = (v[i].x - mean) * inv_std * g.x + bt.x;
+            y.y = (v[i].y - mean) * inv_std * g.y + bt.y;
+            y.z = (v[i].z - mean) * inv_std * g.z + bt.z;
+            y.w = (v[i].w - mean) * inv_std * g.w + bt.w;
+            if (out32) *reinterpret_cast<float4*>(out32 + c) = y;
+            if (out16) {
+                uint2 w;
+                w.x = pack_bf16(y.x, y.y);
+                w.y = pack_bf16(y.z, y.w);
+                *reinterpret_cast<uint2*>(out16 + c) = w;
+            }
+        }
+    }
+}
+
+struct EmbedParams {
+    const uint32_t* ids;       // [B*S]
+    const uint32_t* type_ids;  // [B*S] or nullptr (row 0 of the type table is added to every token)
+    const float* word;         // [vocab, H]
+    const float* pos;          // [max_pos, H] or nullptr
+    const float* type;         // [type_vocab, H] or nullptr
+    const float* gamma;
+    const float* beta;
+    float* x32;                // [B*S, H]
+    __nv_bfloat16* x16;        // [B*S, H]
+    int* err_flag;             // set to 1 on a token-type id out of range (the reference panics)
+    int M, S, H, vocab, max_pos, type_vocab, pos_offset;
+    float eps;
+};
+
+// Embeddings::forward + embed LayerNorm (reference: cpu/embeddings/mod.rs:181-326,
+// cpu/encoder/transformer_encoder.rs:303-305): word[id] (zero row if id >= vocab)
+// + pos[offset + s] (skipped beyond the table) + type[tt] (row 0 if no type ids).
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads) embed_layernorm_kernel(EmbedParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRowThreads / 32) + warp;
+    if (row >= p.M) return;
+    const int s = row % p.S;
+    const uint32_t id = p.ids[row];
+    const bool has_word = id < static_cast<uint32_t>(p.vocab);
+    const int pidx = p.pos_offset + s;
+    const bool has_pos = p.pos != nullptr && pidx < p.max_pos;
+    uint32_t tt = 0;
+    const bool has_type = p.type != nullptr && p.type_vocab > 0;
+    if (has_type && p.type_ids != nullptr) {
+        tt = p.type_ids[row];
+        if (tt >= static_cast<uint32_t>(p.type_vocab)) {
+            if (lane == 0) *p.err_flag = 1;
+            tt = 0;
+        }
+    }
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < p.H) {
+            if (has_word) a = __ldg(reinterpret_cast<const float4*>(p.word + static_cast<size_t>(id) * p.H + c));
+            if (has_pos) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(pidx) * p.H + c));
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (has_type) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.type + static_cast<size_t>(tt) * p.H + c));
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+        }
+        v[i] = a;
+    }
+    warp_layernorm_store<NV>(v, p.H, lane, p.gamma, p.beta, p.eps, p.x32 + static_cast<size_t>(row) * p.H,
+                             p.x16 + static_cast<size_t>(row) * p.H);
+}
+
+// x = LN(y) where y already holds residual + projection (+bias) from the GEMM epilogue.
+template <int NV>
+__global__ void __launch_bounds__(kRowThreads)
+layernorm_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 float* __restrict__ x32, __nv_bfloat16* __restrict__ x16, int M, int H) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (kRowThreads / 32) + warp;
+    if (row >= M) return;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        v[i] = (c < H) ? __ldcs(reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * H + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    warp_layernorm_store<NV>(v, H, lane, gamma, beta, eps, x32 ? x32 + static_cast<size_t>(row) * H : nullptr,
+                             x16 ? x16 + static_cast<size_t>(row) * H : nullptr);
+}
+
+// Pooling modes (reference: kjarni-transformers/src/pooling/mod.rs:11-68 and
+// cpu/encoder/traits.rs:204-225,529-536).
+enum PoolMode : int { POOL_MEAN = 0, POOL_CLS = 1, POOL_MAX = 2, POOL_LAST = 3 };
+
+// One CTA per sequence, one thread per 4 hidden columns; fused optional L2 normalise.
+__global__ void __launch_bounds__(256)
+pool_l2_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int S, int H, int mode,
+               int normalize) {
+    const int b = blockIdx.x;
+    const float* xb = x + static_cast<size_t>(b) * S * H;
+    const float* mb = mask ? mask + static_cast<size_t>(b) * S : nullptr;
+    __shared__ float red[8];
+    __shared__ float s_count;
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        float cnt = 0.f;
+        int last = -1;
+        for (int s = tid; s < S; s += 32) {
+            const float m = mb ? mb[s] : 1.0f;
+            cnt += m;
+            if (m > 0.0f) last = s;
+        }
+        cnt = warp_sum(cnt);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        if (tid == 0) {
+            s_count = cnt;
+            s_last = last < 0 ? 0 : last;
+        }
+    }
+    __syncthreads();
+    const float count = s_count;
+    float sq = 0.0f;
+    float4 acc[2];  // supports H <= 2048
+    for (int it = 0; it < 2; ++it) {
+        const int c = (tid + it * 256) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < H) {
+            if (mode == POOL_CLS || (mode == POOL_MEAN && count == 0.0f)) {
+                a = *reinterpret_cast<const float4*>(xb + c);
+            } else if (mode == POOL_LAST) {
+                a = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(s_last) * H + c);
+            } else if (mode == POOL_MEAN) {
+                for (int s = 0; s < S; ++s) {
+                    const float m = mb ? mb[s] : 1.0f;
+                    if (m != 0.0f) {
+                        const float4 t = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(s) * H + c);
+                        a.x += t.x * m; a.y += t.y * m; a.z += t.z * m; a.w += t.w * m;
+                    }
+                }
+                a.x /= count; a.y /= count; a.z /= count; a.w /= count;
+            } else {  // POOL_MAX: masked positions become -1e9 (MASK_VALUE), result clamped below by it
+                a = make_float4(-1e9f, -1e9f, -1e9f, -1e9f);
+                for (int s = 0; s < S; ++s) {
+                    const float m = mb ? mb[s] : 1.0f;
+                    if (m != 0.0f) {
+                        const float4 t = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(s) * H + c);
+                        a.x = fmaxf(a.x, t.x); a.y = fmaxf(a.y, t.y); a.z = fmaxf(a.z, t.z); a.w = fmaxf(a.w, t.w);
+                    }
+                }
+            }
+            sq += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+        }
+        acc[it] = a;
+    }
+    float scale = 1.0f;
+    if (normalize) {
+        sq = warp_sum(sq);
+        if ((tid & 31) == 0) red[tid >> 5] = sq;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        const float nrm = sqrtf(tot);
+        if (nrm > 0.0f) scale = 1.0f / nrm;  // l2_normalize_inplace: only if norm > 0 (NaN norm leaves the row as is)
+    }
+    for (int it = 0; it < 2; ++it) {
+        const int c = (tid + it * 256) * 4;
+        if (c < H) {
+            float4 a = acc[it];
+            if (scale != 1.0f) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(b) * H + c) = a;
+        }
+    }
+}
+
+// Classification head on the CLS row (reference: cpu/encoder/classifier.rs:210-258):
+//   z = x[b,0,:]; if pre: z = act(W_pre z + b_pre) (tanh | relu); logits = W_cls z + b_cls.
+// fp32 weights and math so the argmax stage matches the fp32 oracle bit-for-bit up to summation order.
+// One CTA per kHeadSeqs sequences: every W_pre row read from L2 is reused for all of them.
+enum HeadAct : int { HEAD_NONE = 0, HEAD_TANH = 1, HEAD_RELU = 2 };
+constexpr int kHeadSeqs = 8;
+struct HeadParams {
+    const float* x;  // [B, S, H] last hidden state (fp32)
+    const float* w_pre; const float* b_pre;  // [H,H], [H] or nullptr
+    const float* w_cls; const float* b_cls;  // [C,H], [C]
+    float* logits;   // [B, C]
+    int B, S, H, C, act;
+};
+__global__ void __launch_bounds__(256) cls_head_kernel(HeadParams p) {
+    extern __shared__ float hs[];  // z0[kHeadSeqs][H], z1[kHeadSeqs][H]
+    float* z0 = hs;
+    float* z1 = hs + kHeadSeqs * p.H;
+    const int b0 = blockIdx.x * kHeadSeqs;
+    const int nb = min(kHeadSeqs, p.B - b0);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < kHeadSeqs * p.H; i += 256) {
+        const int s = i / p.H, c = i % p.H;
+        z0[i] = s < nb ? p.x[static_cast<size_t>(b0 + s) * p.S * p.H + c] : 0.0f;
+    }
+    __syncthreads();
+    const float* zin = z0;
+    if (p.w_pre != nullptr) {
+        for (int r = warp; r < p.H; r += 8) {
+            float acc[kHeadSeqs];
+#pragma unroll
+            for (int s = 0; s < kHeadSeqs; ++s) acc[s] = 0.0f;
+            const float* w = p.w_pre + static_cast<size_t>(r) * p.H;
+            for (int c = lane; c < p.H; c += 32) {
+                const float wv = __ldg(w + c);
+#pragma unroll
+                for (int s = 0; s < kHeadSeqs; ++s) acc[s] = fmaf(wv, z0[s * p.H + c], acc[s]);
+            }
+#pragma unroll
+            for (int s = 0; s < kHeadSeqs; ++s) acc[s] = warp_sum(acc[s]);
+            if (lane == 0) {
+                const float bb = p.b_pre ? p.b_pre[r] : 0.0f;
+#pragma unroll
+                for (int s = 0; s < kHeadSeqs; ++s) {
+                    float v = acc[s] + bb;
+                    if (p.act == HEAD_TANH) v = tanhf(v);
+                    else if (p.act == HEAD_RELU) v = fmaxf(v, 0.0f);
+                    z1[s * p.H + r] = v;
+                }
+            }
+        }
+        __syncthreads();
+        zin = z1;
+    }
+    for (int o = warp; o < p.C * nb; o += 8) {
+        const int cls = o / nb, s = o % nb;
+        const float* w = p.w_cls + static_cast<size_t>(cls) * p.H;
+        float acc = 0.0f;
+        for (int c = lane; c < p.H; c += 32) acc = fmaf(__ldg(w + c), zin[s * p.H + c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) p.logits[static_cast<size_t>(b0 + s) * p.C + cls] = acc + (p.b_cls ? p.b_cls[cls] : 0.0f);
+    }
+}
+
+// fp32 -> bf16 weight pre-pack (done once at load).
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+}  // namespace kj

@@ -1,0 +1,167 @@
+"""Encoder parity through the C ABI: CUDA path vs the fp32 oracle on the same random-init
+model directory and synthetic token ids, and vs the committed HuggingFace goldens."""
+import os
+
+import numpy as np
+import pytest
+
+from kjarni_b200 import _native as N
+from kjarni_b200 import api, synth
+from oracle import kjarni_oracle as ko
+from kj_testutil import cosine_rows, ptr
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hf_goldens.npz"))
+
+# north_star tolerance for embeddings vs the fp32 CPU path
+COS_MIN, MAXABS = 0.9995, 2e-2
+
+
+@pytest.fixture(scope="module")
+def dirs(tmp_path_factory):
+    root = tmp_path_factory.mktemp("models")
+    return {a: synth.write_model_dir(str(root / a), a) for a in
+            ("tiny-bert", "tiny-cross-encoder", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2")}
+
+
+def centred_cos(a, b):
+    return cosine_rows(a - a.mean(0, keepdims=True), b - b.mean(0, keepdims=True))
+
+
+@pytest.mark.parametrize("arch,B,S", [("tiny-bert", 6, 16), ("tiny-bert", 70, 24), ("minilm-l6", 4, 32), ("minilm-l6", 32, 128)])
+def test_embedding_matches_oracle(dirs, arch, B, S):
+    vocab = synth.ARCHS[arch][5]
+    ids, mask, _ = synth.synth_tokens(B, S, vocab, regime="P", seed=7)
+    m = ko.load_model_dir(dirs[arch])
+    enc = api.EncoderModel(dirs[arch])
+    assert enc.arch == m.arch and enc.head_kind is None and enc.hidden_size == m.hidden
+    want = ko.embed(m, ids, mask)
+    got = enc.encode_batch_from_ids(ids, mask)
+    assert got.shape == want.shape and np.isfinite(got).all()
+    assert cosine_rows(got, want).min() >= COS_MIN
+    assert np.abs(got - want).max() <= MAXABS
+    assert centred_cos(got, want).min() >= 0.99  # random-init embeddings share a large common component
+    assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-5
+    # un-normalised mean / cls / max / last pooling go through the same kernel
+    for pooling in ("mean", "cls", "max", "last"):
+        w = ko.embed(m, ids, mask, pooling=pooling, normalize=False)
+        g = enc.encode_batch_from_ids(ids, mask, pooling=pooling, normalize=False)
+        assert cosine_rows(g, w).min() >= COS_MIN, pooling
+    # hidden states: same tolerance on valid tokens, reported per token
+    hw = ko.encoder_forward(m, ids, mask, None, noalloc=ko.use_noalloc(ids.size))
+    hg = enc.get_hidden_states_batch_from_ids(ids, mask)
+    valid = mask.astype(bool)
+    assert cosine_rows(hg[valid], hw[valid]).min() >= COS_MIN
+    assert np.abs(hg[valid] - hw[valid]).max() <= 6e-2
+    enc.close()
+
+
+def test_embedding_matches_hf_goldens(dirs):
+    for arch in ("tiny-bert", "minilm-l6"):
+        B, S = (int(v) for v in G[arch + "/shape"])
+        ids, mask, _ = synth.synth_tokens(B, S, synth.ARCHS[arch][5], regime="P", seed=7)
+        enc = api.EncoderModel(dirs[arch])
+        got = enc.encode_batch_from_ids(ids, mask)
+        want = G[arch + "/embedding"]
+        assert cosine_rows(got, want).min() >= COS_MIN and np.abs(got - want).max() <= MAXABS
+        enc.close()
+
+
+@pytest.mark.parametrize("arch,B,S,pair", [("tiny-distilbert", 6, 16, False), ("tiny-cross-encoder", 6, 16, True),
+                                           ("distilbert-sst2", 16, 128, False), ("minilm-l6-cross-encoder", 12, 256, True)])
+def test_logits_match_oracle(dirs, arch, B, S, pair):
+    vocab = synth.ARCHS[arch][5]
+    ids, mask, types = synth.synth_tokens(B, S, vocab, regime="P", seed=11, pair=pair)
+    m = ko.load_model_dir(dirs[arch])
+    enc = api.EncoderModel(dirs[arch])
+    assert enc.head_kind == m.head_kind and enc.num_labels == m.w_cls.shape[0]
+    want = ko.predict_logits(m, ids, mask, types)
+    got = enc.predict_logits(ids, mask, types)
+    assert got.shape == want.shape
+    scale = max(1.0, float(np.abs(want).max()))
+    assert np.abs(got - want).max() <= 5e-2 * scale
+    if want.shape[1] > 1:
+        margin = np.abs(want[:, 0] - want[:, 1])
+        sure = margin > 0.1 * scale
+        assert (got.argmax(1)[sure] == want.argmax(1)[sure]).all()
+        p = enc.classify_scores_batch(ids, mask, types)
+        assert np.allclose(p.sum(1), 1, atol=1e-5)
+    else:
+        # reranker: ranking by raw logit, stable sort; compare where the oracle's gaps are not ties
+        order_w = ko.stable_argsort_desc(want[:, 0])
+        order_g = [i for i, _ in enc.rerank(ids, mask, types)]
+        gaps = np.abs(np.diff(want[order_w, 0]))
+        if (gaps > 0.1 * scale).all():
+            assert list(order_w) == order_g
+    # the head stage alone on the oracle's fp32 hidden states: argmax / logits bit-for-bit up to summation order
+    hidden = ko.encoder_forward(m, ids, mask, types if m.typ is not None else None, noalloc=False)
+    lg = np.empty_like(want)
+    N.check(N.lib().kjc_dbg_encoder_head(enc._h, ptr(np.ascontiguousarray(hidden)), B, S, ptr(lg)))
+    assert np.abs(lg - want).max() < 1e-4 * scale
+    if want.shape[1] > 1:
+        ties = np.abs(want[:, 0] - want[:, 1]) <= 1e-6
+        assert (lg.argmax(1)[~ties] == want.argmax(1)[~ties]).all()
+    enc.close()
+
+
+def test_hf_golden_logits(dirs):
+    for arch, pair in (("tiny-cross-encoder", True), ("tiny-distilbert", False)):
+        B, S = (int(v) for v in G[arch + "/shape"])
+        ids, mask, types = synth.synth_tokens(B, S, synth.ARCHS[arch][5], regime="P", seed=7, pair=pair)
+        enc = api.EncoderModel(dirs[arch])
+        got = enc.predict_logits(ids, mask, types)
+        assert np.abs(got - G[arch + "/logits"]).max() < 5e-2
+        enc.close()
+
+
+def test_micro_batching_is_invisible(dirs, monkeypatch):
+    """A batch larger than one internal micro-batch gives the same rows as separate calls."""
+    arch = "tiny-bert"
+    ids, mask, _ = synth.synth_tokens(40, 16, synth.ARCHS[arch][5], regime="P", seed=3)
+    monkeypatch.setenv("KJC_MICRO_TOKENS", "128")  # 8 sequences per micro-batch
+    small = api.EncoderModel(dirs[arch])
+    monkeypatch.delenv("KJC_MICRO_TOKENS")
+    big = api.EncoderModel(dirs[arch])
+    assert small.micro_batch(16) == 8 and big.micro_batch(16) > 40
+    a = small.encode_batch_from_ids(ids, mask)
+    b = big.encode_batch_from_ids(ids, mask)
+    assert np.array_equal(a, b)  # rows are independent: identical bits regardless of batching
+    small.close()
+    big.close()
+
+
+def test_edge_cases(dirs):
+    arch = "tiny-bert"
+    enc = api.EncoderModel(dirs[arch])
+    m = ko.load_model_dir(dirs[arch])
+    # single token, single sequence (tokens <= 1 -> no-alloc convention)
+    ids = np.array([[101]], np.uint32)
+    mask = np.ones((1, 1), np.uint32)
+    assert cosine_rows(enc.encode_batch_from_ids(ids, mask), ko.embed(m, ids, mask)).min() >= COS_MIN
+    # ids >= vocab contribute a zero word row; mask=None means all ones
+    ids = np.array([[101, 5000, 999999, 102]], np.uint32)
+    mask = np.ones((1, 4), np.uint32)
+    assert cosine_rows(enc.encode_batch_from_ids(ids, None), ko.embed(m, ids, mask)).min() >= COS_MIN
+    # a fully padded row: alloc convention -> mean-pool falls back to token 0 (count == 0)
+    ids, mask, _ = synth.synth_tokens(3, 8, 1000, regime="T", seed=1)
+    mask[1, :] = 0
+    got = enc._forward(ids, mask, None, N.OUT_POOLED, N.POOL_MEAN, True, N.MASK_ALLOC)
+    hidden = ko.encoder_forward(m, ids, mask, None, noalloc=False)
+    want = ko.l2_normalize(ko.mean_pool(hidden, mask.astype(np.float32)))
+    assert cosine_rows(got, want).min() >= COS_MIN
+    # no-alloc convention: that row is NaN in the reference too
+    got = enc._forward(ids, mask, None, N.OUT_POOLED, N.POOL_MEAN, True, N.MASK_NOALLOC)
+    assert np.isnan(got[1]).all() and np.isfinite(got[[0, 2]]).all()
+    # errors
+    with pytest.raises(N.KjarniCudaError) as e:
+        enc.predict_logits(ids, mask)
+    assert e.value.status == 7
+    with pytest.raises(N.KjarniCudaError):
+        enc._forward(np.zeros((1, 600), np.uint32), None, None, N.OUT_POOLED)
+    with pytest.raises(N.KjarniCudaError) as e:
+        enc.forward_tokens(ids, mask, np.full_like(ids, 9))  # token-type id out of range: the reference panics
+    assert e.value.status == 5
+    enc.close()
+    with pytest.raises(N.KjarniCudaError) as e:
+        api.EncoderModel("/nonexistent/dir")
+    assert e.value.status == 3

@@ -1,0 +1,120 @@
+"""Single-kernel parity (through the C ABI debug hooks): tcgen05 GEMM + epilogues and the
+fused attention kernel against fp32 numpy restatements on the same bf16-rounded inputs."""
+import math
+
+import numpy as np
+import pytest
+
+from kjarni_b200 import _native as N
+from oracle import kjarni_oracle as ko
+from kj_testutil import bf16_round, from_bf16_bits, ptr, to_bf16_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gemm(a, w, bias, res, epi, act=3, block_n=0):
+    M, K = a.shape
+    Nn = w.shape[0]
+    ab, wb = to_bf16_bits(a), to_bf16_bits(w)
+    f32out = epi in (2, 3)
+    out = np.empty((M, Nn), np.float32 if f32out else np.uint16)
+    N.check(N.lib().kjc_dbg_gemm(ptr(ab), ptr(wb), ptr(bias), ptr(res), M, Nn, K, epi, act, block_n, ptr(out)))
+    return out if f32out else from_bf16_bits(out)
+
+
+def ref_gemm(a, w, bias, res, epi, act):
+    y = bf16_round(a).astype(np.float64) @ bf16_round(w).astype(np.float64).T
+    if bias is not None:
+        y = y + bias
+    if epi == 1:
+        y32 = y.astype(np.float32)
+        y = {0: ko.gelu_erf, 1: ko.gelu_tanh, 2: lambda t: np.maximum(t, 0), 3: lambda t: t}[act](y32).astype(np.float64)
+    if epi == 2:
+        y = y + res
+    return y.astype(np.float32)
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (256, 384, 384), (300, 1152, 384), (1000, 384, 1536), (77, 96, 32),
+                                    (4096, 1536, 384), (2048, 768, 3072), (130, 2304, 768)])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+def test_gemm_matches_fp32(M, Nn, K, epi):
+    rng = np.random.default_rng(M * 7 + Nn + K + epi)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((Nn, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(Nn).astype(np.float32)
+    res = rng.standard_normal((M, Nn)).astype(np.float32) if epi == 2 else None
+    got = run_gemm(a, w, bias, res, epi, act=0)
+    want = ref_gemm(a, w, bias, res, epi, 0)
+    tol = 1e-4 if epi in (2, 3) else 2.0 ** -8  # fp32 out: accumulation order only; bf16 out: one rounding
+    err = np.abs(got - want) / (1.0 + np.abs(want))
+    assert np.isfinite(got).all()
+    assert err.max() < tol, (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 192, 256])
+def test_gemm_every_block_n_and_tails(block_n):
+    rng = np.random.default_rng(block_n)
+    M, Nn, K = 333, 416, 200  # M tail, N tail for every BN, K tail (K % 64 != 0)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = rng.standard_normal((Nn, K)).astype(np.float32) * 0.1
+    bias = rng.standard_normal(Nn).astype(np.float32)
+    got = run_gemm(a, w, bias, None, 3, block_n=block_n)
+    want = ref_gemm(a, w, bias, None, 3, 3)
+    assert np.abs(got - want).max() < 1e-3
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_gemm_activations(act):
+    rng = np.random.default_rng(act)
+    a = rng.standard_normal((256, 128)).astype(np.float32) * 2
+    w = rng.standard_normal((256, 128)).astype(np.float32) * 0.3
+    bias = rng.standard_normal(256).astype(np.float32)
+    got = run_gemm(a, w, bias, None, 1, act=act)
+    want = ref_gemm(a, w, bias, None, 1, act)
+    tol = 3e-3 if act == 1 else 2.0 ** -8  # tanh.approx has ~5e-4 absolute error
+    assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2 * tol
+
+
+def ref_attention(qkv, mask, B, S, H, heads, noalloc):
+    d = H // heads
+    x = bf16_round(qkv).reshape(B, S, 3, heads, d)
+    q, k, v = (x[:, :, i].transpose(0, 2, 1, 3) for i in range(3))
+    s = (q @ k.transpose(0, 1, 3, 2)) * np.float32(1.0 / math.sqrt(d))
+    fill = np.float32(-np.inf) if noalloc else ko.MASK_VALUE
+    s = np.where((mask == 0)[:, None, None, :], fill, s).astype(np.float32)
+    p = ko.softmax_rows(s)
+    return (p @ v).transpose(0, 2, 1, 3).reshape(B * S, H)
+
+
+@pytest.mark.parametrize("B,S,H,heads", [(3, 16, 64, 4), (2, 128, 384, 12), (3, 100, 128, 2), (2, 512, 128, 2), (2, 256, 64, 2), (5, 7, 32, 2)])
+def test_attention_matches_fp32(B, S, H, heads):
+    rng = np.random.default_rng(S + H)
+    qkv = rng.standard_normal((B * S, 3 * H)).astype(np.float32)
+    mask = np.ones((B, S), np.float32)
+    mask[0, S // 2:] = 0  # padded tail
+    if B > 1:
+        mask[1, ::3] = 0  # holes, including position 0
+    out = np.empty((B * S, H), np.uint16)
+    N.check(N.lib().kjc_dbg_attention(ptr(to_bf16_bits(qkv)), ptr(mask), B, S, H, heads, 0, ptr(out)))
+    got = from_bf16_bits(out)
+    want = ref_attention(qkv, mask, B, S, H, heads, noalloc=False)
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() < 2e-2  # P and the output are rounded to bf16
+
+
+def test_attention_fully_padded_sequence_conventions():
+    B, S, H, heads = 2, 32, 64, 2
+    rng = np.random.default_rng(0)
+    qkv = rng.standard_normal((B * S, 3 * H)).astype(np.float32)
+    mask = np.ones((B, S), np.float32)
+    mask[1, :] = 0
+    out = np.empty((B * S, H), np.uint16)
+    # alloc convention (-1e9): a fully padded sequence attends uniformly over all S keys
+    N.check(N.lib().kjc_dbg_attention(ptr(to_bf16_bits(qkv)), ptr(mask), B, S, H, heads, 0, ptr(out)))
+    got = from_bf16_bits(out)
+    want = ref_attention(qkv, mask, B, S, H, heads, noalloc=False)
+    assert np.abs(got - want).max() < 2e-2
+    # no-alloc convention (-inf): the reference produces NaN for that sequence, finite elsewhere
+    N.check(N.lib().kjc_dbg_attention(ptr(to_bf16_bits(qkv)), ptr(mask), B, S, H, heads, 1, ptr(out)))
+    got = from_bf16_bits(out)
+    assert np.isnan(got[S:]).all() and np.isfinite(got[:S]).all()
