@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the kjarni-b200 hot path.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): MiniLM-L6 seq-128 sentence embeddings per second (whole job, all GPUs);
+the index top-k scan (queries/s) rides along in the same JSON line under "index_topk".
+One step = one batch of synthetic token ids through the encoder forward + mean-pool + L2.
+  value     : inputs already resident in HBM, device-timed (CUDA events), max over ranks
+  e2e       : the same batch through the host-buffer C ABI call (H2D of ids/mask and D2H of the
+              embeddings inside the timed region)
+  roofline  : dominant kernel class, algorithmic FLOPs / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline : the fp32 oracle port of the reference CPU path, timed on this box's host cores
+`--impl reference` times that CPU port alone (the reference is Rust and cannot be built here:
+no cargo in the image -- see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH = "minilm-l6"
+SEQ = 128
+METRIC = "MiniLM-L6 seq128 embeddings/sec"
+UNIT = "embeddings/s"
+
+
+def flops_per_seq(H, L, I, S):
+    """projection/FFN GEMMs + attention matmuls, 2 flop/MAC."""
+    return L * S * (8 * H * H + 4 * H * I + 4 * S * H)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.proc = dev, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_embed_rate(model_dir, nseq, seconds=12.0):
+    """fp32 oracle port of the reference CPU path (oracle/kjarni_oracle.py), timed here as the CPU baseline."""
+    from kjarni_b200 import synth
+    from oracle import kjarni_oracle as ko
+
+    m = ko.load_model_dir(model_dir)
+    ids, mask, _ = synth.synth_tokens(nseq, SEQ, synth.ARCHS[ARCH][5], regime="T", seed=42)
+    ko.embed(m, ids[:4], mask[:4])  # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        ko.embed(m, ids, mask)
+        n += nseq
+        dt = time.perf_counter() - t0
+        if dt > seconds:
+            break
+    return n / dt, dt, n
+
+
+def model_dir_for(rank):
+    from kjarni_b200 import synth
+
+    d = os.path.join(tempfile.gettempdir(), f"kjarni_b200_bench_{os.getuid()}_{rank}", ARCH)
+    if not os.path.exists(os.path.join(d, "model.safetensors")):
+        synth.write_model_dir(d, ARCH)
+    return d
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the CPU path (oracle port; kind "port") with all host threads numpy's BLAS uses."""
+    if rank != 0:
+        return
+    nseq = 32  # BASELINE configs[0]: batch 32 x seq 128, the reference's own CPU-runnable case
+    d = model_dir_for(0)
+    from kjarni_b200 import synth
+    from oracle import kjarni_oracle as ko
+
+    m = ko.load_model_dir(d)
+    ids, mask, _ = synth.synth_tokens(nseq, SEQ, synth.ARCHS[ARCH][5], regime="T", seed=42)
+    for _ in range(max(args.warmup, 1)):
+        ko.embed(m, ids, mask)
+    steps = min(args.steps, 20)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ko.embed(m, ids, mask)
+    dt = time.perf_counter() - t0
+    val = nseq * steps / dt
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic token ids, random-init weights (no network)",
+        "config": {"workload": "all-MiniLM-L6-v2 architecture sentence embedding (mean-pool + L2), seq 128",
+                   "sample": f"{nseq} sequences x {SEQ} tokens per step (BASELINE configs[0])"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} steps x {nseq} seqs x {SEQ} tokens, numpy fp32 oracle port of the reference CPU path "
+                                   "(the Rust reference cannot be built in this image: no cargo)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU per step (default 28 micro-batches)")
+    ap.add_argument("--index-rows", type=int, default=6_250_000, help="index shard rows per GPU (BASELINE config 4: 50M/8)")
+    ap.add_argument("--no-index", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from kjarni_b200 import _native as N
+    from kjarni_b200 import api, synth
+
+    torch.cuda.set_device(local_rank)
+    # a real (non-NULL) stream: the library treats NULL as "my own stream", and torch events only see the current stream
+    torch.cuda.set_stream(torch.cuda.Stream())
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = N.lib()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d = model_dir_for(rank)
+    enc = api.EncoderModel(d, device=local_rank)
+    info = enc.info
+    H, L, I = info.hidden_size, info.num_layers, info.intermediate_size
+    mb = enc.micro_batch(SEQ)
+    B = args.batch or 28 * mb  # 28 x 148 = 4144 sequences per GPU per step
+    ids_np, mask_np, _ = synth.synth_tokens(B, SEQ, info.vocab_size, regime="T", seed=42 + rank)
+    maskf_np = mask_np.astype(np.float32)
+    ids_d = torch.from_numpy(ids_np.view(np.int32)).cuda()
+    mask_d = torch.from_numpy(maskf_np).cuda()
+    out_d = torch.empty((B, H), dtype=torch.float32, device="cuda")
+    opts = N.KjcForwardOptions(N.OUT_POOLED, N.POOL_MEAN, 1, N.MASK_AUTO)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_dev():
+        N.check(lib.kjc_encoder_forward_device_async(enc._h, ids_d.data_ptr(), mask_d.data_ptr(), None, B, SEQ, C.byref(opts),
+                                                     out_d.data_ptr(), stream))
+
+    # ---------------------------------------------------------------- value: device-resident inputs
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    barrier()
+    ms = max_over_ranks(ms)
+    launches_per_step = enc.last_launch_count
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---------------------------------------------------------------- e2e: host buffers through the C ABI
+    out_h = np.empty((B, H), np.float32)
+    for _ in range(2):
+        enc.encode_batch_from_ids(ids_np, maskf_np)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(e2e_steps):
+        N.check(lib.kjc_encoder_forward(enc._h, ids_np.ctypes.data, maskf_np.ctypes.data, None, B, SEQ, C.byref(opts), out_h.ctypes.data))
+    dt = time.perf_counter() - t0
+    barrier()
+    dt = max_over_ranks(dt)
+    e2e_val = world * B * e2e_steps / dt
+
+    # ---------------------------------------------------------------- roofline: per-kernel-class CUDA events
+    N.check(lib.kjc_encoder_set_profiling(enc._h, 1))
+    prof_steps = 2
+    for _ in range(prof_steps):
+        step_dev()
+    torch.cuda.synchronize()
+    pms = (C.c_double * 8)()
+    pn = (C.c_int64 * 8)()
+    N.check(lib.kjc_encoder_get_profile(enc._h, pms, pn))
+    N.check(lib.kjc_encoder_set_profiling(enc._h, 0))
+    M = B * SEQ
+    tf = {"gemm_qkv": 2.0 * M * 3 * H * H * L, "gemm_out": 2.0 * M * H * H * L, "gemm_ffn_up": 2.0 * M * H * I * L,
+          "gemm_ffn_down": 2.0 * M * H * I * L, "attention": 4.0 * M * SEQ * H * L}
+    gb = {"layernorm": 2.0 * L * M * H * 10, "embed_ln": M * 4.0 + M * H * 4.0 + M * H * 6.0, "output": M * H * 4.0 + B * H * 4.0}
+    kernels = {}
+    tot_ms = sum(pms[i] for i in range(8)) / prof_steps
+    for i, name in enumerate(N.KERNEL_CLASSES):
+        ms_i = pms[i] / prof_steps
+        if pn[i] == 0:
+            continue
+        k = {"ms_per_step": round(ms_i, 4), "share": round(ms_i / tot_ms, 4), "launches_per_step": int(pn[i] // prof_steps)}
+        if name in tf:
+            k.update(bound="tensor", achieved=round(tf[name] / (ms_i * 1e-3) / 1e12, 2), unit="TFLOP/s", peak=peaks["tf_sustained"])
+        else:
+            k.update(bound="hbm", achieved=round(gb[name] / (ms_i * 1e-3) / 1e9, 1), unit="GB/s", peak=peaks["hbm_gbs"])
+        k["frac"] = round(k["achieved"] / k["peak"], 4)
+        kernels[name] = k
+    dom = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "peak": kernels[dom]["peak"],
+                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic,
+                "peak_source": peaks["src"] + (" bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else " hbm_gbs"),
+                "how": f"CUDA events around every launch, {prof_steps} extra steps after the timed region",
+                "whole_step": {"achieved": round(value / world * flops_per_seq(H, L, I, SEQ) / 1e12, 2), "unit": "TFLOP/s",
+                               "frac": round(value / world * flops_per_seq(H, L, I, SEQ) / 1e12 / peaks["tf_sustained"], 4)},
+                "kernels": kernels}
+
+    # ---------------------------------------------------------------- index top-k scan (second half of the metric)
+    index = None
+    if not args.no_index:
+        try:
+            index = bench_index(args, rank, world, local_rank, lib, N, api, torch, dist, barrier, max_over_ranks, peaks)
+        except Exception as ex:  # keep the headline line even if the shard does not fit
+            index = {"error": str(ex)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, secs, nseq = cpu_port_embed_rate(d, 32)
+        cpu = {"value": round(rate, 2), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{nseq} sequences (batches of 32 x {SEQ} tokens = BASELINE configs[0]) in {secs:.1f} s, "
+                         "numpy fp32 oracle port of the reference CPU path"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic token ids, random-init weights (no network)",
+            "config": {"workload": f"all-MiniLM-L6-v2 architecture sentence embedding (mean-pool + L2), seq {SEQ}, "
+                                   f"{B} sequences per GPU per step in micro-batches of {mb}",
+                       "global_batch": B * world, "seq_len": SEQ, "parallelism": f"dp{world} (batch split, no collective)",
+                       "l2": "activations of one step exceed L2 many times over; the 45 MB of bf16 weights stay L2-resident by design"},
+            "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + maskf_np.nbytes),
+                    "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps, "timing": "wall clock around synchronous C-ABI calls, max over ranks"},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "index_topk": index,
+        }
+        print(json.dumps(line))
+    enc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_index(args, rank, world, local_rank, lib, N, api, torch, dist, barrier, max_over_ranks, peaks):
+    """Row-sharded cosine top-10: every rank scans its shard for the same query batch, candidates are gathered over
+    NCCL (all_gather of [Q,k] ids+scores) and merged by the merge kernel.  HBM-bound regime: 8 queries per pass."""
+    dim, k, nq = 384, 10, 8
+    n = args.index_rows
+    sh = api.IndexShard(dim, n, id_base=rank * n, device=local_rank)
+    sh.append_synthetic(7, rank * n, n)
+    from oracle import kjarni_oracle as ko
+
+    q_np = ko.synth_rows(11, 0, nq, dim)
+    q_d = torch.from_numpy(q_np).cuda()
+    ids_d = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    sc_d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    cnt_d = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    if world > 1:
+        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
+        g_sc = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
+        f_ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        f_sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+
+    def step():
+        N.check(lib.kjc_index_search_device_async(sh._h, q_d.data_ptr(), nq, k, N.SCAN_SEGMENT, ids_d.data_ptr(), sc_d.data_ptr(),
+                                                  cnt_d.data_ptr(), stream))
+        if world > 1:
+            dist.all_gather_into_tensor(g_ids, ids_d)
+            dist.all_gather_into_tensor(g_sc, sc_d)
+            N.check(lib.kjc_topk_merge_device_async(local_rank, g_ids.data_ptr(), g_sc.data_ptr(), world, nq, k, f_ids.data_ptr(),
+                                                    f_sc.data_ptr(), None, stream))
+
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(args.steps, 10)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    barrier()
+    # host-buffer call (H2D of the queries, D2H of ids/scores inside) on this rank's shard
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sh.search_batch(q_np, k)
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    bytes_pass = n * dim * 4.0 + n * 4.0  # rows + cached norms, per GPU
+    gbs = bytes_pass / (ms * 1e-3) / 1e9
+    res = {"value": round(nq / (ms * 1e-3), 1), "unit": "queries/s", "ms_per_step": round(ms, 4), "queries_per_step": nq, "k": k,
+           "rows_per_gpu": n, "rows_total": n * world, "dim": dim, "dtype": "f32",
+           "merge": "none (1 shard)" if world == 1 else "NCCL all_gather of per-shard [Q,k] candidates + merge kernel",
+           "e2e": {"value": round(nq / (e2e_ms * 1e-3), 1), "unit": "queries/s", "h2d_bytes_per_step": int(q_np.nbytes),
+                   "d2h_bytes_per_step": nq * k * 12 + nq * 4},
+           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(gbs / peaks["hbm_gbs"], 4), "traffic": None,
+                        "note": "whole search call (query norms + scan + merge) per GPU; index bytes read once per 8-query pass"},
+           "gpu_launches_per_step": sh.last_launch_count}
+    sh.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,23 @@ int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len);
 /* Number of kernel launches the last forward on this handle enqueued (for bench bookkeeping). */
 int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc);
 
+/* Per-kernel-class device timing (CUDA events around every launch of the forwards issued while profiling
+ * is on).  Used by bench.py for the roofline numbers; perturbs overlap slightly, so never on in a timed region. */
+typedef enum KjcKernelClass {
+    KJC_K_EMBED_LN = 0,      /* gather + LayerNorm */
+    KJC_K_GEMM_QKV = 1,
+    KJC_K_ATTENTION = 2,
+    KJC_K_GEMM_OUT = 3,      /* out-proj + bias + residual */
+    KJC_K_LAYERNORM = 4,
+    KJC_K_GEMM_FFN_UP = 5,   /* + bias + GELU */
+    KJC_K_GEMM_FFN_DOWN = 6, /* + bias + residual */
+    KJC_K_OUTPUT = 7,        /* pool+L2 / head / hidden copy */
+    KJC_NUM_KERNEL_CLASSES = 8
+} KjcKernelClass;
+int kjc_encoder_set_profiling(KjcEncoder* enc, int on);
+/* ms[KJC_NUM_KERNEL_CLASSES], launches[KJC_NUM_KERNEL_CLASSES]: totals since profiling was switched on. */
+int kjc_encoder_get_profile(KjcEncoder* enc, double* ms, int64_t* launches);
+
 /* softmax over the label axis in place (SequenceClassifier::classify_scores_batch,
  * KM/models/sequence_classifier/mod.rs:248-263 -> KT/activations.rs:223-242). Host-side helper. */
 void kjc_softmax_rows(float* logits, int rows, int cols);

@@ -22,6 +22,7 @@ SCAN_SEGMENT, SCAN_VECTORSTORE = 0, 1
 ARCH_NAMES = {0: "bert", 1: "bert_prefixed", 2: "distilbert"}
 HEAD_NAMES = {0: None, 1: "dense_tanh", 2: "pre_relu", 3: "pooler_tanh", 4: "none"}
 NO_ID = 0xFFFFFFFFFFFFFFFF
+KERNEL_CLASSES = ("embed_ln", "gemm_qkv", "attention", "gemm_out", "layernorm", "gemm_ffn_up", "gemm_ffn_down", "output")
 
 
 class KjcEncoderInfo(C.Structure):
@@ -59,6 +60,8 @@ SIGNATURES = {
     "kjc_encoder_forward_device_async": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(KjcForwardOptions), _vp, _vp]),
     "kjc_encoder_micro_batch": (_i, [_vp, _i]),
     "kjc_encoder_last_launch_count": (C.c_int64, [_vp]),
+    "kjc_encoder_set_profiling": (_i, [_vp, _i]),
+    "kjc_encoder_get_profile": (_i, [_vp, _vp, _vp]),
     "kjc_softmax_rows": (None, [_vp, _i, _i]),
     "kjc_index_create": (_i, [_i, _u64, _u64, _i, C.POINTER(_vp)]),
     "kjc_index_destroy": (None, [_vp]),

@@ -106,6 +106,17 @@ int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, con
 int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len) { return enc ? enc->impl.micro_batch(seq_len) : 0; }
 int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc) { return enc ? enc->impl.last_launches() : 0; }
 
+int kjc_encoder_set_profiling(KjcEncoder* enc, int on) {
+    KJC_REQUIRE(enc);
+    return guarded([&] { enc->impl.set_profiling(on != 0); });
+}
+int kjc_encoder_get_profile(KjcEncoder* enc, double* ms, int64_t* launches) {
+    KJC_REQUIRE(enc);
+    KJC_REQUIRE(ms);
+    KJC_REQUIRE(launches);
+    return guarded([&] { enc->impl.get_profile(ms, launches); });
+}
+
 void kjc_softmax_rows(float* x, int rows, int cols) {
     // softmax_inplace, KT/activations.rs:223-242: max-subtract, exp, divide only if the sum is > 0
     if (!x) return;

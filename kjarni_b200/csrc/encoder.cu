@@ -122,18 +122,19 @@ void launch_layernorm(const float* y, const float* g, const float* b, float eps,
     KJ_CUDA(cudaGetLastError());
 }
 
-void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
+template <int D>
+static void launch_attention_d(const AttnParams& p, cudaStream_t st) {
+    static int configured[64] = {0};  // per head_dim instantiation
     const size_t smem = attention_smem_bytes(p.S, D);
-    const int grid = p.B * p.heads;
-    auto go = [&](auto kern) {
-        static int configured[64] = {0};
-        if (smem > 48 * 1024) ensure_smem_attr(kern, static_cast<int>(smem), configured);
-        kern<<<grid, kAttnThreads, smem, st>>>(p);
-    };
+    if (smem > 48 * 1024) ensure_smem_attr(attention_kernel<D>, static_cast<int>(smem), configured);
+    attention_kernel<D><<<p.B * p.heads, kAttnThreads, smem, st>>>(p);
+}
+
+void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
     switch (D) {
-        case 16: go(attention_kernel<16>); break;
-        case 32: go(attention_kernel<32>); break;
-        case 64: go(attention_kernel<64>); break;
+        case 16: launch_attention_d<16>(p, st); break;
+        case 32: launch_attention_d<32>(p, st); break;
+        case 64: launch_attention_d<64>(p, st); break;
         default: throw Error(KJC_INVALID_CONFIG, "head_dim must be 16, 32 or 64");
     }
     KJ_CUDA(cudaGetLastError());
@@ -419,6 +420,8 @@ Encoder::~Encoder() {
     if (d_f32_) cudaFree(d_f32_);
     if (d_w16_) cudaFree(d_w16_);
     if (d_err_) cudaFree(d_err_);
+    for (ProfRec& r : prof_recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (cudaEvent_t e : prof_pool_) cudaEventDestroy(e);
     if (d_in_) cudaFree(d_in_);
     if (d_out_) cudaFree(d_out_);
     if (h_stage_in_) cudaFreeHost(h_stage_in_);
@@ -470,37 +473,54 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
         e.M = M; e.S = S; e.H = H; e.vocab = info_.vocab_size; e.max_pos = info_.max_position_embeddings;
         e.type_vocab = info_.type_vocab_size; e.pos_offset = info_.position_offset; e.eps = eps;
         const int grid = (M + 7) / 8;
+        prof_begin(KJC_K_EMBED_LN, st);
         dispatch_nv(H, [&](auto nv) { embed_layernorm_kernel<decltype(nv)::value><<<grid, kRowThreads, 0, st>>>(e); });
         KJ_CUDA(cudaGetLastError());
+        prof_end(st);
         ++launches_;
     }
     for (const LayerDev& L : layers_) {
         GemmParams g{};
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
         g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = qkv16_; g.ldo = 3 * H; g.act = ACT_NONE;
+        prof_begin(KJC_K_GEMM_QKV, st);
         launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, g, num_sms_, st);
+        prof_end(st);
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
         AttnParams a;
         a.qkv = qkv16_; a.mask = d_mask; a.ctx = ctx16_; a.B = nb; a.S = S; a.H = H; a.heads = info_.num_heads;
         a.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
         a.nan_if_all_masked = noalloc_convention ? 1 : 0;
+        prof_begin(KJC_K_ATTENTION, st);
         launch_attention(a, d, st);
+        prof_end(st);
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
         g = GemmParams{};
         g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = x32_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+        prof_begin(KJC_K_GEMM_OUT, st);
         launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_ctx16_, L.t_wo, g, num_sms_, st);
+        prof_end(st);
+        prof_begin(KJC_K_LAYERNORM, st);
         launch_layernorm(y32_, L.g1, L.be1, eps, x32_, x16_, M, H, st);
+        prof_end(st);
         // t = act(x W1^T + b1)                                     (standard_new.rs:47-73)
         g = GemmParams{};
         g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = h16_; g.ldo = I; g.act = act_;
+        prof_begin(KJC_K_GEMM_FFN_UP, st);
         launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, g, num_sms_, st);
+        prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
         g = GemmParams{};
         g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = x32_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+        prof_begin(KJC_K_GEMM_FFN_DOWN, st);
         launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_h16_, L.t_w2, g, num_sms_, st);
+        prof_end(st);
+        prof_begin(KJC_K_LAYERNORM, st);
         launch_layernorm(y32_, L.g2, L.be2, eps, x32_, x16_, M, H, st);
+        prof_end(st);
         launches_ += 7;
     }
+    prof_begin(KJC_K_OUTPUT, st);
     if (o.output == KJC_OUT_HIDDEN) {
         KJ_CUDA(cudaMemcpyAsync(d_out, x32_, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
     } else if (o.output == KJC_OUT_POOLED) {
@@ -519,6 +539,56 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     }
+    prof_end(st);
+}
+
+// ---------------------------------------------------------------- profiling
+cudaEvent_t Encoder::prof_event() {
+    if (!prof_pool_.empty()) {
+        cudaEvent_t e = prof_pool_.back();
+        prof_pool_.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    KJ_CUDA(cudaEventCreate(&e));
+    return e;
+}
+void Encoder::prof_begin(int cls, cudaStream_t st) {
+    if (!profiling_) return;
+    ProfRec r{cls, prof_event(), prof_event()};
+    KJ_CUDA(cudaEventRecord(r.a, st));
+    prof_recs_.push_back(r);
+}
+void Encoder::prof_end(cudaStream_t st) {
+    if (!profiling_) return;
+    KJ_CUDA(cudaEventRecord(prof_recs_.back().b, st));
+}
+void Encoder::prof_collect() {
+    for (ProfRec& r : prof_recs_) {
+        KJ_CUDA(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        KJ_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+        prof_ms_[r.cls] += ms;
+        prof_n_[r.cls] += 1;
+        prof_pool_.push_back(r.a);
+        prof_pool_.push_back(r.b);
+    }
+    prof_recs_.clear();
+}
+void Encoder::set_profiling(bool on) {
+    std::lock_guard<std::mutex> lock(mu_);
+    KJ_CUDA(cudaSetDevice(info_.device));
+    prof_collect();
+    profiling_ = on;
+    if (on) {
+        for (int i = 0; i < KJC_NUM_KERNEL_CLASSES; ++i) { prof_ms_[i] = 0; prof_n_[i] = 0; }
+    }
+}
+void Encoder::get_profile(double* ms, int64_t* launches) {
+    std::lock_guard<std::mutex> lock(mu_);
+    KJ_CUDA(cudaSetDevice(info_.device));
+    prof_collect();
+    for (int i = 0; i < KJC_NUM_KERNEL_CLASSES; ++i) { ms[i] = prof_ms_[i]; launches[i] = prof_n_[i]; }
 }
 
 size_t Encoder::out_row_elems(const KjcForwardOptions& o, int S) const {

@@ -54,6 +54,9 @@ class Encoder {
     const std::vector<std::string>& labels() const { return labels_; }
     int micro_batch(int seq_len) const;
     int64_t last_launches() const { return launches_; }
+    // Per-kernel-class CUDA-event timing of the forwards issued while profiling is on (bench roofline numbers).
+    void set_profiling(bool on);
+    void get_profile(double* ms, int64_t* launches);  // arrays of KJC_NUM_KERNEL_CLASSES; synchronises
 
     void forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o, float* out);
     void head_only_host(const float* hidden, int B, int S, float* logits);
@@ -95,6 +98,17 @@ class Encoder {
     int* d_err_ = nullptr;
     int err_host_ = 0;
     int64_t launches_ = 0;
+    // profiling
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    bool profiling_ = false;
+    std::vector<ProfRec> prof_recs_;
+    std::vector<cudaEvent_t> prof_pool_;
+    double prof_ms_[KJC_NUM_KERNEL_CLASSES] = {0};
+    int64_t prof_n_[KJC_NUM_KERNEL_CLASSES] = {0};
+    cudaEvent_t prof_event();
+    void prof_begin(int cls, cudaStream_t st);
+    void prof_end(cudaStream_t st);
+    void prof_collect();
 };
 
 }  // namespace kj

@@ -203,7 +203,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tmem_ld_32x16(taddr0 + c * 16, v);
                 tmem_ld_wait();
                 const int col0 = n_blk * BN + half * kColsPerHalf + c * 16;
-                if (col0 >= p.N) continue;  // N tail (N is a multiple of 16)
+                if (col0 < p.N) {  // N tail (N is a multiple of 16)
                 float f[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
@@ -222,37 +222,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act);
                 }
-                if (!row_ok) continue;
-                if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                    uint4 w0, w1;
-                    w0.x = pack_bf16(f[0], f[1]);
-                    w0.y = pack_bf16(f[2], f[3]);
-                    w0.z = pack_bf16(f[4], f[5]);
-                    w0.w = pack_bf16(f[6], f[7]);
-                    w1.x = pack_bf16(f[8], f[9]);
-                    w1.y = pack_bf16(f[10], f[11]);
-                    w1.z = pack_bf16(f[12], f[13]);
-                    w1.w = pack_bf16(f[14], f[15]);
-                    reinterpret_cast<uint4*>(o)[0] = w0;
-                    reinterpret_cast<uint4*>(o)[1] = w1;
-                } else {
-                    float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                    if (EPI == EPI_BIAS_RES_F32) {
-                        const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
+                if (row_ok) {
+                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                        uint4 w0, w1;
+                        w0.x = pack_bf16(f[0], f[1]);
+                        w0.y = pack_bf16(f[2], f[3]);
+                        w0.z = pack_bf16(f[4], f[5]);
+                        w0.w = pack_bf16(f[6], f[7]);
+                        w1.x = pack_bf16(f[8], f[9]);
+                        w1.y = pack_bf16(f[10], f[11]);
+                        w1.z = pack_bf16(f[12], f[13]);
+                        w1.w = pack_bf16(f[14], f[15]);
+                        reinterpret_cast<uint4*>(o)[0] = w0;
+                        reinterpret_cast<uint4*>(o)[1] = w1;
+                    } else {
+                        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                        if (EPI == EPI_BIAS_RES_F32) {
+                            const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 r = __ldg(r4 + j);
-                            f[4 * j + 0] += r.x;
-                            f[4 * j + 1] += r.y;
-                            f[4 * j + 2] += r.z;
-                            f[4 * j + 3] += r.w;
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 r = __ldg(r4 + j);
+                                f[4 * j + 0] += r.x;
+                                f[4 * j + 1] += r.y;
+                                f[4 * j + 2] += r.z;
+                                f[4 * j + 3] += r.w;
+                            }
                         }
-                    }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j)
+                            reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    }
                 }
+                }  // col0 < N
             }
             // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator stage
             tc_fence_before();

@@ -59,8 +59,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded spin: a pipeline bug turns into a trapped kernel (cudaErrorLaunchFailure) instead of a hung GPU.
+#ifndef KJ_MBAR_SPIN_LIMIT
+#define KJ_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++spins > KJ_MBAR_SPIN_LIMIT) __trap();
     }
 }
 

@@ -54,12 +54,11 @@ __device__ __forceinline__ void warp_topk_insert(float* sc, uint32_t* id, int k,
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     const int pos = cnt;
     const int end = min(n, k - 1);  // entries [pos, end) move to [pos+1, end+1)
-    for (int base = end - 1 - lane; base >= pos - 31; base -= 32) {
-        // process from the tail towards pos, 32 entries per step
-        const int j = base;
+    for (int top = end - 1; top >= pos; top -= 32) {  // warp-uniform bounds; 32 entries per step, tail first
+        const int j = top - lane;
+        const bool act = j >= pos;
         float ts = 0.f;
         uint32_t ti = 0;
-        const bool act = j >= pos && j < end;
         if (act) { ts = sc[j]; ti = id[j]; }
         __syncwarp();
         if (act) { sc[j + 1] = ts; id[j + 1] = ti; }
