@@ -346,8 +346,8 @@ def bench_index(args, rank, world, local_rank, lib, N, api, torch, dist, barrier
     cnt_d = torch.empty((nq,), dtype=torch.int32, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
     if world > 1:
-        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device="cuda")
-        g_sc = torch.empty((world, nq, k), dtype=torch.float32, device="cuda")
+        g_ids = torch.empty((world * nq, k), dtype=torch.int64, device="cuda")  # rank-major concat = [world, nq, k]
+        g_sc = torch.empty((world * nq, k), dtype=torch.float32, device="cuda")
         f_ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
         f_sc = torch.empty((nq, k), dtype=torch.float32, device="cuda")
 
