@@ -11,6 +11,12 @@ extern "C" {
  * act 0 = erf-GELU, 1 = tanh-GELU, 2 = ReLU, 3 = none; block_n 0 = auto (64/128/192/256). */
 int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* residual, int M, int N, int K, int epi,
                  int act, int block_n, void* out);
+/* out[M,384] (bf16) = LayerNorm(A[M,K] x W[384,K]^T + bias + residual[M,384] (bf16)) with the fused kernel;
+ * iters > 0 additionally times `iters` launches (average us in *out_us). */
+int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
+                    const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us);
+/* GEMM microbenchmark: average us per launch. flags: 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip TMA loads. */
+int kjc_dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters, float* out_us);
 /* ctx[B*S,H] = attention(qkv[B*S,3H], mask[B,S]) with the fused kernel. */
 int kjc_dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16);
 /* logits[B,C] = classification head of `enc` applied to caller-supplied fp32 hidden states [B,S,H]. */

@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams p) {
     float* smask = reinterpret_cast<float*>(sv + static_cast<size_t>(s_pad) * kPitch);  // [s_pad] additive code
     __shared__ int s_valid;
 
+    constexpr float kMaskedLog2 = -1.0e9f * 1.4426950408889634f;
     const int b = blockIdx.x / p.heads;
     const int h = blockIdx.x % p.heads;
     const int tid = threadIdx.x;
@@ -71,32 +72,35 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams p) {
     // ---- stage Q, K, V head slices (16-byte chunks), zero-fill rows >= S
     const size_t ld = static_cast<size_t>(3) * p.H;
     const __nv_bfloat16* base = p.qkv + static_cast<size_t>(b) * S * ld + static_cast<size_t>(h) * D;
+    const uint32_t sq_base = smem_u32(sq), sk_base = smem_u32(sk), sv_base = smem_u32(sv);
     for (int i = tid; i < s_pad * kChunksPerRow * 3; i += kAttnThreads) {
         const int which = i / (s_pad * kChunksPerRow);
         const int r = (i / kChunksPerRow) % s_pad;
         const int c = i % kChunksPerRow;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (r < S) val = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(r) * ld + which * p.H + c * 8));
-        uint8_t* dst = (which == 0 ? sq : (which == 1 ? sk : sv)) + static_cast<size_t>(r) * kPitch + c * 16;
-        *reinterpret_cast<uint4*>(dst) = val;
+        const bool in = r < S;
+        const __nv_bfloat16* src = base + static_cast<size_t>(in ? r : 0) * ld + which * p.H + c * 8;
+        const uint32_t dst = (which == 0 ? sq_base : (which == 1 ? sk_base : sv_base)) + r * kPitch + c * 16;
+        // async 16-byte copies (no register staging, all in flight at once); rows >= S are zero-filled (src-size 0)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
     int local_valid = 0;
     for (int j = tid; j < s_pad; j += kAttnThreads) {
-        float code;  // 0 = keep, 1 = padding (score := -1e9), 2 = beyond S (probability exactly 0)
-        if (j >= S) code = 2.0f;
+        float code;  // 0 = keep; otherwise the value the score is replaced by: -1e9*log2e (padding) or -inf (beyond S)
+        if (j >= S) code = -INFINITY;
         else {
             const bool keep = (p.mask == nullptr) || (p.mask[static_cast<size_t>(b) * S + j] != 0.0f);
-            code = keep ? 0.0f : 1.0f;
+            code = keep ? 0.0f : kMaskedLog2;
             local_valid += keep ? 1 : 0;
         }
         smask[j] = code;
     }
     if (local_valid) atomicAdd(&s_valid, local_valid);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const bool poison = p.nan_if_all_masked && (s_valid == 0);
 
-    const uint32_t sq_u = smem_u32(sq), sk_u = smem_u32(sk), sv_u = smem_u32(sv);
-    constexpr float kMaskedLog2 = -1.0e9f * 1.4426950408889634f;
+    const uint32_t sq_u = sq_base, sk_u = sk_base, sv_u = sv_base;
 
     for (int q0 = warp * 16; q0 < S; q0 += (kAttnThreads / 32) * 16) {
         // Q fragments for this warp's 16 rows
@@ -132,12 +136,12 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnParams p) {
 #pragma unroll
             for (int n = 0; n < 8; ++n) {
                 const int j = kb + n * 8 + (lane & 3) * 2;
-                const float c0 = smask[j], c1 = smask[j + 1];
-                float v;
-                v = sc[n][0] * p.scale_log2e; sc[n][0] = c0 == 0.0f ? v : (c0 == 1.0f ? kMaskedLog2 : -INFINITY);
-                v = sc[n][1] * p.scale_log2e; sc[n][1] = c1 == 0.0f ? v : (c1 == 1.0f ? kMaskedLog2 : -INFINITY);
-                v = sc[n][2] * p.scale_log2e; sc[n][2] = c0 == 0.0f ? v : (c0 == 1.0f ? kMaskedLog2 : -INFINITY);
-                v = sc[n][3] * p.scale_log2e; sc[n][3] = c1 == 0.0f ? v : (c1 == 1.0f ? kMaskedLog2 : -INFINITY);
+                const float2 cm = *reinterpret_cast<const float2*>(smask + j);
+                const float c0 = cm.x, c1 = cm.y;
+                sc[n][0] = c0 == 0.0f ? sc[n][0] * p.scale_log2e : c0;
+                sc[n][1] = c1 == 0.0f ? sc[n][1] * p.scale_log2e : c1;
+                sc[n][2] = c0 == 0.0f ? sc[n][2] * p.scale_log2e : c0;
+                sc[n][3] = c1 == 0.0f ? sc[n][3] * p.scale_log2e : c1;
                 bm0 = fmaxf(bm0, fmaxf(sc[n][0], sc[n][1]));
                 bm1 = fmaxf(bm1, fmaxf(sc[n][2], sc[n][3]));
             }

@@ -208,6 +208,17 @@ int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
     return guarded([&] { kj::dbg_gemm(a_bf16, w_bf16, bias, residual, M, N, K, epi, act, block_n, out); });
 }
 
+int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
+                    const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us) {
+    KJC_REQUIRE(a_bf16); KJC_REQUIRE(w_bf16); KJC_REQUIRE(bias); KJC_REQUIRE(gamma); KJC_REQUIRE(beta); KJC_REQUIRE(res_bf16); KJC_REQUIRE(out_bf16);
+    return guarded([&] { kj::dbg_gemm_ln(a_bf16, w_bf16, bias, gamma, beta, eps, res_bf16, M, K, out_bf16, iters, out_us); });
+}
+
+int kjc_dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters, float* out_us) {
+    KJC_REQUIRE(out_us);
+    return guarded([&] { *out_us = kj::dbg_gemm_time(M, N, K, epi, act, block_n, flags, iters); });
+}
+
 int kjc_dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16) {
     KJC_REQUIRE(qkv_bf16);
     KJC_REQUIRE(ctx_bf16);

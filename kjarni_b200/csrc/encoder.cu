@@ -13,6 +13,7 @@
 
 #include "attention.cuh"
 #include "encoder.hpp"
+#include "gemm_ln.cuh"
 #include "gemm_tcgen05.cuh"
 #include "rowwise.cuh"
 
@@ -38,7 +39,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 // 2-D row-major [rows, cols] tensor, box = [box_rows, 64 elements (128 B)], 128-byte swizzle, zero OOB fill.
 CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                         uint32_t box_cols) {
+                         uint32_t box_cols, int swizzle_bytes) {
     CUtensorMap m;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * static_cast<uint64_t>(elem_bytes)};
@@ -47,7 +48,8 @@ CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_byte
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15))
         throw Error(KJC_INVALID_CONFIG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
     CUresult r = get_encode_fn()(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                 swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error(KJC_INFERENCE_FAILED, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
     return m;
 }
@@ -64,7 +66,7 @@ int pick_block_n(int N) {
 }
 
 template <int BN, int EPI>
-static void launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
+static void launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static int configured[64] = {0};
     auto kern = gemm_tcgen05_kernel<BN, EPI>;
@@ -72,30 +74,43 @@ static void launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int grid = std::min(m_tiles * n_tiles, num_sms);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
     KJ_CUDA(cudaGetLastError());
 }
 
 template <int BN>
-static void launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
+static void launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms, cudaStream_t st) {
     switch (epi) {
-        case EPI_BIAS_BF16: launch_gemm_inst<BN, EPI_BIAS_BF16>(ta, tb, p, num_sms, st); break;
-        case EPI_BIAS_ACT_BF16: launch_gemm_inst<BN, EPI_BIAS_ACT_BF16>(ta, tb, p, num_sms, st); break;
-        case EPI_BIAS_RES_F32: launch_gemm_inst<BN, EPI_BIAS_RES_F32>(ta, tb, p, num_sms, st); break;
-        case EPI_BIAS_F32: launch_gemm_inst<BN, EPI_BIAS_F32>(ta, tb, p, num_sms, st); break;
+        case EPI_BIAS_BF16: launch_gemm_inst<BN, EPI_BIAS_BF16>(ta, tb, tc, p, num_sms, st); break;
+        case EPI_BIAS_ACT_BF16: launch_gemm_inst<BN, EPI_BIAS_ACT_BF16>(ta, tb, tc, p, num_sms, st); break;
+        case EPI_BIAS_RES_F32: launch_gemm_inst<BN, EPI_BIAS_RES_F32>(ta, tb, tc, p, num_sms, st); break;
+        case EPI_BIAS_F32: launch_gemm_inst<BN, EPI_BIAS_F32>(ta, tb, tc, p, num_sms, st); break;
         default: throw Error(KJC_INVALID_CONFIG, "unknown GEMM epilogue");
     }
 }
 
-void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st) {
+void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms,
+                 cudaStream_t st) {
     if (p.N % 16 != 0 || p.K % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs N % 16 == 0 and K % 8 == 0");
     switch (block_n) {
-        case 64: launch_gemm_bn<64>(epi, ta, tb, p, num_sms, st); break;
-        case 128: launch_gemm_bn<128>(epi, ta, tb, p, num_sms, st); break;
-        case 192: launch_gemm_bn<192>(epi, ta, tb, p, num_sms, st); break;
-        case 256: launch_gemm_bn<256>(epi, ta, tb, p, num_sms, st); break;
+        case 64: launch_gemm_bn<64>(epi, ta, tb, tc, p, num_sms, st); break;
+        case 128: launch_gemm_bn<128>(epi, ta, tb, tc, p, num_sms, st); break;
+        case 192: launch_gemm_bn<192>(epi, ta, tb, tc, p, num_sms, st); break;
+        case 256: launch_gemm_bn<256>(epi, ta, tb, tc, p, num_sms, st); break;
         default: throw Error(KJC_INVALID_CONFIG, "unsupported GEMM block N");
     }
+}
+
+void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
+                    const float* beta, float eps, int num_sms, cudaStream_t st) {
+    static int configured[64] = {0};
+    if (K % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs K % 8 == 0");
+    ensure_smem_attr(gemm_ln384_kernel, kLnSmemBytes, configured);
+    GemmLnParams p;
+    p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
+    const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    gemm_ln384_kernel<<<std::min(m_tiles, num_sms), kGemmThreads, kLnSmemBytes, st>>>(ta, tw, t_io, t_io, p);
+    KJ_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------ row-kernel launch
@@ -399,10 +414,10 @@ Encoder::Encoder(const std::string& dir, int device) {
         ld.wqkv = d_w16_ + lo[l].wqkv; ld.wo = d_w16_ + lo[l].wo; ld.w1 = d_w16_ + lo[l].w1; ld.w2 = d_w16_ + lo[l].w2;
         ld.bqkv = d_f32_ + lo[l].bqkv; ld.bo = d_f32_ + lo[l].bo; ld.b1 = d_f32_ + lo[l].b1; ld.b2 = d_f32_ + lo[l].b2;
         ld.g1 = d_f32_ + lo[l].g1; ld.be1 = d_f32_ + lo[l].be1; ld.g2 = d_f32_ + lo[l].g2; ld.be2 = d_f32_ + lo[l].be2;
-        ld.t_wqkv = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, bn_qkv_, kGemmBlockK);
-        ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK);
-        ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK);
-        ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK);
+        ld.t_wqkv = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, bn_qkv_, kGemmBlockK, 128);
+        ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK, 128);
+        ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK, 128);
+        ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK, 128);
     }
     if (info_.head_kind != KJC_HEAD_ABSENT) {
         w_pre_ = pre_w.empty() ? nullptr : d_f32_ + off_wpre;
@@ -410,6 +425,8 @@ Encoder::Encoder(const std::string& dir, int device) {
         w_cls_ = d_f32_ + off_wcls;
         b_cls_ = has_bcls ? d_f32_ + off_bcls : nullptr;
     }
+    // hidden 384: out-proj / FFN-down run as one GEMM + bias + residual + LayerNorm kernel (full rows per CTA)
+    fused_ln_ = (H == kLnN) && !getenv("KJC_NO_FUSED_LN");
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
 }
@@ -430,9 +447,9 @@ Encoder::~Encoder() {
 }
 
 void Encoder::free_workspace() {
-    for (void* p : {(void*)x32_, (void*)y32_, (void*)x16_, (void*)qkv16_, (void*)ctx16_, (void*)h16_})
+    for (void* p : {(void*)y32_, (void*)x16_, (void*)qkv16_, (void*)ctx16_, (void*)h16_})
         if (p) cudaFree(p);
-    x32_ = y32_ = nullptr; x16_ = qkv16_ = ctx16_ = h16_ = nullptr;
+    y32_ = nullptr; x16_ = qkv16_ = ctx16_ = h16_ = nullptr;
     ws_tokens_ = 0;
 }
 
@@ -444,8 +461,7 @@ void Encoder::ensure_workspace(int tokens) {
     free_workspace();
     const size_t T = static_cast<size_t>(std::max(tokens, 128));
     const int H = info_.hidden_size, I = info_.intermediate_size;
-    KJ_CUDA(cudaMalloc(&x32_, T * H * 4));
-    KJ_CUDA(cudaMalloc(&y32_, T * H * 4));
+    if (!fused_ln_) KJ_CUDA(cudaMalloc(&y32_, T * H * 4));  // pre-LayerNorm sums of the unfused path
     KJ_CUDA(cudaMalloc(&x16_, T * H * 2));
     KJ_CUDA(cudaMalloc(&qkv16_, T * 3 * H * 2));
     KJ_CUDA(cudaMalloc(&ctx16_, T * H * 2));
@@ -455,9 +471,12 @@ void Encoder::ensure_workspace(int tokens) {
     KJ_CUDA(cudaMemsetAsync(ctx16_, 0, T * H * 2, stream_));
     KJ_CUDA(cudaMemsetAsync(h16_, 0, T * I * 2, stream_));
     KJ_CUDA(cudaStreamSynchronize(stream_));  // the forward may run on a caller stream
-    t_x16_ = make_tmap_2d(x16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK);
-    t_ctx16_ = make_tmap_2d(ctx16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK);
-    t_h16_ = make_tmap_2d(h16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK);
+    t_x16_ = make_tmap_2d(x16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
+    t_ctx16_ = make_tmap_2d(ctx16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
+    t_h16_ = make_tmap_2d(h16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
+    t_qkv16_out_ = make_tmap_2d(qkv16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
+    t_h16_out_ = make_tmap_2d(h16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
+    t_x16_io_ = make_tmap_2d(x16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
     ws_tokens_ = static_cast<int>(T);
 }
 
@@ -469,7 +488,7 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
     {
         EmbedParams e;
         e.ids = d_ids; e.type_ids = d_types; e.word = word_; e.pos = pos_; e.type = type_; e.gamma = emb_g_; e.beta = emb_b_;
-        e.x32 = x32_; e.x16 = x16_; e.err_flag = d_err_;
+        e.x32 = nullptr; e.x16 = x16_; e.err_flag = d_err_;
         e.M = M; e.S = S; e.H = H; e.vocab = info_.vocab_size; e.max_pos = info_.max_position_embeddings;
         e.type_vocab = info_.type_vocab_size; e.pos_offset = info_.position_offset; e.eps = eps;
         const int grid = (M + 7) / 8;
@@ -484,7 +503,7 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
         g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = qkv16_; g.ldo = 3 * H; g.act = ACT_NONE;
         prof_begin(KJC_K_GEMM_QKV, st);
-        launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, g, num_sms_, st);
+        launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, t_qkv16_out_, g, num_sms_, st);
         prof_end(st);
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
         AttnParams a;
@@ -495,47 +514,64 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
         launch_attention(a, d, st);
         prof_end(st);
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
-        g = GemmParams{};
-        g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = x32_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
-        prof_begin(KJC_K_GEMM_OUT, st);
-        launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_ctx16_, L.t_wo, g, num_sms_, st);
-        prof_end(st);
-        prof_begin(KJC_K_LAYERNORM, st);
-        launch_layernorm(y32_, L.g1, L.be1, eps, x32_, x16_, M, H, st);
-        prof_end(st);
+        if (fused_ln_) {
+            prof_begin(KJC_K_GEMM_OUT, st);
+            launch_gemm_ln(t_ctx16_, L.t_wo, t_x16_io_, M, H, L.bo, L.g1, L.be1, eps, num_sms_, st);
+            prof_end(st);
+        } else {
+            g = GemmParams{};
+            g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = x16_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+            prof_begin(KJC_K_GEMM_OUT, st);
+            launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_ctx16_, L.t_wo, t_qkv16_out_, g, num_sms_, st);
+            prof_end(st);
+            prof_begin(KJC_K_LAYERNORM, st);
+            launch_layernorm(y32_, L.g1, L.be1, eps, nullptr, x16_, M, H, st);
+            prof_end(st);
+            ++launches_;
+        }
         // t = act(x W1^T + b1)                                     (standard_new.rs:47-73)
         g = GemmParams{};
         g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = h16_; g.ldo = I; g.act = act_;
         prof_begin(KJC_K_GEMM_FFN_UP, st);
-        launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, g, num_sms_, st);
+        launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, t_h16_out_, g, num_sms_, st);
         prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
-        g = GemmParams{};
-        g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = x32_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
-        prof_begin(KJC_K_GEMM_FFN_DOWN, st);
-        launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_h16_, L.t_w2, g, num_sms_, st);
-        prof_end(st);
-        prof_begin(KJC_K_LAYERNORM, st);
-        launch_layernorm(y32_, L.g2, L.be2, eps, x32_, x16_, M, H, st);
-        prof_end(st);
-        launches_ += 7;
+        if (fused_ln_) {
+            prof_begin(KJC_K_GEMM_FFN_DOWN, st);
+            launch_gemm_ln(t_h16_, L.t_w2, t_x16_io_, M, I, L.b2, L.g2, L.be2, eps, num_sms_, st);
+            prof_end(st);
+        } else {
+            g = GemmParams{};
+            g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = x16_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+            prof_begin(KJC_K_GEMM_FFN_DOWN, st);
+            launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_h16_, L.t_w2, t_qkv16_out_, g, num_sms_, st);
+            prof_end(st);
+            prof_begin(KJC_K_LAYERNORM, st);
+            launch_layernorm(y32_, L.g2, L.be2, eps, nullptr, x16_, M, H, st);
+            prof_end(st);
+            ++launches_;
+        }
+        launches_ += 5;
     }
     prof_begin(KJC_K_OUTPUT, st);
     if (o.output == KJC_OUT_HIDDEN) {
-        KJ_CUDA(cudaMemcpyAsync(d_out, x32_, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));
+        const size_t n4 = static_cast<size_t>(M) * H / 4;
+        bf16_to_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(x16_, d_out, n4);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
     } else if (o.output == KJC_OUT_POOLED) {
-        pool_l2_kernel<<<nb, 256, 0, st>>>(x32_, d_mask, d_out, S, H, o.pooling, o.normalize);
+        pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(x16_, d_mask, d_out, S, H, o.pooling, o.normalize);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else {
-        HeadParams hp;
-        hp.x = x32_; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
+        HeadParams<__nv_bfloat16> hp;
+        hp.x = x16_; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
         hp.B = nb; hp.S = S; hp.H = H; hp.C = info_.num_labels;
         hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
         const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
         static int configured[64] = {0};
-        if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel, static_cast<int>(smem), configured);
-        cls_head_kernel<<<(nb + kHeadSeqs - 1) / kHeadSeqs, 256, smem, st>>>(hp);
+        if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel<__nv_bfloat16>, static_cast<int>(smem), configured);
+        cls_head_kernel<__nv_bfloat16><<<(nb + kHeadSeqs - 1) / kHeadSeqs, 256, smem, st>>>(hp);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     }
@@ -700,14 +736,14 @@ void Encoder::head_only_host(const float* hidden, int B, int S, float* logits) {
     KJ_CUDA(cudaMalloc(&dh, static_cast<size_t>(B) * S * H * 4));
     KJ_CUDA(cudaMalloc(&dl, static_cast<size_t>(B) * Cn * 4));
     KJ_CUDA(cudaMemcpy(dh, hidden, static_cast<size_t>(B) * S * H * 4, cudaMemcpyHostToDevice));
-    HeadParams hp;
+    HeadParams<float> hp;
     hp.x = dh; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = dl;
     hp.B = B; hp.S = S; hp.H = H; hp.C = Cn;
     hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
     const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
     static int configured[64] = {0};
-    if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel, static_cast<int>(smem), configured);
-    cls_head_kernel<<<(B + kHeadSeqs - 1) / kHeadSeqs, 256, smem, stream_>>>(hp);
+    if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel<float>, static_cast<int>(smem), configured);
+    cls_head_kernel<float><<<(B + kHeadSeqs - 1) / kHeadSeqs, 256, smem, stream_>>>(hp);
     KJ_CUDA(cudaGetLastError());
     KJ_CUDA(cudaStreamSynchronize(stream_));
     KJ_CUDA(cudaMemcpy(logits, dl, static_cast<size_t>(B) * Cn * 4, cudaMemcpyDeviceToHost));
@@ -726,7 +762,8 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         const int bn = block_n > 0 ? block_n : pick_block_n(N);
         const size_t Mp = std::max(M, 128), Np = std::max(N, bn);
         __nv_bfloat16 *dA, *dW;
-        float *dB = nullptr, *dR = nullptr;
+        float* dB = nullptr;
+        __nv_bfloat16* dR = nullptr;
         void* dO;
         const bool f32out = epi == EPI_BIAS_RES_F32 || epi == EPI_BIAS_F32;
         KJ_CUDA(cudaMalloc(&dA, Mp * K * 2));
@@ -737,17 +774,111 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         KJ_CUDA(cudaMemcpy(dA, a_bf16, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
         KJ_CUDA(cudaMemcpy(dW, w_bf16, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
         if (bias) { KJ_CUDA(cudaMalloc(&dB, static_cast<size_t>(N) * 4)); KJ_CUDA(cudaMemcpy(dB, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice)); }
-        if (residual) { KJ_CUDA(cudaMalloc(&dR, static_cast<size_t>(M) * N * 4)); KJ_CUDA(cudaMemcpy(dR, residual, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice)); }
-        CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK);
-        CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK);
+        if (residual) {  // the residual stream is bf16 on device
+            std::vector<__nv_bfloat16> rb(static_cast<size_t>(M) * N);
+            for (size_t i = 0; i < rb.size(); ++i) rb[i] = __float2bfloat16_rn(residual[i]);
+            KJ_CUDA(cudaMalloc(&dR, rb.size() * 2));
+            KJ_CUDA(cudaMemcpy(dR, rb.data(), rb.size() * 2, cudaMemcpyHostToDevice));
+        }
+        CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
+        CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK, 128);
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act;
-        launch_gemm(bn, epi, ta, tb, p, prop.multiProcessorCount, nullptr);
+        CUtensorMap tc = ta;
+        if (!f32out) tc = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
+        launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
         KJ_CUDA(cudaDeviceSynchronize());
         KJ_CUDA(cudaMemcpy(out, dO, static_cast<size_t>(M) * N * (f32out ? 4 : 2), cudaMemcpyDeviceToHost));
         cudaFree(dA); cudaFree(dW); cudaFree(dO);
         if (dB) cudaFree(dB);
         if (dR) cudaFree(dR);
+}
+
+// out[M,384] (bf16) = LN(A W^T + bias + residual) with the fused kernel; residual/out bf16 bit patterns.
+void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
+                 const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* us) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    KJ_CUDA(cudaGetDevice(&dev));
+    KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const size_t Mp = std::max(M, 128);
+    __nv_bfloat16 *dA, *dW, *dX;
+    float *dB, *dG, *dBt;
+    KJ_CUDA(cudaMalloc(&dA, Mp * K * 2));
+    KJ_CUDA(cudaMalloc(&dW, static_cast<size_t>(kLnN) * K * 2));
+    KJ_CUDA(cudaMalloc(&dX, Mp * kLnN * 2));
+    KJ_CUDA(cudaMemset(dA, 0, Mp * K * 2));
+    KJ_CUDA(cudaMemset(dX, 0, Mp * kLnN * 2));
+    KJ_CUDA(cudaMalloc(&dB, kLnN * 4)); KJ_CUDA(cudaMalloc(&dG, kLnN * 4)); KJ_CUDA(cudaMalloc(&dBt, kLnN * 4));
+    KJ_CUDA(cudaMemcpy(dA, a_bf16, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dW, w_bf16, static_cast<size_t>(kLnN) * K * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dX, res_bf16, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dB, bias, kLnN * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dG, gamma, kLnN * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dBt, beta, kLnN * 4, cudaMemcpyHostToDevice));
+    CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
+    CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kLnN, K, kLnHalfN, kGemmBlockK, 128);
+    CUtensorMap tio = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, 32, kEpiChunkCols, 64);
+    launch_gemm_ln(ta, tw, tio, M, K, dB, dG, dBt, eps, prop.multiProcessorCount, nullptr);
+    KJ_CUDA(cudaDeviceSynchronize());
+    KJ_CUDA(cudaMemcpy(out_bf16, dX, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyDeviceToHost));
+    if (iters > 0 && us) {  // timing (in place: the values drift, the work does not)
+        cudaEvent_t e0, e1;
+        KJ_CUDA(cudaEventCreate(&e0));
+        KJ_CUDA(cudaEventCreate(&e1));
+        KJ_CUDA(cudaEventRecord(e0, nullptr));
+        for (int i = 0; i < iters; ++i) launch_gemm_ln(ta, tw, tio, M, K, dB, dG, dBt, eps, prop.multiProcessorCount, nullptr);
+        KJ_CUDA(cudaEventRecord(e1, nullptr));
+        KJ_CUDA(cudaDeviceSynchronize());
+        float ms = 0.f;
+        KJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *us = ms * 1e3f / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dX); cudaFree(dB); cudaFree(dG); cudaFree(dBt);
+}
+
+// GEMM microbenchmark: average microseconds per launch over `iters` launches (device buffers, random-ish data).
+float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    KJ_CUDA(cudaGetDevice(&dev));
+    KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int bn = block_n > 0 ? block_n : pick_block_n(N);
+    const size_t Mp = std::max(M, 128), Np = std::max(N, bn);
+    __nv_bfloat16 *dA, *dW;
+    float* dB;
+    __nv_bfloat16* dR;
+    void* dO;
+    KJ_CUDA(cudaMalloc(&dA, Mp * K * 2));
+    KJ_CUDA(cudaMalloc(&dW, Np * K * 2));
+    KJ_CUDA(cudaMemset(dA, 0x3c, Mp * K * 2));
+    KJ_CUDA(cudaMemset(dW, 0x3c, Np * K * 2));
+    KJ_CUDA(cudaMalloc(&dO, Mp * N * 4));
+    KJ_CUDA(cudaMalloc(&dB, static_cast<size_t>(N) * 4));
+    KJ_CUDA(cudaMalloc(&dR, Mp * N * 2));
+    KJ_CUDA(cudaMemset(dB, 0, static_cast<size_t>(N) * 4));
+    KJ_CUDA(cudaMemset(dR, 0, Mp * N * 2));
+    const bool f32out = epi == EPI_BIAS_RES_F32 || epi == EPI_BIAS_F32;
+    CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
+    CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK, 128);
+    CUtensorMap tc = ta;
+    if (!f32out) tc = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, kEpiChunkCols, 64);
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act; p.dbg = flags;
+    cudaEvent_t e0, e1;
+    KJ_CUDA(cudaEventCreate(&e0));
+    KJ_CUDA(cudaEventCreate(&e1));
+    for (int i = 0; i < 5; ++i) launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
+    KJ_CUDA(cudaEventRecord(e0, nullptr));
+    for (int i = 0; i < iters; ++i) launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
+    KJ_CUDA(cudaEventRecord(e1, nullptr));
+    KJ_CUDA(cudaDeviceSynchronize());
+    float ms = 0.f;
+    KJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dW); cudaFree(dO); cudaFree(dB); cudaFree(dR);
+    return ms * 1e3f / iters;
 }
 
 void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16) {

@@ -15,15 +15,21 @@ struct GemmParams;
 struct AttnParams;
 
 CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                         uint32_t box_cols);
+                         uint32_t box_cols, int swizzle_bytes);
 int pick_block_n(int N);
-void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_sms, cudaStream_t st);
+void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms,
+                 cudaStream_t st);
+void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
+                    const float* beta, float eps, int num_sms, cudaStream_t st);
 void launch_attention(const AttnParams& p, int head_dim, cudaStream_t st);
 void launch_layernorm(const float* y, const float* g, const float* b, float eps, float* x32, __nv_bfloat16* x16, int M, int H,
                       cudaStream_t st);
 
 void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* residual, int M, int N, int K, int epi,
               int act, int block_n, void* out);
+void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
+                 const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* us);
+float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters);
 void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16);
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember what each device was configured with.
@@ -86,9 +92,12 @@ class Encoder {
     std::vector<LayerDev> layers_;
     // activations of one micro-batch
     int ws_tokens_ = 0;
-    float *x32_ = nullptr, *y32_ = nullptr;
+    float* y32_ = nullptr;  // unfused path only
+    bool fused_ln_ = false;
     __nv_bfloat16 *x16_ = nullptr, *qkv16_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr;
-    CUtensorMap t_x16_, t_ctx16_, t_h16_;
+    CUtensorMap t_x16_, t_ctx16_, t_h16_;          // A-operand loads
+    CUtensorMap t_qkv16_out_, t_h16_out_;          // epilogue TMA stores
+    CUtensorMap t_x16_io_;                         // residual load + LayerNorm output store of the fused kernel
     // host-buffer entry point staging
     uint32_t* d_in_ = nullptr;
     float* d_out_ = nullptr;

@@ -29,10 +29,11 @@ enum Activation : int { ACT_GELU_ERF = 0, ACT_GELU_TANH = 1, ACT_RELU = 2, ACT_N
 struct GemmParams {
     int M, N, K;
     const float* bias;      // [N] or nullptr
-    const float* residual;  // [M, ldr] fp32 (EPI_BIAS_RES_F32)
+    const __nv_bfloat16* residual;  // [M, ldr] bf16 residual stream (EPI_BIAS_RES_F32)
     void* out;              // [M, ldo] bf16 or f32
     int ldo, ldr;
     int act;
+    int dbg;  // microbenchmark switches (kjc_dbg_gemm_time): 1 = no epilogue work, 2 = no MMA issue, 4 = no TMA loads
 };
 
 constexpr int kGemmBlockM = 128;
@@ -40,32 +41,41 @@ constexpr int kGemmBlockK = 64;
 constexpr int kGemmThreads = 384;
 constexpr int kGemmEpiWarp0 = 4;
 
+constexpr int kEpiWarps = 8;
+constexpr int kEpiChunkCols = 32;                         // columns per tcgen05.ld / per TMA-store box
+constexpr int kEpiStageBytes = 32 * kEpiChunkCols * 2;    // one warp's bf16 staging tile: 32 rows x 64 B (64B swizzle)
+
 template <int BN>
 struct GemmCfg {
-    static constexpr int kStages = (BN <= 128) ? 6 : (BN <= 192 ? 5 : 4);
+    static constexpr int kStages = (BN <= 128) ? 6 : 4;
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
     static constexpr int kBBytes = BN * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiStageBytes;  // double-buffered store staging per epilogue warp
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// erf-GELU, 0.5*x*(1+erf(x/sqrt2)) (reference activations.rs:57-59), with
-// erf(t) = 1 - 2^-q(t), q a degree-6 polynomial fitted on [0, 4.2] (max |erf| error 7e-6,
-// max GELU error 8e-7 -- far below the bf16 rounding of the stored activation).
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float ax = fabsf(x);
-    const float t = fminf(ax * 0.70710678118654752f, 4.2f);
-    float q = -3.0826393e-04f;
-    q = fmaf(q, t, 4.6386556e-03f);
-    q = fmaf(q, t, -3.3037759e-02f);
-    q = fmaf(q, t, 1.5190166e-01f);
-    q = fmaf(q, t, 9.1710484e-01f);
-    q = fmaf(q, t, 1.6281176e+00f);
-    q = q * t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-q));
-    return 0.5f * fmaf(ax, 1.0f - e, x);
+// erf-GELU, 0.5*x*(1+erf(x/sqrt2)) (reference activations.rs:57-59), with erf(t) = 1 - 2^-q(t) for t >= 0,
+// q a degree-5 polynomial without constant term fitted to -log2(erfc(t)) (monotone, so no clamp is needed;
+// max |erf| error 7e-6, max |GELU| error 8e-6 -- far below the bf16 rounding of the stored activation).
+// Two elements per call on the packed fp32x2 pipe: 9 FFMA2/FMUL2 + 2 FABS + 2 MUFU.EX2 per pair.
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+    const uint64_t X = f2_pack(x0, x1);
+    const uint64_t A = f2_pack(fabsf(x0), fabsf(x1));
+    const uint64_t T = f2_mul(A, f2_pack(0.70710678118654752f, 0.70710678118654752f));
+    uint64_t Q = f2_fma(T, f2_pack(-0.0029109f, -0.0029109f), f2_pack(0.02973f, 0.02973f));  // coefficients negated: Q = -q(t)
+    Q = f2_fma(Q, T, f2_pack(-0.14897549f, -0.14897549f));
+    Q = f2_fma(Q, T, f2_pack(-0.9183444f, -0.9183444f));
+    Q = f2_fma(Q, T, f2_pack(-1.6279123f, -1.6279123f));
+    Q = f2_mul(Q, T);
+    float q0, q1, e0, e1;
+    f2_unpack(Q, q0, q1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+    const uint64_t W = f2_fma(f2_pack(e0, e1), f2_pack(-1.0f, -1.0f), f2_pack(1.0f, 1.0f));  // erf(|x|/sqrt2)
+    const uint64_t R = f2_mul(f2_fma(A, W, X), f2_pack(0.5f, 0.5f));                          // 0.5*(x + |x|*erf)
+    f2_unpack(R, x0, x1);
 }
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
     // gelu_new_scalar, activations.rs:62-66
@@ -74,16 +84,26 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));
     return 0.5f * x * (1.0f + th);
 }
-__device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == ACT_GELU_ERF) return gelu_erf_fast(x);
-    if (act == ACT_GELU_TANH) return gelu_tanh_fast(x);
-    if (act == ACT_RELU) return fmaxf(x, 0.0f);
-    return x;
+// Activation over a register tile; the (warp-uniform) switch sits outside the element loop so the
+// 32 independent polynomial chains interleave.
+template <int NELEM>
+__device__ __forceinline__ void apply_act_tile(float (&f)[NELEM], int act) {
+    if (act == ACT_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < NELEM; j += 2) gelu_erf_fast2(f[j], f[j + 1]);
+    } else if (act == ACT_GELU_TANH) {
+#pragma unroll
+        for (int j = 0; j < NELEM; ++j) f[j] = gelu_tanh_fast(f[j]);
+    } else if (act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < NELEM; ++j) f[j] = fmaxf(f[j], 0.0f);
+    }
 }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
@@ -92,7 +112,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tmem_full = bars + 2 * kStages;
@@ -110,6 +131,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16) tma_prefetch_desc(&tmap_c);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
@@ -137,10 +159,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                    tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM,
-                                kEvictFirst);
-                    tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_blk * BN, kEvictLast);
+                    if (p.dbg & 4) {
+                        mbar_arrive(&full_bar[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        tma_load_2d(smem_a + stage * Cfg::kABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, m_blk * kGemmBlockM,
+                                    kEvictFirst);
+                        tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmap_b, &full_bar[stage], kb * kGemmBlockK, n_blk * BN, kEvictLast);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -166,10 +192,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tc_fence_after();
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                        // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-                        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+                            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
@@ -186,7 +214,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
         const int half = ew >> 2;             // column half handled by this warpgroup
         constexpr int kColsPerHalf = BN / 2;
-        constexpr int kChunks = kColsPerHalf / 16;
+        constexpr bool kStaged = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16);
+        uint8_t* stage_buf = smem_epi + ew * 2 * kEpiStageBytes;
+        int sbuf = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
@@ -194,73 +224,110 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * kGemmBlockM + quad * 32 + lane;
+            const int row0 = m_blk * kGemmBlockM + quad * 32;
+            const int row = row0 + lane;
             const bool row_ok = row < p.M;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * kColsPerHalf;
+            if (p.dbg & 1) {
+                // microbenchmark: accumulator released untouched
+            } else if constexpr (kStaged) {
+                // TMEM -> registers -> bias/activation -> bf16 -> swizzled smem tile -> TMA store (coalesced, async)
+                constexpr int kChunks = kColsPerHalf / kEpiChunkCols;
 #pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
-                uint32_t v[16];
-                tmem_ld_32x16(taddr0 + c * 16, v);
-                tmem_ld_wait();
-                const int col0 = n_blk * BN + half * kColsPerHalf + c * 16;
-                if (col0 < p.N) {  // N tail (N is a multiple of 16)
-                float f[16];
+                for (int c = 0; c < kChunks; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + half * kColsPerHalf + c * kEpiChunkCols;
+                    if (col0 < p.N) {
+                        float f[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.bias != nullptr) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.bias != nullptr) {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float4 b = __ldg(b4 + j);
-                        f[4 * j + 0] += b.x;
-                        f[4 * j + 1] += b.y;
-                        f[4 * j + 2] += b.z;
-                        f[4 * j + 3] += b.w;
-                    }
-                }
-                if (EPI == EPI_BIAS_ACT_BF16) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = apply_act(f[j], p.act);
-                }
-                if (row_ok) {
-                    if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16) {
-                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                        uint4 w0, w1;
-                        w0.x = pack_bf16(f[0], f[1]);
-                        w0.y = pack_bf16(f[2], f[3]);
-                        w0.z = pack_bf16(f[4], f[5]);
-                        w0.w = pack_bf16(f[6], f[7]);
-                        w1.x = pack_bf16(f[8], f[9]);
-                        w1.y = pack_bf16(f[10], f[11]);
-                        w1.z = pack_bf16(f[12], f[13]);
-                        w1.w = pack_bf16(f[14], f[15]);
-                        reinterpret_cast<uint4*>(o)[0] = w0;
-                        reinterpret_cast<uint4*>(o)[1] = w1;
-                    } else {
-                        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                        if (EPI == EPI_BIAS_RES_F32) {
-                            const float4* r4 = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 r = __ldg(r4 + j);
-                                f[4 * j + 0] += r.x;
-                                f[4 * j + 1] += r.y;
-                                f[4 * j + 2] += r.z;
-                                f[4 * j + 3] += r.w;
+                            for (int j = 0; j < 8; ++j) {
+                                if (col0 + 4 * j < p.N) {
+                                    const float4 b = __ldg(b4 + j);
+                                    f[4 * j + 0] += b.x;
+                                    f[4 * j + 1] += b.y;
+                                    f[4 * j + 2] += b.z;
+                                    f[4 * j + 3] += b.w;
+                                }
                             }
                         }
+                        if (EPI == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
+                        // the staging buffer we are about to overwrite must have been read by its previous TMA store
+                        if (lane == 0) bulk_wait_read<1>();
+                        __syncwarp();
+                        uint8_t* buf = stage_buf + sbuf * kEpiStageBytes;
+                        const uint32_t rbase = smem_u32(buf) + lane * 64;
+                        const uint32_t sw = (lane >> 1) & 3;  // 64B swizzle: 16-byte chunk index ^= (row >> 1) & 3
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) {
+                            st_shared_v4(rbase + ((j ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_c, buf, col0, row0);
+                            bulk_commit();
+                        }
+                        sbuf ^= 1;
                     }
                 }
-                }  // col0 < N
+            } else {
+                constexpr int kChunks = kColsPerHalf / 16;
+#pragma unroll 1
+                for (int c = 0; c < kChunks; ++c) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr0 + c * 16, v);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + half * kColsPerHalf + c * 16;
+                    if (col0 < p.N) {  // N tail (N is a multiple of 16)
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                        if (p.bias != nullptr) {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 b = __ldg(b4 + j);
+                                f[4 * j + 0] += b.x;
+                                f[4 * j + 1] += b.y;
+                                f[4 * j + 2] += b.z;
+                                f[4 * j + 3] += b.w;
+                            }
+                        }
+                        if (row_ok) {
+                            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
+                            if (EPI == EPI_BIAS_RES_F32) {
+                                const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    const uint4 r = __ldg(r4 + j);
+                                    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        f[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
+                                        f[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        }
+                    }
+                }
             }
             // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (kStaged && lane == 0) bulk_wait_read<0>();  // smem must stay valid until the last store has read it
     }
 
     tc_fence_before();

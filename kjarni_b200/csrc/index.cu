@@ -23,7 +23,7 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
     KJ_CUDA(cudaSetDevice(device));
     KJ_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     KJ_CUDA(cudaMalloc(&rows_, capacity * dim * sizeof(float)));
-    KJ_CUDA(cudaMalloc(&norms_, capacity * sizeof(float)));
+    KJ_CUDA(cudaMalloc(&norms_, capacity * sizeof(float) + 64));  // slack: tail bulk copies round up to 16 B
 }
 
 Index::~Index() {
@@ -110,25 +110,30 @@ void Index::get_rows(uint64_t row, uint64_t n, float* out) const {
     KJ_CUDA(cudaMemcpy(out, rows_ + row * dim_, n * dim_ * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
-template <int QT, int NCH, int RU>
-static void launch_scan_inst(const ScanParams& p, int grid, cudaStream_t st) {
+template <int QT, int NCH>
+static void launch_scan_inst(ScanParams p, int grid, cudaStream_t st) {
     static int configured[64] = {0};
-    const size_t smem = static_cast<size_t>(kScanWarps) * QT * p.k * 8;
-    auto kern = scan_topk_kernel<QT, NCH, RU>;
-    if (smem > 48 * 1024) ensure_smem_attr(kern, static_cast<int>(smem), configured);
-    kern<<<grid, kScanThreads, smem, st>>>(p);
+    // rows per stage / stage count: as much as fits in ~200 KB next to the top-k lists
+    p.rows_per_stage = p.D <= 512 ? 32 : 16;
+    const size_t budget = 200 * 1024 - scan_list_bytes(QT, p.k) - 512;
+    p.nstages = static_cast<int>(std::min<size_t>(4, budget / scan_stage_bytes(p.D, p.rows_per_stage)));
+    if (p.nstages < 2) throw Error(KJC_INVALID_CONFIG, "index dimension too large for the scan pipeline");
+    const size_t smem = scan_smem_bytes(p.D, p.rows_per_stage, p.nstages, QT, p.k);
+    auto kern = scan_topk_kernel<QT, NCH>;
+    ensure_smem_attr(kern, static_cast<int>(smem), configured);
+    kern<<<grid, kScanCtaThreads, smem, st>>>(p);
     KJ_CUDA(cudaGetLastError());
 }
-template <int QT, int RU>
+template <int QT>
 static void launch_scan_qt(const ScanParams& p, int grid, cudaStream_t st) {
     const int nch = (p.D + 127) / 128;
     switch (nch) {
-        case 1: launch_scan_inst<QT, 1, RU>(p, grid, st); break;
-        case 2: launch_scan_inst<QT, 2, RU>(p, grid, st); break;
-        case 3: launch_scan_inst<QT, 3, RU>(p, grid, st); break;
-        case 4: launch_scan_inst<QT, 4, RU>(p, grid, st); break;
-        case 5: case 6: launch_scan_inst<QT, 6, RU>(p, grid, st); break;
-        default: launch_scan_inst<QT, 8, RU>(p, grid, st); break;
+        case 1: launch_scan_inst<QT, 1>(p, grid, st); break;
+        case 2: launch_scan_inst<QT, 2>(p, grid, st); break;
+        case 3: launch_scan_inst<QT, 3>(p, grid, st); break;
+        case 4: launch_scan_inst<QT, 4>(p, grid, st); break;
+        case 5: case 6: launch_scan_inst<QT, 6>(p, grid, st); break;
+        default: launch_scan_inst<QT, 8>(p, grid, st); break;
     }
 }
 
@@ -146,8 +151,10 @@ void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d
     KJ_CUDA(cudaSetDevice(device_));
     if (!st) st = stream_;
     launches_ = 0;
-    const int qt = k > 64 ? 2 : (k > 32 ? 4 : 8);  // queries per pass, bounded by the per-warp list memory
-    const int grid = std::max(1, std::min<int>(num_sms_ * 2, static_cast<int>((len_ + kScanWarps - 1) / kScanWarps)));
+    // queries per warp: bounded by the per-warp list memory (k) and the register file (dim)
+    int qt_max = k > 64 ? 1 : (k > 32 ? 2 : 4);
+    if (dim_ > 512) qt_max = std::min(qt_max, 2);
+    const int grid = std::max<int>(1, static_cast<int>(std::min<uint64_t>(num_sms_, (len_ + 31) / 32)));  // one CTA per SM
     const size_t cand = static_cast<size_t>(grid) * nq * k;
     if (cand > cand_cap_) {
         if (d_cand_s_) cudaFree(d_cand_s_);
@@ -168,13 +175,16 @@ void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d
         ScanParams p;
         p.rows = rows_; p.norms = norms_; p.queries = d_q; p.qnorms = d_qn_; p.out_scores = d_cand_s_; p.out_ids = d_cand_i_;
         p.n_rows = len_; p.D = dim_; p.Q = nq; p.k = k; p.mode = mode;
-        for (int q0 = 0; q0 < nq; q0 += qt) {
+        for (int q0 = 0; q0 < nq;) {
             p.q0 = q0;
             const int rem = nq - q0;
-            if (qt == 8 && rem > 4) launch_scan_qt<8, 2>(p, grid, st);
-            else if (qt >= 4 && rem > 2) launch_scan_qt<4, 2>(p, grid, st);
-            else if (rem > 1) launch_scan_qt<2, 4>(p, grid, st);
-            else launch_scan_qt<1, 4>(p, grid, st);
+            int qt = qt_max;
+            while (qt > 1 && qt / 2 >= rem) qt /= 2;  // smallest per-warp tile that still covers the remainder in one group
+            p.ngroups = rem > qt ? 2 : 1;
+            if (qt == 4) launch_scan_qt<4>(p, grid, st);
+            else if (qt == 2) launch_scan_qt<2>(p, grid, st);
+            else launch_scan_qt<1>(p, grid, st);
+            q0 += qt * p.ngroups;
             ++launches_;
         }
     }

@@ -9,6 +9,14 @@ namespace kj {
 
 constexpr int kRowThreads = 256;  // 8 rows per CTA
 
+// 4 consecutive activations as fp32, from either fp32 or bf16 storage.
+__device__ __forceinline__ float4 load4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4f(const __nv_bfloat16* p) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+}
+
 // LayerNorm over H held as float4 chunks: biased variance, eps inside the sqrt
 // (reference: kjarni-transformers/src/cpu/normalization/layer_norm.rs:37-134).
 template <int NV>  // float4 chunks per lane
@@ -105,8 +113,8 @@ __global__ void __launch_bounds__(kRowThreads) embed_layernorm_kernel(EmbedParam
         }
         v[i] = a;
     }
-    warp_layernorm_store<NV>(v, p.H, lane, p.gamma, p.beta, p.eps, p.x32 + static_cast<size_t>(row) * p.H,
-                             p.x16 + static_cast<size_t>(row) * p.H);
+    warp_layernorm_store<NV>(v, p.H, lane, p.gamma, p.beta, p.eps, p.x32 ? p.x32 + static_cast<size_t>(row) * p.H : nullptr,
+                             p.x16 ? p.x16 + static_cast<size_t>(row) * p.H : nullptr);
 }
 
 // x = LN(y) where y already holds residual + projection (+bias) from the GEMM epilogue.
@@ -132,11 +140,12 @@ layernorm_kernel(const float* __restrict__ y, const float* __restrict__ gamma, c
 enum PoolMode : int { POOL_MEAN = 0, POOL_CLS = 1, POOL_MAX = 2, POOL_LAST = 3 };
 
 // One CTA per sequence, one thread per 4 hidden columns; fused optional L2 normalise.
+template <typename TIn>
 __global__ void __launch_bounds__(256)
-pool_l2_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int S, int H, int mode,
+pool_l2_kernel(const TIn* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int S, int H, int mode,
                int normalize) {
     const int b = blockIdx.x;
-    const float* xb = x + static_cast<size_t>(b) * S * H;
+    const TIn* xb = x + static_cast<size_t>(b) * S * H;
     const float* mb = mask ? mask + static_cast<size_t>(b) * S : nullptr;
     __shared__ float red[8];
     __shared__ float s_count;
@@ -167,14 +176,14 @@ pool_l2_kernel(const float* __restrict__ x, const float* __restrict__ mask, floa
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < H) {
             if (mode == POOL_CLS || (mode == POOL_MEAN && count == 0.0f)) {
-                a = *reinterpret_cast<const float4*>(xb + c);
+                a = load4f(xb + c);
             } else if (mode == POOL_LAST) {
-                a = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(s_last) * H + c);
+                a = load4f(xb + static_cast<size_t>(s_last) * H + c);
             } else if (mode == POOL_MEAN) {
                 for (int s = 0; s < S; ++s) {
                     const float m = mb ? mb[s] : 1.0f;
                     if (m != 0.0f) {
-                        const float4 t = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(s) * H + c);
+                        const float4 t = load4f(xb + static_cast<size_t>(s) * H + c);
                         a.x += t.x * m; a.y += t.y * m; a.z += t.z * m; a.w += t.w * m;
                     }
                 }
@@ -184,7 +193,7 @@ pool_l2_kernel(const float* __restrict__ x, const float* __restrict__ mask, floa
                 for (int s = 0; s < S; ++s) {
                     const float m = mb ? mb[s] : 1.0f;
                     if (m != 0.0f) {
-                        const float4 t = *reinterpret_cast<const float4*>(xb + static_cast<size_t>(s) * H + c);
+                        const float4 t = load4f(xb + static_cast<size_t>(s) * H + c);
                         a.x = fmaxf(a.x, t.x); a.y = fmaxf(a.y, t.y); a.z = fmaxf(a.z, t.z); a.w = fmaxf(a.w, t.w);
                     }
                 }
@@ -220,14 +229,16 @@ pool_l2_kernel(const float* __restrict__ x, const float* __restrict__ mask, floa
 // One CTA per kHeadSeqs sequences: every W_pre row read from L2 is reused for all of them.
 enum HeadAct : int { HEAD_NONE = 0, HEAD_TANH = 1, HEAD_RELU = 2 };
 constexpr int kHeadSeqs = 8;
+template <typename TIn>
 struct HeadParams {
-    const float* x;  // [B, S, H] last hidden state (fp32)
+    const TIn* x;  // [B, S, H] last hidden state (bf16 from the encoder, fp32 from the debug hook)
     const float* w_pre; const float* b_pre;  // [H,H], [H] or nullptr
     const float* w_cls; const float* b_cls;  // [C,H], [C]
     float* logits;   // [B, C]
     int B, S, H, C, act;
 };
-__global__ void __launch_bounds__(256) cls_head_kernel(HeadParams p) {
+template <typename TIn>
+__global__ void __launch_bounds__(256) cls_head_kernel(HeadParams<TIn> p) {
     extern __shared__ float hs[];  // z0[kHeadSeqs][H], z1[kHeadSeqs][H]
     float* z0 = hs;
     float* z1 = hs + kHeadSeqs * p.H;
@@ -236,7 +247,7 @@ __global__ void __launch_bounds__(256) cls_head_kernel(HeadParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < kHeadSeqs * p.H; i += 256) {
         const int s = i / p.H, c = i % p.H;
-        z0[i] = s < nb ? p.x[static_cast<size_t>(b0 + s) * p.S * p.H + c] : 0.0f;
+        z0[i] = s < nb ? static_cast<float>(p.x[static_cast<size_t>(b0 + s) * p.S * p.H + c]) : 0.0f;
     }
     __syncthreads();
     const float* zin = z0;
@@ -275,6 +286,12 @@ __global__ void __launch_bounds__(256) cls_head_kernel(HeadParams p) {
         acc = warp_sum(acc);
         if (lane == 0) p.logits[static_cast<size_t>(b0 + s) * p.C + cls] = acc + (p.b_cls ? p.b_cls[cls] : 0.0f);
     }
+}
+
+// bf16 -> fp32 (the KJC_OUT_HIDDEN output).
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n4) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n4) *reinterpret_cast<float4*>(out + 4 * i) = load4f(in + 4 * i);
 }
 
 // fp32 -> bf16 weight pre-pack (done once at load).

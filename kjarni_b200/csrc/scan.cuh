@@ -4,10 +4,11 @@
 // (kjarni-search/src/vector.rs:131-165); the per-shard top-k followed by a merge is
 // the shape IndexReader::search_semantic already has (kjarni-rag/src/index_reader.rs:207-228).
 //
-// HBM-bound design: every index byte is read exactly once per pass of up to 8 queries;
-// one warp owns one row at a time (fully coalesced 16-byte loads, several rows in
-// flight per warp), queries live in registers, per-warp sorted top-k lists live in
-// shared memory and are touched only when a score beats the current k-th best.
+// HBM-bound design: every index byte is read exactly once per pass of up to 8 queries.
+// Rows are streamed through a ring of shared-memory stages by the TMA engine (cp.async.bulk,
+// ~190 KB in flight per SM, independent of register pressure); 8 consumer warps own one row
+// at a time, queries live in registers, per-warp sorted top-k lists live in shared memory
+// and are touched only when a score beats the current k-th best.
 // Order everywhere is (score desc, id asc) = the reference's stable sorts.
 #pragma once
 #include "ptx.cuh"
@@ -72,107 +73,192 @@ __device__ __forceinline__ void warp_topk_insert(float* sc, uint32_t* id, int k,
 
 struct ScanParams {
     const float* rows;      // [n_rows, D]
-    const float* norms;     // [n_rows]
+    const float* norms;     // [n_rows] (+16 B slack: the tail chunk's bulk copy is rounded up to 16 B)
     const float* queries;   // [Q, D]
     const float* qnorms;    // [Q]
     float* out_scores;      // [gridDim.x, Q, k]  per-CTA sorted candidates
     uint32_t* out_ids;      // [gridDim.x, Q, k]  local row index, kNoId32 = empty
     size_t n_rows;
     int D, Q, k, q0, mode;  // q0: first query of this pass
+    int rows_per_stage, nstages;
+    int ngroups;            // 1 or 2 warp groups; group g scores queries q0 + g*QT .. q0 + g*QT + QT - 1
 };
 
-// QT queries per pass, NCH = ceil(D/128) float4 chunks per lane, RU rows in flight per warp.
-template <int QT, int NCH, int RU>
-__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(ScanParams p) {
-    extern __shared__ __align__(16) uint8_t smem_scan[];
+constexpr int kScanConsumerWarps = 16;
+constexpr int kScanCtaThreads = (kScanConsumerWarps + 1) * 32;  // + 1 producer warp
+
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map), completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :
+                 : "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+inline size_t scan_stage_bytes(int D, int rows_per_stage) { return static_cast<size_t>(rows_per_stage) * D * 4 + ((rows_per_stage * 4 + 15) & ~15); }
+inline size_t scan_list_bytes(int QT, int k) { return static_cast<size_t>(kScanConsumerWarps) * QT * k * 8; }
+inline size_t scan_smem_bytes(int D, int rows_per_stage, int nstages, int QT, int k) {
+    return 128 /*align*/ + nstages * scan_stage_bytes(D, rows_per_stage) + 2 * nstages * 8 + scan_list_bytes(QT, k);
+}
+
+// QT queries per warp (1/2/4), NCH = ceil(D/128) float4 chunks per lane.
+// One CTA per SM: a producer thread streams chunks of `rows_per_stage` consecutive rows (+ their cached norms) through
+// a ring of shared-memory stages with cp.async.bulk (~190 KB in flight per SM); 16 consumer warps in 1 or 2 groups take
+// one row each per turn from the landed stage (with 2 groups, both read every row and score different queries).
+// Dot products run on the packed FFMA2 pipe; the QT sums of a row are reduced across the warp with a transposed
+// butterfly, so the warp ends up with one finished score per 32/QT lanes and does one divide per row.
+template <int QT, int NCH>
+__global__ void __launch_bounds__(kScanCtaThreads, 1) scan_topk_kernel(ScanParams p) {
+    constexpr int LOGQ = QT == 4 ? 2 : (QT == 2 ? 1 : 0);
+    constexpr int GROUP_SHIFT = 5 - LOGQ;  // lanes per query group = 1 << GROUP_SHIFT
+    extern __shared__ uint8_t smem_scan_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_scan_raw) + 127) & ~uintptr_t(127));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k = p.k, D = p.D;
-    // per-warp lists: [warp][QT][k]
-    float* lsc = reinterpret_cast<float*>(smem_scan) + (static_cast<size_t>(warp) * QT) * k;
-    uint32_t* lid = reinterpret_cast<uint32_t*>(smem_scan + static_cast<size_t>(kScanWarps) * QT * k * 4) + (static_cast<size_t>(warp) * QT) * k;
-    const int nq = min(QT, p.Q - p.q0);
+    const int k = p.k, D = p.D, rps = p.rows_per_stage, nst = p.nstages;
+    const size_t row_bytes = static_cast<size_t>(D) * 4;
+    const size_t stage_rows_bytes = static_cast<size_t>(rps) * row_bytes;
+    const size_t stage_bytes = stage_rows_bytes + ((rps * 4 + 15) & ~15);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
+    uint64_t* empty_bar = full_bar + nst;
+    uint8_t* lists = reinterpret_cast<uint8_t*>(empty_bar + nst);
+    float* all_sc = reinterpret_cast<float*>(lists);
+    uint32_t* all_id = reinterpret_cast<uint32_t*>(lists + static_cast<size_t>(kScanConsumerWarps) * QT * k * 4);
+    __shared__ int s_cnt[kScanConsumerWarps][QT];
 
-    float4 q[QT][NCH];
-    float qn[QT];
-#pragma unroll
-    for (int t = 0; t < QT; ++t) {
-        const int qi = p.q0 + min(t, nq - 1);
-        qn[t] = p.qnorms[qi];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int col = (lane + 32 * c) * 4;
-            q[t][c] = col < D ? *reinterpret_cast<const float4*>(p.queries + static_cast<size_t>(qi) * D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], kScanConsumerWarps);
         }
+        fence_mbar_init();
     }
-    int cnt[QT];
-    float thr[QT];
-#pragma unroll
-    for (int t = 0; t < QT; ++t) { cnt[t] = 0; thr[t] = -INFINITY; }
+    __syncthreads();
 
-    const size_t gw = static_cast<size_t>(blockIdx.x) * kScanWarps + warp;
-    const size_t nw = static_cast<size_t>(gridDim.x) * kScanWarps;
-    for (size_t r0 = gw * RU; r0 < p.n_rows; r0 += nw * RU) {
-        float4 v[RU][NCH];
-        float rn[RU];
+    const size_t n_chunks = (p.n_rows + rps - 1) / rps;
+    const int wpg = kScanConsumerWarps / p.ngroups;  // warps per group
+    const int nq_pass = min(QT * p.ngroups, p.Q - p.q0);
+
+    if (warp == kScanConsumerWarps) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            int it = 0;
+            for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+                const int stage = it % nst;
+                const uint32_t phase = (it / nst) & 1;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const size_t row0 = c * rps;
+                const uint32_t rows_in = static_cast<uint32_t>(min(static_cast<size_t>(rps), p.n_rows - row0));
+                const uint32_t b_rows = rows_in * static_cast<uint32_t>(row_bytes);
+                const uint32_t b_norm = (rows_in * 4 + 15) & ~15u;
+                uint8_t* dst = smem + stage * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[stage], b_rows + b_norm);
+                bulk_load_1d(dst, p.rows + row0 * D, b_rows, &full_bar[stage]);
+                bulk_load_1d(dst + stage_rows_bytes, p.norms + row0, b_norm, &full_bar[stage]);
+            }
+        }
+    } else {
+        // ----------------------------------------------------------- consumers
+        const int grp = warp / wpg, wg = warp % wpg;
+        const int gq0 = p.q0 + grp * QT;                       // first query of this warp's group
+        const int nq = max(0, min(QT, p.Q - gq0));             // live queries of this group (0: idle group, only hand-shakes)
+        float* lsc = all_sc + (static_cast<size_t>(warp) * QT) * k;
+        uint32_t* lid = all_id + (static_cast<size_t>(warp) * QT) * k;
+        uint64_t q[QT][NCH][2];  // packed pairs (x,y) and (z,w)
 #pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            const size_t r = min(r0 + u, p.n_rows - 1);
-            const float* rp = p.rows + r * D;
+        for (int t = 0; t < QT; ++t) {
+            const int qi = min(gq0 + min(t, max(nq - 1, 0)), p.Q - 1);
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 const int col = (lane + 32 * c) * 4;
-                v[u][c] = col < D ? ld_stream_f4(rp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 f = col < D ? *reinterpret_cast<const float4*>(p.queries + static_cast<size_t>(qi) * D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                q[t][c][0] = f2_pack(f.x, f.y);
+                q[t][c][1] = f2_pack(f.z, f.w);
             }
-            rn[u] = __ldg(p.norms + r);
         }
+        const int t_mine = lane >> GROUP_SHIFT;
+        const bool owner = (lane & ((1 << GROUP_SHIFT) - 1)) == 0 && t_mine < nq;
+        const float qn_mine = p.qnorms[min(gq0 + min(t_mine, max(nq - 1, 0)), p.Q - 1)];
+        int cnt_mine = 0;
+        float thr_mine = -INFINITY;
+
+        int it = 0;
+        for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+            const int stage = it % nst;
+            const uint32_t phase = (it / nst) & 1;
+            const size_t row0 = c * rps;
+            const int rows_in = static_cast<int>(min(static_cast<size_t>(rps), p.n_rows - row0));
+            mbar_wait(&full_bar[stage], phase);
+            const uint8_t* sbase = smem + stage * stage_bytes;
+            const float* snorm = reinterpret_cast<const float*>(sbase + stage_rows_bytes);
+            if (nq > 0) {
+                for (int r = wg; r < rows_in; r += wpg) {
+                    const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(sbase + r * row_bytes);
+                    ulonglong2 v[NCH];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) {
-            if (r0 + u >= p.n_rows) break;
-            float d[QT];
+                    for (int cc = 0; cc < NCH; ++cc) v[cc] = (lane + 32 * cc) * 4 < D ? rp[lane + 32 * cc] : make_ulonglong2(0ull, 0ull);
+                    const float rn = snorm[r];
+                    float acc[QT];
 #pragma unroll
-            for (int t = 0; t < QT; ++t) {
-                float a = 0.f;
+                    for (int t = 0; t < QT; ++t) {
+                        uint64_t a2 = 0ull;  // (0.f, 0.f)
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    a = fmaf(v[u][c].x, q[t][c].x, a);
-                    a = fmaf(v[u][c].y, q[t][c].y, a);
-                    a = fmaf(v[u][c].z, q[t][c].z, a);
-                    a = fmaf(v[u][c].w, q[t][c].w, a);
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            a2 = f2_fma(v[cc].x, q[t][cc][0], a2);
+                            a2 = f2_fma(v[cc].y, q[t][cc][1], a2);
+                        }
+                        float lo, hi;
+                        f2_unpack(a2, lo, hi);
+                        acc[t] = lo + hi;
+                    }
+#pragma unroll
+                    for (int step = 0; step < 5; ++step) {
+                        const int o = 16 >> step;
+                        if (step < LOGQ) {
+                            const bool upper = (lane & o) != 0;
+                            const int half = QT >> (step + 1);
+#pragma unroll
+                            for (int i = 0; i < half; ++i) {
+                                const float send = upper ? acc[i] : acc[i + half];
+                                const float keep = upper ? acc[i + half] : acc[i];
+                                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            }
+                        } else {
+                            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+                        }
+                    }
+                    float s;
+                    if (p.mode == SCAN_SEGMENT) s = rn < 1e-9f ? 0.0f : acc[0] / (qn_mine * rn);
+                    else s = acc[0] / fmaxf(qn_mine * rn, 1e-9f);
+                    uint32_t need = __ballot_sync(0xffffffffu, owner && s > thr_mine);
+                    while (need) {
+                        const int b = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int t = b >> GROUP_SHIFT;
+                        const float sb = __shfl_sync(0xffffffffu, s, b);
+                        int n = __shfl_sync(0xffffffffu, cnt_mine, b);
+                        float thr;
+                        warp_topk_insert(lsc + t * k, lid + t * k, k, n, thr, sb, static_cast<uint32_t>(row0 + r), lane);
+                        if (t_mine == t) { cnt_mine = n; thr_mine = thr; }
+                    }
                 }
-                d[t] = a;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                for (int t = 0; t < QT; ++t) d[t] += __shfl_xor_sync(0xffffffffu, d[t], o);
-            }
-#pragma unroll
-            for (int t = 0; t < QT; ++t) {
-                if (t >= nq) break;
-                float s;
-                if (p.mode == SCAN_SEGMENT) s = rn[u] < 1e-9f ? 0.0f : d[t] / (qn[t] * rn[u]);
-                else s = d[t] / fmaxf(qn[t] * rn[u], 1e-9f);
-                if (s > thr[t]) warp_topk_insert(lsc + t * k, lid + t * k, k, cnt[t], thr[t], s, static_cast<uint32_t>(r0 + u), lane);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
         }
-    }
-    // publish list sizes, then merge the 8 per-warp lists of each query into the CTA's output list
-    __shared__ int s_cnt[kScanWarps][QT];
-    if (lane == 0) {
-#pragma unroll
-        for (int t = 0; t < QT; ++t) s_cnt[warp][t] = cnt[t];
+        if ((lane & ((1 << GROUP_SHIFT) - 1)) == 0 && t_mine < QT) s_cnt[warp][t_mine] = cnt_mine;
     }
     __syncthreads();
-    float* all_sc = reinterpret_cast<float*>(smem_scan);
-    uint32_t* all_id = reinterpret_cast<uint32_t*>(smem_scan + static_cast<size_t>(kScanWarps) * QT * k * 4);
-    for (int t = warp; t < nq; t += kScanWarps) {
-        // lanes 0..7 each own the head of one warp's list; k rounds of an 8-way argmax
+    // merge the per-warp lists of each query (the wpg warps of its group) into the CTA's output list
+    for (int tq = warp; tq < nq_pass; tq += kScanConsumerWarps + 1) {
+        const int grp = tq / QT, t = tq % QT;
+        const int src_warp = grp * wpg + min(lane, wpg - 1);
+        // lanes 0..wpg-1 each own the head of one warp's list; k rounds of a wpg-way argmax
         int head = 0;
-        const int mycnt = lane < kScanWarps ? s_cnt[lane][t] : 0;
-        const float* msc = all_sc + (static_cast<size_t>(lane < kScanWarps ? lane : 0) * QT + t) * k;
-        const uint32_t* mid = all_id + (static_cast<size_t>(lane < kScanWarps ? lane : 0) * QT + t) * k;
-        float* os = p.out_scores + (static_cast<size_t>(blockIdx.x) * p.Q + p.q0 + t) * k;
-        uint32_t* oi = p.out_ids + (static_cast<size_t>(blockIdx.x) * p.Q + p.q0 + t) * k;
+        const int mycnt = lane < wpg ? s_cnt[src_warp][t] : 0;
+        const float* msc = all_sc + (static_cast<size_t>(src_warp) * QT + t) * k;
+        const uint32_t* mid = all_id + (static_cast<size_t>(src_warp) * QT + t) * k;
+        float* os = p.out_scores + (static_cast<size_t>(blockIdx.x) * p.Q + p.q0 + tq) * k;
+        uint32_t* oi = p.out_ids + (static_cast<size_t>(blockIdx.x) * p.Q + p.q0 + tq) * k;
         for (int j = 0; j < k; ++j) {
             float s = -INFINITY;
             uint32_t id = kNoId32;
@@ -180,7 +266,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(ScanParams p) {
             float bs = s;
             uint32_t bi = id;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
+            for (int o = 8; o > 0; o >>= 1) {
                 const float os2 = __shfl_xor_sync(0xffffffffu, bs, o);
                 const uint32_t oi2 = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (os2 > bs || (os2 == bs && oi2 < bi)) { bs = os2; bi = oi2; }

@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""Top stalled SASS instructions of one kernel in an .ncu-rep (source page). usage: ncu_hot.py rep kernel_regex [idx] [topn]"""
+import csv, io, subprocess, sys
+rep, rx = sys.argv[1], sys.argv[2]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+topn = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + rx], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(txt)))
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+s = starts[which]
+e = starts[which + 1] if which + 1 < len(starts) else len(rows)
+print(rows[s][1][:120])
+hdr = rows[s + 1]
+col = {h: i for i, h in enumerate(hdr)}
+body = rows[s + 2:e]
+stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+tot = sum(int(r[col["# Samples"]] or 0) for r in body)
+print("total samples", tot)
+agg = {h: sum(int(r[col[h]] or 0) for r in body) for h in stall_cols}
+print("stall totals:", {k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v > tot * 0.01})
+body_s = sorted(body, key=lambda r: -int(r[col["# Samples"]] or 0))[:topn]
+for r in body_s:
+    st = {h[6:]: int(r[col[h]] or 0) for h in stall_cols if int(r[col[h]] or 0) > 0}
+    top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
+    print(f'{r[col["# Samples"]]:>7} {r[col["Address"]][-5:]} {r[col["Source"]][:90]:90s} {top}')

@@ -30,12 +30,12 @@ def ref_gemm(a, w, bias, res, epi, act):
         y32 = y.astype(np.float32)
         y = {0: ko.gelu_erf, 1: ko.gelu_tanh, 2: lambda t: np.maximum(t, 0), 3: lambda t: t}[act](y32).astype(np.float64)
     if epi == 2:
-        y = y + res
+        y = y + bf16_round(res)  # the residual stream is bf16 on device
     return y.astype(np.float32)
 
 
 @pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (256, 384, 384), (300, 1152, 384), (1000, 384, 1536), (77, 96, 32),
-                                    (4096, 1536, 384), (2048, 768, 3072), (130, 2304, 768)])
+                                    (4096, 1536, 384), (2048, 768, 3072), (130, 2304, 768), (130, 112, 64)])
 @pytest.mark.parametrize("epi", [0, 1, 2, 3])
 def test_gemm_matches_fp32(M, Nn, K, epi):
     rng = np.random.default_rng(M * 7 + Nn + K + epi)
@@ -73,6 +73,30 @@ def test_gemm_activations(act):
     want = ref_gemm(a, w, bias, None, 1, act)
     tol = 3e-3 if act == 1 else 2.0 ** -8  # tanh.approx has ~5e-4 absolute error
     assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2 * tol
+
+
+@pytest.mark.parametrize("M,K", [(128, 384), (1000, 384), (300, 1536), (18944, 384), (77, 64)])
+def test_fused_gemm_residual_layernorm(M, K):
+    """out-proj / FFN-down + bias + residual + LayerNorm in one kernel (hidden 384) vs the oracle's LayerNorm on fp32 sums."""
+    import ctypes as C
+
+    rng = np.random.default_rng(M + K)
+    H = 384
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((H, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(H).astype(np.float32) * 0.1
+    gamma = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    res = rng.standard_normal((M, H)).astype(np.float32)
+    out = np.empty((M, H), np.uint16)
+    us = C.c_float()
+    N.check(N.lib().kjc_dbg_gemm_ln(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w)), ptr(bias), ptr(gamma), ptr(beta), 1e-12,
+                                    ptr(to_bf16_bits(res)), M, K, ptr(out), 0, C.byref(us)))
+    got = from_bf16_bits(out)
+    y = (bf16_round(a).astype(np.float64) @ bf16_round(w).astype(np.float64).T + bias + bf16_round(res)).astype(np.float32)
+    want = ko.layer_norm(y, gamma, beta, 1e-12)
+    assert np.isfinite(got).all()
+    assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2.0 ** -7
 
 
 def ref_attention(qkv, mask, B, S, H, heads, noalloc):
