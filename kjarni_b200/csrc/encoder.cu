@@ -12,6 +12,7 @@
 #include <mutex>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "encoder.hpp"
 #include "gemm_ln.cuh"
 #include "gemm_tcgen05.cuh"
@@ -51,6 +52,23 @@ CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_byte
                                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error(KJC_INFERENCE_FAILED, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+
+// 3-D row-major [d2, d1, d0] tensor (d0 contiguous), box = [1, box1, box0].
+CUtensorMap make_tmap_3d(const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0, uint32_t box1, int swizzle_bytes) {
+    CUtensorMap m;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * static_cast<uint64_t>(elem_bytes), d0 * d1 * static_cast<uint64_t>(elem_bytes)};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15))
+        throw Error(KJC_INVALID_CONFIG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(KJC_INFERENCE_FAILED, "cuTensorMapEncodeTiled(3d) failed with code " + std::to_string(static_cast<int>(r)));
     return m;
 }
 
@@ -145,7 +163,33 @@ static void launch_attention_d(const AttnParams& p, cudaStream_t st) {
     attention_kernel<D><<<p.B * p.heads, kAttnThreads, smem, st>>>(p);
 }
 
+// tcgen05 path: S <= 128, head_dim 32 / 64.  Tensor maps depend on (buffers, B, S, H): one-entry cache per thread.
+template <int D>
+static void launch_attention_tc(const AttnParams& p, cudaStream_t st) {
+    static int configured[64] = {0};
+    struct Key { const void *q, *c; int B, S, H; };
+    static thread_local Key key{nullptr, nullptr, 0, 0, 0};
+    static thread_local CUtensorMap t_qkv, t_ctx;
+    if (key.q != p.qkv || key.c != p.ctx || key.B != p.B || key.S != p.S || key.H != p.H) {
+        t_qkv = make_tmap_3d(p.qkv, 2, 3 * static_cast<uint64_t>(p.H), p.S, p.B, D, kAtcS, D * 2);
+        t_ctx = make_tmap_3d(p.ctx, 2, p.H, p.S, p.B, D, 32, D * 2);
+        key = Key{p.qkv, p.ctx, p.B, p.S, p.H};
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ensure_smem_attr(attention_tc_kernel<D>, AtcCfg<D>::kSmemBytes, configured);
+    attention_tc_kernel<D><<<std::min(p.B * p.heads, sms), AtcCfg<D>::kThreads, AtcCfg<D>::kSmemBytes, st>>>(t_qkv, t_ctx, p);
+}
+
 void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
+    static const bool legacy = getenv("KJC_ATTN_LEGACY") != nullptr;
+    if (!legacy && p.S <= kAtcS && (D == 32 || D == 64) && (p.H % 8 == 0)) {
+        if (D == 32) launch_attention_tc<32>(p, st);
+        else launch_attention_tc<64>(p, st);
+        KJ_CUDA(cudaGetLastError());
+        return;
+    }
     switch (D) {
         case 16: launch_attention_d<16>(p, st); break;
         case 32: launch_attention_d<32>(p, st); break;

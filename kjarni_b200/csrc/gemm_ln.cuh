@@ -36,10 +36,6 @@ struct GemmLnParams {
     float eps;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out, GemmLnParams p) {

@@ -110,7 +110,7 @@ def ref_attention(qkv, mask, B, S, H, heads, noalloc):
     return (p @ v).transpose(0, 2, 1, 3).reshape(B * S, H)
 
 
-@pytest.mark.parametrize("B,S,H,heads", [(3, 16, 64, 4), (2, 128, 384, 12), (3, 100, 128, 2), (2, 512, 128, 2), (2, 256, 64, 2), (5, 7, 32, 2)])
+@pytest.mark.parametrize("B,S,H,heads", [(3, 16, 64, 4), (2, 128, 384, 12), (3, 100, 128, 2), (2, 512, 128, 2), (2, 256, 64, 2), (5, 7, 32, 2), (2, 128, 128, 2), (4, 64, 768, 12), (3, 33, 64, 2), (150, 128, 384, 12)])
 def test_attention_matches_fp32(B, S, H, heads):
     rng = np.random.default_rng(S + H)
     qkv = rng.standard_normal((B * S, 3 * H)).astype(np.float32)
