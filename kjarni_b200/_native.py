@@ -75,6 +75,8 @@ SIGNATURES = {
     "kjc_index_search_device_async": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_topk_merge_device_async": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_index_last_launch_count": (C.c_int64, [_vp]),
+    "kjc_index_unverified_count": (C.c_int64, [_vp]),
+    "kjc_dbg_index_set_filter": (_i, [_vp, _f, _i]),
     "kjc_cosine_similarity": (_f, [_vp, _vp, C.c_size_t]),
     "kjc_dbg_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_gemm_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp]),

@@ -210,6 +210,15 @@ class IndexShard:
     def last_launch_count(self) -> int:
         return int(N.lib().kjc_index_last_launch_count(self._h))
 
+    @property
+    def unverified_count(self) -> int:
+        """Queries of async searches whose tensor-core filter result could not be proven exact (see kjarni_cuda.h)."""
+        return int(N.lib().kjc_index_unverified_count(self._h))
+
+    def set_filter(self, eps: float = 0.0045, min_queries: int = 9) -> None:
+        """Test hook (kjarni_cuda_debug.h): proof margin and smallest batch that takes the tensor-core filter path."""
+        N.check(N.lib().kjc_dbg_index_set_filter(self._h, float(eps), int(min_queries)))
+
 
 class VectorStore(IndexShard):
     """In-memory store semantics (KS/vector.rs): scores use max(|q||r|, 1e-9) as denominator."""

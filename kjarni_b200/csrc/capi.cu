@@ -188,6 +188,12 @@ int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const fl
     });
 }
 int64_t kjc_index_last_launch_count(const KjcIndex* idx) { return idx ? idx->impl.last_launches() : 0; }
+int64_t kjc_index_unverified_count(KjcIndex* idx) {
+    if (!idx) return 0;
+    int64_t v = -1;
+    guarded([&] { v = idx->impl.unverified_count(); });
+    return v;
+}
 
 float kjc_cosine_similarity(const float* a, const float* b, size_t len) {
     // kjarni_cosine_similarity (KF/src/lib.rs:177-188) -> VectorStore::cosine_similarity (KS/vector.rs:131-148)
@@ -223,6 +229,11 @@ int kjc_dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S,
     KJC_REQUIRE(qkv_bf16);
     KJC_REQUIRE(ctx_bf16);
     return guarded([&] { kj::dbg_attention(qkv_bf16, mask, B, S, H, heads, nan_if_all_masked, ctx_bf16); });
+}
+
+int kjc_dbg_index_set_filter(KjcIndex* idx, float eps, int min_queries) {
+    KJC_REQUIRE(idx);
+    return guarded([&] { idx->impl.set_filter(eps, min_queries); });
 }
 
 int kjc_dbg_encoder_head(KjcEncoder* enc, const float* hidden, int batch, int seq_len, float* logits) {

@@ -8,6 +8,7 @@
 
 #include "index.hpp"
 #include "scan.cuh"
+#include "scan_gemm.cuh"
 
 namespace kj {
 
@@ -24,12 +25,32 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
     KJ_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     KJ_CUDA(cudaMalloc(&rows_, capacity * dim * sizeof(float)));
     KJ_CUDA(cudaMalloc(&norms_, capacity * sizeof(float) + 64));  // slack: tail bulk copies round up to 16 B
+    // tensor-core filter path: bf16 shadow + 1/|r| (dims the resident 128-query tile supports)
+    gemm_ok_ = dim % kSgBK == 0 && dim <= kSgMaxD && !getenv("KJC_SCAN_NO_GEMM");
+    if (const char* e = getenv("KJC_SCAN_EPS")) filter_eps_ = static_cast<float>(atof(e));
+    if (const char* e = getenv("KJC_SCAN_GEMM_MIN_Q")) filter_min_q_ = std::max(1, atoi(e));
+    if (gemm_ok_) {
+        const uint64_t cap16 = std::max<uint64_t>(capacity, kSgRows);  // at least one TMA box of rows
+        KJ_CUDA(cudaMalloc(&rows16_, cap16 * dim * sizeof(__nv_bfloat16)));
+        KJ_CUDA(cudaMemsetAsync(rows16_, 0, cap16 * dim * sizeof(__nv_bfloat16), stream_));
+        KJ_CUDA(cudaMalloc(&inv_norms_, capacity * sizeof(float) + 64));
+        KJ_CUDA(cudaMalloc(&d_nflag_, 2 * sizeof(int32_t)));  // [0] flagged in the current search, [1] unverified (async) total
+        KJ_CUDA(cudaMemsetAsync(d_nflag_, 0, 2 * sizeof(int32_t), stream_));
+        KJ_CUDA(cudaMalloc(&d_fix_q_, 8 * dim * sizeof(float)));
+        KJ_CUDA(cudaMalloc(&d_fix_s_, 8 * 256 * sizeof(float)));
+        KJ_CUDA(cudaMalloc(&d_fix_i_, 8 * 256 * sizeof(uint64_t)));
+        KJ_CUDA(cudaMalloc(&d_fix_c_, 8 * sizeof(int32_t)));
+        KJ_CUDA(cudaStreamSynchronize(stream_));
+        t_rows16_ = make_tmap_2d(rows16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cap16, dim, kSgRows, kSgBK, 128);
+    }
 }
 
 Index::~Index() {
     cudaSetDevice(device_);
     for (void* p : {(void*)rows_, (void*)norms_, (void*)d_q_, (void*)d_qn_, (void*)d_cand_s_, (void*)d_cand_i_, (void*)d_out_s_,
-                    (void*)d_out_i_, (void*)d_out_c_})
+                    (void*)d_out_i_, (void*)d_out_c_, (void*)rows16_, (void*)d_q16_, (void*)inv_norms_, (void*)d_gc_s_, (void*)d_gc_i_,
+                    (void*)d_am_s_, (void*)d_am_i_, (void*)d_fix_q_, (void*)d_fix_s_, (void*)d_fix_i_, (void*)d_fix_c_, (void*)d_flags_,
+                    (void*)d_nflag_})
         if (p) cudaFree(p);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -37,7 +58,11 @@ Index::~Index() {
 
 void Index::compute_norms(uint64_t row0, uint64_t n, cudaStream_t st) {
     if (n == 0) return;
-    row_norm_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, n, dim_);
+    if (gemm_ok_)
+        row_prep_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, inv_norms_ + row0,
+                                                                          rows16_ + row0 * dim_, n, dim_);
+    else
+        row_norm_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, n, dim_);
     KJ_CUDA(cudaGetLastError());
 }
 
@@ -142,8 +167,8 @@ static void launch_topk_merge(const MergeParams& m, cudaStream_t st) {
     KJ_CUDA(cudaGetLastError());
 }
 
-// Enqueue: query norms -> scan passes of <= 8 queries -> merge of the per-CTA lists.
-void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st) {
+void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st,
+                          bool may_sync) {
     if (nq < 1) throw Error(KJC_INVALID_CONFIG, "nq must be >= 1");
     if (k < 1 || k > 256) throw Error(KJC_INVALID_CONFIG, "k must be in [1, 256]");
     if (mode != SCAN_SEGMENT && mode != SCAN_VECTORSTORE) throw Error(KJC_INVALID_CONFIG, "unknown scan mode");
@@ -151,6 +176,130 @@ void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d
     KJ_CUDA(cudaSetDevice(device_));
     if (!st) st = stream_;
     launches_ = 0;
+    // many queries: tensor-core filter + exact rescoring; few queries: the exact HBM-bound scan
+    if (gemm_ok_ && nq >= filter_min_q_ && 2 * k <= kSgC && len_ > 0) search_gemm(d_q, nq, k, mode, d_ids, d_scores, d_counts, st, may_sync);
+    else search_exact(d_q, nq, k, mode, d_ids, d_scores, d_counts, st);
+}
+
+int64_t Index::unverified_count() {
+    std::lock_guard<std::mutex> lock(mu_);
+    if (!d_nflag_) return 0;
+    KJ_CUDA(cudaSetDevice(device_));
+    int32_t v[2] = {0, 0};
+    KJ_CUDA(cudaDeviceSynchronize());
+    KJ_CUDA(cudaMemcpy(v, d_nflag_, sizeof(v), cudaMemcpyDeviceToHost));
+    return v[1];
+}
+
+void Index::set_filter(float eps, int min_queries) {
+    std::lock_guard<std::mutex> lock(mu_);
+    filter_eps_ = eps;
+    filter_min_q_ = std::max(1, min_queries);
+}
+
+static __global__ void add_counter_kernel(const int32_t* src, int32_t* dst) { atomicAdd(dst, *src); }
+
+// Tensor-core path (scan_gemm.cuh): query prep -> one filter launch per 128-query tile -> merge of the per-CTA candidate
+// lists -> exact rescoring + proof check -> (sync callers) exact re-run of the queries that could not be proven.
+void Index::search_gemm(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st,
+                        bool may_sync) {
+    static int configured[64] = {0};
+    ensure_smem_attr(scan_gemm_kernel, kSgSmemBytes, configured);
+    const uint32_t n_tiles = static_cast<uint32_t>((len_ + kSgRows - 1) / kSgRows);
+    const int grid = static_cast<int>(std::min<uint32_t>(num_sms_, n_tiles));
+    const size_t q16 = static_cast<size_t>(std::max(nq, kSgQ)) * dim_;
+    if (q16 > q16_cap_) {
+        if (d_q16_) cudaFree(d_q16_);
+        KJ_CUDA(cudaMalloc(&d_q16_, q16 * sizeof(__nv_bfloat16)));
+        KJ_CUDA(cudaMemsetAsync(d_q16_, 0, q16 * sizeof(__nv_bfloat16), st));
+        q16_cap_ = q16;
+    }
+    if (static_cast<size_t>(nq) > qn_cap_) {
+        if (d_qn_) cudaFree(d_qn_);
+        KJ_CUDA(cudaMalloc(&d_qn_, static_cast<size_t>(std::max(nq, 8)) * 4));
+        qn_cap_ = std::max(nq, 8);
+    }
+    const size_t gc = static_cast<size_t>(grid) * nq * kSgC;
+    if (gc > gc_cap_) {
+        if (d_gc_s_) cudaFree(d_gc_s_);
+        if (d_gc_i_) cudaFree(d_gc_i_);
+        KJ_CUDA(cudaMalloc(&d_gc_s_, gc * 4));
+        KJ_CUDA(cudaMalloc(&d_gc_i_, gc * 4));
+        gc_cap_ = gc;
+    }
+    const size_t am = static_cast<size_t>(nq) * kSgC;
+    if (am > am_cap_) {
+        if (d_am_s_) cudaFree(d_am_s_);
+        if (d_am_i_) cudaFree(d_am_i_);
+        KJ_CUDA(cudaMalloc(&d_am_s_, am * 4));
+        KJ_CUDA(cudaMalloc(&d_am_i_, am * 8));
+        am_cap_ = am;
+    }
+    if (static_cast<size_t>(nq) > flags_cap_) {
+        if (d_flags_) cudaFree(d_flags_);
+        KJ_CUDA(cudaMalloc(&d_flags_, static_cast<size_t>(nq) * 4));
+        flags_cap_ = nq;
+    }
+    // |q| and the bf16 copy of the queries
+    row_prep_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_q, d_qn_, nullptr, d_q16_, static_cast<size_t>(nq), dim_);
+    KJ_CUDA(cudaGetLastError());
+    KJ_CUDA(cudaMemsetAsync(d_nflag_, 0, sizeof(int32_t), st));
+    ++launches_;
+    const CUtensorMap t_q = make_tmap_2d(d_q16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, std::max(nq, kSgQ), dim_, kSgQ, kSgBK, 128);
+    ScanGemmParams sp;
+    sp.inv_norms = inv_norms_; sp.out_scores = d_gc_s_; sp.out_ids = d_gc_i_;
+    sp.n_rows = static_cast<uint32_t>(len_); sp.D = dim_; sp.Q = nq;
+    for (int q0 = 0; q0 < nq; q0 += kSgQ) {
+        sp.q0 = q0;
+        scan_gemm_kernel<<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, sp);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+    }
+    MergeParams m;
+    m.in_scores = d_gc_s_; m.in_ids32 = d_gc_i_; m.in_ids64 = nullptr; m.id_base = id_base_; m.qnorms = nullptr;
+    m.out_scores = d_am_s_; m.out_ids = d_am_i_; m.out_counts = nullptr; m.L = grid; m.Q = nq; m.k = kSgC; m.mode = SCAN_VECTORSTORE;
+    topk_merge_kernel<<<m.Q, 256, static_cast<size_t>(m.L) * sizeof(int), st>>>(m);
+    KJ_CUDA(cudaGetLastError());
+    ++launches_;
+    RescoreParams r;
+    r.rows = rows_; r.norms = norms_; r.queries = d_q; r.qnorms = d_qn_; r.cand_ids = d_am_i_; r.cand_scores = d_am_s_; r.id_base = id_base_;
+    r.out_ids = d_ids; r.out_scores = d_scores; r.out_counts = d_counts; r.flags = d_flags_; r.n_flagged = d_nflag_;
+    r.eps = filter_eps_; r.D = dim_; r.Q = nq; r.k = k; r.mode = mode;
+    scan_rescore_kernel<<<(nq + 7) / 8, 256, 0, st>>>(r);
+    KJ_CUDA(cudaGetLastError());
+    ++launches_;
+    if (!may_sync) {
+        add_counter_kernel<<<1, 1, 0, st>>>(d_nflag_, d_nflag_ + 1);
+        KJ_CUDA(cudaGetLastError());
+        return;
+    }
+    int32_t nflag = 0;
+    KJ_CUDA(cudaMemcpyAsync(&nflag, d_nflag_, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    KJ_CUDA(cudaStreamSynchronize(st));
+    if (nflag == 0) return;
+    h_flags_.resize(nq);
+    KJ_CUDA(cudaMemcpyAsync(h_flags_.data(), d_flags_, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
+    KJ_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> todo;
+    for (int i = 0; i < nq; ++i)
+        if (h_flags_[i]) todo.push_back(i);
+    for (size_t b = 0; b < todo.size(); b += 8) {
+        const int nb = static_cast<int>(std::min<size_t>(8, todo.size() - b));
+        for (int j = 0; j < nb; ++j)
+            KJ_CUDA(cudaMemcpyAsync(d_fix_q_ + static_cast<size_t>(j) * dim_, d_q + static_cast<size_t>(todo[b + j]) * dim_, dim_ * 4,
+                                    cudaMemcpyDeviceToDevice, st));
+        search_exact(d_fix_q_, nb, k, mode, d_fix_i_, d_fix_s_, d_fix_c_, st);
+        for (int j = 0; j < nb; ++j) {
+            const size_t o = static_cast<size_t>(todo[b + j]) * k;
+            KJ_CUDA(cudaMemcpyAsync(d_ids + o, d_fix_i_ + static_cast<size_t>(j) * k, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, st));
+            KJ_CUDA(cudaMemcpyAsync(d_scores + o, d_fix_s_ + static_cast<size_t>(j) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, st));
+            if (d_counts) KJ_CUDA(cudaMemcpyAsync(d_counts + todo[b + j], d_fix_c_ + j, 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+}
+
+// Exact path.  Enqueue: query norms -> scan passes of <= 8 queries -> merge of the per-CTA lists.
+void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st) {
     // queries per warp: bounded by the per-warp list memory (k) and the register file (dim)
     int qt_max = k > 64 ? 1 : (k > 32 ? 2 : 4);
     if (dim_ > 512) qt_max = std::min(qt_max, 2);
@@ -220,7 +369,7 @@ void Index::search_host(const float* q, int nq, int k, int mode, uint64_t* ids, 
         }
     }
     KJ_CUDA(cudaMemcpyAsync(d_q_, q, qe * 4, cudaMemcpyHostToDevice, stream_));
-    search_device(d_q_, nq, k, mode, d_out_i_, d_out_s_, d_out_c_, stream_);
+    search_device(d_q_, nq, k, mode, d_out_i_, d_out_s_, d_out_c_, stream_, /*may_sync=*/true);
     KJ_CUDA(cudaMemcpyAsync(ids, d_out_i_, oe * 8, cudaMemcpyDeviceToHost, stream_));
     KJ_CUDA(cudaMemcpyAsync(scores, d_out_s_, oe * 4, cudaMemcpyDeviceToHost, stream_));
     if (counts) KJ_CUDA(cudaMemcpyAsync(counts, d_out_c_, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, stream_));

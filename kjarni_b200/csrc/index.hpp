@@ -2,6 +2,7 @@
 #pragma once
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "encoder.hpp"
 
@@ -27,10 +28,18 @@ class Index {
     void append_synthetic(uint32_t seed, uint64_t row0, uint64_t n);
     void get_rows(uint64_t row, uint64_t n, float* out) const;
     void search_host(const float* q, int nq, int k, int mode, uint64_t* ids, float* scores, int32_t* counts);
-    void search_device(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st);
+    // may_sync: the caller allows a stream synchronise (host-buffer API) so that queries the tensor-core filter could not
+    // prove exact are re-run on the exact scan; without it they are counted in unverified_count().
+    void search_device(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st,
+                       bool may_sync = false);
+    int64_t unverified_count();
+    void set_filter(float eps, int min_queries);  // test hook: proof margin and the batch size from which the GEMM filter is used
 
   private:
     void compute_norms(uint64_t row0, uint64_t n, cudaStream_t st);
+    void search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st);
+    void search_gemm(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st,
+                     bool may_sync);
     int dim_;
     uint64_t cap_, id_base_, len_ = 0;
     int device_, num_sms_ = 0;
@@ -44,6 +53,18 @@ class Index {
     float* h_stage_ = nullptr;
     size_t q_cap_ = 0, qn_cap_ = 0, cand_cap_ = 0, out_cap_ = 0, outc_cap_ = 0;
     int64_t launches_ = 0;
+    // tensor-core filter path (scan_gemm.cuh): bf16 shadow of the rows, 1/|r|, staging for query tiles and candidates
+    bool gemm_ok_ = false;
+    float filter_eps_ = 0.0045f;
+    int filter_min_q_ = 9;
+    __nv_bfloat16 *rows16_ = nullptr, *d_q16_ = nullptr;
+    float *inv_norms_ = nullptr, *d_gc_s_ = nullptr, *d_am_s_ = nullptr, *d_fix_q_ = nullptr, *d_fix_s_ = nullptr;
+    uint32_t* d_gc_i_ = nullptr;
+    uint64_t *d_am_i_ = nullptr, *d_fix_i_ = nullptr;
+    int32_t *d_flags_ = nullptr, *d_nflag_ = nullptr, *d_fix_c_ = nullptr;
+    size_t q16_cap_ = 0, gc_cap_ = 0, am_cap_ = 0, flags_cap_ = 0;
+    CUtensorMap t_rows16_;
+    std::vector<int32_t> h_flags_;
 };
 
 }  // namespace kj
