@@ -50,7 +50,7 @@ Index::~Index() {
     for (void* p : {(void*)rows_, (void*)norms_, (void*)d_q_, (void*)d_qn_, (void*)d_cand_s_, (void*)d_cand_i_, (void*)d_out_s_,
                     (void*)d_out_i_, (void*)d_out_c_, (void*)rows16_, (void*)d_q16_, (void*)inv_norms_, (void*)d_gc_s_, (void*)d_gc_i_,
                     (void*)d_am_s_, (void*)d_am_i_, (void*)d_fix_q_, (void*)d_fix_s_, (void*)d_fix_i_, (void*)d_fix_c_, (void*)d_flags_,
-                    (void*)d_nflag_})
+                    (void*)d_nflag_, (void*)d_seed_})
         if (p) cudaFree(p);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -249,6 +249,33 @@ void Index::search_gemm(const float* d_q, int nq, int k, int mode, uint64_t* d_i
     ScanGemmParams sp;
     sp.inv_norms = inv_norms_; sp.out_scores = d_gc_s_; sp.out_ids = d_gc_i_;
     sp.n_rows = static_cast<uint32_t>(len_); sp.D = dim_; sp.Q = nq;
+    sp.thr0 = nullptr; sp.seed_max = nullptr;
+    // seed pass: per-query bound from one tile per CTA
+    const bool seeded = grid >= kSgC && grid <= 256 && !getenv("KJC_SG_NO_SEED");
+    const size_t seed_elems = static_cast<size_t>(grid + 1) * nq;
+    if (seed_elems > seed_cap_) {
+        if (d_seed_) cudaFree(d_seed_);
+        KJ_CUDA(cudaMalloc(&d_seed_, seed_elems * 4));
+        seed_cap_ = seed_elems;
+    }
+    float* d_seed = d_seed_;                                    // [grid, nq]
+    float* d_thr0 = d_seed_ + static_cast<size_t>(grid) * nq;   // [nq]
+    { static const int dbg = getenv("KJC_SG_DBG") ? atoi(getenv("KJC_SG_DBG")) : 0; sp.dbg = dbg; }
+    if (seeded) {
+        ScanGemmParams ss = sp;
+        ss.n_rows = static_cast<uint32_t>(std::min<uint64_t>(len_, static_cast<uint64_t>(grid) * kSgRows));
+        ss.seed_max = d_seed;
+        for (int q0 = 0; q0 < nq; q0 += kSgQ) {
+            ss.q0 = q0;
+            scan_gemm_kernel<<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, ss);
+            KJ_CUDA(cudaGetLastError());
+            ++launches_;
+        }
+        scan_seed_select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_seed, grid, nq, d_thr0);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+        sp.thr0 = d_thr0;
+    }
     for (int q0 = 0; q0 < nq; q0 += kSgQ) {
         sp.q0 = q0;
         scan_gemm_kernel<<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, sp);

@@ -62,7 +62,8 @@ class Index {
     uint32_t* d_gc_i_ = nullptr;
     uint64_t *d_am_i_ = nullptr, *d_fix_i_ = nullptr;
     int32_t *d_flags_ = nullptr, *d_nflag_ = nullptr, *d_fix_c_ = nullptr;
-    size_t q16_cap_ = 0, gc_cap_ = 0, am_cap_ = 0, flags_cap_ = 0;
+    float* d_seed_ = nullptr;
+    size_t q16_cap_ = 0, gc_cap_ = 0, am_cap_ = 0, flags_cap_ = 0, seed_cap_ = 0;
     CUtensorMap t_rows16_;
     std::vector<int32_t> h_flags_;
 };

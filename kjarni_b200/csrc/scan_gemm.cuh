@@ -50,6 +50,9 @@ struct ScanGemmParams {
     uint32_t* out_ids;       // [gridDim.x, Q, C]  local row index, kNoId32 = empty
     uint32_t n_rows;
     int D, Q, q0;            // q0: first query of this launch's 128-query tile
+    const float* thr0;       // [Q] or nullptr: per-query lower bound on the 32nd best approximate score (seed pass), exclusive
+    float* seed_max;         // non-null = SEED MODE: [gridDim.x, Q] best approximate score of the CTA's rows; no lists are kept
+    int dbg;                 // microbenchmark switches (env KJC_SG_DBG): 1 = no epilogue work, 2 = no MMA issue, 4 = no row loads
 };
 
 __global__ void __launch_bounds__(kSgThreads, 1)
@@ -117,8 +120,12 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 bulk_load_1d(s_inv + acc * kSgRows, p.inv_norms + row0, nb, &norm_full[acc]);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&full_bar[stage], kSgBBytes);
-                    tma_load_2d(smem_b + stage * kSgBBytes, &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0), kEvictFirst);
+                    if (p.dbg & 4) {
+                        mbar_arrive(&full_bar[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], kSgBBytes);
+                        tma_load_2d(smem_b + stage * kSgBBytes, &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0), kEvictFirst);
+                    }
                     if (++stage == kSgStages) {
                         stage = 0;
                         phase ^= 1;
@@ -144,8 +151,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     tc_fence_after();
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + kb * kSgABlockBytes));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * kSgBBytes));
+                    if (!(p.dbg & 2)) {
 #pragma unroll
-                    for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[stage]);
                     if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == kSgStages) {
@@ -161,7 +170,11 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int tq = quad * 32 + lane;  // query inside the tile = TMEM lane
         float* my_sc = l_sc + tq;         // entry j at my_sc[j * 128]
         uint32_t* my_id = l_id + tq;
-        float thr = -INFINITY;            // smallest kept score once the list is full
+        const int qi = p.q0 + tq;
+        const bool seed_mode = p.seed_max != nullptr;
+        // candidates must beat thr: the seed bound until the list is full, then the smallest kept score; padded lanes never insert
+        float thr = qi < p.Q ? (p.thr0 != nullptr ? p.thr0[qi] : -INFINITY) : INFINITY;
+        float best = -INFINITY;           // seed mode: running maximum
         int cnt = 0, minpos = 0;
         int it = 0;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -176,7 +189,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const float* inv = s_inv + acc * kSgRows;
 #pragma unroll 1
             for (int c = 0; c < kSgRows / 32; ++c) {
-                if (c * 32 >= rows_in) break;  // warp-uniform
+                if (c * 32 >= rows_in || (p.dbg & 1)) break;  // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32(taddr0 + c * 32, v);
                 float w[32];
@@ -197,7 +210,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 float m = s[0];
 #pragma unroll
                 for (int j = 1; j < 32; ++j) m = fmaxf(m, s[j]);
-                if (m > thr) {
+                best = fmaxf(best, m);
+                if (!seed_mode && m > thr) {
                     const uint32_t rid0 = row0 + c * 32;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -241,8 +255,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             my_sc[(j + 1) * kSgQ] = si;
             my_id[(j + 1) * kSgQ] = ii;
         }
-        const int qi = p.q0 + tq;
-        if (qi < p.Q) {
+        if (seed_mode) {
+            if (qi < p.Q) p.seed_max[static_cast<size_t>(blockIdx.x) * p.Q + qi] = best;
+        } else if (qi < p.Q) {
             float* os = p.out_scores + (static_cast<size_t>(blockIdx.x) * p.Q + qi) * kSgC;
             uint32_t* oi = p.out_ids + (static_cast<size_t>(blockIdx.x) * p.Q + qi) * kSgC;
             for (int j = 0; j < kSgC; ++j) {
@@ -285,6 +300,43 @@ row_prep_kernel(const float* __restrict__ rows, float* __restrict__ norms, float
         if (norms) norms[row] = nm;
         if (inv_norms) inv_norms[row] = nm < 1e-9f ? 0.0f : 1.0f / nm;
     }
+}
+
+// Seed bound for the filter: the 32nd largest of the per-CTA maxima of a sample of the shard (one 256-row tile per CTA).
+// The maxima belong to distinct rows, so at least 32 rows of the shard score >= that value: it is a valid lower bound on
+// the 32nd best approximate score, and lets every CTA skip list maintenance for all but ~0.1 % of its rows.
+// thr0[q] is exclusive (rows must score > thr0), hence the small margin below the selected value.
+__global__ void __launch_bounds__(256) scan_seed_select_kernel(const float* __restrict__ seed_max, int L, int Q, float* __restrict__ thr0) {
+    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (qi >= Q) return;
+    const int lane = threadIdx.x & 31;
+    if (L < kSgC) {
+        if (lane == 0) thr0[qi] = -INFINITY;
+        return;
+    }
+    constexpr int kPer = 8;  // up to 256 CTAs
+    float v[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) v[i] = lane + 32 * i < L ? seed_max[static_cast<size_t>(lane + 32 * i) * Q + qi] : -INFINITY;
+    float sel = -INFINITY;
+    for (int r = 0; r < kSgC; ++r) {
+        float m = v[0];
+        int mi = 0;
+#pragma unroll
+        for (int i = 1; i < kPer; ++i)
+            if (v[i] > m) { m = v[i]; mi = i; }
+        float wm = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        const uint32_t who = __ballot_sync(0xffffffffu, m == wm);
+        if (lane == __ffs(who) - 1) {
+#pragma unroll
+            for (int i = 0; i < kPer; ++i)
+                if (i == mi) v[i] = -INFINITY;
+        }
+        sel = wm;
+    }
+    if (lane == 0) thr0[qi] = sel == -INFINITY ? -INFINITY : sel - fabsf(sel) * 1e-5f - 1e-12f;
 }
 
 struct RescoreParams {
