@@ -33,7 +33,6 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
         const uint64_t cap16 = std::max<uint64_t>(capacity, kSgRows);  // at least one TMA box of rows
         KJ_CUDA(cudaMalloc(&rows16_, cap16 * dim * sizeof(__nv_bfloat16)));
         KJ_CUDA(cudaMemsetAsync(rows16_, 0, cap16 * dim * sizeof(__nv_bfloat16), stream_));
-        KJ_CUDA(cudaMalloc(&inv_norms_, capacity * sizeof(float) + 64));
         KJ_CUDA(cudaMalloc(&d_nflag_, 2 * sizeof(int32_t)));  // [0] flagged in the current search, [1] unverified (async) total
         KJ_CUDA(cudaMemsetAsync(d_nflag_, 0, 2 * sizeof(int32_t), stream_));
         KJ_CUDA(cudaMalloc(&d_fix_q_, 8 * dim * sizeof(float)));
@@ -48,7 +47,7 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
 Index::~Index() {
     cudaSetDevice(device_);
     for (void* p : {(void*)rows_, (void*)norms_, (void*)d_q_, (void*)d_qn_, (void*)d_cand_s_, (void*)d_cand_i_, (void*)d_out_s_,
-                    (void*)d_out_i_, (void*)d_out_c_, (void*)rows16_, (void*)d_q16_, (void*)inv_norms_, (void*)d_gc_s_, (void*)d_gc_i_,
+                    (void*)d_out_i_, (void*)d_out_c_, (void*)rows16_, (void*)d_q16_, (void*)d_gc_s_, (void*)d_gc_i_,
                     (void*)d_am_s_, (void*)d_am_i_, (void*)d_fix_q_, (void*)d_fix_s_, (void*)d_fix_i_, (void*)d_fix_c_, (void*)d_flags_,
                     (void*)d_nflag_, (void*)d_seed_})
         if (p) cudaFree(p);
@@ -58,9 +57,8 @@ Index::~Index() {
 
 void Index::compute_norms(uint64_t row0, uint64_t n, cudaStream_t st) {
     if (n == 0) return;
-    if (gemm_ok_)
-        row_prep_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, inv_norms_ + row0,
-                                                                          rows16_ + row0 * dim_, n, dim_);
+    if (gemm_ok_)  // dim <= 384: three float4 per lane
+        row_prep_kernel<3><<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, rows16_ + row0 * dim_, n, dim_, 1);
     else
         row_norm_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, n, dim_);
     KJ_CUDA(cudaGetLastError());
@@ -199,128 +197,148 @@ void Index::set_filter(float eps, int min_queries) {
 
 static __global__ void add_counter_kernel(const int32_t* src, int32_t* dst) { atomicAdd(dst, *src); }
 
-// Tensor-core path (scan_gemm.cuh): query prep -> one filter launch per 128-query tile -> merge of the per-CTA candidate
-// lists -> exact rescoring + proof check -> (sync callers) exact re-run of the queries that could not be proven.
-void Index::search_gemm(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st,
-                        bool may_sync) {
+// Tensor-core path (scan_gemm.cuh): query prep -> seed pass -> filter pass -> candidate select -> exact rescoring +
+// proof check -> (sync callers) exact re-run of the queries that could not be proven.
+void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint64_t* d_ids_all, float* d_scores_all, int32_t* d_counts_all,
+                        cudaStream_t st, bool may_sync) {
     static int configured[64] = {0};
+    static const int env_R = getenv("KJC_SG_R") ? std::max(1, atoi(getenv("KJC_SG_R"))) : 2;
+    static const int env_dbg = getenv("KJC_SG_DBG") ? atoi(getenv("KJC_SG_DBG")) : 0;
     ensure_smem_attr(scan_gemm_kernel, kSgSmemBytes, configured);
     const uint32_t n_tiles = static_cast<uint32_t>((len_ + kSgRows - 1) / kSgRows);
     const int grid = static_cast<int>(std::min<uint32_t>(num_sms_, n_tiles));
-    const size_t q16 = static_cast<size_t>(std::max(nq, kSgQ)) * dim_;
-    if (q16 > q16_cap_) {
-        if (d_q16_) cudaFree(d_q16_);
-        KJ_CUDA(cudaMalloc(&d_q16_, q16 * sizeof(__nv_bfloat16)));
-        KJ_CUDA(cudaMemsetAsync(d_q16_, 0, q16 * sizeof(__nv_bfloat16), st));
-        q16_cap_ = q16;
+    const int qb_max = std::min(nq_all, 4096);  // queries per pass over the shard (bounds the candidate buffers)
+    {
+        const size_t q16 = static_cast<size_t>(std::max(qb_max, kSgQ)) * dim_;
+        if (q16 > q16_cap_) {
+            if (d_q16_) cudaFree(d_q16_);
+            KJ_CUDA(cudaMalloc(&d_q16_, q16 * sizeof(__nv_bfloat16)));
+            q16_cap_ = q16;
+        }
+        if (static_cast<size_t>(qb_max) > qn_cap_) {
+            if (d_qn_) cudaFree(d_qn_);
+            KJ_CUDA(cudaMalloc(&d_qn_, static_cast<size_t>(std::max(qb_max, 8)) * 4));
+            qn_cap_ = std::max(qb_max, 8);
+        }
+        const size_t gc = static_cast<size_t>(qb_max) * kSgCap;
+        if (gc > gc_cap_) {
+            if (d_gc_s_) cudaFree(d_gc_s_);
+            if (d_gc_i_) cudaFree(d_gc_i_);
+            KJ_CUDA(cudaMalloc(&d_gc_s_, gc * 4));
+            KJ_CUDA(cudaMalloc(&d_gc_i_, gc * 4));
+            gc_cap_ = gc;
+        }
+        const size_t am = static_cast<size_t>(qb_max) * kSgC;
+        if (am > am_cap_) {
+            if (d_am_s_) cudaFree(d_am_s_);
+            if (d_am_i_) cudaFree(d_am_i_);
+            KJ_CUDA(cudaMalloc(&d_am_s_, am * 4));
+            KJ_CUDA(cudaMalloc(&d_am_i_, am * 8));
+            am_cap_ = am;
+        }
+        if (static_cast<size_t>(qb_max) > flags_cap_) {  // flags | overflow | candidate counters
+            if (d_flags_) cudaFree(d_flags_);
+            KJ_CUDA(cudaMalloc(&d_flags_, static_cast<size_t>(qb_max) * 3 * 4));
+            flags_cap_ = qb_max;
+        }
+        const size_t seed_elems = static_cast<size_t>(kSgSeedGroupsMax + 1) * qb_max;
+        if (seed_elems > seed_cap_) {
+            if (d_seed_) cudaFree(d_seed_);
+            KJ_CUDA(cudaMalloc(&d_seed_, seed_elems * 4));
+            seed_cap_ = seed_elems;
+        }
     }
-    if (static_cast<size_t>(nq) > qn_cap_) {
-        if (d_qn_) cudaFree(d_qn_);
-        KJ_CUDA(cudaMalloc(&d_qn_, static_cast<size_t>(std::max(nq, 8)) * 4));
-        qn_cap_ = std::max(nq, 8);
-    }
-    const size_t gc = static_cast<size_t>(grid) * nq * kSgC;
-    if (gc > gc_cap_) {
-        if (d_gc_s_) cudaFree(d_gc_s_);
-        if (d_gc_i_) cudaFree(d_gc_i_);
-        KJ_CUDA(cudaMalloc(&d_gc_s_, gc * 4));
-        KJ_CUDA(cudaMalloc(&d_gc_i_, gc * 4));
-        gc_cap_ = gc;
-    }
-    const size_t am = static_cast<size_t>(nq) * kSgC;
-    if (am > am_cap_) {
-        if (d_am_s_) cudaFree(d_am_s_);
-        if (d_am_i_) cudaFree(d_am_i_);
-        KJ_CUDA(cudaMalloc(&d_am_s_, am * 4));
-        KJ_CUDA(cudaMalloc(&d_am_i_, am * 8));
-        am_cap_ = am;
-    }
-    if (static_cast<size_t>(nq) > flags_cap_) {
-        if (d_flags_) cudaFree(d_flags_);
-        KJ_CUDA(cudaMalloc(&d_flags_, static_cast<size_t>(nq) * 4));
-        flags_cap_ = nq;
-    }
-    // |q| and the bf16 copy of the queries
-    row_prep_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_q, d_qn_, nullptr, d_q16_, static_cast<size_t>(nq), dim_);
-    KJ_CUDA(cudaGetLastError());
-    KJ_CUDA(cudaMemsetAsync(d_nflag_, 0, sizeof(int32_t), st));
-    ++launches_;
-    const CUtensorMap t_q = make_tmap_2d(d_q16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, std::max(nq, kSgQ), dim_, kSgQ, kSgBK, 128);
-    ScanGemmParams sp;
-    sp.inv_norms = inv_norms_; sp.out_scores = d_gc_s_; sp.out_ids = d_gc_i_;
-    sp.n_rows = static_cast<uint32_t>(len_); sp.D = dim_; sp.Q = nq;
-    sp.thr0 = nullptr; sp.seed_max = nullptr;
-    // seed pass: per-query bound from one tile per CTA
-    const bool seeded = grid >= kSgC && grid <= 256 && !getenv("KJC_SG_NO_SEED");
-    const size_t seed_elems = static_cast<size_t>(grid + 1) * nq;
-    if (seed_elems > seed_cap_) {
-        if (d_seed_) cudaFree(d_seed_);
-        KJ_CUDA(cudaMalloc(&d_seed_, seed_elems * 4));
-        seed_cap_ = seed_elems;
-    }
-    float* d_seed = d_seed_;                                    // [grid, nq]
-    float* d_thr0 = d_seed_ + static_cast<size_t>(grid) * nq;   // [nq]
-    { static const int dbg = getenv("KJC_SG_DBG") ? atoi(getenv("KJC_SG_DBG")) : 0; sp.dbg = dbg; }
-    if (seeded) {
-        ScanGemmParams ss = sp;
-        ss.n_rows = static_cast<uint32_t>(std::min<uint64_t>(len_, static_cast<uint64_t>(grid) * kSgRows));
-        ss.seed_max = d_seed;
-        for (int q0 = 0; q0 < nq; q0 += kSgQ) {
-            ss.q0 = q0;
-            scan_gemm_kernel<<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, ss);
+    for (int qoff = 0; qoff < nq_all; qoff += qb_max) {
+        const int nq = std::min(qb_max, nq_all - qoff);
+        const float* d_q = d_q_all + static_cast<size_t>(qoff) * dim_;
+        uint64_t* d_ids = d_ids_all + static_cast<size_t>(qoff) * k;
+        float* d_scores = d_scores_all + static_cast<size_t>(qoff) * k;
+        int32_t* d_counts = d_counts_all ? d_counts_all + qoff : nullptr;
+        int32_t* d_overflow = d_flags_ + flags_cap_;
+        uint32_t* d_cnt = reinterpret_cast<uint32_t*>(d_flags_ + 2 * flags_cap_);
+        float* d_seed = d_seed_;                                                 // [groups, nq]
+        float* d_thr0 = d_seed_ + static_cast<size_t>(kSgSeedGroupsMax) * nq;    // [nq]
+
+        // |q| and the bf16 copy of the queries (rows beyond nq of the last 128-query tile are zero-filled by TMA)
+        row_prep_kernel<3><<<(nq + 7) / 8, 256, 0, st>>>(d_q, d_qn_, d_q16_, static_cast<size_t>(nq), dim_, 0);
+        KJ_CUDA(cudaGetLastError());
+        if (nq < kSgQ)
+            KJ_CUDA(cudaMemsetAsync(d_q16_ + static_cast<size_t>(nq) * dim_, 0, static_cast<size_t>(kSgQ - nq) * dim_ * 2, st));
+        KJ_CUDA(cudaMemsetAsync(d_nflag_, 0, sizeof(int32_t), st));
+        KJ_CUDA(cudaMemsetAsync(d_cnt, 0, static_cast<size_t>(nq) * 4, st));
+        ++launches_;
+        const CUtensorMap t_q = make_tmap_2d(d_q16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, std::max(nq, kSgQ), dim_, kSgQ, kSgBK, 128);
+        ScanGemmParams sp;
+        sp.thr0 = nullptr; sp.cand_scores = d_gc_s_; sp.cand_ids = d_gc_i_; sp.cand_cnt = d_cnt;
+        sp.seed_max = nullptr; sp.n_rows = static_cast<uint32_t>(len_); sp.n_tiles = n_tiles; sp.n_tiles_total = n_tiles;
+        sp.seed_chunks = 0; sp.D = dim_; sp.Q = nq; sp.R = env_R; sp.dbg = env_dbg;
+        // ---- seed pass
+        int seed_groups = 0;
+        if (len_ > static_cast<uint64_t>(kSgCap) && !getenv("KJC_SG_NO_SEED")) {
+            ScanGemmParams ss = sp;
+            ss.seed_max = d_seed;
+            int sgrid;
+            if (n_tiles < static_cast<uint32_t>(kSgC)) {  // small shard: every tile, one group per 32-row chunk
+                ss.seed_chunks = 1; ss.n_tiles = n_tiles; ss.R = 1; sgrid = static_cast<int>(n_tiles);
+                seed_groups = static_cast<int>(n_tiles) * 8;
+            } else {  // evenly spaced sample tiles, 8 per CTA, one group per CTA
+                ss.R = 8; sgrid = std::min(grid, kSgSeedGroupsMax / 2);
+                ss.n_tiles = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sgrid) * 8);
+                seed_groups = 2 * sgrid;  // per CTA and column half
+            }
+            scan_gemm_kernel<<<sgrid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, ss);
             KJ_CUDA(cudaGetLastError());
             ++launches_;
         }
-        scan_seed_select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_seed, grid, nq, d_thr0);
+        scan_seed_select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_seed, seed_groups, nq, d_thr0);  // 0 groups: thr0 = -inf
         KJ_CUDA(cudaGetLastError());
         ++launches_;
+        // ---- filter pass
         sp.thr0 = d_thr0;
-    }
-    for (int q0 = 0; q0 < nq; q0 += kSgQ) {
-        sp.q0 = q0;
         scan_gemm_kernel<<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, sp);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
-    }
-    MergeParams m;
-    m.in_scores = d_gc_s_; m.in_ids32 = d_gc_i_; m.in_ids64 = nullptr; m.id_base = id_base_; m.qnorms = nullptr;
-    m.out_scores = d_am_s_; m.out_ids = d_am_i_; m.out_counts = nullptr; m.L = grid; m.Q = nq; m.k = kSgC; m.mode = SCAN_VECTORSTORE;
-    topk_merge_kernel<<<m.Q, 256, static_cast<size_t>(m.L) * sizeof(int), st>>>(m);
-    KJ_CUDA(cudaGetLastError());
-    ++launches_;
-    RescoreParams r;
-    r.rows = rows_; r.norms = norms_; r.queries = d_q; r.qnorms = d_qn_; r.cand_ids = d_am_i_; r.cand_scores = d_am_s_; r.id_base = id_base_;
-    r.out_ids = d_ids; r.out_scores = d_scores; r.out_counts = d_counts; r.flags = d_flags_; r.n_flagged = d_nflag_;
-    r.eps = filter_eps_; r.D = dim_; r.Q = nq; r.k = k; r.mode = mode;
-    scan_rescore_kernel<<<(nq + 7) / 8, 256, 0, st>>>(r);
-    KJ_CUDA(cudaGetLastError());
-    ++launches_;
-    if (!may_sync) {
-        add_counter_kernel<<<1, 1, 0, st>>>(d_nflag_, d_nflag_ + 1);
+        CandSelectParams cs;
+        cs.cand_scores = d_gc_s_; cs.cand_ids = d_gc_i_; cs.cand_cnt = d_cnt; cs.id_base = id_base_;
+        cs.out_scores = d_am_s_; cs.out_ids = d_am_i_; cs.overflow = d_overflow;
+        scan_cand_select_kernel<<<nq, 256, 0, st>>>(cs);
         KJ_CUDA(cudaGetLastError());
-        return;
-    }
-    int32_t nflag = 0;
-    KJ_CUDA(cudaMemcpyAsync(&nflag, d_nflag_, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    KJ_CUDA(cudaStreamSynchronize(st));
-    if (nflag == 0) return;
-    h_flags_.resize(nq);
-    KJ_CUDA(cudaMemcpyAsync(h_flags_.data(), d_flags_, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
-    KJ_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> todo;
-    for (int i = 0; i < nq; ++i)
-        if (h_flags_[i]) todo.push_back(i);
-    for (size_t b = 0; b < todo.size(); b += 8) {
-        const int nb = static_cast<int>(std::min<size_t>(8, todo.size() - b));
-        for (int j = 0; j < nb; ++j)
-            KJ_CUDA(cudaMemcpyAsync(d_fix_q_ + static_cast<size_t>(j) * dim_, d_q + static_cast<size_t>(todo[b + j]) * dim_, dim_ * 4,
-                                    cudaMemcpyDeviceToDevice, st));
-        search_exact(d_fix_q_, nb, k, mode, d_fix_i_, d_fix_s_, d_fix_c_, st);
-        for (int j = 0; j < nb; ++j) {
-            const size_t o = static_cast<size_t>(todo[b + j]) * k;
-            KJ_CUDA(cudaMemcpyAsync(d_ids + o, d_fix_i_ + static_cast<size_t>(j) * k, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, st));
-            KJ_CUDA(cudaMemcpyAsync(d_scores + o, d_fix_s_ + static_cast<size_t>(j) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, st));
-            if (d_counts) KJ_CUDA(cudaMemcpyAsync(d_counts + todo[b + j], d_fix_c_ + j, 4, cudaMemcpyDeviceToDevice, st));
+        ++launches_;
+        RescoreParams r;
+        r.rows = rows_; r.norms = norms_; r.queries = d_q; r.qnorms = d_qn_; r.cand_ids = d_am_i_; r.cand_scores = d_am_s_; r.id_base = id_base_;
+        r.out_ids = d_ids; r.out_scores = d_scores; r.out_counts = d_counts; r.overflow = d_overflow; r.thr0 = d_thr0;
+        r.flags = d_flags_; r.n_flagged = d_nflag_;
+        r.eps = filter_eps_; r.D = dim_; r.Q = nq; r.k = k; r.mode = mode;
+        scan_rescore_kernel<<<(nq + 7) / 8, 256, 0, st>>>(r);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+        if (!may_sync) {
+            add_counter_kernel<<<1, 1, 0, st>>>(d_nflag_, d_nflag_ + 1);
+            KJ_CUDA(cudaGetLastError());
+            continue;
+        }
+        int32_t nflag = 0;
+        KJ_CUDA(cudaMemcpyAsync(&nflag, d_nflag_, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        KJ_CUDA(cudaStreamSynchronize(st));
+        if (nflag == 0) continue;
+        h_flags_.resize(nq);
+        KJ_CUDA(cudaMemcpyAsync(h_flags_.data(), d_flags_, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
+        KJ_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> todo;
+        for (int i = 0; i < nq; ++i)
+            if (h_flags_[i]) todo.push_back(i);
+        for (size_t b = 0; b < todo.size(); b += 8) {
+            const int nb = static_cast<int>(std::min<size_t>(8, todo.size() - b));
+            for (int j = 0; j < nb; ++j)
+                KJ_CUDA(cudaMemcpyAsync(d_fix_q_ + static_cast<size_t>(j) * dim_, d_q + static_cast<size_t>(todo[b + j]) * dim_, dim_ * 4,
+                                        cudaMemcpyDeviceToDevice, st));
+            search_exact(d_fix_q_, nb, k, mode, d_fix_i_, d_fix_s_, d_fix_c_, st);
+            for (int j = 0; j < nb; ++j) {
+                const size_t o = static_cast<size_t>(todo[b + j]) * k;
+                KJ_CUDA(cudaMemcpyAsync(d_ids + o, d_fix_i_ + static_cast<size_t>(j) * k, static_cast<size_t>(k) * 8, cudaMemcpyDeviceToDevice, st));
+                KJ_CUDA(cudaMemcpyAsync(d_scores + o, d_fix_s_ + static_cast<size_t>(j) * k, static_cast<size_t>(k) * 4, cudaMemcpyDeviceToDevice, st));
+                if (d_counts) KJ_CUDA(cudaMemcpyAsync(d_counts + todo[b + j], d_fix_c_ + j, 4, cudaMemcpyDeviceToDevice, st));
+            }
         }
     }
 }

@@ -58,7 +58,7 @@ class Index {
     float filter_eps_ = 0.0045f;
     int filter_min_q_ = 9;
     __nv_bfloat16 *rows16_ = nullptr, *d_q16_ = nullptr;
-    float *inv_norms_ = nullptr, *d_gc_s_ = nullptr, *d_am_s_ = nullptr, *d_fix_q_ = nullptr, *d_fix_s_ = nullptr;
+    float *d_gc_s_ = nullptr, *d_am_s_ = nullptr, *d_fix_q_ = nullptr, *d_fix_s_ = nullptr;
     uint32_t* d_gc_i_ = nullptr;
     uint64_t *d_am_i_ = nullptr, *d_fix_i_ = nullptr;
     int32_t *d_flags_ = nullptr, *d_nflag_ = nullptr, *d_fix_c_ = nullptr;

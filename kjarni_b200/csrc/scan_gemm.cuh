@@ -5,23 +5,32 @@
 // (kjarni-rag/src/index_reader.rs:207-228).
 //
 // Exactness by construction (top-k ids must be bit-exact on the fp32 index):
-//   1. FILTER (this kernel)  scores S~[q,r] = <bf16(q), bf16(r)> / |r| on the tensor cores against a bf16
-//      shadow of the index (built once at append time); every CTA keeps, per query, the C = 32 best
-//      approximate scores of the rows it streamed.
-//   2. merge of the per-CTA lists to the 32 best approximate candidates per query (topk_merge_kernel),
-//   3. RESCORE (scan_rescore_kernel): exact fp32 cosine of those 32 rows with the same arithmetic as the
-//      exact scan kernel (scan.cuh), final order (score desc, id asc), and a proof check:
-//      every row outside the candidate list has approximate cosine <= m32 (the smallest kept one), hence
-//      exact cosine <= m32 + eps with eps >= 2^-8 (bf16 rounding of both operands, Cauchy-Schwarz);
-//      if exact_kth > m32 + eps the exact top-k is proven.  Otherwise the query is flagged and re-run on
-//      the exact scan kernel.
+//   0. SEED    the same kernel in seed mode scores a sample of the shard (evenly spaced 256-row tiles) and records
+//              group maxima; the 32nd largest maximum is a lower bound thr0[q] on the 32nd best approximate score
+//              of the whole shard (the maxima belong to 32 distinct rows).
+//   1. FILTER  scores S~[q,r] = <bf16(q), bf16(r/|r|)> on the tensor cores against a normalised bf16 shadow of the
+//              index (built once at append time); rows with S~ > thr0[q] (about 0.01 % of them) are appended to the
+//              query's candidate buffer in global memory.
+//   2. SELECT  scan_cand_select_kernel keeps the 32 best approximate candidates per query.
+//   3. RESCORE scan_rescore_kernel: exact fp32 cosine of those 32 rows with the same arithmetic as the exact scan
+//              kernel (scan.cuh), final order (score desc, id asc), and a proof check: every row outside the list
+//              has approximate cosine <= m32 (the smallest kept one), hence exact cosine <= m32 + eps with
+//              eps >= 2^-8 (bf16 rounding of both operands, Cauchy-Schwarz); if exact_kth > m32 + eps the exact
+//              top-k is proven.  Otherwise (or if the candidate buffer overflowed) the query is flagged and re-run
+//              on the exact scan kernel.
 //
-// Kernel shape: one CTA per SM, 256 threads.  The 128-query tile (bf16, K-major, 128 B swizzle) is loaded once
-// and stays resident in shared memory (96 KB at D = 384); index rows stream through a 3-stage TMA ring in
-// 256-row x 64-column boxes; one elected thread issues tcgen05.mma 128 x 256 x 16 into one of two TMEM
-// accumulators (2 x 256 columns) so the filter epilogue of tile i overlaps the MMAs of tile i+1.
-// Epilogue: 4 warps, thread = query (TMEM lane), tcgen05.ld 32 columns at a time, scale by 1/|r| from smem,
-// compare the chunk maximum against the thread's threshold; only then touch the candidate list.
+// Kernel shape: one CTA per SM, 256 threads, persistent over (row superblock, query tile, row tile):
+//   * the shard is cut into superblocks of gridDim.x * R row tiles (R * 196 KB per CTA, ~60-90 MB in total) that stay
+//     L2-resident while ALL query tiles are scored against them, so HBM is read once per search, not once per
+//     128 queries;
+//   * the current 128-query tile (bf16, K-major, 128 B swizzle, 6 k-blocks of 16 KB) lives in shared memory and is
+//     replaced k-block by k-block as soon as the last MMA that reads a k-block has retired (warp 3), so switching
+//     query tiles costs no pipeline drain;
+//   * row tiles stream through a 4-stage TMA ring of 256-row x 64-column boxes (warp 0);
+//   * one elected thread (warp 1) issues tcgen05.mma 128 x 256 x 16 into one of two TMEM accumulators (2 x 256
+//     columns), so the filter epilogue of tile i overlaps the MMAs of tile i+1;
+//   * epilogue (warps 4-11, two per TMEM lane quadrant, 128 columns each): thread = query (TMEM lane), tcgen05.ld
+//     64 columns at a time, tree maximum against the thread's threshold; passers are appended with one atomicAdd each.
 #pragma once
 #include <cuda.h>
 
@@ -30,30 +39,39 @@
 
 namespace kj {
 
-constexpr int kSgThreads = 256;
-constexpr int kSgQ = 128;     // queries per launch tile (TMEM lanes)
+constexpr int kSgThreads = 384;
+constexpr int kSgEpiWarps = 8;
+constexpr int kSgQ = 128;     // queries per tile (TMEM lanes)
 constexpr int kSgRows = 256;  // index rows per MMA tile (N)
 constexpr int kSgBK = 64;     // bf16 per k-block = one 128-byte swizzle atom
-constexpr int kSgStages = 3;
-constexpr int kSgC = 32;      // approximate candidates kept per query per CTA
+constexpr int kSgStages = 4;
+constexpr int kSgC = 32;      // approximate candidates kept per query for the exact rescoring
+constexpr int kSgCap = 2048;  // candidate buffer entries per query
 constexpr int kSgMaxD = 384;
+constexpr int kSgMaxKB = kSgMaxD / kSgBK;                        // 6
 constexpr int kSgABlockBytes = kSgQ * kSgBK * 2;                 // 16 KB per k-block of the resident query tile
-constexpr int kSgABytes = kSgABlockBytes * (kSgMaxD / kSgBK);    // 96 KB
+constexpr int kSgABytes = kSgABlockBytes * kSgMaxKB;             // 96 KB
 constexpr int kSgBBytes = kSgRows * kSgBK * 2;                   // 32 KB per stage
-constexpr int kSgListBytes = kSgQ * kSgC * 8;                    // 32 KB
-constexpr int kSgNormBytes = 2 * kSgRows * 4;                    // inverse row norms of the two tiles in flight
-constexpr int kSgSmemBytes = kSgABytes + kSgStages * kSgBBytes + kSgListBytes + kSgNormBytes + 256;  // 231,680 B
+constexpr int kSgSmemBytes = kSgABytes + kSgStages * kSgBBytes + 256;  // 229,632 B
+constexpr int kSgSeedGroupsMax = 320;                            // seed maxima per query (select kernel: 10 per lane)
 
 struct ScanGemmParams {
-    const float* inv_norms;  // [n_rows (+16 slack)]  1/|r|, 0 where |r| < 1e-9
-    float* out_scores;       // [gridDim.x, Q, C]  per-CTA candidates sorted (approx score desc, id asc); scores are <q,r>/|r|
-    uint32_t* out_ids;       // [gridDim.x, Q, C]  local row index, kNoId32 = empty
+    const float* thr0;       // [Q] or nullptr: exclusive lower bound a row's approximate score must beat
+    float* cand_scores;      // [Q, kSgCap]  approximate <q, r/|r|> of the passers (unordered)
+    uint32_t* cand_ids;      // [Q, kSgCap]  local row index
+    uint32_t* cand_cnt;      // [Q]          passers seen (may exceed kSgCap: overflow)
+    float* seed_max;         // non-null = SEED MODE: [groups, Q] group maxima, no candidates are written
     uint32_t n_rows;
-    int D, Q, q0;            // q0: first query of this launch's 128-query tile
-    const float* thr0;       // [Q] or nullptr: per-query lower bound on the 32nd best approximate score (seed pass), exclusive
-    float* seed_max;         // non-null = SEED MODE: [gridDim.x, Q] best approximate score of the CTA's rows; no lists are kept
+    uint32_t n_tiles;        // tiles this launch visits (seed mode: sample size); tile i covers shard tile tile_of(i)
+    uint32_t n_tiles_total;  // ceil(n_rows / 256)
+    int seed_chunks;         // seed mode: 1 = one group per 32-row chunk (group = tile*8 + chunk), 0 = one group per CTA
+    int D, Q, R;             // R: row tiles per CTA per superblock
     int dbg;                 // microbenchmark switches (env KJC_SG_DBG): 1 = no epilogue work, 2 = no MMA issue, 4 = no row loads
 };
+
+__device__ __forceinline__ uint32_t sg_tile_of(const ScanGemmParams& p, uint32_t i) {
+    return p.n_tiles == p.n_tiles_total ? i : static_cast<uint32_t>(static_cast<uint64_t>(i) * p.n_tiles_total / p.n_tiles);
+}
 
 __global__ void __launch_bounds__(kSgThreads, 1)
 scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rows, ScanGemmParams p) {
@@ -61,22 +79,22 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (smem_u32(smem_sg) & 1023) __trap();
     uint8_t* smem_a = smem_sg;
     uint8_t* smem_b = smem_a + kSgABytes;
-    float* l_sc = reinterpret_cast<float*>(smem_b + kSgStages * kSgBBytes);  // [C][128]
-    uint32_t* l_id = reinterpret_cast<uint32_t*>(l_sc + kSgQ * kSgC);       // [C][128]
-    float* s_inv = reinterpret_cast<float*>(l_id + kSgQ * kSgC);            // [2][256]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 2 * kSgRows);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSgStages * kSgBBytes);
     uint64_t* full_bar = bars;                       // [stages]
-    uint64_t* empty_bar = bars + kSgStages;          // [stages]
-    uint64_t* a_bar = bars + 2 * kSgStages;          // [1]
-    uint64_t* tmem_full = a_bar + 1;                 // [2]
+    uint64_t* empty_bar = full_bar + kSgStages;      // [stages]
+    uint64_t* a_full = empty_bar + kSgStages;        // [6]
+    uint64_t* a_empty = a_full + kSgMaxKB;           // [6]
+    uint64_t* tmem_full = a_empty + kSgMaxKB;        // [2]
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
-    uint64_t* norm_full = tmem_empty + 2;            // [2]
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(norm_full + 2);
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_blocks = p.D / kSgBK;
-    const uint32_t n_tiles = (p.n_rows + kSgRows - 1) / kSgRows;
+    const int n_qt = (p.Q + kSgQ - 1) / kSgQ;
+    const uint32_t tiles_per_sb = gridDim.x * static_cast<uint32_t>(p.R);
+    const uint32_t n_sb = (p.n_tiles + tiles_per_sb - 1) / tiles_per_sb;
+    // tiles of this CTA in superblock sb: i = sb*tiles_per_sb + r*gridDim.x + blockIdx.x, r < R, while i < n_tiles
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -87,11 +105,13 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(a_bar, 1);
+        for (int i = 0; i < kSgMaxKB; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
-            mbar_init(&norm_full[i], 1);
+            mbar_init(&tmem_empty[i], kSgEpiWarps);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -102,33 +122,46 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t tmem_base = *tmem_base_smem;
 
     if (warp == 0) {
-        // ------------------------------------------------------ TMA producer
+        // ------------------------------------------------ TMA producer: row tiles + their 1/|r|
         if (lane == 0) {
-            mbar_arrive_expect_tx(a_bar, k_blocks * kSgABlockBytes);
-            for (int kb = 0; kb < k_blocks; ++kb)
-                tma_load_2d(smem_a + kb * kSgABlockBytes, &tmap_q, a_bar, kb * kSgBK, p.q0, kEvictLast);
             int stage = 0, it = 0;
             uint32_t phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                // the 1/|r| buffer of this accumulator slot is free once the epilogue of tile it-2 has released the slot
-                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-                const uint32_t row0 = tile * kSgRows;
-                const uint32_t rows_in = min(static_cast<uint32_t>(kSgRows), p.n_rows - row0);
-                const uint32_t nb = (rows_in * 4 + 15) & ~15u;
-                mbar_arrive_expect_tx(&norm_full[acc], nb);
-                bulk_load_1d(s_inv + acc * kSgRows, p.inv_norms + row0, nb, &norm_full[acc]);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (p.dbg & 4) {
-                        mbar_arrive(&full_bar[stage]);
-                    } else {
-                        mbar_arrive_expect_tx(&full_bar[stage], kSgBBytes);
-                        tma_load_2d(smem_b + stage * kSgBBytes, &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0), kEvictFirst);
+            for (uint32_t sb = 0; sb < n_sb; ++sb) {
+                for (int qt = 0; qt < n_qt; ++qt) {
+                    for (int r = 0; r < p.R; ++r) {
+                        const uint32_t i = sb * tiles_per_sb + r * gridDim.x + blockIdx.x;
+                        if (i >= p.n_tiles) break;
+                        const uint32_t row0 = sg_tile_of(p, i) * kSgRows;
+                        for (int kb = 0; kb < k_blocks; ++kb) {
+                            mbar_wait(&empty_bar[stage], phase ^ 1);
+                            if (p.dbg & 4) {
+                                mbar_arrive(&full_bar[stage]);
+                            } else {
+                                mbar_arrive_expect_tx(&full_bar[stage], kSgBBytes);
+                                tma_load_2d(smem_b + stage * kSgBBytes, &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0),
+                                            kEvictNormal);
+                            }
+                            if (++stage == kSgStages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                        ++it;
                     }
-                    if (++stage == kSgStages) {
-                        stage = 0;
-                        phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------ TMA producer: query tiles, k-block by k-block
+        if (lane == 0) {
+            uint32_t ai = 0;
+            for (uint32_t sb = 0; sb < n_sb; ++sb) {
+                if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;  // no tile of this CTA in the last superblock
+                for (int qt = 0; qt < n_qt; ++qt, ++ai) {
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        mbar_wait(&a_empty[kb], (ai & 1) ^ 1);
+                        mbar_arrive_expect_tx(&a_full[kb], kSgABlockBytes);
+                        tma_load_2d(smem_a + kb * kSgABlockBytes, &tmap_q, &a_full[kb], kb * kSgBK, qt * kSgQ, kEvictLast);
                     }
                 }
             }
@@ -137,29 +170,38 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // -------------------------------------------------------- MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kSgQ, kSgRows);
-            mbar_wait(a_bar, 0);
-            tc_fence_after();
             int stage = 0, it = 0;
-            uint32_t phase = 0;
-            for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * kSgRows;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + kb * kSgABlockBytes));
-                    const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * kSgBBytes));
-                    if (!(p.dbg & 2)) {
+            uint32_t phase = 0, ai = 0;
+            for (uint32_t sb = 0; sb < n_sb; ++sb) {
+                if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;
+                for (int qt = 0; qt < n_qt; ++qt, ++ai) {
+                    for (int r = 0; r < p.R; ++r) {
+                        const uint32_t i = sb * tiles_per_sb + r * gridDim.x + blockIdx.x;
+                        if (i >= p.n_tiles) break;
+                        const bool last_r = (r + 1 == p.R) || (i + gridDim.x >= p.n_tiles);
+                        const int acc = it & 1;
+                        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t tmem_d = tmem_base + acc * kSgRows;
+                        for (int kb = 0; kb < k_blocks; ++kb) {
+                            if (r == 0) mbar_wait(&a_full[kb], ai & 1);
+                            mbar_wait(&full_bar[stage], phase);
+                            tc_fence_after();
+                            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + kb * kSgABlockBytes));
+                            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * kSgBBytes));
+                            if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == kSgStages) {
-                        stage = 0;
-                        phase ^= 1;
+                                for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            }
+                            umma_commit(&empty_bar[stage]);
+                            if (last_r) umma_commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
+                            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                            if (++stage == kSgStages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                        ++it;
                     }
                 }
             }
@@ -167,102 +209,88 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     } else if (warp >= 4) {
         // ------------------------------------------- filter epilogue: thread = query
         const int quad = warp & 3;
-        const int tq = quad * 32 + lane;  // query inside the tile = TMEM lane
-        float* my_sc = l_sc + tq;         // entry j at my_sc[j * 128]
-        uint32_t* my_id = l_id + tq;
-        const int qi = p.q0 + tq;
+        const int half = (warp - 4) >> 2;  // column half of the 256-row tile handled by this warp
+        const int tq = quad * 32 + lane;   // query inside the tile = TMEM lane
         const bool seed_mode = p.seed_max != nullptr;
-        // candidates must beat thr: the seed bound until the list is full, then the smallest kept score; padded lanes never insert
-        float thr = qi < p.Q ? (p.thr0 != nullptr ? p.thr0[qi] : -INFINITY) : INFINITY;
-        float best = -INFINITY;           // seed mode: running maximum
-        int cnt = 0, minpos = 0;
+        constexpr int kHalfCols = kSgRows / 2;  // 128
         int it = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t ph = (it >> 1) & 1;
-            const uint32_t row0 = tile * kSgRows;
-            const int rows_in = static_cast<int>(min(static_cast<uint32_t>(kSgRows), p.n_rows - row0));
-            mbar_wait(&norm_full[acc], ph);
-            mbar_wait(&tmem_full[acc], ph);
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kSgRows;
-            const float* inv = s_inv + acc * kSgRows;
+        for (uint32_t sb = 0; sb < n_sb; ++sb) {
+            if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;
+            for (int qt = 0; qt < n_qt; ++qt) {
+                const int qi = qt * kSgQ + tq;
+                const bool live = qi < p.Q;
+                // rows must beat thr; padded lanes never pass
+                const float thr = live ? (p.thr0 != nullptr ? p.thr0[qi] : -INFINITY) : INFINITY;
+                float best = -INFINITY;  // seed mode, one group per CTA: running maximum over this CTA's sample tiles
+                for (int r = 0; r < p.R; ++r) {
+                    const uint32_t i = sb * tiles_per_sb + r * gridDim.x + blockIdx.x;
+                    if (i >= p.n_tiles) break;
+                    const int acc = it & 1;
+                    const uint32_t ph = (it >> 1) & 1;
+                    const uint32_t row0 = sg_tile_of(p, i) * kSgRows;
+                    const int rows_in = static_cast<int>(min(static_cast<uint32_t>(kSgRows), p.n_rows - row0));
+                    mbar_wait(&tmem_full[acc], ph);
+                    tc_fence_after();
+                    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kSgRows + half * kHalfCols;
 #pragma unroll 1
-            for (int c = 0; c < kSgRows / 32; ++c) {
-                if (c * 32 >= rows_in || (p.dbg & 1)) break;  // warp-uniform
-                uint32_t v[32];
-                tmem_ld_32x32(taddr0 + c * 32, v);
-                float w[32];
+                    for (int c = 0; c < kHalfCols / 64; ++c) {
+                        const int col0 = half * kHalfCols + c * 64;  // first tile column of this 64-column chunk
+                        float m0 = -INFINITY, m1 = -INFINITY;       // maxima of its two 32-row groups
+                        if (col0 < rows_in && !(p.dbg & 1)) {       // warp-uniform
+                            uint32_t v0[32], v1[32];
+                            tmem_ld_32x32(taddr0 + c * 64, v0);
+                            tmem_ld_32x32(taddr0 + c * 64 + 32, v1);
+                            tmem_ld_wait();
+                            float s[64];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 f = *reinterpret_cast<const float4*>(inv + c * 32 + 4 * j);  // broadcast read
-                    w[4 * j] = f.x; w[4 * j + 1] = f.y; w[4 * j + 2] = f.z; w[4 * j + 3] = f.w;
-                }
-                tmem_ld_wait();
-                float s[32];
+                            for (int j = 0; j < 32; ++j) { s[j] = __uint_as_float(v0[j]); s[32 + j] = __uint_as_float(v1[j]); }
+                            if (col0 + 64 > rows_in) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]) * w[j];
-                if (c * 32 + 32 > rows_in) {
+                                for (int j = 0; j < 64; ++j)
+                                    if (col0 + j >= rows_in) s[j] = -INFINITY;
+                            }
+                            float t[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (c * 32 + j >= rows_in) s[j] = -INFINITY;
-                }
-                float m = s[0];
+                            for (int j = 0; j < 16; ++j) { t[j] = fmaxf(s[2 * j], s[2 * j + 1]); t[16 + j] = fmaxf(s[32 + 2 * j], s[33 + 2 * j]); }
 #pragma unroll
-                for (int j = 1; j < 32; ++j) m = fmaxf(m, s[j]);
-                best = fmaxf(best, m);
-                if (!seed_mode && m > thr) {
-                    const uint32_t rid0 = row0 + c * 32;
+                            for (int w = 8; w > 0; w >>= 1) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (s[j] > thr) {
-                            int pos = cnt;
-                            if (cnt == kSgC) pos = minpos; else ++cnt;
-                            my_sc[pos * kSgQ] = s[j];
-                            my_id[pos * kSgQ] = rid0 + j;
-                            if (cnt == kSgC) {  // list full: new threshold = smallest kept score
-                                float mn = INFINITY;
-                                int mp = 0;
-#pragma unroll 1
-                                for (int e = 0; e < kSgC; ++e) {
-                                    const float x = my_sc[e * kSgQ];
-                                    if (x < mn) { mn = x; mp = e; }
+                                for (int j = 0; j < w; ++j) { t[j] = fmaxf(t[j], t[j + w]); t[16 + j] = fmaxf(t[16 + j], t[16 + j + w]); }
+                            }
+                            m0 = t[0];
+                            m1 = t[16];
+                            if (!seed_mode && fmaxf(m0, m1) > thr) {
+                                const uint32_t rid0 = row0 + col0;
+#pragma unroll
+                                for (int j = 0; j < 64; ++j) {
+                                    if (s[j] > thr) {
+                                        const uint32_t pos = atomicAdd(p.cand_cnt + qi, 1u);
+                                        if (pos < static_cast<uint32_t>(kSgCap)) {
+                                            p.cand_scores[static_cast<size_t>(qi) * kSgCap + pos] = s[j];
+                                            p.cand_ids[static_cast<size_t>(qi) * kSgCap + pos] = rid0 + j;
+                                        }
+                                    }
                                 }
-                                thr = mn;
-                                minpos = mp;
+                            }
+                        }
+                        if (seed_mode) {
+                            if (p.seed_chunks) {
+                                if (live) {
+                                    p.seed_max[static_cast<size_t>(i * 8 + (col0 >> 5)) * p.Q + qi] = m0;
+                                    p.seed_max[static_cast<size_t>(i * 8 + (col0 >> 5) + 1) * p.Q + qi] = m1;
+                                }
+                            } else {
+                                best = fmaxf(best, fmaxf(m0, m1));
                             }
                         }
                     }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    ++it;
                 }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        // sort my list (approx score desc, id asc) and write it out
-        for (int i = 1; i < cnt; ++i) {
-            const float si = my_sc[i * kSgQ];
-            const uint32_t ii = my_id[i * kSgQ];
-            int j = i - 1;
-            while (j >= 0) {
-                const float sj = my_sc[j * kSgQ];
-                const uint32_t ij = my_id[j * kSgQ];
-                if (sj > si || (sj == si && ij < ii)) break;
-                my_sc[(j + 1) * kSgQ] = sj;
-                my_id[(j + 1) * kSgQ] = ij;
-                --j;
-            }
-            my_sc[(j + 1) * kSgQ] = si;
-            my_id[(j + 1) * kSgQ] = ii;
-        }
-        if (seed_mode) {
-            if (qi < p.Q) p.seed_max[static_cast<size_t>(blockIdx.x) * p.Q + qi] = best;
-        } else if (qi < p.Q) {
-            float* os = p.out_scores + (static_cast<size_t>(blockIdx.x) * p.Q + qi) * kSgC;
-            uint32_t* oi = p.out_ids + (static_cast<size_t>(blockIdx.x) * p.Q + qi) * kSgC;
-            for (int j = 0; j < kSgC; ++j) {
-                os[j] = j < cnt ? my_sc[j * kSgQ] : -INFINITY;
-                oi[j] = j < cnt ? my_id[j * kSgQ] : kNoId32;
+                // one group per CTA and column half (2 * gridDim.x groups)
+                if (seed_mode && !p.seed_chunks && live) p.seed_max[static_cast<size_t>(blockIdx.x * 2 + half) * p.Q + qi] = best;
             }
         }
     }
@@ -275,37 +303,101 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
-// |row|, 1/|row| and the bf16 shadow of rows [0, n): one warp per row (append-time preparation, also used for queries).
+// The 32 best approximate candidates of every query, sorted (score desc, id asc): one CTA per query, 32 rounds of a
+// block-wide arg-max over the query's candidate buffer staged in shared memory.
+struct CandSelectParams {
+    const float* cand_scores;  // [Q, kSgCap]
+    const uint32_t* cand_ids;  // [Q, kSgCap]
+    const uint32_t* cand_cnt;  // [Q]
+    uint64_t id_base;
+    float* out_scores;         // [Q, kSgC]  -inf = empty
+    uint64_t* out_ids;         // [Q, kSgC]  kNoId64 = empty
+    int32_t* overflow;         // [Q] 1 = the buffer overflowed (candidates were dropped)
+};
+__global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams p) {
+    __shared__ float sc[kSgCap];
+    __shared__ uint32_t id[kSgCap];
+    __shared__ float ws[8];
+    __shared__ uint32_t wi[8];
+    __shared__ int wp[8];
+    const int qi = blockIdx.x, tid = threadIdx.x;
+    const uint32_t cnt = p.cand_cnt[qi];
+    const int n = static_cast<int>(min(cnt, static_cast<uint32_t>(kSgCap)));
+    for (int j = tid; j < n; j += 256) {
+        sc[j] = p.cand_scores[static_cast<size_t>(qi) * kSgCap + j];
+        id[j] = p.cand_ids[static_cast<size_t>(qi) * kSgCap + j];
+    }
+    if (tid == 0) p.overflow[qi] = cnt > static_cast<uint32_t>(kSgCap) ? 1 : 0;
+    __syncthreads();
+    for (int round = 0; round < kSgC; ++round) {
+        float bs = -INFINITY;
+        uint32_t bi = kNoId32;
+        int bp = -1;
+        for (int j = tid; j < n; j += 256) {
+            const float s = sc[j];
+            const uint32_t ii = id[j];
+            if (ii != kNoId32 && (bp < 0 || s > bs || (s == bs && ii < bi))) { bs = s; bi = ii; bp = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (op >= 0 && (bp < 0 || os > bs || (os == bs && oi < bi))) { bs = os; bi = oi; bp = op; }
+        }
+        if ((tid & 31) == 0) { ws[tid >> 5] = bs; wi[tid >> 5] = bi; wp[tid >> 5] = bp; }
+        __syncthreads();
+        if (tid == 0) {
+            float fs = -INFINITY;
+            uint32_t fi = kNoId32;
+            int fp = -1;
+            for (int w = 0; w < 8; ++w)
+                if (wp[w] >= 0 && (fp < 0 || ws[w] > fs || (ws[w] == fs && wi[w] < fi))) { fs = ws[w]; fi = wi[w]; fp = wp[w]; }
+            p.out_scores[static_cast<size_t>(qi) * kSgC + round] = fp >= 0 ? fs : -INFINITY;
+            p.out_ids[static_cast<size_t>(qi) * kSgC + round] = fp >= 0 ? p.id_base + fi : kNoId64;
+            if (fp >= 0) id[fp] = kNoId32;  // taken
+        }
+        __syncthreads();
+    }
+}
+
+// |row| and the bf16 shadow of rows [0, n): one warp per row (append-time preparation, also used for queries).
+// normalise = 1: the shadow holds bf16(r / |r|) (zero rows stay zero), so the filter GEMM yields cosine * |q| directly.
+template <int NCH>
 __global__ void __launch_bounds__(256)
-row_prep_kernel(const float* __restrict__ rows, float* __restrict__ norms, float* __restrict__ inv_norms, __nv_bfloat16* __restrict__ rows16,
-                size_t n, int D) {
+row_prep_kernel(const float* __restrict__ rows, float* __restrict__ norms, __nv_bfloat16* __restrict__ rows16, size_t n, int D, int normalise) {
     const size_t row = static_cast<size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= n) return;
     const int lane = threadIdx.x & 31;
     const float* r = rows + row * D;
+    float4 v[NCH];
     float s = 0.f;
-    for (int c = lane * 4; c < D; c += 128) {
-        const float4 v = ld_stream_f4(r + c);
-        s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);  // same order as row_norm_kernel: identical cached norms
-        if (rows16) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        v[i] = c < D ? ld_stream_f4(r + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);  // same order as row_norm_kernel: identical norms
+    }
+    s = warp_sum(s);
+    const float nm = sqrtf(s);
+    if (lane == 0 && norms) norms[row] = nm;
+    const float sc = normalise ? (nm < 1e-9f ? 0.0f : 1.0f / nm) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < D) {
             uint2 o;
-            o.x = pack_bf16(v.x, v.y);
-            o.y = pack_bf16(v.z, v.w);
+            o.x = pack_bf16(v[i].x * sc, v[i].y * sc);
+            o.y = pack_bf16(v[i].z * sc, v[i].w * sc);
             *reinterpret_cast<uint2*>(rows16 + row * D + c) = o;
         }
     }
-    s = warp_sum(s);
-    if (lane == 0) {
-        const float nm = sqrtf(s);
-        if (norms) norms[row] = nm;
-        if (inv_norms) inv_norms[row] = nm < 1e-9f ? 0.0f : 1.0f / nm;
-    }
 }
 
-// Seed bound for the filter: the 32nd largest of the per-CTA maxima of a sample of the shard (one 256-row tile per CTA).
-// The maxima belong to distinct rows, so at least 32 rows of the shard score >= that value: it is a valid lower bound on
-// the 32nd best approximate score, and lets every CTA skip list maintenance for all but ~0.1 % of its rows.
-// thr0[q] is exclusive (rows must score > thr0), hence the small margin below the selected value.
+// Seed bound for the filter: the 32nd largest of L <= 320 group maxima of the sample (groups = the sample tiles of one
+// CTA, or 32-row chunks for small shards).  The maxima belong to distinct rows, so at least 32 rows of the shard score
+// >= that value: a valid lower bound on the 32nd best approximate score, which lets the filter drop ~99.99 % of the rows
+// with one compare.  thr0[q] is exclusive (rows must score > thr0), hence the small margin below the selected value.
 __global__ void __launch_bounds__(256) scan_seed_select_kernel(const float* __restrict__ seed_max, int L, int Q, float* __restrict__ thr0) {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (qi >= Q) return;
@@ -314,7 +406,7 @@ __global__ void __launch_bounds__(256) scan_seed_select_kernel(const float* __re
         if (lane == 0) thr0[qi] = -INFINITY;
         return;
     }
-    constexpr int kPer = 8;  // up to 256 CTAs
+    constexpr int kPer = kSgSeedGroupsMax / 32;
     float v[kPer];
 #pragma unroll
     for (int i = 0; i < kPer; ++i) v[i] = lane + 32 * i < L ? seed_max[static_cast<size_t>(lane + 32 * i) * Q + qi] : -INFINITY;
@@ -345,11 +437,13 @@ struct RescoreParams {
     const float* queries;      // [Q, D] fp32
     const float* qnorms;       // [Q]
     const uint64_t* cand_ids;  // [Q, C] merged approximate candidates (global ids; kNoId64 = empty), sorted by approx score desc
-    const float* cand_scores;  // [Q, C] approximate <q,r>/|r|
+    const float* cand_scores;  // [Q, C] approximate <q, r/|r|>
     uint64_t id_base;
     uint64_t* out_ids;         // [Q, k]
     float* out_scores;         // [Q, k]
     int32_t* out_counts;       // [Q] or nullptr
+    const int32_t* overflow;   // [Q] candidate buffer overflowed
+    const float* thr0;         // [Q] seed bound used by the filter (-inf: every row of the shard was a candidate)
     int32_t* flags;            // [Q] 1 = not proven exact, needs the exact scan
     int32_t* n_flagged;        // running count of flagged queries
     float eps;                 // bound on |approx cosine - exact cosine|
@@ -412,8 +506,10 @@ __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
     const float kth = __shfl_sync(0xffffffffu, my_s, kth_lane);
     const float m32 = __shfl_sync(0xffffffffu, my_approx, kSgC - 1);  // lists are sorted descending: last = smallest
     if (lane == 0 && !empty_query) {
-        bool proven = ncand < kSgC;
-        if (!proven && kth_mask != 0 && qn >= 1e-9f) proven = kth > m32 / qn + p.eps;
+        // fewer than 32 candidates proves the result only if nothing was filtered out (unseeded: every row is a candidate)
+        bool proven = ncand < kSgC && p.thr0[qi] == -INFINITY;
+        if (ncand == kSgC && kth_mask != 0 && qn >= 1e-9f) proven = kth > m32 / qn + p.eps;
+        if (p.overflow[qi]) proven = false;
         p.flags[qi] = proven ? 0 : 1;
         if (!proven) atomicAdd(p.n_flagged, 1);
     } else if (lane == 0) {
