@@ -202,7 +202,7 @@ static __global__ void add_counter_kernel(const int32_t* src, int32_t* dst) { at
 void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint64_t* d_ids_all, float* d_scores_all, int32_t* d_counts_all,
                         cudaStream_t st, bool may_sync) {
     static int configured[64] = {0};
-    static const int env_R = getenv("KJC_SG_R") ? std::max(1, atoi(getenv("KJC_SG_R"))) : 2;
+    static const int env_R = getenv("KJC_SG_R") ? std::max(1, atoi(getenv("KJC_SG_R"))) : 3;
     static const int env_dbg = getenv("KJC_SG_DBG") ? atoi(getenv("KJC_SG_DBG")) : 0;
     ensure_smem_attr(scan_gemm_kernel, kSgSmemBytes, configured);
     const uint32_t n_tiles = static_cast<uint32_t>((len_ + kSgRows - 1) / kSgRows);
@@ -282,7 +282,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
                 ss.seed_chunks = 1; ss.n_tiles = n_tiles; ss.R = 1; sgrid = static_cast<int>(n_tiles);
                 seed_groups = static_cast<int>(n_tiles) * 8;
             } else {  // evenly spaced sample tiles, 8 per CTA, one group per CTA
-                ss.R = 8; sgrid = std::min(grid, kSgSeedGroupsMax / 2);
+                ss.R = 2; sgrid = std::min(grid, kSgSeedGroupsMax / 2);  // 4 L2-resident superblocks of 2 tiles per CTA
                 ss.n_tiles = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sgrid) * 8);
                 seed_groups = 2 * sgrid;  // per CTA and column half
             }

@@ -290,7 +290,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     ++it;
                 }
                 // one group per CTA and column half (2 * gridDim.x groups)
-                if (seed_mode && !p.seed_chunks && live) p.seed_max[static_cast<size_t>(blockIdx.x * 2 + half) * p.Q + qi] = best;
+                if (seed_mode && !p.seed_chunks && live) {
+                    float* g = p.seed_max + static_cast<size_t>(blockIdx.x * 2 + half) * p.Q + qi;  // only this thread touches it
+                    *g = sb == 0 ? best : fmaxf(*g, best);
+                }
             }
         }
     }
