@@ -121,6 +121,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+    pdl_launch_dependents();  // the next kernel may begin its own prologue as soon as this CTA's resources are released
 
     auto slot_base = [&](int slot) { return smem_slots + slot * Cfg::kSlotBytes; };  // P tile (+ aliased output staging), codes
     auto in_base = [&](int stage) { return smem_in + stage * Cfg::kInBytes; };      // Q | K | V

@@ -15,6 +15,7 @@
 #include "attention_tc.cuh"
 #include "encoder.hpp"
 #include "gemm_ln.cuh"
+#include "gemm_pair.cuh"
 #include "gemm_tcgen05.cuh"
 #include "rowwise.cuh"
 
@@ -92,8 +93,7 @@ static void launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int grid = std::min(m_tiles * n_tiles, num_sms);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, tc, p);
-    KJ_CUDA(cudaGetLastError());
+    launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, ta, tb, tc, p);
 }
 
 template <int BN>
@@ -119,6 +119,32 @@ void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap&
     }
 }
 
+// CTA-pair kernel (gemm_pair.cuh): K <= 384, bf16 output; `tb_half` has a box of block_n/2 weight rows.
+template <int BN, int EPI>
+static void launch_gemm_pair_inst(const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p, int num_sms,
+                                  cudaStream_t st) {
+    using Cfg = PairCfg<BN>;
+    static int configured[64] = {0};
+    auto kern = gemm_pair_kernel<BN, EPI>;
+    ensure_smem_attr(kern, Cfg::kSmemBytes, configured);
+    const int m_tiles = (p.M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM);
+    const int grid = 2 * std::min(m_tiles, num_sms / 2);
+    launch_pdl(kern, dim3(grid), dim3(kPairThreads), Cfg::kSmemBytes, st, ta, tb_half, tc, p);
+}
+
+void launch_gemm_pair(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p,
+                      int num_sms, cudaStream_t st) {
+    if (p.N % 16 != 0 || p.K % 8 != 0 || p.K > kPairMaxKB * kGemmBlockK) throw Error(KJC_INVALID_CONFIG, "pair GEMM needs N % 16 == 0, K % 8 == 0, K <= 384");
+    if (epi != EPI_BIAS_BF16 && epi != EPI_BIAS_ACT_BF16) throw Error(KJC_INVALID_CONFIG, "pair GEMM stores bf16 only");
+    const bool act = epi == EPI_BIAS_ACT_BF16;
+    switch (block_n) {
+        case 128: act ? launch_gemm_pair_inst<128, EPI_BIAS_ACT_BF16>(ta, tb_half, tc, p, num_sms, st) : launch_gemm_pair_inst<128, EPI_BIAS_BF16>(ta, tb_half, tc, p, num_sms, st); break;
+        case 192: act ? launch_gemm_pair_inst<192, EPI_BIAS_ACT_BF16>(ta, tb_half, tc, p, num_sms, st) : launch_gemm_pair_inst<192, EPI_BIAS_BF16>(ta, tb_half, tc, p, num_sms, st); break;
+        case 256: act ? launch_gemm_pair_inst<256, EPI_BIAS_ACT_BF16>(ta, tb_half, tc, p, num_sms, st) : launch_gemm_pair_inst<256, EPI_BIAS_BF16>(ta, tb_half, tc, p, num_sms, st); break;
+        default: throw Error(KJC_INVALID_CONFIG, "unsupported pair GEMM block N");
+    }
+}
+
 void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
                     const float* beta, float eps, int num_sms, cudaStream_t st) {
     static int configured[64] = {0};
@@ -127,8 +153,7 @@ void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensor
     GemmLnParams p;
     p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
-    gemm_ln384_kernel<<<std::min(m_tiles, num_sms), kGemmThreads, kLnSmemBytes, st>>>(ta, tw, t_io, t_io, p);
-    KJ_CUDA(cudaGetLastError());
+    launch_pdl(gemm_ln384_kernel, dim3(std::min(m_tiles, num_sms)), dim3(kGemmThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
 }
 
 // ------------------------------------------------------------ row-kernel launch
@@ -179,7 +204,7 @@ static void launch_attention_tc(const AttnParams& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     ensure_smem_attr(attention_tc_kernel<D>, AtcCfg<D>::kSmemBytes, configured);
-    attention_tc_kernel<D><<<std::min(p.B * p.heads, sms), AtcCfg<D>::kThreads, AtcCfg<D>::kSmemBytes, st>>>(t_qkv, t_ctx, p);
+    launch_pdl(attention_tc_kernel<D>, dim3(std::min(p.B * p.heads, sms)), dim3(AtcCfg<D>::kThreads), AtcCfg<D>::kSmemBytes, st, t_qkv, t_ctx, p);
 }
 
 void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
@@ -452,6 +477,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     bn_qkv_ = pick_block_n(3 * H);
     bn_h_ = pick_block_n(H);
     bn_i_ = pick_block_n(I);
+    if (const char* e = getenv("KJC_BN_I")) bn_i_ = atoi(e);  // tuning hook
     layers_.resize(L);
     for (int l = 0; l < L; ++l) {
         LayerDev& ld = layers_[l];
@@ -462,7 +488,12 @@ Encoder::Encoder(const std::string& dir, int device) {
         ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK, 128);
         ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK, 128);
         ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK, 128);
+        if (H <= kPairMaxKB * kGemmBlockK && bn_qkv_ >= 128 && bn_i_ >= 128) {  // CTA-pair kernel: each CTA loads half of a weight tile
+            ld.t_wqkv_half = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, bn_qkv_ / 2, kGemmBlockK, 128);
+            ld.t_w1_half = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_ / 2, kGemmBlockK, 128);
+        }
     }
+    pair_gemm_ = H <= kPairMaxKB * kGemmBlockK && H % kGemmBlockK == 0 && bn_qkv_ >= 128 && bn_i_ >= 128 && getenv("KJC_PAIR_GEMM") != nullptr;  // slower than the 1-CTA kernel at one 256-row tile per pair (launch-bound regime): opt-in
     if (info_.head_kind != KJC_HEAD_ABSENT) {
         w_pre_ = pre_w.empty() ? nullptr : d_f32_ + off_wpre;
         b_pre_ = (pre_w.empty() || !has_bpre) ? nullptr : d_f32_ + off_bpre;
@@ -547,7 +578,8 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
         g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = qkv16_; g.ldo = 3 * H; g.act = ACT_NONE;
         prof_begin(KJC_K_GEMM_QKV, st);
-        launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, t_qkv16_out_, g, num_sms_, st);
+        if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv_half, t_qkv16_out_, g, num_sms_, st);
+        else launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, t_qkv16_out_, g, num_sms_, st);
         prof_end(st);
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
         AttnParams a;
@@ -577,7 +609,8 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
         g = GemmParams{};
         g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = h16_; g.ldo = I; g.act = act_;
         prof_begin(KJC_K_GEMM_FFN_UP, st);
-        launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, t_h16_out_, g, num_sms_, st);
+        if (pair_gemm_) launch_gemm_pair(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1_half, t_h16_out_, g, num_sms_, st);
+        else launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, t_h16_out_, g, num_sms_, st);
         prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
         if (fused_ln_) {
@@ -803,6 +836,8 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         int dev = 0;
         KJ_CUDA(cudaGetDevice(&dev));
         KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+        const bool pair = block_n >= 1000;
+        if (pair) block_n -= 1000;
         const int bn = block_n > 0 ? block_n : pick_block_n(N);
         const size_t Mp = std::max(M, 128), Np = std::max(N, bn);
         __nv_bfloat16 *dA, *dW;
@@ -830,6 +865,10 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act;
         CUtensorMap tc = ta;
         if (!f32out) tc = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
+        if (pair) {
+            CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
+            launch_gemm_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
+        } else
         launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
         KJ_CUDA(cudaDeviceSynchronize());
         KJ_CUDA(cudaMemcpy(out, dO, static_cast<size_t>(M) * N * (f32out ? 4 : 2), cudaMemcpyDeviceToHost));
@@ -888,6 +927,8 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     int dev = 0;
     KJ_CUDA(cudaGetDevice(&dev));
     KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const bool pair = block_n >= 1000;
+    if (pair) block_n -= 1000;
     const int bn = block_n > 0 ? block_n : pick_block_n(N);
     const size_t Mp = std::max(M, 128), Np = std::max(N, bn);
     __nv_bfloat16 *dA, *dW;
@@ -913,9 +954,14 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     cudaEvent_t e0, e1;
     KJ_CUDA(cudaEventCreate(&e0));
     KJ_CUDA(cudaEventCreate(&e1));
-    for (int i = 0; i < 5; ++i) launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
+    CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
+    auto go = [&] {
+        if (pair) launch_gemm_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
+        else launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
+    };
+    for (int i = 0; i < 5; ++i) go();
     KJ_CUDA(cudaEventRecord(e0, nullptr));
-    for (int i = 0; i < iters; ++i) launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
+    for (int i = 0; i < iters; ++i) go();
     KJ_CUDA(cudaEventRecord(e1, nullptr));
     KJ_CUDA(cudaDeviceSynchronize());
     float ms = 0.f;

@@ -19,6 +19,8 @@ CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_byte
 int pick_block_n(int N);
 void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms,
                  cudaStream_t st);
+void launch_gemm_pair(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p,
+                      int num_sms, cudaStream_t st);
 void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
                     const float* beta, float eps, int num_sms, cudaStream_t st);
 void launch_attention(const AttnParams& p, int head_dim, cudaStream_t st);
@@ -43,10 +45,29 @@ inline void ensure_smem_attr(K kern, int bytes, int (&configured)[64]) {
     configured[dev & 63] = bytes;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel must call pdl_wait() before it touches global memory its
+// predecessor wrote.  KJC_NO_PDL=1 falls back to plain launches.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    static const bool enabled = getenv("KJC_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = enabled ? 1 : 0;
+    KJ_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+}
+
 struct LayerDev {
     const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
     const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
     CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
+    CUtensorMap t_wqkv_half, t_w1_half;  // box of block_n/2 rows: the CTA-pair GEMM loads half a weight tile per CTA
 };
 
 class Encoder {
@@ -93,7 +114,7 @@ class Encoder {
     // activations of one micro-batch
     int ws_tokens_ = 0;
     float* y32_ = nullptr;  // unfused path only
-    bool fused_ln_ = false;
+    bool fused_ln_ = false, pair_gemm_ = false;
     __nv_bfloat16 *x16_ = nullptr, *qkv16_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr;
     CUtensorMap t_x16_, t_ctx16_, t_h16_;          // A-operand loads
     CUtensorMap t_qkv16_out_, t_h16_out_;          // epilogue TMA stores

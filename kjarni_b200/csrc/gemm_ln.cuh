@@ -80,6 +80,8 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here on
+    pdl_launch_dependents();  // the next kernel may begin its own prologue as soon as this CTA's resources are released
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer

@@ -16,6 +16,10 @@ for name, Nn, K, epi in (("qkv", 1152, 384, 0), ("ffn_up", 1536, 384, 1), ("out"
         print(f"{name:9s} N={Nn} K={K} BN={bn}: full {row[0]:.1f}us ({fl/row[0]/1e6:.0f} TF) | no-epi {row[1]:.1f} | no-mma {row[2]:.1f} | "
               f"tma-only {row[3]:.1f} | no-tma {row[4]:.1f} | mma-only {row[5]:.1f} | epi-only {row[6]:.1f} | empty {row[7]:.1f}")
 
+for name, Nn, K, epi, bn in (("qkv", 1152, 384, 0, 192), ("ffn_up", 1536, 384, 1, 256)):
+    us = t(Nn, K, epi, 1000 + bn, 0)
+    print(f"PAIR {name:9s} N={Nn} K={K} BN={bn}: {us:.1f}us ({2.0*M*Nn*K/us/1e6:.0f} TF)")
+
 # fused out-proj/FFN-down + residual + LayerNorm kernel
 import numpy as np
 for K in (384, 1536):

@@ -63,6 +63,22 @@ def test_gemm_every_block_n_and_tails(block_n):
     assert np.abs(got - want).max() < 1e-3
 
 
+@pytest.mark.parametrize("M,Nn,K,bn", [(256, 1152, 384, 192), (18944, 1152, 384, 192), (300, 1536, 384, 256), (130, 384, 192, 128),
+                                       (4096 + 77, 1536, 384, 256), (100, 416, 320, 256)])
+@pytest.mark.parametrize("epi", [0, 1])
+def test_pair_gemm_matches_fp32(M, Nn, K, bn, epi):
+    """CTA-pair (cta_group::2) A-resident GEMM (gemm_pair.cuh): M tails inside a 256-row pair tile, N tails, several pair counts."""
+    rng = np.random.default_rng(M + Nn + K + epi)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((Nn, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(Nn).astype(np.float32)
+    got = run_gemm(a, w, bias, None, epi, act=0, block_n=1000 + bn)
+    want = ref_gemm(a, w, bias, None, epi, 0)
+    err = np.abs(got - want) / (1.0 + np.abs(want))
+    assert np.isfinite(got).all()
+    assert err.max() < 2.0 ** -8, (err.max(), np.unravel_index(err.argmax(), err.shape))
+
+
 @pytest.mark.parametrize("act", [0, 1, 2])
 def test_gemm_activations(act):
     rng = np.random.default_rng(act)
