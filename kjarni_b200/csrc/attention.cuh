@@ -21,6 +21,7 @@ struct AttnParams {
     int B, S, H, heads;
     float scale_log2e;         // (1/sqrt(d)) * log2(e)
     int nan_if_all_masked;     // 1: no-alloc (-inf) convention, a fully padded sequence yields NaN
+    int max_ctas = 0;          // persistent tcgen05 kernel: CTAs to launch (0 = one per SM)
 };
 
 constexpr int kAttnThreads = 256;

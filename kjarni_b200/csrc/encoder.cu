@@ -75,8 +75,8 @@ CUtensorMap make_tmap_3d(const void* base, int elem_bytes, uint64_t d0, uint64_t
 
 // ----------------------------------------------------------------- GEMM launch
 int pick_block_n(int N) {
+    if (N % 192 == 0) return 192;  // 192-column tiles leave shared memory for the staged bias and a 3-deep store ring
     if (N % 256 == 0) return 256;
-    if (N % 192 == 0) return 192;
     if (N % 128 == 0) return 128;
     if (N <= 64) return 64;
     if (N <= 128) return 128;
@@ -204,6 +204,7 @@ static void launch_attention_tc(const AttnParams& p, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     ensure_smem_attr(attention_tc_kernel<D>, AtcCfg<D>::kSmemBytes, configured);
+    if (p.max_ctas > 0) sms = std::min(sms, p.max_ctas);
     launch_pdl(attention_tc_kernel<D>, dim3(std::min(p.B * p.heads, sms)), dim3(AtcCfg<D>::kThreads), AtcCfg<D>::kSmemBytes, st, t_qkv, t_ctx, p);
 }
 
@@ -504,11 +505,23 @@ Encoder::Encoder(const std::string& dir, int device) {
     fused_ln_ = (H == kLnN) && !getenv("KJC_NO_FUSED_LN");
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
+    if (const char* e = getenv("KJC_LANES")) lanes_ = std::min(8, std::max(1, atoi(e)));
+    ws_.resize(lanes_);
+    for (Workspace& w : ws_) {
+        KJ_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+        KJ_CUDA(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    }
+    KJ_CUDA(cudaEventCreateWithFlags(&ev_in_, cudaEventDisableTiming));
 }
 
 Encoder::~Encoder() {
     cudaSetDevice(info_.device);
-    free_workspace();
+    for (Workspace& w : ws_) {
+        free_workspace(w);
+        if (w.stream) cudaStreamDestroy(w.stream);
+        if (w.done) cudaEventDestroy(w.done);
+    }
+    if (ev_in_) cudaEventDestroy(ev_in_);
     if (d_f32_) cudaFree(d_f32_);
     if (d_w16_) cudaFree(d_w16_);
     if (d_err_) cudaFree(d_err_);
@@ -521,49 +534,50 @@ Encoder::~Encoder() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
-void Encoder::free_workspace() {
-    for (void* p : {(void*)y32_, (void*)x16_, (void*)qkv16_, (void*)ctx16_, (void*)h16_})
+void Encoder::free_workspace(Workspace& w) {
+    for (void* p : {(void*)w.y32, (void*)w.x16, (void*)w.qkv16, (void*)w.ctx16, (void*)w.h16})
         if (p) cudaFree(p);
-    y32_ = nullptr; x16_ = qkv16_ = ctx16_ = h16_ = nullptr;
-    ws_tokens_ = 0;
+    w.y32 = nullptr; w.x16 = w.qkv16 = w.ctx16 = w.h16 = nullptr;
+    w.tokens = 0;
 }
 
 int Encoder::micro_batch(int S) const { return std::max(1, micro_tokens_ / std::max(S, 1)); }
 
 // Activations for one micro-batch; sized once for the largest token count seen (>= 128 rows so TMA boxes fit).
-void Encoder::ensure_workspace(int tokens) {
-    if (tokens <= ws_tokens_) return;
-    free_workspace();
+void Encoder::ensure_workspace(Workspace& w, int tokens) {
+    if (tokens <= w.tokens) return;
+    KJ_CUDA(cudaStreamSynchronize(w.stream));
+    free_workspace(w);
     const size_t T = static_cast<size_t>(std::max(tokens, 128));
     const int H = info_.hidden_size, I = info_.intermediate_size;
-    if (!fused_ln_) KJ_CUDA(cudaMalloc(&y32_, T * H * 4));  // pre-LayerNorm sums of the unfused path
-    KJ_CUDA(cudaMalloc(&x16_, T * H * 2));
-    KJ_CUDA(cudaMalloc(&qkv16_, T * 3 * H * 2));
-    KJ_CUDA(cudaMalloc(&ctx16_, T * H * 2));
-    KJ_CUDA(cudaMalloc(&h16_, T * I * 2));
+    if (!fused_ln_) KJ_CUDA(cudaMalloc(&w.y32, T * H * 4));  // pre-LayerNorm sums of the unfused path
+    KJ_CUDA(cudaMalloc(&w.x16, T * H * 2));
+    KJ_CUDA(cudaMalloc(&w.qkv16, T * 3 * H * 2));
+    KJ_CUDA(cudaMalloc(&w.ctx16, T * H * 2));
+    KJ_CUDA(cudaMalloc(&w.h16, T * I * 2));
     // stale rows beyond the live token count are read by TMA (results discarded): keep them finite
-    KJ_CUDA(cudaMemsetAsync(x16_, 0, T * H * 2, stream_));
-    KJ_CUDA(cudaMemsetAsync(ctx16_, 0, T * H * 2, stream_));
-    KJ_CUDA(cudaMemsetAsync(h16_, 0, T * I * 2, stream_));
-    KJ_CUDA(cudaStreamSynchronize(stream_));  // the forward may run on a caller stream
-    t_x16_ = make_tmap_2d(x16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
-    t_ctx16_ = make_tmap_2d(ctx16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
-    t_h16_ = make_tmap_2d(h16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
-    t_qkv16_out_ = make_tmap_2d(qkv16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
-    t_h16_out_ = make_tmap_2d(h16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
-    t_x16_io_ = make_tmap_2d(x16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
-    ws_tokens_ = static_cast<int>(T);
+    KJ_CUDA(cudaMemsetAsync(w.x16, 0, T * H * 2, w.stream));
+    KJ_CUDA(cudaMemsetAsync(w.ctx16, 0, T * H * 2, w.stream));
+    KJ_CUDA(cudaMemsetAsync(w.h16, 0, T * I * 2, w.stream));
+    KJ_CUDA(cudaStreamSynchronize(w.stream));  // the forward may run on a caller stream
+    w.t_x16 = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
+    w.t_ctx16 = make_tmap_2d(w.ctx16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
+    w.t_h16 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
+    w.t_qkv16_out = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
+    w.t_h16_out = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
+    w.t_x16_io = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
+    w.tokens = static_cast<int>(T);
 }
 
 // One micro-batch: ids/mask/types are device pointers for `nb` sequences of length S.
-void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S,
+void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S,
                             const KjcForwardOptions& o, bool noalloc_convention, float* d_out, cudaStream_t st) {
     const int H = info_.hidden_size, I = info_.intermediate_size, M = nb * S, d = H / info_.num_heads;
     const float eps = info_.layer_norm_eps;
     {
         EmbedParams e;
         e.ids = d_ids; e.type_ids = d_types; e.word = word_; e.pos = pos_; e.type = type_; e.gamma = emb_g_; e.beta = emb_b_;
-        e.x32 = nullptr; e.x16 = x16_; e.err_flag = d_err_;
+        e.x32 = nullptr; e.x16 = w.x16; e.err_flag = d_err_;
         e.M = M; e.S = S; e.H = H; e.vocab = info_.vocab_size; e.max_pos = info_.max_position_embeddings;
         e.type_vocab = info_.type_vocab_size; e.pos_offset = info_.position_offset; e.eps = eps;
         const int grid = (M + 7) / 8;
@@ -576,55 +590,56 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
     for (const LayerDev& L : layers_) {
         GemmParams g{};
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
-        g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = qkv16_; g.ldo = 3 * H; g.act = ACT_NONE;
+        g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = 3 * H; g.act = ACT_NONE;
         prof_begin(KJC_K_GEMM_QKV, st);
-        if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv_half, t_qkv16_out_, g, num_sms_, st);
-        else launch_gemm(bn_qkv_, EPI_BIAS_BF16, t_x16_, L.t_wqkv, t_qkv16_out_, g, num_sms_, st);
+        if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, w.t_qkv16_out, g, sms, st);
+        else launch_gemm(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv, w.t_qkv16_out, g, sms, st);
         prof_end(st);
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
         AttnParams a;
-        a.qkv = qkv16_; a.mask = d_mask; a.ctx = ctx16_; a.B = nb; a.S = S; a.H = H; a.heads = info_.num_heads;
+        a.qkv = w.qkv16; a.mask = d_mask; a.ctx = w.ctx16; a.B = nb; a.S = S; a.H = H; a.heads = info_.num_heads;
         a.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
         a.nan_if_all_masked = noalloc_convention ? 1 : 0;
+        a.max_ctas = sms;
         prof_begin(KJC_K_ATTENTION, st);
         launch_attention(a, d, st);
         prof_end(st);
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
         if (fused_ln_) {
             prof_begin(KJC_K_GEMM_OUT, st);
-            launch_gemm_ln(t_ctx16_, L.t_wo, t_x16_io_, M, H, L.bo, L.g1, L.be1, eps, num_sms_, st);
+            launch_gemm_ln(w.t_ctx16, L.t_wo, w.t_x16_io, M, H, L.bo, L.g1, L.be1, eps, sms, st);
             prof_end(st);
         } else {
             g = GemmParams{};
-            g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = x16_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+            g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = w.x16; g.ldr = H; g.out = w.y32; g.ldo = H; g.act = ACT_NONE;
             prof_begin(KJC_K_GEMM_OUT, st);
-            launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_ctx16_, L.t_wo, t_qkv16_out_, g, num_sms_, st);
+            launch_gemm(bn_h_, EPI_BIAS_RES_F32, w.t_ctx16, L.t_wo, w.t_qkv16_out, g, sms, st);
             prof_end(st);
             prof_begin(KJC_K_LAYERNORM, st);
-            launch_layernorm(y32_, L.g1, L.be1, eps, nullptr, x16_, M, H, st);
+            launch_layernorm(w.y32, L.g1, L.be1, eps, nullptr, w.x16, M, H, st);
             prof_end(st);
             ++launches_;
         }
         // t = act(x W1^T + b1)                                     (standard_new.rs:47-73)
         g = GemmParams{};
-        g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = h16_; g.ldo = I; g.act = act_;
+        g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = w.h16; g.ldo = I; g.act = act_;
         prof_begin(KJC_K_GEMM_FFN_UP, st);
-        if (pair_gemm_) launch_gemm_pair(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1_half, t_h16_out_, g, num_sms_, st);
-        else launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, t_x16_, L.t_w1, t_h16_out_, g, num_sms_, st);
+        if (pair_gemm_) launch_gemm_pair(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1_half, w.t_h16_out, g, sms, st);
+        else launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1, w.t_h16_out, g, sms, st);
         prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
         if (fused_ln_) {
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
-            launch_gemm_ln(t_h16_, L.t_w2, t_x16_io_, M, I, L.b2, L.g2, L.be2, eps, num_sms_, st);
+            launch_gemm_ln(w.t_h16, L.t_w2, w.t_x16_io, M, I, L.b2, L.g2, L.be2, eps, sms, st);
             prof_end(st);
         } else {
             g = GemmParams{};
-            g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = x16_; g.ldr = H; g.out = y32_; g.ldo = H; g.act = ACT_NONE;
+            g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = w.x16; g.ldr = H; g.out = w.y32; g.ldo = H; g.act = ACT_NONE;
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
-            launch_gemm(bn_h_, EPI_BIAS_RES_F32, t_h16_, L.t_w2, t_qkv16_out_, g, num_sms_, st);
+            launch_gemm(bn_h_, EPI_BIAS_RES_F32, w.t_h16, L.t_w2, w.t_qkv16_out, g, sms, st);
             prof_end(st);
             prof_begin(KJC_K_LAYERNORM, st);
-            launch_layernorm(y32_, L.g2, L.be2, eps, nullptr, x16_, M, H, st);
+            launch_layernorm(w.y32, L.g2, L.be2, eps, nullptr, w.x16, M, H, st);
             prof_end(st);
             ++launches_;
         }
@@ -633,16 +648,16 @@ void Encoder::forward_micro(const uint32_t* d_ids, const float* d_mask, const ui
     prof_begin(KJC_K_OUTPUT, st);
     if (o.output == KJC_OUT_HIDDEN) {
         const size_t n4 = static_cast<size_t>(M) * H / 4;
-        bf16_to_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(x16_, d_out, n4);
+        bf16_to_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(w.x16, d_out, n4);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else if (o.output == KJC_OUT_POOLED) {
-        pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(x16_, d_mask, d_out, S, H, o.pooling, o.normalize);
+        pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(w.x16, d_mask, d_out, S, H, o.pooling, o.normalize);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else {
         HeadParams<__nv_bfloat16> hp;
-        hp.x = x16_; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
+        hp.x = w.x16; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
         hp.B = nb; hp.S = S; hp.H = H; hp.C = info_.num_labels;
         hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
         const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
@@ -728,6 +743,44 @@ bool Encoder::resolve_noalloc(int B, int S, const KjcForwardOptions& o) const {
     return tokens <= 1 || tokens >= 1000;
 }
 
+// Micro-batches round-robin over the lanes.  `st` is the caller-visible stream: lane streams start after everything
+// already enqueued on it and `st` resumes after the last lane has finished.
+void Encoder::forward_batches(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S, const KjcForwardOptions& o,
+                              float* d_out, cudaStream_t st) {
+    const int mb = micro_batch(S);
+    const bool noalloc = resolve_noalloc(B, S, o);
+    const size_t row = out_row_elems(o, S);
+    const int n_mb = (B + mb - 1) / mb;
+    // one lane (all SMs, caller's stream) for a single micro-batch or while per-kernel profiling is on
+    const int lanes = (profiling_ || n_mb < 2) ? 1 : std::min(lanes_, n_mb);
+    if (lanes == 1) {
+        ensure_workspace(ws_[0], std::min(B, mb) * S);
+        for (int b0 = 0; b0 < B; b0 += mb) {
+            const int nb = std::min(mb, B - b0);
+            const size_t t0 = static_cast<size_t>(b0) * S;
+            forward_micro(ws_[0], num_sms_, d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, o, noalloc,
+                          d_out + b0 * row, st);
+        }
+        return;
+    }
+    const int sms = std::max(1, num_sms_ / lanes);
+    for (int l = 0; l < lanes; ++l) ensure_workspace(ws_[l], mb * S);
+    KJ_CUDA(cudaEventRecord(ev_in_, st));
+    for (int l = 0; l < lanes; ++l) KJ_CUDA(cudaStreamWaitEvent(ws_[l].stream, ev_in_, 0));
+    int i = 0;
+    for (int b0 = 0; b0 < B; b0 += mb, ++i) {
+        Workspace& w = ws_[i % lanes];
+        const int nb = std::min(mb, B - b0);
+        const size_t t0 = static_cast<size_t>(b0) * S;
+        forward_micro(w, sms, d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, o, noalloc,
+                      d_out + b0 * row, w.stream);
+    }
+    for (int l = 0; l < lanes; ++l) {
+        KJ_CUDA(cudaEventRecord(ws_[l].done, ws_[l].stream));
+        KJ_CUDA(cudaStreamWaitEvent(st, ws_[l].done, 0));
+    }
+}
+
 void Encoder::forward_device(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S,
                              const KjcForwardOptions& o, float* d_out, cudaStream_t st) {
     validate(B, S, o);
@@ -735,15 +788,7 @@ void Encoder::forward_device(const uint32_t* d_ids, const float* d_mask, const u
     KJ_CUDA(cudaSetDevice(info_.device));
     if (!st) st = stream_;
     launches_ = 0;
-    const int mb = micro_batch(S);
-    ensure_workspace(std::min(B, mb) * S);
-    const bool noalloc = resolve_noalloc(B, S, o);
-    const size_t row = out_row_elems(o, S);
-    for (int b0 = 0; b0 < B; b0 += mb) {
-        const int nb = std::min(mb, B - b0);
-        const size_t t0 = static_cast<size_t>(b0) * S;
-        forward_micro(d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, o, noalloc, d_out + b0 * row, st);
-    }
+    forward_batches(d_ids, d_mask, d_types, B, S, o, d_out, st);
 }
 
 void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o,
@@ -781,15 +826,8 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
     const float* d_mask = mask ? reinterpret_cast<const float*>(d_in_ + T) : nullptr;
     const uint32_t* d_types = types ? d_in_ + 2 * T : nullptr;
 
-    const int mb = micro_batch(S);
-    ensure_workspace(std::min(B, mb) * S);
-    const bool noalloc = resolve_noalloc(B, S, o);
-    for (int b0 = 0; b0 < B; b0 += mb) {
-        const int nb = std::min(mb, B - b0);
-        const size_t t0 = static_cast<size_t>(b0) * S;
-        forward_micro(d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, o, noalloc,
-                      d_out_ + b0 * row, stream_);
-    }
+    (void)row;
+    forward_batches(d_ids, d_mask, d_types, B, S, o, d_out_, stream_);
     KJ_CUDA(cudaMemcpyAsync(h_stage_out_, d_out_, out_elems * 4, cudaMemcpyDeviceToHost, stream_));
     int err = 0;
     KJ_CUDA(cudaMemcpyAsync(&err_host_, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
@@ -950,7 +988,7 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     CUtensorMap tc = ta;
     if (!f32out) tc = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, kEpiChunkCols, 64);
     GemmParams p{};
-    p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act; p.dbg = flags;
+    p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act; p.dbg = flags & ~8;
     cudaEvent_t e0, e1;
     KJ_CUDA(cudaEventCreate(&e0));
     KJ_CUDA(cudaEventCreate(&e1));
@@ -960,6 +998,30 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
         else launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
     };
     for (int i = 0; i < 5; ++i) go();
+    if (flags & 8) {  // one traced launch: per-CTA milestone stamps (ns, relative to the earliest kernel entry)
+        unsigned long long* dT;
+        const int ctas = prop.multiProcessorCount;
+        KJ_CUDA(cudaMalloc(&dT, ctas * 32 * 8));
+        KJ_CUDA(cudaMemset(dT, 0, ctas * 32 * 8));
+        p.trace = dT;
+        p.dbg = flags & ~8;
+        go(); go(); go();
+        KJ_CUDA(cudaDeviceSynchronize());
+        std::vector<unsigned long long> h(ctas * 32);
+        KJ_CUDA(cudaMemcpy(h.data(), dT, h.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (int c = 0; c < ctas; ++c) if (h[c * 32]) t0 = std::min(t0, h[c * 32]);
+        static const char* names[18] = {"entry", "prologue", "pdl_wait", "operands0", "acc0", "epi0", "acc1", "epi1", "acc2", "epi2", "acc3", "epi3",
+                                        "acc4", "epi4", "acc5", "epi5", "drained", "exit"};
+        for (int c : {0, 1, ctas / 2, ctas - 1}) {
+            fprintf(stderr, "trace M=%d N=%d K=%d bn=%d cta %3d:", M, N, K, bn, c);
+            for (int i = 0; i < 18; ++i) if (h[c * 32 + i]) fprintf(stderr, " %s=%.2f", names[i], (h[c * 32 + i] - t0) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+        p.trace = nullptr;
+        p.dbg = flags & ~8;
+        cudaFree(dT);
+    }
     KJ_CUDA(cudaEventRecord(e0, nullptr));
     for (int i = 0; i < iters; ++i) go();
     KJ_CUDA(cudaEventRecord(e1, nullptr));

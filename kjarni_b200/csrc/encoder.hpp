@@ -94,10 +94,25 @@ class Encoder {
     void validate(int B, int S, const KjcForwardOptions& o) const;
     bool resolve_noalloc(int B, int S, const KjcForwardOptions& o) const;
     size_t out_row_elems(const KjcForwardOptions& o, int S) const;
-    void ensure_workspace(int tokens);
-    void free_workspace();
-    void forward_micro(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S, const KjcForwardOptions& o,
-                       bool noalloc_convention, float* d_out, cudaStream_t st);
+    // Activations of one micro-batch in flight.  Several "lanes" run concurrently on disjoint groups of SMs (each kernel is
+    // launched with num_sms / lanes persistent CTAs on the lane's own stream), so the fixed per-launch latency of one lane
+    // (launch, prologue, pipeline fill, epilogue drain) is covered by the other lanes' tensor work.
+    struct Workspace {
+        int tokens = 0;
+        float* y32 = nullptr;  // unfused path only
+        __nv_bfloat16 *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr;
+        CUtensorMap t_x16, t_ctx16, t_h16;   // A-operand loads
+        CUtensorMap t_qkv16_out, t_h16_out;  // epilogue TMA stores
+        CUtensorMap t_x16_io;                // residual load + LayerNorm output store of the fused kernel
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+    };
+    void ensure_workspace(Workspace& w, int tokens);
+    void free_workspace(Workspace& w);
+    void forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S,
+                       const KjcForwardOptions& o, bool noalloc_convention, float* d_out, cudaStream_t st);
+    void forward_batches(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S, const KjcForwardOptions& o,
+                         float* d_out, cudaStream_t st);
 
     KjcEncoderInfo info_{};
     std::vector<std::string> labels_;
@@ -111,14 +126,10 @@ class Encoder {
     const float *word_ = nullptr, *pos_ = nullptr, *type_ = nullptr, *emb_g_ = nullptr, *emb_b_ = nullptr;
     const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
     std::vector<LayerDev> layers_;
-    // activations of one micro-batch
-    int ws_tokens_ = 0;
-    float* y32_ = nullptr;  // unfused path only
     bool fused_ln_ = false, pair_gemm_ = false;
-    __nv_bfloat16 *x16_ = nullptr, *qkv16_ = nullptr, *ctx16_ = nullptr, *h16_ = nullptr;
-    CUtensorMap t_x16_, t_ctx16_, t_h16_;          // A-operand loads
-    CUtensorMap t_qkv16_out_, t_h16_out_;          // epilogue TMA stores
-    CUtensorMap t_x16_io_;                         // residual load + LayerNorm output store of the fused kernel
+    int lanes_ = 2;
+    std::vector<Workspace> ws_;
+    cudaEvent_t ev_in_ = nullptr;
     // host-buffer entry point staging
     uint32_t* d_in_ = nullptr;
     float* d_out_ = nullptr;

@@ -34,7 +34,15 @@ struct GemmParams {
     int ldo, ldr;
     int act;
     int dbg;  // microbenchmark switches (kjc_dbg_gemm_time): 1 = no epilogue work, 2 = no MMA issue, 4 = no TMA loads
+    unsigned long long* trace;  // optional [gridDim.x][32] %globaltimer stamps of CTA milestones (kjc_dbg_gemm_time flag 8)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define KJ_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 32 + (slot)] = gtimer(); } while (0)
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
@@ -44,16 +52,20 @@ constexpr int kGemmEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiChunkCols = 32;                         // columns per tcgen05.ld / per TMA-store box
 constexpr int kEpiStageBytes = 32 * kEpiChunkCols * 2;    // one warp's bf16 staging tile: 32 rows x 64 B (64B swizzle)
+constexpr int kEpiBiasMax = 3072;                         // bias columns staged in shared memory (BN <= 192 configurations)
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int kStages = (BN <= 128) ? 6 : 4;
+    static constexpr int kStages = (BN <= 64) ? 6 : ((BN <= 128) ? 5 : 4);
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
     static constexpr int kBBytes = BN * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiStageBytes;  // double-buffered store staging per epilogue warp
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiBufs = (BN <= 192) ? 3 : 2;              // store staging ring per epilogue warp
+    static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiStageBytes;
+    static constexpr int kBiasBytes = (BN <= 192) ? kEpiBiasMax * 4 : 0;  // bias staged in smem where it fits
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // erf-GELU, 0.5*x*(1+erf(x/sqrt2)) (reference activations.rs:57-59), with erf(t) = 1 - 2^-q(t) for t >= 0,
@@ -109,6 +121,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 
     extern __shared__ uint8_t smem_raw[];
+    if (threadIdx.x == 0) KJ_TRACE(0);  // kernel entry
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
@@ -119,9 +132,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* tmem_full = bars + 2 * kStages;
     uint64_t* tmem_empty = bars + 2 * kStages + 2;
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    const bool bias_in_smem = Cfg::kBiasBytes > 0 && p.bias != nullptr && p.N <= kEpiBiasMax;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // the bias is a weight: it does not depend on the predecessor kernel, so it is staged before pdl_wait()
+    if (bias_in_smem)
+        for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = __ldg(p.bias + i);
 
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int n_tiles = (p.N + BN - 1) / BN;
@@ -149,8 +167,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    if (threadIdx.x == 0) KJ_TRACE(1);  // prologue done
     pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here on
     pdl_launch_dependents();  // the next kernel may begin its own prologue as soon as this CTA's resources are released
+    if (threadIdx.x == 0) KJ_TRACE(2);  // predecessor complete
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
@@ -191,6 +211,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (it == 0 && kb == 0) KJ_TRACE(3);  // first operands landed
                     tc_fence_after();
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
@@ -217,7 +238,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int half = ew >> 2;             // column half handled by this warpgroup
         constexpr int kColsPerHalf = BN / 2;
         constexpr bool kStaged = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16);
-        uint8_t* stage_buf = smem_epi + ew * 2 * kEpiStageBytes;
+        uint8_t* stage_buf = smem_epi + ew * Cfg::kEpiBufs * kEpiStageBytes;
         int sbuf = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -225,6 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
+            if (ew == 0 && lane == 0 && it < 6) KJ_TRACE(4 + 2 * it);  // accumulator of tile `it` ready
             tc_fence_after();
             const int row0 = m_blk * kGemmBlockM + quad * 32;
             const int row = row0 + lane;
@@ -233,24 +255,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (p.dbg & 1) {
                 // microbenchmark: accumulator released untouched
             } else if constexpr (kStaged) {
-                // TMEM -> registers -> bias/activation -> bf16 -> swizzled smem tile -> TMA store (coalesced, async)
+                // TMEM -> registers -> bias/activation -> bf16 -> swizzled smem tile -> TMA store (coalesced, async).
+                // The tcgen05.ld of chunk c+1 is in flight while chunk c is processed; the accumulator is released as soon
+                // as the last load has landed, before the math and stores of the last chunk.
                 constexpr int kChunks = kColsPerHalf / kEpiChunkCols;
-#pragma unroll 1
+                constexpr int kBufs = Cfg::kEpiBufs;
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(taddr0, va);
+#pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
-                    uint32_t v[32];
-                    tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
+                    uint32_t(&v)[32] = (c & 1) ? vb : va;
                     tmem_ld_wait();
+                    if (c + 1 < kChunks) {
+                        tmem_ld_32x32(taddr0 + (c + 1) * kEpiChunkCols, (c & 1) ? va : vb);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
                     const int col0 = n_blk * BN + half * kColsPerHalf + c * kEpiChunkCols;
                     if (col0 < p.N) {
                         float f[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                         if (p.bias != nullptr) {
-                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 if (col0 + 4 * j < p.N) {
-                                    const float4 b = __ldg(b4 + j);
+                                    const float4 b = bias_in_smem ? *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j)
+                                                                  : __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
                                     f[4 * j + 0] += b.x;
                                     f[4 * j + 1] += b.y;
                                     f[4 * j + 2] += b.z;
@@ -260,7 +293,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                         if (EPI == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
                         // the staging buffer we are about to overwrite must have been read by its previous TMA store
-                        if (lane == 0) bulk_wait_read<1>();
+                        if (lane == 0) bulk_wait_read<kBufs - 1>();
                         __syncwarp();
                         uint8_t* buf = stage_buf + sbuf * kEpiStageBytes;
                         const uint32_t rbase = smem_u32(buf) + lane * 64;
@@ -270,13 +303,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             st_shared_v4(rbase + ((j ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                          pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                         }
-                        fence_proxy_async_smem();
+                        if (!(p.dbg & 32)) fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(p.dbg & 16)) {
                             tma_store_2d(&tmap_c, buf, col0, row0);
                             bulk_commit();
                         }
-                        sbuf ^= 1;
+                        if (++sbuf == kBufs) sbuf = 0;
                     }
                 }
             } else {
@@ -325,11 +358,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             // all tcgen05.ld of this warp have completed (wait::ld above): release the accumulator stage
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            // (the staged path released it right after its last load)
+            if (!kStaged || (p.dbg & 1)) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            if (ew == 0 && lane == 0 && it < 6) KJ_TRACE(5 + 2 * it);  // epilogue of tile `it` done (stores issued)
         }
         if (kStaged && lane == 0) bulk_wait_read<0>();  // smem must stay valid until the last store has read it
+        if (ew == 0 && lane == 0) KJ_TRACE(16);  // stores drained
     }
 
     tc_fence_before();
@@ -338,6 +376,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tc_fence_after();
         tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
+    if (threadIdx.x == 64) KJ_TRACE(17);  // exit
 }
 
 }  // namespace kj

@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for cfg in "X=1" "KJC_BN_I=192" "KJC_NO_PDL=1 KJC_BN_I=192" "KJC_BN_I=128"; do
-  echo "== $cfg"; env $cfg timeout 300 python bench.py --no-index --no-cpu --steps 10 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], {k:v['ms_per_step'] for k,v in d['roofline']['kernels'].items()})"
-done 2>&1 | tee gpurun_out/pdl.txt
+TESTS="test_gpu_encoder" bash scripts/gpu_tests.sh | tail -4
+for cfg in "KJC_LANES=1" "KJC_LANES=2" "KJC_LANES=3" "KJC_LANES=4" "KJC_LANES=2 KJC_MICRO_TOKENS=37888" "KJC_LANES=4 KJC_MICRO_TOKENS=9472"; do
+  echo "== $cfg"; env $cfg timeout 300 python bench.py --no-index --no-cpu --steps 10 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['config']['workload'][-40:])"
+done 2>&1 | tee gpurun_out/lanes.txt
