@@ -203,7 +203,7 @@ int kjc_index_search_device_async(KjcIndex* idx, const float* d_queries, int nq,
 int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const float* d_cand_scores, int n_lists, int nq, int k,
                                 uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, void* stream);
 int64_t kjc_index_last_launch_count(const KjcIndex* idx);
-/* Query batches of >= 9 queries (k <= 16, dim a multiple of 64 and <= 384) run as a tensor-core similarity GEMM over a
+/* Searches with k <= 16 on shards whose dim is a multiple of 64 and <= 384 run as a tensor-core similarity GEMM over a
  * bf16 shadow of the shard that only FILTERS 32 candidates per query; the candidates are re-scored in exact fp32 and a
  * per-query bound proves the exact top-k (see kjarni_b200/csrc/scan_gemm.cuh).  A query whose bound does not hold is re-run
  * on the exact scan by kjc_index_search (which may synchronise); kjc_index_search_device_async cannot synchronise and

@@ -20,7 +20,7 @@ int kjc_dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int fl
 /* ctx[B*S,H] = attention(qkv[B*S,3H], mask[B,S]) with the fused kernel. */
 int kjc_dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16);
 /* Index filter knobs: `eps` = proof margin on |approximate - exact cosine| (default 0.0045; a huge value forces every
- * query through the exact re-run), `min_queries` = smallest batch that takes the tensor-core filter path (default 9). */
+ * query through the exact re-run), `min_queries` = smallest batch that takes the tensor-core filter path (default 1; a huge value forces the exact scan). */
 struct KjcIndex;
 int kjc_dbg_index_set_filter(struct KjcIndex* idx, float eps, int min_queries);
 /* logits[B,C] = classification head of `enc` applied to caller-supplied fp32 hidden states [B,S,H]. */

@@ -215,7 +215,7 @@ class IndexShard:
         """Queries of async searches whose tensor-core filter result could not be proven exact (see kjarni_cuda.h)."""
         return int(N.lib().kjc_index_unverified_count(self._h))
 
-    def set_filter(self, eps: float = 0.0045, min_queries: int = 9) -> None:
+    def set_filter(self, eps: float = 0.0045, min_queries: int = 1) -> None:
         """Test hook (kjarni_cuda_debug.h): proof margin and smallest batch that takes the tensor-core filter path."""
         N.check(N.lib().kjc_dbg_index_set_filter(self._h, float(eps), int(min_queries)))
 

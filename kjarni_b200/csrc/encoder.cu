@@ -93,7 +93,7 @@ static void launch_gemm_inst(const CUtensorMap& ta, const CUtensorMap& tb, const
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int n_tiles = (p.N + BN - 1) / BN;
     const int grid = std::min(m_tiles * n_tiles, num_sms);
-    launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, ta, tb, tc, p);
+    launch_pdl(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, ta, tb, tc, p);
 }
 
 template <int BN>
@@ -129,7 +129,7 @@ static void launch_gemm_pair_inst(const CUtensorMap& ta, const CUtensorMap& tb_h
     ensure_smem_attr(kern, Cfg::kSmemBytes, configured);
     const int m_tiles = (p.M + 2 * kGemmBlockM - 1) / (2 * kGemmBlockM);
     const int grid = 2 * std::min(m_tiles, num_sms / 2);
-    launch_pdl(kern, dim3(grid), dim3(kPairThreads), Cfg::kSmemBytes, st, ta, tb_half, tc, p);
+    launch_pdl(kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, ta, tb_half, tc, p);
 }
 
 void launch_gemm_pair(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p,
@@ -505,6 +505,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     fused_ln_ = (H == kLnN) && !getenv("KJC_NO_FUSED_LN");
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
+    lanes_ = 1;  // measured: no gain from concurrent lanes (the kernels are epilogue-issue-bound, not launch-latency-bound)
     if (const char* e = getenv("KJC_LANES")) lanes_ = std::min(8, std::max(1, atoi(e)));
     ws_.resize(lanes_);
     for (Workspace& w : ws_) {
@@ -563,8 +564,13 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     w.t_x16 = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
     w.t_ctx16 = make_tmap_2d(w.ctx16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
     w.t_h16 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
-    w.t_qkv16_out = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
-    w.t_h16_out = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
+    // store boxes: 192-column tiles store 32 x 64 parts (128B swizzle), the other widths 32 x 32 chunks (64B swizzle)
+    w.t_qkv16_out = bn_qkv_ == 192 ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128)
+                                   : make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
+    w.t_qkv16_out32 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);  // CTA-pair kernel
+    w.t_h16_out32 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
+    w.t_h16_out = bn_i_ == 192 ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
+                               : make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
     w.t_x16_io = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
     w.tokens = static_cast<int>(T);
 }
@@ -592,7 +598,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
         g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = 3 * H; g.act = ACT_NONE;
         prof_begin(KJC_K_GEMM_QKV, st);
-        if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, w.t_qkv16_out, g, sms, st);
+        if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, (bn_qkv_ == 192 ? w.t_qkv16_out : w.t_qkv16_out32), g, sms, st);
         else launch_gemm(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv, w.t_qkv16_out, g, sms, st);
         prof_end(st);
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
@@ -624,7 +630,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         g = GemmParams{};
         g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = w.h16; g.ldo = I; g.act = act_;
         prof_begin(KJC_K_GEMM_FFN_UP, st);
-        if (pair_gemm_) launch_gemm_pair(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1_half, w.t_h16_out, g, sms, st);
+        if (pair_gemm_) launch_gemm_pair(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1_half, (bn_i_ == 192 ? w.t_h16_out : w.t_h16_out32), g, sms, st);
         else launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1, w.t_h16_out, g, sms, st);
         prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
@@ -902,7 +908,8 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act;
         CUtensorMap tc = ta;
-        if (!f32out) tc = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
+        if (!f32out) tc = (bn == 192) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, 64, 128)
+                                               : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
         if (pair) {
             CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
             launch_gemm_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
@@ -986,7 +993,8 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
     CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK, 128);
     CUtensorMap tc = ta;
-    if (!f32out) tc = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, kEpiChunkCols, 64);
+    if (!f32out) tc = (bn == 192) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, 64, 128)
+                                           : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, kEpiChunkCols, 64);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act; p.dbg = flags & ~8;
     cudaEvent_t e0, e1;

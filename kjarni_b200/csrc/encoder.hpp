@@ -103,6 +103,7 @@ class Encoder {
         __nv_bfloat16 *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr;
         CUtensorMap t_x16, t_ctx16, t_h16;   // A-operand loads
         CUtensorMap t_qkv16_out, t_h16_out;  // epilogue TMA stores
+        CUtensorMap t_qkv16_out32, t_h16_out32;  // 32-column store boxes (CTA-pair kernel)
         CUtensorMap t_x16_io;                // residual load + LayerNorm output store of the fused kernel
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;

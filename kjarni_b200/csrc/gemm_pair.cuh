@@ -23,21 +23,30 @@
 namespace kj {
 
 constexpr int kPairMaxKB = 6;  // K <= 384
-constexpr int kPairThreads = 384;
 
 template <int BN>
 struct PairCfg {
-    static constexpr int kStages = 6;
+    static constexpr int kStages = 5;
     static constexpr int kABlockBytes = kGemmBlockM * kGemmBlockK * 2;  // 16 KB per k-block, resident
     static constexpr int kABytes = kPairMaxKB * kABlockBytes;           // 96 KB
     static constexpr int kBBytes = (BN / 2) * kGemmBlockK * 2;          // this CTA's half of a weight k-block
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kEpiBytes = kEpiWarps * 2 * kEpiStageBytes;    // 32 KB
-    static constexpr int kSmemBytes = kABytes + kStages * kBBytes + kEpiBytes + 256;
+    // epilogue geometry as in GemmCfg: 192-column tiles -> 12 warps, each stages a 32 x 64 part and issues one TMA store per tile
+    static constexpr int kParts = (BN == 192) ? 3 : 2;
+    static constexpr int kEpiWarpsN = 4 * kParts;
+    static constexpr int kThreads = 128 + 32 * kEpiWarpsN;
+    static constexpr int kColsPerPart = BN / kParts;
+    static constexpr int kStoreCols = (BN == 192) ? 64 : kEpiChunkCols;
+    static constexpr int kEpiBufs = (BN == 192) ? 1 : 2;
+    static constexpr int kEpiBufBytes = 32 * kStoreCols * 2;
+    static constexpr int kEpiBytes = kEpiWarpsN * kEpiBufs * kEpiBufBytes;
+    static constexpr int kBiasBytes = kEpiBiasMax * 4;
+    static constexpr int kSmemBytes = kABytes + kStages * kBBytes + kEpiBytes + 256 + kBiasBytes;
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<BN>::kThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
     using Cfg = PairCfg<BN>;
@@ -58,9 +67,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* tmem_full = a_empty + kPairMaxKB;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;             // [2]        (leader's are used)
     uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    const bool bias_in_smem = p.bias != nullptr && p.N <= kEpiBiasMax;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (bias_in_smem)  // a weight: staged before pdl_wait()
+        for (int i = threadIdx.x; i < p.N; i += Cfg::kThreads) s_bias[i] = __ldg(p.bias + i);
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = static_cast<int>(cluster_id_x());
@@ -86,7 +99,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // the epilogue warps of both CTAs
+            mbar_init(&tmem_empty[i], 2 * Cfg::kEpiWarpsN);  // the epilogue warps of both CTAs
         }
         fence_mbar_init();
     }
@@ -159,12 +172,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp >= kGemmEpiWarp0) {
         // ---------------------------------------------------------- epilogue
-        const int ew = warp - kGemmEpiWarp0;  // 0..7
+        const int ew = warp - kGemmEpiWarp0;
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;             // column half handled by this warpgroup
-        constexpr int kColsPerHalf = BN / 2;
-        constexpr int kChunks = kColsPerHalf / kEpiChunkCols;
-        uint8_t* stage_buf = smem_epi + ew * 2 * kEpiStageBytes;
+        const int part = ew >> 2;             // column part handled by this warpgroup
+        constexpr int kColsPerPart = Cfg::kColsPerPart;
+        uint8_t* stage_buf = smem_epi + ew * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
         const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty[0]), 0);
         const uint32_t leader_empty1 = mapa_shared(smem_u32(&tmem_empty[1]), 0);
         int sbuf = 0, it = 0;
@@ -174,34 +186,55 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int acc = it & 1;
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * kColsPerHalf;
-#pragma unroll 1
+                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * kColsPerPart;
+                const int colp = nb * BN + part * kColsPerPart;
+                constexpr int kChunks = kColsPerPart / 32;
+                if constexpr (Cfg::kStoreCols == 64) {
+                    if (lane == 0) bulk_wait_read<0>();  // the previous tile's store has read the staging tile
+                    __syncwarp();
+                }
+#pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
                     uint32_t v[32];
-                    tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
+                    tmem_ld_32x32(taddr0 + c * 32, v);
                     tmem_ld_wait();
-                    const int col0 = nb * BN + half * kColsPerHalf + c * kEpiChunkCols;
-                    if (col0 < p.N) {
-                        float f[32];
+                    if (c + 1 == kChunks) {  // last load landed: release the accumulator (on the leader's barrier)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
+                    }
+                    const int col0 = colp + c * 32;
+                    float f[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                        if (p.bias != nullptr) {
-                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias != nullptr) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                if (col0 + 4 * j < p.N) {
-                                    const float4 b = __ldg(b4 + j);
-                                    f[4 * j + 0] += b.x;
-                                    f[4 * j + 1] += b.y;
-                                    f[4 * j + 2] += b.z;
-                                    f[4 * j + 3] += b.w;
-                                }
+                        for (int j = 0; j < 8; ++j) {
+                            if (col0 + 4 * j < p.N) {
+                                float4 b;
+                                if (bias_in_smem) b = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j);
+                                else b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                                f[4 * j + 0] += b.x;
+                                f[4 * j + 1] += b.y;
+                                f[4 * j + 2] += b.z;
+                                f[4 * j + 3] += b.w;
                             }
                         }
-                        if (EPI == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
-                        if (lane == 0) bulk_wait_read<1>();  // the staging buffer's previous TMA store has read it
+                    }
+                    if (EPI == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
+                    if constexpr (Cfg::kStoreCols == 64) {
+                        const uint32_t rbase = smem_u32(stage_buf) + lane * 128;
+                        const uint32_t sw = lane & 7;  // 128B swizzle
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            st_shared_v4(rbase + ((static_cast<uint32_t>(c * 4 + j) ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]),
+                                         pack_bf16(f[8 * j + 2], f[8 * j + 3]), pack_bf16(f[8 * j + 4], f[8 * j + 5]),
+                                         pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        }
+                    } else if (col0 < p.N) {
+                        if (lane == 0) bulk_wait_read<1>();
                         __syncwarp();
-                        uint8_t* buf = stage_buf + sbuf * kEpiStageBytes;
+                        uint8_t* buf = stage_buf + sbuf * Cfg::kEpiBufBytes;
                         const uint32_t rbase = smem_u32(buf) + lane * 64;
                         const uint32_t sw = (lane >> 1) & 3;  // 64B swizzle
 #pragma unroll
@@ -218,9 +251,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         sbuf ^= 1;
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
+                if constexpr (Cfg::kStoreCols == 64) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && colp < p.N) {
+                        tma_store_2d(&tmap_c, stage_buf, colp, row0);
+                        bulk_commit();
+                    }
+                }
             }
         }
         if (lane == 0) bulk_wait_read<0>();

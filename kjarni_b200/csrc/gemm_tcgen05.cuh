@@ -61,8 +61,18 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    static constexpr int kEpiBufs = (BN <= 192) ? 3 : 2;              // store staging ring per epilogue warp
-    static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiStageBytes;
+    // epilogue warps: 4 TMEM lane quadrants x kParts column parts.  192-column tiles use 3 parts of 64 columns (12 warps, 3 per
+    // scheduler: the epilogue is issue/latency-bound, more resident warps hide its waits); the other widths use 2 parts.
+    static constexpr int kParts = (BN == 192) ? 3 : 2;
+    static constexpr int kEpiWarpsN = 4 * kParts;
+    static constexpr int kThreads = 128 + 32 * kEpiWarpsN;
+    static constexpr int kColsPerPart = BN / kParts;
+    // output staging per epilogue warp: 192-column tiles stage the warp's whole 32 x 64 part (4 KB, 128-byte rows, one TMA store
+    // per tile: the TMA store path is charged per row segment, 128-byte segments halve its load); others 2 x (32 x 32) chunks
+    static constexpr int kStoreCols = (BN == 192) ? 64 : kEpiChunkCols;
+    static constexpr int kEpiBufs = (BN == 192) ? 1 : 2;
+    static constexpr int kEpiBufBytes = 32 * kStoreCols * 2;
+    static constexpr int kEpiBytes = kEpiWarpsN * kEpiBufs * kEpiBufBytes;
     static constexpr int kBiasBytes = (BN <= 192) ? kEpiBiasMax * 4 : 0;  // bias staged in smem where it fits
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
@@ -113,7 +123,7 @@ __device__ __forceinline__ void apply_act_tile(float (&f)[NELEM], int act) {
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -139,7 +149,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lane = threadIdx.x & 31;
     // the bias is a weight: it does not depend on the predecessor kernel, so it is staged before pdl_wait()
     if (bias_in_smem)
-        for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = __ldg(p.bias + i);
+        for (int i = threadIdx.x; i < p.N; i += Cfg::kThreads) s_bias[i] = __ldg(p.bias + i);
 
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int n_tiles = (p.N + BN - 1) / BN;
@@ -158,7 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], Cfg::kEpiWarpsN);  // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -233,12 +243,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp >= kGemmEpiWarp0) {
         // ---------------------------------------------------------- epilogue
-        const int ew = warp - kGemmEpiWarp0;  // 0..7
+        const int ew = warp - kGemmEpiWarp0;  // 0 .. kEpiWarpsN-1
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;             // column half handled by this warpgroup
-        constexpr int kColsPerHalf = BN / 2;
+        const int half = ew >> 2;             // column part handled by this warpgroup
+        constexpr int kColsPerHalf = Cfg::kColsPerPart;
         constexpr bool kStaged = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16);
-        uint8_t* stage_buf = smem_epi + ew * Cfg::kEpiBufs * kEpiStageBytes;
+        uint8_t* stage_buf = smem_epi + ew * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
         int sbuf = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -254,21 +264,70 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + half * kColsPerHalf;
             if (p.dbg & 1) {
                 // microbenchmark: accumulator released untouched
+            } else if constexpr (kStaged && Cfg::kStoreCols == 64) {
+                // 192-column tiles: this warp owns a 32-row x 64-column part.  TMEM -> registers -> bias/activation -> bf16 ->
+                // 128B-swizzled 4 KB smem tile -> ONE TMA store per tile.  The accumulator is released as soon as the last
+                // tcgen05.ld has landed.
+                static_assert(kColsPerHalf == 64, "part width");
+                const int colp = n_blk * BN + half * kColsPerHalf;
+                if (lane == 0) bulk_wait_read<0>();  // the previous tile's store has read the staging tile
+                __syncwarp();
+                const uint32_t rbase = smem_u32(stage_buf) + lane * 128;
+                const uint32_t sw = lane & 7;  // 128B swizzle: 16-byte chunk index ^= row & 7
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr0 + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    }
+                    const int col0 = colp + c * 32;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (col0 + 4 * j < p.N) {
+                                float4 b;
+                                if (bias_in_smem) b = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j);
+                                else b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
+                                f[4 * j + 0] += b.x;
+                                f[4 * j + 1] += b.y;
+                                f[4 * j + 2] += b.z;
+                                f[4 * j + 3] += b.w;
+                            }
+                        }
+                    }
+                    if (EPI == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        st_shared_v4(rbase + ((static_cast<uint32_t>(c * 4 + j) ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]),
+                                     pack_bf16(f[8 * j + 2], f[8 * j + 3]), pack_bf16(f[8 * j + 4], f[8 * j + 5]),
+                                     pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                    }
+                }
+                if (!(p.dbg & 32)) fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && colp < p.N && !(p.dbg & 16)) {  // columns >= N are clipped by the tensor map
+                    tma_store_2d(&tmap_c, stage_buf, colp, row0);
+                    bulk_commit();
+                }
             } else if constexpr (kStaged) {
                 // TMEM -> registers -> bias/activation -> bf16 -> swizzled smem tile -> TMA store (coalesced, async).
                 // The tcgen05.ld of chunk c+1 is in flight while chunk c is processed; the accumulator is released as soon
                 // as the last load has landed, before the math and stores of the last chunk.
                 constexpr int kChunks = kColsPerHalf / kEpiChunkCols;
                 constexpr int kBufs = Cfg::kEpiBufs;
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(taddr0, va);
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
-                    uint32_t(&v)[32] = (c & 1) ? vb : va;
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
                     tmem_ld_wait();
-                    if (c + 1 < kChunks) {
-                        tmem_ld_32x32(taddr0 + (c + 1) * kEpiChunkCols, (c & 1) ? va : vb);
-                    } else {
+                    if (c + 1 == kChunks) {  // last load landed: release the accumulator before the math and stores of this chunk
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&tmem_empty[acc]);

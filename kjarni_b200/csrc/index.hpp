@@ -56,7 +56,7 @@ class Index {
     // tensor-core filter path (scan_gemm.cuh): bf16 shadow of the rows, 1/|r|, staging for query tiles and candidates
     bool gemm_ok_ = false;
     float filter_eps_ = 0.0045f;
-    int filter_min_q_ = 9;
+    int filter_min_q_ = 1;  // the filter pass reads half the bytes of the exact scan, so it wins from a single query on
     __nv_bfloat16 *rows16_ = nullptr, *d_q16_ = nullptr;
     float *d_gc_s_ = nullptr, *d_am_s_ = nullptr, *d_fix_q_ = nullptr, *d_fix_s_ = nullptr;
     uint32_t* d_gc_i_ = nullptr;

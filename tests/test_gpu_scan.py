@@ -31,12 +31,14 @@ def test_search_matches_oracle(n, dim, nq, k):
     sh = api.IndexShard(dim, n, id_base=1000)
     sh.add_rows(rows)
     assert len(sh) == n
-    ids, sc, cnt = sh.search_batch(q, k)
     wi, ws = ko.batched_topk(rows, q, k, row_offset=1000)
     kk = min(k, n)
-    assert (cnt == kk).all()
-    check_topk(ids[:, :kk], sc[:, :kk], wi[:, :kk], ws[:, :kk])
-    assert (ids[:, kk:] == np.uint64(N.NO_ID)).all() and np.isneginf(sc[:, kk:]).all()
+    for min_q in (1, 1 << 30):  # default dispatch (tensor-core filter where it applies), then the exact scan kernel alone
+        sh.set_filter(min_queries=min_q)
+        ids, sc, cnt = sh.search_batch(q, k)
+        assert (cnt == kk).all()
+        check_topk(ids[:, :kk], sc[:, :kk], wi[:, :kk], ws[:, :kk])
+        assert (ids[:, kk:] == np.uint64(N.NO_ID)).all() and np.isneginf(sc[:, kk:]).all()
     sh.close()
 
 
@@ -152,7 +154,7 @@ def test_gemm_filter_matches_oracle_and_exact_path(n, dim, nq, k):
     sh.add_rows(rows)
     sh.add_rows(np.stack([rows[n // 3], np.zeros(dim, np.float32), rows[n // 3] * 0.5]))  # duplicates (ties -> lower id) + a zero row
     allrows = np.concatenate([rows, rows[n // 3][None], np.zeros((1, dim), np.float32), rows[n // 3][None] * 0.5])
-    ids, sc, cnt = sh.search_batch(q, k)  # nq >= 9: filter path
+    ids, sc, cnt = sh.search_batch(q, k)  # filter path
     wi, ws = ko.batched_topk(allrows, q, k, row_offset=500)
     kk = min(k, n + 3)
     assert (cnt == kk).all()
@@ -162,7 +164,7 @@ def test_gemm_filter_matches_oracle_and_exact_path(n, dim, nq, k):
     ids2, sc2, cnt2 = sh.search_batch(q, k)
     assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2) and np.array_equal(cnt, cnt2)
     # forcing the proof to fail sends every query through the exact re-run: same answer again
-    sh.set_filter(eps=10.0, min_queries=9)
+    sh.set_filter(eps=10.0, min_queries=1)
     ids3, sc3, cnt3 = sh.search_batch(q, k)
     assert np.array_equal(ids, ids3) and np.array_equal(sc, sc3) and np.array_equal(cnt, cnt3)
     sh.close()
