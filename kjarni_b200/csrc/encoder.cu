@@ -153,7 +153,7 @@ void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensor
     GemmLnParams p;
     p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
-    launch_pdl(gemm_ln384_kernel, dim3(std::min(m_tiles, num_sms)), dim3(kGemmThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
+    launch_pdl(gemm_ln384_kernel, dim3(std::min(m_tiles, num_sms)), dim3(kLnThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
 }
 
 // ------------------------------------------------------------ row-kernel launch

@@ -6,11 +6,14 @@
 // (cpu/normalization/layer_norm.rs:37-134: per-row mean, biased variance, eps inside the sqrt).
 //
 // One CTA owns full rows: tile 128 x 384, fp32 accumulators in 384 TMEM columns (two 128x192x16 tcgen05.mma per
-// k-step), so the row statistics never leave the SM.  Epilogue (8 warps, thread = row, 2 column halves):
-//   pass 1  v = acc + bias + residual (residual tile TMA-loaded into swizzled smem), row sum; v written back to TMEM
-//   pass 2  sum of (v - mean)^2   (exact two-pass variance, as the reference)
-//   pass 3  (v - mean) * rstd * gamma + beta -> bf16 -> swizzled smem -> TMA store
-// The residual may alias the output (in place): every warp reads its whole region before it writes it.
+// k-step), so the row statistics never leave the SM.  Epilogue: 12 warps = 4 TMEM lane quadrants x 3 column parts of 128,
+// thread = row (the epilogue is issue/latency-bound, so it gets three warps per scheduler), two passes:
+//   pass A  v = acc + bias + residual (residual chunks TMA-loaded into swizzled smem), row sum and sum of squares;
+//           v written back to TMEM
+//   pass B  (v - mean) * rstd * gamma + beta -> bf16 -> swizzled smem -> TMA store
+// Variance = E[v^2] - mean^2 in fp32 (clamped at 0): with |mean| <~ 10 sigma its rounding error is ~1e-5 relative,
+// far below the bf16 rounding of the output.  The residual may alias the output (in place): every warp reads its whole
+// region before it writes it.  bias / gamma / beta are staged in shared memory before griddepcontrol.wait.
 #pragma once
 #include <cuda.h>
 
@@ -20,13 +23,19 @@ namespace kj {
 
 constexpr int kLnN = 384;
 constexpr int kLnHalfN = 192;
-constexpr int kLnStages = 3;
+constexpr int kLnStages = 2;
+constexpr int kLnParts = 3;                                // column parts per lane quadrant
+constexpr int kLnPartCols = kLnN / kLnParts;               // 128
+constexpr int kLnEpiWarps = 4 * kLnParts;                  // 12
+constexpr int kLnThreads = 128 + 32 * kLnEpiWarps;         // 512
 constexpr int kLnABytes = kGemmBlockM * kGemmBlockK * 2;   // 16 KB
 constexpr int kLnBBytes = kLnN * kGemmBlockK * 2;          // 48 KB (two TMA boxes of 192 rows)
 constexpr int kLnStageBytes = kLnABytes + kLnBBytes;       // 64 KB
 constexpr int kLnEpiBytesPerWarp = 2 * kEpiStageBytes;     // 2 x 2 KB: residual double buffer, then store double buffer
-constexpr int kLnStatBytes = 2 * 2 * 128 * 4;              // [pass][half][row] partial sums
-constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + kEpiWarps * kLnEpiBytesPerWarp + kLnStatBytes + 256;  // 231,680 B of the 232,448 B limit
+constexpr int kLnStatBytes = kLnParts * 128 * 8;           // [part][row] (sum, sum of squares)
+constexpr int kLnVecBytes = 3 * kLnN * 4;                  // bias | gamma | beta
+constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + kLnEpiWarps * kLnEpiBytesPerWarp + kLnStatBytes + kLnVecBytes + 512;
+static_assert(kLnSmemBytes <= 232448, "shared memory budget");
 
 struct GemmLnParams {
     int M, K;
@@ -36,29 +45,38 @@ struct GemmLnParams {
     float eps;
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kLnThreads, 1)
 gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out, GemmLnParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_ln[];  // no slack left for manual alignment: checked below
+    extern __shared__ __align__(1024) uint8_t smem_ln[];
     uint8_t* smem = smem_ln;
     if (smem_u32(smem) & 1023) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kLnStages * kLnABytes;
     uint8_t* smem_epi = smem + kLnStages * kLnStageBytes;
-    float* stat = reinterpret_cast<float*>(smem_epi + kEpiWarps * kLnEpiBytesPerWarp);  // [2][2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stat) + kLnStatBytes);
+    float2* stat = reinterpret_cast<float2*>(smem_epi + kLnEpiWarps * kLnEpiBytesPerWarp);  // [3][128]
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stat) + kLnStatBytes);
+    float* s_gamma = s_bias + kLnN;
+    float* s_beta = s_gamma + kLnN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + kLnN);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kLnStages;
     uint64_t* tmem_full = bars + 2 * kLnStages;
     uint64_t* tmem_empty = bars + 2 * kLnStages + 1;
-    uint64_t* res_bar = bars + 2 * kLnStages + 2;  // [8 warps][2 buffers]
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+    uint64_t* res_bar = bars + 2 * kLnStages + 2;  // [12 warps][2 buffers]
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * kLnEpiWarps);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int k_blocks = (p.K + kGemmBlockK - 1) / kGemmBlockK;
 
+    // weights: independent of the predecessor kernel, staged before griddepcontrol.wait
+    for (int i = threadIdx.x; i < kLnN; i += kLnThreads) {
+        s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
+        s_gamma[i] = __ldg(p.gamma + i);
+        s_beta[i] = __ldg(p.beta + i);
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
@@ -71,8 +89,8 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, kEpiWarps);
-        for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+        mbar_init(tmem_empty, kLnEpiWarps);
+        for (int i = 0; i < 2 * kLnEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_base_smem);
@@ -134,10 +152,10 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
     } else if (warp >= kGemmEpiWarp0) {
         // ---------------------------------------------------------- epilogue
-        const int ew = warp - kGemmEpiWarp0;
+        const int ew = warp - kGemmEpiWarp0;  // 0..11
         const int quad = warp & 3;
-        const int half = ew >> 2;
-        constexpr int kChunks = kLnHalfN / kEpiChunkCols;  // 6
+        const int part = ew >> 2;             // column part [part*128, part*128 + 128)
+        constexpr int kChunks = kLnPartCols / kEpiChunkCols;  // 4
         uint8_t* ebuf = smem_epi + ew * kLnEpiBytesPerWarp;
         uint64_t* rbar = res_bar + 2 * ew;
         const uint32_t sw = (lane >> 1) & 3;  // 64B swizzle of this lane's row
@@ -146,7 +164,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         int it = 0;
         for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
             const int row0 = tile * kGemmBlockM + quad * 32;
-            const int col_base = half * kLnHalfN;
+            const int col_base = part * kLnPartCols;
             // the store staging of the previous tile aliases the residual buffers: wait until TMA has read it
             if (lane == 0) {
                 bulk_wait_read<0>();
@@ -161,8 +179,8 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             tc_fence_after();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
 
-            // ---- pass 1: v = acc + bias + residual ; row sum ; v -> TMEM
-            float sum = 0.0f;
+            // ---- pass A: v = acc + bias + residual ; row sum and sum of squares ; v -> TMEM
+            float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c) {
                 const int b = c & 1;
@@ -175,21 +193,21 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
                 for (int j = 0; j < 4; ++j) r4[j] = ld_shared_v4(rbase + ((j ^ sw) << 4));
                 tmem_ld_wait();
-                const int col0 = col_base + c * kEpiChunkCols;
+                const float* bs = s_bias + col_base + c * kEpiChunkCols;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
+                    const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-                        float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo;
-                        float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi;
-                        if (p.bias != nullptr) {
-                            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + 8 * j + 2 * e));
-                            a0 += bb.x;
-                            a1 += bb.y;
-                        }
-                        sum += a0 + a1;
+                        const float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo + bb[2 * e];
+                        const float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi + bb[2 * e + 1];
+                        s1 += a0 + a1;
+                        s2 = fmaf(a0, a0, s2);
+                        s2 = fmaf(a1, a1, s2);
                         v[8 * j + 2 * e] = __float_as_uint(a0);
                         v[8 * j + 2 * e + 1] = __float_as_uint(a1);
                     }
@@ -202,45 +220,42 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
             }
             tmem_st_wait();
-            stat[(0 * 2 + half) * 128 + trow] = sum;
-            named_bar_sync(1, kEpiWarps * 32);
-            const float mean = (stat[(0 * 2 + 0) * 128 + trow] + stat[(0 * 2 + 1) * 128 + trow]) * (1.0f / kLnN);
-
-            // ---- pass 2: sum of squared deviations
-            float sq = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
-                tmem_ld_wait();
+            stat[part * 128 + trow] = make_float2(s1, s2);
+            named_bar_sync(1, kLnEpiWarps * 32);
+            float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float d = __uint_as_float(v[j]) - mean;
-                    sq = fmaf(d, d, sq);
-                }
+            for (int q = 0; q < kLnParts; ++q) {
+                const float2 t = stat[q * 128 + trow];
+                t1 += t.x;
+                t2 += t.y;
             }
-            stat[(1 * 2 + half) * 128 + trow] = sq;
-            named_bar_sync(1, kEpiWarps * 32);
-            const float var = (stat[(1 * 2 + 0) * 128 + trow] + stat[(1 * 2 + 1) * 128 + trow]) * (1.0f / kLnN);
+            const float mean = t1 * (1.0f / kLnN);
+            const float var = fmaxf(t2 * (1.0f / kLnN) - mean * mean, 0.0f);
             const float rstd = 1.0f / sqrtf(var + p.eps);
+            const float nmr = -mean * rstd;
 
-            // ---- pass 3: normalise, bf16, swizzled smem, TMA store
+            // ---- pass B: normalise, bf16, swizzled smem, TMA store
             int sbuf = 0;
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
                 tmem_ld_wait();
+                if (c + 1 == kChunks) {  // accumulator fully consumed: the MMA warp may start the next tile
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
                 const int col0 = col_base + c * kEpiChunkCols;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col0) + j);
-                    const float4 bt = __ldg(reinterpret_cast<const float4*>(p.beta + col0) + j);
-                    f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) - mean) * rstd * g.x + bt.x;
-                    f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) - mean) * rstd * g.y + bt.y;
-                    f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) - mean) * rstd * g.z + bt.z;
-                    f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) - mean) * rstd * g.w + bt.w;
+                    const float4 g = *reinterpret_cast<const float4*>(s_gamma + col0 + 4 * j);
+                    const float4 bt = *reinterpret_cast<const float4*>(s_beta + col0 + 4 * j);
+                    f[4 * j + 0] = fmaf(fmaf(__uint_as_float(v[4 * j + 0]), rstd, nmr), g.x, bt.x);
+                    f[4 * j + 1] = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr), g.y, bt.y);
+                    f[4 * j + 2] = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr), g.z, bt.z);
+                    f[4 * j + 3] = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr), g.w, bt.w);
                 }
                 if (lane == 0) bulk_wait_read<1>();
                 __syncwarp();
@@ -259,12 +274,8 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 sbuf ^= 1;
             }
-            // accumulator fully consumed: the MMA warp may start the next tile
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty);
-            // the second stat exchange of this tile and the first of the next use different slots; a slow warp still
-            // reading stat[1] cannot be overtaken by a write to stat[1] (that needs two more barriers), so no extra sync.
+            // the stat exchange of the next tile happens after its tmem_full wait, i.e. after every warp of this tile has
+            // passed the barrier above and read stat[]: no extra sync is needed before stat[] is overwritten.
         }
         if (lane == 0) bulk_wait_read<0>();
     }
