@@ -565,11 +565,11 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     w.t_ctx16 = make_tmap_2d(w.ctx16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
     w.t_h16 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
     // store boxes: 192-column tiles store 32 x 64 parts (128B swizzle), the other widths 32 x 32 chunks (64B swizzle)
-    w.t_qkv16_out = bn_qkv_ == 192 ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128)
+    w.t_qkv16_out = (bn_qkv_ == 192 && (kGemm192WideStore || pair_gemm_)) ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128)
                                    : make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
     w.t_qkv16_out32 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);  // CTA-pair kernel
     w.t_h16_out32 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
-    w.t_h16_out = bn_i_ == 192 ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
+    w.t_h16_out = (bn_i_ == 192 && (kGemm192WideStore || pair_gemm_)) ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
                                : make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
     w.t_x16_io = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
     w.tokens = static_cast<int>(T);
@@ -658,7 +658,14 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else if (o.output == KJC_OUT_POOLED) {
-        pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(w.x16, d_mask, d_out, S, H, o.pooling, o.normalize);
+        if (o.pooling == KJC_POOL_MEAN && H <= 1024 && H % 4 == 0) {
+            const size_t smem = static_cast<size_t>(8) * H * sizeof(float);
+            dispatch_nv(H, [&](auto nv) {
+                mean_pool_l2_kernel<decltype(nv)::value><<<nb, 256, smem, st>>>(w.x16, d_mask, d_out, S, H, o.normalize);
+            });
+        } else {
+            pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(w.x16, d_mask, d_out, S, H, o.pooling, o.normalize);
+        }
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else {
@@ -908,7 +915,7 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act;
         CUtensorMap tc = ta;
-        if (!f32out) tc = (bn == 192) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, 64, 128)
+        if (!f32out) tc = (bn == 192 && (kGemm192WideStore || pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, 64, 128)
                                                : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
         if (pair) {
             CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
@@ -993,7 +1000,7 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
     CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK, 128);
     CUtensorMap tc = ta;
-    if (!f32out) tc = (bn == 192) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, 64, 128)
+    if (!f32out) tc = (bn == 192 && (kGemm192WideStore || pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, 64, 128)
                                            : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, kEpiChunkCols, 64);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act; p.dbg = flags & ~8;

@@ -54,6 +54,11 @@ constexpr int kEpiChunkCols = 32;                         // columns per tcgen05
 constexpr int kEpiStageBytes = 32 * kEpiChunkCols * 2;    // one warp's bf16 staging tile: 32 rows x 64 B (64B swizzle)
 constexpr int kEpiBiasMax = 3072;                         // bias columns staged in shared memory (BN <= 192 configurations)
 
+#ifndef KJ_GEMM_PARTS192
+#define KJ_GEMM_PARTS192 3
+#endif
+constexpr bool kGemm192WideStore = KJ_GEMM_PARTS192 == 3;  // host side: 192-column tiles store 32 x 64 boxes (128B swizzle)
+
 template <int BN>
 struct GemmCfg {
     static constexpr int kStages = (BN <= 64) ? 6 : ((BN <= 128) ? 5 : 4);
@@ -63,14 +68,17 @@ struct GemmCfg {
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
     // epilogue warps: 4 TMEM lane quadrants x kParts column parts.  192-column tiles use 3 parts of 64 columns (12 warps, 3 per
     // scheduler: the epilogue is issue/latency-bound, more resident warps hide its waits); the other widths use 2 parts.
-    static constexpr int kParts = (BN == 192) ? 3 : 2;
+#ifndef KJ_GEMM_PARTS192
+#define KJ_GEMM_PARTS192 3
+#endif
+    static constexpr int kParts = (BN == 192) ? KJ_GEMM_PARTS192 : 2;
     static constexpr int kEpiWarpsN = 4 * kParts;
     static constexpr int kThreads = 128 + 32 * kEpiWarpsN;
     static constexpr int kColsPerPart = BN / kParts;
     // output staging per epilogue warp: 192-column tiles stage the warp's whole 32 x 64 part (4 KB, 128-byte rows, one TMA store
     // per tile: the TMA store path is charged per row segment, 128-byte segments halve its load); others 2 x (32 x 32) chunks
-    static constexpr int kStoreCols = (BN == 192) ? 64 : kEpiChunkCols;
-    static constexpr int kEpiBufs = (BN == 192) ? 1 : 2;
+    static constexpr int kStoreCols = (BN == 192 && kParts == 3) ? 64 : kEpiChunkCols;
+    static constexpr int kEpiBufs = (BN == 192 && kParts == 3) ? 1 : ((BN <= 192) ? 3 : 2);
     static constexpr int kEpiBufBytes = 32 * kStoreCols * 2;
     static constexpr int kEpiBytes = kEpiWarpsN * kEpiBufs * kEpiBufBytes;
     static constexpr int kBiasBytes = (BN <= 192) ? kEpiBiasMax * 4 : 0;  // bias staged in smem where it fits

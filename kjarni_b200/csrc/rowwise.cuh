@@ -223,6 +223,82 @@ pool_l2_kernel(const TIn* __restrict__ x, const float* __restrict__ mask, float*
     }
 }
 
+// Masked mean pool + optional L2 normalise, the Embedder's default (reference: pooling/mod.rs:11-34,
+// cpu/encoder/traits.rs:529-536), with the rows of a sequence spread over the 8 warps: warp w sums rows w, w+8, ...
+// with coalesced 8-byte-per-lane loads (many independent loads in flight), partial sums meet in shared memory.
+// One CTA per sequence; H <= 1024 and a multiple of 4.  Same arithmetic as pool_l2_kernel up to summation order.
+template <int NCH>  // float4 column chunks per lane: ceil(H / 128)
+__global__ void __launch_bounds__(256)
+mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int S, int H,
+                    int normalize) {
+    extern __shared__ float s_part[];  // [8][H]
+    __shared__ float s_cnt[8];
+    __shared__ float red[8];
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const __nv_bfloat16* xb = x + static_cast<size_t>(b) * S * H;
+    const float* mb = mask ? mask + static_cast<size_t>(b) * S : nullptr;
+    float4 acc[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cnt = 0.f;
+    for (int s0 = warp; s0 < S; s0 += 8) {
+        const float m = mb ? mb[s0] : 1.0f;
+        cnt += m;
+        if (m != 0.0f) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                const int c = (lane + 32 * i) * 4;
+                if (c < H) {
+                    const float4 t = load4f(xb + static_cast<size_t>(s0) * H + c);
+                    acc[i].x += t.x * m; acc[i].y += t.y * m; acc[i].z += t.z * m; acc[i].w += t.w * m;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (lane + 32 * i) * 4;
+        if (c < H) *reinterpret_cast<float4*>(s_part + warp * H + c) = acc[i];
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    float count = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) count += s_cnt[w];
+    // thread t owns columns 4t .. 4t+3
+    const int c = threadIdx.x * 4;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sq = 0.f;
+    if (c < H) {
+        if (count == 0.0f) {
+            a = load4f(xb + c);  // no valid token: the token-0 row (pooling/mod.rs:24-31)
+        } else {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const float4 t = *reinterpret_cast<const float4*>(s_part + w * H + c);
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+            a.x /= count; a.y /= count; a.z /= count; a.w /= count;
+        }
+        sq = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+    }
+    float scale = 1.0f;
+    if (normalize) {
+        sq = warp_sum(sq);
+        if (lane == 0) red[warp] = sq;
+        __syncthreads();
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += red[i];
+        const float nrm = sqrtf(tot);
+        if (nrm > 0.0f) scale = 1.0f / nrm;
+    }
+    if (c < H) {
+        if (scale != 1.0f) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
+        *reinterpret_cast<float4*>(out + static_cast<size_t>(b) * H + c) = a;
+    }
+}
+
 // Classification head on the CLS row (reference: cpu/encoder/classifier.rs:210-258):
 //   z = x[b,0,:]; if pre: z = act(W_pre z + b_pre) (tanh | relu); logits = W_cls z + b_cls.
 // fp32 weights and math so the argmax stage matches the fp32 oracle bit-for-bit up to summation order.

@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-TESTS="test_gpu_kernels test_gpu_encoder" bash scripts/gpu_tests.sh | tail -6
-python scripts/gemm_micro.py 2>&1 | grep -E "gemm_ln" 
+TESTS="test_gpu_encoder" bash scripts/gpu_tests.sh | tail -4
 timeout 300 python bench.py --no-index --no-cpu --steps 10 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], {k:v['ms_per_step'] for k,v in d['roofline']['kernels'].items()})"
