@@ -294,6 +294,8 @@ def main():
     tf = {"gemm_qkv": 2.0 * M * 3 * H * H * L, "gemm_out": 2.0 * M * H * H * L, "gemm_ffn_up": 2.0 * M * H * I * L,
           "gemm_ffn_down": 2.0 * M * H * I * L, "attention": 4.0 * M * SEQ * H * L}
     gb = {"layernorm": 2.0 * L * M * H * 10, "embed_ln": M * 4.0 + M * H * 4.0 + M * H * 6.0, "output": M * H * 4.0 + B * H * 4.0}
+    if pn[N.KERNEL_CLASSES.index("gemm_ffn_down")] == 0:  # fused feed-forward kernel: up + GELU + down + residual + LayerNorm in one launch
+        tf["gemm_ffn_up"] += tf["gemm_ffn_down"]
     kernels = {}
     tot_ms = sum(pms[i] for i in range(8)) / prof_steps
     for i, name in enumerate(N.KERNEL_CLASSES):

@@ -15,6 +15,10 @@ int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
  * iters > 0 additionally times `iters` launches (average us in *out_us). */
 int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                     const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us);
+/* out[M,384] (bf16) = LayerNorm(x + act(x W1^T + b1) W2^T + b2) with the fused feed-forward kernel; W1 [I,384], W2 [384,I];
+ * iters > 0 additionally times `iters` launches (average us in *out_us). */
+int kjc_dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
+                   const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* out_us);
 /* GEMM microbenchmark: average us per launch. flags: 1 = skip epilogue work, 2 = skip MMA issue, 4 = skip TMA loads. */
 int kjc_dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters, float* out_us);
 /* ctx[B*S,H] = attention(qkv[B*S,3H], mask[B,S]) with the fused kernel. */

@@ -80,6 +80,7 @@ SIGNATURES = {
     "kjc_cosine_similarity": (_f, [_vp, _vp, C.c_size_t]),
     "kjc_dbg_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_gemm_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp]),
+    "kjc_dbg_ffn_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_gemm_time": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_encoder_head": (_i, [_vp, _vp, _i, _i, _vp]),

@@ -220,6 +220,13 @@ int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float*
     return guarded([&] { kj::dbg_gemm_ln(a_bf16, w_bf16, bias, gamma, beta, eps, res_bf16, M, K, out_bf16, iters, out_us); });
 }
 
+int kjc_dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
+                   const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* out_us) {
+    KJC_REQUIRE(x_bf16); KJC_REQUIRE(w1_bf16); KJC_REQUIRE(b1); KJC_REQUIRE(w2_bf16); KJC_REQUIRE(b2); KJC_REQUIRE(gamma); KJC_REQUIRE(beta);
+    KJC_REQUIRE(out_bf16);
+    return guarded([&] { kj::dbg_ffn_ln(x_bf16, w1_bf16, b1, w2_bf16, b2, gamma, beta, eps, M, I, act, out_bf16, iters, out_us); });
+}
+
 int kjc_dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters, float* out_us) {
     KJC_REQUIRE(out_us);
     return guarded([&] { *out_us = kj::dbg_gemm_time(M, N, K, epi, act, block_n, flags, iters); });

@@ -14,6 +14,7 @@
 #include "attention.cuh"
 #include "attention_tc.cuh"
 #include "encoder.hpp"
+#include "ffn_fused.cuh"
 #include "gemm_ln.cuh"
 #include "gemm_pair.cuh"
 #include "gemm_tcgen05.cuh"
@@ -154,6 +155,25 @@ void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensor
     p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
     launch_pdl(gemm_ln384_kernel, dim3(std::min(m_tiles, num_sms)), dim3(kLnThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
+}
+
+void launch_ffn_ln(const CUtensorMap& t_x, const CUtensorMap& t_w1, const CUtensorMap& t_w1_pair, const CUtensorMap& t_w2, int M, int I,
+                   const float* b1, const float* b2, const float* gamma, const float* beta, float eps, int act, int num_sms, cudaStream_t st) {
+    static int configured[64] = {0};
+    if (I % kFfChunk != 0 || I <= 0) throw Error(KJC_INVALID_CONFIG, "fused FFN needs an intermediate size that is a multiple of 64");
+    static int configured2[64] = {0};
+    static const bool pair = getenv("KJC_FFN_NO_PAIR") == nullptr;
+    FfnParams p;
+    p.M = M; p.I = I; p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps; p.act = act;
+    const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    if (pair && m_tiles >= 2 && num_sms >= 2) {  // CTA pairs: tcgen05.mma.cta_group::2, each CTA holds half of every weight tile
+        ensure_smem_attr(ffn_ln384_kernel<true>, kFfSmemBytes, configured2);
+        const int pairs = std::min((m_tiles + 1) / 2, num_sms / 2);
+        launch_pdl_cluster(2, ffn_ln384_kernel<true>, dim3(2 * pairs), dim3(kFfThreads), kFfSmemBytes, st, t_x, t_w1_pair, t_w2, p);
+    } else {
+        ensure_smem_attr(ffn_ln384_kernel<false>, kFfSmemBytes, configured);
+        launch_pdl(ffn_ln384_kernel<false>, dim3(std::min(m_tiles, num_sms)), dim3(kFfThreads), kFfSmemBytes, st, t_x, t_w1, t_w2, p);
+    }
 }
 
 // ------------------------------------------------------------ row-kernel launch
@@ -489,6 +509,11 @@ Encoder::Encoder(const std::string& dir, int device) {
         ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK, 128);
         ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK, 128);
         ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK, 128);
+        if (H == kFfH && I % kFfChunk == 0) {
+            ld.t_w1_ffn = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 64, kGemmBlockK, 128);
+            ld.t_w1_ffn32 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 32, kGemmBlockK, 128);
+            ld.t_w2_ffn = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, 64, kGemmBlockK, 128);
+        }
         if (H <= kPairMaxKB * kGemmBlockK && bn_qkv_ >= 128 && bn_i_ >= 128) {  // CTA-pair kernel: each CTA loads half of a weight tile
             ld.t_wqkv_half = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, bn_qkv_ / 2, kGemmBlockK, 128);
             ld.t_w1_half = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_ / 2, kGemmBlockK, 128);
@@ -503,6 +528,9 @@ Encoder::Encoder(const std::string& dir, int device) {
     }
     // hidden 384: out-proj / FFN-down run as one GEMM + bias + residual + LayerNorm kernel (full rows per CTA)
     fused_ln_ = (H == kLnN) && !getenv("KJC_NO_FUSED_LN");
+    // whole-FFN fusion (ffn_fused.cuh) is correct but shared-memory-bandwidth-bound (the 128 x 384 x tile is re-read for every 64
+    // intermediate columns): 64-75 us per launch against 35 + 33 us for the two-kernel path, so it is opt-in
+    fused_ffn_ = fused_ln_ && I % kFfChunk == 0 && getenv("KJC_FUSED_FFN") != nullptr;
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
     lanes_ = 1;  // measured: no gain from concurrent lanes (the kernels are epilogue-issue-bound, not launch-latency-bound)
@@ -625,6 +653,14 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
             launch_layernorm(w.y32, L.g1, L.be1, eps, nullptr, w.x16, M, H, st);
             prof_end(st);
             ++launches_;
+        }
+        if (fused_ffn_) {
+            // x = LN2(x + act(x W1^T + b1) W2^T + b2) in one kernel      (standard_new.rs:47-80, encoder_layer.rs:150-176)
+            prof_begin(KJC_K_GEMM_FFN_UP, st);
+            launch_ffn_ln(w.t_x16, L.t_w1_ffn, L.t_w1_ffn32, L.t_w2_ffn, M, I, L.b1, L.b2, L.g2, L.be2, eps, act_, sms, st);
+            prof_end(st);
+            launches_ += 4;
+            continue;
         }
         // t = act(x W1^T + b1)                                     (standard_new.rs:47-73)
         g = GemmParams{};
@@ -971,6 +1007,52 @@ void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
     cudaFree(dA); cudaFree(dW); cudaFree(dX); cudaFree(dB); cudaFree(dG); cudaFree(dBt);
+}
+
+// x_out[M,384] (bf16) = LN(x + act(x W1^T + b1) W2^T + b2) with the fused FFN kernel (in place on a device copy of x).
+void dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
+                const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* us) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    KJ_CUDA(cudaGetDevice(&dev));
+    KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const size_t Mp = std::max(M, 128);
+    __nv_bfloat16 *dX, *dW1, *dW2;
+    float *dB1, *dB2, *dG, *dBt;
+    KJ_CUDA(cudaMalloc(&dX, Mp * kFfH * 2));
+    KJ_CUDA(cudaMemset(dX, 0, Mp * kFfH * 2));
+    KJ_CUDA(cudaMalloc(&dW1, static_cast<size_t>(I) * kFfH * 2));
+    KJ_CUDA(cudaMalloc(&dW2, static_cast<size_t>(I) * kFfH * 2));
+    KJ_CUDA(cudaMalloc(&dB1, static_cast<size_t>(I) * 4));
+    KJ_CUDA(cudaMalloc(&dB2, kFfH * 4)); KJ_CUDA(cudaMalloc(&dG, kFfH * 4)); KJ_CUDA(cudaMalloc(&dBt, kFfH * 4));
+    KJ_CUDA(cudaMemcpy(dX, x_bf16, static_cast<size_t>(M) * kFfH * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dW1, w1_bf16, static_cast<size_t>(I) * kFfH * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dW2, w2_bf16, static_cast<size_t>(I) * kFfH * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dB1, b1, static_cast<size_t>(I) * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dB2, b2, kFfH * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dG, gamma, kFfH * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dBt, beta, kFfH * 4, cudaMemcpyHostToDevice));
+    CUtensorMap tx = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, kFfH, kGemmBlockM, kGemmBlockK, 128);
+    CUtensorMap t1 = make_tmap_2d(dW1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, kFfH, 64, kGemmBlockK, 128);
+    CUtensorMap t1p = make_tmap_2d(dW1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, kFfH, 32, kGemmBlockK, 128);
+    CUtensorMap t2 = make_tmap_2d(dW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kFfH, I, 64, kGemmBlockK, 128);
+    launch_ffn_ln(tx, t1, t1p, t2, M, I, dB1, dB2, dG, dBt, eps, act, prop.multiProcessorCount, nullptr);
+    KJ_CUDA(cudaDeviceSynchronize());
+    KJ_CUDA(cudaMemcpy(out_bf16, dX, static_cast<size_t>(M) * kFfH * 2, cudaMemcpyDeviceToHost));
+    if (iters > 0 && us) {  // timing (in place: the values drift, the work does not)
+        cudaEvent_t e0, e1;
+        KJ_CUDA(cudaEventCreate(&e0));
+        KJ_CUDA(cudaEventCreate(&e1));
+        KJ_CUDA(cudaEventRecord(e0, nullptr));
+        for (int i = 0; i < iters; ++i) launch_ffn_ln(tx, t1, t1p, t2, M, I, dB1, dB2, dG, dBt, eps, act, prop.multiProcessorCount, nullptr);
+        KJ_CUDA(cudaEventRecord(e1, nullptr));
+        KJ_CUDA(cudaDeviceSynchronize());
+        float ms = 0.f;
+        KJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *us = ms * 1e3f / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(dX); cudaFree(dW1); cudaFree(dW2); cudaFree(dB1); cudaFree(dB2); cudaFree(dG); cudaFree(dBt);
 }
 
 // GEMM microbenchmark: average microseconds per launch over `iters` launches (device buffers, random-ish data).

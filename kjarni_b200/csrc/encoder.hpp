@@ -21,6 +21,10 @@ void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap&
                  cudaStream_t st);
 void launch_gemm_pair(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p,
                       int num_sms, cudaStream_t st);
+void launch_ffn_ln(const CUtensorMap& t_x, const CUtensorMap& t_w1, const CUtensorMap& t_w1_pair, const CUtensorMap& t_w2, int M, int I,
+                   const float* b1, const float* b2, const float* gamma, const float* beta, float eps, int act, int num_sms, cudaStream_t st);
+void dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
+                const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* us);
 void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
                     const float* beta, float eps, int num_sms, cudaStream_t st);
 void launch_attention(const AttnParams& p, int head_dim, cudaStream_t st);
@@ -48,25 +52,41 @@ inline void ensure_smem_attr(K kern, int bytes, int (&configured)[64]) {
 // Launch with programmatic stream serialization (PDL): the kernel must call pdl_wait() before it touches global memory its
 // predecessor wrote.  KJC_NO_PDL=1 falls back to plain launches.
 template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline void launch_pdl_cluster(int cluster_x, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     static const bool enabled = getenv("KJC_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (enabled) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (cluster_x > 1) {  // thread-block cluster of `cluster_x` CTAs along x
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = enabled ? 1 : 0;
+    cfg.numAttrs = n;
     KJ_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    launch_pdl_cluster(1, kern, grid, block, smem, st, std::forward<Args>(args)...);
 }
 
 struct LayerDev {
     const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
     const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
     CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
+    CUtensorMap t_w1_ffn, t_w1_ffn32, t_w2_ffn;  // fused FFN kernel: W1 boxes of 64 (one CTA) / 32 (CTA pair) rows, W2 boxes of 64 rows
     CUtensorMap t_wqkv_half, t_w1_half;  // box of block_n/2 rows: the CTA-pair GEMM loads half a weight tile per CTA
 };
 
@@ -127,7 +147,7 @@ class Encoder {
     const float *word_ = nullptr, *pos_ = nullptr, *type_ = nullptr, *emb_g_ = nullptr, *emb_b_ = nullptr;
     const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
     std::vector<LayerDev> layers_;
-    bool fused_ln_ = false, pair_gemm_ = false;
+    bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false;
     int lanes_ = 2;
     std::vector<Workspace> ws_;
     cudaEvent_t ev_in_ = nullptr;

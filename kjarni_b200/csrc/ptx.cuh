@@ -271,6 +271,23 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap
         : "r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(cache_hint)
         : "memory");
 }
+// TMA load multicast to every CTA of `cta_mask`: the box lands at the same shared-memory offset and signals the mbarrier at the
+// same offset in each destination CTA.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1, uint16_t cta_mask,
+                                                  uint64_t cache_hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "l"(cache_hint)
+        : "memory");
+}
+// tcgen05.commit (1-CTA MMAs) arriving on the barrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {  // same warp index in both CTAs of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols)

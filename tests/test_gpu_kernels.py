@@ -115,6 +115,34 @@ def test_fused_gemm_residual_layernorm(M, K):
     assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2.0 ** -7
 
 
+@pytest.mark.parametrize("M,I", [(128, 1536), (300, 1536), (18944, 1536), (77, 128), (1000, 3072)])
+def test_fused_ffn_layernorm(M, I):
+    """FFN-up + erf-GELU + FFN-down + residual + LayerNorm in one kernel (hidden 384) vs the oracle chain in fp32, with the
+    intermediate rounded to bf16 where the kernel rounds it."""
+    import ctypes as C
+
+    rng = np.random.default_rng(M + I)
+    H = 384
+    x = rng.standard_normal((M, H)).astype(np.float32)
+    w1 = (rng.standard_normal((I, H)) / math.sqrt(H)).astype(np.float32)
+    w2 = (rng.standard_normal((H, I)) / math.sqrt(I)).astype(np.float32)
+    b1 = rng.standard_normal(I).astype(np.float32) * 0.1
+    b2 = rng.standard_normal(H).astype(np.float32) * 0.1
+    gamma = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    out = np.empty((M, H), np.uint16)
+    us = C.c_float()
+    N.check(N.lib().kjc_dbg_ffn_ln(ptr(to_bf16_bits(x)), ptr(to_bf16_bits(w1)), ptr(b1), ptr(to_bf16_bits(w2)), ptr(b2), ptr(gamma), ptr(beta),
+                                   1e-12, M, I, 0, ptr(out), 0, C.byref(us)))
+    got = from_bf16_bits(out)
+    xb = bf16_round(x).astype(np.float64)
+    h = ko.gelu_erf((xb @ bf16_round(w1).astype(np.float64).T + b1).astype(np.float32))
+    y = (bf16_round(h).astype(np.float64) @ bf16_round(w2).astype(np.float64).T + b2 + xb).astype(np.float32)
+    want = ko.layer_norm(y, gamma, beta, 1e-12)
+    assert np.isfinite(got).all()
+    assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2.0 ** -6
+
+
 def ref_attention(qkv, mask, B, S, H, heads, noalloc):
     d = H // heads
     x = bf16_round(qkv).reshape(B, S, 3, heads, d)
