@@ -183,6 +183,36 @@ int kjc_index_load_vectors_bin(KjcIndex* idx, const char* path);
 /* Append `n` rows of the counter-based synthetic generator shared with the oracle
  * (bench / test input only): x[r,c] = (hash32(seed, row0+r, c) >> 8) * 2^-24 - 0.5. */
 int kjc_index_append_synthetic(KjcIndex* idx, uint32_t seed, uint64_t row0, uint64_t n);
+/* ---- on-disk index directory (row f1 of SURVEY 8f): what IndexReader::open reads, KR/index_reader.rs:161-204 ----
+ *   <root>/config.json                      IndexConfig {dimension, max_docs_per_segment, ...}   KR/config.rs:5-27
+ *   <root>/segments/seg_%06d/segment.json   SegmentMeta {id, doc_count, dimension, ...}          KR/segment.rs:10-19
+ *   <root>/segments/seg_%06d/vectors.bin    raw LE f32 [doc_count, dimension]                    KR/segment.rs:87-123
+ * Segment directories are taken in file-name order; one that Segment::open would reject (segment.json, vectors.bin,
+ * docs.idx or bm25.bin missing, unparsable segment.json) is skipped as the reference does (it logs a warning), so global
+ * ids = sum of preceding segment lengths + local id (KR/index_reader.rs:313-319) agree with the host-side IndexReader,
+ * which keeps serving text / metadata / BM25 from the same directory. */
+typedef struct KjcIndexDirInfo {
+    int32_t dimension;
+    int32_t n_segments;           /* segments that load */
+    int32_t n_skipped;            /* segment directories skipped (see above) */
+    int32_t reserved;
+    uint64_t total_rows;          /* IndexReader::len */
+    uint64_t max_docs_per_segment;
+} KjcIndexDirInfo;
+/* Host-only (no GPU needed). Errors: KJC_MODEL_NOT_FOUND (no config.json), KJC_LOAD_FAILED (bad config.json, a segment whose
+ * dimension differs from the index's), KJC_INVALID_CONFIG. */
+int kjc_index_dir_info(const char* root, KjcIndexDirInfo* out);
+/* doc_count of each loadable segment in order (up to `cap` entries); returns the number of segments, or -1 on error. */
+int kjc_index_dir_segment_lens(const char* root, uint64_t* out_lens, int cap);
+/* Global-id range [*lo, *hi) of part `part` of `parts` over `total_rows` rows: contiguous blocks whose sizes differ by at
+ * most one row -- the row-sharding of SURVEY 8e (rank r of a world of `parts` loads part r). */
+int kjc_index_part_range(uint64_t total_rows, int part, int parts, uint64_t* lo, uint64_t* hi);
+/* New shard on `device` holding rows [lo, hi) of part `part` of `parts` of the on-disk index; id_base = lo; rows are copied
+ * from the mmap'ed vectors.bin files through pinned staging.  parts = 1 loads the whole index on one GPU. */
+int kjc_index_open_dir(const char* root, int device, int part, int parts, KjcIndex** out);
+/* Global id of local row 0 of this shard. */
+uint64_t kjc_index_id_base(const KjcIndex* idx);
+
 /* Copy local rows [row, row+n) back to the host (Segment::get_embedding, KR/segment.rs:240-262). */
 int kjc_index_get_rows(const KjcIndex* idx, uint64_t row, uint64_t n, float* out);
 

@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkjarni_cuda.so")
 
 KJC_OK = 0
+KJC_NULL_POINTER, KJC_INVALID_UTF8, KJC_MODEL_NOT_FOUND, KJC_LOAD_FAILED, KJC_INFERENCE_FAILED = 1, 2, 3, 4, 5
+KJC_GPU_UNAVAILABLE, KJC_INVALID_CONFIG = 6, 7
 STATUS_NAMES = {0: "Ok", 1: "NullPointer", 2: "InvalidUtf8", 3: "ModelNotFound", 4: "LoadFailed", 5: "InferenceFailed",
                 6: "GpuUnavailable", 7: "InvalidConfig", 8: "Cancelled", 9: "Timeout", 10: "StreamEnded", 255: "Unknown"}
 
@@ -29,6 +31,11 @@ class KjcEncoderInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "arch", "hidden_size", "num_layers", "num_heads", "intermediate_size", "vocab_size", "max_position_embeddings",
         "type_vocab_size", "position_offset", "head_kind", "num_labels", "device")] + [("layer_norm_eps", C.c_float)]
+
+
+class KjcIndexDirInfo(C.Structure):
+    _fields_ = [("dimension", C.c_int32), ("n_segments", C.c_int32), ("n_skipped", C.c_int32), ("reserved", C.c_int32),
+                ("total_rows", C.c_uint64), ("max_docs_per_segment", C.c_uint64)]
 
 
 class KjcForwardOptions(C.Structure):
@@ -67,6 +74,11 @@ SIGNATURES = {
     "kjc_index_destroy": (None, [_vp]),
     "kjc_index_len": (_u64, [_vp]),
     "kjc_index_dim": (_i, [_vp]),
+    "kjc_index_dir_info": (_i, [C.c_char_p, C.POINTER(KjcIndexDirInfo)]),
+    "kjc_index_dir_segment_lens": (_i, [C.c_char_p, _vp, _i]),
+    "kjc_index_part_range": (_i, [_u64, _i, _i, C.POINTER(_u64), C.POINTER(_u64)]),
+    "kjc_index_open_dir": (_i, [C.c_char_p, _i, _i, _i, C.POINTER(_vp)]),
+    "kjc_index_id_base": (_u64, [_vp]),
     "kjc_index_add_rows": (_i, [_vp, _vp, _u64]),
     "kjc_index_load_vectors_bin": (_i, [_vp, C.c_char_p]),
     "kjc_index_append_synthetic": (_i, [_vp, C.c_uint32, _u64, _u64]),

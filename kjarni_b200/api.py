@@ -150,6 +150,19 @@ class IndexShard:
         self.device = device
         N.check(N.lib().kjc_index_create(int(dim), int(capacity_rows), int(id_base), int(device), C.byref(self._h)))
 
+    @classmethod
+    def open_dir(cls, root: str, device: int = 0, part: int = 0, parts: int = 1) -> "IndexShard":
+        """Rows of part `part` of `parts` of an on-disk index directory (kjc_index_open_dir; IndexReader::open,
+        KR/index_reader.rs:161-204): all segments in file-name order, contiguous global-id range, id_base = first row."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.mode = N.SCAN_SEGMENT
+        self.device = device
+        N.check(N.lib().kjc_index_open_dir(str(root).encode(), int(device), int(part), int(parts), C.byref(self._h)))
+        self.dim = int(N.lib().kjc_index_dim(self._h))
+        self.id_base = int(N.lib().kjc_index_id_base(self._h))
+        return self
+
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             N.lib().kjc_index_destroy(self._h)
@@ -242,12 +255,38 @@ class IndexReader:
     def __init__(self, shards: Sequence[IndexShard]):
         self.shards = list(shards)
 
+    @classmethod
+    def open(cls, root: str, devices: Sequence[int] = (0,)) -> "IndexReader":
+        """IndexReader::open (KR/index_reader.rs:161-204) onto GPU shards: one contiguous part per device."""
+        return cls([IndexShard.open_dir(root, dev, i, len(devices)) for i, dev in enumerate(devices)])
+
+    def __len__(self) -> int:
+        return sum(len(s) for s in self.shards)
+
     def search_semantic(self, query, limit: int) -> List[Tuple[int, float]]:
         allr: List[Tuple[int, float]] = []
         for sh in self.shards:
             allr.extend((i + sh.id_base, s) for i, s in sh.search_vectors(query, limit))
         order = np.argsort(-np.array([r[1] for r in allr], np.float32), kind="stable") if allr else []
         return [allr[i] for i in order[:limit]]
+
+
+def index_dir_info(root: str) -> dict:
+    """config.json + segment table of an on-disk index (host-only, kjc_index_dir_info / kjc_index_dir_segment_lens)."""
+    info = N.KjcIndexDirInfo()
+    N.check(N.lib().kjc_index_dir_info(str(root).encode(), C.byref(info)))
+    lens = np.zeros((max(info.n_segments, 1),), np.uint64)
+    n = N.lib().kjc_index_dir_segment_lens(str(root).encode(), _ptr(lens), int(lens.shape[0]))
+    if n < 0:
+        N.check(N.KJC_LOAD_FAILED)
+    return {"dimension": info.dimension, "n_segments": info.n_segments, "n_skipped": info.n_skipped, "total_rows": int(info.total_rows),
+            "max_docs_per_segment": int(info.max_docs_per_segment), "segment_lens": [int(x) for x in lens[:n]]}
+
+
+def index_part_range(total_rows: int, part: int, parts: int) -> Tuple[int, int]:
+    lo, hi = C.c_uint64(), C.c_uint64()
+    N.check(N.lib().kjc_index_part_range(int(total_rows), int(part), int(parts), C.byref(lo), C.byref(hi)))
+    return int(lo.value), int(hi.value)
 
 
 def cosine_similarity(a, b) -> float:

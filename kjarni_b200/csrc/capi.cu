@@ -12,7 +12,12 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 }  // namespace kj
 
 struct KjcEncoder { kj::Encoder impl; KjcEncoder(const char* d, int dev) : impl(d, dev) {} };
-struct KjcIndex { kj::Index impl; KjcIndex(int dim, uint64_t cap, uint64_t base, int dev) : impl(dim, cap, base, dev) {} };
+struct KjcIndex {
+    std::unique_ptr<kj::Index> own;
+    kj::Index& impl;
+    KjcIndex(int dim, uint64_t cap, uint64_t base, int dev) : own(new kj::Index(dim, cap, base, dev)), impl(*own) {}
+    explicit KjcIndex(kj::Index* p) : own(p), impl(*own) {}
+};
 
 template <typename F>
 static int guarded(F&& f) {
@@ -139,6 +144,48 @@ int kjc_index_create(int dim, uint64_t capacity_rows, uint64_t id_base, int devi
 void kjc_index_destroy(KjcIndex* idx) { delete idx; }
 uint64_t kjc_index_len(const KjcIndex* idx) { return idx ? idx->impl.len() : 0; }
 int kjc_index_dim(const KjcIndex* idx) { return idx ? idx->impl.dim() : 0; }
+int kjc_index_dir_info(const char* root, KjcIndexDirInfo* out) {
+    KJC_REQUIRE(root);
+    KJC_REQUIRE(out);
+    memset(out, 0, sizeof *out);
+    return guarded([&] {
+        const kj::IndexDir d = kj::scan_index_dir(root);
+        out->dimension = d.dimension;
+        out->n_segments = static_cast<int32_t>(d.segments.size());
+        out->n_skipped = d.skipped;
+        out->total_rows = d.total_rows;
+        out->max_docs_per_segment = d.max_docs_per_segment;
+    });
+}
+int kjc_index_dir_segment_lens(const char* root, uint64_t* out_lens, int cap) {
+    if (!root || (cap > 0 && !out_lens)) {
+        kj::set_last_error("null pointer argument");
+        return -1;
+    }
+    int n = -1;
+    guarded([&] {
+        const kj::IndexDir d = kj::scan_index_dir(root);
+        for (size_t i = 0; i < d.segments.size() && static_cast<int>(i) < cap; ++i) out_lens[i] = d.segments[i].doc_count;
+        n = static_cast<int>(d.segments.size());
+    });
+    return n;
+}
+int kjc_index_part_range(uint64_t total_rows, int part, int parts, uint64_t* lo, uint64_t* hi) {
+    KJC_REQUIRE(lo);
+    KJC_REQUIRE(hi);
+    return guarded([&] { kj::index_part_range(total_rows, part, parts, lo, hi); });
+}
+int kjc_index_open_dir(const char* root, int device, int part, int parts, KjcIndex** out) {
+    KJC_REQUIRE(root);
+    KJC_REQUIRE(out);
+    *out = nullptr;
+    return guarded([&] {
+        std::unique_ptr<kj::Index> p(kj::open_index_dir(root, device, part, parts));
+        *out = new KjcIndex(p.get());
+        p.release();
+    });
+}
+uint64_t kjc_index_id_base(const KjcIndex* idx) { return idx ? idx->impl.id_base() : 0; }
 int kjc_index_add_rows(KjcIndex* idx, const float* rows, uint64_t n) {
     KJC_REQUIRE(idx);
     if (n == 0) return KJC_OK;

@@ -498,7 +498,8 @@ Encoder::Encoder(const std::string& dir, int device) {
     bn_qkv_ = pick_block_n(3 * H);
     bn_h_ = pick_block_n(H);
     bn_i_ = pick_block_n(I);
-    if (const char* e = getenv("KJC_BN_I")) bn_i_ = atoi(e);  // tuning hook
+    if (const char* e = getenv("KJC_BN_I")) bn_i_ = atoi(e);  // tuning hooks
+    if (const char* e = getenv("KJC_BN_QKV")) bn_qkv_ = atoi(e);
     layers_.resize(L);
     for (int l = 0; l < L; ++l) {
         LayerDev& ld = layers_[l];
@@ -593,11 +594,11 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     w.t_ctx16 = make_tmap_2d(w.ctx16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
     w.t_h16 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
     // store boxes: 192-column tiles store 32 x 64 parts (128B swizzle), the other widths 32 x 32 chunks (64B swizzle)
-    w.t_qkv16_out = (bn_qkv_ == 192 && (kGemm192WideStore || pair_gemm_)) ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128)
+    w.t_qkv16_out = (gemm_wide_store(bn_qkv_) || (bn_qkv_ == 192 && pair_gemm_)) ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128)
                                    : make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
     w.t_qkv16_out32 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);  // CTA-pair kernel
     w.t_h16_out32 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
-    w.t_h16_out = (bn_i_ == 192 && (kGemm192WideStore || pair_gemm_)) ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
+    w.t_h16_out = (gemm_wide_store(bn_i_) || (bn_i_ == 192 && pair_gemm_)) ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
                                : make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
     w.t_x16_io = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
     w.tokens = static_cast<int>(T);
@@ -951,7 +952,7 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         GemmParams p{};
         p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act;
         CUtensorMap tc = ta;
-        if (!f32out) tc = (bn == 192 && (kGemm192WideStore || pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, 64, 128)
+        if (!f32out) tc = ((!pair && gemm_wide_store(bn)) || (bn == 192 && pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, 64, 128)
                                                : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
         if (pair) {
             CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
@@ -1082,7 +1083,7 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
     CUtensorMap tb = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn, kGemmBlockK, 128);
     CUtensorMap tc = ta;
-    if (!f32out) tc = (bn == 192 && (kGemm192WideStore || pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, 64, 128)
+    if (!f32out) tc = ((!pair && gemm_wide_store(bn)) || (bn == 192 && pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, 64, 128)
                                            : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, N, 32, kEpiChunkCols, 64);
     GemmParams p{};
     p.M = M; p.N = N; p.K = K; p.bias = dB; p.residual = dR; p.ldr = N; p.out = dO; p.ldo = N; p.act = act; p.dbg = flags & ~8;
@@ -1113,6 +1114,7 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
         for (int c : {0, 1, ctas / 2, ctas - 1}) {
             fprintf(stderr, "trace M=%d N=%d K=%d bn=%d cta %3d:", M, N, K, bn, c);
             for (int i = 0; i < 18; ++i) if (h[c * 32 + i]) fprintf(stderr, " %s=%.2f", names[i], (h[c * 32 + i] - t0) * 1e-3);
+            if (h[c * 32 + 16] > h[c * 32 + 2]) fprintf(stderr, " sm_mhz=%.0f", (h[c * 32 + 21] - h[c * 32 + 20]) * 1e3 / double(h[c * 32 + 16] - h[c * 32 + 2]));
             fprintf(stderr, "\n");
         }
         p.trace = nullptr;

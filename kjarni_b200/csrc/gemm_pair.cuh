@@ -55,6 +55,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     static_assert(EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_ACT_BF16, "pair kernel stores bf16");
 
     extern __shared__ __align__(1024) uint8_t smem_pair[];
+    if (threadIdx.x == 0) KJ_TRACE(0);
     if (smem_u32(smem_pair) & 1023) __trap();
     uint8_t* smem_a = smem_pair;
     uint8_t* smem_b = smem_a + Cfg::kABytes;
@@ -108,8 +109,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA completion
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    if (threadIdx.x == 0) KJ_TRACE(1);
     pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here on
     pdl_launch_dependents();  // the next kernel may begin its own prologue as soon as this CTA's resources are released
+    if (threadIdx.x == 0) KJ_TRACE(2);
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
@@ -154,6 +157,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         if (nb == 0) mbar_wait(&a_full[kb], ai & 1);
                         mbar_wait(&full_bar[stage], phase);
+                        if (it == 0 && kb == 0) KJ_TRACE(3);
                         tc_fence_after();
                         const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + kb * Cfg::kABlockBytes));
                         const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
@@ -185,6 +189,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int nb = 0; nb < n_tiles; ++nb, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+                if (ew == 0 && lane == 0 && it < 6) KJ_TRACE(4 + 2 * it);
                 tc_fence_after();
                 const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + part * kColsPerPart;
                 const int colp = nb * BN + part * kColsPerPart;
@@ -259,9 +264,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         bulk_commit();
                     }
                 }
+                if (ew == 0 && lane == 0 && it < 6) KJ_TRACE(5 + 2 * it);
             }
         }
         if (lane == 0) bulk_wait_read<0>();
+        if (ew == 0 && lane == 0) KJ_TRACE(16);
     }
 
     tc_fence_before();
@@ -270,6 +277,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
         tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
     }
+    if (threadIdx.x == 64) KJ_TRACE(17);
 }
 
 }  // namespace kj

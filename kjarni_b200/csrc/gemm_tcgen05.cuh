@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define KJ_TRACE(slot) do { if (p.trace) p.trace[blockIdx.x * 32 + (slot)] = gtimer(); } while (0)
+#define KJ_TRACE(slot) do { if (p.trace) { p.trace[blockIdx.x * 32 + (slot)] = gtimer(); if ((slot) == 2 || (slot) == 16) p.trace[blockIdx.x * 32 + 20 + ((slot) == 16)] = clock64(); } } while (0)
 
 constexpr int kGemmBlockM = 128;
 constexpr int kGemmBlockK = 64;
@@ -57,31 +57,37 @@ constexpr int kEpiBiasMax = 3072;                         // bias columns staged
 #ifndef KJ_GEMM_PARTS192
 #define KJ_GEMM_PARTS192 3
 #endif
-constexpr bool kGemm192WideStore = KJ_GEMM_PARTS192 == 3;  // host side: 192-column tiles store 32 x 64 boxes (128B swizzle)
+#ifndef KJ_GEMM_WIDE256
+#define KJ_GEMM_WIDE256 1
+#endif
+constexpr bool kGemm192WideStore = KJ_GEMM_PARTS192 == 3;
+// Tiles whose bf16 epilogue stages 32 x 64 parts (128B swizzle) and issues one TMA store per warp per tile; the host builds the
+// output tensor map with a 32 x 64 box for these widths.
+constexpr bool gemm_wide_store(int bn) { return (bn == 192 && kGemm192WideStore) || (bn == 256 && KJ_GEMM_WIDE256 != 0); }
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int kStages = (BN <= 64) ? 6 : ((BN <= 128) ? 5 : 4);
+    static constexpr bool kWide = gemm_wide_store(BN);
+    // 256-column tiles: a tcgen05.mma of M = 128 costs ~128 clk whatever N <= 256 is (measured, scripts/mma_rate.py), so the widest
+    // tile wastes no tensor time; its 16 epilogue warps need 64 KB of staging, hence 3 operand stages of 48 KB
+    static constexpr int kStages = (BN <= 64) ? 6 : ((BN <= 128) ? 5 : ((BN == 256 && kWide) ? 3 : 4));
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
     static constexpr int kBBytes = BN * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    // epilogue warps: 4 TMEM lane quadrants x kParts column parts.  192-column tiles use 3 parts of 64 columns (12 warps, 3 per
-    // scheduler: the epilogue is issue/latency-bound, more resident warps hide its waits); the other widths use 2 parts.
-#ifndef KJ_GEMM_PARTS192
-#define KJ_GEMM_PARTS192 3
-#endif
-    static constexpr int kParts = (BN == 192) ? KJ_GEMM_PARTS192 : 2;
+    // epilogue warps: 4 TMEM lane quadrants x kParts column parts.  Wide-store tiles use parts of 64 columns (12 / 16 warps, 3 / 4 per
+    // scheduler: the epilogue is a latency chain per warp, more resident warps hide its waits); the other widths use 2 parts.
+    static constexpr int kParts = kWide ? BN / 64 : 2;
     static constexpr int kEpiWarpsN = 4 * kParts;
     static constexpr int kThreads = 128 + 32 * kEpiWarpsN;
     static constexpr int kColsPerPart = BN / kParts;
-    // output staging per epilogue warp: 192-column tiles stage the warp's whole 32 x 64 part (4 KB, 128-byte rows, one TMA store
-    // per tile: the TMA store path is charged per row segment, 128-byte segments halve its load); others 2 x (32 x 32) chunks
-    static constexpr int kStoreCols = (BN == 192 && kParts == 3) ? 64 : kEpiChunkCols;
-    static constexpr int kEpiBufs = (BN == 192 && kParts == 3) ? 1 : ((BN <= 192) ? 3 : 2);
+    // output staging per epilogue warp: wide-store tiles stage the warp's whole 32 x 64 part (4 KB, 128-byte rows, one TMA store
+    // per tile: the TMA store path is charged per row segment, 128-byte segments halve its load); others 2-3 x (32 x 32) chunks
+    static constexpr int kStoreCols = kWide ? 64 : kEpiChunkCols;
+    static constexpr int kEpiBufs = kWide ? 1 : ((BN <= 192) ? 3 : 2);
     static constexpr int kEpiBufBytes = 32 * kStoreCols * 2;
     static constexpr int kEpiBytes = kEpiWarpsN * kEpiBufs * kEpiBufBytes;
-    static constexpr int kBiasBytes = (BN <= 192) ? kEpiBiasMax * 4 : 0;  // bias staged in smem where it fits
+    static constexpr int kBiasBytes = (BN <= 192 || kWide) ? kEpiBiasMax * 4 : 0;  // bias staged in smem where it fits
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -195,7 +201,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < num_tiles && !(p.dbg & 64); tile += gridDim.x) {
                 const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -228,7 +234,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    if (!(p.dbg & 64)) mbar_wait(&full_bar[stage], phase);  // 64: raw MMA issue rate (no operand handshake)
                     if (it == 0 && kb == 0) KJ_TRACE(3);  // first operands landed
                     tc_fence_after();
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
@@ -240,7 +246,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                    if (!(p.dbg & 64)) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                     if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
                     if (++stage == kStages) {
                         stage = 0;
@@ -285,8 +291,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     uint32_t v[32];
-                    tmem_ld_32x32(taddr0 + c * 32, v);
-                    tmem_ld_wait();
+                    if (p.dbg & 128) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = lane + j;
+                    } else {
+                        tmem_ld_32x32(taddr0 + c * 32, v);
+                        tmem_ld_wait();
+                    }
                     if (c == 1) {
                         tc_fence_before();
                         __syncwarp();
@@ -296,7 +307,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias != nullptr) {
+                    if (bias_in_smem && col0 + 32 <= p.N && !(p.dbg & 512)) {  // whole chunk inside N: no per-column checks
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = *reinterpret_cast<const float4*>(s_bias + col0 + 4 * j);
+                            f[4 * j + 0] += b.x;
+                            f[4 * j + 1] += b.y;
+                            f[4 * j + 2] += b.z;
+                            f[4 * j + 3] += b.w;
+                        }
+                    } else if (p.bias != nullptr && !(p.dbg & 512)) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             if (col0 + 4 * j < p.N) {
@@ -310,7 +330,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             }
                         }
                     }
-                    if (EPI == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
+                    if (EPI == EPI_BIAS_ACT_BF16 && !(p.dbg & 512)) apply_act_tile(f, p.act);
+                    if (!(p.dbg & 256))
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         st_shared_v4(rbase + ((static_cast<uint32_t>(c * 4 + j) ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]),

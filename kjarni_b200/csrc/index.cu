@@ -3,6 +3,8 @@
 // Host-side mirror of Segment (kjarni-rag/src/segment.rs:195-337), VectorStore
 // (kjarni-search/src/vector.rs:5-165) and the per-segment -> merge shape of
 // IndexReader::search_semantic (kjarni-rag/src/index_reader.rs:207-228,313-319).
+#include <dirent.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -84,20 +86,26 @@ void Index::add_rows_host(const float* rows, uint64_t n) {
     len_ += n;
 }
 
-void Index::load_vectors_bin(const std::string& path) {
-    // vectors.bin = raw little-endian f32 [doc_count x dim] (kjarni-rag/src/segment.rs:87-123,211-262)
+void Index::load_vectors_bin(const std::string& path) { load_vectors_bin_range(path, 0, UINT64_MAX); }
+
+void Index::load_vectors_bin_range(const std::string& path, uint64_t row0, uint64_t n_rows) {
+    // vectors.bin = raw little-endian f32 [doc_count x dim] (kjarni-rag/src/segment.rs:87-123,211-262);
+    // n_rows == UINT64_MAX: every row from row0 to the end of the file
     int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) throw Error(KJC_MODEL_NOT_FOUND, "cannot open " + path);
     struct stat sb;
     if (fstat(fd, &sb) != 0) { close(fd); throw Error(KJC_LOAD_FAILED, "cannot stat " + path); }
     const size_t bytes = static_cast<size_t>(sb.st_size);
-    if (bytes % (dim_ * sizeof(float)) != 0) { close(fd); throw Error(KJC_LOAD_FAILED, "vectors.bin size is not a multiple of 4*dim: " + path); }
-    const uint64_t n = bytes / (dim_ * sizeof(float));
-    if (n == 0) { close(fd); return; }
+    const size_t row_bytes = dim_ * sizeof(float);
+    if (bytes % row_bytes != 0) { close(fd); throw Error(KJC_LOAD_FAILED, "vectors.bin size is not a multiple of 4*dim: " + path); }
+    const uint64_t file_rows = bytes / row_bytes;
+    if (n_rows == UINT64_MAX) n_rows = file_rows > row0 ? file_rows - row0 : 0;
+    if (row0 + n_rows > file_rows) { close(fd); throw Error(KJC_LOAD_FAILED, "vectors.bin holds fewer rows than segment.json declares: " + path); }
+    if (n_rows == 0) { close(fd); return; }
     void* map = mmap(nullptr, bytes, PROT_READ, MAP_PRIVATE, fd, 0);
     if (map == MAP_FAILED) { close(fd); throw Error(KJC_LOAD_FAILED, "mmap failed for " + path); }
     try {
-        add_rows_host(static_cast<const float*>(map), n);
+        add_rows_host(static_cast<const float*>(map) + row0 * dim_, n_rows);
     } catch (...) {
         munmap(map, bytes);
         close(fd);
@@ -428,6 +436,93 @@ void merge_lists_u64(const uint64_t* d_ids, const float* d_scores, int n_lists, 
     m.out_scores = d_out_scores; m.out_ids = d_out_ids; m.out_counts = d_out_counts; m.L = n_lists; m.Q = nq; m.k = k;
     m.mode = SCAN_VECTORSTORE;
     launch_topk_merge(m, st);
+}
+
+// ------------------------------------------------------------------ on-disk index directory (IndexReader::open)
+static bool file_exists(const std::string& p) {
+    struct stat sb;
+    return stat(p.c_str(), &sb) == 0 && S_ISREG(sb.st_mode);
+}
+
+IndexDir scan_index_dir(const std::string& root) {
+    IndexDir d;
+    const std::string cfg_text = read_text_file(root + "/config.json", KJC_MODEL_NOT_FOUND);
+    Json cfg;
+    try {
+        cfg = JsonParser(cfg_text.data(), cfg_text.size()).parse();
+    } catch (const Error& e) {
+        throw Error(KJC_LOAD_FAILED, root + "/config.json: " + e.what());
+    }
+    // IndexConfig: `dimension` and `max_docs_per_segment` are required serde fields (kjarni-rag/src/config.rs:5-14)
+    if (!cfg.has("dimension") || !cfg.has("max_docs_per_segment"))
+        throw Error(KJC_LOAD_FAILED, root + "/config.json: missing field `dimension` / `max_docs_per_segment`");
+    d.dimension = static_cast<int>(cfg.number("dimension", 0));
+    d.max_docs_per_segment = static_cast<uint64_t>(cfg.number("max_docs_per_segment", 0));
+    if (d.dimension <= 0) throw Error(KJC_INVALID_CONFIG, root + "/config.json: dimension must be positive");
+    const std::string seg_root = root + "/segments";
+    DIR* dp = opendir(seg_root.c_str());
+    if (!dp) return d;  // `if segments_dir.exists()`: an index without segments is empty, not an error
+    std::vector<std::string> names;
+    while (struct dirent* e = readdir(dp)) {
+        const std::string name = e->d_name;
+        if (name == "." || name == "..") continue;
+        struct stat sb;
+        if (stat((seg_root + "/" + name).c_str(), &sb) == 0 && S_ISDIR(sb.st_mode)) names.push_back(name);
+    }
+    closedir(dp);
+    std::sort(names.begin(), names.end());  // entries.sort_by_key(file_name)
+    for (const std::string& name : names) {
+        const std::string sd = seg_root + "/" + name;
+        // Segment::open (segment.rs:212-238) fails -- and IndexReader::open then skips the segment with a warning --
+        // when any of these is missing or segment.json does not parse.
+        if (!file_exists(sd + "/segment.json") || !file_exists(sd + "/vectors.bin") || !file_exists(sd + "/docs.idx") ||
+            !file_exists(sd + "/bm25.bin")) {
+            ++d.skipped;
+            continue;
+        }
+        Json meta;
+        try {
+            const std::string mt = read_text_file(sd + "/segment.json", KJC_LOAD_FAILED);
+            meta = JsonParser(mt.data(), mt.size()).parse();
+        } catch (const Error&) {
+            ++d.skipped;
+            continue;
+        }
+        if (!meta.has("id") || !meta.has("doc_count") || !meta.has("dimension") || !meta.has("created_at") || !meta.has("total_bytes")) {
+            ++d.skipped;
+            continue;
+        }
+        if (static_cast<int>(meta.number("dimension", 0)) != d.dimension)
+            throw Error(KJC_LOAD_FAILED, sd + ": segment dimension differs from the index dimension (the reference would score no row of "
+                                              "it, segment.rs:308-310; a mixed-dimension index is not loadable as one GPU shard)");
+        IndexDirSegment s;
+        s.dir = sd;
+        s.doc_count = static_cast<uint64_t>(meta.number("doc_count", 0));
+        s.global_base = d.total_rows;
+        d.total_rows += s.doc_count;
+        d.segments.push_back(std::move(s));
+    }
+    return d;
+}
+
+void index_part_range(uint64_t total, int part, int parts, uint64_t* lo, uint64_t* hi) {
+    if (parts < 1 || part < 0 || part >= parts) throw Error(KJC_INVALID_CONFIG, "part must be in [0, parts)");
+    const uint64_t base = total / parts, rem = total % parts, p = static_cast<uint64_t>(part);
+    *lo = p * base + std::min<uint64_t>(p, rem);
+    *hi = *lo + base + (p < rem ? 1 : 0);
+}
+
+Index* open_index_dir(const std::string& root, int device, int part, int parts) {
+    const IndexDir d = scan_index_dir(root);
+    uint64_t lo, hi;
+    index_part_range(d.total_rows, part, parts, &lo, &hi);
+    std::unique_ptr<Index> idx(new Index(d.dimension, std::max<uint64_t>(hi - lo, 1), lo, device));
+    for (const IndexDirSegment& s : d.segments) {
+        const uint64_t a = std::max(lo, s.global_base), b = std::min(hi, s.global_base + s.doc_count);
+        if (a >= b) continue;
+        idx->load_vectors_bin_range(s.dir + "/vectors.bin", a - s.global_base, b - a);
+    }
+    return idx.release();
 }
 
 }  // namespace kj

@@ -20,11 +20,13 @@ class Index {
 
     uint64_t len() const { return len_; }
     int dim() const { return dim_; }
+    uint64_t id_base() const { return id_base_; }
     int device() const { return device_; }
     int64_t last_launches() const { return launches_; }
 
     void add_rows_host(const float* rows, uint64_t n);
     void load_vectors_bin(const std::string& path);
+    void load_vectors_bin_range(const std::string& path, uint64_t row0, uint64_t n_rows);
     void append_synthetic(uint32_t seed, uint64_t row0, uint64_t n);
     void get_rows(uint64_t row, uint64_t n, float* out) const;
     void search_host(const float* q, int nq, int k, int mode, uint64_t* ids, float* scores, int32_t* counts);
@@ -67,5 +69,35 @@ class Index {
     CUtensorMap t_rows16_;
     std::vector<int32_t> h_flags_;
 };
+
+}  // namespace kj
+
+namespace kj {
+
+// On-disk index directory as IndexWriter leaves it (kjarni-rag/src/index_writer.rs:128-170, config.rs:5-27):
+//   <root>/config.json                         IndexConfig {dimension, max_docs_per_segment, ...}
+//   <root>/segments/seg_%06d/segment.json      SegmentMeta {id, doc_count, dimension, created_at, total_bytes}
+//   <root>/segments/seg_%06d/vectors.bin       raw LE f32 [doc_count, dimension]
+//   (+ docs.bin, docs.idx, metadata.jsonl, bm25.bin: text / keyword side, stays with the Rust host)
+// Segments are taken in file-name order and a segment the reference's Segment::open would reject (missing segment.json,
+// vectors.bin, docs.idx or bm25.bin) is skipped exactly as IndexReader::open does (index_reader.rs:161-204), so the
+// global ids (sum of preceding segment lengths + local id, index_reader.rs:313-319) agree with the host's.
+struct IndexDirSegment {
+    std::string dir;       // absolute path of the segment directory
+    uint64_t doc_count;    // SegmentMeta::doc_count
+    uint64_t global_base;  // global id of local row 0
+};
+struct IndexDir {
+    int dimension = 0;
+    uint64_t max_docs_per_segment = 0;
+    uint64_t total_rows = 0;
+    int skipped = 0;  // segment directories IndexReader::open would have skipped
+    std::vector<IndexDirSegment> segments;
+};
+IndexDir scan_index_dir(const std::string& root);
+// Rows [lo, hi) of global-id space of part `part` of `parts` (contiguous, sizes differ by at most one row).
+void index_part_range(uint64_t total, int part, int parts, uint64_t* lo, uint64_t* hi);
+// New shard on `device` holding this part's rows of the on-disk index; id_base = lo.
+Index* open_index_dir(const std::string& root, int device, int part, int parts);
 
 }  // namespace kj

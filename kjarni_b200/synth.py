@@ -153,3 +153,48 @@ def synth_tokens(batch: int, seq: int, vocab: int = 30522, *, regime: str = "T",
             ids[b, cut - 1] = 102
             types[b, cut:n] = 1
     return ids, mask, types
+
+
+def write_index_dir(root: str, segments, *, dimension: int = None, max_docs_per_segment: int = 10_000, broken=()) -> str:
+    """Writes an index directory in the layout IndexWriter::commit leaves (kjarni-rag/src/index_writer.rs:128-170,
+    segment.rs:140-193): config.json, index.json, segments/seg_%06d/{segment.json, vectors.bin, docs.bin, docs.idx,
+    metadata.jsonl, bm25.bin}.  `segments` = list of float32 [n_i, dim] arrays.  docs.idx is a bincode Vec<u64>
+    (u64 length + offsets); bm25.bin is a placeholder (the GPU reader only checks that it exists, as Segment::open would
+    fail without it).  `broken` = segment indices written WITHOUT bm25.bin, which IndexReader::open skips."""
+    import json
+    import struct
+    import time
+
+    segs = [np.ascontiguousarray(x, np.float32) for x in segments]
+    dim = int(dimension if dimension is not None else segs[0].shape[1])
+    os.makedirs(os.path.join(root, "segments"), exist_ok=True)
+    with open(os.path.join(root, "config.json"), "w") as f:
+        json.dump({"dimension": dim, "max_docs_per_segment": max_docs_per_segment, "max_segment_memory": 100 * 1024 * 1024,
+                   "embedding_model": None, "model_name": None, "created_at": None, "version": 1}, f, indent=2)
+    total = 0
+    for i, rows in enumerate(segs):
+        sd = os.path.join(root, "segments", "seg_%06d" % i)
+        os.makedirs(sd, exist_ok=True)
+        rows.astype("<f4").tofile(os.path.join(sd, "vectors.bin"))
+        docs = [("doc %d of segment %d" % (j, i)).encode() for j in range(rows.shape[0])]
+        offs, cur = [], 0
+        with open(os.path.join(sd, "docs.bin"), "wb") as f:
+            for d in docs:
+                offs.append(cur)
+                f.write(d + b"\n")
+                cur += len(d) + 1
+        with open(os.path.join(sd, "docs.idx"), "wb") as f:
+            f.write(struct.pack("<Q", len(offs)) + b"".join(struct.pack("<Q", o) for o in offs))
+        with open(os.path.join(sd, "metadata.jsonl"), "w") as f:
+            f.write("{}\n" * rows.shape[0])
+        if i not in broken:
+            with open(os.path.join(sd, "bm25.bin"), "wb") as f:
+                f.write(b"\0" * 8)
+        with open(os.path.join(sd, "segment.json"), "w") as f:
+            json.dump({"id": i, "doc_count": int(rows.shape[0]), "dimension": int(rows.shape[1]), "created_at": int(time.time()),
+                       "total_bytes": int(rows.nbytes + cur)}, f, indent=2)
+        if i not in broken:
+            total += rows.shape[0]
+    with open(os.path.join(root, "index.json"), "w") as f:
+        json.dump({"total_docs": total, "segment_count": len(segs), "dimension": dim}, f, indent=2)
+    return root

@@ -4,7 +4,7 @@ sys.path.insert(0, ".")
 from kjarni_b200 import _native as N
 lib = N.lib()
 M = 18944
-for name, Nn, K, epi, bn in (("qkv", 1152, 384, 0, 192), ("ffn_up", 1536, 384, 1, 192)):
+for name, Nn, K, epi, bn in (("qkv", 1152, 384, 0, 192), ("ffn_up", 1536, 384, 1, 192), ("qkv-pair", 1152, 384, 0, 1192), ("ffn_up-pair", 1536, 384, 1, 1192), ("ffn_up-pair", 1536, 384, 1, 1256)):
     us = C.c_float()
     for fl in (8,):
         N.check(lib.kjc_dbg_gemm_time(M, Nn, K, epi, 0, bn, fl, 20, C.byref(us)))

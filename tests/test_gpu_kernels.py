@@ -63,6 +63,22 @@ def test_gemm_every_block_n_and_tails(block_n):
     assert np.abs(got - want).max() < 1e-3
 
 
+@pytest.mark.parametrize("block_n", [128, 192, 256])
+@pytest.mark.parametrize("Nn", [1152, 416, 1536])
+@pytest.mark.parametrize("epi", [0, 1])
+def test_gemm_bf16_epilogue_n_tails(block_n, Nn, epi):
+    """bf16 (TMA-store) epilogues with N not a multiple of the tile width: QKV 1152 on 256-column tiles (4.5 tiles), 416."""
+    rng = np.random.default_rng(block_n + Nn + epi)
+    M, K = 300, 384
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((Nn, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(Nn).astype(np.float32)
+    got = run_gemm(a, w, bias, None, epi, act=0, block_n=block_n)
+    want = ref_gemm(a, w, bias, None, epi, 0)
+    err = np.abs(got - want) / (1.0 + np.abs(want))
+    assert np.isfinite(got).all() and err.max() < 2.0 ** -8, err.max()
+
+
 @pytest.mark.parametrize("M,Nn,K,bn", [(256, 1152, 384, 192), (18944, 1152, 384, 192), (300, 1536, 384, 256), (130, 384, 192, 128),
                                        (4096 + 77, 1536, 384, 256), (100, 416, 320, 256)])
 @pytest.mark.parametrize("epi", [0, 1])
