@@ -56,7 +56,13 @@ typedef struct KjcEncoder KjcEncoder;
 
 /* Layout selected from config.json (KM/models/sentence_encoder/model.rs:41-54,
  * KM/models/sentence_encoder/configs.rs:271-364,638-687). */
-typedef enum KjcArch { KJC_ARCH_BERT = 0, KJC_ARCH_BERT_PREFIXED = 1, KJC_ARCH_DISTILBERT = 2 } KjcArch;
+typedef enum KjcArch {
+    KJC_ARCH_BERT = 0,
+    KJC_ARCH_BERT_PREFIXED = 1,
+    KJC_ARCH_DISTILBERT = 2,
+    KJC_ARCH_ROBERTA = 3, /* `roberta.` prefix, positions from row 2 (KM/models/sequence_classifier/configs.rs:147-283) */
+    KJC_ARCH_MPNET = 4    /* attention.attn.{q,k,v,o}, tanh-GELU, positions from row 2 (KM/models/sentence_encoder/configs.rs:370-468) */
+} KjcArch;
 /* Head auto-detected from tensor names, first match wins (KT/cpu/encoder/classifier.rs:113-206). */
 typedef enum KjcHeadKind {
     KJC_HEAD_ABSENT = 0,      /* sentence encoder: no classifier tensors */
@@ -75,7 +81,7 @@ typedef struct KjcEncoderInfo {
     int32_t vocab_size;
     int32_t max_position_embeddings;
     int32_t type_vocab_size; /* 0: no token-type table (DistilBERT) */
-    int32_t position_offset; /* extra_pos_embeddings: 0 BERT/DistilBERT */
+    int32_t position_offset; /* extra_pos_embeddings: 0 BERT/DistilBERT, 2 RoBERTa/MPNet */
     int32_t head_kind;       /* KjcHeadKind */
     int32_t num_labels;      /* rows of the classifier weight; 0 without a head */
     int32_t device;
@@ -160,6 +166,9 @@ int kjc_encoder_get_profile(KjcEncoder* enc, double* ms, int64_t* launches);
 /* softmax over the label axis in place (SequenceClassifier::classify_scores_batch,
  * KM/models/sequence_classifier/mod.rs:248-263 -> KT/activations.rs:223-242). Host-side helper. */
 void kjc_softmax_rows(float* logits, int rows, int cols);
+/* sigmoid per logit in place: ClassificationMode::MultiLabel scores (kjarni/src/classifier/model.rs:313-335,528-531).
+ * Host-side helper. */
+void kjc_sigmoid_rows(float* logits, int rows, int cols);
 
 /* ---------------------------------------------------------------- index scan */
 

@@ -21,7 +21,7 @@ OUT_HIDDEN, OUT_POOLED, OUT_LOGITS = 0, 1, 2
 POOL_MEAN, POOL_CLS, POOL_MAX, POOL_LAST = 0, 1, 2, 3
 MASK_AUTO, MASK_ALLOC, MASK_NOALLOC = 0, 1, 2
 SCAN_SEGMENT, SCAN_VECTORSTORE = 0, 1
-ARCH_NAMES = {0: "bert", 1: "bert_prefixed", 2: "distilbert"}
+ARCH_NAMES = {0: "bert", 1: "bert_prefixed", 2: "distilbert", 3: "roberta", 4: "mpnet"}
 HEAD_NAMES = {0: None, 1: "dense_tanh", 2: "pre_relu", 3: "pooler_tanh", 4: "none"}
 NO_ID = 0xFFFFFFFFFFFFFFFF
 KERNEL_CLASSES = ("embed_ln", "gemm_qkv", "attention", "gemm_out", "layernorm", "gemm_ffn_up", "gemm_ffn_down", "output")
@@ -70,6 +70,7 @@ SIGNATURES = {
     "kjc_encoder_set_profiling": (_i, [_vp, _i]),
     "kjc_encoder_get_profile": (_i, [_vp, _vp, _vp]),
     "kjc_softmax_rows": (None, [_vp, _i, _i]),
+    "kjc_sigmoid_rows": (None, [_vp, _i, _i]),
     "kjc_index_create": (_i, [_i, _u64, _u64, _i, C.POINTER(_vp)]),
     "kjc_index_destroy": (None, [_vp]),
     "kjc_index_len": (_u64, [_vp]),

@@ -115,6 +115,12 @@ class EncoderModel:
         N.lib().kjc_softmax_rows(_ptr(logits), logits.shape[0], logits.shape[1])
         return logits
 
+    def classify_multi_label(self, input_ids, attention_mask, token_type_ids=None) -> np.ndarray:
+        """ClassificationMode::MultiLabel: raw logits -> sigmoid per label (kjarni/src/classifier/model.rs:313-335,528-531)."""
+        logits = self.predict_logits(input_ids, attention_mask, token_type_ids)
+        N.lib().kjc_sigmoid_rows(_ptr(logits), logits.shape[0], logits.shape[1])
+        return logits
+
     def predict_pairs(self, input_ids, attention_mask, token_type_ids) -> np.ndarray:
         """Cross-encoder relevance scores = logits[:, 0] (raw) (KM/models/cross_encoder/model.rs:239)."""
         return self.predict_logits(input_ids, attention_mask, token_type_ids)[:, 0].copy()

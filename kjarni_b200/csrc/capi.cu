@@ -135,6 +135,13 @@ void kjc_softmax_rows(float* x, int rows, int cols) {
     }
 }
 
+void kjc_sigmoid_rows(float* x, int rows, int cols) {
+    // multi-label scores: sigmoid(x) = 1 / (1 + exp(-x)) per logit (kjarni/src/classifier/model.rs:313-335,528-531)
+    if (!x) return;
+    const size_t n = static_cast<size_t>(rows) * cols;
+    for (size_t i = 0; i < n; ++i) x[i] = 1.0f / (1.0f + expf(-x[i]));
+}
+
 // -------------------------------------------------------------------- index
 int kjc_index_create(int dim, uint64_t capacity_rows, uint64_t id_base, int device, KjcIndex** out) {
     KJC_REQUIRE(out);

@@ -281,7 +281,9 @@ Encoder::Encoder(const std::string& dir, int device) {
     if (cfg.type != Json::Obj) throw Error(KJC_INVALID_CONFIG, "config.json is not an object");
     SafeTensors st(dir + "/model.safetensors");
 
-    const std::string model_type = cfg.string("model_type", "bert");
+    std::string model_type = cfg.string("model_type", "bert");
+    for (char& c : model_type) c = static_cast<char>(tolower(static_cast<unsigned char>(c)));  // eq_ignore_ascii_case, model_weights.rs:197-211
+    int pos_offset = 0;
     std::string ep, lp;  // embedding prefix, layer prefix (with "{}" for the index)
     const char *nq, *nk, *nv, *no, *nln1, *nf1, *nf2, *nln2;
     int H, L, heads, max_pos, vocab;
@@ -300,8 +302,40 @@ Encoder::Encoder(const std::string& dir, int device) {
         lp = "distilbert.transformer.layer.";
         nq = "attention.q_lin"; nk = "attention.k_lin"; nv = "attention.v_lin"; no = "attention.out_lin";
         nln1 = "sa_layer_norm"; nf1 = "ffn.lin1"; nf2 = "ffn.lin2"; nln2 = "output_layer_norm";
-    } else if (model_type == "roberta" || model_type == "distilroberta" || model_type == "mpnet" || model_type == "xlm-roberta") {
-        throw Error(KJC_INVALID_CONFIG, "model_type '" + model_type + "' (RoBERTa/MPNet layouts) is not supported by the CUDA backend yet");
+    } else if (model_type == "roberta" || model_type == "distilroberta") {
+        // RobertaConfig, KM/models/sequence_classifier/configs.rs:147-283 (also what SentenceEncoder::load_config picks for
+        // RoBERTa, KM/models/sentence_encoder/model.rs:46-47): `roberta.` prefix, positions start at row 2
+        info_.arch = KJC_ARCH_ROBERTA;
+        H = json_int(cfg, "hidden_size");
+        L = json_int(cfg, "num_hidden_layers");
+        heads = json_int(cfg, "num_attention_heads");
+        max_pos = json_int(cfg, "max_position_embeddings");
+        vocab = json_int(cfg, "vocab_size");
+        info_.layer_norm_eps = static_cast<float>(cfg.number("layer_norm_eps", 1e-5));
+        const std::string a = cfg.string("hidden_act", "gelu");  // configs.rs:217-222: unknown strings fall back to erf-GELU
+        act = a == "gelu_new" ? ACT_GELU_TANH : (a == "relu" ? ACT_RELU : ACT_GELU_ERF);
+        pos_offset = 2;  // extra_pos_embeddings, configs.rs:223
+        ep = "roberta.embeddings.";
+        lp = "roberta.encoder.layer.";
+        nq = "attention.self.query"; nk = "attention.self.key"; nv = "attention.self.value"; no = "attention.output.dense";
+        nln1 = "attention.output.LayerNorm"; nf1 = "intermediate.dense"; nf2 = "output.dense"; nln2 = "output.LayerNorm";
+    } else if (model_type == "mpnet") {
+        // MpnetConfig, KM/models/sentence_encoder/configs.rs:370-468: no prefix, attention.attn.{q,k,v,o}, tanh-GELU hard-coded
+        // (Activation::GeluNew :408), no token types, positions start at row 2 (:415).  As in the reference, MPNet's relative
+        // attention bias tensor is not part of the layout and is ignored.
+        info_.arch = KJC_ARCH_MPNET;
+        H = json_int(cfg, "hidden_size");
+        L = json_int(cfg, "num_hidden_layers");
+        heads = json_int(cfg, "num_attention_heads");
+        max_pos = json_int(cfg, "max_position_embeddings");
+        vocab = json_int(cfg, "vocab_size");
+        info_.layer_norm_eps = static_cast<float>(cfg.number("layer_norm_eps", 1e-5));
+        act = ACT_GELU_TANH;
+        pos_offset = 2;
+        ep = "embeddings.";
+        lp = "encoder.layer.";
+        nq = "attention.attn.q"; nk = "attention.attn.k"; nv = "attention.attn.v"; no = "attention.attn.o";
+        nln1 = "attention.LayerNorm"; nf1 = "intermediate.dense"; nf2 = "output.dense"; nln2 = "output.LayerNorm";
     } else {
         // BertConfig, KM/models/sentence_encoder/configs.rs:15-65,174-366
         const bool prefixed = cfg.has("id2label") || cfg.has("num_labels");  // is_hf_classification, configs.rs:92-95
@@ -328,7 +362,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     info_.num_heads = heads;
     info_.vocab_size = vocab;
     info_.max_position_embeddings = max_pos;
-    info_.position_offset = 0;
+    info_.position_offset = pos_offset;
     act_ = act;
 
     auto shape_is = [&](const std::string& name, std::initializer_list<int64_t> want) {
@@ -375,7 +409,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     size_t off_type = 0;
     info_.type_vocab_size = 0;
     const std::string type_name = ep + "token_type_embeddings.weight";
-    if (st.contains(type_name)) {
+    if (info_.arch != KJC_ARCH_MPNET && st.contains(type_name)) {
         const StTensor& tt = st.at(type_name);
         if (tt.shape.size() != 2 || tt.shape[1] != H) throw Error(KJC_LOAD_FAILED, "token-type table has the wrong hidden size");
         info_.type_vocab_size = static_cast<int>(tt.shape[0]);

@@ -21,6 +21,12 @@ ARCHS = {
     "minilm-l6-cross-encoder": ("bert_prefixed", 384, 6, 12, 1536, 30522, 512, 2, 1),
     "distilbert-sst2": ("distilbert", 768, 6, 12, 3072, 30522, 512, 0, 2),
     "bert-base": ("bert", 768, 12, 12, 3072, 30522, 512, 2, 0),
+    # RoBERTa-family classifier (distilroberta-emotion shape: 7 labels, classifier.dense + out_proj head)
+    # and MPNet sentence encoder (all-mpnet-base-v2 shape); both take positions from row 2 of the table
+    "distilroberta-emotion": ("roberta", 768, 6, 12, 3072, 50265, 514, 1, 7),
+    "mpnet-base": ("mpnet", 768, 12, 12, 3072, 30527, 514, 0, 0),
+    "tiny-roberta": ("roberta", 64, 2, 4, 256, 1000, 66, 1, 3),
+    "tiny-mpnet": ("mpnet", 64, 2, 4, 256, 1000, 66, 0, 0),
     # tiny shapes for CPU-speed tests
     "tiny-bert": ("bert", 64, 2, 4, 256, 1000, 64, 2, 0),
     "tiny-cross-encoder": ("bert_prefixed", 64, 2, 4, 256, 1000, 64, 2, 1),
@@ -64,8 +70,12 @@ def make_weights(arch: str, seed: int = 1234) -> Tuple[Dict[str, np.ndarray], di
         ep, lp = "distilbert.embeddings.", "distilbert.transformer.layer.{}."
         n = dict(q="attention.q_lin", k="attention.k_lin", v="attention.v_lin", o="attention.out_lin",
                  ln1="sa_layer_norm", f1="ffn.lin1", f2="ffn.lin2", ln2="output_layer_norm")
+    elif family == "mpnet":
+        ep, lp = "embeddings.", "encoder.layer.{}."
+        n = dict(q="attention.attn.q", k="attention.attn.k", v="attention.attn.v", o="attention.attn.o",
+                 ln1="attention.LayerNorm", f1="intermediate.dense", f2="output.dense", ln2="output.LayerNorm")
     else:
-        pre = "bert." if family == "bert_prefixed" else ""
+        pre = {"bert_prefixed": "bert.", "roberta": "roberta."}.get(family, "")
         ep, lp = pre + "embeddings.", pre + "encoder.layer.{}."
         n = dict(q="attention.self.query", k="attention.self.key", v="attention.self.value",
                  o="attention.output.dense", ln1="attention.output.LayerNorm",
@@ -92,6 +102,18 @@ def make_weights(arch: str, seed: int = 1234) -> Tuple[Dict[str, np.ndarray], di
         cfg = dict(model_type="distilbert", activation="gelu", dim=H, hidden_dim=I, n_layers=L, n_heads=heads,
                    max_position_embeddings=max_pos, vocab_size=vocab,
                    id2label={"0": "NEGATIVE", "1": "POSITIVE"}, label2id={"NEGATIVE": 0, "POSITIVE": 1})
+    elif family == "roberta":
+        t["classifier.dense.weight"] = mat(H, H, std=0.05)
+        t["classifier.dense.bias"] = bias(H)
+        t["classifier.out_proj.weight"] = mat(num_labels, H, std=0.5)
+        t["classifier.out_proj.bias"] = bias(num_labels)
+        cfg = dict(model_type="roberta", hidden_size=H, num_hidden_layers=L, num_attention_heads=heads, intermediate_size=I,
+                   vocab_size=vocab, layer_norm_eps=1e-5, hidden_act="gelu", type_vocab_size=type_vocab,
+                   max_position_embeddings=max_pos, position_embedding_type="absolute", pad_token_id=1,
+                   id2label={str(i): f"LABEL_{i}" for i in range(num_labels)})
+    elif family == "mpnet":
+        cfg = dict(model_type="mpnet", hidden_size=H, num_hidden_layers=L, num_attention_heads=heads, intermediate_size=I,
+                   vocab_size=vocab, layer_norm_eps=1e-5, hidden_act="gelu", max_position_embeddings=max_pos)
     else:
         cfg = dict(model_type="bert", hidden_size=H, num_hidden_layers=L, num_attention_heads=heads,
                    intermediate_size=I, vocab_size=vocab, layer_norm_eps=1e-12, hidden_act="gelu",

@@ -301,7 +301,7 @@ def classification_head(
 # --------------------------------------------------------------------------- #
 @dataclass
 class EncoderModel:
-    arch: str  # 'bert' | 'bert_prefixed' | 'distilbert'
+    arch: str  # 'bert' | 'bert_prefixed' | 'distilbert' | 'roberta' | 'mpnet'
     hidden: int
     layers: int
     heads: int
@@ -318,6 +318,7 @@ class EncoderModel:
     w_cls: Optional[np.ndarray] = None
     b_cls: Optional[np.ndarray] = None
     position_offset: int = 0
+    act: str = "gelu"  # 'gelu' (erf) | 'gelu_new' (tanh) | 'relu'
     labels: List[str] = field(default_factory=list)
 
 
@@ -359,8 +360,35 @@ def load_model_dir(model_dir: str) -> EncoderModel:
     with open(os.path.join(model_dir, "config.json")) as f:
         cfg = json.load(f)
     t = _read_safetensors(os.path.join(model_dir, "model.safetensors"))
-    mt = cfg.get("model_type", "bert")
-    if mt == "distilbert":
+    mt = str(cfg.get("model_type", "bert")).lower()
+    act, pos_off = "gelu", 0
+    if mt in ("roberta", "distilroberta"):
+        # RobertaConfig, KM/models/sequence_classifier/configs.rs:147-283 (extra_pos_embeddings 2 :223; act map :217-222)
+        arch = "roberta"
+        hidden, layers, heads = cfg["hidden_size"], cfg["num_hidden_layers"], cfg["num_attention_heads"]
+        eps = float(cfg["layer_norm_eps"])
+        act = {"gelu": "gelu", "gelu_new": "gelu_new", "relu": "relu"}.get(cfg["hidden_act"], "gelu")
+        pos_off = 2
+        ep = "roberta.embeddings."
+        lp = "roberta.encoder.layer.{}."
+        names = dict(
+            q="attention.self.query", k="attention.self.key", v="attention.self.value",
+            o="attention.output.dense", ln1="attention.output.LayerNorm",
+            f1="intermediate.dense", f2="output.dense", ln2="output.LayerNorm",
+        )
+    elif mt == "mpnet":
+        # MpnetConfig, KM/models/sentence_encoder/configs.rs:370-468: GeluNew hard-coded (:408), offset 2 (:415), no token types
+        arch = "mpnet"
+        hidden, layers, heads = cfg["hidden_size"], cfg["num_hidden_layers"], cfg["num_attention_heads"]
+        eps = float(cfg["layer_norm_eps"])
+        act, pos_off = "gelu_new", 2
+        ep = "embeddings."
+        lp = "encoder.layer.{}."
+        names = dict(
+            q="attention.attn.q", k="attention.attn.k", v="attention.attn.v", o="attention.attn.o",
+            ln1="attention.LayerNorm", f1="intermediate.dense", f2="output.dense", ln2="output.LayerNorm",
+        )
+    elif mt == "distilbert":
         arch = "distilbert"
         hidden, layers, heads = cfg["dim"], cfg["n_layers"], cfg["n_heads"]
         eps = 1e-12  # hard-coded, configs.rs:620
@@ -376,6 +404,7 @@ def load_model_dir(model_dir: str) -> EncoderModel:
         arch = "bert_prefixed" if prefixed else "bert"
         hidden, layers, heads = cfg["hidden_size"], cfg["num_hidden_layers"], cfg["num_attention_heads"]
         eps = float(cfg.get("layer_norm_eps", 1e-12))
+        act = {"gelu": "gelu", "gelu_new": "gelu_new", "relu": "relu"}[cfg.get("hidden_act", "gelu")]  # configs.rs:194-200
         pre = "bert." if arch == "bert_prefixed" else ""
         ep = pre + "embeddings."
         lp = pre + "encoder.layer.{}."
@@ -406,8 +435,9 @@ def load_model_dir(model_dir: str) -> EncoderModel:
     m = EncoderModel(
         arch=arch, hidden=hidden, layers=layers, heads=heads, eps=eps,
         word=t[ep + "word_embeddings.weight"], pos=t[ep + "position_embeddings.weight"],
-        typ=opt(ep + "token_type_embeddings.weight"),
+        typ=None if arch == "mpnet" else opt(ep + "token_type_embeddings.weight"),
         emb_g=t[ep + "LayerNorm.weight"], emb_b=t[ep + "LayerNorm.bias"], layer=ls,
+        position_offset=pos_off, act=act,
     )
     # head auto-detection, first match wins (classifier.rs:113-206)
     if "classifier.dense.weight" in t:
@@ -445,7 +475,7 @@ def encoder_forward(
     x = layer_norm(x, m.emb_g, m.emb_b, m.eps)
     maskf = np.asarray(mask, dtype=F32)
     for lw in m.layer:
-        x = encoder_layer(x, maskf, lw, m.heads, m.eps, noalloc=noalloc)
+        x = encoder_layer(x, maskf, lw, m.heads, m.eps, noalloc=noalloc, act=m.act)
     return x
 
 

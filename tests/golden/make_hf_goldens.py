@@ -27,7 +27,16 @@ def load_hf(arch, d):
     t, cfg = synth.make_weights(arch)
     family = synth.ARCHS[arch][0]
     sd = {k: torch.from_numpy(v.copy()) for k, v in t.items()}
-    if family == "distilbert":
+    if family == "roberta":
+        from transformers import RobertaConfig, RobertaForSequenceClassification
+
+        c = RobertaConfig(vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"], num_hidden_layers=cfg["num_hidden_layers"],
+                          num_attention_heads=cfg["num_attention_heads"], intermediate_size=cfg["intermediate_size"],
+                          hidden_act="gelu", layer_norm_eps=cfg["layer_norm_eps"], type_vocab_size=cfg["type_vocab_size"],
+                          max_position_embeddings=cfg["max_position_embeddings"], hidden_dropout_prob=0.0,
+                          attention_probs_dropout_prob=0.0, classifier_dropout=0.0, num_labels=len(cfg["id2label"]), pad_token_id=1)
+        m = RobertaForSequenceClassification(c)
+    elif family == "distilbert":
         c = DistilBertConfig(vocab_size=cfg["vocab_size"], dim=cfg["dim"], hidden_dim=cfg["hidden_dim"],
                              n_layers=cfg["n_layers"], n_heads=cfg["n_heads"], activation="gelu",
                              max_position_embeddings=cfg["max_position_embeddings"], num_labels=2,
@@ -49,7 +58,7 @@ def load_hf(arch, d):
 
 def main():
     out = {}
-    cases = [("tiny-bert", 6, 16), ("tiny-cross-encoder", 6, 16), ("tiny-distilbert", 6, 16), ("minilm-l6", 4, 32)]
+    cases = [("tiny-bert", 6, 16), ("tiny-cross-encoder", 6, 16), ("tiny-distilbert", 6, 16), ("minilm-l6", 4, 32), ("tiny-roberta", 6, 16)]
     for arch, B, S in cases:
         family, H, L, heads, I, vocab = synth.ARCHS[arch][:6]
         ids, mask, types = synth.synth_tokens(B, S, vocab, regime="P", seed=7, pair=(family == "bert_prefixed"))
@@ -65,6 +74,13 @@ def main():
                 e = e / np.linalg.norm(e, axis=1, keepdims=True)
                 out[arch + "/hidden_valid"] = (h * mf[:, :, None]).astype(np.float32)
                 out[arch + "/embedding"] = e.astype(np.float32)
+            elif family == "roberta":
+                # Kjarni adds position rows offset+s = 2+s to token s (extra_pos_embeddings 2,
+                # KM/models/sequence_classifier/configs.rs:223 -> KT/cpu/embeddings/mod.rs:199-214); HF derives the same rows
+                # from padding_idx for left-aligned text, given explicitly here so pad ids play no role
+                pos = torch.arange(2, 2 + S).unsqueeze(0).expand(B, S)
+                lg = m(input_ids=ti, attention_mask=tm, position_ids=pos, token_type_ids=torch.zeros_like(ti)).logits
+                out[arch + "/logits"] = lg.numpy().astype(np.float32)
             elif family == "bert_prefixed":
                 lg = m(input_ids=ti, attention_mask=tm, token_type_ids=torch.from_numpy(types.astype(np.int64))).logits
                 out[arch + "/logits"] = lg.numpy().astype(np.float32)

@@ -21,14 +21,16 @@ COS_MIN, MAXABS = 0.9995, 2e-2
 def dirs(tmp_path_factory):
     root = tmp_path_factory.mktemp("models")
     return {a: synth.write_model_dir(str(root / a), a) for a in
-            ("tiny-bert", "tiny-cross-encoder", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2")}
+            ("tiny-bert", "tiny-cross-encoder", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2",
+             "tiny-roberta", "tiny-mpnet", "distilroberta-emotion", "mpnet-base")}
 
 
 def centred_cos(a, b):
     return cosine_rows(a - a.mean(0, keepdims=True), b - b.mean(0, keepdims=True))
 
 
-@pytest.mark.parametrize("arch,B,S", [("tiny-bert", 6, 16), ("tiny-bert", 70, 24), ("minilm-l6", 4, 32), ("minilm-l6", 32, 128)])
+@pytest.mark.parametrize("arch,B,S", [("tiny-bert", 6, 16), ("tiny-bert", 70, 24), ("minilm-l6", 4, 32), ("minilm-l6", 32, 128),
+                                      ("tiny-mpnet", 6, 16), ("tiny-mpnet", 5, 64), ("mpnet-base", 8, 128)])
 def test_embedding_matches_oracle(dirs, arch, B, S):
     vocab = synth.ARCHS[arch][5]
     ids, mask, _ = synth.synth_tokens(B, S, vocab, regime="P", seed=7)
@@ -70,7 +72,8 @@ def test_embedding_matches_hf_goldens(dirs):
 
 
 @pytest.mark.parametrize("arch,B,S,pair", [("tiny-distilbert", 6, 16, False), ("tiny-cross-encoder", 6, 16, True),
-                                           ("distilbert-sst2", 16, 128, False), ("minilm-l6-cross-encoder", 12, 256, True)])
+                                           ("distilbert-sst2", 16, 128, False), ("minilm-l6-cross-encoder", 12, 256, True),
+                                           ("tiny-roberta", 6, 16, False), ("distilroberta-emotion", 8, 128, False)])
 def test_logits_match_oracle(dirs, arch, B, S, pair):
     vocab = synth.ARCHS[arch][5]
     ids, mask, types = synth.synth_tokens(B, S, vocab, regime="P", seed=11, pair=pair)
@@ -107,7 +110,7 @@ def test_logits_match_oracle(dirs, arch, B, S, pair):
 
 
 def test_hf_golden_logits(dirs):
-    for arch, pair in (("tiny-cross-encoder", True), ("tiny-distilbert", False)):
+    for arch, pair in (("tiny-cross-encoder", True), ("tiny-distilbert", False), ("tiny-roberta", False)):
         B, S = (int(v) for v in G[arch + "/shape"])
         ids, mask, types = synth.synth_tokens(B, S, synth.ARCHS[arch][5], regime="P", seed=7, pair=pair)
         enc = api.EncoderModel(dirs[arch])
@@ -167,3 +170,22 @@ def test_edge_cases(dirs):
     with pytest.raises(N.KjarniCudaError) as e:
         api.EncoderModel("/nonexistent/dir")
     assert e.value.status == 3
+
+
+def test_roberta_mpnet_layouts_and_multi_label(dirs):
+    """positions start at row 2 of the table (and stop adding beyond it), multi-label sigmoid scores."""
+    enc = api.EncoderModel(dirs["tiny-roberta"])
+    m = ko.load_model_dir(dirs["tiny-roberta"])
+    assert enc.arch == "roberta" and enc.info.position_offset == 2 and enc.info.type_vocab_size == 1 and enc.head_kind == "dense_tanh"
+    assert enc.labels == ["LABEL_0", "LABEL_1", "LABEL_2"]
+    # S = 66 = table rows: the last two tokens sit beyond the table and get no position row (embeddings/mod.rs:199-214)
+    ids, mask, _ = synth.synth_tokens(3, 66, 1000, regime="T", seed=5)
+    want = ko.predict_logits(m, ids, mask)
+    got = enc.predict_logits(ids, mask)
+    assert np.abs(got - want).max() <= 5e-2 * max(1.0, float(np.abs(want).max()))
+    sig = enc.classify_multi_label(ids, mask)
+    assert np.allclose(sig, 1.0 / (1.0 + np.exp(-got)), atol=1e-6) and ((sig > 0) & (sig < 1)).all()
+    enc.close()
+    enc = api.EncoderModel(dirs["tiny-mpnet"])
+    assert enc.arch == "mpnet" and enc.info.position_offset == 2 and enc.info.type_vocab_size == 0 and enc.head_kind is None
+    enc.close()

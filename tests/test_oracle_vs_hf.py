@@ -15,7 +15,7 @@ G = np.load(os.path.join(os.path.dirname(__file__), "golden", "hf_goldens.npz"))
 def model_dirs(tmp_path_factory):
     root = tmp_path_factory.mktemp("models")
     return {a: synth.write_model_dir(str(root / a), a) for a in
-            ("tiny-bert", "tiny-cross-encoder", "tiny-distilbert", "minilm-l6")}
+            ("tiny-bert", "tiny-cross-encoder", "tiny-distilbert", "minilm-l6", "tiny-roberta", "tiny-mpnet")}
 
 
 @pytest.mark.parametrize("arch", ["tiny-bert", "minilm-l6"])
@@ -56,3 +56,33 @@ def test_distilbert_classifier_matches_hf(model_dirs):
     assert np.abs(lg - G[arch + "/logits"]).max() < 2e-5
     p = ko.classify_probs(lg)
     assert np.allclose(p.sum(1), 1, atol=1e-6)
+
+
+def test_roberta_classifier_matches_hf(model_dirs):
+    """`roberta.` layout, positions from row 2, classifier.dense + tanh + out_proj head."""
+    arch = "tiny-roberta"
+    B, S = G[arch + "/shape"]
+    ids, mask, _ = synth.synth_tokens(int(B), int(S), synth.ARCHS[arch][5], regime="P", seed=7)
+    m = ko.load_model_dir(model_dirs[arch])
+    assert m.arch == "roberta" and m.head_kind == "dense_tanh" and m.position_offset == 2 and m.typ.shape[0] == 1
+    lg = ko.predict_logits(m, ids, mask)
+    assert lg.shape == (B, 3)
+    assert np.abs(lg - G[arch + "/logits"]).max() < 2e-5
+    m.position_offset = 0  # the offset matters: without it the logits move well outside the tolerance
+    assert np.abs(ko.predict_logits(m, ids, mask) - G[arch + "/logits"]).max() > 1e-3
+
+
+def test_mpnet_layout_loads_with_reference_semantics(model_dirs):
+    """MpnetConfig (KM/models/sentence_encoder/configs.rs:370-468): tanh-GELU hard-coded, offset 2, no token types.  HF's
+    MPNetModel adds a relative attention bias that Kjarni's layout does not load, so there is no HF golden for it; the
+    oracle is checked here against a hand-assembled forward from the same primitives."""
+    arch = "tiny-mpnet"
+    ids, mask, _ = synth.synth_tokens(4, 12, synth.ARCHS[arch][5], regime="P", seed=3)
+    m = ko.load_model_dir(model_dirs[arch])
+    assert m.arch == "mpnet" and m.act == "gelu_new" and m.position_offset == 2 and m.typ is None and m.head_kind is None
+    x = ko.embeddings_forward(ids, m.word, m.pos, None, None, 2)
+    assert np.array_equal(x[0, 3], (m.word[ids[0, 3]] + m.pos[5]).astype(np.float32))
+    x = ko.layer_norm(x, m.emb_g, m.emb_b, m.eps)
+    for lw in m.layer:
+        x = ko.encoder_layer(x, mask.astype(np.float32), lw, m.heads, m.eps, noalloc=False, act="gelu_new")
+    assert np.array_equal(x, ko.encoder_forward(m, ids, mask, None, noalloc=False))
