@@ -170,6 +170,25 @@ void kjc_softmax_rows(float* logits, int rows, int cols);
  * Host-side helper. */
 void kjc_sigmoid_rows(float* logits, int rows, int cols);
 
+/* ---------------------------------------------------------------- tokenizer
+ * Text -> ids for the WordPiece / WordLevel tokenizer.json files of the BERT-family checkpoints, with the configuration
+ * EncoderLoader applies (KT/pipeline/encoder/loader.rs:99-115): truncation to `max_length` (LongestFirst, right) and
+ * BatchLongest padding with id 0; pairs are encoded as `[CLS] a [SEP] b [SEP]` with type ids 0/1 by the file's
+ * post-processor (KM/models/cross_encoder/model.rs:176-194).  Host-only; restates the `tokenizers` 0.22 crate's published
+ * algorithm (kjarni_b200/csrc/tokenizer.hpp), pinned by goldens from that crate's Python binding. */
+typedef struct KjcTokenizer KjcTokenizer;
+/* max_length <= 0: no truncation.  Errors: KJC_MODEL_NOT_FOUND, KJC_LOAD_FAILED (bad JSON), KJC_INVALID_CONFIG (BPE /
+ * Unigram models, unsupported normalizer / pre-tokenizer / post-processor). */
+int kjc_tokenizer_create(const char* tokenizer_json_path, int max_length, KjcTokenizer** out);
+void kjc_tokenizer_destroy(KjcTokenizer* tok);
+/* Tokenizer::token_to_id: 1 and *out_id set when the token is in the vocabulary (or an added token), else 0. */
+int kjc_tokenizer_token_to_id(const KjcTokenizer* tok, const char* token, uint32_t* out_id);
+/* encode_batch(texts, add_special_tokens): `pairs` NULL or one second segment per text.  *out_seq_len = padded length.
+ * ids NULL: only the length is computed; otherwise ids / mask / type_ids are [n, cap_seq] (mask, type_ids may be NULL)
+ * and cap_seq >= *out_seq_len is required (KJC_INVALID_CONFIG otherwise); columns beyond the length are zero. */
+int kjc_tokenizer_encode_batch(const KjcTokenizer* tok, const char* const* texts, const char* const* pairs, int n, int add_special_tokens,
+                               uint32_t* ids, float* mask, uint32_t* type_ids, int cap_seq, int* out_seq_len);
+
 /* ---------------------------------------------------------------- index scan */
 
 typedef struct KjcIndex KjcIndex;

@@ -71,6 +71,10 @@ SIGNATURES = {
     "kjc_encoder_get_profile": (_i, [_vp, _vp, _vp]),
     "kjc_softmax_rows": (None, [_vp, _i, _i]),
     "kjc_sigmoid_rows": (None, [_vp, _i, _i]),
+    "kjc_tokenizer_create": (_i, [C.c_char_p, _i, C.POINTER(_vp)]),
+    "kjc_tokenizer_destroy": (None, [_vp]),
+    "kjc_tokenizer_token_to_id": (_i, [_vp, C.c_char_p, C.POINTER(C.c_uint32)]),
+    "kjc_tokenizer_encode_batch": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_i)]),
     "kjc_index_create": (_i, [_i, _u64, _u64, _i, C.POINTER(_vp)]),
     "kjc_index_destroy": (None, [_vp]),
     "kjc_index_len": (_u64, [_vp]),

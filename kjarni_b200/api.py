@@ -139,6 +139,44 @@ class EncoderModel:
         return int(N.lib().kjc_encoder_last_launch_count(self._h))
 
 
+class Tokenizer:
+    """tokenizer.json -> ids with the reference's settings (KjcTokenizer; KT/pipeline/encoder/loader.rs:99-115):
+    truncation to `max_length`, BatchLongest padding with id 0, special tokens from the file's post-processor."""
+
+    def __init__(self, tokenizer_json: str, max_length: int = 512):
+        self._h = C.c_void_p()
+        N.check(N.lib().kjc_tokenizer_create(str(tokenizer_json).encode(), int(max_length), C.byref(self._h)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().kjc_tokenizer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def token_to_id(self, token: str) -> Optional[int]:
+        out = C.c_uint32()
+        return int(out.value) if N.lib().kjc_tokenizer_token_to_id(self._h, token.encode(), C.byref(out)) else None
+
+    def encode_batch(self, texts: Sequence[str], pairs: Optional[Sequence[str]] = None, add_special_tokens: bool = True):
+        """(ids u32 [n,S], attention_mask f32 [n,S], type_ids u32 [n,S])"""
+        n = len(texts)
+        ta = (C.c_char_p * max(n, 1))(*[t.encode("utf-8") for t in texts])
+        tb = None if pairs is None else (C.c_char_p * max(n, 1))(*[t.encode("utf-8") for t in pairs])
+        S = C.c_int()
+        N.check(N.lib().kjc_tokenizer_encode_batch(self._h, ta, tb, n, 1 if add_special_tokens else 0, None, None, None, 0, C.byref(S)))
+        s = max(S.value, 1)
+        ids = np.zeros((n, s), np.uint32)
+        mask = np.zeros((n, s), np.float32)
+        types = np.zeros((n, s), np.uint32)
+        N.check(N.lib().kjc_tokenizer_encode_batch(self._h, ta, tb, n, 1 if add_special_tokens else 0, _ptr(ids), _ptr(mask), _ptr(types), s, C.byref(S)))
+        return ids[:, :S.value], mask[:, :S.value], types[:, :S.value]
+
+
 def scores_to_top_k(probs: np.ndarray, labels: Sequence[str], k: int) -> List[Tuple[str, float]]:
     """Stable sort descending => ties resolve to the lowest label index (KM/models/sequence_classifier/mod.rs:369-390)."""
     order = np.argsort(-np.asarray(probs, np.float32), kind="stable")[:k]

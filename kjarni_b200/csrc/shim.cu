@@ -1,0 +1,731 @@
+// Public kjarni-ffi C ABI (include/kjarni_ffi.h) over the B200 backend: the text-level handles the C#/Go/Python bindings
+// use -- Embedder, Classifier, Reranker, Searcher -- built from Tokenizer (tokenizer.hpp) + Encoder (encoder.cu) + Index
+// (index.cu).  Each function restates the control flow of its reference counterpart in kjarni-ffi/src/*.rs (cited in the
+// header) with the model forward, the pooling/head and the cosine scan running on the GPU.
+#include <fnmatch.h>
+
+#include <cmath>
+#include <map>
+#include <mutex>
+
+#include "../../include/kjarni_ffi.h"
+#include "index.hpp"
+#include "tokenizer.hpp"
+
+namespace kj {
+namespace {
+
+struct Fail {
+    int code;
+    std::string msg;
+};
+
+bool file_ok(const std::string& p) {
+    struct stat sb;
+    return stat(p.c_str(), &sb) == 0 && S_ISREG(sb.st_mode);
+}
+std::string lower(std::string s) {
+    for (char& c : s) c = static_cast<char>(tolower(static_cast<unsigned char>(c)));
+    return s;
+}
+
+// ModelType::from_cli_name + repo_id().replace('/', "_") for the encoder-family entries of the registry
+// (kjarni-transformers/src/models/registry.rs:226-262,754-800,809-811,851-860; weights_url lines :318-478)
+const char* registry_dir(const std::string& name_in) {
+    static const std::pair<const char*, const char*> table[] = {
+        {"minilm-l6-v2", "sentence-transformers_all-MiniLM-L6-v2"},
+        {"all-minilm-l6-v2", "sentence-transformers_all-MiniLM-L6-v2"},
+        {"sentence-transformers/all-minilm-l6-v2", "sentence-transformers_all-MiniLM-L6-v2"},
+        {"mpnet-base-v2", "sentence-transformers_all-mpnet-base-v2"},
+        {"all-mpnet-base-v2", "sentence-transformers_all-mpnet-base-v2"},
+        {"sentence-transformers/all-mpnet-base-v2", "sentence-transformers_all-mpnet-base-v2"},
+        {"distilbert-base", "distilbert-base-cased-distilled-squad_resolve"},  // the URL heuristic takes parts[3]/parts[4] (:851-860)
+        {"minilm-l6-v2-cross-encoder", "cross-encoder_ms-marco-MiniLM-L-6-v2"},
+        {"ms-marco-minilm-l-6-v2", "cross-encoder_ms-marco-MiniLM-L-6-v2"},
+        {"cross-encoder/ms-marco-minilm-l-6-v2", "cross-encoder_ms-marco-MiniLM-L-6-v2"},
+        {"sentiment", "distilbert_distilbert-base-uncased-finetuned-sst-2-english"},  // Classifier::builder("sentiment") default preset
+        {"distilbert-sentiment", "distilbert_distilbert-base-uncased-finetuned-sst-2-english"},
+        {"distilbert-base-uncased-finetuned-sst-2-english", "distilbert_distilbert-base-uncased-finetuned-sst-2-english"},
+        {"roberta-sentiment", "olafuraron_twitter-roberta-base-sentiment-latest-safetensors"},
+        {"twitter-roberta-base-sentiment-latest", "olafuraron_twitter-roberta-base-sentiment-latest-safetensors"},
+        {"bert-sentiment-multilingual", "olafuraron_bert-base-multilingual-uncased-sentiment-safetensors"},
+        {"bert-base-multilingual-uncased-sentiment", "olafuraron_bert-base-multilingual-uncased-sentiment-safetensors"},
+        {"roberta-emotions", "SamLowe_roberta-base-go_emotions"},
+        {"roberta-base-go_emotions", "SamLowe_roberta-base-go_emotions"},
+        {"distilroberta-emotion", "olafuraron_emotion-english-distilroberta-base-safetensors"},
+        {"emotion-english-distilroberta-base", "olafuraron_emotion-english-distilroberta-base-safetensors"},
+        {"toxic-bert", "olafuraron_toxic-bert-safetensors"},
+    };
+    const std::string name = lower(name_in);
+    for (auto& e : table)
+        if (name == e.first) return e.second;
+    return nullptr;
+}
+
+std::string default_cache_dir() {
+    // get_default_cache_dir, registry.rs:958-966: $KJARNI_CACHE_DIR, else dirs::cache_dir()/kjarni
+    if (const char* e = getenv("KJARNI_CACHE_DIR")) return e;
+    if (const char* x = getenv("XDG_CACHE_HOME"))
+        if (*x) return std::string(x) + "/kjarni";
+    const char* home = getenv("HOME");
+    return std::string(home ? home : ".") + "/.cache/kjarni";
+}
+
+const char* cstr_or_null(const char* p, bool& bad_utf8) {
+    if (p && !uni::valid_utf8(p)) bad_utf8 = true;
+    return p;
+}
+
+// Resolves the model directory the way the builders do; throws Fail{ModelNotFound} when it is not on disk (no download here).
+std::string resolve_model_dir(const char* cache_dir, const char* model_name, const char* model_path, const char* default_name) {
+    if (model_path && *model_path) {
+        struct stat sb;
+        if (stat(model_path, &sb) != 0 || !S_ISDIR(sb.st_mode)) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, std::string("Model path does not exist: ") + model_path};
+        return model_path;
+    }
+    const std::string name = (model_name && *model_name) ? model_name : default_name;
+    const char* dir = registry_dir(name);
+    if (!dir) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, "Unknown model: '" + name + "'"};
+    const std::string root = (cache_dir && *cache_dir) ? cache_dir : default_cache_dir();
+    const std::string d = root + "/" + dir;
+    // ModelType::is_downloaded, registry.rs:814-827
+    if (!file_ok(d + "/config.json") || !file_ok(d + "/tokenizer.json") || !file_ok(d + "/model.safetensors"))
+        throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, "Model '" + name + "' not downloaded (expected config.json, tokenizer.json, model.safetensors in " + d +
+                                                     "); this backend never downloads"};
+    return d;
+}
+
+// One text model on cuda:0: tokenizer + encoder (EncoderLoader::load_from_pretrained, pipeline/encoder/loader.rs:82-141)
+struct TextModel {
+    std::unique_ptr<Encoder> enc;
+    std::unique_ptr<Tokenizer> tok;
+    std::string name;
+
+    TextModel(const std::string& dir, const std::string& nm) : name(nm) {
+        if (!file_ok(dir + "/tokenizer.json")) throw Fail{KJARNI_ERROR_LOAD_FAILED, "Tokenizer not found at \"" + dir + "/tokenizer.json\""};
+        enc.reset(new Encoder(dir, 0));
+        tok.reset(new Tokenizer(dir + "/tokenizer.json", enc->info().max_position_embeddings));  // truncation max_length = meta.max_seq_len
+    }
+
+    // texts (+ optional second segments) -> [n, out_cols] through one encoder forward
+    void run(const std::vector<std::string>& a, const std::vector<std::string>& b, const KjcForwardOptions& o, bool with_types, std::vector<float>& out,
+             size_t out_cols) {
+        std::vector<uint32_t> ids, types;
+        std::vector<float> mask;
+        int S = 0;
+        tok->encode_batch(a, b, true, ids, mask, types, S);
+        if (S == 0) throw Error(KJC_INFERENCE_FAILED, "Tokenizer produced an empty batch");
+        out.assign(a.size() * out_cols, 0.f);
+        const bool types_ok = with_types && enc->info().type_vocab_size > 0;
+        enc->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(a.size()), S, o, out.data());
+    }
+};
+
+int device_check(KjarniDevice d) {
+    if (d != KJARNI_DEVICE_GPU) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "libkjarni_cuda serves KJARNI_DEVICE_GPU only: there is no CPU path in this library"};
+    return 0;
+}
+
+template <typename F>
+KjarniErrorCode guarded(KjarniErrorCode on_error, F&& f, bool passthrough = false) {
+    try {
+        f();
+        return KJARNI_OK;
+    } catch (const Fail& e) {
+        set_last_error(e.msg);
+        return static_cast<KjarniErrorCode>(e.code);
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        // construction paths surface the backend's own status; inference paths collapse to InferenceFailed as the reference does
+        return (passthrough || on_error == KJARNI_ERROR_LOAD_FAILED) ? static_cast<KjarniErrorCode>(e.status) : on_error;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return on_error;
+    } catch (...) {
+        set_last_error("unknown error");
+        return KJARNI_ERROR_UNKNOWN;
+    }
+}
+
+char* dup_cstr(const std::string& s) {
+    char* p = static_cast<char*>(malloc(s.size() + 1));
+    if (!p) throw std::bad_alloc();
+    memcpy(p, s.c_str(), s.size() + 1);
+    return p;
+}
+float* dup_floats(const float* src, size_t n) {
+    float* p = static_cast<float*>(malloc(std::max<size_t>(n, 1) * sizeof(float)));
+    if (!p) throw std::bad_alloc();
+    memcpy(p, src, n * sizeof(float));
+    return p;
+}
+std::string json_escape(const std::string& s) {
+    std::string o;
+    for (unsigned char c : s) {
+        if (c == '"') o += "\\\"";
+        else if (c == '\\') o += "\\\\";
+        else if (c == '\n') o += "\\n";
+        else if (c == '\r') o += "\\r";
+        else if (c == '\t') o += "\\t";
+        else if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+        else o += static_cast<char>(c);
+    }
+    return o;
+}
+
+}  // namespace
+}  // namespace kj
+
+using namespace kj;
+
+struct KjarniEmbedder {
+    std::unique_ptr<TextModel> m;
+    bool normalize;
+    std::mutex mu;
+    void embed(const std::vector<std::string>& texts, std::vector<float>& out) {
+        std::lock_guard<std::mutex> lock(mu);
+        const KjcForwardOptions o{KJC_OUT_POOLED, KJC_POOL_MEAN, normalize ? 1 : 0, KJC_MASK_AUTO};
+        // Embedder path: no token-type ids, row 0 of the type table for every token (cpu/encoder/traits.rs:80)
+        m->run(texts, {}, o, false, out, static_cast<size_t>(m->enc->info().hidden_size));
+    }
+};
+struct KjarniClassifier {
+    std::unique_ptr<TextModel> m;
+    std::vector<std::string> labels;
+    bool multi_label;
+    std::mutex mu;
+};
+struct KjarniReranker {
+    std::unique_ptr<TextModel> m;
+    std::mutex mu;
+    void score(const std::string& query, const std::vector<std::string>& docs, std::vector<float>& out) {
+        std::lock_guard<std::mutex> lock(mu);
+        const KjcForwardOptions o{KJC_OUT_LOGITS, KJC_POOL_CLS, 0, KJC_MASK_ALLOC};
+        std::vector<std::string> q(docs.size(), query);
+        std::vector<float> logits;
+        const size_t C = static_cast<size_t>(m->enc->info().num_labels);
+        m->run(q, docs, o, true, logits, C);
+        out.resize(docs.size());
+        for (size_t i = 0; i < docs.size(); ++i) out[i] = logits[i * C];  // logits.column(0), cross_encoder/model.rs:239
+    }
+};
+struct KjarniSearcher {
+    std::unique_ptr<KjarniEmbedder> embedder;
+    std::unique_ptr<KjarniReranker> reranker;
+    KjarniSearchMode default_mode;
+    size_t default_top_k;
+    std::mutex mu;
+    // GPU shards of the index directories searched so far (the reference re-opens the index per call: IndexReader::open is an
+    // mmap there; here it is an upload, so it is kept)
+    struct Opened {
+        std::unique_ptr<Index> idx;
+        IndexDir dir;
+    };
+    std::map<std::string, Opened> opened;
+};
+
+namespace {
+
+// Segment::get_document / get_metadata (kjarni-rag/src/segment.rs:264-304) for one global id
+void fetch_doc(const IndexDir& d, uint64_t gid, std::string& text, std::vector<std::pair<std::string, std::string>>& meta) {
+    const IndexDirSegment* seg = nullptr;
+    for (const IndexDirSegment& s : d.segments)
+        if (gid >= s.global_base && gid < s.global_base + s.doc_count) { seg = &s; break; }
+    if (!seg) throw Error(KJC_INFERENCE_FAILED, "Document ID out of range");
+    const uint64_t local = gid - seg->global_base;
+    // docs.idx: bincode Vec<u64> = u64 length + offsets
+    FILE* f = fopen((seg->dir + "/docs.idx").c_str(), "rb");
+    if (!f) throw Error(KJC_INFERENCE_FAILED, "cannot open docs.idx");
+    uint64_t n = 0, off[2] = {0, 0};
+    bool ok = fread(&n, 8, 1, f) == 1 && local < n && fseek(f, static_cast<long>(8 + 8 * local), SEEK_SET) == 0 && fread(&off[0], 8, 1, f) == 1;
+    const bool has_next = ok && local + 1 < n && fread(&off[1], 8, 1, f) == 1;
+    fclose(f);
+    if (!ok) throw Error(KJC_INFERENCE_FAILED, "Document ID out of range");
+    FILE* g = fopen((seg->dir + "/docs.bin").c_str(), "rb");
+    if (!g) throw Error(KJC_INFERENCE_FAILED, "cannot open docs.bin");
+    uint64_t end;
+    if (has_next) end = off[1] - 1;  // -1 for the newline
+    else {
+        fseek(g, 0, SEEK_END);
+        end = static_cast<uint64_t>(ftell(g)) - 1;
+    }
+    text.assign(end > off[0] ? end - off[0] : 0, '\0');
+    fseek(g, static_cast<long>(off[0]), SEEK_SET);
+    if (!text.empty() && fread(&text[0], 1, text.size(), g) != text.size()) { fclose(g); throw Error(KJC_INFERENCE_FAILED, "short read in docs.bin"); }
+    fclose(g);
+    // metadata.jsonl: line `local` is a JSON object of strings
+    meta.clear();
+    FILE* h = fopen((seg->dir + "/metadata.jsonl").c_str(), "rb");
+    if (!h) throw Error(KJC_INFERENCE_FAILED, "cannot open metadata.jsonl");
+    std::string line;
+    uint64_t ln = 0;
+    int c;
+    bool found = false;
+    while ((c = fgetc(h)) != EOF) {
+        if (c == '\n') {
+            if (ln == local) { found = true; break; }
+            ++ln;
+            line.clear();
+        } else if (ln == local) line.push_back(static_cast<char>(c));
+    }
+    if (!found && ln == local && !line.empty()) found = true;
+    fclose(h);
+    if (!found) throw Error(KJC_INFERENCE_FAILED, "Document ID out of range");
+    const Json j = JsonParser(line.data(), line.size()).parse();
+    if (j.type == Json::Obj)
+        for (auto& kv : j.obj)
+            if (kv.second.type == Json::Str) meta.emplace_back(kv.first, kv.second.str);
+}
+
+const std::string* meta_get(const std::vector<std::pair<std::string, std::string>>& m, const std::string& k) {
+    for (auto& kv : m)
+        if (kv.first == k) return &kv.second;
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ runtime / errors / frees
+KjarniErrorCode kjarni_init(void) { return KJARNI_OK; }
+void kjarni_shutdown(void) {}
+const char* kjarni_version(void) { return "0.1.0+b200"; }
+void kjarni_float_array_free(const KjarniFloatArray* arr) {
+    if (arr && arr->data && arr->len > 0) free(arr->data);
+}
+void kjarni_float_2d_array_free(const KjarniFloat2DArray* arr) {
+    if (arr && arr->data && arr->rows > 0 && arr->cols > 0) free(arr->data);
+}
+void kjarni_string_free(char* s) { free(s); }
+void kjarni_string_array_free(const KjarniStringArray* arr) {
+    if (!arr || !arr->strings || arr->len == 0) return;
+    for (size_t i = 0; i < arr->len; ++i) free(arr->strings[i]);
+    free(arr->strings);
+}
+float kjarni_cosine_similarity(const float* a, const float* b, size_t len) { return kjc_cosine_similarity(a, b, len); }
+const char* kjarni_error_name(KjarniErrorCode err) { return kjc_error_name(static_cast<int>(err)); }
+const char* kjarni_error_code_to_string(KjarniErrorCode err) { return kjc_error_name(static_cast<int>(err)); }
+const char* kjarni_last_error_message(void) { return kjc_last_error_message(); }
+void kjarni_clear_error(void) { kjc_clear_error(); }
+
+#define KJ_NULLCHECK(cond)                       \
+    do {                                         \
+        if (cond) return KJARNI_ERROR_NULL_POINTER; \
+    } while (0)
+#define KJ_UTF8(p)                                                  \
+    do {                                                            \
+        if ((p) && !uni::valid_utf8(p)) return KJARNI_ERROR_INVALID_UTF8; \
+    } while (0)
+
+// ------------------------------------------------------------------ Embedder
+KjarniEmbedderConfig kjarni_embedder_config_default(void) { return KjarniEmbedderConfig{KJARNI_DEVICE_CPU, nullptr, nullptr, nullptr, 1, 0}; }
+
+KjarniErrorCode kjarni_embedder_new(const KjarniEmbedderConfig* config, KjarniEmbedder** out) {
+    KJ_NULLCHECK(!out);
+    *out = nullptr;
+    const KjarniEmbedderConfig dflt = kjarni_embedder_config_default();
+    const KjarniEmbedderConfig& c = config ? *config : dflt;
+    KJ_UTF8(c.cache_dir);
+    KJ_UTF8(c.model_name);
+    KJ_UTF8(c.model_path);
+    return guarded(KJARNI_ERROR_LOAD_FAILED, [&] {
+        device_check(c.device);
+        const std::string dir = resolve_model_dir(c.cache_dir, c.model_name, c.model_path, "minilm-l6-v2");
+        std::unique_ptr<KjarniEmbedder> e(new KjarniEmbedder);
+        e->m.reset(new TextModel(dir, c.model_name ? c.model_name : "minilm-l6-v2"));
+        e->normalize = c.normalize != 0;
+        *out = e.release();
+    });
+}
+void kjarni_embedder_free(KjarniEmbedder* e) { delete e; }
+
+KjarniErrorCode kjarni_embedder_encode(KjarniEmbedder* e, const char* text, KjarniFloatArray* out) {
+    KJ_NULLCHECK(!e || !text || !out);
+    *out = KjarniFloatArray{nullptr, 0};
+    KJ_UTF8(text);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::vector<float> v;
+        e->embed({std::string(text)}, v);
+        out->data = dup_floats(v.data(), v.size());
+        out->len = v.size();
+    });
+}
+
+KjarniErrorCode kjarni_embedder_encode_batch(KjarniEmbedder* e, const char* const* texts, size_t n, KjarniFloat2DArray* out) {
+    KJ_NULLCHECK(!e || !texts || !out);
+    *out = KjarniFloat2DArray{nullptr, 0, 0};
+    if (n == 0) return KJARNI_OK;
+    std::vector<std::string> tv;
+    tv.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        KJ_NULLCHECK(!texts[i]);
+        KJ_UTF8(texts[i]);
+        tv.emplace_back(texts[i]);
+    }
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::vector<float> v;
+        e->embed(tv, v);
+        out->data = dup_floats(v.data(), v.size());
+        out->rows = n;
+        out->cols = v.size() / n;
+    });
+}
+
+KjarniErrorCode kjarni_embedder_similarity(KjarniEmbedder* e, const char* t1, const char* t2, float* out) {
+    KJ_NULLCHECK(!e || !t1 || !t2 || !out);
+    *out = 0.0f;
+    KJ_UTF8(t1);
+    KJ_UTF8(t2);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        // Embedder::similarity: embed both (one batch of two = BatchLongest padding over the pair), cosine of the two rows
+        std::vector<float> v;
+        e->embed({std::string(t1), std::string(t2)}, v);
+        const size_t H = v.size() / 2;
+        *out = kjc_cosine_similarity(v.data(), v.data() + H, H);
+    });
+}
+size_t kjarni_embedder_dim(const KjarniEmbedder* e) { return e ? static_cast<size_t>(e->m->enc->info().hidden_size) : 0; }
+
+// ------------------------------------------------------------------ Classifier
+void kjarni_class_results_free(const KjarniClassResults* r) {
+    if (!r || !r->results || r->len == 0) return;
+    for (size_t i = 0; i < r->len; ++i) free(r->results[i].label);
+    free(r->results);
+}
+KjarniClassifierConfig kjarni_classifier_config_default(void) {
+    return KjarniClassifierConfig{KJARNI_DEVICE_CPU, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+}
+KjarniErrorCode kjarni_classifier_new(const KjarniClassifierConfig* config, KjarniClassifier** out) {
+    KJ_NULLCHECK(!out);
+    *out = nullptr;
+    const KjarniClassifierConfig dflt = kjarni_classifier_config_default();
+    const KjarniClassifierConfig& c = config ? *config : dflt;
+    KJ_UTF8(c.cache_dir);
+    KJ_UTF8(c.model_name);
+    KJ_UTF8(c.model_path);
+    std::vector<std::string> custom;
+    if (c.labels && c.num_labels > 0)
+        for (size_t i = 0; i < c.num_labels; ++i) {
+            KJ_NULLCHECK(!c.labels[i]);
+            KJ_UTF8(c.labels[i]);
+            custom.emplace_back(c.labels[i]);
+        }
+    return guarded(KJARNI_ERROR_LOAD_FAILED, [&] {
+        device_check(c.device);
+        const std::string dir = resolve_model_dir(c.cache_dir, c.model_name, c.model_path, "sentiment");
+        std::unique_ptr<KjarniClassifier> k(new KjarniClassifier);
+        k->m.reset(new TextModel(dir, c.model_name ? c.model_name : "sentiment"));
+        const KjcEncoderInfo& info = k->m->enc->info();
+        if (info.head_kind == KJC_HEAD_ABSENT) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "model has no classification head"};
+        if (!custom.empty()) {
+            if (static_cast<int>(custom.size()) != info.num_labels)
+                throw Fail{KJARNI_ERROR_INVALID_CONFIG, "Label count mismatch: model has " + std::to_string(info.num_labels) + " outputs, " +
+                                                            std::to_string(custom.size()) + " labels given"};
+            k->labels = custom;
+        } else {
+            k->labels = k->m->enc->labels();
+            for (int i = static_cast<int>(k->labels.size()); i < info.num_labels; ++i) k->labels.push_back("LABEL_" + std::to_string(i));
+        }
+        k->multi_label = c.multi_label != 0;
+        *out = k.release();
+    });
+}
+void kjarni_classifier_free(KjarniClassifier* k) { delete k; }
+
+KjarniErrorCode kjarni_classifier_classify(KjarniClassifier* k, const char* text, KjarniClassResults* out) {
+    KJ_NULLCHECK(!k || !text || !out);
+    *out = KjarniClassResults{nullptr, 0};
+    KJ_UTF8(text);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::lock_guard<std::mutex> lock(k->mu);
+        const KjcForwardOptions o{KJC_OUT_LOGITS, KJC_POOL_CLS, 0, KJC_MASK_ALLOC};
+        const size_t C = static_cast<size_t>(k->m->enc->info().num_labels);
+        std::vector<float> s;
+        k->m->run({std::string(text)}, {}, o, true, s, C);  // predict_logits passes the tokenizer's type ids (sequence_classifier/mod.rs:281-296)
+        if (k->multi_label) kjc_sigmoid_rows(s.data(), 1, static_cast<int>(C));
+        else kjc_softmax_rows(s.data(), 1, static_cast<int>(C));
+        std::vector<size_t> order(C);
+        for (size_t i = 0; i < C; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return s[a] > s[b]; });  // types.rs:106-131
+        KjarniClassResult* r = static_cast<KjarniClassResult*>(calloc(C, sizeof(KjarniClassResult)));
+        if (!r) throw std::bad_alloc();
+        for (size_t i = 0; i < C; ++i) {
+            r[i].label = dup_cstr(k->labels[order[i]]);
+            r[i].score = s[order[i]];
+        }
+        out->results = r;
+        out->len = C;
+    });
+}
+KjarniErrorCode kjarni_classifier_labels(const KjarniClassifier* k, KjarniStringArray* out) {
+    KJ_NULLCHECK(!k || !out);
+    *out = KjarniStringArray{nullptr, 0};
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        if (k->labels.empty()) return;
+        char** p = static_cast<char**>(calloc(k->labels.size(), sizeof(char*)));
+        if (!p) throw std::bad_alloc();
+        for (size_t i = 0; i < k->labels.size(); ++i) p[i] = dup_cstr(k->labels[i]);
+        out->strings = p;
+        out->len = k->labels.size();
+    });
+}
+size_t kjarni_classifier_num_labels(const KjarniClassifier* k) { return k ? k->labels.size() : 0; }
+
+// ------------------------------------------------------------------ Reranker
+void kjarni_rerank_results_free(const KjarniRerankResults* r) {
+    if (r && r->results && r->len > 0) free(r->results);
+}
+KjarniRerankerConfig kjarni_reranker_config_default(void) { return KjarniRerankerConfig{KJARNI_DEVICE_CPU, nullptr, nullptr, nullptr, 0}; }
+KjarniErrorCode kjarni_reranker_new(const KjarniRerankerConfig* config, KjarniReranker** out) {
+    KJ_NULLCHECK(!out);
+    *out = nullptr;
+    const KjarniRerankerConfig dflt = kjarni_reranker_config_default();
+    const KjarniRerankerConfig& c = config ? *config : dflt;
+    KJ_UTF8(c.cache_dir);
+    KJ_UTF8(c.model_name);
+    KJ_UTF8(c.model_path);
+    return guarded(KJARNI_ERROR_LOAD_FAILED, [&] {
+        device_check(c.device);
+        const std::string dir = resolve_model_dir(c.cache_dir, c.model_name, c.model_path, "minilm-l6-v2-cross-encoder");
+        std::unique_ptr<KjarniReranker> r(new KjarniReranker);
+        r->m.reset(new TextModel(dir, c.model_name ? c.model_name : "minilm-l6-v2-cross-encoder"));
+        if (r->m->enc->info().head_kind == KJC_HEAD_ABSENT) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "model has no classification head"};
+        *out = r.release();
+    });
+}
+void kjarni_reranker_free(KjarniReranker* r) { delete r; }
+KjarniErrorCode kjarni_reranker_score(KjarniReranker* r, const char* query, const char* document, float* out) {
+    KJ_NULLCHECK(!r || !query || !document || !out);
+    *out = 0.0f;
+    KJ_UTF8(query);
+    KJ_UTF8(document);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::vector<float> s;
+        r->score(query, {std::string(document)}, s);
+        *out = s[0];
+    });
+}
+KjarniErrorCode kjarni_reranker_rerank_top_k(KjarniReranker* r, const char* query, const char* const* documents, size_t n, size_t top_k,
+                                             KjarniRerankResults* out) {
+    KJ_NULLCHECK(!r || !query || !documents || !out);
+    *out = KjarniRerankResults{nullptr, 0};
+    KJ_UTF8(query);
+    if (n == 0) return KJARNI_OK;
+    std::vector<std::string> docs;
+    for (size_t i = 0; i < n; ++i) {
+        KJ_NULLCHECK(!documents[i]);
+        KJ_UTF8(documents[i]);
+        docs.emplace_back(documents[i]);
+    }
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::vector<float> s;
+        r->score(query, docs, s);
+        std::vector<size_t> order(n);
+        for (size_t i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return s[a] > s[b]; });  // cross_encoder/model.rs:243-255
+        const size_t m = std::min(n, top_k);
+        if (m == 0) return;
+        KjarniRerankResult* res = static_cast<KjarniRerankResult*>(calloc(m, sizeof(KjarniRerankResult)));
+        if (!res) throw std::bad_alloc();
+        for (size_t i = 0; i < m; ++i) res[i] = KjarniRerankResult{order[i], s[order[i]]};
+        out->results = res;
+        out->len = m;
+    });
+}
+KjarniErrorCode kjarni_reranker_rerank(KjarniReranker* r, const char* query, const char* const* documents, size_t n, KjarniRerankResults* out) {
+    return kjarni_reranker_rerank_top_k(r, query, documents, n, static_cast<size_t>(-1), out);
+}
+
+// ------------------------------------------------------------------ Searcher
+void kjarni_search_results_free(const KjarniSearchResults* r) {
+    if (!r || !r->results || r->len == 0) return;
+    for (size_t i = 0; i < r->len; ++i) {
+        free(r->results[i].text);
+        free(r->results[i].metadata_json);
+    }
+    free(r->results);
+}
+KjarniSearchOptions kjarni_search_options_default(void) { return KjarniSearchOptions{-1, 0, -1, 0.0f, nullptr, nullptr, nullptr}; }
+KjarniSearcherConfig kjarni_searcher_config_default(void) {
+    return KjarniSearcherConfig{KJARNI_DEVICE_CPU, nullptr, nullptr, nullptr, KJARNI_SEARCH_MODE_HYBRID, 10, 0};
+}
+KjarniErrorCode kjarni_searcher_new(const KjarniSearcherConfig* config, KjarniSearcher** out) {
+    KJ_NULLCHECK(!out);
+    *out = nullptr;
+    const KjarniSearcherConfig dflt = kjarni_searcher_config_default();
+    const KjarniSearcherConfig& c = config ? *config : dflt;
+    KJ_UTF8(c.cache_dir);
+    KJ_UTF8(c.model_name);
+    KJ_UTF8(c.rerank_model);
+    return guarded(KJARNI_ERROR_LOAD_FAILED, [&] {
+        device_check(c.device);
+        std::unique_ptr<KjarniSearcher> s(new KjarniSearcher);
+        s->embedder.reset(new KjarniEmbedder);
+        s->embedder->m.reset(new TextModel(resolve_model_dir(c.cache_dir, c.model_name, nullptr, "minilm-l6-v2"), c.model_name ? c.model_name : "minilm-l6-v2"));
+        s->embedder->normalize = true;
+        if (c.rerank_model && *c.rerank_model) {
+            s->reranker.reset(new KjarniReranker);
+            s->reranker->m.reset(new TextModel(resolve_model_dir(c.cache_dir, c.rerank_model, nullptr, "minilm-l6-v2-cross-encoder"), c.rerank_model));
+        }
+        s->default_mode = c.default_mode;
+        s->default_top_k = c.default_top_k;
+        *out = s.release();
+    });
+}
+void kjarni_searcher_free(KjarniSearcher* s) { delete s; }
+bool kjarni_searcher_has_reranker(const KjarniSearcher* s) { return s && s->reranker; }
+KjarniSearchMode kjarni_searcher_default_mode(const KjarniSearcher* s) { return s ? s->default_mode : KJARNI_SEARCH_MODE_HYBRID; }
+size_t kjarni_searcher_default_top_k(const KjarniSearcher* s) { return s ? s->default_top_k : 0; }
+
+KjarniErrorCode kjarni_searcher_search_with_options(KjarniSearcher* s, const char* index_path, const char* query, const KjarniSearchOptions* options,
+                                                    KjarniSearchResults* out) {
+    KJ_NULLCHECK(!s || !index_path || !query || !out);
+    *out = KjarniSearchResults{nullptr, 0};
+    KJ_UTF8(index_path);
+    KJ_UTF8(query);
+    const KjarniSearchOptions dflt = kjarni_search_options_default();
+    const KjarniSearchOptions& o = options ? *options : dflt;
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        // Searcher::search_with_options, kjarni/src/searcher/model.rs:96-189
+        std::lock_guard<std::mutex> lock(s->mu);
+        if (!file_ok(std::string(index_path) + "/config.json")) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, std::string("Index not found: ") + index_path};
+        auto it = s->opened.find(index_path);
+        if (it == s->opened.end()) {
+            KjarniSearcher::Opened op;
+            op.dir = scan_index_dir(index_path);
+            if (op.dir.total_rows > 0) op.idx.reset(open_index_dir(index_path, 0, 0, 1));
+            it = s->opened.emplace(index_path, std::move(op)).first;
+        }
+        KjarniSearcher::Opened& op = it->second;
+        const int model_dim = s->embedder->m->enc->info().hidden_size;
+        if (op.dir.dimension != model_dim)
+            throw Fail{KJARNI_ERROR_INVALID_CONFIG, "Dimension mismatch: index has " + std::to_string(op.dir.dimension) + ", model has " + std::to_string(model_dim)};
+        const int mode = o.mode >= 0 ? (o.mode == 0 ? 0 : (o.mode == 1 ? 1 : 2)) : static_cast<int>(s->default_mode);
+        if (mode != KJARNI_SEARCH_MODE_SEMANTIC)
+            throw Fail{KJARNI_ERROR_INVALID_CONFIG, "keyword / hybrid search needs the BM25 index, which stays with the CPU host; the CUDA backend serves "
+                                                    "KJARNI_SEARCH_MODE_SEMANTIC"};
+        const size_t top_k = o.top_k > 0 ? o.top_k : s->default_top_k;
+        const bool use_reranker = (o.use_reranker >= 0 ? o.use_reranker != 0 : static_cast<bool>(s->reranker)) && s->reranker;
+        const size_t fetch_k = use_reranker ? top_k * 5 : top_k;
+        const bool has_filter = (o.source_pattern && uni::valid_utf8(o.source_pattern)) || (o.filter_key && o.filter_value);
+        const size_t scan_k = std::min<size_t>(has_filter ? fetch_k * 3 : fetch_k, 256);  // search_semantic_filtered: limit * 3 then filter
+        struct Hit {
+            float score;
+            uint64_t id;
+            std::string text;
+            std::vector<std::pair<std::string, std::string>> meta;
+        };
+        std::vector<Hit> hits;
+        if (op.idx && scan_k > 0) {
+            std::vector<float> q;
+            s->embedder->embed({std::string(query)}, q);
+            std::vector<uint64_t> ids(scan_k);
+            std::vector<float> sc(scan_k);
+            int32_t cnt = 0;
+            op.idx->search_host(q.data(), 1, static_cast<int>(scan_k), KJC_SCAN_SEGMENT, ids.data(), sc.data(), &cnt);
+            for (int i = 0; i < cnt; ++i) {
+                Hit h{sc[i], ids[i], {}, {}};
+                fetch_doc(op.dir, ids[i], h.text, h.meta);
+                if (has_filter) {  // MetadataFilter::matches, kjarni-rag/src/index_reader.rs:27-80
+                    if (o.filter_key && o.filter_value) {
+                        const std::string* v = meta_get(h.meta, o.filter_key);
+                        if (!v || *v != o.filter_value) continue;
+                    }
+                    if (o.source_pattern && uni::valid_utf8(o.source_pattern)) {
+                        const std::string* src = meta_get(h.meta, "source");
+                        if (!src) continue;
+                        const std::string pat = o.source_pattern;
+                        const std::string name = pat.find('/') != std::string::npos ? *src : src->substr(src->find_last_of('/') + 1);
+                        if (fnmatch(pat.c_str(), name.c_str(), 0) != 0) continue;
+                    }
+                }
+                hits.push_back(std::move(h));
+                if (hits.size() >= fetch_k) break;
+            }
+        }
+        if (use_reranker && !hits.empty()) {
+            std::vector<std::string> docs;
+            for (const Hit& h : hits) docs.push_back(h.text);
+            std::vector<float> rs;
+            s->reranker->score(query, docs, rs);
+            std::vector<size_t> order(hits.size());
+            for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return rs[a] > rs[b]; });
+            std::vector<Hit> re;
+            for (size_t i = 0; i < order.size() && i < top_k; ++i) {
+                re.push_back(hits[order[i]]);
+                re.back().score = rs[order[i]];
+            }
+            hits.swap(re);
+        }
+        if (o.threshold > 0.0f) {
+            std::vector<Hit> kept;
+            for (Hit& h : hits)
+                if (h.score >= o.threshold) kept.push_back(std::move(h));
+            hits.swap(kept);
+        }
+        if (hits.size() > top_k) hits.resize(top_k);
+        if (hits.empty()) return;
+        KjarniSearchResult* r = static_cast<KjarniSearchResult*>(calloc(hits.size(), sizeof(KjarniSearchResult)));
+        if (!r) throw std::bad_alloc();
+        for (size_t i = 0; i < hits.size(); ++i) {
+            std::string mj = "{";
+            for (size_t k = 0; k < hits[i].meta.size(); ++k)
+                mj += std::string(k ? "," : "") + "\"" + json_escape(hits[i].meta[k].first) + "\":\"" + json_escape(hits[i].meta[k].second) + "\"";
+            mj += "}";
+            r[i] = KjarniSearchResult{hits[i].score, static_cast<size_t>(hits[i].id), dup_cstr(hits[i].text), dup_cstr(mj)};
+        }
+        out->results = r;
+        out->len = hits.size();
+    });
+}
+KjarniErrorCode kjarni_searcher_search(KjarniSearcher* s, const char* index_path, const char* query, KjarniSearchResults* out) {
+    const KjarniSearchOptions o = kjarni_search_options_default();
+    return kjarni_searcher_search_with_options(s, index_path, query, &o, out);
+}
+
+// ------------------------------------------------------------------ tokenizer (inner ABI, include/kjarni_cuda.h)
+struct KjcTokenizer {
+    Tokenizer impl;
+    KjcTokenizer(const char* p, int max_len) : impl(p, max_len) {}
+};
+int kjc_tokenizer_create(const char* tokenizer_json_path, int max_length, KjcTokenizer** out) {
+    if (!tokenizer_json_path || !out) { set_last_error("null pointer argument"); return KJC_NULL_POINTER; }
+    *out = nullptr;
+    return guarded(KJARNI_ERROR_LOAD_FAILED, [&] { *out = new KjcTokenizer(tokenizer_json_path, max_length); });
+}
+void kjc_tokenizer_destroy(KjcTokenizer* t) { delete t; }
+int kjc_tokenizer_token_to_id(const KjcTokenizer* t, const char* token, uint32_t* out_id) {
+    if (!t || !token || !out_id) return 0;
+    return t->impl.token_to_id(token, *out_id) ? 1 : 0;
+}
+int kjc_tokenizer_encode_batch(const KjcTokenizer* t, const char* const* texts, const char* const* pairs, int n, int add_special_tokens,
+                               uint32_t* ids, float* mask, uint32_t* type_ids, int cap_seq, int* out_seq_len) {
+    if (!t || !texts || !out_seq_len || n < 0) { set_last_error("null pointer argument"); return KJC_NULL_POINTER; }
+    std::vector<std::string> a, b;
+    for (int i = 0; i < n; ++i) {
+        if (!texts[i] || (pairs && !pairs[i])) { set_last_error("null pointer argument"); return KJC_NULL_POINTER; }
+        if (!uni::valid_utf8(texts[i]) || (pairs && !uni::valid_utf8(pairs[i]))) { set_last_error("invalid UTF-8"); return KJC_INVALID_UTF8; }
+        a.emplace_back(texts[i]);
+        if (pairs) b.emplace_back(pairs[i]);
+    }
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::vector<uint32_t> vi, vt;
+        std::vector<float> vm;
+        int S = 0;
+        t->impl.encode_batch(a, b, add_special_tokens != 0, vi, vm, vt, S);
+        *out_seq_len = S;
+        if (!ids) return;  // query call: sequence length only
+        if (S > cap_seq) throw Error(KJC_INVALID_CONFIG, "kjc_tokenizer_encode_batch: buffers hold " + std::to_string(cap_seq) + " tokens per row, need " + std::to_string(S));
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < cap_seq; ++k) {
+                const bool in = k < S;
+                ids[static_cast<size_t>(i) * cap_seq + k] = in ? vi[static_cast<size_t>(i) * S + k] : 0u;
+                if (mask) mask[static_cast<size_t>(i) * cap_seq + k] = in ? vm[static_cast<size_t>(i) * S + k] : 0.f;
+                if (type_ids) type_ids[static_cast<size_t>(i) * cap_seq + k] = in ? vt[static_cast<size_t>(i) * S + k] : 0u;
+            }
+    }, true);
+}
+
+}  // extern "C"

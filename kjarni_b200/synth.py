@@ -177,8 +177,10 @@ def synth_tokens(batch: int, seq: int, vocab: int = 30522, *, regime: str = "T",
     return ids, mask, types
 
 
-def write_index_dir(root: str, segments, *, dimension: int = None, max_docs_per_segment: int = 10_000, broken=()) -> str:
-    """Writes an index directory in the layout IndexWriter::commit leaves (kjarni-rag/src/index_writer.rs:128-170,
+def write_index_dir(root: str, segments, *, dimension: int = None, max_docs_per_segment: int = 10_000, broken=(), docs=None,
+                    metadata=None) -> str:
+    """`docs` / `metadata`: optional per-segment lists of texts / {str: str} dicts (defaults: generated text, {}).
+    Writes an index directory in the layout IndexWriter::commit leaves (kjarni-rag/src/index_writer.rs:128-170,
     segment.rs:140-193): config.json, index.json, segments/seg_%06d/{segment.json, vectors.bin, docs.bin, docs.idx,
     metadata.jsonl, bm25.bin}.  `segments` = list of float32 [n_i, dim] arrays.  docs.idx is a bincode Vec<u64>
     (u64 length + offsets); bm25.bin is a placeholder (the GPU reader only checks that it exists, as Segment::open would
@@ -198,17 +200,21 @@ def write_index_dir(root: str, segments, *, dimension: int = None, max_docs_per_
         sd = os.path.join(root, "segments", "seg_%06d" % i)
         os.makedirs(sd, exist_ok=True)
         rows.astype("<f4").tofile(os.path.join(sd, "vectors.bin"))
-        docs = [("doc %d of segment %d" % (j, i)).encode() for j in range(rows.shape[0])]
+        seg_docs = [("doc %d of segment %d" % (j, i)).encode() for j in range(rows.shape[0])] if docs is None else [t.encode() for t in docs[i]]
         offs, cur = [], 0
         with open(os.path.join(sd, "docs.bin"), "wb") as f:
-            for d in docs:
+            for d in seg_docs:
                 offs.append(cur)
                 f.write(d + b"\n")
                 cur += len(d) + 1
         with open(os.path.join(sd, "docs.idx"), "wb") as f:
             f.write(struct.pack("<Q", len(offs)) + b"".join(struct.pack("<Q", o) for o in offs))
         with open(os.path.join(sd, "metadata.jsonl"), "w") as f:
-            f.write("{}\n" * rows.shape[0])
+            if metadata is None:
+                f.write("{}\n" * rows.shape[0])
+            else:
+                for m in metadata[i]:
+                    f.write(json.dumps(m) + "\n")
         if i not in broken:
             with open(os.path.join(sd, "bm25.bin"), "wb") as f:
                 f.write(b"\0" * 8)

@@ -90,3 +90,23 @@ def test_api_scores_to_top_k_is_stable():
     # ties resolve to the lowest label index (kjarni-models/src/models/sequence_classifier/mod.rs:369-372)
     r = api.scores_to_top_k(np.array([0.25, 0.5, 0.25, 0.0], np.float32), ["a", "b", "c", "d"], 3)
     assert [n for n, _ in r] == ["b", "a", "c"]
+
+
+def test_public_ffi_symbols_are_exported():
+    """Every kjarni_* entry point include/kjarni_ffi.h declares is exported under the reference's names."""
+    txt = open(os.path.join(ROOT, "include", "kjarni_ffi.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = set(re.findall(r"\b(kjarni_[a-z0-9_]+)\s*\(", txt))
+    assert len(names) >= 40
+    lib = C.CDLL(os.path.join(os.path.dirname(N.LIB_PATH), "libkjarni_ffi.so"))
+    for name in sorted(names):
+        assert hasattr(lib, name), name
+    lib.kjarni_error_name.restype = C.c_char_p
+    assert lib.kjarni_error_name(6) == b"GpuUnavailable" and lib.kjarni_init() == 0
+    lib.kjarni_cosine_similarity.restype = C.c_float
+    a = (C.c_float * 3)(1, 0, 0)
+    assert lib.kjarni_cosine_similarity(a, a, 3) == pytest.approx(1.0)
+    # frees accept NULL and empty results (pointer form, as the Rust source declares them)
+    for fn in ("kjarni_float_array_free", "kjarni_float_2d_array_free", "kjarni_string_array_free", "kjarni_class_results_free",
+               "kjarni_rerank_results_free", "kjarni_search_results_free", "kjarni_string_free"):
+        getattr(lib, fn)(None)
