@@ -23,7 +23,15 @@ namespace kj {
 
 constexpr int kLnN = 384;
 constexpr int kLnHalfN = 192;
-constexpr int kLnStages = 2;
+#ifndef KJ_LN_STAGES
+#define KJ_LN_STAGES 3
+#endif
+constexpr int kLnStages = KJ_LN_STAGES;
+// With 3 operand stages (192 KB) the epilogue's staging buffers no longer fit beside the ring, so they ALIAS ring stage 0: the
+// epilogue only touches them after tmem_full (every MMA of the tile has retired, the ring is idle), and the producer waits on
+// `epi_free` before it loads the next tile's operands.  Two 64 KB stages left the K-loop TMA-latency-bound (one k-block of
+// MMAs, 0.6 us, could not cover a load round trip under load): 30 us per FFN-down launch against a 14 us MMA floor.
+constexpr bool kLnAliasEpi = kLnStages >= 3;
 constexpr int kLnParts = 3;                                // column parts per lane quadrant
 constexpr int kLnPartCols = kLnN / kLnParts;               // 128
 constexpr int kLnEpiWarps = 4 * kLnParts;                  // 12
@@ -34,7 +42,8 @@ constexpr int kLnStageBytes = kLnABytes + kLnBBytes;       // 64 KB
 constexpr int kLnEpiBytesPerWarp = 2 * kEpiStageBytes;     // 2 x 2 KB: residual double buffer, then store double buffer
 constexpr int kLnStatBytes = kLnParts * 128 * 8;           // [part][row] (sum, sum of squares)
 constexpr int kLnVecBytes = 3 * kLnN * 4;                  // bias | gamma | beta
-constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + kLnEpiWarps * kLnEpiBytesPerWarp + kLnStatBytes + kLnVecBytes + 512;
+constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + (kLnAliasEpi ? 0 : kLnEpiWarps * kLnEpiBytesPerWarp) + kLnStatBytes + kLnVecBytes + 512;
+static_assert(kLnEpiWarps * kLnEpiBytesPerWarp <= kLnStageBytes, "aliased epilogue staging must fit in one ring stage");
 static_assert(kLnSmemBytes <= 232448, "shared memory budget");
 
 struct GemmLnParams {
@@ -53,8 +62,10 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (smem_u32(smem) & 1023) __trap();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kLnStages * kLnABytes;
-    uint8_t* smem_epi = smem + kLnStages * kLnStageBytes;
-    float2* stat = reinterpret_cast<float2*>(smem_epi + kLnEpiWarps * kLnEpiBytesPerWarp);  // [3][128]
+    uint8_t* smem_tail = smem + kLnStages * kLnStageBytes;
+    // aliased staging = stage 0 of the W array: 48 KB, exactly 12 warps x 4 KB
+    uint8_t* smem_epi = kLnAliasEpi ? smem_b : smem_tail;
+    float2* stat = reinterpret_cast<float2*>(smem_tail + (kLnAliasEpi ? 0 : kLnEpiWarps * kLnEpiBytesPerWarp));  // [3][128]
     float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stat) + kLnStatBytes);
     float* s_gamma = s_bias + kLnN;
     float* s_beta = s_gamma + kLnN;
@@ -64,7 +75,8 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint64_t* tmem_full = bars + 2 * kLnStages;
     uint64_t* tmem_empty = bars + 2 * kLnStages + 1;
     uint64_t* res_bar = bars + 2 * kLnStages + 2;  // [12 warps][2 buffers]
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(res_bar + 2 * kLnEpiWarps);
+    uint64_t* epi_free = res_bar + 2 * kLnEpiWarps;  // epilogue staging (aliased on the ring) released for the next tile's loads
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(epi_free + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -91,6 +103,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, kLnEpiWarps);
         for (int i = 0; i < 2 * kLnEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+        mbar_init(epi_free, kLnEpiWarps);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_base_smem);
@@ -106,7 +119,9 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                if (kLnAliasEpi && it > 0) mbar_wait(epi_free, (it - 1) & 1);  // the previous tile's epilogue is done with the ring
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kLnStageBytes);
@@ -166,17 +181,22 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int row0 = tile * kGemmBlockM + quad * 32;
             const int col_base = part * kLnPartCols;
             // the store staging of the previous tile aliases the residual buffers: wait until TMA has read it
-            if (lane == 0) {
-                bulk_wait_read<0>();
-                // prefetch the first two residual chunks; they land while the MMAs of this tile run
-                for (int c = 0; c < 2; ++c) {
-                    mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
-                    tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
+            auto prefetch_residual = [&] {
+                if (lane == 0) {
+                    bulk_wait_read<0>();
+                    for (int c = 0; c < 2; ++c) {
+                        mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
+                        tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
+                    }
                 }
-            }
-            __syncwarp();
+                __syncwarp();
+            };
+            // separate staging: the first two residual chunks land while the MMAs of this tile run; aliased staging: the ring is
+            // only free once the accumulator is complete
+            if (!kLnAliasEpi) prefetch_residual();
             mbar_wait(tmem_full, it & 1);
             tc_fence_after();
+            if (kLnAliasEpi) prefetch_residual();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
 
             // ---- pass A: v = acc + bias + residual ; row sum and sum of squares ; v -> TMEM
@@ -276,6 +296,13 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             }
             // the stat exchange of the next tile happens after its tmem_full wait, i.e. after every warp of this tile has
             // passed the barrier above and read stat[]: no extra sync is needed before stat[] is overwritten.
+            if (kLnAliasEpi && tile + static_cast<int>(gridDim.x) < m_tiles) {  // hand the ring back to the producer
+                if (lane == 0) {
+                    bulk_wait_read<0>();
+                    mbar_arrive(epi_free);
+                }
+                __syncwarp();
+            }
         }
         if (lane == 0) bulk_wait_read<0>();
     }
