@@ -182,10 +182,29 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """Exactly one JSON line on the process's real stdout (see main(): fd 1 is pointed at stderr for everything else)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    # Libraries print banners on stdout (NCCL: "NCCL version ..." at communicator creation); the contract is ONE JSON line
+    # there, so fd 1 is redirected to stderr and the result line goes to a duplicate of the original stdout.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -361,7 +380,7 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "index_topk": index,
         }
-        print(json.dumps(line))
+        emit(line)
     enc.close()
     if world > 1:
         dist.destroy_process_group()

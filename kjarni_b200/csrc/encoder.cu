@@ -1148,6 +1148,9 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
         for (int c : {0, 1, ctas / 2, ctas - 1}) {
             fprintf(stderr, "trace M=%d N=%d K=%d bn=%d cta %3d:", M, N, K, bn, c);
             for (int i = 0; i < 18; ++i) if (h[c * 32 + i]) fprintf(stderr, " %s=%.2f", names[i], (h[c * 32 + i] - t0) * 1e-3);
+            if (h[c * 32 + 22]) fprintf(stderr, " | epi(warp5,tile2): start=%.2f wait_read=+%.2f ld0=+%.2f ld1=+%.2f math+sts=+%.2f store=+%.2f", (h[c * 32 + 22] - t0) * 1e-3,
+                                        (h[c * 32 + 23] - h[c * 32 + 22]) * 1e-3, (h[c * 32 + 24] - h[c * 32 + 23]) * 1e-3, (h[c * 32 + 25] - h[c * 32 + 24]) * 1e-3,
+                                        (h[c * 32 + 26] - h[c * 32 + 25]) * 1e-3, (h[c * 32 + 27] - h[c * 32 + 26]) * 1e-3);
             if (h[c * 32 + 16] > h[c * 32 + 2]) fprintf(stderr, " sm_mhz=%.0f", (h[c * 32 + 21] - h[c * 32 + 20]) * 1e3 / double(h[c * 32 + 16] - h[c * 32 + 2]));
             fprintf(stderr, "\n");
         }

@@ -32,12 +32,14 @@ struct PairCfg {
     static constexpr int kBBytes = (BN / 2) * kGemmBlockK * 2;          // this CTA's half of a weight k-block
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
     // epilogue geometry as in GemmCfg: 192-column tiles -> 12 warps, each stages a 32 x 64 part and issues one TMA store per tile
-    static constexpr int kParts = (BN == 192) ? 3 : 2;
+    // 256-column tiles: 4 parts of 64 columns = 16 epilogue warps (the epilogue is a per-warp latency chain of ~1 us per 32-column
+    // chunk under load, so the parallelism has to come from more warps), each staging one 32 x 32 chunk at a time
+    static constexpr int kParts = (BN == 192) ? 3 : ((BN == 256) ? 4 : 2);
     static constexpr int kEpiWarpsN = 4 * kParts;
     static constexpr int kThreads = 128 + 32 * kEpiWarpsN;
     static constexpr int kColsPerPart = BN / kParts;
     static constexpr int kStoreCols = (BN == 192) ? 64 : kEpiChunkCols;
-    static constexpr int kEpiBufs = (BN == 192) ? 1 : 2;
+    static constexpr int kEpiBufs = (BN == 192 || BN == 256) ? 1 : 2;
     static constexpr int kEpiBufBytes = 32 * kStoreCols * 2;
     static constexpr int kEpiBytes = kEpiWarpsN * kEpiBufs * kEpiBufBytes;
     static constexpr int kBiasBytes = kEpiBiasMax * 4;
@@ -237,7 +239,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                          pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                         }
                     } else if (col0 < p.N) {
-                        if (lane == 0) bulk_wait_read<1>();
+                        if (lane == 0) bulk_wait_read<Cfg::kEpiBufs - 1>();
                         __syncwarp();
                         uint8_t* buf = stage_buf + sbuf * Cfg::kEpiBufBytes;
                         const uint32_t rbase = smem_u32(buf) + lane * 64;
@@ -253,7 +255,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             tma_store_2d(&tmap_c, buf, col0, row0);
                             bulk_commit();
                         }
-                        sbuf ^= 1;
+                        if (++sbuf == Cfg::kEpiBufs) sbuf = 0;
                     }
                 }
                 if constexpr (Cfg::kStoreCols == 64) {

@@ -284,8 +284,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // tcgen05.ld has landed.
                 static_assert(kColsPerHalf == 64, "part width");
                 const int colp = n_blk * BN + half * kColsPerHalf;
+                const bool tr = p.trace != nullptr && ew == 5 && lane == 0 && it == 2;  // epilogue sub-steps of one warp, third tile
+                if (tr) p.trace[blockIdx.x * 32 + 22] = gtimer();
                 if (lane == 0) bulk_wait_read<0>();  // the previous tile's store has read the staging tile
                 __syncwarp();
+                if (tr) p.trace[blockIdx.x * 32 + 23] = gtimer();
                 const uint32_t rbase = smem_u32(stage_buf) + lane * 128;
                 const uint32_t sw = lane & 7;  // 128B swizzle: 16-byte chunk index ^= row & 7
 #pragma unroll
@@ -298,6 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tmem_ld_32x32(taddr0 + c * 32, v);
                         tmem_ld_wait();
                     }
+                    if (tr) p.trace[blockIdx.x * 32 + 24 + c] = gtimer();
                     if (c == 1) {
                         tc_fence_before();
                         __syncwarp();
@@ -339,12 +343,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                      pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
+                if (tr) p.trace[blockIdx.x * 32 + 26] = gtimer();
                 if (!(p.dbg & 32)) fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0 && colp < p.N && !(p.dbg & 16)) {  // columns >= N are clipped by the tensor map
                     tma_store_2d(&tmap_c, stage_buf, colp, row0);
                     bulk_commit();
                 }
+                if (tr) p.trace[blockIdx.x * 32 + 27] = gtimer();
             } else if constexpr (kStaged) {
                 // TMEM -> registers -> bias/activation -> bf16 -> swizzled smem tile -> TMA store (coalesced, async).
                 // The tcgen05.ld of chunk c+1 is in flight while chunk c is processed; the accumulator is released as soon

@@ -11,3 +11,6 @@ def t(Nn, K, epi, bn, flags=0):
 for name, Nn, K, epi in (("qkv", 1152, 384, 0), ("ffn_up", 1536, 384, 1)):
     for bn in (192, 256):
         print(f"{name} BN={bn}: full {t(Nn, K, epi, bn):.1f} us | no-epi {t(Nn, K, epi, bn, 1):.1f} | mma-only {t(Nn, K, epi, bn, 5):.1f}", flush=True)
+for name, Nn, K, epi in (("qkv", 1152, 384, 0), ("ffn_up", 1536, 384, 1)):
+    for bn in (192, 256):
+        print(f"PAIR {name} BN={bn}: full {t(Nn, K, epi, 1000 + bn):.1f} us", flush=True)
