@@ -241,16 +241,30 @@ mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 #pragma unroll
     for (int i = 0; i < NCH; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     float cnt = 0.f;
-    for (int s0 = warp; s0 < S; s0 += 8) {
-        const float m = mb ? mb[s0] : 1.0f;
-        cnt += m;
-        if (m != 0.0f) {
+    // four rows per trip with every load issued before the first use: the kernel is a latency chain (one CTA per sequence),
+    // so memory-level parallelism is what sets its time.  Rows are loaded unconditionally (they exist even when masked) but
+    // only accumulated when the mask is non-zero: a masked row may hold NaN (no-alloc convention) and NaN * 0 is NaN.
+    constexpr int kU = 4;
+    for (int s0 = warp; s0 < S; s0 += 8 * kU) {
+        float m[kU];
+        float4 t[kU][NCH];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int sr = s0 + 8 * u;
+            m[u] = sr < S ? (mb ? mb[sr] : 1.0f) : 0.0f;
 #pragma unroll
             for (int i = 0; i < NCH; ++i) {
                 const int c = (lane + 32 * i) * 4;
-                if (c < H) {
-                    const float4 t = load4f(xb + static_cast<size_t>(s0) * H + c);
-                    acc[i].x += t.x * m; acc[i].y += t.y * m; acc[i].z += t.z * m; acc[i].w += t.w * m;
+                t[u][i] = (sr < S && c < H) ? load4f(xb + static_cast<size_t>(sr) * H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            cnt += m[u];
+            if (m[u] != 0.0f) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    acc[i].x += t[u][i].x * m[u]; acc[i].y += t[u][i].y * m[u]; acc[i].z += t[u][i].z * m[u]; acc[i].w += t[u][i].w * m[u];
                 }
             }
         }

@@ -117,7 +117,48 @@ struct TextModel {
         if (S == 0) throw Error(KJC_INFERENCE_FAILED, "Tokenizer produced an empty batch");
         out.assign(a.size() * out_cols, 0.f);
         const bool types_ok = with_types && enc->info().type_vocab_size > 0;
-        enc->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(a.size()), S, o, out.data());
+        const size_t n = a.size();
+        // Length-bucketed batching: BatchLongest pads every text of the call to the longest one, and padded
+        // positions are pure waste on the GPU (masked keys contribute exactly 0 to every valid token, so pooled rows and logits
+        // do not depend on the padding).  Texts are grouped by token count rounded up to 16 and each group runs at its own
+        // length; results land in the caller's order.  A call whose texts share one bucket is a single forward as before.
+        std::vector<int> len(n, 0);
+        bool one_bucket = true;
+        for (size_t i = 0; i < n; ++i) {
+            int l = 0;
+            for (int k = 0; k < S; ++k) l += mask[i * S + k] != 0.0f;
+            len[i] = std::max(l, 1);
+            if ((len[i] + 15) / 16 != (len[0] + 15) / 16) one_bucket = false;
+        }
+        if (one_bucket || getenv("KJC_NO_LENGTH_BUCKETS")) {
+            enc->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(n), S, o, out.data());
+            return;
+        }
+        std::vector<size_t> order(n);
+        for (size_t i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return len[x] < len[y]; });
+        std::vector<uint32_t> gi, gt;
+        std::vector<float> gm, go;
+        for (size_t g0 = 0; g0 < n;) {
+            const int bucket = (len[order[g0]] + 15) / 16;
+            size_t g1 = g0;
+            while (g1 < n && (len[order[g1]] + 15) / 16 == bucket) ++g1;
+            const int Sg = std::min(S, len[order[g1 - 1]]);  // longest text of the group: tokens are left-aligned, the rest is padding
+            const size_t nb = g1 - g0;
+            gi.assign(nb * Sg, 0u);
+            gt.assign(nb * Sg, 0u);
+            gm.assign(nb * Sg, 0.f);
+            go.assign(nb * out_cols, 0.f);
+            for (size_t r = 0; r < nb; ++r) {
+                const size_t src = order[g0 + r];
+                memcpy(&gi[r * Sg], &ids[src * S], Sg * sizeof(uint32_t));
+                memcpy(&gt[r * Sg], &types[src * S], Sg * sizeof(uint32_t));
+                memcpy(&gm[r * Sg], &mask[src * S], Sg * sizeof(float));
+            }
+            enc->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, go.data());
+            for (size_t r = 0; r < nb; ++r) memcpy(&out[order[g0 + r] * out_cols], &go[r * out_cols], out_cols * sizeof(float));
+            g0 = g1;
+        }
     }
 };
 

@@ -328,3 +328,33 @@ def test_searcher_semantic_search_over_an_index_directory(ffi, models, tmp_path)
     assert scores == sorted(scores, reverse=True)
     ffi.kjarni_search_results_free(C.byref(res))
     ffi.kjarni_searcher_free(h)
+
+
+def test_length_bucketed_batching_matches_batch_longest(ffi, models, monkeypatch):
+    """texts of very different lengths run in per-length groups; the rows equal the BatchLongest forward
+    (padding never reaches a valid token) and come back in the caller's order."""
+    cfg = ffi.kjarni_embedder_config_default()
+    cfg.device, cfg.cache_dir = GPU, models["cache"].encode()
+    h = C.c_void_p()
+    assert ffi.kjarni_embedder_new(C.byref(cfg), C.byref(h)) == 0
+    texts = ["a", "the quick brown fox " * 20, "hello world", "search " * 30, "vector database retrieval of relevant passage", "dog",
+             "ranking documents by cosine similarity score " * 3, "water"]
+    out = Float2DArray()
+
+    def run():
+        assert ffi.kjarni_embedder_encode_batch(h, strs(texts), len(texts), C.byref(out)) == 0
+        v = np.ctypeslib.as_array(out.data, shape=(out.rows, out.cols)).copy()
+        ffi.kjarni_float_2d_array_free(C.byref(out))
+        return v
+
+    bucketed = run()
+    monkeypatch.setenv("KJC_NO_LENGTH_BUCKETS", "1")
+    padded = run()
+    monkeypatch.delenv("KJC_NO_LENGTH_BUCKETS")
+    assert cosine_rows(bucketed, padded).min() >= 0.99999 and np.abs(bucketed - padded).max() < 2e-3
+    tok = api.Tokenizer(TOK, 64)
+    ids, mask, _ = tok.encode_batch(texts)
+    assert mask.sum(1).min() == 3 and mask.sum(1).max() == 64  # [CLS] a [SEP] ... truncated to the 64-position table
+    want = ko.embed(ko.load_model_dir(models["tiny-bert"]), ids, mask)
+    assert cosine_rows(bucketed, want).min() >= 0.9995 and np.abs(bucketed - want).max() <= 2e-2
+    ffi.kjarni_embedder_free(h)
