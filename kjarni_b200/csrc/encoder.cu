@@ -532,6 +532,10 @@ Encoder::Encoder(const std::string& dir, int device) {
     bn_qkv_ = pick_block_n(3 * H);
     bn_h_ = pick_block_n(H);
     bn_i_ = pick_block_n(I);
+    // FFN-up: 256-column tiles where they divide I.  A tcgen05.mma of M = 128 costs ~128 clk for any N <= 256 (scripts/mma_rate.py),
+    // so 1536 = 6 x 256 needs 25 % fewer MMA instructions than 8 x 192; with the 16-warp epilogue the launch is 26.4 us against
+    // 28.8 us (profiles/r01_gemm_probes.md).  QKV (1152 = 4.5 x 256) measures the same either way and keeps 192.
+    if (I % 256 == 0 && gemm_wide_store(256)) bn_i_ = 256;
     if (const char* e = getenv("KJC_BN_I")) bn_i_ = atoi(e);  // tuning hooks
     if (const char* e = getenv("KJC_BN_QKV")) bn_qkv_ = atoi(e);
     layers_.resize(L);

@@ -189,3 +189,33 @@ def test_roberta_mpnet_layouts_and_multi_label(dirs):
     enc = api.EncoderModel(dirs["tiny-mpnet"])
     assert enc.arch == "mpnet" and enc.info.position_offset == 2 and enc.info.type_vocab_size == 0 and enc.head_kind is None
     enc.close()
+
+
+def test_full_size_configs_by_properties(dirs, tmp_path_factory):
+    """BASELINE configs C2 (DistilBERT 256 x 128) and C5 (BERT-base 512 x 512) at full size: the oracle cannot finish them in
+    seconds, so they are checked through size-independent properties -- rows are independent (a row of the big batch equals,
+    bit for bit, the same sequence run in a small batch), a subset of rows matches the oracle, outputs are finite / unit norm."""
+    # C2: every row of the 256-batch vs the same rows in batches of 16; first 8 rows vs the oracle
+    arch = "distilbert-sst2"
+    ids, mask, _ = synth.synth_tokens(256, 128, synth.ARCHS[arch][5], regime="P", seed=21)
+    enc = api.EncoderModel(dirs[arch])
+    big = enc.predict_logits(ids, mask)
+    assert big.shape == (256, 2) and np.isfinite(big).all()
+    for b0 in (0, 112, 240):
+        assert np.array_equal(big[b0:b0 + 16], enc.predict_logits(ids[b0:b0 + 16], mask[b0:b0 + 16]))
+    want = ko.predict_logits(ko.load_model_dir(dirs[arch]), ids[:8], mask[:8])
+    assert np.abs(big[:8] - want).max() <= 5e-2 * max(1.0, float(np.abs(want).max()))
+    enc.close()
+    # C5: BERT-base shape, 512 sequences x 512 tokens (2 micro-batches of 37 sequences x 7 ... handled inside the call)
+    arch = "bert-base"
+    d = synth.write_model_dir(str(tmp_path_factory.mktemp("bertbase") / arch), arch)
+    ids, mask, _ = synth.synth_tokens(512, 512, synth.ARCHS[arch][5], regime="P", seed=22)
+    enc = api.EncoderModel(d)
+    big = enc.encode_batch_from_ids(ids, mask)
+    assert big.shape == (512, 768) and np.isfinite(big).all()
+    assert np.abs(np.linalg.norm(big, axis=1) - 1).max() < 1e-5
+    for b0 in (0, 300, 508):
+        assert np.array_equal(big[b0:b0 + 4], enc.encode_batch_from_ids(ids[b0:b0 + 4], mask[b0:b0 + 4]))
+    want = ko.embed(ko.load_model_dir(d), ids[:2], mask[:2])
+    assert cosine_rows(big[:2], want).min() >= COS_MIN and np.abs(big[:2] - want).max() <= MAXABS
+    enc.close()
