@@ -590,6 +590,8 @@ Encoder::~Encoder() {
         if (w.done) cudaEventDestroy(w.done);
     }
     if (ev_in_) cudaEventDestroy(ev_in_);
+    for (cudaEvent_t e : ev_chunk_)
+        if (e) cudaEventDestroy(e);
     if (d_f32_) cudaFree(d_f32_);
     if (d_w16_) cudaFree(d_w16_);
     if (d_err_) cudaFree(d_err_);
@@ -902,21 +904,44 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
         KJ_CUDA(cudaMallocHost(&h_stage_out_, out_elems * 4));
         out_cap_ = out_elems;
     }
-    // stage through pinned memory so the copies are true async DMA transfers
+    // Stage through pinned memory so the copies are true async DMA transfers, in chunks of a few micro-batches: the host-side
+    // copy of chunk c+1 into the staging buffer and of chunk c-1 out of it run while the GPU works on chunk c, so only the
+    // first stage-in and the last stage-out are exposed (they were ~6 % of a 4144-sequence call when done up front).
     uint32_t* hs = h_stage_in_;
-    memcpy(hs, ids, T * 4);
-    if (mask) memcpy(hs + T, mask, T * 4);
-    if (types) memcpy(hs + 2 * T, types, T * 4);
-    KJ_CUDA(cudaMemcpyAsync(d_in_, hs, T * 4, cudaMemcpyHostToDevice, stream_));
-    if (mask) KJ_CUDA(cudaMemcpyAsync(d_in_ + T, hs + T, T * 4, cudaMemcpyHostToDevice, stream_));
-    if (types) KJ_CUDA(cudaMemcpyAsync(d_in_ + 2 * T, hs + 2 * T, T * 4, cudaMemcpyHostToDevice, stream_));
     const uint32_t* d_ids = d_in_;
     const float* d_mask = mask ? reinterpret_cast<const float*>(d_in_ + T) : nullptr;
     const uint32_t* d_types = types ? d_in_ + 2 * T : nullptr;
-
-    (void)row;
-    forward_batches(d_ids, d_mask, d_types, B, S, o, d_out_, stream_);
-    KJ_CUDA(cudaMemcpyAsync(h_stage_out_, d_out_, out_elems * 4, cudaMemcpyDeviceToHost, stream_));
+    KjcForwardOptions oc = o;  // the padding convention is decided once for the whole call, not per chunk
+    oc.mask_convention = resolve_noalloc(B, S, o) ? KJC_MASK_NOALLOC : KJC_MASK_ALLOC;
+    const int chunk = std::max(1, 4 * micro_batch(S));
+    if (!ev_chunk_[0]) {
+        KJ_CUDA(cudaEventCreateWithFlags(&ev_chunk_[0], cudaEventDisableTiming));
+        KJ_CUDA(cudaEventCreateWithFlags(&ev_chunk_[1], cudaEventDisableTiming));
+    }
+    int c = 0, prev_b0 = 0, prev_nb = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++c) {
+        const int nb = std::min(chunk, B - b0);
+        const size_t t0 = static_cast<size_t>(b0) * S, tn = static_cast<size_t>(nb) * S;
+        memcpy(hs + t0, ids + t0, tn * 4);
+        KJ_CUDA(cudaMemcpyAsync(d_in_ + t0, hs + t0, tn * 4, cudaMemcpyHostToDevice, stream_));
+        if (mask) {
+            memcpy(hs + T + t0, mask + t0, tn * 4);
+            KJ_CUDA(cudaMemcpyAsync(d_in_ + T + t0, hs + T + t0, tn * 4, cudaMemcpyHostToDevice, stream_));
+        }
+        if (types) {
+            memcpy(hs + 2 * T + t0, types + t0, tn * 4);
+            KJ_CUDA(cudaMemcpyAsync(d_in_ + 2 * T + t0, hs + 2 * T + t0, tn * 4, cudaMemcpyHostToDevice, stream_));
+        }
+        forward_batches(d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, oc, d_out_ + b0 * row, stream_);
+        KJ_CUDA(cudaMemcpyAsync(h_stage_out_ + b0 * row, d_out_ + b0 * row, nb * row * 4, cudaMemcpyDeviceToHost, stream_));
+        KJ_CUDA(cudaEventRecord(ev_chunk_[c & 1], stream_));
+        if (c > 0) {
+            KJ_CUDA(cudaEventSynchronize(ev_chunk_[(c - 1) & 1]));
+            memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);
+        }
+        prev_b0 = b0;
+        prev_nb = nb;
+    }
     int err = 0;
     KJ_CUDA(cudaMemcpyAsync(&err_host_, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
     KJ_CUDA(cudaStreamSynchronize(stream_));
@@ -925,7 +950,7 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
         KJ_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), stream_));
         throw Error(KJC_INFERENCE_FAILED, "Token type ID out of range");
     }
-    memcpy(out, h_stage_out_, out_elems * 4);
+    memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);  // the last chunk (earlier ones were copied in the loop)
 }
 
 // Head stage alone on caller-supplied fp32 hidden states (debug hook: the argmax stage must be

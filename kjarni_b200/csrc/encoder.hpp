@@ -159,6 +159,7 @@ class Encoder {
     size_t in_cap_ = 0, out_cap_ = 0;
     int* d_err_ = nullptr;
     int err_host_ = 0;
+    cudaEvent_t ev_chunk_[2] = {nullptr, nullptr};  // forward_host: per-chunk completion (stage-out of chunk c-1 overlaps chunk c)
     int64_t launches_ = 0;
     // profiling
     struct ProfRec { int cls; cudaEvent_t a, b; };
