@@ -110,3 +110,26 @@ def test_public_ffi_symbols_are_exported():
     for fn in ("kjarni_float_array_free", "kjarni_float_2d_array_free", "kjarni_string_array_free", "kjarni_class_results_free",
                "kjarni_rerank_results_free", "kjarni_search_results_free", "kjarni_string_free"):
         getattr(lib, fn)(None)
+
+
+def test_headers_are_valid_c99_and_link(tmp_path):
+    """The three headers are consumed from C (cgo / P/Invoke generators / a Rust bindgen run): they must parse as plain C99 and a C
+    program must link against the library by name."""
+    import subprocess
+
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include "kjarni_cuda.h"\n#include "kjarni_cuda_debug.h"\n#include "kjarni_ffi.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  KjarniEmbedderConfig c = kjarni_embedder_config_default();\n"
+        "  KjcIndexDirInfo info; KjcForwardOptions o = {KJC_OUT_POOLED, KJC_POOL_MEAN, 1, KJC_MASK_AUTO};\n"
+        "  (void)info; (void)o;\n"
+        '  printf("%s|%s|%d|%d\\n", kjc_version(), kjarni_error_name(KJARNI_ERROR_GPU_UNAVAILABLE), (int)c.device, (int)c.normalize);\n'
+        "  return kjc_index_dir_info(NULL, NULL) == KJC_NULL_POINTER ? 0 : 1;\n}\n")
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(N.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lkjarni_cuda", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "sm_100a" in r.stdout and "GpuUnavailable|0|1" in r.stdout, (r.stdout, r.stderr)
