@@ -107,7 +107,8 @@ def test_gemm_activations(act):
     assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2 * tol
 
 
-@pytest.mark.parametrize("M,K", [(128, 384), (1000, 384), (300, 1536), (18944, 384), (77, 64)])
+@pytest.mark.parametrize("M,K", [(128, 384), (1000, 384), (300, 1536), (18944, 384), (77, 64),
+                                 (37965, 384), (56900, 128), (19000, 1536)])  # more row tiles than SMs: the ring <-> epilogue hand-back
 def test_fused_gemm_residual_layernorm(M, K):
     """out-proj / FFN-down + bias + residual + LayerNorm in one kernel (hidden 384) vs the oracle's LayerNorm on fp32 sums."""
     import ctypes as C
