@@ -39,6 +39,19 @@ class DistributedIndex:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
+    @classmethod
+    def open_dir(cls, root: str, device: int, group=None) -> "DistributedIndex":
+        """Every rank uploads its contiguous part of an on-disk index directory (kjc_index_open_dir: IndexReader::open,
+        kjarni-rag/src/index_reader.rs:161-204, split by rows as `shard_rows` does); global ids stay those of the host's
+        IndexReader, so rank-local results merge without remapping."""
+        import torch.distributed as dist
+
+        from . import api
+
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        return cls(api.IndexShard.open_dir(root, device, rank, world), group)
+
     # -- the two device-side steps, overridable so the exchange logic can be exercised on CPU (gloo) in tests
     def _search_local(self, queries, k: int, mode: int):
         import torch
