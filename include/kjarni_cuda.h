@@ -143,6 +143,9 @@ int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, con
 /* Largest number of sequences processed per internal micro-batch for `seq_len` (activations are
  * sized to stay L2-resident); larger batches are looped internally. */
 int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len);
+/* 1 when the handle runs out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next QKV as one launch each (hidden size 384); the
+ * per-kernel-class profile then books those launches under KJC_K_GEMM_FFN_UP / KJC_K_GEMM_FFN_DOWN. */
+int kjc_encoder_chained(const KjcEncoder* enc);
 /* Number of kernel launches the last forward on this handle enqueued (for bench bookkeeping). */
 int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc);
 

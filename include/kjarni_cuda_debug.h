@@ -15,6 +15,11 @@ int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
  * iters > 0 additionally times `iters` launches (average us in *out_us). */
 int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                     const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us);
+/* The chained kernel alone: out_x[M,384] = LayerNorm(A[M,K1] x W1[384,K1]^T + bias1 + res), out2[M,N2] = epi2(out_x x W2[N2,384]^T + bias2)
+ * (epi2: 0 = bias->bf16, 1 = act(bias)->bf16); M <= 128 * number of SMs, N2 <= 1536; iters > 0 additionally times `iters` launches. */
+int kjc_dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const float* bias1, const float* gamma, const float* beta, float eps,
+                         const uint16_t* res_bf16, int M, int K1, const uint16_t* w2_bf16, const float* bias2, int N2, int epi2, int act,
+                         uint16_t* out_x_bf16, uint16_t* out2_bf16, int iters, float* out_us);
 /* out[M,384] (bf16) = LayerNorm(x + act(x W1^T + b1) W2^T + b2) with the fused feed-forward kernel; W1 [I,384], W2 [384,I];
  * iters > 0 additionally times `iters` launches (average us in *out_us). */
 int kjc_dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,

@@ -66,6 +66,7 @@ SIGNATURES = {
     "kjc_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(KjcForwardOptions), _vp]),
     "kjc_encoder_forward_device_async": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(KjcForwardOptions), _vp, _vp]),
     "kjc_encoder_micro_batch": (_i, [_vp, _i]),
+    "kjc_encoder_chained": (_i, [_vp]),
     "kjc_encoder_last_launch_count": (C.c_int64, [_vp]),
     "kjc_encoder_set_profiling": (_i, [_vp, _i]),
     "kjc_encoder_get_profile": (_i, [_vp, _vp, _vp]),
@@ -96,6 +97,7 @@ SIGNATURES = {
     "kjc_dbg_index_set_filter": (_i, [_vp, _f, _i]),
     "kjc_cosine_similarity": (_f, [_vp, _vp, C.c_size_t]),
     "kjc_dbg_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "kjc_dbg_gemm_ln_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kjc_dbg_gemm_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_ffn_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_gemm_time": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp]),

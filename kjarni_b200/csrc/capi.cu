@@ -108,6 +108,7 @@ int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, con
     const KjcForwardOptions o = opts ? *opts : default_opts();
     return guarded([&] { enc->impl.forward_device(d_ids, d_mask, d_type_ids, batch, seq_len, o, d_out, static_cast<cudaStream_t>(stream)); });
 }
+int kjc_encoder_chained(const KjcEncoder* enc) { return enc && enc->impl.chained() ? 1 : 0; }
 int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len) { return enc ? enc->impl.micro_batch(seq_len) : 0; }
 int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc) { return enc ? enc->impl.last_launches() : 0; }
 
@@ -268,6 +269,13 @@ int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
     return guarded([&] { kj::dbg_gemm(a_bf16, w_bf16, bias, residual, M, N, K, epi, act, block_n, out); });
 }
 
+int kjc_dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const float* bias1, const float* gamma, const float* beta, float eps,
+                         const uint16_t* res_bf16, int M, int K1, const uint16_t* w2_bf16, const float* bias2, int N2, int epi2, int act,
+                         uint16_t* out_x_bf16, uint16_t* out2_bf16, int iters, float* out_us) {
+    return guarded([&] {
+        kj::dbg_gemm_ln_gemm(a_bf16, w1_bf16, bias1, gamma, beta, eps, res_bf16, M, K1, w2_bf16, bias2, N2, epi2, act, out_x_bf16, out2_bf16, iters, out_us);
+    });
+}
 int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                     const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us) {
     KJC_REQUIRE(a_bf16); KJC_REQUIRE(w_bf16); KJC_REQUIRE(bias); KJC_REQUIRE(gamma); KJC_REQUIRE(beta); KJC_REQUIRE(res_bf16); KJC_REQUIRE(out_bf16);

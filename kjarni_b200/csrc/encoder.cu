@@ -16,6 +16,7 @@
 #include "encoder.hpp"
 #include "ffn_fused.cuh"
 #include "gemm_ln.cuh"
+#include "gemm_ln_gemm.cuh"
 #include "gemm_pair.cuh"
 #include "gemm_tcgen05.cuh"
 #include "rowwise.cuh"
@@ -155,6 +156,24 @@ void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensor
     p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
     launch_pdl(gemm_ln384_kernel, dim3(std::min(m_tiles, num_sms)), dim3(kLnThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
+}
+
+// GEMM + residual + LayerNorm chained with the next projection of the same 128-row tiles (gemm_ln_gemm.cuh); one tile per CTA
+void launch_gemm_ln_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_res, const CUtensorMap& t_x, const CUtensorMap& tw2,
+                         const CUtensorMap& t_out2, int M, int K1, const float* bias1, const float* gamma, const float* beta, float eps, int N2,
+                         const float* bias2, int epi2, int act, cudaStream_t st) {
+    static int configured_act[64] = {0}, configured_plain[64] = {0};  // one attribute cache per kernel instantiation
+    if (K1 % 8 != 0 || N2 % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs K % 8 == 0 and N % 8 == 0");
+    GemmLnGemmParams p;
+    p.M = M; p.K1 = K1; p.bias1 = bias1; p.gamma = gamma; p.beta = beta; p.eps = eps; p.N2 = N2; p.bias2 = bias2; p.act = act;
+    const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    if (epi2 == EPI_BIAS_ACT_BF16) {
+        ensure_smem_attr(gemm_ln_gemm_kernel<EPI_BIAS_ACT_BF16>, kLg2SmemBytes, configured_act);
+        launch_pdl(gemm_ln_gemm_kernel<EPI_BIAS_ACT_BF16>, dim3(m_tiles), dim3(kLnThreads), kLg2SmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
+    } else {
+        ensure_smem_attr(gemm_ln_gemm_kernel<EPI_BIAS_BF16>, kLg2SmemBytes, configured_plain);
+        launch_pdl(gemm_ln_gemm_kernel<EPI_BIAS_BF16>, dim3(m_tiles), dim3(kLnThreads), kLg2SmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
+    }
 }
 
 void launch_ffn_ln(const CUtensorMap& t_x, const CUtensorMap& t_w1, const CUtensorMap& t_w1_pair, const CUtensorMap& t_w2, int M, int I,
@@ -548,6 +567,8 @@ Encoder::Encoder(const std::string& dir, int device) {
         ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK, 128);
         ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK, 128);
         ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK, 128);
+        ld.t_w1_192 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, kLg2BN, kGemmBlockK, 128);      // chained kernels: 192-row boxes
+        ld.t_wqkv_192 = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, kLg2BN, kGemmBlockK, 128);
         if (H == kFfH && I % kFfChunk == 0) {
             ld.t_w1_ffn = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 64, kGemmBlockK, 128);
             ld.t_w1_ffn32 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 32, kGemmBlockK, 128);
@@ -570,6 +591,8 @@ Encoder::Encoder(const std::string& dir, int device) {
     // whole-FFN fusion (ffn_fused.cuh) is correct but shared-memory-bandwidth-bound (the 128 x 384 x tile is re-read for every 64
     // intermediate columns): 64-75 us per launch against 35 + 33 us for the two-kernel path, so it is opt-in
     fused_ffn_ = fused_ln_ && I % kFfChunk == 0 && getenv("KJC_FUSED_FFN") != nullptr;
+    // out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next layer's QKV as one launch each (gemm_ln_gemm.cuh)
+    chain_ = fused_ln_ && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
     lanes_ = 1;  // measured: no gain from concurrent lanes (the kernels are epilogue-issue-bound, not launch-latency-bound)
@@ -662,14 +685,20 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         prof_end(st);
         ++launches_;
     }
-    for (const LayerDev& L : layers_) {
+    // chained launches need one 128-row tile per CTA
+    const bool chain = chain_ && !pair_gemm_ && (M + kGemmBlockM - 1) / kGemmBlockM <= sms;
+    for (size_t li = 0; li < layers_.size(); ++li) {
+        const LayerDev& L = layers_[li];
         GemmParams g{};
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
-        g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = 3 * H; g.act = ACT_NONE;
-        prof_begin(KJC_K_GEMM_QKV, st);
-        if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, (bn_qkv_ == 192 ? w.t_qkv16_out : w.t_qkv16_out32), g, sms, st);
-        else launch_gemm(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv, w.t_qkv16_out, g, sms, st);
-        prof_end(st);
+        if (!chain || li == 0) {  // chained: layers 1.. get their QKV from the previous layer's FFN-down + LN2 launch
+            g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = 3 * H; g.act = ACT_NONE;
+            prof_begin(KJC_K_GEMM_QKV, st);
+            if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, (bn_qkv_ == 192 ? w.t_qkv16_out : w.t_qkv16_out32), g, sms, st);
+            else launch_gemm(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv, w.t_qkv16_out, g, sms, st);
+            prof_end(st);
+            ++launches_;
+        }
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
         AttnParams a;
         a.qkv = w.qkv16; a.mask = d_mask; a.ctx = w.ctx16; a.B = nb; a.S = S; a.H = H; a.heads = info_.num_heads;
@@ -679,6 +708,25 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         prof_begin(KJC_K_ATTENTION, st);
         launch_attention(a, d, st);
         prof_end(st);
+        if (chain) {
+            // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
+            prof_begin(KJC_K_GEMM_FFN_UP, st);
+            launch_gemm_ln_gemm(w.t_ctx16, L.t_wo, w.t_x16_io, w.t_x16, L.t_w1_192, w.t_h16_out32, M, H, L.bo, L.g1, L.be1, eps, I, L.b1,
+                                EPI_BIAS_ACT_BF16, act_, st);
+            prof_end(st);
+            // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
+            prof_begin(KJC_K_GEMM_FFN_DOWN, st);
+            if (li + 1 < layers_.size()) {
+                const LayerDev& Ln = layers_[li + 1];
+                launch_gemm_ln_gemm(w.t_h16, L.t_w2, w.t_x16_io, w.t_x16, Ln.t_wqkv_192, w.t_qkv16_out32, M, I, L.b2, L.g2, L.be2, eps, 3 * H, Ln.bqkv,
+                                    EPI_BIAS_BF16, ACT_NONE, st);
+            } else {
+                launch_gemm_ln(w.t_h16, L.t_w2, w.t_x16_io, M, I, L.b2, L.g2, L.be2, eps, sms, st);
+            }
+            prof_end(st);
+            launches_ += 3;
+            continue;
+        }
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
         if (fused_ln_) {
             prof_begin(KJC_K_GEMM_OUT, st);
@@ -700,7 +748,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
             prof_begin(KJC_K_GEMM_FFN_UP, st);
             launch_ffn_ln(w.t_x16, L.t_w1_ffn, L.t_w1_ffn32, L.t_w2_ffn, M, I, L.b1, L.b2, L.g2, L.be2, eps, act_, sms, st);
             prof_end(st);
-            launches_ += 4;
+            launches_ += 3;
             continue;
         }
         // t = act(x W1^T + b1)                                     (standard_new.rs:47-73)
@@ -726,7 +774,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
             prof_end(st);
             ++launches_;
         }
-        launches_ += 5;
+        launches_ += 4;
     }
     prof_begin(KJC_K_OUTPUT, st);
     if (o.output == KJC_OUT_HIDDEN) {
@@ -1074,6 +1122,65 @@ void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
 }
 
 // x_out[M,384] (bf16) = LN(x + act(x W1^T + b1) W2^T + b2) with the fused FFN kernel (in place on a device copy of x).
+// Chained kernel alone (gemm_ln_gemm.cuh): x' = LN(A W1^T + b1 + res), out2 = act(x' W2^T + b2); optional timing.
+void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const float* bias1, const float* gamma, const float* beta, float eps,
+                      const uint16_t* res_bf16, int M, int K1, const uint16_t* w2_bf16, const float* bias2, int N2, int epi2, int act,
+                      uint16_t* out_x_bf16, uint16_t* out2_bf16, int iters, float* us) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    KJ_CUDA(cudaGetDevice(&dev));
+    KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if ((M + kGemmBlockM - 1) / kGemmBlockM > prop.multiProcessorCount) throw Error(KJC_INVALID_CONFIG, "chained kernel: one 128-row tile per SM at most");
+    if (N2 > kLg2BiasMax) throw Error(KJC_INVALID_CONFIG, "chained kernel: N2 too large");
+    const size_t Mp = std::max(M, 128), N2p = std::max(N2, kLg2BN);
+    __nv_bfloat16 *dA, *dW, *dX, *dW2, *dO;
+    float *dB, *dG, *dBt, *dB2;
+    KJ_CUDA(cudaMalloc(&dA, Mp * K1 * 2));
+    KJ_CUDA(cudaMalloc(&dW, static_cast<size_t>(kLnN) * K1 * 2));
+    KJ_CUDA(cudaMalloc(&dX, Mp * kLnN * 2));
+    KJ_CUDA(cudaMalloc(&dW2, N2p * kLnN * 2));
+    KJ_CUDA(cudaMalloc(&dO, Mp * N2 * 2));
+    KJ_CUDA(cudaMemset(dA, 0, Mp * K1 * 2));
+    KJ_CUDA(cudaMemset(dX, 0, Mp * kLnN * 2));
+    KJ_CUDA(cudaMemset(dW2, 0, N2p * kLnN * 2));
+    KJ_CUDA(cudaMemset(dO, 0, Mp * N2 * 2));
+    KJ_CUDA(cudaMalloc(&dB, kLnN * 4)); KJ_CUDA(cudaMalloc(&dG, kLnN * 4)); KJ_CUDA(cudaMalloc(&dBt, kLnN * 4));
+    KJ_CUDA(cudaMalloc(&dB2, static_cast<size_t>(N2) * 4));
+    KJ_CUDA(cudaMemcpy(dA, a_bf16, static_cast<size_t>(M) * K1 * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dW, w1_bf16, static_cast<size_t>(kLnN) * K1 * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dX, res_bf16, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dW2, w2_bf16, static_cast<size_t>(N2) * kLnN * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dB, bias1, kLnN * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dG, gamma, kLnN * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dBt, beta, kLnN * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dB2, bias2, static_cast<size_t>(N2) * 4, cudaMemcpyHostToDevice));
+    CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K1, kGemmBlockM, kGemmBlockK, 128);
+    CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kLnN, K1, kLnHalfN, kGemmBlockK, 128);
+    CUtensorMap tres = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, 32, kEpiChunkCols, 64);
+    CUtensorMap tx = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, kGemmBlockM, kGemmBlockK, 128);
+    CUtensorMap tw2 = make_tmap_2d(dW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N2p, kLnN, kLg2BN, kGemmBlockK, 128);
+    CUtensorMap to2 = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N2, 32, kEpiChunkCols, 64);
+    auto go = [&] { launch_gemm_ln_gemm(ta, tw, tres, tx, tw2, to2, M, K1, dB, dG, dBt, eps, N2, dB2, epi2, act, nullptr); };
+    go();
+    KJ_CUDA(cudaDeviceSynchronize());
+    KJ_CUDA(cudaMemcpy(out_x_bf16, dX, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyDeviceToHost));
+    KJ_CUDA(cudaMemcpy(out2_bf16, dO, static_cast<size_t>(M) * N2 * 2, cudaMemcpyDeviceToHost));
+    if (iters > 0 && us) {  // timing (in place: the values drift, the work does not)
+        cudaEvent_t e0, e1;
+        KJ_CUDA(cudaEventCreate(&e0));
+        KJ_CUDA(cudaEventCreate(&e1));
+        KJ_CUDA(cudaEventRecord(e0, nullptr));
+        for (int i = 0; i < iters; ++i) go();
+        KJ_CUDA(cudaEventRecord(e1, nullptr));
+        KJ_CUDA(cudaDeviceSynchronize());
+        float ms = 0.f;
+        KJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *us = ms * 1e3f / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(dA); cudaFree(dW); cudaFree(dX); cudaFree(dW2); cudaFree(dO); cudaFree(dB); cudaFree(dG); cudaFree(dBt); cudaFree(dB2);
+}
+
 void dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
                 const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* us) {
     cudaDeviceProp prop;

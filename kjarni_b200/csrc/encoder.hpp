@@ -33,6 +33,9 @@ void launch_layernorm(const float* y, const float* g, const float* b, float eps,
 
 void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* residual, int M, int N, int K, int epi,
               int act, int block_n, void* out);
+void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const float* bias1, const float* gamma, const float* beta, float eps,
+                      const uint16_t* res_bf16, int M, int K1, const uint16_t* w2_bf16, const float* bias2, int N2, int epi2, int act,
+                      uint16_t* out_x_bf16, uint16_t* out2_bf16, int iters, float* us);
 void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                  const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* us);
 float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters);
@@ -87,6 +90,7 @@ struct LayerDev {
     const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
     CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
     CUtensorMap t_w1_ffn, t_w1_ffn32, t_w2_ffn;  // fused FFN kernel: W1 boxes of 64 (one CTA) / 32 (CTA pair) rows, W2 boxes of 64 rows
+    CUtensorMap t_w1_192, t_wqkv_192;    // 192-row boxes: phase-2 weights of the chained GEMM+LN -> GEMM kernel
     CUtensorMap t_wqkv_half, t_w1_half;  // box of block_n/2 rows: the CTA-pair GEMM loads half a weight tile per CTA
 };
 
@@ -101,6 +105,7 @@ class Encoder {
     const std::vector<std::string>& labels() const { return labels_; }
     int micro_batch(int seq_len) const;
     int64_t last_launches() const { return launches_; }
+    bool chained() const { return chain_; }
     // Per-kernel-class CUDA-event timing of the forwards issued while profiling is on (bench roofline numbers).
     void set_profiling(bool on);
     void get_profile(double* ms, int64_t* launches);  // arrays of KJC_NUM_KERNEL_CLASSES; synchronises
@@ -147,7 +152,7 @@ class Encoder {
     const float *word_ = nullptr, *pos_ = nullptr, *type_ = nullptr, *emb_g_ = nullptr, *emb_b_ = nullptr;
     const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
     std::vector<LayerDev> layers_;
-    bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false;
+    bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false;
     int lanes_ = 2;
     std::vector<Workspace> ws_;
     cudaEvent_t ev_in_ = nullptr;

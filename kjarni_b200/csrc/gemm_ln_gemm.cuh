@@ -1,0 +1,399 @@
+// Two dependent projections of the encoder layer in ONE launch, for hidden size 384 (MiniLM):
+//     x'  [M,384]  (bf16) = LayerNorm( A[M,K1] x W1[384,K1]^T + b1 + x[M,384] ; gamma, beta, eps )     (phase 1)
+//     out [M,N2]   (bf16) = act( x' x W2[N2,384]^T + b2 )                                                (phase 2)
+// i.e.  attention out-proj + residual + LN1  ->  FFN-up (+ erf-GELU)            (encoder_layer.rs:120-147 + standard_new.rs:47-73)
+// and   FFN-down + residual + LN2            ->  the NEXT layer's fused QKV     (encoder_layer.rs:150-176 + qkv_projection.rs:93-138).
+//
+// Why: every op of the layer is local to a 128-token tile, so the CTA that produced tile b of x' can run the next projection of
+// tile b straight away.  Against two launches this removes one launch's fill and drain bubbles (~5 us of a ~20 us launch,
+// DESIGN.md section 5), the re-load of x' as the A operand (it never leaves shared memory: 6 k-blocks of 16 KB written by the
+// LayerNorm epilogue directly in the 128B-swizzled K-major layout the tensor core reads) and one third of the TMA writes into
+// shared memory during phase 2 -- shared-memory bandwidth is what bounds these K = 384 GEMMs.
+//
+// One tile per CTA (the host falls back to the two separate kernels when there are more 128-row tiles than SMs).
+// Shared memory (bytes) -- phase 2 lives entirely inside phase 1's operand ring:
+//     [0, 48K)       phase 1: A ring, 3 x 16 KB               | phase 2: W2 stages 0, 1 (2 x 24 KB)
+//     [48K, 96K)     phase 1: W ring stage 0 (= LN staging)   | phase 2: W2 stage 2 (24 KB) + output staging (12 x 2 KB)
+//     [96K, 192K)    phase 1: W ring stages 1, 2              | phase 2: x' tile, 6 x 16 KB (A operand, resident)
+// TMEM: phase 1 accumulates the full 128 x 384 rows in columns [0, 384); phase 2 double-buffers 128 x 192 accumulators in
+// [0, 192) and [192, 384).  Warp roles as in gemm_ln.cuh (warp 0 TMA, warp 1 MMA, warp 2 TMEM, warps 4-15 epilogue).
+// Results are bit-identical to gemm_ln384_kernel followed by gemm_tcgen05_kernel<192, EPI>: same MMA shapes, same k order.
+#pragma once
+#include <cuda.h>
+
+#include "gemm_ln.cuh"
+
+namespace kj {
+
+constexpr int kLg2BN = 192;                                 // phase-2 tile width
+constexpr int kLg2WBytes = kLg2BN * kGemmBlockK * 2;        // 24 KB per W2 stage
+constexpr int kLg2Stages = 3;
+constexpr int kLg2KB = kLnN / kGemmBlockK;                  // 6 k-blocks of the resident x' tile
+constexpr int kLg2BiasMax = 1536;                           // phase-2 bias columns staged in shared memory
+constexpr int kLg2RingBytes = 3 * kLnStageBytes;            // 192 KB: phase 1 always runs a 3-stage ring here
+constexpr int kLg2SmemBytes = kLg2RingBytes + kLnStatBytes + kLnVecBytes + kLg2BiasMax * 4 + 512;
+static_assert(kLg2SmemBytes <= 232448, "shared memory budget");
+static_assert(2 * kLg2WBytes <= 3 * kLnABytes && kLg2WBytes + kLnEpiWarps * kEpiStageBytes <= kLnBBytes, "phase-2 aliasing");
+
+struct GemmLnGemmParams {
+    int M, K1;
+    const float* bias1;  // [384] or nullptr
+    const float* gamma;  // [384]
+    const float* beta;   // [384]
+    float eps;
+    int N2;              // phase-2 output columns (multiple of 8; tiles of 192, the last one may be partial)
+    const float* bias2;  // [N2] or nullptr
+    int act;             // Activation (EPI_BIAS_ACT_BF16)
+};
+
+template <int EPI2>
+__global__ void __launch_bounds__(kLnThreads, 1)
+gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x,
+                    const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out2, GemmLnGemmParams p) {
+    static_assert(EPI2 == EPI_BIAS_BF16 || EPI2 == EPI_BIAS_ACT_BF16, "phase 2 stores bf16");
+    extern __shared__ __align__(1024) uint8_t smem_lg[];
+    uint8_t* smem = smem_lg;
+    if (smem_u32(smem) & 1023) __trap();
+    // phase 1 views
+    uint8_t* smem_a = smem;                         // 3 x 16 KB
+    uint8_t* smem_b = smem + 3 * kLnABytes;         // 3 x 48 KB
+    uint8_t* smem_epi1 = smem_b;                    // LN residual staging (12 x 4 KB), aliased on W stage 0
+    // phase 2 views
+    uint8_t* smem_x = smem_b + kLnBBytes;           // x' tile: 6 x 16 KB
+    auto w2_stage = [&](int s) -> uint8_t* { return s < 2 ? smem + s * kLg2WBytes : smem_b; };
+    uint8_t* smem_epi2 = smem_b + kLg2WBytes;       // 12 x 2 KB
+    uint8_t* tail = smem + kLg2RingBytes;
+    float2* stat = reinterpret_cast<float2*>(tail);  // [3][128]
+    float* s_bias = reinterpret_cast<float*>(tail + kLnStatBytes);
+    float* s_gamma = s_bias + kLnN;
+    float* s_beta = s_gamma + kLnN;
+    float* s_bias2 = s_beta + kLnN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias2 + kLg2BiasMax);
+    uint64_t* full1 = bars;               // [3]
+    uint64_t* empty1 = bars + 3;          // [3]
+    uint64_t* tmem_full1 = bars + 6;      // phase-1 accumulator complete (all phase-1 MMAs retired)
+    uint64_t* res_bar = bars + 7;         // [12 warps][2 buffers]
+    uint64_t* x_ready = bars + 31;        // x' tile written, LN accumulator consumed, staging region free (12 arrivals)
+    uint64_t* full2 = bars + 32;          // [3]
+    uint64_t* empty2 = bars + 35;         // [3]
+    uint64_t* acc_full = bars + 38;       // [2]
+    uint64_t* acc_empty = bars + 40;      // [2] (12 arrivals each)
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 42);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;  // one 128-row tile per CTA
+    const int k_blocks1 = (p.K1 + kGemmBlockK - 1) / kGemmBlockK;
+    const int n2_tiles = (p.N2 + kLg2BN - 1) / kLg2BN;
+    const bool bias2_in_smem = p.bias2 != nullptr && p.N2 <= kLg2BiasMax;
+
+    // weights: independent of the predecessor kernel, staged before griddepcontrol.wait
+    for (int i = threadIdx.x; i < kLnN; i += kLnThreads) {
+        s_bias[i] = p.bias1 != nullptr ? __ldg(p.bias1 + i) : 0.0f;
+        s_gamma[i] = __ldg(p.gamma + i);
+        s_beta[i] = __ldg(p.beta + i);
+    }
+    if (bias2_in_smem)
+        for (int i = threadIdx.x; i < p.N2; i += kLnThreads) s_bias2[i] = __ldg(p.bias2 + i);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_res);
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w2);
+        tma_prefetch_desc(&tmap_out2);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&full1[i], 1);
+            mbar_init(&empty1[i], 1);
+            mbar_init(&full2[i], 1);
+            mbar_init(&empty2[i], 1);
+        }
+        mbar_init(tmem_full1, 1);
+        for (int i = 0; i < 2 * kLnEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+        mbar_init(x_ready, kLnEpiWarps);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], kLnEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<512>(tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_smem;
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < k_blocks1; ++kb) {
+                mbar_wait(&empty1[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full1[stage], kLnStageBytes);
+                tma_load_2d(smem_a + stage * kLnABytes, &tmap_a, &full1[stage], kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
+                tma_load_2d(smem_b + stage * kLnBBytes, &tmap_w, &full1[stage], kb * kGemmBlockK, 0, kEvictLast);
+                tma_load_2d(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, &full1[stage], kb * kGemmBlockK, kLnHalfN, kEvictLast);
+                if (++stage == 3) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            // phase 2: W2 tiles.  Stages 0 and 1 alias the phase-1 A ring (free once every phase-1 MMA has retired), stage 2 aliases
+            // the LayerNorm staging (free once the LayerNorm epilogue is done): the first two stages are prefetched under the epilogue.
+            mbar_wait(tmem_full1, 0);
+            int it = 0;
+            for (int nb = 0; nb < n2_tiles; ++nb) {
+                for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
+                    const int s = it % kLg2Stages;
+                    if (it == 2) mbar_wait(x_ready, 0);
+                    mbar_wait(&empty2[s], ((it / kLg2Stages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full2[s], kLg2WBytes);
+                    tma_load_2d(w2_stage(s), &tmap_w2, &full2[s], kb * kGemmBlockK, nb * kLg2BN, kEvictLast);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, kLnHalfN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < k_blocks1; ++kb) {
+                mbar_wait(&full1[stage], phase);
+                tc_fence_after();
+                const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * kLnABytes));
+                const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes));
+                const uint64_t db1 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes + kLnHalfN * 128));
+#pragma unroll
+                for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                    umma_f16(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                    umma_f16(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty1[stage]);
+                if (kb == k_blocks1 - 1) umma_commit(tmem_full1);
+                if (++stage == 3) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            // phase 2: A = the resident x' tile, W2 streamed; accumulators [0,192) / [192,384) alternate
+            mbar_wait(x_ready, 0);
+            tc_fence_after();
+            int it = 0;
+            for (int nb = 0; nb < n2_tiles; ++nb) {
+                const int acc = nb & 1;
+                mbar_wait(&acc_empty[acc], ((nb >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * kLg2BN;
+                for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
+                    const int s = it % kLg2Stages;
+                    mbar_wait(&full2[s], (it / kLg2Stages) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_x + kb * kLnABytes));
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(w2_stage(s)));
+#pragma unroll
+                    for (int k = 0; k < kGemmBlockK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty2[s]);
+                    if (kb == kLg2KB - 1) umma_commit(&acc_full[acc]);
+                }
+            }
+        }
+    } else if (warp >= kGemmEpiWarp0) {
+        // ---------------------------------------------------------- epilogues
+        const int ew = warp - kGemmEpiWarp0;  // 0..11
+        const int quad = warp & 3;
+        const int part = ew >> 2;
+        constexpr int kChunks = kLnPartCols / kEpiChunkCols;  // 4
+        uint8_t* ebuf = smem_epi1 + ew * kLnEpiBytesPerWarp;
+        uint64_t* rbar = res_bar + 2 * ew;
+        const uint32_t sw = (lane >> 1) & 3;  // 64B swizzle of this lane's row (residual / phase-2 staging tiles)
+        const int trow = quad * 32 + lane;    // row inside the tile
+        const int row0 = tile * kGemmBlockM + quad * 32;
+        uint32_t rphase = 0;
+        {
+            // ===== phase 1: bias + residual + LayerNorm, output into the resident x' tile
+            const int col_base = part * kLnPartCols;
+            mbar_wait(tmem_full1, 0);
+            tc_fence_after();
+            if (lane == 0) {
+                for (int c = 0; c < 2; ++c) {
+                    mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
+                    tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
+                }
+            }
+            __syncwarp();
+            const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
+            float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                const int b = c & 1;
+                uint32_t v[32];
+                tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
+                mbar_wait(&rbar[b], (rphase >> b) & 1);
+                rphase ^= 1u << b;
+                const uint32_t rbase = smem_u32(ebuf + b * kEpiStageBytes) + lane * 64;
+                uint4 r4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r4[j] = ld_shared_v4(rbase + ((j ^ sw) << 4));
+                tmem_ld_wait();
+                const float* bs = s_bias + col_base + c * kEpiChunkCols;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
+                    const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
+                    const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                        const float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo + bb[2 * e];
+                        const float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi + bb[2 * e + 1];
+                        s1 += a0 + a1;
+                        s2 = fmaf(a0, a0, s2);
+                        s2 = fmaf(a1, a1, s2);
+                        v[8 * j + 2 * e] = __float_as_uint(a0);
+                        v[8 * j + 2 * e + 1] = __float_as_uint(a1);
+                    }
+                }
+                tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
+                __syncwarp();
+                if (lane == 0 && c + 2 < kChunks) {
+                    mbar_arrive_expect_tx(&rbar[b], kEpiStageBytes);
+                    tma_load_2d(ebuf + b * kEpiStageBytes, &tmap_res, &rbar[b], col_base + (c + 2) * kEpiChunkCols, row0, kEvictFirst);
+                }
+            }
+            tmem_st_wait();
+            stat[part * 128 + trow] = make_float2(s1, s2);
+            named_bar_sync(1, kLnEpiWarps * 32);
+            float t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < kLnParts; ++q) {
+                const float2 t = stat[q * 128 + trow];
+                t1 += t.x;
+                t2 += t.y;
+            }
+            const float mean = t1 * (1.0f / kLnN);
+            const float var = fmaxf(t2 * (1.0f / kLnN) - mean * mean, 0.0f);
+            const float rstd = 1.0f / sqrtf(var + p.eps);
+            const float nmr = -mean * rstd;
+            // pass B: normalise -> bf16 -> the x' tile in the K-major 128B-swizzled layout (k-block = 64 columns, row = 128 B,
+            // 16-byte chunk index ^= row & 7): exactly what a TMA load of x' with the A-operand tensor map would have produced
+            const uint32_t xsw = static_cast<uint32_t>(trow & 7);
+#pragma unroll 1
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
+                tmem_ld_wait();
+                const int col0 = col_base + c * kEpiChunkCols;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 g = *reinterpret_cast<const float4*>(s_gamma + col0 + 4 * j);
+                    const float4 bt = *reinterpret_cast<const float4*>(s_beta + col0 + 4 * j);
+                    f[4 * j + 0] = fmaf(fmaf(__uint_as_float(v[4 * j + 0]), rstd, nmr), g.x, bt.x);
+                    f[4 * j + 1] = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr), g.y, bt.y);
+                    f[4 * j + 2] = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr), g.z, bt.z);
+                    f[4 * j + 3] = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr), g.w, bt.w);
+                }
+                const uint32_t xrow = smem_u32(smem_x) + (col0 >> 6) * kLnABytes + trow * 128;
+                const uint32_t chunk0 = static_cast<uint32_t>((col0 & 63) >> 3);  // 0 or 4
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    st_shared_v4(xrow + (((chunk0 + j) ^ xsw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                }
+            }
+            fence_proxy_async_smem();  // x' (generic-proxy stores) -> visible to the tensor core and to the TMA store below
+            tc_fence_before();         // the LayerNorm accumulator is fully read: phase-2 MMAs may overwrite it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_ready);
+        }
+        // x' goes to global memory as well (residual of the next LayerNorm, pooling / hidden-state output): six 16 KB stores
+        // straight out of the operand tile; rows >= M are clipped by the tensor map
+        if (ew == 0 && lane == 0) {
+            mbar_wait(x_ready, 0);
+            for (int kb = 0; kb < kLg2KB; ++kb) tma_store_2d(&tmap_x, smem_x + kb * kLnABytes, kb * kGemmBlockK, tile * kGemmBlockM);
+            bulk_commit();
+        }
+        {
+            // ===== phase 2: bias (+ activation) -> bf16 -> 32 x 32 staging chunk -> TMA store, per 192-column tile
+            uint8_t* sbuf = smem_epi2 + ew * kEpiStageBytes;
+            mbar_wait(x_ready, 0);  // the staging chunk aliases the LayerNorm staging of OTHER warps
+            for (int nb = 0; nb < n2_tiles; ++nb) {
+                const int acc = nb & 1;
+                mbar_wait(&acc_full[acc], (nb >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kLg2BN + part * 64;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr0 + c * 32, v);
+                    tmem_ld_wait();
+                    if (c == 1) {  // last load landed: release the accumulator before the math and stores of this chunk
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
+                    const int col0 = nb * kLg2BN + part * 64 + c * 32;
+                    if (col0 < p.N2) {
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (bias2_in_smem && col0 + 32 <= p.N2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b = *reinterpret_cast<const float4*>(s_bias2 + col0 + 4 * j);
+                                f[4 * j + 0] += b.x;
+                                f[4 * j + 1] += b.y;
+                                f[4 * j + 2] += b.z;
+                                f[4 * j + 3] += b.w;
+                            }
+                        } else if (p.bias2 != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (col0 + 4 * j < p.N2) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + col0) + j);
+                                    f[4 * j + 0] += b.x;
+                                    f[4 * j + 1] += b.y;
+                                    f[4 * j + 2] += b.z;
+                                    f[4 * j + 3] += b.w;
+                                }
+                            }
+                        }
+                        if (EPI2 == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
+                        if (lane == 0) bulk_wait_read<0>();  // the previous chunk's store (and, for warp 4, the x' stores) has read smem
+                        __syncwarp();
+                        const uint32_t rbase = smem_u32(sbuf) + lane * 64;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            st_shared_v4(rbase + ((j ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_out2, sbuf, col0, row0);
+                            bulk_commit();
+                        }
+                    }
+                }
+            }
+            if (lane == 0) bulk_wait_read<0>();  // shared memory stays valid until the last store has read it
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+}  // namespace kj

@@ -203,3 +203,43 @@ def test_attention_fully_padded_sequence_conventions():
     N.check(N.lib().kjc_dbg_attention(ptr(to_bf16_bits(qkv)), ptr(mask), B, S, H, heads, 1, ptr(out)))
     got = from_bf16_bits(out)
     assert np.isnan(got[S:]).all() and np.isfinite(got[:S]).all()
+
+
+@pytest.mark.parametrize("M,K1,N2,epi2", [(128, 384, 1536, 1), (1000, 384, 1536, 1), (300, 1536, 1152, 0), (18944, 384, 1536, 1),
+                                          (18944, 1536, 1152, 0), (77, 64, 208, 0)])
+def test_chained_gemm_ln_gemm(M, K1, N2, epi2):
+    """GEMM + residual + LayerNorm chained with the next projection in one launch (gemm_ln_gemm.cuh): x' must equal the fused
+    GEMM+LN kernel bit for bit, the second projection must equal the stand-alone GEMM on x' bit for bit (same MMA shapes and k
+    order), and both must match the fp32 oracle formulas."""
+    import ctypes as C
+
+    rng = np.random.default_rng(M + K1 + N2)
+    H = 384
+    a = rng.standard_normal((M, K1)).astype(np.float32)
+    w1 = (rng.standard_normal((H, K1)) / math.sqrt(K1)).astype(np.float32)
+    b1 = rng.standard_normal(H).astype(np.float32) * 0.1
+    gamma = (1 + 0.1 * rng.standard_normal(H)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(H)).astype(np.float32)
+    res = rng.standard_normal((M, H)).astype(np.float32)
+    w2 = (rng.standard_normal((N2, H)) / math.sqrt(H)).astype(np.float32)
+    b2 = rng.standard_normal(N2).astype(np.float32) * 0.1
+    out_x = np.empty((M, H), np.uint16)
+    out2 = np.empty((M, N2), np.uint16)
+    us = C.c_float()
+    N.check(N.lib().kjc_dbg_gemm_ln_gemm(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w1)), ptr(b1), ptr(gamma), ptr(beta), 1e-12, ptr(to_bf16_bits(res)),
+                                         M, K1, ptr(to_bf16_bits(w2)), ptr(b2), N2, epi2, 0, ptr(out_x), ptr(out2), 0, C.byref(us)))
+    # the two-kernel path
+    ref_x = np.empty((M, H), np.uint16)
+    N.check(N.lib().kjc_dbg_gemm_ln(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w1)), ptr(b1), ptr(gamma), ptr(beta), 1e-12, ptr(to_bf16_bits(res)), M, K1,
+                                    ptr(ref_x), 0, C.byref(us)))
+    assert np.array_equal(out_x, ref_x)
+    ref2 = np.empty((M, N2), np.uint16)
+    N.check(N.lib().kjc_dbg_gemm(ptr(ref_x), ptr(to_bf16_bits(w2)), ptr(b2), None, M, N2, H, epi2, 0, 192, ptr(ref2)))
+    assert np.array_equal(out2, ref2)
+    # and the oracle
+    y = (bf16_round(a).astype(np.float64) @ bf16_round(w1).astype(np.float64).T + b1 + bf16_round(res)).astype(np.float32)
+    want_x = ko.layer_norm(y, gamma, beta, 1e-12)
+    got_x = from_bf16_bits(out_x)
+    assert (np.abs(got_x - want_x) / (1.0 + np.abs(want_x))).max() < 2.0 ** -7
+    want2 = ref_gemm(got_x, w2, b2, None, epi2, 0)
+    assert (np.abs(from_bf16_bits(out2) - want2) / (1.0 + np.abs(want2))).max() < 2.0 ** -8
