@@ -315,6 +315,19 @@ def main():
     gb = {"layernorm": 2.0 * L * M * H * 10, "embed_ln": M * 4.0 + M * H * 4.0 + M * H * 6.0, "output": M * H * 4.0 + B * H * 4.0}
     if pn[N.KERNEL_CLASSES.index("gemm_ffn_down")] == 0:  # fused feed-forward kernel: up + GELU + down + residual + LayerNorm in one launch
         tf["gemm_ffn_up"] += tf["gemm_ffn_down"]
+    chained = bool(lib.kjc_encoder_chained(enc._h))
+    contains = {}
+    if chained:
+        # chained launches (gemm_ln_gemm.cuh): class gemm_ffn_up = out-proj + LN1 + FFN-up, class gemm_ffn_down = FFN-down + LN2 + the
+        # NEXT layer's QKV (plain FFN-down + LN2 in the last layer), class gemm_qkv = layer 0 only; their algorithmic flops follow
+        qkv_l = tf["gemm_qkv"] / L
+        tf["gemm_ffn_up"] += tf.pop("gemm_out")
+        tf["gemm_ffn_down"] += qkv_l * (L - 1)
+        tf["gemm_qkv"] = qkv_l
+        if pn[N.KERNEL_CLASSES.index("embed_ln")] == 0:
+            gb.pop("embed_ln", None)
+        contains = {"gemm_qkv": "embedding gather + embed LN -> QKV projection of layer 0, one launch", "gemm_ffn_up": "out-proj + residual + LN1 -> FFN-up + GELU, one launch per layer",
+                    "gemm_ffn_down": "FFN-down + residual + LN2 -> next layer's QKV, one launch per layer (last layer: FFN-down + LN2 only)"}
     kernels = {}
     tot_ms = sum(pms[i] for i in range(8)) / prof_steps
     for i, name in enumerate(N.KERNEL_CLASSES):
@@ -327,6 +340,8 @@ def main():
         else:
             k.update(bound="hbm", achieved=round(gb[name] / (ms_i * 1e-3) / 1e9, 1), unit="GB/s", peak=peaks["hbm_gbs"])
         k["frac"] = round(k["achieved"] / k["peak"], 4)
+        if name in contains:
+            k["contains"] = contains[name]
         kernels[name] = k
     dom = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
     traffic = None

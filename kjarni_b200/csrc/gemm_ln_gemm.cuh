@@ -44,9 +44,21 @@ struct GemmLnGemmParams {
     int N2;              // phase-2 output columns (multiple of 8; tiles of 192, the last one may be partial)
     const float* bias2;  // [N2] or nullptr
     int act;             // Activation (EPI_BIAS_ACT_BF16)
+    // P1 == 1 (embedding front end): phase 1 = Embeddings::forward + embed LayerNorm instead of a GEMM (rowwise.cuh EmbedParams)
+    const uint32_t* ids;       // [M]
+    const uint32_t* type_ids;  // [M] or nullptr (row 0 of the type table for every token)
+    const float* word;         // [vocab, 384]
+    const float* pos;          // [max_pos, 384] or nullptr
+    const float* type;         // [type_vocab, 384] or nullptr
+    int* err_flag;             // set to 1 on a token-type id out of range (the reference panics)
+    int S, vocab, max_pos, type_vocab, pos_offset;
 };
 
-template <int EPI2>
+// P1 = 0: phase 1 is the GEMM + residual + LayerNorm described above.
+// P1 = 1: phase 1 is the embedding front end -- word[id] (+ pos[offset + s]) (+ type[tt]) -> embed LayerNorm (reference:
+//         cpu/embeddings/mod.rs:181-326, transformer_encoder.rs:303-305), gathered by the epilogue warps (thread = token, 128
+//         columns each) straight into TMEM for the same two-pass LayerNorm; phase 2 is then layer 0's QKV projection.
+template <int EPI2, int P1 = 0>
 __global__ void __launch_bounds__(kLnThreads, 1)
 gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x,
@@ -133,7 +145,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < k_blocks1; ++kb) {
+            for (int kb = 0; kb < (P1 == 0 ? k_blocks1 : 0); ++kb) {
                 mbar_wait(&empty1[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&full1[stage], kLnStageBytes);
                 tma_load_2d(smem_a + stage * kLnABytes, &tmap_a, &full1[stage], kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
@@ -146,7 +158,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             // phase 2: W2 tiles.  Stages 0 and 1 alias the phase-1 A ring (free once every phase-1 MMA has retired), stage 2 aliases
             // the LayerNorm staging (free once the LayerNorm epilogue is done): the first two stages are prefetched under the epilogue.
-            mbar_wait(tmem_full1, 0);
+            if (P1 == 0) mbar_wait(tmem_full1, 0);
             int it = 0;
             for (int nb = 0; nb < n2_tiles; ++nb) {
                 for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
@@ -164,7 +176,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, kLnHalfN);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < k_blocks1; ++kb) {
+            for (int kb = 0; kb < (P1 == 0 ? k_blocks1 : 0); ++kb) {
                 mbar_wait(&full1[stage], phase);
                 tc_fence_after();
                 const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * kLnABytes));
@@ -219,53 +231,101 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         {
             // ===== phase 1: bias + residual + LayerNorm, output into the resident x' tile
             const int col_base = part * kLnPartCols;
-            mbar_wait(tmem_full1, 0);
-            tc_fence_after();
-            if (lane == 0) {
-                for (int c = 0; c < 2; ++c) {
-                    mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
-                    tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
-                }
-            }
-            __syncwarp();
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
             float s1 = 0.0f, s2 = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < kChunks; ++c) {
-                const int b = c & 1;
-                uint32_t v[32];
-                tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
-                mbar_wait(&rbar[b], (rphase >> b) & 1);
-                rphase ^= 1u << b;
-                const uint32_t rbase = smem_u32(ebuf + b * kEpiStageBytes) + lane * 64;
-                uint4 r4[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) r4[j] = ld_shared_v4(rbase + ((j ^ sw) << 4));
-                tmem_ld_wait();
-                const float* bs = s_bias + col_base + c * kEpiChunkCols;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
-                    const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-                        const float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo + bb[2 * e];
-                        const float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi + bb[2 * e + 1];
-                        s1 += a0 + a1;
-                        s2 = fmaf(a0, a0, s2);
-                        s2 = fmaf(a1, a1, s2);
-                        v[8 * j + 2 * e] = __float_as_uint(a0);
-                        v[8 * j + 2 * e + 1] = __float_as_uint(a1);
+            if constexpr (P1 == 0) {
+                mbar_wait(tmem_full1, 0);
+                tc_fence_after();
+                if (lane == 0) {
+                    for (int c = 0; c < 2; ++c) {
+                        mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
+                        tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
                     }
                 }
-                tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
                 __syncwarp();
-                if (lane == 0 && c + 2 < kChunks) {
-                    mbar_arrive_expect_tx(&rbar[b], kEpiStageBytes);
-                    tma_load_2d(ebuf + b * kEpiStageBytes, &tmap_res, &rbar[b], col_base + (c + 2) * kEpiChunkCols, row0, kEvictFirst);
+#pragma unroll 1
+                for (int c = 0; c < kChunks; ++c) {
+                    const int b = c & 1;
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
+                    mbar_wait(&rbar[b], (rphase >> b) & 1);
+                    rphase ^= 1u << b;
+                    const uint32_t rbase = smem_u32(ebuf + b * kEpiStageBytes) + lane * 64;
+                    uint4 r4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) r4[j] = ld_shared_v4(rbase + ((j ^ sw) << 4));
+                    tmem_ld_wait();
+                    const float* bs = s_bias + col_base + c * kEpiChunkCols;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
+                        const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
+                        const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+                            const float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo + bb[2 * e];
+                            const float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi + bb[2 * e + 1];
+                            s1 += a0 + a1;
+                            s2 = fmaf(a0, a0, s2);
+                            s2 = fmaf(a1, a1, s2);
+                            v[8 * j + 2 * e] = __float_as_uint(a0);
+                            v[8 * j + 2 * e + 1] = __float_as_uint(a1);
+                        }
+                    }
+                    tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
+                    __syncwarp();
+                    if (lane == 0 && c + 2 < kChunks) {
+                        mbar_arrive_expect_tx(&rbar[b], kEpiStageBytes);
+                        tma_load_2d(ebuf + b * kEpiStageBytes, &tmap_res, &rbar[b], col_base + (c + 2) * kEpiChunkCols, row0, kEvictFirst);
+                    }
+                }
+            } else {
+                // embedding gather: this thread's token, columns [col_base, col_base + 128)
+                const int row = tile * kGemmBlockM + trow;
+                const bool live = row < p.M;
+                uint32_t id = 0, tt = 0;
+                bool has_word = false, has_pos = false;
+                int pidx = 0;
+                const bool has_type = p.type != nullptr && p.type_vocab > 0;
+                if (live) {
+                    id = __ldg(p.ids + row);
+                    has_word = id < static_cast<uint32_t>(p.vocab);       // ids >= vocab contribute a zero row (embeddings/mod.rs:227-246)
+                    pidx = p.pos_offset + row % p.S;
+                    has_pos = p.pos != nullptr && pidx < p.max_pos;       // positions beyond the table add nothing (:199-214)
+                    if (has_type && p.type_ids != nullptr) {
+                        tt = __ldg(p.type_ids + row);
+                        if (tt >= static_cast<uint32_t>(p.type_vocab)) {  // the reference panics (:312-317)
+                            *p.err_flag = 1;
+                            tt = 0;
+                        }
+                    }
+                }
+                const float4* wrow = reinterpret_cast<const float4*>(p.word + static_cast<size_t>(has_word ? id : 0) * kLnN + col_base);
+                const float4* prow = reinterpret_cast<const float4*>((has_pos ? p.pos : p.word) + static_cast<size_t>(has_pos ? pidx : 0) * kLnN + col_base);
+                const float4* trw = reinterpret_cast<const float4*>((has_type ? p.type : p.word) + static_cast<size_t>(tt) * kLnN + col_base);
+                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int c = 0; c < kChunks; ++c) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 a = (live && has_word) ? __ldg(wrow + c * 8 + j) : z4;
+                        const float4 b = (live && has_pos) ? __ldg(prow + c * 8 + j) : z4;
+                        const float4 t = (live && has_type) ? __ldg(trw + c * 8 + j) : z4;
+                        const float e0 = (a.x + b.x) + t.x, e1 = (a.y + b.y) + t.y, e2 = (a.z + b.z) + t.z, e3 = (a.w + b.w) + t.w;
+                        s1 += (e0 + e1) + (e2 + e3);
+                        s2 = fmaf(e0, e0, s2);
+                        s2 = fmaf(e1, e1, s2);
+                        s2 = fmaf(e2, e2, s2);
+                        s2 = fmaf(e3, e3, s2);
+                        v[4 * j + 0] = __float_as_uint(e0);
+                        v[4 * j + 1] = __float_as_uint(e1);
+                        v[4 * j + 2] = __float_as_uint(e2);
+                        v[4 * j + 3] = __float_as_uint(e3);
+                    }
+                    tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
                 }
             }
             tmem_st_wait();

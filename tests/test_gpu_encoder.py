@@ -219,3 +219,27 @@ def test_full_size_configs_by_properties(dirs, tmp_path_factory):
     want = ko.embed(ko.load_model_dir(d), ids[:2], mask[:2])
     assert cosine_rows(big[:2], want).min() >= COS_MIN and np.abs(big[:2] - want).max() <= MAXABS
     enc.close()
+
+
+def test_chained_launch_variants_agree(dirs, monkeypatch):
+    """The chained launches (GEMM+LN -> next projection; optional embedding front end) give the same embeddings as the
+    one-kernel-per-op path: bit-identical for the GEMM chain (same MMA shapes and order), within bf16 noise for the
+    embedding front end (its LayerNorm sums in a different order)."""
+    arch = "minilm-l6"
+    ids, mask, _ = synth.synth_tokens(24, 128, synth.ARCHS[arch][5], regime="P", seed=31)
+    base = api.EncoderModel(dirs[arch])
+    assert N.lib().kjc_encoder_chained(base._h) == 1
+    a = base.encode_batch_from_ids(ids, mask)
+    base.close()
+    monkeypatch.setenv("KJC_NO_CHAIN", "1")
+    plain = api.EncoderModel(dirs[arch])
+    assert N.lib().kjc_encoder_chained(plain._h) == 0
+    b = plain.encode_batch_from_ids(ids, mask)
+    plain.close()
+    monkeypatch.delenv("KJC_NO_CHAIN")
+    assert np.array_equal(a, b)
+    monkeypatch.setenv("KJC_CHAIN_EMBED", "1")
+    emb = api.EncoderModel(dirs[arch])
+    c = emb.encode_batch_from_ids(ids, mask)
+    emb.close()
+    assert cosine_rows(a, c).min() >= 0.99999 and np.abs(a - c).max() < 5e-3
