@@ -607,6 +607,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     fused_ffn_ = fused_ln_ && I % kFfChunk == 0 && getenv("KJC_FUSED_FFN") != nullptr;
     // out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next layer's QKV as one launch each (gemm_ln_gemm.cuh)
     chain_ = fused_ln_ && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
+    chain_embed_ = chain_ && getenv("KJC_CHAIN_EMBED") != nullptr;
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
     lanes_ = 1;  // measured: no gain from concurrent lanes (the kernels are epilogue-issue-bound, not launch-latency-bound)
@@ -690,8 +691,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
     const bool chain = chain_ && !pair_gemm_ && (M + kGemmBlockM - 1) / kGemmBlockM <= sms;
     // the embedding front end of the chained kernel is correct but measured slower than the two launches (its thread-per-token
     // gather is latency-bound: 64 us against 17 + 27 us), so it stays opt-in
-    static const bool chain_embed_env = getenv("KJC_CHAIN_EMBED") != nullptr;
-    const bool chain_embed = chain && chain_embed_env && !layers_.empty();
+    const bool chain_embed = chain && chain_embed_ && !layers_.empty();
     {
         EmbedParams e;
         e.ids = d_ids; e.type_ids = d_types; e.word = word_; e.pos = pos_; e.type = type_; e.gamma = emb_g_; e.beta = emb_b_;

@@ -152,7 +152,7 @@ class Encoder {
     const float *word_ = nullptr, *pos_ = nullptr, *type_ = nullptr, *emb_g_ = nullptr, *emb_b_ = nullptr;
     const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
     std::vector<LayerDev> layers_;
-    bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false;
+    bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false, chain_embed_ = false;
     int lanes_ = 2;
     std::vector<Workspace> ws_;
     cudaEvent_t ev_in_ = nullptr;
