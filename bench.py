@@ -324,9 +324,8 @@ def main():
         tf["gemm_ffn_up"] += tf.pop("gemm_out")
         tf["gemm_ffn_down"] += qkv_l * (L - 1)
         tf["gemm_qkv"] = qkv_l
-        if pn[N.KERNEL_CLASSES.index("embed_ln")] == 0:
-            gb.pop("embed_ln", None)
-        contains = {"gemm_qkv": "embedding gather + embed LN -> QKV projection of layer 0, one launch", "gemm_ffn_up": "out-proj + residual + LN1 -> FFN-up + GELU, one launch per layer",
+        embed_chained = pn[N.KERNEL_CLASSES.index("embed_ln")] == 0
+        contains = {"gemm_qkv": "embedding gather + embed LN -> QKV projection of layer 0, one launch" if embed_chained else "QKV projection of layer 0", "gemm_ffn_up": "out-proj + residual + LN1 -> FFN-up + GELU, one launch per layer",
                     "gemm_ffn_down": "FFN-down + residual + LN2 -> next layer's QKV, one launch per layer (last layer: FFN-down + LN2 only)"}
     kernels = {}
     tot_ms = sum(pms[i] for i in range(8)) / prof_steps

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 3 --batch 296 --index-rows 1000000 --no-cpu"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 264 -c 500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05|gemm_ln384" -s 24 -c 4 -o gpurun_out/prof_gemm -f $CMD > gpurun_out/prof_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05|gemm_ln384|gemm_ln_gemm" -s 18 -c 6 -o gpurun_out/prof_gemm -f $CMD > gpurun_out/prof_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attention -s 6 -c 1 -o gpurun_out/prof_attn -f $CMD > gpurun_out/prof_attn.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"pool_l2|embed_layernorm" -s 4 -c 2 -o gpurun_out/prof_rows -f $CMD > gpurun_out/prof_rows.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"scan_gemm|scan_topk|cand_select|rescore" -c 6 -o gpurun_out/prof_scan -f $CMD > gpurun_out/prof_scan.log 2>&1
