@@ -22,6 +22,7 @@ struct AttnParams {
     float scale_log2e;         // (1/sqrt(d)) * log2(e)
     int nan_if_all_masked;     // 1: no-alloc (-inf) convention, a fully padded sequence yields NaN
     int max_ctas = 0;          // persistent tcgen05 kernel: CTAs to launch (0 = one per SM)
+    unsigned long long* trace = nullptr;  // optional [gridDim.x][64] %globaltimer stamps (KJC_ATTN_TRACE, dbg_attention)
 };
 
 constexpr int kAttnThreads = 256;

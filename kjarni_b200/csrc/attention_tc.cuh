@@ -27,11 +27,14 @@ struct AtcCfg {
     static constexpr int kWarpGroups = D == 32 ? 3 : 2;           // softmax warpgroups = (smem P, TMEM S/O) slots in flight
     static constexpr int kThreads = 128 + kWarpGroups * 128;
     static constexpr int kInStages = D == 32 ? 5 : 3;             // TMA runs this many units ahead of the tensor core
+    // A separate output staging tile per slot (instead of aliasing the P tile) was measured: no change (18.4 us per launch,
+    // scripts/attn_trace.py), so the staging stays aliased and the TMA ring keeps its fifth stage
+    static constexpr bool kSepOut = false;
     static constexpr int kTmemO = kWarpGroups * 128;              // TMEM columns: S[w] at w*128, O[w] at kTmemO + w*D
     static constexpr int kPBytes = kAtcS * kAtcS * 2;             // 32 KB: two K-blocks of [128 rows x 128 B]; the output
                                                                   // staging of the same unit aliases it (P is dead by then)
     static constexpr int kStageOutBytes = 32 * kRowBytes;         // per-warp output staging
-    static constexpr int kSlotBytes = kPBytes + 1024;             // + mask codes / flags
+    static constexpr int kSlotBytes = kPBytes + 1024 + (kSepOut ? 4 * kStageOutBytes : 0);  // + mask codes / flags (+ output staging)
     static constexpr int kSmemBytes = kInStages * kInBytes + kWarpGroups * kSlotBytes + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint32_t kSwizzleLayout = D == 32 ? 4u : 2u;  // UMMA layout type: SWIZZLE_64B / SWIZZLE_128B
     static constexpr uint32_t kSbo = 8 * kRowBytes;                // bytes between 8-row groups
@@ -199,7 +202,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         const int row = quad * 32 + lane;  // query row = TMEM lane
         const int slot = wg;
         uint8_t* sp = slot_base(slot);
-        uint8_t* sout = sp + quad * Cfg::kStageOutBytes;                       // aliases the P tile (dead once o_full fires)
+        uint8_t* sout = Cfg::kSepOut ? sp + Cfg::kPBytes + 1024 + quad * Cfg::kStageOutBytes
+                                     : sp + quad * Cfg::kStageOutBytes;        // D = 64: aliases the P tile (dead once o_full fires)
         float* codes = reinterpret_cast<float*>(sp + Cfg::kPBytes);            // [128] + flags
         int* wvalid = reinterpret_cast<int*>(codes + kAtcS);                   // [4] any key kept, per 32-key chunk
         int* wfull = wvalid + 4;                                               // [4] all 32 keys of the chunk kept
@@ -215,11 +219,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             if (i % NWG != wg) continue;
             const uint32_t par = n & 1;
             ++n;
+            const bool tr = p.trace != nullptr && quad == 0 && lane == 0 && n >= 2 && n <= 4;
+            unsigned long long* tp = tr ? p.trace + blockIdx.x * 64 + wg * 20 + (n - 2) * 6 : nullptr;
+            auto stamp = [&](int k) { if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tp[k] = t; } };
+            stamp(0);
             // the previous unit's TMA stores have left the staging area (it aliases the P tile every thread is about to
             // write) and its readers of codes[] are done
-            if (lane == 0) bulk_wait_read<0>();
-            named_bar_sync(bar_id, 128);
+            if constexpr (!Cfg::kSepOut) {
+                if (lane == 0) bulk_wait_read<0>();
+                named_bar_sync(bar_id, 128);
+            }
             if (b != last_b) {
+                if constexpr (Cfg::kSepOut) named_bar_sync(bar_id, 128);  // every reader of the previous sequence's codes[] is done
                 // mask codes of this sequence: 0 = keep, else the value the score is replaced by
                 last_b = b;
                 const int j = quad * 32 + lane;
@@ -242,6 +253,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             }
 
             mbar_wait(&s_full[slot], par);
+            stamp(1);
             tc_fence_after();
             // pass 1: row max of the scaled + masked scores (next chunk's TMEM load overlaps this chunk's math)
             float mx = -INFINITY;
@@ -274,6 +286,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             tmem_ld_wait();
             tmem_ld_32x32(t_s, va);  // first chunk of pass 2
             max_chunk(vb, 3);
+            stamp(2);
             // pass 2: p = exp2(s - max), row sum, bf16 P into the swizzled K-major smem tile
             float sum = 0.0f;
             const uint32_t prow = smem_u32(sp) + row * 128;
@@ -317,11 +330,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             tc_fence_before();         // S fully read before the MMA warp may overwrite it
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[slot]);
+            stamp(3);
 
             // epilogue: O / rowsum -> bf16 -> swizzled staging -> TMA store
             float inv = 1.0f / sum;
             if (poison) inv = __int_as_float(0x7fc00000);
             mbar_wait(&o_full[slot], par);
+            stamp(4);
             tc_fence_after();
             uint32_t o[D];
             if constexpr (D == 32) {
@@ -334,6 +349,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&o_empty[slot]);
+            if constexpr (Cfg::kSepOut) {  // this warp's previous ctx store (one unit ago) has read its staging tile
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+            }
             const uint32_t obase = smem_u32(sout) + lane * Cfg::kRowBytes;
             const uint32_t sw = D == 32 ? ((lane >> 1) & 3) : (lane & 7);
 #pragma unroll
@@ -350,6 +369,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                 tma_store_3d(&tmap_ctx, sout, h * D, quad * 32, b);  // rows >= S are clipped by the tensor map
                 bulk_commit();
             }
+            stamp(5);
         }
         if (lane == 0) bulk_wait_read<0>();
     }

@@ -1346,6 +1346,43 @@ void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, in
         launch_attention(a, d, nullptr);
         KJ_CUDA(cudaDeviceSynchronize());
         KJ_CUDA(cudaMemcpy(ctx_bf16, dc, T * H * 2, cudaMemcpyDeviceToHost));
+        if (getenv("KJC_ATTN_TRACE")) {  // per-unit milestones of the softmax warpgroups + average launch time
+            cudaDeviceProp prop;
+            int dev = 0;
+            KJ_CUDA(cudaGetDevice(&dev));
+            KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+            unsigned long long* dT;
+            const int ctas = prop.multiProcessorCount;
+            KJ_CUDA(cudaMalloc(&dT, ctas * 64 * 8));
+            KJ_CUDA(cudaMemset(dT, 0, ctas * 64 * 8));
+            for (int i = 0; i < 3; ++i) launch_attention(a, d, nullptr);
+            a.trace = dT;
+            launch_attention(a, d, nullptr);
+            a.trace = nullptr;
+            cudaEvent_t e0, e1;
+            KJ_CUDA(cudaEventCreate(&e0));
+            KJ_CUDA(cudaEventCreate(&e1));
+            KJ_CUDA(cudaEventRecord(e0, nullptr));
+            for (int i = 0; i < 20; ++i) launch_attention(a, d, nullptr);
+            KJ_CUDA(cudaEventRecord(e1, nullptr));
+            KJ_CUDA(cudaDeviceSynchronize());
+            float ms = 0.f;
+            KJ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            std::vector<unsigned long long> h(ctas * 64);
+            KJ_CUDA(cudaMemcpy(h.data(), dT, h.size() * 8, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "attention B=%d S=%d H=%d heads=%d: %.1f us/launch\n", B, S, H, heads, ms * 1e3f / 20);
+            for (int c : {0, ctas / 2}) {
+                for (int wgi = 0; wgi < 3; ++wgi)
+                    for (int u = 0; u < 3; ++u) {
+                        const unsigned long long* t = &h[c * 64 + wgi * 20 + u * 6];
+                        if (!t[0]) continue;
+                        fprintf(stderr, "  cta %3d wg %d unit %d: top=%.2f wait_s=+%.2f pass1=+%.2f pass2=+%.2f wait_o=+%.2f epi=+%.2f (us)\n", c, wgi, u + 1,
+                                (t[0] - h[c * 64]) * 1e-3, (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3);
+                    }
+            }
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+            cudaFree(dT);
+        }
         cudaFree(dq); cudaFree(dc);
         if (dm) cudaFree(dm);
 }
