@@ -689,8 +689,8 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
     const float eps = info_.layer_norm_eps;
     // chained launches need one 128-row tile per CTA
     const bool chain = chain_ && !pair_gemm_ && (M + kGemmBlockM - 1) / kGemmBlockM <= sms;
-    // the embedding front end of the chained kernel is correct but measured slower than the two launches (its thread-per-token
-    // gather is latency-bound: 64 us against 17 + 27 us), so it stays opt-in
+    // the embedding front end of the chained kernel is bit-identical but measured slower than the two launches (12 gathering warps
+    // per SM are latency-bound: 50 us against 17 + 27 us), so it stays opt-in (KJC_CHAIN_EMBED)
     const bool chain_embed = chain && chain_embed_ && !layers_.empty();
     {
         EmbedParams e;

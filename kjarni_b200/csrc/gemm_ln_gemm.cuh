@@ -228,7 +228,90 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int trow = quad * 32 + lane;    // row inside the tile
         const int row0 = tile * kGemmBlockM + quad * 32;
         uint32_t rphase = 0;
-        {
+        if constexpr (P1 == 1) {
+            // ===== phase 1 (embedding front end): one warp per token, lanes across the 384 columns (coalesced 1536-byte rows, three
+            // tokens in flight per warp), the arithmetic of embed_layernorm_kernel / warp_layernorm_store (rowwise.cuh) bit for bit,
+            // rows written straight into the swizzled x' operand tile
+            const bool has_type = p.type != nullptr && p.type_vocab > 0;
+            constexpr int kU = 3;
+            for (int r0 = ew; r0 < kGemmBlockM; r0 += kLnEpiWarps * kU) {
+                float4 v[kU][3];
+                bool live[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int r = r0 + u * kLnEpiWarps;
+                    const int row = tile * kGemmBlockM + r;
+                    live[u] = r < kGemmBlockM && row < p.M;
+                    uint32_t id = 0, tt = 0;
+                    bool has_word = false, has_pos = false;
+                    int pidx = 0;
+                    if (live[u]) {
+                        id = __ldg(p.ids + row);
+                        has_word = id < static_cast<uint32_t>(p.vocab);   // ids >= vocab contribute a zero row (embeddings/mod.rs:227-246)
+                        pidx = p.pos_offset + row % p.S;
+                        has_pos = p.pos != nullptr && pidx < p.max_pos;   // positions beyond the table add nothing (:199-214)
+                        if (has_type && p.type_ids != nullptr) {
+                            tt = __ldg(p.type_ids + row);
+                            if (tt >= static_cast<uint32_t>(p.type_vocab)) {  // the reference panics (:312-317)
+                                if (lane == 0) *p.err_flag = 1;
+                                tt = 0;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int c = (lane + 32 * i) * 4;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live[u]) {
+                            if (has_word) a = __ldg(reinterpret_cast<const float4*>(p.word + static_cast<size_t>(id) * kLnN + c));
+                            if (has_pos) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(pidx) * kLnN + c));
+                                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                            }
+                            if (has_type) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(p.type + static_cast<size_t>(tt) * kLnN + c));
+                                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                            }
+                        }
+                        v[u][i] = a;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int r = r0 + u * kLnEpiWarps;
+                    if (r >= kGemmBlockM) continue;  // warp-uniform
+                    float sm = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) sm += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+                    const float mean = warp_sum(sm) / static_cast<float>(kLnN);
+                    float q = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const float a = v[u][i].x - mean, b = v[u][i].y - mean, c = v[u][i].z - mean, d = v[u][i].w - mean;
+                        q += (a * a + b * b) + (c * c + d * d);
+                    }
+                    const float inv_std = 1.0f / sqrtf(warp_sum(q) / static_cast<float>(kLnN) + p.eps);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int c = (lane + 32 * i) * 4;
+                        const float4 g = *reinterpret_cast<const float4*>(s_gamma + c);
+                        const float4 bt = *reinterpret_cast<const float4*>(s_beta + c);
+                        float y0 = (v[u][i].x - mean) * inv_std * g.x + bt.x;
+                        float y1 = (v[u][i].y - mean) * inv_std * g.y + bt.y;
+                        float y2 = (v[u][i].z - mean) * inv_std * g.z + bt.z;
+                        float y3 = (v[u][i].w - mean) * inv_std * g.w + bt.w;
+                        if (!live[u]) y0 = y1 = y2 = y3 = 0.0f;  // rows beyond M: a defined (zero) operand row
+                        // x' tile: k-block c / 64, row r (128 B), 16-byte chunk ((c % 64) / 8) ^ (r & 7), 8 bytes at (c % 8) * 2
+                        const uint32_t addr = smem_u32(smem_x) + (c >> 6) * kLnABytes + r * 128 + (((static_cast<uint32_t>(c & 63) >> 3) ^ static_cast<uint32_t>(r & 7)) << 4) +
+                                              static_cast<uint32_t>(c & 7) * 2;
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(pack_bf16(y0, y1)), "r"(pack_bf16(y2, y3)) : "memory");
+                    }
+                }
+            }
+            fence_proxy_async_smem();  // x' (generic-proxy stores) -> visible to the tensor core and to the TMA store below
+            __syncwarp();
+            if (lane == 0) mbar_arrive(x_ready);
+        } else {
             // ===== phase 1: bias + residual + LayerNorm, output into the resident x' tile
             const int col_base = part * kLnPartCols;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
@@ -280,52 +363,6 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         mbar_arrive_expect_tx(&rbar[b], kEpiStageBytes);
                         tma_load_2d(ebuf + b * kEpiStageBytes, &tmap_res, &rbar[b], col_base + (c + 2) * kEpiChunkCols, row0, kEvictFirst);
                     }
-                }
-            } else {
-                // embedding gather: this thread's token, columns [col_base, col_base + 128)
-                const int row = tile * kGemmBlockM + trow;
-                const bool live = row < p.M;
-                uint32_t id = 0, tt = 0;
-                bool has_word = false, has_pos = false;
-                int pidx = 0;
-                const bool has_type = p.type != nullptr && p.type_vocab > 0;
-                if (live) {
-                    id = __ldg(p.ids + row);
-                    has_word = id < static_cast<uint32_t>(p.vocab);       // ids >= vocab contribute a zero row (embeddings/mod.rs:227-246)
-                    pidx = p.pos_offset + row % p.S;
-                    has_pos = p.pos != nullptr && pidx < p.max_pos;       // positions beyond the table add nothing (:199-214)
-                    if (has_type && p.type_ids != nullptr) {
-                        tt = __ldg(p.type_ids + row);
-                        if (tt >= static_cast<uint32_t>(p.type_vocab)) {  // the reference panics (:312-317)
-                            *p.err_flag = 1;
-                            tt = 0;
-                        }
-                    }
-                }
-                const float4* wrow = reinterpret_cast<const float4*>(p.word + static_cast<size_t>(has_word ? id : 0) * kLnN + col_base);
-                const float4* prow = reinterpret_cast<const float4*>((has_pos ? p.pos : p.word) + static_cast<size_t>(has_pos ? pidx : 0) * kLnN + col_base);
-                const float4* trw = reinterpret_cast<const float4*>((has_type ? p.type : p.word) + static_cast<size_t>(tt) * kLnN + col_base);
-                const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                for (int c = 0; c < kChunks; ++c) {
-                    uint32_t v[32];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 a = (live && has_word) ? __ldg(wrow + c * 8 + j) : z4;
-                        const float4 b = (live && has_pos) ? __ldg(prow + c * 8 + j) : z4;
-                        const float4 t = (live && has_type) ? __ldg(trw + c * 8 + j) : z4;
-                        const float e0 = (a.x + b.x) + t.x, e1 = (a.y + b.y) + t.y, e2 = (a.z + b.z) + t.z, e3 = (a.w + b.w) + t.w;
-                        s1 += (e0 + e1) + (e2 + e3);
-                        s2 = fmaf(e0, e0, s2);
-                        s2 = fmaf(e1, e1, s2);
-                        s2 = fmaf(e2, e2, s2);
-                        s2 = fmaf(e3, e3, s2);
-                        v[4 * j + 0] = __float_as_uint(e0);
-                        v[4 * j + 1] = __float_as_uint(e1);
-                        v[4 * j + 2] = __float_as_uint(e2);
-                        v[4 * j + 3] = __float_as_uint(e3);
-                    }
-                    tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
                 }
             }
             tmem_st_wait();
