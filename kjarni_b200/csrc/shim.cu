@@ -71,11 +71,6 @@ std::string default_cache_dir() {
     return std::string(home ? home : ".") + "/.cache/kjarni";
 }
 
-const char* cstr_or_null(const char* p, bool& bad_utf8) {
-    if (p && !uni::valid_utf8(p)) bad_utf8 = true;
-    return p;
-}
-
 // Resolves the model directory the way the builders do; throws Fail{ModelNotFound} when it is not on disk (no download here).
 std::string resolve_model_dir(const char* cache_dir, const char* model_name, const char* model_path, const char* default_name) {
     if (model_path && *model_path) {
