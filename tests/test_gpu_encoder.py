@@ -243,3 +243,28 @@ def test_chained_launch_variants_agree(dirs, monkeypatch):
     c = emb.encode_batch_from_ids(ids, mask)
     emb.close()
     assert np.array_equal(a, c)  # the front end restates the embed kernel's arithmetic bit for bit
+
+
+def test_host_call_chunking_is_invisible(dirs):
+    """kjc_encoder_forward stages large batches through pinned memory in chunks of four micro-batches overlapped with the GPU
+    work; the rows must equal those of small calls bit for bit, in order, including the last partial chunk."""
+    arch = "tiny-bert"
+    enc = api.EncoderModel(dirs[arch])
+    chunk = 4 * enc.micro_batch(16)
+    B = 2 * chunk + 37  # two full chunks + a tail
+    ids, mask, _ = synth.synth_tokens(B, 16, synth.ARCHS[arch][5], regime="P", seed=77)
+    big = enc.encode_batch_from_ids(ids, mask)
+    assert big.shape == (B, 64) and np.isfinite(big).all()
+    for b0 in (0, chunk - 3, chunk, 2 * chunk - 1, 2 * chunk + 30):
+        n = min(7, B - b0)
+        assert np.array_equal(big[b0:b0 + n], enc.encode_batch_from_ids(ids[b0:b0 + n], mask[b0:b0 + n])), b0
+    lg_dir = dirs["tiny-distilbert"]
+    cls = api.EncoderModel(lg_dir)
+    ids2, mask2, _ = synth.synth_tokens(B, 16, synth.ARCHS["tiny-distilbert"][5], regime="P", seed=78)
+    lg = cls.predict_logits(ids2, mask2)
+    assert np.array_equal(lg[chunk - 2:chunk + 2], cls.predict_logits(ids2[chunk - 2:chunk + 2], mask2[chunk - 2:chunk + 2]))
+    m = ko.load_model_dir(dirs[arch])
+    want = ko.embed(m, ids[-5:], mask[-5:])
+    assert cosine_rows(big[-5:], want).min() >= COS_MIN
+    enc.close()
+    cls.close()
