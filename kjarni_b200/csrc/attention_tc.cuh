@@ -24,34 +24,18 @@ struct AtcCfg {
     static constexpr int kRowBytes = D * 2;                       // 64 or 128: one swizzle atom wide
     static constexpr int kTileBytes = kAtcS * kRowBytes;          // Q / K / V head slice
     static constexpr int kInBytes = 3 * kTileBytes;               // one input stage (Q, K, V of a unit)
-#ifndef KJ_ATTN_WG32
-#define KJ_ATTN_WG32 3
-#endif
-    // D = 32 can also run four slots (-DKJ_ATTN_WG32=4): O (32 columns) then accumulates in the first columns of its slot's S
-    // region (S is dead once P is published), so a slot costs 128 TMEM columns and four fit.  Measured slower (21.3 vs 18.4 us per
-    // launch): every warpgroup's softmax stretches in proportion, i.e. the SM's softmax throughput, not the slot count, is the limit
-    static constexpr int kWarpGroups = D == 32 ? KJ_ATTN_WG32 : 2; // softmax warpgroups = (smem P, TMEM S/O) slots in flight
-    static constexpr bool kOinS = kWarpGroups == 4;
+    static constexpr int kWarpGroups = D == 32 ? 3 : 2;           // softmax warpgroups = (smem P, TMEM S/O) slots in flight
     static constexpr int kThreads = 128 + kWarpGroups * 128;
-    static constexpr int kInStages = D == 32 ? (kOinS ? 4 : 5) : 3;  // TMA runs this many units ahead of the tensor core
+    static constexpr int kInStages = D == 32 ? 5 : 3;             // TMA runs this many units ahead of the tensor core
     // A separate output staging tile per slot (instead of aliasing the P tile) was measured: no change (18.4 us per launch,
     // scripts/attn_trace.py), so the staging stays aliased and the TMA ring keeps its fifth stage
     static constexpr bool kSepOut = false;
-    static constexpr int kTmemO = kOinS ? 0 : kWarpGroups * 128;  // TMEM columns: S[w] at w*128, O[w] at kTmemO + w*kOStride
-    static constexpr int kOStride = kOinS ? 128 : D;
+    static constexpr int kTmemO = kWarpGroups * 128;              // TMEM columns: S[w] at w*128, O[w] at kTmemO + w*D
     static constexpr int kPBytes = kAtcS * kAtcS * 2;             // 32 KB: two K-blocks of [128 rows x 128 B]; the output
                                                                   // staging of the same unit aliases it (P is dead by then)
     static constexpr int kStageOutBytes = 32 * kRowBytes;         // per-warp output staging
     static constexpr int kSlotBytes = kPBytes + 1024 + (kSepOut ? 4 * kStageOutBytes : 0);  // + mask codes / flags (+ output staging)
-    // slot s: P tile at kSlotStride * s (1024-byte aligned: swizzle atoms), mask codes / flags at codes_off(s).  The four-slot layout
-    // packs the four P tiles back to back and the code blocks (640 B each) behind them: 4 x 24 KB inputs + 4 x 32 KB P + codes +
-    // barriers = 232,320 B, which only fits without alignment slack
-    static constexpr int kSlotStride = kOinS ? kPBytes : kSlotBytes;
-    static constexpr int kCodesBytes = 640;
-    __host__ __device__ static constexpr int codes_off(int s) { return kOinS ? kWarpGroups * kPBytes + s * kCodesBytes : s * kSlotBytes + kPBytes; }
-    static constexpr int kBarsOff = kOinS ? kWarpGroups * (kPBytes + kCodesBytes) : kWarpGroups * kSlotBytes;
-    static constexpr int kSmemBytes = kInStages * kInBytes + kBarsOff + (kOinS ? 0 : 1024) /*align*/ + 384 /*barriers*/;
-    static_assert(kSmemBytes <= 232448, "shared memory budget");
+    static constexpr int kSmemBytes = kInStages * kInBytes + kWarpGroups * kSlotBytes + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr uint32_t kSwizzleLayout = D == 32 ? 4u : 2u;  // UMMA layout type: SWIZZLE_64B / SWIZZLE_128B
     static constexpr uint32_t kSbo = 8 * kRowBytes;                // bytes between 8-row groups
 };
@@ -86,14 +70,13 @@ template <int D>
 __global__ void __launch_bounds__(AtcCfg<D>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_ctx, AttnParams p) {
     using Cfg = AtcCfg<D>;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    if (Cfg::kOinS && smem != smem_raw) __trap();  // the four-slot layout has no slack for a misaligned base
     constexpr int NIN = Cfg::kInStages;
     constexpr int NWG = Cfg::kWarpGroups;
     uint8_t* smem_in = smem;
     uint8_t* smem_slots = smem + NIN * Cfg::kInBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slots + Cfg::kBarsOff);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slots + NWG * Cfg::kSlotBytes);
     uint64_t* in_full = bars;                     // [NIN] TMA -> MMA
     uint64_t* in_empty = bars + NIN;              // [NIN] MMA (PV done) -> TMA
     uint64_t* s_full = bars + 2 * NIN;            // [NWG] MMA (QK done) -> warpgroup
@@ -144,7 +127,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here on
     pdl_launch_dependents();  // the next kernel may begin its own prologue as soon as this CTA's resources are released
 
-    auto slot_base = [&](int slot) { return smem_slots + slot * Cfg::kSlotStride; };  // P tile (+ aliased output staging)
+    auto slot_base = [&](int slot) { return smem_slots + slot * Cfg::kSlotBytes; };  // P tile (+ aliased output staging), codes
     auto in_base = [&](int stage) { return smem_in + stage * Cfg::kInBytes; };      // Q | K | V
 
     if (warp == 0) {
@@ -176,11 +159,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             // published its P, i.e. PV of that unit was already issued), PV of unit v as soon as its P is published.
             int qk_next = 0, pv_next = 0;
             while (pv_next < n_mine) {
-                // slot free for a new S: three-slot layout -- P of the previous occupant published (its PV was issued); O-in-S layout --
-                // the previous occupant's O has also been read out of these columns
-                bool slot_free = qk_next < pv_next + NWG;
-                if (Cfg::kOinS && slot_free && qk_next >= NWG) slot_free = mbar_try_wait(&o_empty[qk_next % NWG], ((qk_next / NWG) - 1) & 1);
-                if (qk_next < n_mine && slot_free && mbar_try_wait(&in_full[qk_next % NIN], (qk_next / NIN) & 1)) {
+                if (qk_next < n_mine && qk_next < pv_next + NWG && mbar_try_wait(&in_full[qk_next % NIN], (qk_next / NIN) & 1)) {
                     const int slot = qk_next % NWG, stage = qk_next % NIN;
                     tc_fence_after();
                     uint8_t* sb = in_base(stage);
@@ -194,7 +173,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                 if (pv_next < qk_next) {
                     const int j = pv_next, slot = j % NWG;
                     const uint32_t par = (j / NWG) & 1;
-                    if (mbar_try_wait(&p_full[slot], par) && (Cfg::kOinS || mbar_try_wait(&o_empty[slot], par ^ 1))) {
+                    if (mbar_try_wait(&p_full[slot], par) && mbar_try_wait(&o_empty[slot], par ^ 1)) {
                         tc_fence_after();
                         const int stage = j % NIN;
                         const uint64_t dv = umma_desc_atom(smem_u32(in_base(stage) + 2 * Cfg::kTileBytes), Cfg::kSbo, Cfg::kSwizzleLayout);
@@ -205,7 +184,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 // V advances 16 keys = 16 rows per k-step
-                                umma_f16(tmem_base + Cfg::kTmemO + slot * Cfg::kOStride, dp + 2 * k, dv + ((kb * 4 + k) * 16 * Cfg::kRowBytes >> 4),
+                                umma_f16(tmem_base + Cfg::kTmemO + slot * D, dp + 2 * k, dv + ((kb * 4 + k) * 16 * Cfg::kRowBytes >> 4),
                                          idesc_pv, (kb | k) != 0);
                             }
                         }
@@ -225,12 +204,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         uint8_t* sp = slot_base(slot);
         uint8_t* sout = Cfg::kSepOut ? sp + Cfg::kPBytes + 1024 + quad * Cfg::kStageOutBytes
                                      : sp + quad * Cfg::kStageOutBytes;        // D = 64: aliases the P tile (dead once o_full fires)
-        float* codes = reinterpret_cast<float*>(smem_slots + Cfg::codes_off(slot));  // [128] + flags
+        float* codes = reinterpret_cast<float*>(sp + Cfg::kPBytes);            // [128] + flags
         int* wvalid = reinterpret_cast<int*>(codes + kAtcS);                   // [4] any key kept, per 32-key chunk
         int* wfull = wvalid + 4;                                               // [4] all 32 keys of the chunk kept
         constexpr float kMaskedLog2 = -1.0e9f * 1.4426950408889634f;
         const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * 128;
-        const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + Cfg::kTmemO + slot * Cfg::kOStride;
+        const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + Cfg::kTmemO + slot * D;
         const int bar_id = 1 + wg;
 
         int n = 0, last_b = -1, b = 0, h = 0;
