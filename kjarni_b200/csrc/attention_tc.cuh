@@ -19,6 +19,12 @@ namespace kj {
 // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4.. softmax+epilogue warpgroups (AtcCfg<D>::kThreads in total)
 constexpr int kAtcS = 128;        // padded sequence tile
 
+// Milestone stamps of the softmax warpgroups (scripts/attn_trace.py) are compiled in only with
+// `make EXTRA=-DKJ_ATTN_TRACE_BUILD=1`: even untaken, their per-unit checks cost ~0.3 us per launch.
+#ifndef KJ_ATTN_TRACE_BUILD
+#define KJ_ATTN_TRACE_BUILD 0
+#endif
+
 template <int D>
 struct AtcCfg {
     static constexpr int kRowBytes = D * 2;                       // 64 or 128: one swizzle atom wide
@@ -219,7 +225,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             if (i % NWG != wg) continue;
             const uint32_t par = n & 1;
             ++n;
-            const bool tr = p.trace != nullptr && quad == 0 && lane == 0 && n >= 2 && n <= 4;
+            const bool tr = KJ_ATTN_TRACE_BUILD && p.trace != nullptr && quad == 0 && lane == 0 && n >= 2 && n <= 4;
             unsigned long long* tp = tr ? p.trace + blockIdx.x * 64 + wg * 20 + (n - 2) * 6 : nullptr;
             auto stamp = [&](int k) { if (tr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tp[k] = t; } };
             stamp(0);

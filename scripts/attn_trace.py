@@ -1,4 +1,6 @@
-"""Milestone trace of the tcgen05 attention kernel (KJC_ATTN_TRACE through kjc_dbg_attention): where a softmax warpgroup's time goes."""
+"""Milestone trace of the tcgen05 attention kernel (KJC_ATTN_TRACE through kjc_dbg_attention): where a softmax warpgroup's time goes.
+The per-unit stamps need a library built with `make -C kjarni_b200/csrc clean all EXTRA=-DKJ_ATTN_TRACE_BUILD=1`; without it only the
+average launch time is printed."""
 import os, sys
 sys.path.insert(0, ".")
 os.environ["KJC_ATTN_TRACE"] = "1"
