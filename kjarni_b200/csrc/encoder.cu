@@ -809,9 +809,12 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         ++launches_;
     } else if (o.output == KJC_OUT_POOLED) {
         if (o.pooling == KJC_POOL_MEAN && H <= 1024 && H % 4 == 0) {
-            const size_t smem = static_cast<size_t>(8) * H * sizeof(float);
+            const size_t smem = static_cast<size_t>(kPoolWarps) * H * sizeof(float);  // <= 64 KB at H = 1024
             dispatch_nv(H, [&](auto nv) {
-                mean_pool_l2_kernel<decltype(nv)::value><<<nb, 256, smem, st>>>(w.x16, d_mask, d_out, S, H, o.normalize);
+                static int configured[64] = {0};  // one per instantiation (the lambda is instantiated per NV)
+                auto kern = mean_pool_l2_kernel<decltype(nv)::value>;
+                if (smem > 40 * 1024) ensure_smem_attr(kern, static_cast<int>(smem), configured);  // static + dynamic beyond the 48 KB default
+                kern<<<nb, kPoolThreads, smem, st>>>(w.x16, d_mask, d_out, S, H, o.normalize);
             });
         } else {
             pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(w.x16, d_mask, d_out, S, H, o.pooling, o.normalize);
@@ -977,7 +980,7 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
         KJ_CUDA(cudaMallocHost(&h_stage_out_, out_elems * 4));
         out_cap_ = out_elems;
     }
-    // Stage through pinned memory so the copies are true async DMA transfers, in chunks of a few micro-batches: the host-side
+    // Stage through pinned memory so the copies are true async DMA transfers, in chunks of two micro-batches: the host-side
     // copy of chunk c+1 into the staging buffer and of chunk c-1 out of it run while the GPU works on chunk c, so only the
     // first stage-in and the last stage-out are exposed (they were ~6 % of a 4144-sequence call when done up front).
     uint32_t* hs = h_stage_in_;
@@ -986,7 +989,7 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
     const uint32_t* d_types = types ? d_in_ + 2 * T : nullptr;
     KjcForwardOptions oc = o;  // the padding convention is decided once for the whole call, not per chunk
     oc.mask_convention = resolve_noalloc(B, S, o) ? KJC_MASK_NOALLOC : KJC_MASK_ALLOC;
-    const int chunk = std::max(1, 4 * micro_batch(S));
+    const int chunk = std::max(1, 2 * micro_batch(S));
     if (!ev_chunk_[0]) {
         KJ_CUDA(cudaEventCreateWithFlags(&ev_chunk_[0], cudaEventDisableTiming));
         KJ_CUDA(cudaEventCreateWithFlags(&ev_chunk_[1], cudaEventDisableTiming));

@@ -227,13 +227,16 @@ pool_l2_kernel(const TIn* __restrict__ x, const float* __restrict__ mask, float*
 // cpu/encoder/traits.rs:529-536), with the rows of a sequence spread over the 8 warps: warp w sums rows w, w+8, ...
 // with coalesced 8-byte-per-lane loads (many independent loads in flight), partial sums meet in shared memory.
 // One CTA per sequence; H <= 1024 and a multiple of 4.  Same arithmetic as pool_l2_kernel up to summation order.
+// 16 warps per sequence: at S = 128 every warp issues its 8 rows in two trips of four, so a CTA is two memory round trips long
+constexpr int kPoolWarps = 16;
+constexpr int kPoolThreads = kPoolWarps * 32;
 template <int NCH>  // float4 column chunks per lane: ceil(H / 128)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kPoolThreads)
 mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int S, int H,
                     int normalize) {
-    extern __shared__ float s_part[];  // [8][H]
-    __shared__ float s_cnt[8];
-    __shared__ float red[8];
+    extern __shared__ float s_part[];  // [kPoolWarps][H]
+    __shared__ float s_cnt[kPoolWarps];
+    __shared__ float red[kPoolWarps];
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const __nv_bfloat16* xb = x + static_cast<size_t>(b) * S * H;
     const float* mb = mask ? mask + static_cast<size_t>(b) * S : nullptr;
@@ -245,12 +248,12 @@ mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
     // so memory-level parallelism is what sets its time.  Rows are loaded unconditionally (they exist even when masked) but
     // only accumulated when the mask is non-zero: a masked row may hold NaN (no-alloc convention) and NaN * 0 is NaN.
     constexpr int kU = 4;
-    for (int s0 = warp; s0 < S; s0 += 8 * kU) {
+    for (int s0 = warp; s0 < S; s0 += kPoolWarps * kU) {
         float m[kU];
         float4 t[kU][NCH];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const int sr = s0 + 8 * u;
+            const int sr = s0 + kPoolWarps * u;
             m[u] = sr < S ? (mb ? mb[sr] : 1.0f) : 0.0f;
 #pragma unroll
             for (int i = 0; i < NCH; ++i) {
@@ -278,7 +281,7 @@ mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
     __syncthreads();
     float count = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) count += s_cnt[w];
+    for (int w = 0; w < kPoolWarps; ++w) count += s_cnt[w];
     // thread t owns columns 4t .. 4t+3
     const int c = threadIdx.x * 4;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,7 +291,7 @@ mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
             a = load4f(xb + c);  // no valid token: the token-0 row (pooling/mod.rs:24-31)
         } else {
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < kPoolWarps; ++w) {
                 const float4 t = *reinterpret_cast<const float4*>(s_part + w * H + c);
                 a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
             }
@@ -303,7 +306,7 @@ mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
         __syncthreads();
         float tot = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) tot += red[i];
+        for (int i = 0; i < kPoolWarps; ++i) tot += red[i];
         const float nrm = sqrtf(tot);
         if (nrm > 0.0f) scale = 1.0f / nrm;
     }

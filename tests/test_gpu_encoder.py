@@ -246,11 +246,11 @@ def test_chained_launch_variants_agree(dirs, monkeypatch):
 
 
 def test_host_call_chunking_is_invisible(dirs):
-    """kjc_encoder_forward stages large batches through pinned memory in chunks of four micro-batches overlapped with the GPU
+    """kjc_encoder_forward stages large batches through pinned memory in chunks of two micro-batches overlapped with the GPU
     work; the rows must equal those of small calls bit for bit, in order, including the last partial chunk."""
     arch = "tiny-bert"
     enc = api.EncoderModel(dirs[arch])
-    chunk = 4 * enc.micro_batch(16)
+    chunk = 2 * enc.micro_batch(16)
     B = 2 * chunk + 37  # two full chunks + a tail
     ids, mask, _ = synth.synth_tokens(B, 16, synth.ARCHS[arch][5], regime="P", seed=77)
     big = enc.encode_batch_from_ids(ids, mask)
