@@ -706,7 +706,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
             prof_end(st);
         } else {
             prof_begin(KJC_K_EMBED_LN, st);
-            dispatch_nv(H, [&](auto nv) { embed_layernorm_kernel<decltype(nv)::value><<<grid, kRowThreads, 0, st>>>(e); });
+            dispatch_nv(H, [&](auto nv) { launch_pdl(embed_layernorm_kernel<decltype(nv)::value>, dim3(grid), dim3(kRowThreads), 0, st, e); });
             KJ_CUDA(cudaGetLastError());
             prof_end(st);
         }
@@ -814,7 +814,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
                 static int configured[64] = {0};  // one per instantiation (the lambda is instantiated per NV)
                 auto kern = mean_pool_l2_kernel<decltype(nv)::value>;
                 if (smem > 40 * 1024) ensure_smem_attr(kern, static_cast<int>(smem), configured);  // static + dynamic beyond the 48 KB default
-                kern<<<nb, kPoolThreads, smem, st>>>(w.x16, d_mask, d_out, S, H, o.normalize);
+                launch_pdl(kern, dim3(nb), dim3(kPoolThreads), smem, st, static_cast<const __nv_bfloat16*>(w.x16), d_mask, d_out, S, H, static_cast<int>(o.normalize));
             });
         } else {
             pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(w.x16, d_mask, d_out, S, H, o.pooling, o.normalize);

@@ -78,6 +78,8 @@ struct EmbedParams {
 // + pos[offset + s] (skipped beyond the table) + type[tt] (row 0 if no type ids).
 template <int NV>
 __global__ void __launch_bounds__(kRowThreads) embed_layernorm_kernel(EmbedParams p) {
+    pdl_wait();               // launched with programmatic stream serialization: x16 may still be read by the previous micro-batch
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (kRowThreads / 32) + warp;
     if (row >= p.M) return;
@@ -234,6 +236,8 @@ template <int NCH>  // float4 column chunks per lane: ceil(H / 128)
 __global__ void __launch_bounds__(kPoolThreads)
 mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int S, int H,
                     int normalize) {
+    pdl_wait();  // launched with programmatic stream serialization
+    pdl_launch_dependents();
     extern __shared__ float s_part[];  // [kPoolWarps][H]
     __shared__ float s_cnt[kPoolWarps];
     __shared__ float red[kPoolWarps];
