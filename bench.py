@@ -94,6 +94,23 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _host_threads():
+    """Threads the CPU arm uses: every physical core, as kjarni_init sizes the reference's rayon pool
+    (kjarni-ffi/src/lib.rs:36-40).  torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the port to one thread."""
+    try:
+        import psutil
+
+        n = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        n = 0
+    n = n or (os.cpu_count() or 1)
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def _cpu_model(model_dir):
     """The CPU port of the reference path: the C restatement (oracle/kjarni_oracle.c, AVX2 + OpenMP, structured like the
     reference's own kernels) when its library was built, else the numpy restatement.  Returns (embed_fn, cores, what)."""
@@ -104,6 +121,7 @@ def _cpu_model(model_dir):
         from oracle import kjarni_oracle_c as koc
 
         cm = koc.CModel(m)
+        koc.set_num_threads(_host_threads())
         return (lambda ids, mask: cm.embed(ids, mask.astype(np.float32))), koc.num_threads(), \
             "C restatement of the reference CPU kernels (oracle/kjarni_oracle.c: 64-token blocks x 4x3 AVX2/FMA micro-kernel, OpenMP)"
     except (ImportError, OSError):
@@ -133,6 +151,7 @@ def cpu_scan_rate(dim, k, rows, nq):
     from oracle import kjarni_oracle as ko
     from oracle import kjarni_oracle_c as koc
 
+    koc.set_num_threads(_host_threads())
     r = ko.synth_rows(7, 0, rows, dim)
     q = ko.synth_rows(11, 0, nq, dim)
     koc.scan_topk(r[:1000], q, k)
@@ -214,6 +233,7 @@ def main():
     ap.add_argument("--index-rows", type=int, default=6_250_000, help="index shard rows per GPU (BASELINE config 4: 50M/8)")
     ap.add_argument("--no-index", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C1-latency / C2 / C3 / C5 lines")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -380,6 +400,15 @@ def main():
             except Exception as ex:
                 index["cpu_baseline"] = {"error": str(ex)}
 
+    extra = {}
+    if not args.no_extra:
+        for name in EXTRA_CONFIGS:
+            try:
+                extra[name] = bench_extra(name, args, rank, world, local_rank, lib, N, api, torch, barrier, max_over_ranks, peaks,
+                                          with_cpu=(rank == 0 and world == 1 and not args.no_cpu))
+            except Exception as ex:
+                extra[name] = {"error": str(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -392,12 +421,138 @@ def main():
             "e2e": {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": int(ids_np.nbytes + maskf_np.nbytes),
                     "d2h_bytes_per_step": int(out_h.nbytes), "steps": e2e_steps, "timing": "wall clock around synchronous C-ABI calls, max over ranks"},
             "gpu_launches": int(launches_per_step * args.steps),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "index_topk": index,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "index_topk": index, "configs": extra,
         }
         emit(line)
     enc.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# BASELINE.json configs beyond the headline ("plus classifier seq/s (C2), rerank pairs/s (C3), BERT-base seq/s (C5)"),
+# and the reference's own batch-32 case as a latency line.  name -> (arch, batch per GPU per step, seq, output, pair inputs, unit, what)
+EXTRA_CONFIGS = {
+    "c1_batch32_latency": ("minilm-l6", 32, 128, "pooled", False, "embeddings/s",
+                           "configs[0]: all-MiniLM-L6-v2 architecture, ONE batch of 32 x 128 per call (latency case)"),
+    "c2_classify": ("distilbert-sst2", 256, 128, "logits", False, "sequences/s",
+                    "configs[1]: DistilBERT (distilbert-sentiment architecture) sequence classification, batch 256 x seq 128 per GPU"),
+    "c3_rerank": ("minilm-l6-cross-encoder", 1000, 256, "logits", True, "pairs/s",
+                  "configs[2]: MiniLM-L6 cross-encoder, 64 queries x 1000 candidate passages, seq 256; one step = one query's 1000 pairs"),
+    "c5_bertbase": ("bert-base", 512, 512, "pooled", False, "sequences/s",
+                    "configs[4]: BERT-base-size (768-dim, 12-layer) embedding, batch 512 x seq 512 per GPU"),
+}
+
+
+def _model_dir(arch, rank):
+    from kjarni_b200 import synth
+
+    d = os.path.join(tempfile.gettempdir(), f"kjarni_b200_bench_{os.getuid()}_{rank}", arch)
+    if not os.path.exists(os.path.join(d, "model.safetensors")):
+        synth.write_model_dir(d, arch)
+    return d
+
+
+def cpu_port_rate(model_dir, S, pair, seconds, nseq):
+    """The reference CPU forward (encoder hidden states; the head is O(H^2) per sequence) restated in C, on a bounded sample."""
+    from kjarni_b200 import synth
+    from oracle import kjarni_oracle as ko
+    from oracle import kjarni_oracle_c as koc
+
+    m = ko.load_model_dir(model_dir)
+    cm = koc.CModel(m)
+    koc.set_num_threads(_host_threads())
+    ids, mask, types = synth.synth_tokens(nseq, S, m.word.shape[0], regime="T", seed=42, pair=pair)
+    maskf = mask.astype(np.float32)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        cm.hidden_states(ids, maskf, types, noalloc=False)
+        n += nseq
+        dt = time.perf_counter() - t0
+        if dt > seconds:
+            break
+    return n / dt, dt, n, koc.num_threads()
+
+
+def bench_extra(name, args, rank, world, local_rank, lib, N, api, torch, barrier, max_over_ranks, peaks, with_cpu):
+    from kjarni_b200 import synth
+
+    arch, B, S, out, pair, unit, what = EXTRA_CONFIGS[name]
+    enc = api.EncoderModel(_model_dir(arch, rank), device=local_rank)
+    info = enc.info
+    H, L, I = info.hidden_size, info.num_layers, info.intermediate_size
+    ids_np, mask_np, types_np = synth.synth_tokens(B, S, info.vocab_size, regime="T", seed=4242 + rank, pair=pair)
+    maskf_np = mask_np.astype(np.float32)
+    ids_d = torch.from_numpy(ids_np.view(np.int32)).cuda()
+    mask_d = torch.from_numpy(maskf_np).cuda()
+    types_d = torch.from_numpy(types_np.view(np.int32)).cuda() if pair else None
+    cols = H if out == "pooled" else info.num_labels
+    out_d = torch.empty((B, cols), dtype=torch.float32, device="cuda")
+    out_h = np.empty((B, cols), np.float32)
+    opts = N.KjcForwardOptions(N.OUT_POOLED if out == "pooled" else N.OUT_LOGITS, N.POOL_MEAN, 1, N.MASK_AUTO)
+    stream = torch.cuda.current_stream().cuda_stream
+    tptr = types_d.data_ptr() if pair else None
+    tptr_h = types_np.ctypes.data if pair else None
+
+    def step_dev():
+        N.check(lib.kjc_encoder_forward_device_async(enc._h, ids_d.data_ptr(), mask_d.data_ptr(), tptr, B, S, C.byref(opts), out_d.data_ptr(), stream))
+
+    def step_host():
+        N.check(lib.kjc_encoder_forward(enc._h, ids_np.ctypes.data, maskf_np.ctypes.data, tptr_h, B, S, C.byref(opts), out_h.ctypes.data))
+
+    fl = flops_per_seq(H, L, I, S)
+    # steps: C3 = the whole 64-query job; the others enough steps for ~0.3 s of device time
+    steps = 64 if name == "c3_rerank" else max(args.steps, int(min(2000, max(10, 0.15 * peaks["tf_sustained"] * 1e12 / (fl * B)))))
+    for _ in range(3):
+        step_dev()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_dev()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    launches = enc.last_launch_count
+    barrier()
+    for _ in range(2):
+        step_host()
+    e_steps = max(3, steps // 4)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        step_host()
+    e_ms = max_over_ranks((time.perf_counter() - t0) / e_steps * 1e3)
+    # per-kernel-class shares (CUDA events around every launch)
+    N.check(lib.kjc_encoder_set_profiling(enc._h, 1))
+    step_dev()
+    torch.cuda.synchronize()
+    pms = (C.c_double * 8)()
+    pn = (C.c_int64 * 8)()
+    N.check(lib.kjc_encoder_get_profile(enc._h, pms, pn))
+    N.check(lib.kjc_encoder_set_profiling(enc._h, 0))
+    tot = sum(pms[i] for i in range(8)) or 1.0
+    shares = {n: {"ms": round(pms[i], 4), "share": round(pms[i] / tot, 4), "launches": int(pn[i])} for i, n in enumerate(N.KERNEL_CLASSES) if pn[i]}
+    rate = world * B / (ms * 1e-3)
+    tfs = rate / world * fl / 1e12
+    res = {"workload": what, "value": round(rate, 1), "unit": unit, "ms_per_step": round(ms, 4), "steps": steps, "batch_per_gpu": B, "seq_len": S,
+           "e2e": {"value": round(world * B / (e_ms * 1e-3), 1), "unit": unit, "ms_per_step": round(e_ms, 4), "steps": e_steps,
+                   "h2d_bytes_per_step": int(ids_np.nbytes + maskf_np.nbytes + (types_np.nbytes if pair else 0)), "d2h_bytes_per_step": int(out_h.nbytes)},
+           "roofline": {"bound": "tensor", "achieved": round(tfs, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": round(tfs / peaks["tf_sustained"], 4),
+                        "flops_per_seq": fl, "note": "F_seq = L*S*(8H^2 + 4HI + 4SH) (SURVEY 8d) x sequences/s per GPU vs bf16_tflops_sustained"},
+           "gpu_launches_per_step": int(launches), "kernels": shares}
+    if name == "c1_batch32_latency":
+        res["latency_ms"] = {"device": round(ms, 4), "e2e_host_buffers": round(e_ms, 4)}
+    if with_cpu:
+        try:
+            nseq = {"c1_batch32_latency": 32, "c2_classify": 32, "c3_rerank": 16, "c5_bertbase": 4}[name]
+            r, secs, n, cores = cpu_port_rate(_model_dir(arch, rank), S, pair, 4.0, nseq)
+            res["cpu_baseline"] = {"value": round(r, 2), "unit": unit, "cores": cores, "kind": "port",
+                                   "sample": f"{n} sequences x {S} tokens (batches of {nseq}) in {secs:.1f} s; C restatement of the reference CPU forward (oracle/kjarni_oracle.c)"}
+        except Exception as ex:
+            res["cpu_baseline"] = {"error": str(ex)}
+    enc.close()
+    return res
 
 
 def bench_index(args, rank, world, local_rank, lib, N, api, torch, dist, barrier, max_over_ranks, peaks):

@@ -22,6 +22,7 @@ struct AttnParams {
     float scale_log2e;         // (1/sqrt(d)) * log2(e)
     int nan_if_all_masked;     // 1: no-alloc (-inf) convention, a fully padded sequence yields NaN
     int max_ctas = 0;          // persistent tcgen05 kernel: CTAs to launch (0 = one per SM)
+    int dbg = 0;               // probes (KJC_ATTN_DBG through kjc_dbg_attention): 1 = TMA loads only (no MMA, no softmax)
     unsigned long long* trace = nullptr;  // optional [gridDim.x][64] %globaltimer stamps (KJC_ATTN_TRACE, dbg_attention)
 };
 

@@ -13,6 +13,7 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_ts.cuh"
 #include "encoder.hpp"
 #include "ffn_fused.cuh"
 #include "gemm_ln.cuh"
@@ -261,9 +262,53 @@ static void launch_attention_tc(const AttnParams& p, cudaStream_t st) {
     launch_pdl(attention_tc_kernel<D>, dim3(std::min(p.B * p.heads, sms)), dim3(AtcCfg<D>::kThreads), AtcCfg<D>::kSmemBytes, st, t_qkv, t_ctx, p);
 }
 
+// Round-2 kernel (attention_ts.cuh): P in TMEM, S <= 512.  Tensor maps depend on (buffers, B, S, H): one-entry cache per thread.
+template <int D, int NKB>
+static void launch_attention_ts(const AttnParams& p, cudaStream_t st) {
+    using Cfg = AtsCfg<D, NKB>;
+    static int configured[64] = {0};
+    struct Key { const void *q, *c; int B, S, H; };
+    static thread_local Key key{nullptr, nullptr, 0, 0, 0};
+    static thread_local CUtensorMap t_qkv, t_ctx;
+    if (key.q != p.qkv || key.c != p.ctx || key.B != p.B || key.S != p.S || key.H != p.H) {
+        t_qkv = make_tmap_3d(p.qkv, 2, 3 * static_cast<uint64_t>(p.H), p.S, p.B, D, 128, D * 2);
+        t_ctx = make_tmap_3d(p.ctx, 2, p.H, p.S, p.B, D, 32, D * 2);
+        key = Key{p.qkv, p.ctx, p.B, p.S, p.H};
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ensure_smem_attr(attention_ts_kernel<D, NKB>, Cfg::kSmemBytes, configured);
+    if (p.max_ctas > 0) sms = std::min(sms, p.max_ctas);
+    launch_pdl(attention_ts_kernel<D, NKB>, dim3(std::min(p.B * p.heads, sms)), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, t_qkv, t_ctx, p);
+}
+template <int D>
+static void launch_attention_ts_d(const AttnParams& p, cudaStream_t st) {
+    if (p.S <= 128) launch_attention_ts<D, 1>(p, st);
+    else if (p.S <= 256) launch_attention_ts<D, 2>(p, st);
+    else launch_attention_ts<D, 4>(p, st);
+}
+
+// KJC_ATTN = "ts" (default: attention_ts.cuh), "tc" (round-1 tcgen05 kernel, S <= 128), "legacy" (mma.sync kernel): A/B switch
+static int attention_variant() {
+    static const int v = [] {
+        const char* e = getenv("KJC_ATTN");
+        if (getenv("KJC_ATTN_LEGACY") || (e && !strcmp(e, "legacy"))) return 2;
+        if (e && !strcmp(e, "tc")) return 1;
+        return 0;
+    }();
+    return v;
+}
+
 void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
-    static const bool legacy = getenv("KJC_ATTN_LEGACY") != nullptr;
-    if (!legacy && p.S <= kAtcS && (D == 32 || D == 64) && (p.H % 8 == 0)) {
+    const int variant = attention_variant();
+    if (variant == 0 && p.S <= 512 && (D == 32 || D == 64) && (p.H % 8 == 0)) {
+        if (D == 32) launch_attention_ts_d<32>(p, st);
+        else launch_attention_ts_d<64>(p, st);
+        KJ_CUDA(cudaGetLastError());
+        return;
+    }
+    if (variant <= 1 && p.S <= kAtcS && (D == 32 || D == 64) && (p.H % 8 == 0)) {
         if (D == 32) launch_attention_tc<32>(p, st);
         else launch_attention_tc<64>(p, st);
         KJ_CUDA(cudaGetLastError());
@@ -1346,6 +1391,7 @@ void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, in
         a.qkv = dq; a.mask = dm; a.ctx = dc; a.B = B; a.S = S; a.H = H; a.heads = heads;
         a.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
         a.nan_if_all_masked = nan_if_all_masked;
+        if (const char* e = getenv("KJC_ATTN_DBG")) a.dbg = atoi(e);
         launch_attention(a, d, nullptr);
         KJ_CUDA(cudaDeviceSynchronize());
         KJ_CUDA(cudaMemcpy(ctx_bf16, dc, T * H * 2, cudaMemcpyDeviceToHost));
@@ -1359,9 +1405,34 @@ void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, in
             KJ_CUDA(cudaMalloc(&dT, ctas * 64 * 8));
             KJ_CUDA(cudaMemset(dT, 0, ctas * 64 * 8));
             for (int i = 0; i < 3; ++i) launch_attention(a, d, nullptr);
+            unsigned long long* dT2;
+            KJ_CUDA(cudaMalloc(&dT2, ctas * 64 * 8));
+            KJ_CUDA(cudaMemset(dT2, 0, ctas * 64 * 8));
             a.trace = dT;
             launch_attention(a, d, nullptr);
+            a.trace = dT2;
+            launch_attention(a, d, nullptr);
             a.trace = nullptr;
+            launch_attention(a, d, nullptr);
+            KJ_CUDA(cudaDeviceSynchronize());
+            {
+                std::vector<unsigned long long> h1(ctas * 64), h2(ctas * 64);
+                KJ_CUDA(cudaMemcpy(h1.data(), dT, h1.size() * 8, cudaMemcpyDeviceToHost));
+                KJ_CUDA(cudaMemcpy(h2.data(), dT2, h2.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long t0 = ~0ull, e1max = 0, n2min = ~0ull, x2max = 0, e1min = ~0ull;
+                for (int c = 0; c < ctas; ++c) {
+                    if (!h1[c * 64 + 60]) continue;
+                    t0 = std::min(t0, h1[c * 64 + 60]);
+                    e1max = std::max(e1max, h1[c * 64 + 62]);
+                    e1min = std::min(e1min, h1[c * 64 + 62]);
+                    n2min = std::min(n2min, h2[c * 64 + 60]);
+                    x2max = std::max(x2max, h2[c * 64 + 62]);
+                }
+                if (t0 != ~0ull)
+                    fprintf(stderr, "  two launches back to back (us since first entry): launch1 exits %.2f .. %.2f | launch2 first entry %.2f, last exit %.2f\n",
+                            (e1min - t0) * 1e-3, (e1max - t0) * 1e-3, (n2min - t0) * 1e-3, (x2max - t0) * 1e-3);
+            }
+            cudaFree(dT2);
             cudaEvent_t e0, e1;
             KJ_CUDA(cudaEventCreate(&e0));
             KJ_CUDA(cudaEventCreate(&e1));
@@ -1374,13 +1445,23 @@ void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, in
             std::vector<unsigned long long> h(ctas * 64);
             KJ_CUDA(cudaMemcpy(h.data(), dT, h.size() * 8, cudaMemcpyDeviceToHost));
             fprintf(stderr, "attention B=%d S=%d H=%d heads=%d: %.1f us/launch\n", B, S, H, heads, ms * 1e3f / 20);
+            const bool ts = attention_variant() == 0;  // attention_ts.cuh: 4 warpgroups x units 2, 3 at [wg * 16 + u * 6]
             for (int c : {0, ctas / 2}) {
-                for (int wgi = 0; wgi < 3; ++wgi)
-                    for (int u = 0; u < 3; ++u) {
-                        const unsigned long long* t = &h[c * 64 + wgi * 20 + u * 6];
+                if (ts && h[c * 64 + 60]) {
+                    fprintf(stderr, "  cta %3d: entry=0 prologue_done=+%.2f exit=+%.2f (us)\n", c, (h[c * 64 + 61] - h[c * 64 + 60]) * 1e-3,
+                            (h[c * 64 + 62] - h[c * 64 + 60]) * 1e-3);
+                    fprintf(stderr, "    QK issue:");
+                    for (int g = 0; g < 8; ++g) if (h[c * 64 + 24 + g]) fprintf(stderr, " %.2f", (h[c * 64 + 24 + g] - h[c * 64 + 60]) * 1e-3);
+                    fprintf(stderr, "\n    PV issue:");
+                    for (int g = 0; g < 8; ++g) if (h[c * 64 + 32 + g]) fprintf(stderr, " %.2f", (h[c * 64 + 32 + g] - h[c * 64 + 60]) * 1e-3);
+                    fprintf(stderr, "\n");
+                }
+                for (int wgi = 0; wgi < (ts ? 4 : 3); ++wgi)
+                    for (int u = 0; u < (ts ? 1 : 3); ++u) {
+                        const unsigned long long* t = &h[c * 64 + wgi * (ts ? 6 : 20) + u * 6];
                         if (!t[0]) continue;
                         fprintf(stderr, "  cta %3d wg %d unit %d: top=%.2f wait_s=+%.2f pass1=+%.2f pass2=+%.2f wait_o=+%.2f epi=+%.2f (us)\n", c, wgi, u + 1,
-                                (t[0] - h[c * 64]) * 1e-3, (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3);
+                                (t[0] - h[c * 64 + (ts ? 60 : 0)]) * 1e-3, (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3);
                     }
             }
             cudaEventDestroy(e0); cudaEventDestroy(e1);

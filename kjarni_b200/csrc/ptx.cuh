@@ -59,6 +59,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking phase test: mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is not complete,
+// which a thread that polls SEVERAL barriers (the attention MMA issuer) cannot afford.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a pipeline bug turns into a trapped kernel (cudaErrorLaunchFailure) instead of a hung GPU.
 #ifndef KJ_MBAR_SPIN_LIMIT
 #define KJ_MBAR_SPIN_LIMIT (1u << 26)

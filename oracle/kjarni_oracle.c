@@ -43,6 +43,15 @@ typedef struct {
     const KoLayer* layer;
 } KoModel;
 
+/* rayon::ThreadPoolBuilder::num_threads(physical_cores) in kjarni_init (kjarni-ffi/src/lib.rs:36-40) */
+void ko_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ko_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -34,6 +34,8 @@ def lib() -> C.CDLL:
             raise ImportError(f"{LIB_PATH} is missing: build it with `make -C oracle`")
         l = C.CDLL(LIB_PATH)
         l.ko_num_threads.restype = C.c_int
+        l.ko_set_num_threads.restype = None
+        l.ko_set_num_threads.argtypes = [C.c_int]
         l.ko_embed.restype = C.c_int
         l.ko_embed.argtypes = [C.POINTER(KoModel), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.ko_encoder_forward.restype = C.c_int
@@ -104,6 +106,10 @@ def scan_topk(rows, queries, k):
     sc = np.empty((q.shape[0], k), np.float32)
     lib().ko_scan_topk(rows.ctypes.data, norms.ctypes.data, n, dim, q.ctypes.data, q.shape[0], k, ids.ctypes.data, sc.ctypes.data)
     return ids, sc
+
+
+def set_num_threads(n: int) -> None:
+    lib().ko_set_num_threads(int(n))
 
 
 def num_threads() -> int:
