@@ -614,6 +614,11 @@ Encoder::Encoder(const std::string& dir, int device) {
     // so 1536 = 6 x 256 needs 25 % fewer MMA instructions than 8 x 192; with the 16-warp epilogue the launch is 26.4 us against
     // 28.8 us (profiles/r01_gemm_probes.md).  QKV (1152 = 4.5 x 256) measures the same either way and keeps 192.
     if (I % 256 == 0 && gemm_wide_store(256)) bn_i_ = 256;
+    // The same holds for every projection whose width is a whole number of 256-column tiles: a tcgen05.mma of M = 128 retires in
+    // N / 2 clk (scripts/ubench/mma_issue.cu) and the issuing warp shares its scheduler with busy epilogue warps, so the widest
+    // tile amortises the per-instruction issue cost best.  Hidden 768: Q|K|V = 9 x 256, out-proj / FFN-down = 3 x 256.
+    if ((3 * H) % 256 == 0 && gemm_wide_store(256)) bn_qkv_ = 256;
+    if (H % 256 == 0 && gemm_wide_store(256)) bn_h_ = 256;
     if (const char* e = getenv("KJC_BN_I")) bn_i_ = atoi(e);  // tuning hooks
     if (const char* e = getenv("KJC_BN_QKV")) bn_qkv_ = atoi(e);
     layers_.resize(L);
@@ -688,9 +693,10 @@ Encoder::~Encoder() {
 }
 
 void Encoder::free_workspace(Workspace& w) {
-    for (void* p : {(void*)w.y32, (void*)w.x16, (void*)w.qkv16, (void*)w.ctx16, (void*)w.h16})
+    for (void* p : {(void*)w.y32, (void*)w.x16, (void*)w.qkv16, (void*)w.ctx16, (void*)w.h16, (void*)w.head32})
         if (p) cudaFree(p);
     w.y32 = nullptr; w.x16 = w.qkv16 = w.ctx16 = w.h16 = nullptr;
+    w.head32 = nullptr;
     w.tokens = 0;
 }
 
@@ -708,6 +714,7 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     KJ_CUDA(cudaMalloc(&w.qkv16, T * 3 * H * 2));
     KJ_CUDA(cudaMalloc(&w.ctx16, T * H * 2));
     KJ_CUDA(cudaMalloc(&w.h16, T * I * 2));
+    if (w_pre_) KJ_CUDA(cudaMalloc(&w.head32, T * H * 4));  // pre-classifier output, at most one sequence per token
     // stale rows beyond the live token count are read by TMA (results discarded): keep them finite
     KJ_CUDA(cudaMemsetAsync(w.x16, 0, T * H * 2, w.stream));
     KJ_CUDA(cudaMemsetAsync(w.ctx16, 0, T * H * 2, w.stream));
@@ -871,12 +878,10 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         hp.x = w.x16; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
         hp.B = nb; hp.S = S; hp.H = H; hp.C = info_.num_labels;
         hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
-        const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
-        static int configured[64] = {0};
-        if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel<__nv_bfloat16>, static_cast<int>(smem), configured);
-        cls_head_kernel<__nv_bfloat16><<<(nb + kHeadSeqs - 1) / kHeadSeqs, 256, smem, st>>>(hp);
+        hp.z1 = w.head32;  // sized by ensure_workspace for one sequence per token
+        launch_cls_head(hp, st);
         KJ_CUDA(cudaGetLastError());
-        ++launches_;
+        launches_ += w_pre_ ? 2 : 1;
     }
     prof_end(st);
 }
@@ -1003,7 +1008,7 @@ void Encoder::forward_device(const uint32_t* d_ids, const float* d_mask, const u
 }
 
 void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o,
-                           float* out) {
+                           float* out, const RowSink* sink) {
     validate(B, S, o);
     std::lock_guard<std::mutex> lock(mu_);
     KJ_CUDA(cudaSetDevice(info_.device));
@@ -1058,7 +1063,8 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
         KJ_CUDA(cudaEventRecord(ev_chunk_[c & 1], stream_));
         if (c > 0) {
             KJ_CUDA(cudaEventSynchronize(ev_chunk_[(c - 1) & 1]));
-            memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);
+            if (sink) (*sink)(h_stage_out_ + prev_b0 * row, static_cast<size_t>(prev_b0), static_cast<size_t>(prev_nb));
+            else memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);
         }
         prev_b0 = b0;
         prev_nb = nb;
@@ -1071,7 +1077,9 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
         KJ_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), stream_));
         throw Error(KJC_INFERENCE_FAILED, "Token type ID out of range");
     }
-    memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);  // the last chunk (earlier ones were copied in the loop)
+    // the last chunk (earlier ones were handed over in the loop)
+    if (sink) (*sink)(h_stage_out_ + prev_b0 * row, static_cast<size_t>(prev_b0), static_cast<size_t>(prev_nb));
+    else memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);
 }
 
 // Head stage alone on caller-supplied fp32 hidden states (debug hook: the argmax stage must be
@@ -1089,15 +1097,16 @@ void Encoder::head_only_host(const float* hidden, int B, int S, float* logits) {
     hp.x = dh; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = dl;
     hp.B = B; hp.S = S; hp.H = H; hp.C = Cn;
     hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
-    const size_t smem = static_cast<size_t>(2) * kHeadSeqs * H * sizeof(float);
-    static int configured[64] = {0};
-    if (smem > 48 * 1024) ensure_smem_attr(cls_head_kernel<float>, static_cast<int>(smem), configured);
-    cls_head_kernel<float><<<(B + kHeadSeqs - 1) / kHeadSeqs, 256, smem, stream_>>>(hp);
+    float* dz = nullptr;
+    KJ_CUDA(cudaMalloc(&dz, static_cast<size_t>(B) * H * 4));
+    hp.z1 = dz;
+    launch_cls_head(hp, stream_);
     KJ_CUDA(cudaGetLastError());
     KJ_CUDA(cudaStreamSynchronize(stream_));
     KJ_CUDA(cudaMemcpy(logits, dl, static_cast<size_t>(B) * Cn * 4, cudaMemcpyDeviceToHost));
     cudaFree(dh);
     cudaFree(dl);
+    cudaFree(dz);
 }
 
 // -------------------------------------------------------------- debug hooks

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -110,7 +111,11 @@ class Encoder {
     void set_profiling(bool on);
     void get_profile(double* ms, int64_t* launches);  // arrays of KJC_NUM_KERNEL_CLASSES; synchronises
 
-    void forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o, float* out);
+    // `sink` (optional): instead of copying the result rows into `out`, each finished block of rows is handed over while it still
+    // sits in the pinned staging buffer -- sink(rows, first_row, n_rows) -- e.g. to be written to a file (indexer: vectors.bin).
+    using RowSink = std::function<void(const float* rows, size_t first_row, size_t n_rows)>;
+    void forward_host(const uint32_t* ids, const float* mask, const uint32_t* types, int B, int S, const KjcForwardOptions& o, float* out,
+                      const RowSink* sink = nullptr);
     void head_only_host(const float* hidden, int B, int S, float* logits);
     void forward_device(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S, const KjcForwardOptions& o,
                         float* d_out, cudaStream_t st);
@@ -125,6 +130,7 @@ class Encoder {
     struct Workspace {
         int tokens = 0;
         float* y32 = nullptr;  // unfused path only
+        float* head32 = nullptr;  // classification head: pre-classifier output [sequences, H]
         __nv_bfloat16 *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr;
         CUtensorMap t_x16, t_ctx16, t_h16;   // A-operand loads
         CUtensorMap t_qkv16_out, t_h16_out;  // epilogue TMA stores

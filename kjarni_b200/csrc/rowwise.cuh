@@ -323,66 +323,105 @@ mean_pool_l2_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict
 // Classification head on the CLS row (reference: cpu/encoder/classifier.rs:210-258):
 //   z = x[b,0,:]; if pre: z = act(W_pre z + b_pre) (tanh | relu); logits = W_cls z + b_cls.
 // fp32 weights and math so the argmax stage matches the fp32 oracle bit-for-bit up to summation order.
-// One CTA per kHeadSeqs sequences: every W_pre row read from L2 is reused for all of them.
+// Two kernels so that every SM takes part whatever the batch is (round 1 ran ONE CTA per 8 sequences with a scalar, latency-
+// bound weight loop: 112 us for the 1000 pairs of a rerank call, 12-14 % of the C2 / C3 steps):
+//   head_dense_kernel  grid (ceil(B / 8), H / 64): 64 rows of W_pre x 8 sequences per CTA, a warp's W_pre row is fetched with up to
+//                      eight independent 16-byte loads per lane before the FMAs start; z1 [B,H] fp32 to global memory
+//   head_cls_kernel    one warp per (sequence, label) dot product
 enum HeadAct : int { HEAD_NONE = 0, HEAD_TANH = 1, HEAD_RELU = 2 };
 constexpr int kHeadSeqs = 8;
+constexpr int kHeadRows = 64;   // W_pre rows per CTA (8 per warp)
 template <typename TIn>
 struct HeadParams {
     const TIn* x;  // [B, S, H] last hidden state (bf16 from the encoder, fp32 from the debug hook)
     const float* w_pre; const float* b_pre;  // [H,H], [H] or nullptr
     const float* w_cls; const float* b_cls;  // [C,H], [C]
+    float* z1;       // [B, H] fp32 scratch (pre-classifier output); unused when w_pre == nullptr
     float* logits;   // [B, C]
     int B, S, H, C, act;
 };
 template <typename TIn>
-__global__ void __launch_bounds__(256) cls_head_kernel(HeadParams<TIn> p) {
-    extern __shared__ float hs[];  // z0[kHeadSeqs][H], z1[kHeadSeqs][H]
+__global__ void __launch_bounds__(256) head_dense_kernel(HeadParams<TIn> p) {
+    extern __shared__ __align__(16) float hs[];  // z0[kHeadSeqs][H]
     float* z0 = hs;
-    float* z1 = hs + kHeadSeqs * p.H;
     const int b0 = blockIdx.x * kHeadSeqs;
     const int nb = min(kHeadSeqs, p.B - b0);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < kHeadSeqs * p.H; i += 256) {
-        const int s = i / p.H, c = i % p.H;
-        z0[i] = s < nb ? static_cast<float>(p.x[static_cast<size_t>(b0 + s) * p.S * p.H + c]) : 0.0f;
+    const int H = p.H, H4 = H >> 2;
+    for (int i = tid; i < kHeadSeqs * H; i += 256) {
+        const int s = i / H, c = i % H;
+        z0[i] = s < nb ? static_cast<float>(p.x[static_cast<size_t>(b0 + s) * p.S * H + c]) : 0.0f;
     }
     __syncthreads();
-    const float* zin = z0;
-    if (p.w_pre != nullptr) {
-        for (int r = warp; r < p.H; r += 8) {
-            float acc[kHeadSeqs];
+    constexpr int kMaxV = 8;  // H <= 1024: at most 8 float4 per lane
+    for (int rr = 0; rr < kHeadRows / 8; ++rr) {
+        const int r = blockIdx.y * kHeadRows + rr * 8 + warp;
+        if (r >= H) break;  // warp-uniform
+        const float4* w4 = reinterpret_cast<const float4*>(p.w_pre + static_cast<size_t>(r) * H);
+        float4 wv[kMaxV];
 #pragma unroll
-            for (int s = 0; s < kHeadSeqs; ++s) acc[s] = 0.0f;
-            const float* w = p.w_pre + static_cast<size_t>(r) * p.H;
-            for (int c = lane; c < p.H; c += 32) {
-                const float wv = __ldg(w + c);
+        for (int i = 0; i < kMaxV; ++i) {
+            const int c4 = lane + 32 * i;
+            wv[i] = c4 < H4 ? __ldg(w4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float acc[kHeadSeqs];
 #pragma unroll
-                for (int s = 0; s < kHeadSeqs; ++s) acc[s] = fmaf(wv, z0[s * p.H + c], acc[s]);
-            }
+        for (int s = 0; s < kHeadSeqs; ++s) acc[s] = 0.0f;
 #pragma unroll
-            for (int s = 0; s < kHeadSeqs; ++s) acc[s] = warp_sum(acc[s]);
-            if (lane == 0) {
-                const float bb = p.b_pre ? p.b_pre[r] : 0.0f;
+        for (int i = 0; i < kMaxV; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 < H4) {
 #pragma unroll
                 for (int s = 0; s < kHeadSeqs; ++s) {
-                    float v = acc[s] + bb;
-                    if (p.act == HEAD_TANH) v = tanhf(v);
-                    else if (p.act == HEAD_RELU) v = fmaxf(v, 0.0f);
-                    z1[s * p.H + r] = v;
+                    const float4 z = *reinterpret_cast<const float4*>(z0 + s * H + 4 * c4);
+                    acc[s] = fmaf(wv[i].x, z.x, acc[s]);
+                    acc[s] = fmaf(wv[i].y, z.y, acc[s]);
+                    acc[s] = fmaf(wv[i].z, z.z, acc[s]);
+                    acc[s] = fmaf(wv[i].w, z.w, acc[s]);
                 }
             }
         }
-        __syncthreads();
-        zin = z1;
+#pragma unroll
+        for (int s = 0; s < kHeadSeqs; ++s) acc[s] = warp_sum(acc[s]);
+        if (lane == 0) {
+            const float bb = p.b_pre ? p.b_pre[r] : 0.0f;
+#pragma unroll
+            for (int s = 0; s < kHeadSeqs; ++s) {
+                if (s < nb) {
+                    float v = acc[s] + bb;
+                    if (p.act == HEAD_TANH) v = tanhf(v);
+                    else if (p.act == HEAD_RELU) v = fmaxf(v, 0.0f);
+                    p.z1[static_cast<size_t>(b0 + s) * H + r] = v;
+                }
+            }
+        }
     }
-    for (int o = warp; o < p.C * nb; o += 8) {
-        const int cls = o / nb, s = o % nb;
-        const float* w = p.w_cls + static_cast<size_t>(cls) * p.H;
-        float acc = 0.0f;
-        for (int c = lane; c < p.H; c += 32) acc = fmaf(__ldg(w + c), zin[s * p.H + c], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) p.logits[static_cast<size_t>(b0 + s) * p.C + cls] = acc + (p.b_cls ? p.b_cls[cls] : 0.0f);
+}
+// logits[b, cls] = W_cls[cls] . z[b] + b_cls[cls]; z = z1[b] (pre-classifier ran) or the CLS row of x.  One warp per output.
+template <typename TIn>
+__global__ void __launch_bounds__(256) head_cls_kernel(HeadParams<TIn> p) {
+    const int o = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (o >= p.B * p.C) return;
+    const int b = o / p.C, cls = o % p.C;
+    const float* w = p.w_cls + static_cast<size_t>(cls) * p.H;
+    float acc = 0.0f;
+    if (p.w_pre != nullptr) {
+        const float* z = p.z1 + static_cast<size_t>(b) * p.H;
+        for (int c = lane; c < p.H; c += 32) acc = fmaf(__ldg(w + c), z[c], acc);
+    } else {
+        const TIn* z = p.x + static_cast<size_t>(b) * p.S * p.H;
+        for (int c = lane; c < p.H; c += 32) acc = fmaf(__ldg(w + c), static_cast<float>(z[c]), acc);
     }
+    acc = warp_sum(acc);
+    if (lane == 0) p.logits[o] = acc + (p.b_cls ? p.b_cls[cls] : 0.0f);
+}
+template <typename TIn>
+inline void launch_cls_head(const HeadParams<TIn>& p, cudaStream_t st) {
+    if (p.w_pre != nullptr) {
+        const dim3 grid((p.B + kHeadSeqs - 1) / kHeadSeqs, (p.H + kHeadRows - 1) / kHeadRows);
+        head_dense_kernel<TIn><<<grid, 256, static_cast<size_t>(kHeadSeqs) * p.H * sizeof(float), st>>>(p);
+    }
+    head_cls_kernel<TIn><<<(p.B * p.C + 7) / 8, 256, 0, st>>>(p);
 }
 
 // bf16 -> fp32 (the KJC_OUT_HIDDEN output).

@@ -9,7 +9,11 @@
 #include <mutex>
 
 #include "../../include/kjarni_ffi.h"
+#include <atomic>
+#include <chrono>
+
 #include "index.hpp"
+#include "indexer.hpp"
 #include "tokenizer.hpp"
 
 namespace kj {
@@ -102,15 +106,18 @@ struct TextModel {
         tok.reset(new Tokenizer(dir + "/tokenizer.json", enc->info().max_position_embeddings));  // truncation max_length = meta.max_seq_len
     }
 
-    // texts (+ optional second segments) -> [n, out_cols] through one encoder forward
+    // Result rows handed over while they still sit in the encoder's pinned staging buffer: rows[i] belongs to text index[i]
+    using TextSink = std::function<void(const float* rows, size_t n, const size_t* index)>;
+
+    // texts (+ optional second segments) -> [n, out_cols] through one encoder forward (into `out`, or into `sink` when given)
     void run(const std::vector<std::string>& a, const std::vector<std::string>& b, const KjcForwardOptions& o, bool with_types, std::vector<float>& out,
-             size_t out_cols) {
+             size_t out_cols, const TextSink* sink = nullptr) {
         std::vector<uint32_t> ids, types;
         std::vector<float> mask;
         int S = 0;
         tok->encode_batch(a, b, true, ids, mask, types, S);
         if (S == 0) throw Error(KJC_INFERENCE_FAILED, "Tokenizer produced an empty batch");
-        out.assign(a.size() * out_cols, 0.f);
+        if (!sink) out.assign(a.size() * out_cols, 0.f);
         const bool types_ok = with_types && enc->info().type_vocab_size > 0;
         const size_t n = a.size();
         // Length-bucketed batching: BatchLongest pads every text of the call to the longest one, and padded
@@ -125,12 +132,14 @@ struct TextModel {
             len[i] = std::max(l, 1);
             if ((len[i] + 15) / 16 != (len[0] + 15) / 16) one_bucket = false;
         }
-        if (one_bucket || getenv("KJC_NO_LENGTH_BUCKETS")) {
-            enc->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(n), S, o, out.data());
-            return;
-        }
         std::vector<size_t> order(n);
         for (size_t i = 0; i < n; ++i) order[i] = i;
+        static const bool no_buckets = getenv("KJC_NO_LENGTH_BUCKETS") != nullptr;
+        if (one_bucket || no_buckets) {
+            const Encoder::RowSink rs = [&](const float* rows, size_t first, size_t cnt) { (*sink)(rows, cnt, order.data() + first); };
+            enc->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(n), S, o, sink ? nullptr : out.data(), sink ? &rs : nullptr);
+            return;
+        }
         std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return len[x] < len[y]; });
         std::vector<uint32_t> gi, gt;
         std::vector<float> gm, go;
@@ -150,8 +159,13 @@ struct TextModel {
                 memcpy(&gt[r * Sg], &types[src * S], Sg * sizeof(uint32_t));
                 memcpy(&gm[r * Sg], &mask[src * S], Sg * sizeof(float));
             }
-            enc->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, go.data());
-            for (size_t r = 0; r < nb; ++r) memcpy(&out[order[g0 + r] * out_cols], &go[r * out_cols], out_cols * sizeof(float));
+            if (sink) {
+                const Encoder::RowSink rs = [&](const float* rows, size_t first, size_t cnt) { (*sink)(rows, cnt, order.data() + g0 + first); };
+                enc->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, nullptr, &rs);
+            } else {
+                enc->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, go.data());
+                for (size_t r = 0; r < nb; ++r) memcpy(&out[order[g0 + r] * out_cols], &go[r * out_cols], out_cols * sizeof(float));
+            }
             g0 = g1;
         }
     }
@@ -256,8 +270,25 @@ struct KjarniSearcher {
     struct Opened {
         std::unique_ptr<Index> idx;
         IndexDir dir;
+        std::string fingerprint;  // segment list + file sizes / mtimes at open: a rebuilt or appended index is re-opened
+        std::vector<std::unique_ptr<Bm25Index>> bm25;  // per segment, loaded on the first keyword / hybrid query
+        uint64_t last_use = 0;
     };
     std::map<std::string, Opened> opened;
+    uint64_t use_counter = 0;
+    std::string model_name, reranker_name;
+};
+struct KjarniCancelToken {
+    std::atomic<bool> flag{false};
+};
+struct KjarniIndexer {
+    std::unique_ptr<KjarniEmbedder> embedder;
+    std::string model_name;
+    TextSplitter splitter;
+    LoaderOptions loader;
+    size_t batch_size = 32, max_docs_per_segment = 10000;
+    bool quiet = false;
+    std::mutex mu;
 };
 
 namespace {
@@ -313,10 +344,115 @@ void fetch_doc(const IndexDir& d, uint64_t gid, std::string& text, std::vector<s
             if (kv.second.type == Json::Str) meta.emplace_back(kv.first, kv.second.str);
 }
 
+// What IndexReader::open would see: every segment directory with the size and mtime of its vectors.bin and segment.json
+std::string index_fingerprint(const IndexDir& d) {
+    std::string f = std::to_string(d.dimension) + ":" + std::to_string(d.total_rows);
+    for (const IndexDirSegment& s : d.segments) {
+        f += "|" + s.dir + ":" + std::to_string(s.doc_count);
+        for (const char* name : {"/vectors.bin", "/segment.json"}) {
+            struct stat sb;
+            if (stat((s.dir + name).c_str(), &sb) == 0)
+                f += ":" + std::to_string(static_cast<long long>(sb.st_size)) + "@" + std::to_string(static_cast<long long>(sb.st_mtim.tv_sec)) + "." +
+                     std::to_string(static_cast<long long>(sb.st_mtim.tv_nsec));
+        }
+    }
+    return f;
+}
+
+// IndexReader::search_keywords (kjarni-rag/src/index_reader.rs:230-245): per-segment BM25 top-`limit`, concatenated in segment order,
+// stable sort by score descending, truncated; ids are global.  `bm25` caches the segments' indexes (nullptr entries are loaded).
+std::vector<std::pair<uint64_t, float>> keyword_search(const IndexDir& d, std::vector<std::unique_ptr<Bm25Index>>& bm25, const std::string& query, size_t limit) {
+    if (bm25.size() != d.segments.size()) {
+        bm25.clear();
+        bm25.resize(d.segments.size());
+    }
+    std::vector<std::pair<uint64_t, float>> all;
+    for (size_t i = 0; i < d.segments.size(); ++i) {
+        if (!bm25[i]) bm25[i].reset(new Bm25Index(Bm25Index::load(d.segments[i].dir + "/bm25.bin")));
+        for (const auto& hit : bm25[i]->search(query, limit)) all.emplace_back(d.segments[i].global_base + hit.first, hit.second);
+    }
+    std::stable_sort(all.begin(), all.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+    if (all.size() > limit) all.resize(limit);
+    return all;
+}
+
+struct SearchHit {
+    float score;
+    uint64_t id;
+    std::string text;
+    std::vector<std::pair<std::string, std::string>> meta;
+};
+
+// MetadataFilter::matches for the two filters the C ABI can express (kjarni-rag/src/index_reader.rs:27-80)
+bool filter_matches(const KjarniSearchOptions& o, const SearchHit& h);
+
+void fill_results(std::vector<SearchHit>& hits, KjarniSearchResults* out) {
+    if (hits.empty()) return;
+    KjarniSearchResult* r = static_cast<KjarniSearchResult*>(calloc(hits.size(), sizeof(KjarniSearchResult)));
+    if (!r) throw std::bad_alloc();
+    for (size_t i = 0; i < hits.size(); ++i) {
+        std::string mj = "{";
+        for (size_t k = 0; k < hits[i].meta.size(); ++k)
+            mj += std::string(k ? "," : "") + "\"" + json_escape(hits[i].meta[k].first) + "\":\"" + json_escape(hits[i].meta[k].second) + "\"";
+        mj += "}";
+        r[i] = KjarniSearchResult{hits[i].score, static_cast<size_t>(hits[i].id), dup_cstr(hits[i].text), dup_cstr(mj)};
+    }
+    out->results = r;
+    out->len = hits.size();
+}
+
+size_t copy_name(const std::string& name, char* buf, size_t buf_len) {  // the buffer protocol of kjarni_*_model_name
+    const size_t required = name.size() + 1;
+    if (!buf || buf_len == 0) return required;
+    const size_t n = std::min(name.size(), buf_len - 1);
+    memcpy(buf, name.data(), n);
+    buf[n] = 0;
+    return required;
+}
+
+std::vector<std::string> split_csv(const char* s, bool strip_dot) {
+    std::vector<std::string> out;
+    if (!s) return out;
+    std::string cur;
+    auto push = [&] {
+        size_t a = 0, b = cur.size();
+        while (a < b && isspace(static_cast<unsigned char>(cur[a]))) ++a;
+        while (b > a && isspace(static_cast<unsigned char>(cur[b - 1]))) --b;
+        std::string t = cur.substr(a, b - a);
+        if (strip_dot) {
+            t = lower(t);
+            while (!t.empty() && t[0] == '.') t.erase(0, 1);
+        }
+        out.push_back(t);
+        cur.clear();
+    };
+    for (const char* p = s; *p; ++p) {
+        if (*p == ',') push();
+        else cur.push_back(*p);
+    }
+    push();
+    return out;
+}
+
 const std::string* meta_get(const std::vector<std::pair<std::string, std::string>>& m, const std::string& k) {
     for (auto& kv : m)
         if (kv.first == k) return &kv.second;
     return nullptr;
+}
+
+bool filter_matches(const KjarniSearchOptions& o, const SearchHit& h) {
+    if (o.filter_key && o.filter_value) {
+        const std::string* v = meta_get(h.meta, o.filter_key);
+        if (!v || *v != o.filter_value) return false;
+    }
+    if (o.source_pattern && uni::valid_utf8(o.source_pattern)) {
+        const std::string* src = meta_get(h.meta, "source");
+        if (!src) return false;
+        const std::string pat = o.source_pattern;
+        const std::string name = pat.find('/') != std::string::npos ? *src : src->substr(src->find_last_of('/') + 1);
+        if (fnmatch(pat.c_str(), name.c_str(), 0) != 0) return false;
+    }
+    return true;
 }
 
 }  // namespace
@@ -606,6 +742,8 @@ KjarniErrorCode kjarni_searcher_new(const KjarniSearcherConfig* config, KjarniSe
         }
         s->default_mode = c.default_mode;
         s->default_top_k = c.default_top_k;
+        s->model_name = (c.model_name && *c.model_name) ? c.model_name : "minilm-l6-v2";
+        if (s->reranker) s->reranker_name = c.rerank_model;
         *out = s.release();
     });
 }
@@ -626,69 +764,77 @@ KjarniErrorCode kjarni_searcher_search_with_options(KjarniSearcher* s, const cha
         // Searcher::search_with_options, kjarni/src/searcher/model.rs:96-189
         std::lock_guard<std::mutex> lock(s->mu);
         if (!file_ok(std::string(index_path) + "/config.json")) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, std::string("Index not found: ") + index_path};
+        // The reference opens the index on every call (IndexReader::open is an mmap there).  Here opening is an upload, so the
+        // shard is kept -- but only while the directory is what it was: the segment list with the sizes and mtimes of the files
+        // is compared on every call, and at most eight indexes stay resident (least recently used goes first).
+        IndexDir now = scan_index_dir(index_path);
+        const std::string fp = index_fingerprint(now);
         auto it = s->opened.find(index_path);
+        if (it != s->opened.end() && it->second.fingerprint != fp) {
+            s->opened.erase(it);
+            it = s->opened.end();
+        }
         if (it == s->opened.end()) {
+            if (s->opened.size() >= 8) {
+                auto victim = s->opened.begin();
+                for (auto j = s->opened.begin(); j != s->opened.end(); ++j)
+                    if (j->second.last_use < victim->second.last_use) victim = j;
+                s->opened.erase(victim);
+            }
             KjarniSearcher::Opened op;
-            op.dir = scan_index_dir(index_path);
+            op.dir = std::move(now);
+            op.fingerprint = fp;
             if (op.dir.total_rows > 0) op.idx.reset(open_index_dir(index_path, 0, 0, 1));
             it = s->opened.emplace(index_path, std::move(op)).first;
         }
         KjarniSearcher::Opened& op = it->second;
+        op.last_use = ++s->use_counter;
         const int model_dim = s->embedder->m->enc->info().hidden_size;
         if (op.dir.dimension != model_dim)
             throw Fail{KJARNI_ERROR_INVALID_CONFIG, "Dimension mismatch: index has " + std::to_string(op.dir.dimension) + ", model has " + std::to_string(model_dim)};
         const int mode = o.mode >= 0 ? (o.mode == 0 ? 0 : (o.mode == 1 ? 1 : 2)) : static_cast<int>(s->default_mode);
-        if (mode != KJARNI_SEARCH_MODE_SEMANTIC)
-            throw Fail{KJARNI_ERROR_INVALID_CONFIG, "keyword / hybrid search needs the BM25 index, which stays with the CPU host; the CUDA backend serves "
-                                                    "KJARNI_SEARCH_MODE_SEMANTIC"};
         const size_t top_k = o.top_k > 0 ? o.top_k : s->default_top_k;
         const bool use_reranker = (o.use_reranker >= 0 ? o.use_reranker != 0 : static_cast<bool>(s->reranker)) && s->reranker;
         const size_t fetch_k = use_reranker ? top_k * 5 : top_k;
         const bool has_filter = (o.source_pattern && uni::valid_utf8(o.source_pattern)) || (o.filter_key && o.filter_value);
-        const size_t scan_k = std::min<size_t>(has_filter ? fetch_k * 3 : fetch_k, 256);  // search_semantic_filtered: limit * 3 then filter
-        struct Hit {
-            float score;
-            uint64_t id;
-            std::string text;
-            std::vector<std::pair<std::string, std::string>> meta;
-        };
-        std::vector<Hit> hits;
-        if (op.idx && scan_k > 0) {
+        const size_t limit = has_filter ? fetch_k * 3 : fetch_k;  // search_*_filtered: limit * 3 candidates, then filter, then take(limit)
+
+        // IndexReader::search_semantic on the GPU shard: exact cosine top-`n` in global ids, (score desc, id asc)
+        auto semantic = [&](size_t n) {
+            std::vector<std::pair<uint64_t, float>> res;
+            if (!op.idx || n == 0) return res;
+            if (n > 256) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "the GPU scan returns at most 256 candidates per query; top_k x rerank / filter / hybrid factors ask for " + std::to_string(n)};
             std::vector<float> q;
             s->embedder->embed({std::string(query)}, q);
-            std::vector<uint64_t> ids(scan_k);
-            std::vector<float> sc(scan_k);
+            std::vector<uint64_t> ids(n);
+            std::vector<float> sc(n);
             int32_t cnt = 0;
-            op.idx->search_host(q.data(), 1, static_cast<int>(scan_k), KJC_SCAN_SEGMENT, ids.data(), sc.data(), &cnt);
-            for (int i = 0; i < cnt; ++i) {
-                Hit h{sc[i], ids[i], {}, {}};
-                fetch_doc(op.dir, ids[i], h.text, h.meta);
-                if (has_filter) {  // MetadataFilter::matches, kjarni-rag/src/index_reader.rs:27-80
-                    if (o.filter_key && o.filter_value) {
-                        const std::string* v = meta_get(h.meta, o.filter_key);
-                        if (!v || *v != o.filter_value) continue;
-                    }
-                    if (o.source_pattern && uni::valid_utf8(o.source_pattern)) {
-                        const std::string* src = meta_get(h.meta, "source");
-                        if (!src) continue;
-                        const std::string pat = o.source_pattern;
-                        const std::string name = pat.find('/') != std::string::npos ? *src : src->substr(src->find_last_of('/') + 1);
-                        if (fnmatch(pat.c_str(), name.c_str(), 0) != 0) continue;
-                    }
-                }
-                hits.push_back(std::move(h));
-                if (hits.size() >= fetch_k) break;
-            }
+            op.idx->search_host(q.data(), 1, static_cast<int>(n), KJC_SCAN_SEGMENT, ids.data(), sc.data(), &cnt);
+            for (int i = 0; i < cnt; ++i) res.emplace_back(ids[i], sc[i]);
+            return res;
+        };
+        std::vector<std::pair<uint64_t, float>> ranked;
+        if (mode == KJARNI_SEARCH_MODE_KEYWORD) ranked = keyword_search(op.dir, op.bm25, query, limit);
+        else if (mode == KJARNI_SEARCH_MODE_SEMANTIC) ranked = semantic(limit);
+        else  // IndexReader::search_hybrid (index_reader.rs:248-289): 2 x limit of each, reciprocal-rank fusion (hybrid.rs:3-31)
+            ranked = rrf_fuse(keyword_search(op.dir, op.bm25, query, limit * 2), semantic(limit * 2), limit);
+        std::vector<SearchHit> hits;
+        for (const auto& r : ranked) {
+            SearchHit h{r.second, r.first, {}, {}};
+            fetch_doc(op.dir, r.first, h.text, h.meta);
+            if (has_filter && !filter_matches(o, h)) continue;
+            hits.push_back(std::move(h));
+            if (hits.size() >= fetch_k) break;
         }
         if (use_reranker && !hits.empty()) {
             std::vector<std::string> docs;
-            for (const Hit& h : hits) docs.push_back(h.text);
+            for (const SearchHit& h : hits) docs.push_back(h.text);
             std::vector<float> rs;
             s->reranker->score(query, docs, rs);
             std::vector<size_t> order(hits.size());
             for (size_t i = 0; i < order.size(); ++i) order[i] = i;
             std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return rs[a] > rs[b]; });
-            std::vector<Hit> re;
+            std::vector<SearchHit> re;
             for (size_t i = 0; i < order.size() && i < top_k; ++i) {
                 re.push_back(hits[order[i]]);
                 re.back().score = rs[order[i]];
@@ -696,30 +842,325 @@ KjarniErrorCode kjarni_searcher_search_with_options(KjarniSearcher* s, const cha
             hits.swap(re);
         }
         if (o.threshold > 0.0f) {
-            std::vector<Hit> kept;
-            for (Hit& h : hits)
+            std::vector<SearchHit> kept;
+            for (SearchHit& h : hits)
                 if (h.score >= o.threshold) kept.push_back(std::move(h));
             hits.swap(kept);
         }
         if (hits.size() > top_k) hits.resize(top_k);
-        if (hits.empty()) return;
-        KjarniSearchResult* r = static_cast<KjarniSearchResult*>(calloc(hits.size(), sizeof(KjarniSearchResult)));
-        if (!r) throw std::bad_alloc();
-        for (size_t i = 0; i < hits.size(); ++i) {
-            std::string mj = "{";
-            for (size_t k = 0; k < hits[i].meta.size(); ++k)
-                mj += std::string(k ? "," : "") + "\"" + json_escape(hits[i].meta[k].first) + "\":\"" + json_escape(hits[i].meta[k].second) + "\"";
-            mj += "}";
-            r[i] = KjarniSearchResult{hits[i].score, static_cast<size_t>(hits[i].id), dup_cstr(hits[i].text), dup_cstr(mj)};
-        }
-        out->results = r;
-        out->len = hits.size();
+        fill_results(hits, out);
     });
 }
 KjarniErrorCode kjarni_searcher_search(KjarniSearcher* s, const char* index_path, const char* query, KjarniSearchResults* out) {
     const KjarniSearchOptions o = kjarni_search_options_default();
     return kjarni_searcher_search_with_options(s, index_path, query, &o, out);
 }
+
+size_t kjarni_searcher_model_name(const KjarniSearcher* s, char* buf, size_t buf_len) { return s ? copy_name(s->model_name, buf, buf_len) : 0; }
+size_t kjarni_searcher_reranker_model(const KjarniSearcher* s, char* buf, size_t buf_len) {
+    return (s && s->reranker) ? copy_name(s->reranker_name, buf, buf_len) : 0;
+}
+KjarniErrorCode kjarni_search_keywords(const char* index_path, const char* query, size_t top_k, KjarniSearchResults* out) {
+    KJ_NULLCHECK(!index_path || !query || !out);
+    *out = KjarniSearchResults{nullptr, 0};
+    KJ_UTF8(index_path);
+    KJ_UTF8(query);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {  // Searcher::search_keywords: IndexReader::open + search_keywords, host only
+        const IndexDir d = scan_index_dir(index_path);
+        std::vector<std::unique_ptr<Bm25Index>> cache;
+        std::vector<SearchHit> hits;
+        for (const auto& r : keyword_search(d, cache, query, top_k)) {
+            SearchHit h{r.second, r.first, {}, {}};
+            fetch_doc(d, r.first, h.text, h.meta);
+            hits.push_back(std::move(h));
+        }
+        fill_results(hits, out);
+    });
+}
+
+// ------------------------------------------------------------------ cancellation tokens (kjarni-ffi/src/callback.rs:46-92)
+KjarniCancelToken* kjarni_cancel_token_new(void) { return new (std::nothrow) KjarniCancelToken; }
+void kjarni_cancel_token_cancel(KjarniCancelToken* t) { if (t) t->flag.store(true); }
+bool kjarni_cancel_token_is_cancelled(const KjarniCancelToken* t) { return t && t->flag.load(); }
+void kjarni_cancel_token_reset(KjarniCancelToken* t) { if (t) t->flag.store(false); }
+void kjarni_cancel_token_free(KjarniCancelToken* t) { delete t; }
+
+// ------------------------------------------------------------------ Indexer (kjarni-ffi/src/indexer.rs, kjarni/src/indexer/model.rs)
+void kjarni_index_info_free(KjarniIndexInfo info) {
+    free(info.path);
+    free(info.embedding_model);
+}
+KjarniIndexerConfig kjarni_indexer_config_default(void) {
+    return KjarniIndexerConfig{KJARNI_DEVICE_CPU, nullptr, nullptr, 512, 50, 32, nullptr, nullptr, 1, 0, 10u * 1024 * 1024, 0};
+}
+KjarniErrorCode kjarni_indexer_new(const KjarniIndexerConfig* config, KjarniIndexer** out) {
+    KJ_NULLCHECK(!out);
+    *out = nullptr;
+    const KjarniIndexerConfig dflt = kjarni_indexer_config_default();
+    const KjarniIndexerConfig& c = config ? *config : dflt;
+    KJ_UTF8(c.cache_dir);
+    KJ_UTF8(c.model_name);
+    KJ_UTF8(c.extensions);
+    KJ_UTF8(c.exclude_patterns);
+    return guarded(KJARNI_ERROR_LOAD_FAILED, [&] {
+        device_check(c.device);
+        if (c.chunk_size == 0) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "chunk_size must be greater than 0"};               // SplitterConfig::validate
+        if (c.chunk_overlap >= c.chunk_size) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "chunk_overlap must be less than chunk_size"};
+        std::unique_ptr<KjarniIndexer> ix(new KjarniIndexer);
+        ix->model_name = (c.model_name && *c.model_name) ? c.model_name : "minilm-l6-v2";
+        ix->embedder.reset(new KjarniEmbedder);
+        ix->embedder->m.reset(new TextModel(resolve_model_dir(c.cache_dir, c.model_name, nullptr, "minilm-l6-v2"), ix->model_name));
+        ix->embedder->normalize = true;
+        ix->splitter.chunk_size = c.chunk_size;
+        ix->splitter.chunk_overlap = c.chunk_overlap;
+        ix->batch_size = std::max<size_t>(c.batch_size, 1);
+        ix->loader.extensions = split_csv(c.extensions, true);
+        ix->loader.exclude_patterns = split_csv(c.exclude_patterns, false);
+        ix->loader.recursive = c.recursive != 0;
+        ix->loader.include_hidden = c.include_hidden != 0;
+        if (c.max_file_size > 0) ix->loader.max_file_size = c.max_file_size;
+        ix->quiet = c.quiet != 0;
+        *out = ix.release();
+    });
+}
+void kjarni_indexer_free(KjarniIndexer* ix) { delete ix; }
+size_t kjarni_indexer_model_name(const KjarniIndexer* ix, char* buf, size_t buf_len) { return ix ? copy_name(ix->model_name, buf, buf_len) : 0; }
+size_t kjarni_indexer_dimension(const KjarniIndexer* ix) { return ix ? static_cast<size_t>(ix->embedder->m->enc->info().hidden_size) : 0; }
+size_t kjarni_indexer_chunk_size(const KjarniIndexer* ix) { return ix ? ix->splitter.chunk_size : 0; }
+
+}  // extern "C"
+
+namespace {
+// Indexer::create_internal / add_internal (kjarni/src/indexer/model.rs:169-300,466-570): discover -> load + split -> embed -> write.
+// Chunks are embedded in GPU-sized groups (at least the caller's batch_size, up to 1024 texts: rows are independent, so the
+// grouping is invisible in the result) and every embedding row goes from the encoder's pinned output buffer straight into the
+// segment's vectors.bin.
+size_t run_indexer(KjarniIndexer* ix, IndexWriter& writer, const std::vector<std::string>& inputs, KjarniProgressCallbackFn cb, void* user,
+                   const KjarniCancelToken* cancel, KjarniIndexStats* stats) {
+    auto report = [&](KjarniProgressStage st, size_t cur, size_t total, const char* msg) {
+        if (cb) cb(KjarniProgress{st, cur, total, msg}, user);
+    };
+    auto check_cancel = [&] {
+        if (cancel && cancel->flag.load()) throw Fail{KJARNI_ERROR_CANCELLED, "Operation cancelled"};
+    };
+    report(KJARNI_PROGRESS_SCANNING, 0, 0, "Discovering files...");
+    std::vector<std::string> files;
+    try {
+        files = collect_files(inputs, ix->loader);
+    } catch (const Error& e) {
+        throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, e.what()};
+    }
+    check_cancel();
+    const size_t group = std::max<size_t>(ix->batch_size, 1024);
+    const int dim = writer.dimension();
+    std::vector<std::string> texts;
+    std::vector<std::vector<std::pair<std::string, std::string>>> metas;
+    size_t total_docs = 0, total_chunks = 0, processed = 0, skipped = 0;
+    auto flush = [&] {
+        size_t done = 0;
+        while (done < texts.size()) {
+            check_cancel();
+            report(KJARNI_PROGRESS_EMBEDDING, total_docs, 0, nullptr);
+            SegmentWriter& seg = writer.current();
+            const size_t n = std::min(texts.size() - done, seg.room());
+            std::vector<std::string> part(texts.begin() + done, texts.begin() + done + n);
+            std::vector<size_t> row_id(n);
+            for (size_t i = 0; i < n; ++i) row_id[i] = seg.add_text(part[i], metas[done + i]);
+            const TextModel::TextSink sink = [&](const float* rows, size_t cnt, const size_t* index) {
+                size_t i = 0;
+                while (i < cnt) {  // runs of consecutive documents go out as one write
+                    size_t j = i + 1;
+                    while (j < cnt && index[j] == index[j - 1] + 1) ++j;
+                    seg.write_rows(row_id[index[i]], rows + i * dim, j - i);
+                    i = j;
+                }
+            };
+            {
+                std::lock_guard<std::mutex> lock(ix->embedder->mu);
+                const KjcForwardOptions o{KJC_OUT_POOLED, KJC_POOL_MEAN, 1, KJC_MASK_AUTO};
+                std::vector<float> unused;
+                ix->embedder->m->run(part, {}, o, false, unused, static_cast<size_t>(dim), &sink);
+            }
+            writer.note_added(n);
+            total_docs += n;
+            done += n;
+        }
+        texts.clear();
+        metas.clear();
+    };
+    for (size_t fi = 0; fi < files.size(); ++fi) {
+        check_cancel();
+        report(KJARNI_PROGRESS_LOADING, fi, files.size(), files[fi].c_str());
+        std::string content;
+        bool ok = true;
+        try {
+            content = read_text_file(files[fi], KJC_LOAD_FAILED);
+            ok = uni::valid_utf8(content.c_str()) && content.find('\0') == std::string::npos;  // fs::read_to_string fails on invalid UTF-8
+        } catch (const Error&) {
+            ok = false;
+        }
+        if (!ok) {
+            ++skipped;
+            if (!ix->quiet) fprintf(stderr, "Warning: Failed to load %s\n", files[fi].c_str());
+            continue;
+        }
+        const std::vector<std::string> chunks = ix->splitter.split(content);  // DocumentLoader::load_file, loader.rs:71-93
+        total_chunks += chunks.size();
+        ++processed;
+        for (size_t ci = 0; ci < chunks.size(); ++ci) {
+            texts.push_back(chunks[ci]);
+            metas.push_back({{"source", files[fi]}, {"chunk_index", std::to_string(ci)}, {"total_chunks", std::to_string(chunks.size())}});
+            if (texts.size() >= group) flush();
+        }
+    }
+    if (!texts.empty()) flush();
+    report(KJARNI_PROGRESS_COMMITTING, total_docs, total_docs, "Finalizing index...");
+    writer.commit();
+    if (stats) {
+        stats->documents_indexed = total_docs;
+        stats->chunks_created = total_chunks;
+        stats->dimension = static_cast<size_t>(dim);
+        stats->files_processed = processed;
+        stats->files_skipped = skipped;
+    }
+    return total_docs;
+}
+
+bool parse_inputs(const char* const* inputs, size_t n, std::vector<std::string>& out, KjarniErrorCode& err) {
+    for (size_t i = 0; i < n; ++i) {
+        if (!inputs[i]) { err = KJARNI_ERROR_NULL_POINTER; return false; }
+        if (!uni::valid_utf8(inputs[i])) { err = KJARNI_ERROR_INVALID_UTF8; return false; }
+        out.emplace_back(inputs[i]);
+    }
+    return true;
+}
+bool path_exists(const std::string& p) {
+    struct stat sb;
+    return stat(p.c_str(), &sb) == 0;
+}
+}  // namespace
+
+extern "C" {
+
+KjarniErrorCode kjarni_indexer_create_with_callback(KjarniIndexer* ix, const char* index_path, const char* const* inputs, size_t num_inputs, int32_t force,
+                                                    KjarniProgressCallbackFn cb, void* user_data, const KjarniCancelToken* cancel, KjarniIndexStats* out) {
+    KJ_NULLCHECK(!ix || !index_path || !inputs || !out);
+    *out = KjarniIndexStats{};
+    KJ_UTF8(index_path);
+    std::vector<std::string> in;
+    KjarniErrorCode perr = KJARNI_OK;
+    if (!parse_inputs(inputs, num_inputs, in, perr)) return perr;
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        const auto t0 = std::chrono::steady_clock::now();
+        if (in.empty()) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "No input paths specified"};
+        if (path_exists(index_path)) {
+            if (!force) throw Fail{KJARNI_ERROR_INVALID_CONFIG, std::string("Index already exists at ") + index_path + ". Use force=true to overwrite."};
+            remove_tree(index_path);
+        }
+        IndexWriter writer(index_path, true, ix->embedder->m->enc->info().hidden_size, ix->max_docs_per_segment, ix->model_name);
+        run_indexer(ix, writer, in, cb, user_data, cancel, out);
+        out->size_bytes = tree_size(index_path);
+        out->elapsed_ms = static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count());
+    });
+}
+KjarniErrorCode kjarni_indexer_create(KjarniIndexer* ix, const char* index_path, const char* const* inputs, size_t num_inputs, int32_t force,
+                                      KjarniIndexStats* out) {
+    return kjarni_indexer_create_with_callback(ix, index_path, inputs, num_inputs, force, nullptr, nullptr, nullptr, out);
+}
+KjarniErrorCode kjarni_indexer_add_with_callback(KjarniIndexer* ix, const char* index_path, const char* const* inputs, size_t num_inputs,
+                                                 KjarniProgressCallbackFn cb, void* user_data, const KjarniCancelToken* cancel, size_t* documents_added) {
+    KJ_NULLCHECK(!ix || !index_path || !inputs || !documents_added);
+    *documents_added = 0;
+    if (num_inputs == 0) return KJARNI_OK;
+    KJ_UTF8(index_path);
+    std::vector<std::string> in;
+    KjarniErrorCode perr = KJARNI_OK;
+    if (!parse_inputs(inputs, num_inputs, in, perr)) return perr;
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        if (!path_exists(index_path)) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, std::string("Index not found at ") + index_path};
+        IndexWriter writer(index_path, false, 0, 0, "");
+        const int model_dim = ix->embedder->m->enc->info().hidden_size;
+        if (writer.dimension() != model_dim)
+            throw Fail{KJARNI_ERROR_INVALID_CONFIG, "Dimension mismatch: index has " + std::to_string(writer.dimension()) + ", model produces " + std::to_string(model_dim)};
+        *documents_added = run_indexer(ix, writer, in, cb, user_data, cancel, nullptr);
+    });
+}
+KjarniErrorCode kjarni_indexer_add(KjarniIndexer* ix, const char* index_path, const char* const* inputs, size_t num_inputs, size_t* documents_added) {
+    return kjarni_indexer_add_with_callback(ix, index_path, inputs, num_inputs, nullptr, nullptr, nullptr, documents_added);
+}
+KjarniErrorCode kjarni_index_info(const char* index_path, KjarniIndexInfo* out) {
+    KJ_NULLCHECK(!index_path || !out);
+    *out = KjarniIndexInfo{};
+    KJ_UTF8(index_path);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {  // Indexer::info, kjarni/src/indexer/model.rs:95-124
+        if (!path_exists(index_path)) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, std::string("Index not found at ") + index_path};
+        const IndexDir d = scan_index_dir(index_path);
+        std::string model;
+        {
+            const std::string txt = read_text_file(std::string(index_path) + "/config.json", KJC_MODEL_NOT_FOUND);
+            const Json cfg = JsonParser(txt.data(), txt.size()).parse();
+            model = cfg.string("embedding_model", "");
+        }
+        out->path = dup_cstr(index_path);
+        out->document_count = static_cast<size_t>(d.total_rows);
+        out->segment_count = d.segments.size();
+        out->dimension = static_cast<size_t>(d.dimension);
+        out->size_bytes = tree_size(index_path);
+        out->embedding_model = model.empty() ? nullptr : dup_cstr(model);
+    });
+}
+KjarniErrorCode kjarni_index_delete(const char* index_path) {
+    KJ_NULLCHECK(!index_path);
+    KJ_UTF8(index_path);
+    return guarded(KJARNI_ERROR_INFERENCE_FAILED, [&] {
+        if (!path_exists(index_path)) throw Fail{KJARNI_ERROR_MODEL_NOT_FOUND, std::string("Index not found at ") + index_path};
+        remove_tree(index_path);
+    });
+}
+
+// ------------------------------------------------------------------ Chat: out of scope (LLM decode), load-compatibility stubs
+KjarniChatConfig kjarni_chat_config_default(void) { return KjarniChatConfig{KJARNI_DEVICE_CPU, nullptr, nullptr, nullptr, nullptr, 0, 0}; }
+KjarniGenerationConfig kjarni_generation_config_default(void) { return KjarniGenerationConfig{-1.0f, -1, -1.0f, -1.0f, -1.0f, -1, -1}; }
+static KjarniErrorCode chat_unsupported() {
+    set_last_error("chat / text generation is not served by the CUDA encoder backend (autoregressive decode is outside its scope)");
+    return KJARNI_ERROR_INVALID_CONFIG;
+}
+KjarniErrorCode kjarni_chat_new(const KjarniChatConfig*, KjarniChat** out) {
+    KJ_NULLCHECK(!out);
+    *out = nullptr;
+    return chat_unsupported();
+}
+void kjarni_chat_free(KjarniChat*) {}
+KjarniErrorCode kjarni_chat_send(KjarniChat*, const char*, const KjarniGenerationConfig*, char** out) {
+    if (out) *out = nullptr;
+    return chat_unsupported();
+}
+KjarniErrorCode kjarni_chat_stream(KjarniChat*, const char*, const KjarniGenerationConfig*, KjarniStreamCallbackFn, void*, const KjarniCancelToken*) {
+    return chat_unsupported();
+}
+KjarniErrorCode kjarni_chat_send_with_history(KjarniChat*, const int32_t*, const char* const*, size_t, const char*, const KjarniGenerationConfig*, char** out) {
+    if (out) *out = nullptr;
+    return chat_unsupported();
+}
+KjarniErrorCode kjarni_chat_conversation_new(KjarniChat*, KjarniChatConversation** out) {
+    if (out) *out = nullptr;
+    return chat_unsupported();
+}
+void kjarni_chat_conversation_free(KjarniChatConversation*) {}
+KjarniErrorCode kjarni_chat_conversation_send(KjarniChatConversation*, const char*, const KjarniGenerationConfig*, char** out) {
+    if (out) *out = nullptr;
+    return chat_unsupported();
+}
+KjarniErrorCode kjarni_chat_conversation_stream(KjarniChatConversation*, const char*, const KjarniGenerationConfig*, KjarniStreamCallbackFn, void*,
+                                                const KjarniCancelToken*) {
+    return chat_unsupported();
+}
+size_t kjarni_chat_conversation_len(const KjarniChatConversation*) { return 0; }
+void kjarni_chat_conversation_clear(KjarniChatConversation*, int32_t) {}
+size_t kjarni_chat_model_name(const KjarniChat*, char*, size_t) { return 0; }
+size_t kjarni_chat_context_size(const KjarniChat*) { return 0; }
 
 // ------------------------------------------------------------------ tokenizer (inner ABI, include/kjarni_cuda.h)
 struct KjcTokenizer {

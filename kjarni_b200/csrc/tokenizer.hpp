@@ -42,6 +42,7 @@ inline bool is_white(uint32_t c) { return in_ranges(kUniWhite, kUniWhite_n, c); 
 inline bool is_other(uint32_t c) { return in_ranges(kUniOther, kUniOther_n, c); }
 inline bool is_mn(uint32_t c) { return in_ranges(kUniMn, kUniMn_n, c); }
 inline bool is_word(uint32_t c) { return in_ranges(kUniWord, kUniWord_n, c); }
+inline bool is_alnum(uint32_t c) { return in_ranges(kUniAlnum, kUniAlnum_n, c); }  // ~ Rust char::is_alphanumeric (see gen_unicode_tables.py)
 inline bool is_ascii_punct(uint32_t c) { return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126); }
 inline bool is_punct(uint32_t c) { return is_ascii_punct(c) || in_ranges(kUniPunct, kUniPunct_n, c); }
 // BertNormalizer::is_chinese_char ranges

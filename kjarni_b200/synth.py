@@ -177,14 +177,55 @@ def synth_tokens(batch: int, seq: int, vocab: int = 30522, *, regime: str = "T",
     return ids, mask, types
 
 
+def bm25_bincode(texts) -> bytes:
+    """bm25.bin of a segment holding `texts`: the Bm25Index that SegmentBuilder::add builds document by document
+    (kjarni-search/src/bm25.rs:115-147), serialised as bincode 1.3 does (kjarni-rag/src/segment.rs:163-165): u64 lengths,
+    little-endian fixed-width integers, struct fields in declaration order."""
+    import struct
+
+    def tokenize(text):  # bm25.rs:192-198
+        out, cur = [], []
+        for ch in text.lower():
+            if ch.isalnum():
+                cur.append(ch)
+            else:
+                if cur:
+                    out.append("".join(cur))
+                cur = []
+        if cur:
+            out.append("".join(cur))
+        return [t for t in out if len(t.encode()) >= 2]
+
+    df, inv, lens, total_len = {}, {}, [], 0
+    for i, t in enumerate(texts):
+        toks = tokenize(t)
+        lens.append(len(toks))
+        total_len += len(toks)
+        counts = {}
+        for k in toks:
+            counts[k] = counts.get(k, 0) + 1
+        for k, c in counts.items():
+            inv.setdefault(k, []).append((i, c))
+            df[k] = df.get(k, 0) + 1
+    n = len(texts)
+    avg = np.float32(total_len) / np.float32(n) if n else np.float32(0)
+    u64 = lambda v: struct.pack("<Q", v)
+    st = lambda s: u64(len(s.encode())) + s.encode()
+    b = u64(len(df)) + b"".join(st(k) + u64(v) for k, v in df.items())
+    b += u64(len(lens)) + b"".join(u64(v) for v in lens)
+    b += struct.pack("<f", float(avg)) + u64(n)
+    b += u64(len(inv)) + b"".join(st(k) + u64(len(v)) + b"".join(u64(d) + u64(c) for d, c in v) for k, v in inv.items())
+    b += struct.pack("<fff", 1.2, 0.75, 0.25) + u64(0) + u64(total_len)
+    return b
+
+
 def write_index_dir(root: str, segments, *, dimension: int = None, max_docs_per_segment: int = 10_000, broken=(), docs=None,
                     metadata=None) -> str:
     """`docs` / `metadata`: optional per-segment lists of texts / {str: str} dicts (defaults: generated text, {}).
     Writes an index directory in the layout IndexWriter::commit leaves (kjarni-rag/src/index_writer.rs:128-170,
     segment.rs:140-193): config.json, index.json, segments/seg_%06d/{segment.json, vectors.bin, docs.bin, docs.idx,
     metadata.jsonl, bm25.bin}.  `segments` = list of float32 [n_i, dim] arrays.  docs.idx is a bincode Vec<u64>
-    (u64 length + offsets); bm25.bin is a placeholder (the GPU reader only checks that it exists, as Segment::open would
-    fail without it).  `broken` = segment indices written WITHOUT bm25.bin, which IndexReader::open skips."""
+    (u64 length + offsets); bm25.bin is the bincode Bm25Index of the segment's texts (`bm25_bincode`).  `broken` = segment indices written WITHOUT bm25.bin, which IndexReader::open skips."""
     import json
     import struct
     import time
@@ -217,7 +258,7 @@ def write_index_dir(root: str, segments, *, dimension: int = None, max_docs_per_
                     f.write(json.dumps(m) + "\n")
         if i not in broken:
             with open(os.path.join(sd, "bm25.bin"), "wb") as f:
-                f.write(b"\0" * 8)
+                f.write(bm25_bincode([d.decode() for d in seg_docs]))
         with open(os.path.join(sd, "segment.json"), "w") as f:
             json.dump({"id": i, "doc_count": int(rows.shape[0]), "dimension": int(rows.shape[1]), "created_at": int(time.time()),
                        "total_bytes": int(rows.nbytes + cur)}, f, indent=2)

@@ -646,3 +646,184 @@ def synth_rows(seed: int, row0: int, n: int, dim: int) -> np.ndarray:
     c = np.arange(dim, dtype=np.uint64)[None, :]
     h = hash32(seed, r, c)
     return ((h >> np.uint32(8)).astype(F32) * F32(2.0 ** -24) - F32(0.5)).astype(F32)
+
+
+# --------------------------------------------------------------------------- #
+# Keyword (BM25) and hybrid (RRF) search, text splitting -- CPU in the reference too
+# --------------------------------------------------------------------------- #
+def bm25_tokenize(text: str) -> List[str]:
+    """kjarni-search/src/bm25.rs:192-198: to_lowercase, split on non-alphanumeric chars, keep tokens of >= 2 BYTES."""
+    out, cur = [], []
+    for ch in text.lower():
+        if ch.isalnum():
+            cur.append(ch)
+        else:
+            if cur:
+                out.append("".join(cur))
+            cur = []
+    if cur:
+        out.append("".join(cur))
+    return [t for t in out if len(t.encode("utf-8")) >= 2]
+
+
+class Bm25:
+    """Bm25Index, kjarni-search/src/bm25.rs:43-190 (k1 1.2, b 0.75; all score arithmetic in f32)."""
+
+    def __init__(self):
+        self.doc_frequencies: Dict[str, int] = {}
+        self.doc_lengths: List[int] = []
+        self.avg_doc_length = F32(0.0)
+        self.total_docs = 0
+        self.inverted_index: Dict[str, List[Tuple[int, int]]] = {}
+        self.k1, self.b, self.epsilon = F32(1.2), F32(0.75), F32(0.25)
+        self.total_length = 0
+
+    def add_document(self, doc_id: int, text: str) -> None:  # :115-147
+        tokens = bm25_tokenize(text)
+        if doc_id >= len(self.doc_lengths):
+            self.doc_lengths.extend([0] * (doc_id + 1 - len(self.doc_lengths)))
+        self.doc_lengths[doc_id] = len(tokens)
+        counts: Dict[str, int] = {}
+        for t in tokens:
+            counts[t] = counts.get(t, 0) + 1
+        for term, c in counts.items():
+            self.inverted_index.setdefault(term, []).append((doc_id, c))
+            self.doc_frequencies[term] = self.doc_frequencies.get(term, 0) + 1
+        self.total_docs = max(self.total_docs, doc_id + 1)
+        self.total_length += len(tokens)
+        self.avg_doc_length = F32(F32(self.total_length) / F32(self.total_docs))
+
+    def score(self, query_tokens: Sequence[str], doc_id: int) -> np.float32:  # calculate_score, :149-176
+        score = F32(0.0)
+        doc_length = F32(self.doc_lengths[doc_id])
+        length_norm = F32(F32(1.0) - self.b + self.b * F32(doc_length / self.avg_doc_length))
+        for term in query_tokens:
+            tf = F32(next((f for d, f in self.inverted_index.get(term, []) if d == doc_id), 0))
+            if tf == 0.0:
+                continue
+            df = F32(self.doc_frequencies.get(term, 0))
+            if df == 0.0:
+                continue
+            idf = F32(np.log(F32(F32(F32(F32(self.total_docs) - df) + F32(0.5)) / F32(df + F32(0.5)) + F32(1.0))))
+            ntf = F32(F32(tf * F32(self.k1 + F32(1.0))) / F32(tf + F32(self.k1 * length_norm)))
+            score = F32(score + F32(idf * ntf))
+        return score
+
+    def search(self, query: str, limit: int) -> List[Tuple[int, float]]:  # :85-113; equal scores: ascending doc id (reference: HashMap order)
+        if self.total_docs == 0:
+            return []
+        q = bm25_tokenize(query)
+        if not q:
+            return []
+        res = [(d, float(self.score(q, d))) for d in range(self.total_docs)]
+        res = [(d, s) for d, s in res if s > 0.0]
+        res.sort(key=lambda t: (-t[1], t[0]))
+        return res[:limit]
+
+
+def bm25_from_bincode(buf: bytes) -> Bm25:
+    """bm25.bin as SegmentBuilder::flush writes it (bincode 1.3 default options), kjarni-rag/src/segment.rs:163-165."""
+    import struct
+
+    p = 0
+
+    def u64():
+        nonlocal p
+        v = struct.unpack_from("<Q", buf, p)[0]
+        p += 8
+        return v
+
+    def f32():
+        nonlocal p
+        v = struct.unpack_from("<f", buf, p)[0]
+        p += 4
+        return F32(v)
+
+    def s():
+        nonlocal p
+        n = u64()
+        v = buf[p:p + n].decode("utf-8")
+        p += n
+        return v
+
+    ix = Bm25()
+    for _ in range(u64()):
+        k = s()
+        ix.doc_frequencies[k] = u64()
+    ix.doc_lengths = [u64() for _ in range(u64())]
+    ix.avg_doc_length = f32()
+    ix.total_docs = u64()
+    for _ in range(u64()):
+        k = s()
+        ix.inverted_index[k] = [(u64(), u64()) for _ in range(u64())]
+    ix.k1, ix.b, ix.epsilon = f32(), f32(), f32()
+    for _ in range(u64()):
+        s()
+        p += 8 * u64()
+    ix.total_length = u64()
+    assert p == len(buf), (p, len(buf))
+    return ix
+
+
+def rrf_hybrid(keyword: Sequence[Tuple[int, float]], semantic: Sequence[Tuple[int, float]], limit: int) -> List[Tuple[int, float]]:
+    """hybrid_search, kjarni-search/src/hybrid.rs:3-31: reciprocal-rank fusion with k = 60 (f32); equal scores: ascending id."""
+    sc: Dict[int, np.float32] = {}
+    for lst in (keyword, semantic):
+        for rank, (idx, _s) in enumerate(lst):
+            v = F32(F32(1.0) / F32(F32(60.0) + F32(rank + 1)))
+            sc[idx] = F32(sc[idx] + v) if idx in sc else v
+    out = sorted(((i, float(v)) for i, v in sc.items()), key=lambda t: (-t[1], t[0]))
+    return out[:limit]
+
+
+def index_search_keywords(segment_texts: Sequence[Sequence[str]], query: str, limit: int) -> List[Tuple[int, float]]:
+    """IndexReader::search_keywords, kjarni-rag/src/index_reader.rs:230-245: per-segment BM25 top-limit, segment order, stable sort."""
+    allr, base = [], 0
+    for texts in segment_texts:
+        ix = Bm25()
+        for i, t in enumerate(texts):
+            ix.add_document(i, t)
+        allr += [(base + d, s) for d, s in ix.search(query, limit)]
+        base += len(texts)
+    allr.sort(key=lambda t: -t[1])  # stable
+    return allr[:limit]
+
+
+def split_text(text: str, chunk_size: int = 1000, chunk_overlap: int = 200, separator: str = "\n\n") -> List[str]:
+    """TextSplitter::split, kjarni-rag/src/splitter.rs:59-163 (section sizes in bytes, overlap / hard split in chars)."""
+    def blen(s):
+        return len(s.encode("utf-8"))
+
+    def split_large(t):
+        out, start = [], 0
+        while start < len(t):
+            end = min(start + chunk_size, len(t))
+            out.append(t[start:end])
+            if end >= len(t):
+                break
+            step = chunk_size - chunk_overlap if 0 < chunk_overlap < chunk_size else chunk_size
+            start = start + step if step > 0 else start + 1
+        return out
+
+    if not text:
+        return []
+    chunks, cur = [], ""
+    for section in text.split(separator):
+        if not section:
+            continue
+        if blen(section) > chunk_size:
+            if cur:
+                chunks.append(cur)
+                cur = ""
+            chunks += split_large(section)
+            continue
+        would = blen(section) if not cur else blen(cur) + blen(separator) + blen(section)
+        if would > chunk_size and cur:
+            chunks.append(cur)
+            cur = (cur if len(cur) <= chunk_overlap else cur[len(cur) - chunk_overlap:]) if chunk_overlap > 0 else ""
+        if cur:
+            cur += separator
+        cur += section
+    if cur:
+        chunks.append(cur)
+    return chunks
