@@ -254,8 +254,14 @@ int kjc_index_get_rows(const KjcIndex* idx, uint64_t row, uint64_t n, float* out
  * Errors: KJC_NULL_POINTER, KJC_INVALID_CONFIG (k < 1 or k > 256, nq < 1), KJC_INFERENCE_FAILED. */
 int kjc_index_search(KjcIndex* idx, const float* queries, int nq, int k, int mode, uint64_t* out_ids, float* out_scores,
                      int32_t* out_counts);
-/* Device-pointer variant, enqueued on `stream` (NULL = the index's stream), no synchronise.
- * Produces this shard's sorted candidates -- the per-segment top-k of IndexReader::search_semantic. */
+/* Device-pointer variant on `stream` (NULL = the index's stream): this shard's sorted candidates -- the per-segment top-k of
+ * IndexReader::search_semantic -- left in device memory for the gather + merge.  ALWAYS exact: it reads one 4-byte counter back
+ * (one stream synchronise) and re-runs on the exact scan every query the tensor-core filter could not prove, like kjc_index_search.
+ * This is the entry the multi-GPU paths use (kjarni_b200/distributed.py, kjc_sharded_index_search). */
+int kjc_index_search_device(KjcIndex* idx, const float* d_queries, int nq, int k, int mode, uint64_t* d_out_ids, float* d_out_scores,
+                            int32_t* d_out_counts, void* stream);
+/* The same without any synchronise (graph capture, latency-critical pipelines): queries the filter could not prove are NOT
+ * re-run, only counted in kjc_index_unverified_count -- the caller must poll that counter (or use the entry above). */
 int kjc_index_search_device_async(KjcIndex* idx, const float* d_queries, int nq, int k, int mode, uint64_t* d_out_ids,
                                   float* d_out_scores, int32_t* d_out_counts, void* stream);
 /* Merge `n_lists` sorted candidate lists (e.g. one per shard/rank after the NVLink gather) into the final

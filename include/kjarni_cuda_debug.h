@@ -15,6 +15,9 @@ int kjc_dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
  * iters > 0 additionally times `iters` launches (average us in *out_us). */
 int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                     const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us);
+/* The same for hidden size H = 384 (one CTA per 128-row tile) or 768 (a CTA pair per tile, statistics exchanged through DSMEM). */
+int kjc_dbg_gemm_ln_h(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
+                      const uint16_t* res_bf16, int M, int H, int K, uint16_t* out_bf16, int iters, float* out_us);
 /* The chained kernel alone: out_x[M,384] = LayerNorm(A[M,K1] x W1[384,K1]^T + bias1 + res), out2[M,N2] = epi2(out_x x W2[N2,384]^T + bias2)
  * (epi2: 0 = bias->bf16, 1 = act(bias)->bf16); M <= 128 * number of SMs, N2 <= 1536; iters > 0 additionally times `iters` launches. */
 int kjc_dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const float* bias1, const float* gamma, const float* beta, float eps,

@@ -91,6 +91,7 @@ SIGNATURES = {
     "kjc_index_get_rows": (_i, [_vp, _u64, _u64, _vp]),
     "kjc_index_search": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "kjc_index_search_device_async": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "kjc_index_search_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_topk_merge_device_async": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_index_last_launch_count": (C.c_int64, [_vp]),
     "kjc_index_unverified_count": (C.c_int64, [_vp]),
@@ -99,6 +100,7 @@ SIGNATURES = {
     "kjc_dbg_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_gemm_ln_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kjc_dbg_gemm_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp]),
+    "kjc_dbg_gemm_ln_h": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_ffn_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_gemm_time": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -230,6 +230,16 @@ int kjc_index_search_device_async(KjcIndex* idx, const float* d_queries, int nq,
     KJC_REQUIRE(d_out_scores);
     return guarded([&] { idx->impl.search_device(d_queries, nq, k, mode, d_out_ids, d_out_scores, d_out_counts, static_cast<cudaStream_t>(stream)); });
 }
+int kjc_index_search_device(KjcIndex* idx, const float* d_queries, int nq, int k, int mode, uint64_t* d_out_ids, float* d_out_scores,
+                            int32_t* d_out_counts, void* stream) {
+    KJC_REQUIRE(idx);
+    KJC_REQUIRE(d_queries);
+    KJC_REQUIRE(d_out_ids);
+    KJC_REQUIRE(d_out_scores);
+    return guarded([&] {
+        idx->impl.search_device(d_queries, nq, k, mode, d_out_ids, d_out_scores, d_out_counts, static_cast<cudaStream_t>(stream), /*may_sync=*/true);
+    });
+}
 int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const float* d_cand_scores, int n_lists, int nq, int k,
                                 uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, void* stream) {
     KJC_REQUIRE(d_cand_ids);
@@ -279,7 +289,12 @@ int kjc_dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const 
 int kjc_dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
                     const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* out_us) {
     KJC_REQUIRE(a_bf16); KJC_REQUIRE(w_bf16); KJC_REQUIRE(bias); KJC_REQUIRE(gamma); KJC_REQUIRE(beta); KJC_REQUIRE(res_bf16); KJC_REQUIRE(out_bf16);
-    return guarded([&] { kj::dbg_gemm_ln(a_bf16, w_bf16, bias, gamma, beta, eps, res_bf16, M, K, out_bf16, iters, out_us); });
+    return guarded([&] { kj::dbg_gemm_ln(a_bf16, w_bf16, bias, gamma, beta, eps, res_bf16, M, 384, K, out_bf16, iters, out_us); });
+}
+int kjc_dbg_gemm_ln_h(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
+                      const uint16_t* res_bf16, int M, int H, int K, uint16_t* out_bf16, int iters, float* out_us) {
+    KJC_REQUIRE(a_bf16); KJC_REQUIRE(w_bf16); KJC_REQUIRE(bias); KJC_REQUIRE(gamma); KJC_REQUIRE(beta); KJC_REQUIRE(res_bf16); KJC_REQUIRE(out_bf16);
+    return guarded([&] { kj::dbg_gemm_ln(a_bf16, w_bf16, bias, gamma, beta, eps, res_bf16, M, H, K, out_bf16, iters, out_us); });
 }
 
 int kjc_dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,

@@ -148,15 +148,23 @@ void launch_gemm_pair(int block_n, int epi, const CUtensorMap& ta, const CUtenso
     }
 }
 
-void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
+void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int H, int K, const float* bias, const float* gamma,
                     const float* beta, float eps, int num_sms, cudaStream_t st) {
-    static int configured[64] = {0};
+    static int configured[64] = {0}, configured2[64] = {0};
     if (K % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs K % 8 == 0");
-    ensure_smem_attr(gemm_ln384_kernel, kLnSmemBytes, configured);
     GemmLnParams p;
     p.M = M; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.eps = eps;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
-    launch_pdl(gemm_ln384_kernel, dim3(std::min(m_tiles, num_sms)), dim3(kLnThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
+    if (H == kLnN) {
+        ensure_smem_attr(gemm_ln_kernel<1>, kLnSmemBytes, configured);
+        launch_pdl(gemm_ln_kernel<1>, dim3(std::min(m_tiles, num_sms)), dim3(kLnThreads), kLnSmemBytes, st, ta, tw, t_io, t_io, p);
+    } else if (H == 2 * kLnN) {  // CTA pair per row tile: each CTA owns 384 of the 768 columns, row statistics exchanged through DSMEM
+        ensure_smem_attr(gemm_ln_kernel<2>, kLnSmemBytes, configured2);
+        launch_pdl_cluster(2, gemm_ln_kernel<2>, dim3(2 * std::min(m_tiles, std::max(1, num_sms / 2))), dim3(kLnThreads), kLnSmemBytes, st, ta, tw, t_io,
+                           t_io, p);
+    } else {
+        throw Error(KJC_INVALID_CONFIG, "fused GEMM + LayerNorm supports hidden sizes 384 and 768");
+    }
 }
 
 // GEMM + residual + LayerNorm chained with the next projection of the same 128-row tiles (gemm_ln_gemm.cuh); one tile per CTA
@@ -631,6 +639,8 @@ Encoder::Encoder(const std::string& dir, int device) {
         ld.t_wo = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, bn_h_, kGemmBlockK, 128);
         ld.t_w1 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_, kGemmBlockK, 128);
         ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK, 128);
+        ld.t_wo_ln = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, kLnHalfN, kGemmBlockK, 128);  // GEMM + LN kernels: 192-row boxes
+        ld.t_w2_ln = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, kLnHalfN, kGemmBlockK, 128);
         ld.t_w1_192 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, kLg2BN, kGemmBlockK, 128);      // chained kernels: 192-row boxes
         ld.t_wqkv_192 = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, kLg2BN, kGemmBlockK, 128);
         if (H == kFfH && I % kFfChunk == 0) {
@@ -651,12 +661,13 @@ Encoder::Encoder(const std::string& dir, int device) {
         b_cls_ = has_bcls ? d_f32_ + off_bcls : nullptr;
     }
     // hidden 384: out-proj / FFN-down run as one GEMM + bias + residual + LayerNorm kernel (full rows per CTA)
-    fused_ln_ = (H == kLnN) && !getenv("KJC_NO_FUSED_LN");
+    // hidden 768: the same kernel on a CTA pair per row tile (row statistics exchanged through distributed shared memory)
+    fused_ln_ = (H == kLnN || H == 2 * kLnN) && !getenv("KJC_NO_FUSED_LN");
     // whole-FFN fusion (ffn_fused.cuh) is correct but shared-memory-bandwidth-bound (the 128 x 384 x tile is re-read for every 64
     // intermediate columns): 64-75 us per launch against 35 + 33 us for the two-kernel path, so it is opt-in
-    fused_ffn_ = fused_ln_ && I % kFfChunk == 0 && getenv("KJC_FUSED_FFN") != nullptr;
+    fused_ffn_ = fused_ln_ && H == kFfH && I % kFfChunk == 0 && getenv("KJC_FUSED_FFN") != nullptr;
     // out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next layer's QKV as one launch each (gemm_ln_gemm.cuh)
-    chain_ = fused_ln_ && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
+    chain_ = fused_ln_ && H == kLnN && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
     chain_embed_ = chain_ && getenv("KJC_CHAIN_EMBED") != nullptr;
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
@@ -788,17 +799,17 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         if (chain) {
             // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
             prof_begin(KJC_K_GEMM_FFN_UP, st);
-            launch_gemm_ln_gemm(w.t_ctx16, L.t_wo, w.t_x16_io, w.t_x16, L.t_w1_192, w.t_h16_out32, M, H, L.bo, L.g1, L.be1, eps, I, L.b1,
+            launch_gemm_ln_gemm(w.t_ctx16, L.t_wo_ln, w.t_x16_io, w.t_x16, L.t_w1_192, w.t_h16_out32, M, H, L.bo, L.g1, L.be1, eps, I, L.b1,
                                 EPI_BIAS_ACT_BF16, act_, st);
             prof_end(st);
             // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
             if (li + 1 < layers_.size()) {
                 const LayerDev& Ln = layers_[li + 1];
-                launch_gemm_ln_gemm(w.t_h16, L.t_w2, w.t_x16_io, w.t_x16, Ln.t_wqkv_192, w.t_qkv16_out32, M, I, L.b2, L.g2, L.be2, eps, 3 * H, Ln.bqkv,
+                launch_gemm_ln_gemm(w.t_h16, L.t_w2_ln, w.t_x16_io, w.t_x16, Ln.t_wqkv_192, w.t_qkv16_out32, M, I, L.b2, L.g2, L.be2, eps, 3 * H, Ln.bqkv,
                                     EPI_BIAS_BF16, ACT_NONE, st);
             } else {
-                launch_gemm_ln(w.t_h16, L.t_w2, w.t_x16_io, M, I, L.b2, L.g2, L.be2, eps, sms, st);
+                launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             }
             prof_end(st);
             launches_ += 3;
@@ -807,7 +818,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
         if (fused_ln_) {
             prof_begin(KJC_K_GEMM_OUT, st);
-            launch_gemm_ln(w.t_ctx16, L.t_wo, w.t_x16_io, M, H, L.bo, L.g1, L.be1, eps, sms, st);
+            launch_gemm_ln(w.t_ctx16, L.t_wo_ln, w.t_x16_io, M, H, H, L.bo, L.g1, L.be1, eps, sms, st);
             prof_end(st);
         } else {
             g = GemmParams{};
@@ -838,7 +849,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
         if (fused_ln_) {
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
-            launch_gemm_ln(w.t_h16, L.t_w2, w.t_x16_io, M, I, L.b2, L.g2, L.be2, eps, sms, st);
+            launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             prof_end(st);
         } else {
             g = GemmParams{};
@@ -1159,9 +1170,9 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         if (dR) cudaFree(dR);
 }
 
-// out[M,384] (bf16) = LN(A W^T + bias + residual) with the fused kernel; residual/out bf16 bit patterns.
+// out[M,H] (bf16), H = 384 or 768, = LN(A W^T + bias + residual) with the fused kernel; residual/out bf16 bit patterns.
 void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
-                 const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* us) {
+                 const uint16_t* res_bf16, int M, int H, int K, uint16_t* out_bf16, int iters, float* us) {
     cudaDeviceProp prop;
     int dev = 0;
     KJ_CUDA(cudaGetDevice(&dev));
@@ -1170,29 +1181,29 @@ void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bi
     __nv_bfloat16 *dA, *dW, *dX;
     float *dB, *dG, *dBt;
     KJ_CUDA(cudaMalloc(&dA, Mp * K * 2));
-    KJ_CUDA(cudaMalloc(&dW, static_cast<size_t>(kLnN) * K * 2));
-    KJ_CUDA(cudaMalloc(&dX, Mp * kLnN * 2));
+    KJ_CUDA(cudaMalloc(&dW, static_cast<size_t>(H) * K * 2));
+    KJ_CUDA(cudaMalloc(&dX, Mp * H * 2));
     KJ_CUDA(cudaMemset(dA, 0, Mp * K * 2));
-    KJ_CUDA(cudaMemset(dX, 0, Mp * kLnN * 2));
-    KJ_CUDA(cudaMalloc(&dB, kLnN * 4)); KJ_CUDA(cudaMalloc(&dG, kLnN * 4)); KJ_CUDA(cudaMalloc(&dBt, kLnN * 4));
+    KJ_CUDA(cudaMemset(dX, 0, Mp * H * 2));
+    KJ_CUDA(cudaMalloc(&dB, H * 4)); KJ_CUDA(cudaMalloc(&dG, H * 4)); KJ_CUDA(cudaMalloc(&dBt, H * 4));
     KJ_CUDA(cudaMemcpy(dA, a_bf16, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
-    KJ_CUDA(cudaMemcpy(dW, w_bf16, static_cast<size_t>(kLnN) * K * 2, cudaMemcpyHostToDevice));
-    KJ_CUDA(cudaMemcpy(dX, res_bf16, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyHostToDevice));
-    KJ_CUDA(cudaMemcpy(dB, bias, kLnN * 4, cudaMemcpyHostToDevice));
-    KJ_CUDA(cudaMemcpy(dG, gamma, kLnN * 4, cudaMemcpyHostToDevice));
-    KJ_CUDA(cudaMemcpy(dBt, beta, kLnN * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dW, w_bf16, static_cast<size_t>(H) * K * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dX, res_bf16, static_cast<size_t>(M) * H * 2, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dB, bias, H * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dG, gamma, H * 4, cudaMemcpyHostToDevice));
+    KJ_CUDA(cudaMemcpy(dBt, beta, H * 4, cudaMemcpyHostToDevice));
     CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K, kGemmBlockM, kGemmBlockK, 128);
-    CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kLnN, K, kLnHalfN, kGemmBlockK, 128);
-    CUtensorMap tio = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, 32, kEpiChunkCols, 64);
-    launch_gemm_ln(ta, tw, tio, M, K, dB, dG, dBt, eps, prop.multiProcessorCount, nullptr);
+    CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, K, kLnHalfN, kGemmBlockK, 128);
+    CUtensorMap tio = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, H, 32, kEpiChunkCols, 64);
+    launch_gemm_ln(ta, tw, tio, M, H, K, dB, dG, dBt, eps, prop.multiProcessorCount, nullptr);
     KJ_CUDA(cudaDeviceSynchronize());
-    KJ_CUDA(cudaMemcpy(out_bf16, dX, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyDeviceToHost));
+    KJ_CUDA(cudaMemcpy(out_bf16, dX, static_cast<size_t>(M) * H * 2, cudaMemcpyDeviceToHost));
     if (iters > 0 && us) {  // timing (in place: the values drift, the work does not)
         cudaEvent_t e0, e1;
         KJ_CUDA(cudaEventCreate(&e0));
         KJ_CUDA(cudaEventCreate(&e1));
         KJ_CUDA(cudaEventRecord(e0, nullptr));
-        for (int i = 0; i < iters; ++i) launch_gemm_ln(ta, tw, tio, M, K, dB, dG, dBt, eps, prop.multiProcessorCount, nullptr);
+        for (int i = 0; i < iters; ++i) launch_gemm_ln(ta, tw, tio, M, H, K, dB, dG, dBt, eps, prop.multiProcessorCount, nullptr);
         KJ_CUDA(cudaEventRecord(e1, nullptr));
         KJ_CUDA(cudaDeviceSynchronize());
         float ms = 0.f;

@@ -26,7 +26,7 @@ void launch_ffn_ln(const CUtensorMap& t_x, const CUtensorMap& t_w1, const CUtens
                    const float* b1, const float* b2, const float* gamma, const float* beta, float eps, int act, int num_sms, cudaStream_t st);
 void dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
                 const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* us);
-void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int K, const float* bias, const float* gamma,
+void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_io, int M, int H, int K, const float* bias, const float* gamma,
                     const float* beta, float eps, int num_sms, cudaStream_t st);
 void launch_attention(const AttnParams& p, int head_dim, cudaStream_t st);
 void launch_layernorm(const float* y, const float* g, const float* b, float eps, float* x32, __nv_bfloat16* x16, int M, int H,
@@ -38,7 +38,7 @@ void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const flo
                       const uint16_t* res_bf16, int M, int K1, const uint16_t* w2_bf16, const float* bias2, int N2, int epi2, int act,
                       uint16_t* out_x_bf16, uint16_t* out2_bf16, int iters, float* us);
 void dbg_gemm_ln(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias, const float* gamma, const float* beta, float eps,
-                 const uint16_t* res_bf16, int M, int K, uint16_t* out_bf16, int iters, float* us);
+                 const uint16_t* res_bf16, int M, int H, int K, uint16_t* out_bf16, int iters, float* us);
 float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flags, int iters);
 void dbg_attention(const uint16_t* qkv_bf16, const float* mask, int B, int S, int H, int heads, int nan_if_all_masked, uint16_t* ctx_bf16);
 
@@ -91,6 +91,7 @@ struct LayerDev {
     const float *bqkv, *bo, *b1, *b2, *g1, *be1, *g2, *be2;
     CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
     CUtensorMap t_w1_ffn, t_w1_ffn32, t_w2_ffn;  // fused FFN kernel: W1 boxes of 64 (one CTA) / 32 (CTA pair) rows, W2 boxes of 64 rows
+    CUtensorMap t_wo_ln, t_w2_ln;        // 192-row boxes: weights of the GEMM + residual + LayerNorm kernels (hidden 384 / 768)
     CUtensorMap t_w1_192, t_wqkv_192;    // 192-row boxes: phase-2 weights of the chained GEMM+LN -> GEMM kernel
     CUtensorMap t_wqkv_half, t_w1_half;  // box of block_n/2 rows: the CTA-pair GEMM loads half a weight tile per CTA
 };

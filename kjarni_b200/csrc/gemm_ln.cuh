@@ -1,5 +1,5 @@
-// Projection + bias + residual + LayerNorm in one kernel, for hidden size 384 (MiniLM):
-//     x_out[M,384] (bf16) = LayerNorm( A[M,K] x W[384,K]^T + bias + x_res[M,384] ; gamma, beta, eps )
+// Projection + bias + residual + LayerNorm in one kernel, for hidden size 384 (MiniLM) and 768 (DistilBERT / BERT-base):
+//     x_out[M,H] (bf16) = LayerNorm( A[M,K] x W[H,K]^T + bias + x_res[M,H] ; gamma, beta, eps ),  H = 384 * kCluster
 // Fuses  attention out-proj -> residual add -> LN1   (reference: cpu/encoder/encoder_layer.rs:120-147) and
 //        FFN down-proj      -> residual add -> LN2   (cpu/feedforward/standard_new.rs:76-79, encoder_layer.rs:150-176),
 // i.e. LinearLayer::matmul_noalloc + the scalar residual loop + LayerNorm::forward_noalloc
@@ -14,6 +14,13 @@
 // Variance = E[v^2] - mean^2 in fp32 (clamped at 0): with |mean| <~ 10 sigma its rounding error is ~1e-5 relative,
 // far below the bf16 rounding of the output.  The residual may alias the output (in place): every warp reads its whole
 // region before it writes it.  bias / gamma / beta are staged in shared memory before griddepcontrol.wait.
+//
+// H = 768 (kCluster = 2): a thread-block cluster of two CTAs owns a 128-row tile, CTA `rank` computes columns
+// [384 * rank, 384 * rank + 384) exactly as above (its own 512 TMEM columns on its own SM).  After pass A every epilogue thread
+// stores its row's partial (sum, sum of squares) into the PEER's shared memory (st.shared::cluster) and arrives on the peer's
+// mbarrier with release.cluster; the peer waits with acquire.cluster, so the full-row statistics cost one DSMEM round trip and
+// nothing [M,768]-sized in fp32 ever goes to HBM (round 1 wrote fp32 sums and ran a separate layernorm_kernel).  The peer
+// buffer and its mbarrier are double-buffered by tile parity: a CTA can be at most one exchange ahead of its peer.
 #pragma once
 #include <cuda.h>
 
@@ -42,20 +49,43 @@ constexpr int kLnStageBytes = kLnABytes + kLnBBytes;       // 64 KB
 constexpr int kLnEpiBytesPerWarp = 2 * kEpiStageBytes;     // 2 x 2 KB: residual double buffer, then store double buffer
 constexpr int kLnStatBytes = kLnParts * 128 * 8;           // [part][row] (sum, sum of squares)
 constexpr int kLnVecBytes = 3 * kLnN * 4;                  // bias | gamma | beta
-constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + (kLnAliasEpi ? 0 : kLnEpiWarps * kLnEpiBytesPerWarp) + kLnStatBytes + kLnVecBytes + 512;
+constexpr int kLnPeerStatBytes = 2 * kLnStatBytes;         // the peer CTA's partial sums, double-buffered by tile parity (kCluster = 2)
+constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + (kLnAliasEpi ? 0 : kLnEpiWarps * kLnEpiBytesPerWarp) + kLnStatBytes + kLnPeerStatBytes + kLnVecBytes + 512;
 static_assert(kLnEpiWarps * kLnEpiBytesPerWarp <= kLnStageBytes, "aliased epilogue staging must fit in one ring stage");
 static_assert(kLnSmemBytes <= 232448, "shared memory budget");
 
 struct GemmLnParams {
     int M, K;
-    const float* bias;   // [384] or nullptr
-    const float* gamma;  // [384]
-    const float* beta;   // [384]
+    const float* bias;   // [H] or nullptr
+    const float* gamma;  // [H]
+    const float* beta;   // [H]
     float eps;
 };
 
+// acquire at cluster scope: pairs with the peer's mbarrier.arrive.release.cluster after its st.shared::cluster
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        if (++spins > KJ_MBAR_SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int kCluster>
 __global__ void __launch_bounds__(kLnThreads, 1)
-gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out, GemmLnParams p) {
     extern __shared__ __align__(1024) uint8_t smem_ln[];
     uint8_t* smem = smem_ln;
@@ -66,7 +96,8 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // aliased staging = stage 0 of the W array: 48 KB, exactly 12 warps x 4 KB
     uint8_t* smem_epi = kLnAliasEpi ? smem_b : smem_tail;
     float2* stat = reinterpret_cast<float2*>(smem_tail + (kLnAliasEpi ? 0 : kLnEpiWarps * kLnEpiBytesPerWarp));  // [3][128]
-    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stat) + kLnStatBytes);
+    float2* peer_stat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stat) + kLnStatBytes);  // [2][3][128], written by the peer CTA
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(peer_stat) + kLnPeerStatBytes);
     float* s_gamma = s_bias + kLnN;
     float* s_beta = s_gamma + kLnN;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + kLnN);
@@ -76,7 +107,13 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     uint64_t* tmem_empty = bars + 2 * kLnStages + 1;
     uint64_t* res_bar = bars + 2 * kLnStages + 2;  // [12 warps][2 buffers]
     uint64_t* epi_free = res_bar + 2 * kLnEpiWarps;  // epilogue staging (aliased on the ring) released for the next tile's loads
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(epi_free + 1);
+    uint64_t* xstat_bar = epi_free + 1;              // [2] by tile parity (kCluster = 2): the peer's 384 epilogue threads arrive once per tile
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(xstat_bar + 2);
+    static_assert(kCluster == 1 || kCluster == 2, "one CTA or a CTA pair per row tile");
+    const uint32_t rank = kCluster == 1 ? 0u : cluster_ctarank();
+    const int ncol0 = static_cast<int>(rank) * kLnN;   // this CTA's first output column
+    const int tile0 = kCluster == 1 ? static_cast<int>(blockIdx.x) : static_cast<int>(cluster_id_x());
+    const int tile_step = kCluster == 1 ? static_cast<int>(gridDim.x) : static_cast<int>(cluster_nctaid_x());
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -85,9 +122,9 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
     // weights: independent of the predecessor kernel, staged before griddepcontrol.wait
     for (int i = threadIdx.x; i < kLnN; i += kLnThreads) {
-        s_bias[i] = p.bias != nullptr ? __ldg(p.bias + i) : 0.0f;
-        s_gamma[i] = __ldg(p.gamma + i);
-        s_beta[i] = __ldg(p.beta + i);
+        s_bias[i] = p.bias != nullptr ? __ldg(p.bias + ncol0 + i) : 0.0f;
+        s_gamma[i] = __ldg(p.gamma + ncol0 + i);
+        s_beta[i] = __ldg(p.beta + ncol0 + i);
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -104,11 +141,14 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         mbar_init(tmem_empty, kLnEpiWarps);
         for (int i = 0; i < 2 * kLnEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         mbar_init(epi_free, kLnEpiWarps);
+        mbar_init(&xstat_bar[0], kLnEpiWarps * 32);
+        mbar_init(&xstat_bar[1], kLnEpiWarps * 32);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_base_smem);
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();  // the peer's xstat_bar is initialised before anyone can arrive on it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     pdl_wait();               // everything above overlapped the previous kernel's tail; its outputs are visible from here on
@@ -120,14 +160,14 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < m_tiles; tile += tile_step, ++it) {
                 if (kLnAliasEpi && it > 0) mbar_wait(epi_free, (it - 1) & 1);  // the previous tile's epilogue is done with the ring
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], kLnStageBytes);
                     tma_load_2d(smem_a + stage * kLnABytes, &tmap_a, &full_bar[stage], kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
-                    tma_load_2d(smem_b + stage * kLnBBytes, &tmap_w, &full_bar[stage], kb * kGemmBlockK, 0, kEvictLast);
-                    tma_load_2d(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, &full_bar[stage], kb * kGemmBlockK, kLnHalfN, kEvictLast);
+                    tma_load_2d(smem_b + stage * kLnBBytes, &tmap_w, &full_bar[stage], kb * kGemmBlockK, ncol0, kEvictLast);
+                    tma_load_2d(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, &full_bar[stage], kb * kGemmBlockK, ncol0 + kLnHalfN, kEvictLast);
                     if (++stage == kLnStages) {
                         stage = 0;
                         phase ^= 1;
@@ -142,7 +182,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < m_tiles; tile += tile_step, ++it) {
                 mbar_wait(tmem_empty, (it & 1) ^ 1);  // single accumulator: the previous tile's epilogue must have drained it
                 tc_fence_after();
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -177,7 +217,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int trow = quad * 32 + lane;    // row inside the tile
         uint32_t rphase = 0;                  // bit b = parity of rbar[b]
         int it = 0;
-        for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < m_tiles; tile += tile_step, ++it) {
             const int row0 = tile * kGemmBlockM + quad * 32;
             const int col_base = part * kLnPartCols;
             // the store staging of the previous tile aliases the residual buffers: wait until TMA has read it
@@ -186,7 +226,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     bulk_wait_read<0>();
                     for (int c = 0; c < 2; ++c) {
                         mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
-                        tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
+                        tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], ncol0 + col_base + c * kEpiChunkCols, row0, kEvictFirst);
                     }
                 }
                 __syncwarp();
@@ -236,11 +276,16 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 __syncwarp();  // every lane has read residual buffer b
                 if (lane == 0 && c + 2 < kChunks) {
                     mbar_arrive_expect_tx(&rbar[b], kEpiStageBytes);
-                    tma_load_2d(ebuf + b * kEpiStageBytes, &tmap_res, &rbar[b], col_base + (c + 2) * kEpiChunkCols, row0, kEvictFirst);
+                    tma_load_2d(ebuf + b * kEpiStageBytes, &tmap_res, &rbar[b], ncol0 + col_base + (c + 2) * kEpiChunkCols, row0, kEvictFirst);
                 }
             }
             tmem_st_wait();
             stat[part * 128 + trow] = make_float2(s1, s2);
+            if (kCluster > 1) {  // the same partial sums into the peer's buffer for this tile parity, then a releasing remote arrive
+                const uint32_t peer = rank ^ 1u;
+                st_cluster_f2(mapa_shared(smem_u32(peer_stat + (it & 1) * (kLnParts * 128) + part * 128 + trow), peer), s1, s2);
+                mbar_arrive_cluster(mapa_shared(smem_u32(&xstat_bar[it & 1]), peer));
+            }
             named_bar_sync(1, kLnEpiWarps * 32);
             float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
@@ -249,8 +294,22 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 t1 += t.x;
                 t2 += t.y;
             }
-            const float mean = t1 * (1.0f / kLnN);
-            const float var = fmaxf(t2 * (1.0f / kLnN) - mean * mean, 0.0f);
+            if (kCluster > 1) {
+                mbar_wait_cluster(&xstat_bar[it & 1], (it >> 1) & 1);
+                float u1 = 0.0f, u2 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < kLnParts; ++q) {
+                    const float2 t = peer_stat[(it & 1) * (kLnParts * 128) + q * 128 + trow];
+                    u1 += t.x;
+                    u2 += t.y;
+                }
+                // rank 0 adds (own + peer), rank 1 (peer + own): both CTAs use the same column order, hence the same statistics
+                t1 = rank == 0 ? t1 + u1 : u1 + t1;
+                t2 = rank == 0 ? t2 + u2 : u2 + t2;
+            }
+            constexpr float kInvN = 1.0f / (kLnN * kCluster);
+            const float mean = t1 * kInvN;
+            const float var = fmaxf(t2 * kInvN - mean * mean, 0.0f);
             const float rstd = 1.0f / sqrtf(var + p.eps);
             const float nmr = -mean * rstd;
 
@@ -266,7 +325,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty);
                 }
-                const int col0 = col_base + c * kEpiChunkCols;
+                const int col0 = col_base + c * kEpiChunkCols;  // within this CTA's 384 columns
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -289,14 +348,14 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_2d(&tmap_out, buf, col0, row0);
+                    tma_store_2d(&tmap_out, buf, ncol0 + col0, row0);
                     bulk_commit();
                 }
                 sbuf ^= 1;
             }
             // the stat exchange of the next tile happens after its tmem_full wait, i.e. after every warp of this tile has
             // passed the barrier above and read stat[]: no extra sync is needed before stat[] is overwritten.
-            if (kLnAliasEpi && tile + static_cast<int>(gridDim.x) < m_tiles) {  // hand the ring back to the producer
+            if (kLnAliasEpi && tile + tile_step < m_tiles) {  // hand the ring back to the producer
                 if (lane == 0) {
                     bulk_wait_read<0>();
                     mbar_arrive(epi_free);
@@ -309,6 +368,7 @@ gemm_ln384_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (kCluster > 1) cluster_sync_all();  // no CTA exits while its peer may still write into its shared memory
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);

@@ -67,7 +67,7 @@ void Index::compute_norms(uint64_t row0, uint64_t n, cudaStream_t st) {
 }
 
 void Index::add_rows_host(const float* rows, uint64_t n) {
-    std::lock_guard<std::mutex> lock(mu_);
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     if (len_ + n > cap_) throw Error(KJC_INVALID_CONFIG, "index shard capacity exceeded");
     KJ_CUDA(cudaSetDevice(device_));
     // chunked pinned staging (true async DMA, bounded host memory)
@@ -116,7 +116,7 @@ void Index::load_vectors_bin_range(const std::string& path, uint64_t row0, uint6
 }
 
 void Index::append_synthetic(uint32_t seed, uint64_t row0, uint64_t n) {
-    std::lock_guard<std::mutex> lock(mu_);
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     if (len_ + n > cap_) throw Error(KJC_INVALID_CONFIG, "index shard capacity exceeded");
     KJ_CUDA(cudaSetDevice(device_));
     const size_t total = n * dim_;
@@ -136,6 +136,7 @@ void Index::append_synthetic(uint32_t seed, uint64_t row0, uint64_t n) {
 }
 
 void Index::get_rows(uint64_t row, uint64_t n, float* out) const {
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     if (row + n > len_) throw Error(KJC_INVALID_CONFIG, "Document ID out of range");
     KJ_CUDA(cudaSetDevice(device_));
     KJ_CUDA(cudaMemcpy(out, rows_ + row * dim_, n * dim_ * sizeof(float), cudaMemcpyDeviceToHost));
@@ -178,7 +179,7 @@ void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d
     if (nq < 1) throw Error(KJC_INVALID_CONFIG, "nq must be >= 1");
     if (k < 1 || k > 256) throw Error(KJC_INVALID_CONFIG, "k must be in [1, 256]");
     if (mode != SCAN_SEGMENT && mode != SCAN_VECTORSTORE) throw Error(KJC_INVALID_CONFIG, "unknown scan mode");
-    std::lock_guard<std::mutex> lock(mu_);
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     KJ_CUDA(cudaSetDevice(device_));
     if (!st) st = stream_;
     launches_ = 0;
@@ -188,7 +189,7 @@ void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d
 }
 
 int64_t Index::unverified_count() {
-    std::lock_guard<std::mutex> lock(mu_);
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     if (!d_nflag_) return 0;
     KJ_CUDA(cudaSetDevice(device_));
     int32_t v[2] = {0, 0};
@@ -198,7 +199,7 @@ int64_t Index::unverified_count() {
 }
 
 void Index::set_filter(float eps, int min_queries) {
-    std::lock_guard<std::mutex> lock(mu_);
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     filter_eps_ = eps;
     filter_min_q_ = std::max(1, min_queries);
 }
@@ -212,6 +213,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
     static int configured[64] = {0};
     static const int env_R = getenv("KJC_SG_R") ? std::max(1, atoi(getenv("KJC_SG_R"))) : 3;
     static const int env_dbg = getenv("KJC_SG_DBG") ? atoi(getenv("KJC_SG_DBG")) : 0;
+    static const bool env_no_seed = getenv("KJC_SG_NO_SEED") != nullptr;
     ensure_smem_attr(scan_gemm_kernel, kSgSmemBytes, configured);
     const uint32_t n_tiles = static_cast<uint32_t>((len_ + kSgRows - 1) / kSgRows);
     const int grid = static_cast<int>(std::min<uint32_t>(num_sms_, n_tiles));
@@ -282,7 +284,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         sp.seed_chunks = 0; sp.D = dim_; sp.Q = nq; sp.R = env_R; sp.dbg = env_dbg;
         // ---- seed pass
         int seed_groups = 0;
-        if (len_ > static_cast<uint64_t>(kSgCap) && !getenv("KJC_SG_NO_SEED")) {
+        if (len_ > static_cast<uint64_t>(kSgCap) && !env_no_seed) {
             ScanGemmParams ss = sp;
             ss.seed_max = d_seed;
             int sgrid;
@@ -400,10 +402,12 @@ void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_
 void Index::search_host(const float* q, int nq, int k, int mode, uint64_t* ids, float* scores, int32_t* counts) {
     if (nq < 1) throw Error(KJC_INVALID_CONFIG, "nq must be >= 1");
     if (k < 1 || k > 256) throw Error(KJC_INVALID_CONFIG, "k must be in [1, 256]");
+    // the staging buffers (d_q_, d_out_*) are shared by every caller of this handle: one lock from the H2D copy of the queries to
+    // the synchronise after the D2H copies, so that two host threads cannot overwrite each other's queries or read each other's results
+    std::lock_guard<std::recursive_mutex> lock(mu_);
     KJ_CUDA(cudaSetDevice(device_));
     const size_t qe = static_cast<size_t>(nq) * dim_, oe = static_cast<size_t>(nq) * k;
     {
-        std::lock_guard<std::mutex> lock(mu_);
         if (qe > q_cap_) {
             if (d_q_) cudaFree(d_q_);
             KJ_CUDA(cudaMalloc(&d_q_, qe * 4));

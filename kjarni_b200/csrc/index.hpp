@@ -45,7 +45,7 @@ class Index {
     int dim_;
     uint64_t cap_, id_base_, len_ = 0;
     int device_, num_sms_ = 0;
-    std::mutex mu_;
+    mutable std::recursive_mutex mu_;  // one lock per handle call, held from staging-in to the final synchronise (kjarni_cuda.h: calls on one handle are serialised)
     cudaStream_t stream_ = nullptr;
     float *rows_ = nullptr, *norms_ = nullptr;
     float *d_q_ = nullptr, *d_qn_ = nullptr, *d_cand_s_ = nullptr, *d_out_s_ = nullptr;

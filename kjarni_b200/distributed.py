@@ -60,8 +60,10 @@ class DistributedIndex:
         ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
         sc = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
         stream = torch.cuda.current_stream().cuda_stream
-        N.check(N.lib().kjc_index_search_device_async(self.shard._h, queries.data_ptr(), nq, k, mode, ids.data_ptr(), sc.data_ptr(),
-                                                      None, stream if stream else None))
+        # the synchronising entry: queries the tensor-core filter cannot prove are re-run on the exact scan, so the merged result is
+        # the exact top-k in every case (IndexReader::search_semantic is exact)
+        N.check(N.lib().kjc_index_search_device(self.shard._h, queries.data_ptr(), nq, k, mode, ids.data_ptr(), sc.data_ptr(),
+                                                None, stream if stream else None))
         return ids, sc
 
     def _merge(self, g_ids, g_sc, nq: int, k: int):

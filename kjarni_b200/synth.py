@@ -31,7 +31,11 @@ ARCHS = {
     "tiny-bert": ("bert", 64, 2, 4, 256, 1000, 64, 2, 0),
     "tiny-cross-encoder": ("bert_prefixed", 64, 2, 4, 256, 1000, 64, 2, 1),
     "tiny-distilbert": ("distilbert", 128, 2, 2, 512, 1000, 64, 0, 2),
+    # same shape as tiny-cross-encoder with wider-initialised layer weights (ARCH_STD): the token content reaches the CLS row, so
+    # candidate scores are spread far beyond the bf16 error and rank-order checks have clearly separated pairs to decide
+    "tiny-reranker": ("bert_prefixed", 64, 2, 4, 256, 1000, 64, 2, 1),
 }
+ARCH_STD = {"tiny-reranker": 0.15}  # std of the projection weights (default 0.02)
 
 
 def write_safetensors(path: str, tensors: Dict[str, np.ndarray]) -> None:
@@ -57,7 +61,10 @@ def make_weights(arch: str, seed: int = 1234) -> Tuple[Dict[str, np.ndarray], di
     rng = np.random.default_rng(seed)
     t: Dict[str, np.ndarray] = {}
 
-    def mat(*shape, std=0.02):
+    wstd = ARCH_STD.get(arch, 0.02)
+
+    def mat(*shape, std=None):
+        std = wstd if std is None else std
         return (rng.standard_normal(shape) * std).astype(np.float32)
 
     def bias(n):

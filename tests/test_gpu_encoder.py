@@ -21,7 +21,7 @@ COS_MIN, MAXABS = 0.9995, 2e-2
 def dirs(tmp_path_factory):
     root = tmp_path_factory.mktemp("models")
     return {a: synth.write_model_dir(str(root / a), a) for a in
-            ("tiny-bert", "tiny-cross-encoder", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2",
+            ("tiny-bert", "tiny-cross-encoder", "tiny-reranker", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2",
              "tiny-roberta", "tiny-mpnet", "distilroberta-emotion", "mpnet-base")}
 
 
@@ -71,7 +71,7 @@ def test_embedding_matches_hf_goldens(dirs):
         enc.close()
 
 
-@pytest.mark.parametrize("arch,B,S,pair", [("tiny-distilbert", 6, 16, False), ("tiny-cross-encoder", 6, 16, True),
+@pytest.mark.parametrize("arch,B,S,pair", [("tiny-distilbert", 6, 16, False), ("tiny-cross-encoder", 6, 16, True), ("tiny-reranker", 6, 16, True),
                                            ("distilbert-sst2", 16, 128, False), ("minilm-l6-cross-encoder", 48, 256, True),
                                            ("tiny-roberta", 6, 16, False), ("distilroberta-emotion", 8, 128, False)])
 def test_logits_match_oracle(dirs, arch, B, S, pair):
@@ -102,7 +102,9 @@ def test_logits_match_oracle(dirs, arch, B, S, pair):
         err = float(np.abs(got - want).max())
         w0 = want[:, 0]
         decided = (w0[:, None] - w0[None, :]) > 4 * err + 1e-6  # i clearly ahead of j
-        assert decided.sum() >= (B if B >= 32 else 1), (decided.sum(), err)  # tiny models: few clearly separated pairs
+        # tiny-cross-encoder (init std 0.02) scores its candidates within a few errors of each other; tiny-reranker and the full-size
+        # model have clearly separated pairs
+        assert decided.sum() >= (1 if arch == "tiny-cross-encoder" else B), (decided.sum(), err)
         ii, jj = np.nonzero(decided)
         assert (rank_g[ii] < rank_g[jj]).all()
         # and the returned order is the stable descending sort of the returned scores

@@ -121,7 +121,7 @@ def models(tmp_path_factory):
     cache = tmp_path_factory.mktemp("kjarni-cache")
     out = {"cache": str(cache)}
     for arch, sub in (("tiny-bert", "sentence-transformers_all-MiniLM-L6-v2"), ("tiny-distilbert", "distilbert_distilbert-base-uncased-finetuned-sst-2-english"),
-                      ("tiny-cross-encoder", "cross-encoder_ms-marco-MiniLM-L-6-v2")):
+                      ("tiny-reranker", "cross-encoder_ms-marco-MiniLM-L-6-v2")):
         d = synth.write_model_dir(str(cache / sub), arch)
         shutil.copy(TOK, os.path.join(d, "tokenizer.json"))
         out[arch] = d
@@ -242,7 +242,7 @@ def test_reranker_matches_oracle(ffi, models):
     tok = api.Tokenizer(TOK, 64)
     ids, mask, types = tok.encode_batch([query] * len(docs), docs)
     assert types.max() == 1  # [CLS] q [SEP] d [SEP] with type ids 0 / 1
-    m = ko.load_model_dir(models["tiny-cross-encoder"])
+    m = ko.load_model_dir(models["tiny-reranker"])
     want = ko.predict_logits(m, ids, mask, types)[:, 0]
     res = RerankResults()
     assert ffi.kjarni_reranker_rerank(h, query.encode(), strs(docs), len(docs), C.byref(res)) == 0 and res.len == len(docs)
@@ -257,7 +257,7 @@ def test_reranker_matches_oracle(ffi, models):
     rank = np.empty(len(docs), np.int64)
     rank[np.asarray(idx)] = np.arange(len(docs))
     decided = (want[:, None] - want[None, :]) > 4 * err + 1e-6
-    assert decided.sum() >= 1
+    assert decided.sum() >= len(docs), (decided.sum(), err)  # tiny-reranker spreads its scores: most pairs are clearly separated
     ii, jj = np.nonzero(decided)
     assert (rank[ii] < rank[jj]).all()
     assert ffi.kjarni_reranker_rerank_top_k(h, query.encode(), strs(docs), len(docs), 3, C.byref(res)) == 0 and res.len == 3
@@ -316,10 +316,29 @@ def test_searcher_semantic_search_over_an_index_directory(ffi, models, tmp_path)
     o.threshold = 0.999
     assert ffi.kjarni_searcher_search_with_options(h, root.encode(), docs[2].encode(), C.byref(o), C.byref(res)) == 0 and res.len == 1
     ffi.kjarni_search_results_free(C.byref(res))
-    # keyword / hybrid stay with the CPU host; missing index; dimension mismatch
-    o = ffi.kjarni_search_options_default()
-    o.mode = 2
-    assert ffi.kjarni_searcher_search_with_options(h, root.encode(), b"x", C.byref(o), C.byref(res)) == 7 and res.len == 0
+    # keyword mode (0): BM25 over the segments' bm25.bin, per-segment top-k -> stable merge (index_reader.rs:230-245)
+    def hits(mode, query, top_k):
+        oo = ffi.kjarni_search_options_default()
+        oo.mode, oo.top_k = mode, top_k
+        assert ffi.kjarni_searcher_search_with_options(h, root.encode(), query.encode(), C.byref(oo), C.byref(res)) == 0, ffi.kjarni_last_error_message()
+        out = [(res.results[i].document_id, res.results[i].score) for i in range(res.len)]
+        ffi.kjarni_search_results_free(C.byref(res))
+        return out
+
+    kq = "ranking the vector index"
+    want_kw = ko.index_search_keywords([docs[:5], docs[5:]], kq, 4)
+    got_kw = hits(0, kq, 4)
+    assert [d for d, _ in got_kw] == [d for d, _ in want_kw] and len(got_kw) >= 2
+    assert np.allclose([v for _, v in got_kw], [v for _, v in want_kw], rtol=1e-5)
+    # hybrid mode (2, the default of the reference's SearcherConfig): 2 x limit keyword and semantic hits fused by reciprocal rank
+    # (index_reader.rs:248-289, hybrid.rs:3-31); the semantic half is this library's own GPU scan, the fusion is checked against the oracle
+    top_k = 4
+    sem = hits(1, kq, 2 * top_k)
+    want_h = ko.rrf_hybrid(ko.index_search_keywords([docs[:5], docs[5:]], kq, 2 * top_k), sem, top_k)
+    got_h = hits(2, kq, top_k)
+    assert [d for d, _ in got_h] == [d for d, _ in want_h]
+    assert np.allclose([v for _, v in got_h], [v for _, v in want_h], rtol=1e-6)
+    # missing index; dimension mismatch
     assert ffi.kjarni_searcher_search(h, str(tmp_path / "nope").encode(), b"x", C.byref(res)) == 3
     bad = synth.write_index_dir(str(tmp_path / "idx32"), [np.ones((3, 32), np.float32)])
     assert ffi.kjarni_searcher_search(h, bad.encode(), b"x", C.byref(res)) == 7 and b"Dimension mismatch" in ffi.kjarni_last_error_message()

@@ -107,14 +107,15 @@ def test_gemm_activations(act):
     assert (np.abs(got - want) / (1.0 + np.abs(want))).max() < 2 * tol
 
 
-@pytest.mark.parametrize("M,K", [(128, 384), (1000, 384), (300, 1536), (18944, 384), (77, 64),
-                                 (37965, 384), (56900, 128), (19000, 1536)])  # more row tiles than SMs: the ring <-> epilogue hand-back
-def test_fused_gemm_residual_layernorm(M, K):
-    """out-proj / FFN-down + bias + residual + LayerNorm in one kernel (hidden 384) vs the oracle's LayerNorm on fp32 sums."""
+@pytest.mark.parametrize("M,K,H", [(128, 384, 384), (1000, 384, 384), (300, 1536, 384), (18944, 384, 384), (77, 64, 384),
+                                   (37965, 384, 384), (56900, 128, 384), (19000, 1536, 384),  # more row tiles than SMs: the ring <-> epilogue hand-back
+                                   # hidden 768: a CTA pair per row tile, row statistics exchanged through distributed shared memory
+                                   (128, 768, 768), (77, 64, 768), (1000, 3072, 768), (18944, 768, 768), (19000, 128, 768), (40000, 768, 768)])
+def test_fused_gemm_residual_layernorm(M, K, H):
+    """out-proj / FFN-down + bias + residual + LayerNorm in one kernel (hidden 384 / 768) vs the oracle's LayerNorm on fp32 sums."""
     import ctypes as C
 
-    rng = np.random.default_rng(M + K)
-    H = 384
+    rng = np.random.default_rng(M + K + H)
     a = rng.standard_normal((M, K)).astype(np.float32)
     w = (rng.standard_normal((H, K)) / math.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(H).astype(np.float32) * 0.1
@@ -123,8 +124,8 @@ def test_fused_gemm_residual_layernorm(M, K):
     res = rng.standard_normal((M, H)).astype(np.float32)
     out = np.empty((M, H), np.uint16)
     us = C.c_float()
-    N.check(N.lib().kjc_dbg_gemm_ln(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w)), ptr(bias), ptr(gamma), ptr(beta), 1e-12,
-                                    ptr(to_bf16_bits(res)), M, K, ptr(out), 0, C.byref(us)))
+    N.check(N.lib().kjc_dbg_gemm_ln_h(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w)), ptr(bias), ptr(gamma), ptr(beta), 1e-12,
+                                      ptr(to_bf16_bits(res)), M, H, K, ptr(out), 0, C.byref(us)))
     got = from_bf16_bits(out)
     y = (bf16_round(a).astype(np.float64) @ bf16_round(w).astype(np.float64).T + bias + bf16_round(res)).astype(np.float32)
     want = ko.layer_norm(y, gamma, beta, 1e-12)
