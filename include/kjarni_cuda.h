@@ -98,6 +98,15 @@ typedef struct KjcEncoderInfo {
  * tensor, shape mismatch), KJC_INVALID_CONFIG (bad config.json / unsupported sizes),
  * KJC_GPU_UNAVAILABLE (no device / not sm_100). */
 int kjc_encoder_create(const char* model_dir, int device, KjcEncoder** out);
+/* The same handle type backed by ONE WEIGHT REPLICA PER DEVICE of `device_ids[0..n_devices)`, inside this process (the Rust / C# /
+ * Go hosts have no torchrun): one persistent host thread, stream and pinned staging slice per GPU.  kjc_encoder_forward splits a
+ * host batch by contiguous rows over the replicas -- sequences are independent (KT/cpu/encoder/traits.rs:66-139), so there is NO
+ * collective and the rows are bit-identical to a one-GPU forward of the same batch.  The device-pointer entry
+ * (kjc_encoder_forward_device_async), profiling and the debug hooks address replica 0.
+ * A device may be listed more than once (several replicas on one GPU; only useful for testing the split on a one-GPU box).
+ * Errors: as kjc_encoder_create, plus KJC_INVALID_CONFIG for an empty list. */
+int kjc_encoder_create_multi(const char* model_dir, const int* device_ids, int n_devices, KjcEncoder** out);
+int kjc_encoder_device_count(const KjcEncoder* enc);
 void kjc_encoder_destroy(KjcEncoder* enc);
 int kjc_encoder_info(const KjcEncoder* enc, KjcEncoderInfo* out);
 /* Label `i` of config.json:id2label (sorted by numeric key), or NULL. Borrowed; valid until destroy.
@@ -276,6 +285,32 @@ int64_t kjc_index_last_launch_count(const KjcIndex* idx);
  * on the exact scan by kjc_index_search (which may synchronise); kjc_index_search_device_async cannot synchronise and
  * counts such queries here instead (synchronises the device; 0 = every async result so far was proven exact). */
 int64_t kjc_index_unverified_count(KjcIndex* idx);
+
+/* ---- row-sharded index over several devices of one process -------------------------------------------------------------
+ * Contiguous row shards, shard p on device_ids[p] holds global rows [lo_p, hi_p) (kjc_index_part_range; global id = shard base +
+ * local id, KR/index_reader.rs:313-319).  A search runs the same query batch on every shard concurrently (one host thread per
+ * GPU; per-shard results are always exact, see kjc_index_search_device), gathers the per-shard [nq,k] candidates on
+ * device_ids[0] with peer copies over NVLink (12 B per candidate) and merges them with the merge kernel: the per-segment top-k ->
+ * concat -> sort -> truncate of IndexReader::search_semantic (KR/index_reader.rs:207-228).  Ids, scores, order (score desc, id
+ * asc) and counts are those of one shard holding all the rows. */
+typedef struct KjcShardedIndex KjcShardedIndex;
+/* Empty index of `capacity_rows` rows in total; rows arrive in global-id order (add_rows / append_synthetic). */
+int kjc_sharded_index_create(int dim, uint64_t capacity_rows, const int* device_ids, int n_devices, KjcShardedIndex** out);
+/* IndexReader::open (KR/index_reader.rs:161-204) with the rows of the on-disk index split over the devices. */
+int kjc_sharded_index_open_dir(const char* root, const int* device_ids, int n_devices, KjcShardedIndex** out);
+void kjc_sharded_index_destroy(KjcShardedIndex* idx);
+uint64_t kjc_sharded_index_len(const KjcShardedIndex* idx);
+int kjc_sharded_index_dim(const KjcShardedIndex* idx);
+int kjc_sharded_index_shards(const KjcShardedIndex* idx);
+uint64_t kjc_sharded_index_shard_len(const KjcShardedIndex* idx, int shard);
+int kjc_sharded_index_add_rows(KjcShardedIndex* idx, const float* rows, uint64_t n);
+/* Appends the next `n` rows of the deterministic synthetic sequence of `seed` (row g of the index = synthetic row g). */
+int kjc_sharded_index_append_synthetic(KjcShardedIndex* idx, uint32_t seed, uint64_t n);
+/* Same outputs as kjc_index_search, over all shards. */
+int kjc_sharded_index_search(KjcShardedIndex* idx, const float* queries, int nq, int k, int mode, uint64_t* out_ids, float* out_scores,
+                             int32_t* out_counts);
+/* Launches of the last search summed over the shards + the merge. */
+int64_t kjc_sharded_index_last_launch_count(const KjcShardedIndex* idx);
 
 /* cosine of two host vectors (kjarni_cosine_similarity, KF/src/lib.rs:177-188 -> KS/vector.rs:131-148). */
 float kjc_cosine_similarity(const float* a, const float* b, size_t len);

@@ -23,6 +23,10 @@ int kjc_dbg_gemm_ln_h(const uint16_t* a_bf16, const uint16_t* w_bf16, const floa
 int kjc_dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const float* bias1, const float* gamma, const float* beta, float eps,
                          const uint16_t* res_bf16, int M, int K1, const uint16_t* w2_bf16, const float* bias2, int N2, int epi2, int act,
                          uint16_t* out_x_bf16, uint16_t* out2_bf16, int iters, float* out_us);
+/* 1 if the library was built with -DKJ_EXPERIMENTAL_KERNELS (the CTA-pair GEMM and the whole-FFN fusion, both slower than the
+ * default path, are then available to kjc_dbg_gemm(block_n + 1000) / kjc_dbg_ffn_ln / KJC_PAIR_GEMM / KJC_FUSED_FFN); else those
+ * entries return KJC_INVALID_CONFIG. */
+int kjc_dbg_experimental_kernels(void);
 /* out[M,384] (bf16) = LayerNorm(x + act(x W1^T + b1) W2^T + b2) with the fused feed-forward kernel; W1 [I,384], W2 [384,I];
  * iters > 0 additionally times `iters` launches (average us in *out_us). */
 int kjc_dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,

@@ -60,6 +60,8 @@ SIGNATURES = {
     "kjc_version": (C.c_char_p, []),
     "kjc_device_count": (_i, []),
     "kjc_encoder_create": (_i, [C.c_char_p, _i, C.POINTER(_vp)]),
+    "kjc_encoder_create_multi": (_i, [C.c_char_p, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "kjc_encoder_device_count": (_i, [_vp]),
     "kjc_encoder_destroy": (None, [_vp]),
     "kjc_encoder_info": (_i, [_vp, C.POINTER(KjcEncoderInfo)]),
     "kjc_encoder_label": (C.c_char_p, [_vp, _i]),
@@ -94,6 +96,17 @@ SIGNATURES = {
     "kjc_index_search_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_topk_merge_device_async": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_index_last_launch_count": (C.c_int64, [_vp]),
+    "kjc_sharded_index_create": (_i, [_i, _u64, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "kjc_sharded_index_open_dir": (_i, [C.c_char_p, C.POINTER(_i), _i, C.POINTER(_vp)]),
+    "kjc_sharded_index_destroy": (None, [_vp]),
+    "kjc_sharded_index_len": (_u64, [_vp]),
+    "kjc_sharded_index_dim": (_i, [_vp]),
+    "kjc_sharded_index_shards": (_i, [_vp]),
+    "kjc_sharded_index_shard_len": (_u64, [_vp, _i]),
+    "kjc_sharded_index_add_rows": (_i, [_vp, _vp, _u64]),
+    "kjc_sharded_index_append_synthetic": (_i, [_vp, C.c_uint32, _u64]),
+    "kjc_sharded_index_search": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "kjc_sharded_index_last_launch_count": (C.c_int64, [_vp]),
     "kjc_index_unverified_count": (C.c_int64, [_vp]),
     "kjc_dbg_index_set_filter": (_i, [_vp, _f, _i]),
     "kjc_cosine_similarity": (_f, [_vp, _vp, C.c_size_t]),
@@ -101,6 +114,7 @@ SIGNATURES = {
     "kjc_dbg_gemm_ln_gemm": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "kjc_dbg_gemm_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_gemm_ln_h": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "kjc_dbg_experimental_kernels": (_i, []),
     "kjc_dbg_ffn_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp, _i, _vp]),
     "kjc_dbg_gemm_time": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "kjc_dbg_attention": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

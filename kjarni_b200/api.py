@@ -35,11 +35,17 @@ def _c(a, dtype) -> np.ndarray:
 
 
 class EncoderModel:
-    """One encoder checkpoint resident on one GPU (KjcEncoder)."""
+    """One encoder checkpoint resident on one GPU, or one replica per GPU of `devices` (KjcEncoder; a host batch is then split by
+    contiguous rows over the replicas inside the library, no collective)."""
 
-    def __init__(self, model_dir: str, device: int = 0):
+    def __init__(self, model_dir: str, device: int = 0, devices: Optional[Sequence[int]] = None):
         self._h = C.c_void_p()
-        N.check(N.lib().kjc_encoder_create(str(model_dir).encode(), int(device), C.byref(self._h)))
+        if devices is None:
+            N.check(N.lib().kjc_encoder_create(str(model_dir).encode(), int(device), C.byref(self._h)))
+        else:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            N.check(N.lib().kjc_encoder_create_multi(str(model_dir).encode(), arr, len(devices), C.byref(self._h)))
+        self.n_devices = int(N.lib().kjc_encoder_device_count(self._h))
         info = N.KjcEncoderInfo()
         N.check(N.lib().kjc_encoder_info(self._h, C.byref(info)))
         self.info = info
@@ -181,6 +187,71 @@ def scores_to_top_k(probs: np.ndarray, labels: Sequence[str], k: int) -> List[Tu
     """Stable sort descending => ties resolve to the lowest label index (KM/models/sequence_classifier/mod.rs:369-390)."""
     order = np.argsort(-np.asarray(probs, np.float32), kind="stable")[:k]
     return [(labels[i] if i < len(labels) else f"LABEL_{i}", float(probs[i])) for i in order]
+
+
+class ShardedIndex:
+    """The whole index row-sharded over the GPUs of `devices` inside this process (KjcShardedIndex): per-shard exact top-k, peer-copy
+    candidate gather on devices[0], merge kernel -- IndexReader::search_semantic over all rows (KR/index_reader.rs:207-228)."""
+
+    def __init__(self, dim: int, capacity_rows: int, devices: Sequence[int], mode: int = N.SCAN_SEGMENT):
+        self._h = C.c_void_p()
+        self.mode = mode
+        self.dim = dim
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        N.check(N.lib().kjc_sharded_index_create(int(dim), int(capacity_rows), arr, len(devices), C.byref(self._h)))
+
+    @classmethod
+    def open_dir(cls, root: str, devices: Sequence[int]) -> "ShardedIndex":
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.mode = N.SCAN_SEGMENT
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        N.check(N.lib().kjc_sharded_index_open_dir(str(root).encode(), arr, len(devices), C.byref(self._h)))
+        self.dim = int(N.lib().kjc_sharded_index_dim(self._h))
+        return self
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().kjc_sharded_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(N.lib().kjc_sharded_index_len(self._h))
+
+    @property
+    def shard_lens(self) -> List[int]:
+        return [int(N.lib().kjc_sharded_index_shard_len(self._h, p)) for p in range(int(N.lib().kjc_sharded_index_shards(self._h)))]
+
+    def add_rows(self, rows) -> None:
+        rows = _c(rows, np.float32)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise ValueError("rows must be [n, dim]")
+        N.check(N.lib().kjc_sharded_index_add_rows(self._h, _ptr(rows), rows.shape[0]))
+
+    def append_synthetic(self, seed: int, n: int) -> None:
+        N.check(N.lib().kjc_sharded_index_append_synthetic(self._h, int(seed), int(n)))
+
+    def search_batch(self, queries, k: int, mode: Optional[int] = None):
+        """(ids u64 [Q,k] global, scores f32 [Q,k], counts i32 [Q]); order (score desc, id asc)."""
+        q = _c(queries, np.float32)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError("queries must be [nq, dim]")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), np.uint64)
+        sc = np.empty((nq, k), np.float32)
+        cnt = np.empty((nq,), np.int32)
+        N.check(N.lib().kjc_sharded_index_search(self._h, _ptr(q), nq, int(k), self.mode if mode is None else mode, _ptr(ids), _ptr(sc), _ptr(cnt)))
+        return ids, sc, cnt
+
+    @property
+    def last_launches(self) -> int:
+        return int(N.lib().kjc_sharded_index_last_launch_count(self._h))
 
 
 class IndexShard:

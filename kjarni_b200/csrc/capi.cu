@@ -3,7 +3,7 @@
 // (same contract as kjarni-ffi/src/error.rs:7-101 in the reference).
 #include <cmath>
 
-#include "index.hpp"
+#include "multi.hpp"
 #include "../../include/kjarni_cuda_debug.h"
 
 namespace kj {
@@ -11,7 +11,16 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 }  // namespace kj
 
-struct KjcEncoder { kj::Encoder impl; KjcEncoder(const char* d, int dev) : impl(d, dev) {} };
+struct KjcEncoder {
+    kj::EncoderGroup grp;  // one replica (kjc_encoder_create) or one per device (kjc_encoder_create_multi)
+    kj::Encoder& impl;     // replica 0: info, labels, device-pointer entry, profiling, debug hooks
+    KjcEncoder(const char* d, const int* devs, int n) : grp(d, devs, n), impl(grp.replica(0)) {}
+};
+struct KjcShardedIndex {
+    kj::ShardedIndex impl;
+    KjcShardedIndex(int dim, uint64_t cap, const int* devs, int n) : impl(dim, cap, devs, n) {}
+    KjcShardedIndex(const char* root, const int* devs, int n) : impl(std::string(root), devs, n) {}
+};
 struct KjcIndex {
     std::unique_ptr<kj::Index> own;
     kj::Index& impl;
@@ -78,8 +87,16 @@ int kjc_encoder_create(const char* model_dir, int device, KjcEncoder** out) {
     KJC_REQUIRE(out);
     *out = nullptr;
     KJC_REQUIRE(model_dir);
-    return guarded([&] { *out = new KjcEncoder(model_dir, device); });
+    return guarded([&] { *out = new KjcEncoder(model_dir, &device, 1); });
 }
+int kjc_encoder_create_multi(const char* model_dir, const int* device_ids, int n_devices, KjcEncoder** out) {
+    KJC_REQUIRE(out);
+    *out = nullptr;
+    KJC_REQUIRE(model_dir);
+    KJC_REQUIRE(device_ids);
+    return guarded([&] { *out = new KjcEncoder(model_dir, device_ids, n_devices); });
+}
+int kjc_encoder_device_count(const KjcEncoder* enc) { return enc ? enc->grp.size() : 0; }
 void kjc_encoder_destroy(KjcEncoder* enc) { delete enc; }
 int kjc_encoder_info(const KjcEncoder* enc, KjcEncoderInfo* out) {
     KJC_REQUIRE(enc);
@@ -98,7 +115,7 @@ int kjc_encoder_forward(KjcEncoder* enc, const uint32_t* ids, const float* mask,
     KJC_REQUIRE(ids);
     KJC_REQUIRE(out);
     const KjcForwardOptions o = opts ? *opts : default_opts();
-    return guarded([&] { enc->impl.forward_host(ids, mask, type_ids, batch, seq_len, o, out); });
+    return guarded([&] { enc->grp.forward_host(ids, mask, type_ids, batch, seq_len, o, out); });
 }
 int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_type_ids, int batch,
                                      int seq_len, const KjcForwardOptions* opts, float* d_out, void* stream) {
@@ -110,7 +127,7 @@ int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, con
 }
 int kjc_encoder_chained(const KjcEncoder* enc) { return enc && enc->impl.chained() ? 1 : 0; }
 int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len) { return enc ? enc->impl.micro_batch(seq_len) : 0; }
-int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc) { return enc ? enc->impl.last_launches() : 0; }
+int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc) { return enc ? enc->grp.last_launches() : 0; }
 
 int kjc_encoder_set_profiling(KjcEncoder* enc, int on) {
     KJC_REQUIRE(enc);
@@ -252,6 +269,53 @@ int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const fl
         kj::merge_lists_u64(d_cand_ids, d_cand_scores, n_lists, nq, k, d_out_ids, d_out_scores, d_out_counts, static_cast<cudaStream_t>(stream));
     });
 }
+// ------------------------------------------------------------ sharded index
+int kjc_sharded_index_create(int dim, uint64_t capacity_rows, const int* device_ids, int n_devices, KjcShardedIndex** out) {
+    KJC_REQUIRE(out);
+    *out = nullptr;
+    KJC_REQUIRE(device_ids);
+    return guarded([&] { *out = new KjcShardedIndex(dim, capacity_rows, device_ids, n_devices); });
+}
+int kjc_sharded_index_open_dir(const char* root, const int* device_ids, int n_devices, KjcShardedIndex** out) {
+    KJC_REQUIRE(out);
+    *out = nullptr;
+    KJC_REQUIRE(root);
+    KJC_REQUIRE(device_ids);
+    return guarded([&] { *out = new KjcShardedIndex(root, device_ids, n_devices); });
+}
+void kjc_sharded_index_destroy(KjcShardedIndex* idx) { delete idx; }
+uint64_t kjc_sharded_index_len(const KjcShardedIndex* idx) { return idx ? idx->impl.len() : 0; }
+int kjc_sharded_index_dim(const KjcShardedIndex* idx) { return idx ? idx->impl.dim() : 0; }
+int kjc_sharded_index_shards(const KjcShardedIndex* idx) { return idx ? idx->impl.n_shards() : 0; }
+uint64_t kjc_sharded_index_shard_len(const KjcShardedIndex* idx, int shard) {
+    if (!idx || shard < 0 || shard >= idx->impl.n_shards()) return 0;
+    return const_cast<KjcShardedIndex*>(idx)->impl.shard(shard).len();
+}
+int kjc_sharded_index_add_rows(KjcShardedIndex* idx, const float* rows, uint64_t n) {
+    KJC_REQUIRE(idx);
+    if (n == 0) return KJC_OK;
+    KJC_REQUIRE(rows);
+    return guarded([&] { idx->impl.add_rows_host(rows, n); });
+}
+int kjc_sharded_index_append_synthetic(KjcShardedIndex* idx, uint32_t seed, uint64_t n) {
+    KJC_REQUIRE(idx);
+    return guarded([&] { idx->impl.append_synthetic(seed, n); });
+}
+int kjc_sharded_index_search(KjcShardedIndex* idx, const float* queries, int nq, int k, int mode, uint64_t* out_ids, float* out_scores,
+                             int32_t* out_counts) {
+    KJC_REQUIRE(idx);
+    KJC_REQUIRE(queries);
+    KJC_REQUIRE(out_ids);
+    KJC_REQUIRE(out_scores);
+    return guarded([&] { idx->impl.search_host(queries, nq, k, mode, out_ids, out_scores, out_counts); });
+}
+int64_t kjc_sharded_index_last_launch_count(const KjcShardedIndex* idx) {
+    if (!idx) return 0;
+    int64_t s = 0;
+    KjcShardedIndex* m = const_cast<KjcShardedIndex*>(idx);
+    for (int p = 0; p < m->impl.n_shards(); ++p) s += m->impl.shard(p).last_launches();
+    return s + (m->impl.n_shards() > 1 ? 1 : 0);
+}
 int64_t kjc_index_last_launch_count(const KjcIndex* idx) { return idx ? idx->impl.last_launches() : 0; }
 int64_t kjc_index_unverified_count(KjcIndex* idx) {
     if (!idx) return 0;
@@ -297,6 +361,7 @@ int kjc_dbg_gemm_ln_h(const uint16_t* a_bf16, const uint16_t* w_bf16, const floa
     return guarded([&] { kj::dbg_gemm_ln(a_bf16, w_bf16, bias, gamma, beta, eps, res_bf16, M, H, K, out_bf16, iters, out_us); });
 }
 
+int kjc_dbg_experimental_kernels(void) { return kj::experimental_kernels_built() ? 1 : 0; }
 int kjc_dbg_ffn_ln(const uint16_t* x_bf16, const uint16_t* w1_bf16, const float* b1, const uint16_t* w2_bf16, const float* b2, const float* gamma,
                    const float* beta, float eps, int M, int I, int act, uint16_t* out_bf16, int iters, float* out_us) {
     KJC_REQUIRE(x_bf16); KJC_REQUIRE(w1_bf16); KJC_REQUIRE(b1); KJC_REQUIRE(w2_bf16); KJC_REQUIRE(b2); KJC_REQUIRE(gamma); KJC_REQUIRE(beta);

@@ -20,6 +20,7 @@ CUtensorMap make_tmap_2d(const void* base, CUtensorMapDataType dt, int elem_byte
 int pick_block_n(int N);
 void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms,
                  cudaStream_t st);
+bool experimental_kernels_built();
 void launch_gemm_pair(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p,
                       int num_sms, cudaStream_t st);
 void launch_ffn_ln(const CUtensorMap& t_x, const CUtensorMap& t_w1, const CUtensorMap& t_w1_pair, const CUtensorMap& t_w2, int M, int I,
@@ -121,10 +122,19 @@ class Encoder {
     void forward_device(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S, const KjcForwardOptions& o,
                         float* d_out, cudaStream_t st);
 
+    // `o` with KJC_MASK_AUTO replaced by the convention the reference's ComputeStrategy picks for a batch of B x S tokens (validates
+    // first).  A caller that splits one batch over several replicas resolves once for the whole batch and passes the result down.
+    KjcForwardOptions resolved_options(int B, int S, const KjcForwardOptions& o) const {
+        validate(B, S, o);
+        KjcForwardOptions oc = o;
+        oc.mask_convention = resolve_noalloc(B, S, o) ? KJC_MASK_NOALLOC : KJC_MASK_ALLOC;
+        return oc;
+    }
+    size_t out_row_elems(const KjcForwardOptions& o, int S) const;
+
   private:
     void validate(int B, int S, const KjcForwardOptions& o) const;
     bool resolve_noalloc(int B, int S, const KjcForwardOptions& o) const;
-    size_t out_row_elems(const KjcForwardOptions& o, int S) const;
     // Activations of one micro-batch in flight.  Several "lanes" run concurrently on disjoint groups of SMs (each kernel is
     // launched with num_sms / lanes persistent CTAs on the lane's own stream), so the fixed per-launch latency of one lane
     // (launch, prologue, pipeline fill, epilogue drain) is covered by the other lanes' tensor work.

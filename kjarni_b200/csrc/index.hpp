@@ -23,6 +23,7 @@ class Index {
     uint64_t id_base() const { return id_base_; }
     int device() const { return device_; }
     int64_t last_launches() const { return launches_; }
+    cudaStream_t stream() const { return stream_; }
 
     void add_rows_host(const float* rows, uint64_t n);
     void load_vectors_bin(const std::string& path);

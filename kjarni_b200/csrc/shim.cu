@@ -12,7 +12,7 @@
 #include <atomic>
 #include <chrono>
 
-#include "index.hpp"
+#include "multi.hpp"
 #include "indexer.hpp"
 #include "tokenizer.hpp"
 
@@ -94,15 +94,42 @@ std::string resolve_model_dir(const char* cache_dir, const char* model_name, con
     return d;
 }
 
-// One text model on cuda:0: tokenizer + encoder (EncoderLoader::load_from_pretrained, pipeline/encoder/loader.rs:82-141)
+// The reference's configs only say KJARNI_DEVICE_GPU; which GPUs that means is deployment configuration:
+// KJARNI_GPU_DEVICES = "all" | comma-separated device indices (default "0").  With more than one device every model holds one weight
+// replica per GPU (batches are split by rows, no collective) and every opened index is row-sharded over the same GPUs (multi.hpp).
+std::vector<int> shim_devices() {
+    std::vector<int> d;
+    const char* e = getenv("KJARNI_GPU_DEVICES");
+    if (e && !strcmp(e, "all")) {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+        for (int i = 0; i < n; ++i) d.push_back(i);
+    } else if (e && *e) {
+        for (const char* p = e; *p;) {
+            char* end = nullptr;
+            const long v = strtol(p, &end, 10);
+            if (end == p) throw Fail{KJARNI_ERROR_INVALID_CONFIG, "KJARNI_GPU_DEVICES must be \"all\" or a comma-separated list of device indices"};
+            d.push_back(static_cast<int>(v));
+            p = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') throw Fail{KJARNI_ERROR_INVALID_CONFIG, "KJARNI_GPU_DEVICES must be \"all\" or a comma-separated list of device indices"};
+        }
+    }
+    if (d.empty()) d.push_back(0);
+    return d;
+}
+
+// One text model: tokenizer + encoder replica(s) (EncoderLoader::load_from_pretrained, pipeline/encoder/loader.rs:82-141)
 struct TextModel {
-    std::unique_ptr<Encoder> enc;
+    std::unique_ptr<EncoderGroup> grp;
+    Encoder* enc = nullptr;  // replica 0: info / labels
     std::unique_ptr<Tokenizer> tok;
     std::string name;
 
     TextModel(const std::string& dir, const std::string& nm) : name(nm) {
         if (!file_ok(dir + "/tokenizer.json")) throw Fail{KJARNI_ERROR_LOAD_FAILED, "Tokenizer not found at \"" + dir + "/tokenizer.json\""};
-        enc.reset(new Encoder(dir, 0));
+        const std::vector<int> devs = shim_devices();
+        grp.reset(new EncoderGroup(dir, devs.data(), static_cast<int>(devs.size())));
+        enc = &grp->replica(0);
         tok.reset(new Tokenizer(dir + "/tokenizer.json", enc->info().max_position_embeddings));  // truncation max_length = meta.max_seq_len
     }
 
@@ -137,7 +164,7 @@ struct TextModel {
         static const bool no_buckets = getenv("KJC_NO_LENGTH_BUCKETS") != nullptr;
         if (one_bucket || no_buckets) {
             const Encoder::RowSink rs = [&](const float* rows, size_t first, size_t cnt) { (*sink)(rows, cnt, order.data() + first); };
-            enc->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(n), S, o, sink ? nullptr : out.data(), sink ? &rs : nullptr);
+            grp->forward_host(ids.data(), mask.data(), types_ok ? types.data() : nullptr, static_cast<int>(n), S, o, sink ? nullptr : out.data(), sink ? &rs : nullptr);
             return;
         }
         std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return len[x] < len[y]; });
@@ -161,9 +188,9 @@ struct TextModel {
             }
             if (sink) {
                 const Encoder::RowSink rs = [&](const float* rows, size_t first, size_t cnt) { (*sink)(rows, cnt, order.data() + g0 + first); };
-                enc->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, nullptr, &rs);
+                grp->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, nullptr, &rs);
             } else {
-                enc->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, go.data());
+                grp->forward_host(gi.data(), gm.data(), types_ok ? gt.data() : nullptr, static_cast<int>(nb), Sg, o, go.data());
                 for (size_t r = 0; r < nb; ++r) memcpy(&out[order[g0 + r] * out_cols], &go[r * out_cols], out_cols * sizeof(float));
             }
             g0 = g1;
@@ -268,7 +295,7 @@ struct KjarniSearcher {
     // GPU shards of the index directories searched so far (the reference re-opens the index per call: IndexReader::open is an
     // mmap there; here it is an upload, so it is kept)
     struct Opened {
-        std::unique_ptr<Index> idx;
+        std::unique_ptr<ShardedIndex> idx;
         IndexDir dir;
         std::string fingerprint;  // segment list + file sizes / mtimes at open: a rebuilt or appended index is re-opened
         std::vector<std::unique_ptr<Bm25Index>> bm25;  // per segment, loaded on the first keyword / hybrid query
@@ -784,7 +811,10 @@ KjarniErrorCode kjarni_searcher_search_with_options(KjarniSearcher* s, const cha
             KjarniSearcher::Opened op;
             op.dir = std::move(now);
             op.fingerprint = fp;
-            if (op.dir.total_rows > 0) op.idx.reset(open_index_dir(index_path, 0, 0, 1));
+            if (op.dir.total_rows > 0) {
+                const std::vector<int> devs = shim_devices();
+                op.idx.reset(new ShardedIndex(index_path, devs.data(), static_cast<int>(devs.size())));
+            }
             it = s->opened.emplace(index_path, std::move(op)).first;
         }
         KjarniSearcher::Opened& op = it->second;
