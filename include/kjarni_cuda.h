@@ -155,6 +155,15 @@ int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len);
 /* 1 when the handle runs out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next QKV as one launch each (hidden size 384); the
  * per-kernel-class profile then books those launches under KJC_K_GEMM_FFN_UP / KJC_K_GEMM_FFN_DOWN. */
 int kjc_encoder_chained(const KjcEncoder* enc);
+/* Precision of the residual stream between kernels (every replica of the handle):
+ *   0  bf16 for every output -- the fused / chained kernels everywhere (fastest; hidden states then carry one bf16 rounding per
+ *      LayerNorm output: max-abs error up to ~6e-2 at |x| ~ 5 against the fp32 reference);
+ *   1  (default) fp32 for KJC_OUT_HIDDEN, bf16 for pooled embeddings and logits: the hidden states -- the tensor
+ *      EncoderLanguageModel::get_hidden_states_batch_from_ids returns (KT/cpu/encoder/traits.rs:66-139) -- keep an fp32 residual
+ *      stream and only the GEMM operands are rounded to bf16 (max-abs error < 2e-2, measured ~8e-3);
+ *   2  fp32 for every output.
+ * The fp32 mode runs projection -> fp32 sums (+ fp32 residual) -> LayerNorm kernel instead of the fused kernels. */
+int kjc_encoder_set_fp32_residual(KjcEncoder* enc, int mode);
 /* Number of kernel launches the last forward on this handle enqueued (for bench bookkeeping). */
 int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc);
 

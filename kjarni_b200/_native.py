@@ -69,6 +69,7 @@ SIGNATURES = {
     "kjc_encoder_forward_device_async": (_i, [_vp, _vp, _vp, _vp, _i, _i, C.POINTER(KjcForwardOptions), _vp, _vp]),
     "kjc_encoder_micro_batch": (_i, [_vp, _i]),
     "kjc_encoder_chained": (_i, [_vp]),
+    "kjc_encoder_set_fp32_residual": (_i, [_vp, _i]),
     "kjc_encoder_last_launch_count": (C.c_int64, [_vp]),
     "kjc_encoder_set_profiling": (_i, [_vp, _i]),
     "kjc_encoder_get_profile": (_i, [_vp, _vp, _vp]),

@@ -63,6 +63,10 @@ class EncoderModel:
             self.labels.append(s.decode())
             i += 1
 
+    def set_fp32_residual(self, mode: int) -> None:
+        """0 = bf16 residual stream everywhere, 1 = fp32 for hidden-state output (default), 2 = fp32 for every output."""
+        N.check(N.lib().kjc_encoder_set_fp32_residual(self._h, int(mode)))
+
     @classmethod
     def from_pretrained(cls, model_dir: str, device: int = 0) -> "EncoderModel":
         return cls(model_dir, device)

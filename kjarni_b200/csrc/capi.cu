@@ -126,6 +126,11 @@ int kjc_encoder_forward_device_async(KjcEncoder* enc, const uint32_t* d_ids, con
     return guarded([&] { enc->impl.forward_device(d_ids, d_mask, d_type_ids, batch, seq_len, o, d_out, static_cast<cudaStream_t>(stream)); });
 }
 int kjc_encoder_chained(const KjcEncoder* enc) { return enc && enc->impl.chained() ? 1 : 0; }
+int kjc_encoder_set_fp32_residual(KjcEncoder* enc, int mode) {
+    KJC_REQUIRE(enc);
+    for (int p = 0; p < enc->grp.size(); ++p) enc->grp.replica(p).set_fp32_residual(mode);
+    return KJC_OK;
+}
 int kjc_encoder_micro_batch(const KjcEncoder* enc, int seq_len) { return enc ? enc->impl.micro_batch(seq_len) : 0; }
 int64_t kjc_encoder_last_launch_count(const KjcEncoder* enc) { return enc ? enc->grp.last_launches() : 0; }
 

@@ -694,6 +694,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     // out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next layer's QKV as one launch each (gemm_ln_gemm.cuh)
     chain_ = fused_ln_ && H == kLnN && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
     chain_embed_ = chain_ && getenv("KJC_CHAIN_EMBED") != nullptr;
+    if (const char* e = getenv("KJC_FP32_RESIDUAL")) set_fp32_residual(atoi(e));
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
     lanes_ = 1;  // measured: no gain from concurrent lanes (the kernels are epilogue-issue-bound, not launch-latency-bound)
@@ -729,9 +730,9 @@ Encoder::~Encoder() {
 }
 
 void Encoder::free_workspace(Workspace& w) {
-    for (void* p : {(void*)w.y32, (void*)w.x16, (void*)w.qkv16, (void*)w.ctx16, (void*)w.h16, (void*)w.head32})
+    for (void* p : {(void*)w.y32, (void*)w.x32, (void*)w.x16, (void*)w.qkv16, (void*)w.ctx16, (void*)w.h16, (void*)w.head32})
         if (p) cudaFree(p);
-    w.y32 = nullptr; w.x16 = w.qkv16 = w.ctx16 = w.h16 = nullptr;
+    w.y32 = w.x32 = nullptr; w.x16 = w.qkv16 = w.ctx16 = w.h16 = nullptr;
     w.head32 = nullptr;
     w.tokens = 0;
 }
@@ -745,7 +746,7 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     free_workspace(w);
     const size_t T = static_cast<size_t>(std::max(tokens, 128));
     const int H = info_.hidden_size, I = info_.intermediate_size;
-    if (!fused_ln_) KJ_CUDA(cudaMalloc(&w.y32, T * H * 4));  // pre-LayerNorm sums of the unfused path
+    if (!fused_ln_) KJ_CUDA(cudaMalloc(&w.y32, T * H * 4));  // pre-LayerNorm sums of the unfused path (fp32-residual mode allocates lazily)
     KJ_CUDA(cudaMalloc(&w.x16, T * H * 2));
     KJ_CUDA(cudaMalloc(&w.qkv16, T * 3 * H * 2));
     KJ_CUDA(cudaMalloc(&w.ctx16, T * H * 2));
@@ -770,20 +771,32 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     w.tokens = static_cast<int>(T);
 }
 
+// fp32-residual mode: the fp32 copy of the residual stream and the pre-LayerNorm sums, allocated on first use
+void Encoder::ensure_fp32_stream(Workspace& w) {
+    const size_t T = static_cast<size_t>(w.tokens), H = info_.hidden_size;
+    if (!w.y32) KJ_CUDA(cudaMalloc(&w.y32, T * H * 4));
+    if (!w.x32) KJ_CUDA(cudaMalloc(&w.x32, T * H * 4));
+}
+
 // One micro-batch: ids/mask/types are device pointers for `nb` sequences of length S.
 void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S,
                             const KjcForwardOptions& o, bool noalloc_convention, float* d_out, cudaStream_t st) {
     const int H = info_.hidden_size, I = info_.intermediate_size, M = nb * S, d = H / info_.num_heads;
     const float eps = info_.layer_norm_eps;
+    // fp32 residual stream (default for hidden-state output): x32 is the stream, x16 its bf16 copy feeding the tensor cores; the
+    // projections run as GEMM -> fp32 sums (+ fp32 residual) -> LayerNorm kernel (writes x32 and x16) instead of the fused kernels
+    const bool precise = fp32_residual_for(o);
+    if (precise) ensure_fp32_stream(w);
+    const bool fused_ln = fused_ln_ && !precise;
     // chained launches need one 128-row tile per CTA
-    const bool chain = chain_ && !pair_gemm_ && (M + kGemmBlockM - 1) / kGemmBlockM <= sms;
+    const bool chain = chain_ && !precise && !pair_gemm_ && (M + kGemmBlockM - 1) / kGemmBlockM <= sms;
     // the embedding front end of the chained kernel is bit-identical but measured slower than the two launches (12 gathering warps
     // per SM are latency-bound: 50 us against 17 + 27 us), so it stays opt-in (KJC_CHAIN_EMBED)
     const bool chain_embed = chain && chain_embed_ && !layers_.empty();
     {
         EmbedParams e;
         e.ids = d_ids; e.type_ids = d_types; e.word = word_; e.pos = pos_; e.type = type_; e.gamma = emb_g_; e.beta = emb_b_;
-        e.x32 = nullptr; e.x16 = w.x16; e.err_flag = d_err_;
+        e.x32 = precise ? w.x32 : nullptr; e.x16 = w.x16; e.err_flag = d_err_;
         e.M = M; e.S = S; e.H = H; e.vocab = info_.vocab_size; e.max_pos = info_.max_position_embeddings;
         e.type_vocab = info_.type_vocab_size; e.pos_offset = info_.position_offset; e.eps = eps;
         const int grid = (M + 7) / 8;
@@ -841,22 +854,22 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
             continue;
         }
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)
-        if (fused_ln_) {
+        if (fused_ln) {
             prof_begin(KJC_K_GEMM_OUT, st);
             launch_gemm_ln(w.t_ctx16, L.t_wo_ln, w.t_x16_io, M, H, H, L.bo, L.g1, L.be1, eps, sms, st);
             prof_end(st);
         } else {
             g = GemmParams{};
-            g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = w.x16; g.ldr = H; g.out = w.y32; g.ldo = H; g.act = ACT_NONE;
+            g.M = M; g.N = H; g.K = H; g.bias = L.bo; g.residual = w.x16; g.residual32 = precise ? w.x32 : nullptr; g.ldr = H; g.out = w.y32; g.ldo = H; g.act = ACT_NONE;
             prof_begin(KJC_K_GEMM_OUT, st);
             launch_gemm(bn_h_, EPI_BIAS_RES_F32, w.t_ctx16, L.t_wo, w.t_qkv16_out, g, sms, st);
             prof_end(st);
             prof_begin(KJC_K_LAYERNORM, st);
-            launch_layernorm(w.y32, L.g1, L.be1, eps, nullptr, w.x16, M, H, st);
+            launch_layernorm(w.y32, L.g1, L.be1, eps, precise ? w.x32 : nullptr, w.x16, M, H, st);
             prof_end(st);
             ++launches_;
         }
-        if (fused_ffn_) {
+        if (fused_ffn_ && !precise) {
             // x = LN2(x + act(x W1^T + b1) W2^T + b2) in one kernel      (standard_new.rs:47-80, encoder_layer.rs:150-176)
             prof_begin(KJC_K_GEMM_FFN_UP, st);
             launch_ffn_ln(w.t_x16, L.t_w1_ffn, L.t_w1_ffn32, L.t_w2_ffn, M, I, L.b1, L.b2, L.g2, L.be2, eps, act_, sms, st);
@@ -872,27 +885,33 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         else launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1, w.t_h16_out, g, sms, st);
         prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
-        if (fused_ln_) {
+        if (fused_ln) {
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
             launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             prof_end(st);
         } else {
             g = GemmParams{};
-            g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = w.x16; g.ldr = H; g.out = w.y32; g.ldo = H; g.act = ACT_NONE;
+            g.M = M; g.N = H; g.K = I; g.bias = L.b2; g.residual = w.x16; g.residual32 = precise ? w.x32 : nullptr; g.ldr = H; g.out = w.y32; g.ldo = H; g.act = ACT_NONE;
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
             launch_gemm(bn_h_, EPI_BIAS_RES_F32, w.t_h16, L.t_w2, w.t_qkv16_out, g, sms, st);
             prof_end(st);
             prof_begin(KJC_K_LAYERNORM, st);
-            launch_layernorm(w.y32, L.g2, L.be2, eps, nullptr, w.x16, M, H, st);
+            launch_layernorm(w.y32, L.g2, L.be2, eps, precise ? w.x32 : nullptr, w.x16, M, H, st);
             prof_end(st);
             ++launches_;
         }
         launches_ += 4;
     }
     prof_begin(KJC_K_OUTPUT, st);
-    if (o.output == KJC_OUT_HIDDEN) {
+    if (o.output == KJC_OUT_HIDDEN && precise) {
+        KJ_CUDA(cudaMemcpyAsync(d_out, w.x32, static_cast<size_t>(M) * H * 4, cudaMemcpyDeviceToDevice, st));  // the fp32 stream itself
+    } else if (o.output == KJC_OUT_HIDDEN) {
         const size_t n4 = static_cast<size_t>(M) * H / 4;
         bf16_to_f32_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(w.x16, d_out, n4);
+        KJ_CUDA(cudaGetLastError());
+        ++launches_;
+    } else if (o.output == KJC_OUT_POOLED && precise) {
+        pool_l2_kernel<float><<<nb, 256, 0, st>>>(w.x32, d_mask, d_out, S, H, o.pooling, o.normalize);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else if (o.output == KJC_OUT_POOLED) {
@@ -909,6 +928,15 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         }
         KJ_CUDA(cudaGetLastError());
         ++launches_;
+    } else if (precise) {
+        HeadParams<float> hp;
+        hp.x = w.x32; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;
+        hp.B = nb; hp.S = S; hp.H = H; hp.C = info_.num_labels;
+        hp.act = info_.head_kind == KJC_HEAD_PRE_RELU ? HEAD_RELU : (info_.head_kind == KJC_HEAD_LINEAR ? HEAD_NONE : HEAD_TANH);
+        hp.z1 = w.head32;
+        launch_cls_head(hp, st);
+        KJ_CUDA(cudaGetLastError());
+        launches_ += w_pre_ ? 2 : 1;
     } else {
         HeadParams<__nv_bfloat16> hp;
         hp.x = w.x16; hp.w_pre = w_pre_; hp.b_pre = b_pre_; hp.w_cls = w_cls_; hp.b_cls = b_cls_; hp.logits = d_out;

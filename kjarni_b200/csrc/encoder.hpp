@@ -109,6 +109,11 @@ class Encoder {
     int micro_batch(int seq_len) const;
     int64_t last_launches() const { return launches_; }
     bool chained() const { return chain_; }
+    // Residual stream precision: 0 = bf16 between kernels for every output (fastest), 1 = fp32 for KJC_OUT_HIDDEN only (default: the
+    // hidden states then carry only the bf16 rounding of the GEMM operands, max-abs error < 2e-2 against the fp32 reference), 2 = fp32
+    // for every output.  The fp32 mode runs the un-chained kernels: GEMM -> fp32 sums -> LayerNorm kernel.
+    void set_fp32_residual(int mode) { fp32_residual_ = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+    int fp32_residual() const { return fp32_residual_; }
     // Per-kernel-class CUDA-event timing of the forwards issued while profiling is on (bench roofline numbers).
     void set_profiling(bool on);
     void get_profile(double* ms, int64_t* launches);  // arrays of KJC_NUM_KERNEL_CLASSES; synchronises
@@ -140,7 +145,8 @@ class Encoder {
     // (launch, prologue, pipeline fill, epilogue drain) is covered by the other lanes' tensor work.
     struct Workspace {
         int tokens = 0;
-        float* y32 = nullptr;  // unfused path only
+        float* y32 = nullptr;  // unfused path only: pre-LayerNorm sums
+        float* x32 = nullptr;  // fp32-residual mode: the residual stream in fp32 (x16 is its bf16 copy for the tensor-core operands)
         float* head32 = nullptr;  // classification head: pre-classifier output [sequences, H]
         __nv_bfloat16 *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr;
         CUtensorMap t_x16, t_ctx16, t_h16;   // A-operand loads
@@ -151,9 +157,11 @@ class Encoder {
         cudaEvent_t done = nullptr;
     };
     void ensure_workspace(Workspace& w, int tokens);
+    void ensure_fp32_stream(Workspace& w);
     void free_workspace(Workspace& w);
     void forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int nb, int S,
                        const KjcForwardOptions& o, bool noalloc_convention, float* d_out, cudaStream_t st);
+    bool fp32_residual_for(const KjcForwardOptions& o) const { return fp32_residual_ == 2 || (fp32_residual_ == 1 && o.output == KJC_OUT_HIDDEN); }
     void forward_batches(const uint32_t* d_ids, const float* d_mask, const uint32_t* d_types, int B, int S, const KjcForwardOptions& o,
                          float* d_out, cudaStream_t st);
 
@@ -169,6 +177,7 @@ class Encoder {
     const float *word_ = nullptr, *pos_ = nullptr, *type_ = nullptr, *emb_g_ = nullptr, *emb_b_ = nullptr;
     const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
     std::vector<LayerDev> layers_;
+    int fp32_residual_ = 1;
     bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false, chain_embed_ = false;
     int lanes_ = 2;
     std::vector<Workspace> ws_;

@@ -30,6 +30,7 @@ struct GemmParams {
     int M, N, K;
     const float* bias;      // [N] or nullptr
     const __nv_bfloat16* residual;  // [M, ldr] bf16 residual stream (EPI_BIAS_RES_F32)
+    const float* residual32;        // [M, ldr] fp32 residual stream: used instead of `residual` when non-null (fp32-residual mode)
     void* out;              // [M, ldo] bf16 or f32
     int ldo, ldr;
     int act;
@@ -431,7 +432,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                         if (row_ok) {
                             float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + col0;
-                            if (EPI == EPI_BIAS_RES_F32) {
+                            if (EPI == EPI_BIAS_RES_F32 && p.residual32 != nullptr) {
+                                const float4* r4 = reinterpret_cast<const float4*>(p.residual32 + static_cast<size_t>(row) * p.ldr + col0);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 r = __ldg(r4 + j);
+                                    f[4 * j + 0] += r.x;
+                                    f[4 * j + 1] += r.y;
+                                    f[4 * j + 2] += r.z;
+                                    f[4 * j + 3] += r.w;
+                                }
+                            } else if (EPI == EPI_BIAS_RES_F32) {
                                 const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ldr + col0);
 #pragma unroll
                                 for (int j = 0; j < 2; ++j) {

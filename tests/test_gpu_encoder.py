@@ -54,9 +54,20 @@ def test_embedding_matches_oracle(dirs, arch, B, S):
     hg = enc.get_hidden_states_batch_from_ids(ids, mask)
     valid = mask.astype(bool)
     assert cosine_rows(hg[valid], hw[valid]).min() >= COS_MIN
-    # the residual stream is stored in bf16 between kernels: one bf16 ulp at |x| in [2,4) is 1.6e-2
-    assert np.abs(hg[valid] - hw[valid]).max() <= 1e-1
-    assert np.abs(hg[valid] - hw[valid]).mean() <= 8e-3
+    # hidden-state output keeps the residual stream in fp32 (kjc_encoder_set_fp32_residual mode 1, the default): only the GEMM
+    # operands are rounded to bf16 and the north-star bound (max-abs <= 2e-2 against the fp32 reference) holds per element
+    assert np.abs(hg[valid] - hw[valid]).max() <= MAXABS
+    assert np.abs(hg[valid] - hw[valid]).mean() <= 3e-3
+    # mode 2: the same fp32 stream under the pooled output -- tighter than the bf16-stream embeddings, same tolerance gate
+    enc.set_fp32_residual(2)
+    g2 = enc.encode_batch_from_ids(ids, mask)
+    assert cosine_rows(g2, want).min() >= COS_MIN and np.abs(g2 - want).max() <= MAXABS
+    assert np.abs(g2 - want).max() <= np.abs(got - want).max() + 1e-4
+    # mode 0: bf16 stream everywhere (the fused / chained kernels): one bf16 ulp at |x| in [2,4) is 1.6e-2 per LayerNorm output
+    enc.set_fp32_residual(0)
+    hf = enc.get_hidden_states_batch_from_ids(ids, mask)
+    assert cosine_rows(hf[valid], hw[valid]).min() >= COS_MIN
+    assert np.abs(hf[valid] - hw[valid]).max() <= 1e-1 and np.abs(hf[valid] - hw[valid]).mean() <= 8e-3
     enc.close()
 
 
@@ -85,6 +96,11 @@ def test_logits_match_oracle(dirs, arch, B, S, pair):
     assert got.shape == want.shape
     scale = max(1.0, float(np.abs(want).max()))
     assert np.abs(got - want).max() <= 5e-2 * scale
+    # with the fp32 residual stream (mode 2) the logits meet the 2e-2 bound the north star states for embeddings
+    enc.set_fp32_residual(2)
+    got32 = enc.predict_logits(ids, mask, types)
+    enc.set_fp32_residual(1)
+    assert np.abs(got32 - want).max() <= 2e-2 * scale, (np.abs(got32 - want).max(), np.abs(got - want).max(), scale)
     if want.shape[1] > 1:
         margin = np.abs(want[:, 0] - want[:, 1])
         sure = margin > 0.1 * scale

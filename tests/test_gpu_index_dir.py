@@ -82,3 +82,56 @@ def test_truncated_vectors_bin_is_a_load_error(tmp_path):
     with pytest.raises(N.KjarniCudaError) as e:
         api.IndexShard.open_dir(root)
     assert e.value.status == N.KJC_LOAD_FAILED
+
+
+def test_reference_rag_full_lifecycle(tmp_path):
+    """`test_rag_full_lifecycle` of the reference (kjarni-rag/src/tests.rs:8-79), transcribed: three documents with dimension 4 and
+    max_docs_per_segment 2 (=> two segments), exact vectors and texts as in the reference test.  Semantic search runs on the GPU
+    shard, keyword search through kjarni_search_keywords (the segments' bm25.bin), hybrid = reciprocal-rank fusion of the two
+    (index_reader.rs:248-289, hybrid.rs:3-31)."""
+    import ctypes as C
+    import json
+    import os
+
+    from kjarni_b200 import _native as N
+
+    docs = [["Apple is a fruit", "Car is a vehicle"], ["Banana is yellow"]]
+    vecs = [np.array([[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0]], np.float32), np.array([[0.9, 0.1, 0.0, 0.0]], np.float32)]
+    meta = [[{"category": "fruit"}, {}], [{}]]
+    root = synth.write_index_dir(str(tmp_path / "my_index"), vecs, dimension=4, max_docs_per_segment=2, docs=docs, metadata=meta)
+    flat = docs[0] + docs[1]
+    info = N.KjcIndexDirInfo()
+    N.check(N.lib().kjc_index_dir_info(root.encode(), C.byref(info)))
+    assert (info.total_rows, info.dimension, info.n_segments) == (3, 4, 2)  # reader.len() / dimension() / segment_count()
+    sh = api.IndexShard.open_dir(root)
+    sem = sh.search_vectors(np.array([1.0, 0.0, 0.0, 0.0], np.float32), 10)
+    assert len(sem) == 3
+    assert [flat[i] for i, _ in sem] == ["Apple is a fruit", "Banana is yellow", "Car is a vehicle"]
+    assert sem[0][1] > 0.99
+    sh.close()
+
+    class SearchResult(C.Structure):
+        _fields_ = [("score", C.c_float), ("document_id", C.c_size_t), ("text", C.c_char_p), ("metadata_json", C.c_char_p)]
+
+    class SearchResults(C.Structure):
+        _fields_ = [("results", C.POINTER(SearchResult)), ("len", C.c_size_t)]
+
+    ffi = C.CDLL(os.path.join(os.path.dirname(N.LIB_PATH), "libkjarni_ffi.so"))
+    ffi.kjarni_search_keywords.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(SearchResults)]
+    ffi.kjarni_search_results_free.argtypes = [C.POINTER(SearchResults)]
+
+    def keywords(q, k):
+        res = SearchResults()
+        assert ffi.kjarni_search_keywords(root.encode(), q.encode(), k, C.byref(res)) == 0
+        out = [(res.results[i].document_id, res.results[i].score, res.results[i].text.decode(), json.loads(res.results[i].metadata_json)) for i in range(res.len)]
+        ffi.kjarni_search_results_free(C.byref(res))
+        return out
+
+    kw = keywords("yellow", 10)
+    assert len(kw) == 1 and kw[0][2] == "Banana is yellow"
+    # search_hybrid("vehicle", [1,0,0,0], 10): keyword and semantic lists of 2 x limit each, fused
+    hyb = ko.rrf_hybrid([(d, s) for d, s, _, _ in keywords("vehicle", 20)], sem, 10)
+    top2 = [flat[i] for i, _ in hyb[:2]]
+    assert "Car is a vehicle" in top2 and "Apple is a fruit" in top2
+    apple = [r for r in keywords("apple", 10) if "Apple" in r[2]][0]
+    assert apple[3].get("category") == "fruit"

@@ -154,3 +154,26 @@ def test_segment_and_index_semantics():
     dup = np.stack([q, q, q * 2]).astype(F32)
     assert [i for i, _ in ko.segment_search(dup, q, 2)][0] in (0, 1, 2)
     assert ko.stable_argsort_desc(np.array([1.0, 1.0, 0.5], dtype=F32)).tolist() == [0, 1, 2]
+
+
+def test_embeddings_forward_reference_vectors():
+    """Embeddings::forward known answers transcribed from the reference's own unit tests
+    (kjarni-transformers/src/cpu/embeddings/tests.rs:59-220): word + position (+ offset, clamped to the table) + token type."""
+    ones = lambda r, c: np.full((r, c), 1.0, np.float32)
+    # test_cpu_embeddings_math / test_position_embedding_broadcasting_batch / test_batch_sequence_broadcasting
+    for (b, s, h) in ((1, 2, 4), (2, 3, 4), (3, 4, 2)):
+        out = ko.embeddings_forward(np.zeros((b, s), np.uint32), ones(10, h), np.full((10, h), 0.5, np.float32), None, None, 0)
+        assert out.shape == (b, s, h) and (out == 1.5).all()
+    # test_position_embedding_with_offset: pos[i, j] = 0.1 i + j, offset 2
+    pos = np.fromfunction(lambda i, j: i * np.float32(0.1) + j, (10, 2), dtype=np.float32).astype(np.float32)
+    out = ko.embeddings_forward(np.zeros((1, 4), np.uint32), ones(10, 2), pos, None, None, 2)
+    assert out[0, 0, 0] == np.float32(1.0) + np.float32(2 * np.float32(0.1)) and out[0, 0, 1] == np.float32(1.0) + (np.float32(2 * np.float32(0.1)) + 1)
+    assert out[0, 3, 0] == np.float32(1.0) + np.float32(0.5) and out[0, 3, 1] == np.float32(1.0) + np.float32(1.5)
+    # test_token_type_embeddings: type[i, j] = i + 0.1 j, all type ids 1
+    typ = np.fromfunction(lambda i, j: i + np.float32(0.1) * j, (2, 3), dtype=np.float32).astype(np.float32)
+    out = ko.embeddings_forward(np.zeros((1, 2), np.uint32), ones(5, 3), None, typ, np.ones((1, 2), np.uint32), 0)
+    for h in range(3):
+        assert (out[:, :, h] == np.float32(1.0) + typ[1, h]).all()
+    # test_position_offset_clamping: a 3-row position table, offset 1, sequence 4 -> only two positions receive a row
+    out = ko.embeddings_forward(np.zeros((1, 4), np.uint32), ones(5, 2), np.full((3, 2), 0.5, np.float32), None, None, 1)
+    assert out[0, 0, 0] == 1.5 and out[0, 1, 0] == 1.5 and out[0, 2, 0] == 1.0 and out[0, 3, 0] == 1.0
