@@ -287,9 +287,15 @@ int kjc_index_search_device_async(KjcIndex* idx, const float* d_queries, int nq,
  * tie-break (score desc, global id asc).  Device pointers: cand_* are [n_lists, nq, k]. */
 int kjc_topk_merge_device_async(int device, const uint64_t* d_cand_ids, const float* d_cand_scores, int n_lists, int nq, int k,
                                 uint64_t* d_out_ids, float* d_out_scores, int32_t* d_out_counts, void* stream);
+/* The same for candidates gathered with ONE collective: `d_packed` holds n_lists records of kjc_packed_record_bytes(nq, k) bytes
+ * (12*nq*k rounded up to 16), each = one rank's [nq,k] u64 ids followed by its [nq,k] f32 scores (the rank points
+ * kjc_index_search_device's two outputs into one buffer and all-gathers that buffer). */
+size_t kjc_packed_record_bytes(int nq, int k);
+int kjc_topk_merge_packed_device_async(int device, const void* d_packed, int n_lists, int nq, int k, uint64_t* d_out_ids, float* d_out_scores,
+                                       int32_t* d_out_counts, void* stream);
 int64_t kjc_index_last_launch_count(const KjcIndex* idx);
-/* Searches with k <= 16 on shards whose dim is a multiple of 64 and <= 384 run as a tensor-core similarity GEMM over a
- * bf16 shadow of the shard that only FILTERS 32 candidates per query; the candidates are re-scored in exact fp32 and a
+/* Searches with k <= 64 on shards whose dim is a multiple of 64 and <= 1024 run as a tensor-core similarity GEMM over a
+ * bf16 shadow of the shard that only FILTERS 32 (k <= 16) or 128 (k <= 64) candidates per query; the candidates are re-scored in exact fp32 and a
  * per-query bound proves the exact top-k (see kjarni_b200/csrc/scan_gemm.cuh).  A query whose bound does not hold is re-run
  * on the exact scan by kjc_index_search (which may synchronise); kjc_index_search_device_async cannot synchronise and
  * counts such queries here instead (synchronises the device; 0 = every async result so far was proven exact). */

@@ -96,6 +96,8 @@ SIGNATURES = {
     "kjc_index_search_device_async": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_index_search_device": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_topk_merge_device_async": (_i, [_i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "kjc_packed_record_bytes": (C.c_size_t, [_i, _i]),
+    "kjc_topk_merge_packed_device_async": (_i, [_i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "kjc_index_last_launch_count": (C.c_int64, [_vp]),
     "kjc_sharded_index_create": (_i, [_i, _u64, C.POINTER(_i), _i, C.POINTER(_vp)]),
     "kjc_sharded_index_open_dir": (_i, [C.c_char_p, C.POINTER(_i), _i, C.POINTER(_vp)]),

@@ -321,6 +321,22 @@ int64_t kjc_sharded_index_last_launch_count(const KjcShardedIndex* idx) {
     for (int p = 0; p < m->impl.n_shards(); ++p) s += m->impl.shard(p).last_launches();
     return s + (m->impl.n_shards() > 1 ? 1 : 0);
 }
+size_t kjc_packed_record_bytes(int nq, int k) { return kj::packed_record_bytes(nq, k); }
+int kjc_topk_merge_packed_device_async(int device, const void* d_packed, int n_lists, int nq, int k, uint64_t* d_out_ids, float* d_out_scores,
+                                       int32_t* d_out_counts, void* stream) {
+    KJC_REQUIRE(d_packed);
+    KJC_REQUIRE(d_out_ids);
+    KJC_REQUIRE(d_out_scores);
+    return guarded([&] {
+        if (n_lists < 1 || nq < 1 || k < 1) throw kj::Error(KJC_INVALID_CONFIG, "n_lists, nq and k must be positive");
+        KJ_CUDA(cudaSetDevice(device));
+        // record of one list: nq*k u64 ids, then nq*k f32 scores, padded to a multiple of 16 bytes; strides in elements of each array
+        const size_t rec = kj::packed_record_bytes(nq, k);
+        const uint8_t* base = static_cast<const uint8_t*>(d_packed);
+        kj::merge_lists_u64(reinterpret_cast<const uint64_t*>(base), reinterpret_cast<const float*>(base + static_cast<size_t>(nq) * k * 8), n_lists, nq, k,
+                            d_out_ids, d_out_scores, d_out_counts, static_cast<cudaStream_t>(stream), rec / 8, rec / 4);
+    });
+}
 int64_t kjc_index_last_launch_count(const KjcIndex* idx) { return idx ? idx->impl.last_launches() : 0; }
 int64_t kjc_index_unverified_count(KjcIndex* idx) {
     if (!idx) return 0;

@@ -181,15 +181,29 @@ void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensor
     }
 }
 
-// GEMM + residual + LayerNorm chained with the next projection of the same 128-row tiles (gemm_ln_gemm.cuh); one tile per CTA
+// GEMM + residual + LayerNorm chained with the next projection of the same 128-row tiles (gemm_ln_gemm.cuh); one tile per CTA.
+// pair: two CTAs per cluster share every weight tile (tcgen05.mma.cta_group::2); tw / tw2 must then have 96-row boxes.
 void launch_gemm_ln_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_res, const CUtensorMap& t_x, const CUtensorMap& tw2,
                          const CUtensorMap& t_out2, int M, int K1, const float* bias1, const float* gamma, const float* beta, float eps, int N2,
-                         const float* bias2, int epi2, int act, cudaStream_t st) {
-    static int configured_act[64] = {0}, configured_plain[64] = {0};  // one attribute cache per kernel instantiation
+                         const float* bias2, int epi2, int act, cudaStream_t st, bool pair = false) {
+    static int configured_act[64] = {0}, configured_plain[64] = {0}, configured_act2[64] = {0}, configured_plain2[64] = {0};  // per instantiation
     if (K1 % 8 != 0 || N2 % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs K % 8 == 0 and N % 8 == 0");
     GemmLnGemmParams p;
     p.M = M; p.K1 = K1; p.bias1 = bias1; p.gamma = gamma; p.beta = beta; p.eps = eps; p.N2 = N2; p.bias2 = bias2; p.act = act;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    if (pair) {
+        const int ctas = 2 * ((m_tiles + 1) / 2);  // whole clusters; a tile beyond M is all padding (loads zero-filled, stores clipped)
+        if (epi2 == EPI_BIAS_ACT_BF16) {
+            auto kern = gemm_ln_gemm_kernel<EPI_BIAS_ACT_BF16, 0, true>;
+            ensure_smem_attr(kern, kLg2SmemBytes, configured_act2);
+            launch_pdl_cluster(2, kern, dim3(ctas), dim3(kLnThreads), kLg2SmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
+        } else {
+            auto kern = gemm_ln_gemm_kernel<EPI_BIAS_BF16, 0, true>;
+            ensure_smem_attr(kern, kLg2SmemBytes, configured_plain2);
+            launch_pdl_cluster(2, kern, dim3(ctas), dim3(kLnThreads), kLg2SmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
+        }
+        return;
+    }
     if (epi2 == EPI_BIAS_ACT_BF16) {
         ensure_smem_attr(gemm_ln_gemm_kernel<EPI_BIAS_ACT_BF16>, kLg2SmemBytes, configured_act);
         launch_pdl(gemm_ln_gemm_kernel<EPI_BIAS_ACT_BF16>, dim3(m_tiles), dim3(kLnThreads), kLg2SmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
@@ -473,6 +487,7 @@ Encoder::Encoder(const std::string& dir, int device) {
     info_.num_heads = heads;
     info_.vocab_size = vocab;
     info_.max_position_embeddings = max_pos;
+    cfg_max_seq_len_ = max_pos;  // ModelMetadata::max_seq_len = config.json max_position_embeddings (the tokenizer's truncation length)
     info_.position_offset = pos_offset;
     act_ = act;
 
@@ -666,6 +681,12 @@ Encoder::Encoder(const std::string& dir, int device) {
         ld.t_w2 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, bn_h_, kGemmBlockK, 128);
         ld.t_wo_ln = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, kLnHalfN, kGemmBlockK, 128);  // GEMM + LN kernels: 192-row boxes
         ld.t_w2_ln = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, kLnHalfN, kGemmBlockK, 128);
+        if (H == kLnN) {  // CTA-pair chained kernels: each CTA loads 96 of the 192 rows of a weight tile
+            ld.t_wo_96 = make_tmap_2d(ld.wo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, H, kLnHalfN / 2, kGemmBlockK, 128);
+            ld.t_w2_96 = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, kLnHalfN / 2, kGemmBlockK, 128);
+            ld.t_w1_96 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, kLg2BN / 2, kGemmBlockK, 128);
+            ld.t_wqkv_96 = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, kLg2BN / 2, kGemmBlockK, 128);
+        }
         ld.t_w1_192 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, kLg2BN, kGemmBlockK, 128);      // chained kernels: 192-row boxes
         ld.t_wqkv_192 = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, kLg2BN, kGemmBlockK, 128);
         if (H == kFfH && I % kFfChunk == 0) {
@@ -694,6 +715,8 @@ Encoder::Encoder(const std::string& dir, int device) {
     // out-proj + LN1 -> FFN-up and FFN-down + LN2 -> next layer's QKV as one launch each (gemm_ln_gemm.cuh)
     chain_ = fused_ln_ && H == kLnN && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
     chain_embed_ = chain_ && getenv("KJC_CHAIN_EMBED") != nullptr;
+    // two CTAs per cluster share the weight tiles of the chained kernels (cta_group::2): needs an even number of CTAs resident
+    chain_pair_ = chain_ && num_sms_ % 2 == 0 && getenv("KJC_CHAIN_PAIR") != nullptr;
     if (const char* e = getenv("KJC_FP32_RESIDUAL")) set_fp32_residual(atoi(e));
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
@@ -837,15 +860,15 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         if (chain) {
             // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
             prof_begin(KJC_K_GEMM_FFN_UP, st);
-            launch_gemm_ln_gemm(w.t_ctx16, L.t_wo_ln, w.t_x16_io, w.t_x16, L.t_w1_192, w.t_h16_out32, M, H, L.bo, L.g1, L.be1, eps, I, L.b1,
-                                EPI_BIAS_ACT_BF16, act_, st);
+            launch_gemm_ln_gemm(w.t_ctx16, chain_pair_ ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, chain_pair_ ? L.t_w1_96 : L.t_w1_192, w.t_h16_out32, M, H,
+                                L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, chain_pair_);
             prof_end(st);
             // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
             if (li + 1 < layers_.size()) {
                 const LayerDev& Ln = layers_[li + 1];
-                launch_gemm_ln_gemm(w.t_h16, L.t_w2_ln, w.t_x16_io, w.t_x16, Ln.t_wqkv_192, w.t_qkv16_out32, M, I, L.b2, L.g2, L.be2, eps, 3 * H, Ln.bqkv,
-                                    EPI_BIAS_BF16, ACT_NONE, st);
+                launch_gemm_ln_gemm(w.t_h16, chain_pair_ ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16, chain_pair_ ? Ln.t_wqkv_96 : Ln.t_wqkv_192, w.t_qkv16_out32,
+                                    M, I, L.b2, L.g2, L.be2, eps, 3 * H, Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, chain_pair_);
             } else {
                 launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             }
@@ -1277,6 +1300,8 @@ void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const flo
     KJ_CUDA(cudaGetDevice(&dev));
     KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
     if ((M + kGemmBlockM - 1) / kGemmBlockM > prop.multiProcessorCount) throw Error(KJC_INVALID_CONFIG, "chained kernel: one 128-row tile per SM at most");
+    const bool pair = (epi2 & 16) != 0;  // epi2 + 16: the CTA-pair variant (cta_group::2, each CTA loads half of every weight tile)
+    epi2 &= 15;
     if (N2 > kLg2BiasMax) throw Error(KJC_INVALID_CONFIG, "chained kernel: N2 too large");
     const size_t Mp = std::max(M, 128), N2p = std::max(N2, kLg2BN);
     __nv_bfloat16 *dA, *dW, *dX, *dW2, *dO;
@@ -1301,12 +1326,12 @@ void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const flo
     KJ_CUDA(cudaMemcpy(dBt, beta, kLnN * 4, cudaMemcpyHostToDevice));
     KJ_CUDA(cudaMemcpy(dB2, bias2, static_cast<size_t>(N2) * 4, cudaMemcpyHostToDevice));
     CUtensorMap ta = make_tmap_2d(dA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mp, K1, kGemmBlockM, kGemmBlockK, 128);
-    CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kLnN, K1, kLnHalfN, kGemmBlockK, 128);
+    CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kLnN, K1, pair ? kLnHalfN / 2 : kLnHalfN, kGemmBlockK, 128);
     CUtensorMap tres = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, 32, kEpiChunkCols, 64);
     CUtensorMap tx = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, kGemmBlockM, kGemmBlockK, 128);
-    CUtensorMap tw2 = make_tmap_2d(dW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N2p, kLnN, kLg2BN, kGemmBlockK, 128);
+    CUtensorMap tw2 = make_tmap_2d(dW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N2p, kLnN, pair ? kLg2BN / 2 : kLg2BN, kGemmBlockK, 128);
     CUtensorMap to2 = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N2, 32, kEpiChunkCols, 64);
-    auto go = [&] { launch_gemm_ln_gemm(ta, tw, tres, tx, tw2, to2, M, K1, dB, dG, dBt, eps, N2, dB2, epi2, act, nullptr); };
+    auto go = [&] { launch_gemm_ln_gemm(ta, tw, tres, tx, tw2, to2, M, K1, dB, dG, dBt, eps, N2, dB2, epi2, act, nullptr, pair); };
     go();
     KJ_CUDA(cudaDeviceSynchronize());
     KJ_CUDA(cudaMemcpy(out_x_bf16, dX, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyDeviceToHost));

@@ -93,6 +93,7 @@ struct LayerDev {
     CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
     CUtensorMap t_w1_ffn, t_w1_ffn32, t_w2_ffn;  // fused FFN kernel: W1 boxes of 64 (one CTA) / 32 (CTA pair) rows, W2 boxes of 64 rows
     CUtensorMap t_wo_ln, t_w2_ln;        // 192-row boxes: weights of the GEMM + residual + LayerNorm kernels (hidden 384 / 768)
+    CUtensorMap t_wo_96, t_w2_96, t_w1_96, t_wqkv_96;  // 96-row boxes: the CTA-pair chained kernels load half a weight tile per CTA
     CUtensorMap t_w1_192, t_wqkv_192;    // 192-row boxes: phase-2 weights of the chained GEMM+LN -> GEMM kernel
     CUtensorMap t_wqkv_half, t_w1_half;  // box of block_n/2 rows: the CTA-pair GEMM loads half a weight tile per CTA
 };
@@ -109,6 +110,9 @@ class Encoder {
     int micro_batch(int seq_len) const;
     int64_t last_launches() const { return launches_; }
     bool chained() const { return chain_; }
+    // config.json's max_position_embeddings (meta.max_seq_len, pipeline/encoder/loader.rs:108); info().max_position_embeddings is
+    // the number of ROWS of the position table, which is what bounds the gather (embeddings/mod.rs:199-214)
+    int config_max_seq_len() const { return cfg_max_seq_len_; }
     // Residual stream precision: 0 = bf16 between kernels for every output (fastest), 1 = fp32 for KJC_OUT_HIDDEN only (default: the
     // hidden states then carry only the bf16 rounding of the GEMM operands, max-abs error < 2e-2 against the fp32 reference), 2 = fp32
     // for every output.  The fp32 mode runs the un-chained kernels: GEMM -> fp32 sums -> LayerNorm kernel.
@@ -178,6 +182,8 @@ class Encoder {
     const float *w_pre_ = nullptr, *b_pre_ = nullptr, *w_cls_ = nullptr, *b_cls_ = nullptr;
     std::vector<LayerDev> layers_;
     int fp32_residual_ = 1;
+    int cfg_max_seq_len_ = 0;
+    bool chain_pair_ = false;
     bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false, chain_embed_ = false;
     int lanes_ = 2;
     std::vector<Workspace> ws_;

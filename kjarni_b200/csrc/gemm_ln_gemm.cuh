@@ -18,6 +18,14 @@
 // TMEM: phase 1 accumulates the full 128 x 384 rows in columns [0, 384); phase 2 double-buffers 128 x 192 accumulators in
 // [0, 192) and [192, 384).  Warp roles as in gemm_ln.cuh (warp 0 TMA, warp 1 MMA, warp 2 TMEM, warps 4-15 epilogue).
 // Results are bit-identical to gemm_ln384_kernel followed by gemm_tcgen05_kernel<192, EPI>: same MMA shapes, same k order.
+//
+// kPair = true: two CTAs of a cluster (one TPC) run their two row tiles together with tcgen05.mma.cta_group::2 (M = 256: 128 rows
+// per CTA).  Each CTA loads only HALF of every weight tile (96 of the 192 rows of W1 / W2 per MMA) and the tensor core reads both
+// halves, so the weight bytes written into and read out of each SM's shared memory halve -- shared-memory bandwidth (TMA writes +
+// operand reads + epilogue staging against 128 B/clk) is what bounds these kernels.  Rows are still owned by
+// one CTA (its 128 TMEM lanes), so LayerNorm, the x' tile and both epilogues are unchanged; only the leader CTA issues MMAs, the
+// leader's barriers count both CTAs' TMA bytes, commits are multicast to both CTAs and the peer's epilogue warps release
+// accumulators / publish x' on the leader's barriers.
 #pragma once
 #include <cuda.h>
 
@@ -58,12 +66,13 @@ struct GemmLnGemmParams {
 // P1 = 1: phase 1 is the embedding front end -- word[id] (+ pos[offset + s]) (+ type[tt]) -> embed LayerNorm (reference:
 //         cpu/embeddings/mod.rs:181-326, transformer_encoder.rs:303-305), gathered by the epilogue warps (thread = token, 128
 //         columns each) straight into TMEM for the same two-pass LayerNorm; phase 2 is then layer 0's QKV projection.
-template <int EPI2, int P1 = 0>
+template <int EPI2, int P1 = 0, bool kPair = false>
 __global__ void __launch_bounds__(kLnThreads, 1)
 gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x,
                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out2, GemmLnGemmParams p) {
     static_assert(EPI2 == EPI_BIAS_BF16 || EPI2 == EPI_BIAS_ACT_BF16, "phase 2 stores bf16");
+    static_assert(!(kPair && P1 == 1), "the embedding front end runs one CTA per tile");
     extern __shared__ __align__(1024) uint8_t smem_lg[];
     uint8_t* smem = smem_lg;
     if (smem_u32(smem) & 1023) __trap();
@@ -90,8 +99,14 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* full2 = bars + 32;          // [3]
     uint64_t* empty2 = bars + 35;         // [3]
     uint64_t* acc_full = bars + 38;       // [2]
-    uint64_t* acc_empty = bars + 40;      // [2] (12 arrivals each)
-    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 42);
+    uint64_t* acc_empty = bars + 40;      // [2] (12 arrivals each; kPair: the leader's, 24 arrivals = both CTAs' epilogue warps)
+    uint64_t* x_pair = bars + 42;         // kPair, leader's: both CTAs' x' tiles are written (24 arrivals)
+    uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 43);
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    constexpr int kWRows = kPair ? kLnHalfN / 2 : kLnHalfN;          // weight rows this CTA loads per 192-column MMA tile
+    constexpr uint32_t kWBoxBytes = kWRows * kGemmBlockK * 2;        // 24 KB, or 12 KB per CTA of a pair
+    constexpr int kEpiArrivals = kPair ? 2 * kLnEpiWarps : kLnEpiWarps;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,15 +141,20 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_init(tmem_full1, 1);
         for (int i = 0; i < 2 * kLnEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         mbar_init(x_ready, kLnEpiWarps);
+        mbar_init(x_pair, kEpiArrivals);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], kLnEpiWarps);
+            mbar_init(&acc_empty[i], kEpiArrivals);
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_base_smem);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_alloc_2sm<512>(tmem_base_smem);
+        else tmem_alloc<512>(tmem_base_smem);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / TMA completion
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     pdl_wait();
@@ -147,10 +167,20 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             for (int kb = 0; kb < (P1 == 0 ? k_blocks1 : 0); ++kb) {
                 mbar_wait(&empty1[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full1[stage], kLnStageBytes);
-                tma_load_2d(smem_a + stage * kLnABytes, &tmap_a, &full1[stage], kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
-                tma_load_2d(smem_b + stage * kLnBBytes, &tmap_w, &full1[stage], kb * kGemmBlockK, 0, kEvictLast);
-                tma_load_2d(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, &full1[stage], kb * kGemmBlockK, kLnHalfN, kEvictLast);
+                if constexpr (kPair) {
+                    // this CTA's A rows and its 96-row half of each 192-row weight tile; all bytes are counted on the LEADER's barrier
+                    const uint32_t lbar = mapa_shared(smem_u32(&full1[stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full1[stage], 2 * (kLnABytes + 2 * kWBoxBytes));
+                    tma_load_2d_2sm(smem_a + stage * kLnABytes, &tmap_a, lbar, kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
+                    tma_load_2d_2sm(smem_b + stage * kLnBBytes, &tmap_w, lbar, kb * kGemmBlockK, static_cast<int>(rank) * kWRows, kEvictLast);
+                    tma_load_2d_2sm(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, lbar, kb * kGemmBlockK,
+                                    kLnHalfN + static_cast<int>(rank) * kWRows, kEvictLast);
+                } else {
+                    mbar_arrive_expect_tx(&full1[stage], kLnStageBytes);
+                    tma_load_2d(smem_a + stage * kLnABytes, &tmap_a, &full1[stage], kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
+                    tma_load_2d(smem_b + stage * kLnBBytes, &tmap_w, &full1[stage], kb * kGemmBlockK, 0, kEvictLast);
+                    tma_load_2d(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, &full1[stage], kb * kGemmBlockK, kLnHalfN, kEvictLast);
+                }
                 if (++stage == 3) {
                     stage = 0;
                     phase ^= 1;
@@ -165,15 +195,29 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const int s = it % kLg2Stages;
                     if (it == 2) mbar_wait(x_ready, 0);
                     mbar_wait(&empty2[s], ((it / kLg2Stages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full2[s], kLg2WBytes);
-                    tma_load_2d(w2_stage(s), &tmap_w2, &full2[s], kb * kGemmBlockK, nb * kLg2BN, kEvictLast);
+                    if constexpr (kPair) {
+                        if (leader) mbar_arrive_expect_tx(&full2[s], 2 * kWBoxBytes);
+                        tma_load_2d_2sm(w2_stage(s), &tmap_w2, mapa_shared(smem_u32(&full2[s]), 0), kb * kGemmBlockK,
+                                        nb * kLg2BN + static_cast<int>(rank) * kWRows, kEvictLast);
+                    } else {
+                        mbar_arrive_expect_tx(&full2[s], kLg2WBytes);
+                        tma_load_2d(w2_stage(s), &tmap_w2, &full2[s], kb * kGemmBlockK, nb * kLg2BN, kEvictLast);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // -------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, kLnHalfN);
+        // -------------------------------------------------------- MMA issuer (kPair: the leader CTA issues for both)
+        auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+            if constexpr (kPair) umma_f16_2sm(d, da, db, idesc, accum);
+            else umma_f16(d, da, db, idesc, accum);
+        };
+        auto commit = [&](uint64_t* bar) {
+            if constexpr (kPair) umma_commit_2sm(bar, 3);  // the barrier at this offset in both CTAs
+            else umma_commit(bar);
+        };
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kPair ? 2 * kGemmBlockM : kGemmBlockM, kLnHalfN);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < (P1 == 0 ? k_blocks1 : 0); ++kb) {
@@ -184,23 +228,25 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint64_t db1 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes + kLnHalfN * 128));
 #pragma unroll
                 for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                    umma_f16(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
-                    umma_f16(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+                    mma(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                    mma(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
                 }
-                umma_commit(&empty1[stage]);
-                if (kb == k_blocks1 - 1) umma_commit(tmem_full1);
+                commit(&empty1[stage]);
+                if (kb == k_blocks1 - 1) commit(tmem_full1);
                 if (++stage == 3) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
             // phase 2: A = the resident x' tile, W2 streamed; accumulators [0,192) / [192,384) alternate
-            mbar_wait(x_ready, 0);
+            if constexpr (kPair) mbar_wait_cluster(x_pair, 0);  // both CTAs' x' tiles (the peer's arrives are remote)
+            else mbar_wait(x_ready, 0);
             tc_fence_after();
             int it = 0;
             for (int nb = 0; nb < n2_tiles; ++nb) {
                 const int acc = nb & 1;
-                mbar_wait(&acc_empty[acc], ((nb >> 1) & 1) ^ 1);
+                if constexpr (kPair) mbar_wait_cluster(&acc_empty[acc], ((nb >> 1) & 1) ^ 1);
+                else mbar_wait(&acc_empty[acc], ((nb >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * kLg2BN;
                 for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
@@ -210,9 +256,9 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_x + kb * kLnABytes));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(w2_stage(s)));
 #pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    umma_commit(&empty2[s]);
-                    if (kb == kLg2KB - 1) umma_commit(&acc_full[acc]);
+                    for (int k = 0; k < kGemmBlockK / 16; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    commit(&empty2[s]);
+                    if (kb == kLg2KB - 1) commit(&acc_full[acc]);
                 }
             }
         }
@@ -409,7 +455,10 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             fence_proxy_async_smem();  // x' (generic-proxy stores) -> visible to the tensor core and to the TMA store below
             tc_fence_before();         // the LayerNorm accumulator is fully read: phase-2 MMAs may overwrite it
             __syncwarp();
-            if (lane == 0) mbar_arrive(x_ready);
+            if (lane == 0) {
+                mbar_arrive(x_ready);
+                if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(x_pair), 0));  // the leader's MMA warp waits for both tiles
+            }
         }
         // x' goes to global memory as well (residual of the next LayerNorm, pooling / hidden-state output): six 16 KB stores
         // straight out of the operand tile; rows >= M are clipped by the tensor map
@@ -435,7 +484,10 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (c == 1) {  // last load landed: release the accumulator before the math and stores of this chunk
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                        if (lane == 0) {
+                            if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[acc]), 0));
+                            else mbar_arrive(&acc_empty[acc]);
+                        }
                     }
                     const int col0 = nb * kLg2BN + part * 64 + c * 32;
                     if (col0 < p.N2) {
@@ -486,10 +538,12 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // peer shared memory / barriers stay valid until both CTAs are done
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_2sm<512>(tmem_base);
+        else tmem_dealloc<512>(tmem_base);
     }
 }
 

@@ -28,9 +28,10 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
     KJ_CUDA(cudaMalloc(&rows_, capacity * dim * sizeof(float)));
     KJ_CUDA(cudaMalloc(&norms_, capacity * sizeof(float) + 64));  // slack: tail bulk copies round up to 16 B
     // tensor-core filter path: bf16 shadow + 1/|r| (dims the resident 128-query tile supports)
-    gemm_ok_ = dim % kSgBK == 0 && dim <= kSgMaxD && !getenv("KJC_SCAN_NO_GEMM");
+    gemm_ok_ = dim % kSgBK == 0 && dim <= kSgMaxDStream && !getenv("KJC_SCAN_NO_GEMM");
     if (const char* e = getenv("KJC_SCAN_EPS")) filter_eps_ = static_cast<float>(atof(e));
     if (const char* e = getenv("KJC_SCAN_GEMM_MIN_Q")) filter_min_q_ = std::max(1, atoi(e));
+    scan_q8_ = getenv("KJC_SCAN_NO_Q8") == nullptr;
     if (gemm_ok_) {
         const uint64_t cap16 = std::max<uint64_t>(capacity, kSgRows);  // at least one TMA box of rows
         KJ_CUDA(cudaMalloc(&rows16_, cap16 * dim * sizeof(__nv_bfloat16)));
@@ -57,10 +58,18 @@ Index::~Index() {
     if (stream_) cudaStreamDestroy(stream_);
 }
 
+// |row| + bf16 shadow: NCH = float4 chunks per lane (dim <= 384: 3, <= 768: 6, <= 1024: 8)
+static void launch_row_prep(const float* rows, float* norms, __nv_bfloat16* rows16, size_t n, int D, int normalise, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>((n + 7) / 8);
+    if (D <= 384) row_prep_kernel<3><<<grid, 256, 0, st>>>(rows, norms, rows16, n, D, normalise);
+    else if (D <= 768) row_prep_kernel<6><<<grid, 256, 0, st>>>(rows, norms, rows16, n, D, normalise);
+    else row_prep_kernel<8><<<grid, 256, 0, st>>>(rows, norms, rows16, n, D, normalise);
+}
+
 void Index::compute_norms(uint64_t row0, uint64_t n, cudaStream_t st) {
     if (n == 0) return;
-    if (gemm_ok_)  // dim <= 384: three float4 per lane
-        row_prep_kernel<3><<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, rows16_ + row0 * dim_, n, dim_, 1);
+    if (gemm_ok_)
+        launch_row_prep(rows_ + row0 * dim_, norms_ + row0, rows16_ + row0 * dim_, n, dim_, 1, st);
     else
         row_norm_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, st>>>(rows_ + row0 * dim_, norms_ + row0, n, dim_);
     KJ_CUDA(cudaGetLastError());
@@ -142,20 +151,35 @@ void Index::get_rows(uint64_t row, uint64_t n, float* out) const {
     KJ_CUDA(cudaMemcpy(out, rows_ + row * dim_, n * dim_ * sizeof(float), cudaMemcpyDeviceToHost));
 }
 
-template <int QT, int NCH>
+template <int QT, int NCH, int CW = kScanConsumerWarps, int RU = 1>
 static void launch_scan_inst(ScanParams p, int grid, cudaStream_t st) {
     static int configured[64] = {0};
     // rows per stage / stage count: as much as fits in ~200 KB next to the top-k lists
     p.rows_per_stage = p.D <= 512 ? 32 : 16;
-    const size_t budget = 200 * 1024 - scan_list_bytes(QT, p.k) - 512;
+    const size_t budget = 200 * 1024 - scan_list_bytes(QT, p.k, CW) - 512;
     p.nstages = static_cast<int>(std::min<size_t>(4, budget / scan_stage_bytes(p.D, p.rows_per_stage)));
     if (p.nstages < 2) throw Error(KJC_INVALID_CONFIG, "index dimension too large for the scan pipeline");
-    const size_t smem = scan_smem_bytes(p.D, p.rows_per_stage, p.nstages, QT, p.k);
-    auto kern = scan_topk_kernel<QT, NCH>;
+    const size_t smem = scan_smem_bytes(p.D, p.rows_per_stage, p.nstages, QT, p.k, CW);
+    auto kern = scan_topk_kernel<QT, NCH, CW, RU>;
     ensure_smem_attr(kern, static_cast<int>(smem), configured);
-    kern<<<grid, kScanCtaThreads, smem, st>>>(p);
+    kern<<<grid, (CW + 1) * 32, smem, st>>>(p);
     KJ_CUDA(cudaGetLastError());
 }
+// 8 queries per warp, one warp group; variant (KJC_SCAN_Q8_VARIANT): 0 = 8 warps x 2 rows per turn, 1 = 8 warps x 4 rows, 2 = 12 warps x 1 row
+static void launch_scan_q8(const ScanParams& p, int grid, cudaStream_t st) {
+    static const int variant = getenv("KJC_SCAN_Q8_VARIANT") ? atoi(getenv("KJC_SCAN_Q8_VARIANT")) : 0;
+    const int nch = (p.D + 127) / 128;
+    if (nch >= 3) {
+        if (variant == 1) launch_scan_inst<8, 3, 8, 4>(p, grid, st);
+        else if (variant == 2) launch_scan_inst<8, 3, 12, 1>(p, grid, st);
+        else launch_scan_inst<8, 3, 8, 2>(p, grid, st);
+    } else if (nch == 2) {
+        launch_scan_inst<8, 2, 8, 2>(p, grid, st);
+    } else {
+        launch_scan_inst<8, 1, 8, 2>(p, grid, st);
+    }
+}
+
 template <int QT>
 static void launch_scan_qt(const ScanParams& p, int grid, cudaStream_t st) {
     const int nch = (p.D + 127) / 128;
@@ -184,7 +208,9 @@ void Index::search_device(const float* d_q, int nq, int k, int mode, uint64_t* d
     if (!st) st = stream_;
     launches_ = 0;
     // many queries: tensor-core filter + exact rescoring; few queries: the exact HBM-bound scan
-    if (gemm_ok_ && nq >= filter_min_q_ && 2 * k <= kSgC && len_ > 0) search_gemm(d_q, nq, k, mode, d_ids, d_scores, d_counts, st, may_sync);
+    // the filter keeps C >= 2k approximate candidates per query: C = 32 for k <= 16, 128 for k <= 64 (a reranking Searcher fetches
+    // top_k * 5 = 50); beyond that the exact scan
+    if (gemm_ok_ && nq >= filter_min_q_ && 2 * k <= kSgCWide && len_ > 0) search_gemm(d_q, nq, k, mode, d_ids, d_scores, d_counts, st, may_sync);
     else search_exact(d_q, nq, k, mode, d_ids, d_scores, d_counts, st);
 }
 
@@ -218,6 +244,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
     const uint32_t n_tiles = static_cast<uint32_t>((len_ + kSgRows - 1) / kSgRows);
     const int grid = static_cast<int>(std::min<uint32_t>(num_sms_, n_tiles));
     const int qb_max = std::min(nq_all, 4096);  // queries per pass over the shard (bounds the candidate buffers)
+    const int C = 2 * k <= kSgC ? kSgC : kSgCWide;  // approximate candidates kept per query
     {
         const size_t q16 = static_cast<size_t>(std::max(qb_max, kSgQ)) * dim_;
         if (q16 > q16_cap_) {
@@ -238,7 +265,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
             KJ_CUDA(cudaMalloc(&d_gc_i_, gc * 4));
             gc_cap_ = gc;
         }
-        const size_t am = static_cast<size_t>(qb_max) * kSgC;
+        const size_t am = static_cast<size_t>(qb_max) * C;
         if (am > am_cap_) {
             if (d_am_s_) cudaFree(d_am_s_);
             if (d_am_i_) cudaFree(d_am_i_);
@@ -270,7 +297,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         float* d_thr0 = d_seed_ + static_cast<size_t>(kSgSeedGroupsMax) * nq;    // [nq]
 
         // |q| and the bf16 copy of the queries (rows beyond nq of the last 128-query tile are zero-filled by TMA)
-        row_prep_kernel<3><<<(nq + 7) / 8, 256, 0, st>>>(d_q, d_qn_, d_q16_, static_cast<size_t>(nq), dim_, 0);
+        launch_row_prep(d_q, d_qn_, d_q16_, static_cast<size_t>(nq), dim_, 0, st);
         KJ_CUDA(cudaGetLastError());
         if (nq < kSgQ)
             KJ_CUDA(cudaMemsetAsync(d_q16_ + static_cast<size_t>(nq) * dim_, 0, static_cast<size_t>(kSgQ - nq) * dim_ * 2, st));
@@ -281,14 +308,14 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         ScanGemmParams sp;
         sp.thr0 = nullptr; sp.cand_scores = d_gc_s_; sp.cand_ids = d_gc_i_; sp.cand_cnt = d_cnt;
         sp.seed_max = nullptr; sp.n_rows = static_cast<uint32_t>(len_); sp.n_tiles = n_tiles; sp.n_tiles_total = n_tiles;
-        sp.seed_chunks = 0; sp.D = dim_; sp.Q = nq; sp.R = env_R; sp.dbg = env_dbg;
+        sp.seed_chunks = 0; sp.D = dim_; sp.Q = nq; sp.R = env_R; sp.dbg = env_dbg; sp.stream_a = dim_ > kSgMaxD ? 1 : 0;
         // ---- seed pass
         int seed_groups = 0;
         if (len_ > static_cast<uint64_t>(kSgCap) && !env_no_seed) {
             ScanGemmParams ss = sp;
             ss.seed_max = d_seed;
             int sgrid;
-            if (n_tiles < static_cast<uint32_t>(kSgC)) {  // small shard: every tile, one group per 32-row chunk
+            if (n_tiles < static_cast<uint32_t>(std::min(C, kSgSeedGroupsMax / 8))) {  // small shard: every tile, one group per 32-row chunk
                 ss.seed_chunks = 1; ss.n_tiles = n_tiles; ss.R = 1; sgrid = static_cast<int>(n_tiles);
                 seed_groups = static_cast<int>(n_tiles) * 8;
             } else {  // evenly spaced sample tiles, 8 per CTA, one group per CTA
@@ -300,7 +327,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
             KJ_CUDA(cudaGetLastError());
             ++launches_;
         }
-        scan_seed_select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_seed, seed_groups, nq, d_thr0);  // 0 groups: thr0 = -inf
+        scan_seed_select_kernel<<<(nq + 7) / 8, 256, 0, st>>>(d_seed, seed_groups, nq, d_thr0, C);  // 0 groups: thr0 = -inf
         KJ_CUDA(cudaGetLastError());
         ++launches_;
         // ---- filter pass
@@ -310,7 +337,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         ++launches_;
         CandSelectParams cs;
         cs.cand_scores = d_gc_s_; cs.cand_ids = d_gc_i_; cs.cand_cnt = d_cnt; cs.id_base = id_base_;
-        cs.out_scores = d_am_s_; cs.out_ids = d_am_i_; cs.overflow = d_overflow;
+        cs.out_scores = d_am_s_; cs.out_ids = d_am_i_; cs.overflow = d_overflow; cs.C = C;
         scan_cand_select_kernel<<<nq, 256, 0, st>>>(cs);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
@@ -319,7 +346,8 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         r.out_ids = d_ids; r.out_scores = d_scores; r.out_counts = d_counts; r.overflow = d_overflow; r.thr0 = d_thr0;
         r.flags = d_flags_; r.n_flagged = d_nflag_;
         r.eps = filter_eps_; r.D = dim_; r.Q = nq; r.k = k; r.mode = mode;
-        scan_rescore_kernel<<<(nq + 7) / 8, 256, 0, st>>>(r);
+        if (C == kSgC) scan_rescore_kernel<1><<<(nq + 7) / 8, 256, 0, st>>>(r);
+        else scan_rescore_kernel<kSgCWide / 32><<<(nq + 7) / 8, 256, 0, st>>>(r);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
         if (!may_sync) {
@@ -382,6 +410,13 @@ void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_
         for (int q0 = 0; q0 < nq;) {
             p.q0 = q0;
             const int rem = nq - q0;
+            if (scan_q8_ && rem > 4 && k <= 32 && dim_ <= 384) {  // 5..8 queries: one warp group scores all of them per row
+                p.ngroups = 1;
+                launch_scan_q8(p, grid, st);
+                q0 += 8;
+                ++launches_;
+                continue;
+            }
             int qt = qt_max;
             while (qt > 1 && qt / 2 >= rem) qt /= 2;  // smallest per-warp tile that still covers the remainder in one group
             p.ngroups = rem > qt ? 2 : 1;
@@ -395,6 +430,7 @@ void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_
     MergeParams m;
     m.in_scores = d_cand_s_; m.in_ids32 = d_cand_i_; m.in_ids64 = nullptr; m.id_base = id_base_; m.qnorms = d_qn_;
     m.out_scores = d_scores; m.out_ids = d_ids; m.out_counts = d_counts; m.L = len_ > 0 ? grid : 0; m.Q = nq; m.k = k; m.mode = mode;
+    m.ids_stride = m.scores_stride = 0;
     launch_topk_merge(m, st);
     ++launches_;
 }
@@ -434,8 +470,10 @@ void Index::search_host(const float* q, int nq, int k, int mode, uint64_t* ids, 
 }
 
 void merge_lists_u64(const uint64_t* d_ids, const float* d_scores, int n_lists, int nq, int k, uint64_t* d_out_ids, float* d_out_scores,
-                     int32_t* d_out_counts, cudaStream_t st) {
+                     int32_t* d_out_counts, cudaStream_t st, size_t ids_stride, size_t scores_stride) {
     MergeParams m;
+    m.ids_stride = ids_stride;
+    m.scores_stride = scores_stride;
     m.in_scores = d_scores; m.in_ids32 = nullptr; m.in_ids64 = d_ids; m.id_base = 0; m.qnorms = nullptr;
     m.out_scores = d_out_scores; m.out_ids = d_out_ids; m.out_counts = d_out_counts; m.L = n_lists; m.Q = nq; m.k = k;
     m.mode = SCAN_VECTORSTORE;

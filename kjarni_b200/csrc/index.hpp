@@ -8,8 +8,12 @@
 
 namespace kj {
 
+// list l of the candidates starts at d_ids + l * stride / d_scores + l * stride (stride in elements; 0 = nq * k, densely packed)
 void merge_lists_u64(const uint64_t* d_ids, const float* d_scores, int n_lists, int nq, int k, uint64_t* d_out_ids, float* d_out_scores,
-                     int32_t* d_out_counts, cudaStream_t st);
+                     int32_t* d_out_counts, cudaStream_t st, size_t ids_stride = 0, size_t scores_stride = 0);
+
+// Bytes of one shard's packed candidate record: [nq,k] u64 ids | [nq,k] f32 scores, rounded up to 16 bytes.
+inline size_t packed_record_bytes(int nq, int k) { return (static_cast<size_t>(nq) * k * 12 + 15) & ~static_cast<size_t>(15); }
 
 class Index {
   public:
@@ -58,6 +62,7 @@ class Index {
     int64_t launches_ = 0;
     // tensor-core filter path (scan_gemm.cuh): bf16 shadow of the rows, 1/|r|, staging for query tiles and candidates
     bool gemm_ok_ = false;
+    bool scan_q8_ = true;  // exact scan: 8-query passes as one warp group (scan.cuh <8, NCH, 8, 2>); KJC_SCAN_NO_Q8 = the two-group kernel
     float filter_eps_ = 0.0045f;
     int filter_min_q_ = 1;  // the filter pass reads half the bytes of the exact scan, so it wins from a single query on
     __nv_bfloat16 *rows16_ = nullptr, *d_q16_ = nullptr;

@@ -187,11 +187,11 @@ class ShardedIndex {
         for (size_t p = 0; p < bufs_.size(); ++p) {
             cudaSetDevice(devs_[p]);
             Buf& b = bufs_[p];
-            for (void* q : {(void*)b.d_q, (void*)b.d_ids, (void*)b.d_sc}) if (q) cudaFree(q);
+            for (void* q : {(void*)b.d_q, (void*)b.d_rec}) if (q) cudaFree(q);
             if (b.done) cudaEventDestroy(b.done);
         }
         cudaSetDevice(devs_[0]);
-        for (void* q : {(void*)g_ids_, (void*)g_sc_, (void*)o_ids_, (void*)o_sc_, (void*)o_cnt_}) if (q) cudaFree(q);
+        for (void* q : {(void*)g_rec_, (void*)o_ids_, (void*)o_sc_, (void*)o_cnt_}) if (q) cudaFree(q);
         if (h_out_) cudaFreeHost(h_out_);
         if (stream0_) cudaStreamDestroy(stream0_);
     }
@@ -241,12 +241,12 @@ class ShardedIndex {
         }
         std::lock_guard<std::mutex> lock(mu_);
         const size_t qe = static_cast<size_t>(nq) * dim_, oe = static_cast<size_t>(nq) * k;
+        const size_t rec = packed_record_bytes(nq, k);  // one shard's candidates: ids | scores, one peer copy
         KJ_CUDA(cudaSetDevice(devs_[0]));
         if (oe > out_cap_) {
-            for (void* p : {(void*)g_ids_, (void*)g_sc_, (void*)o_ids_, (void*)o_sc_, (void*)o_cnt_}) if (p) cudaFree(p);
+            for (void* p : {(void*)g_rec_, (void*)o_ids_, (void*)o_sc_, (void*)o_cnt_}) if (p) cudaFree(p);
             if (h_out_) cudaFreeHost(h_out_);
-            KJ_CUDA(cudaMalloc(&g_ids_, oe * ns * 8));
-            KJ_CUDA(cudaMalloc(&g_sc_, oe * ns * 4));
+            KJ_CUDA(cudaMalloc(&g_rec_, rec * ns));
             KJ_CUDA(cudaMalloc(&o_ids_, oe * 8));
             KJ_CUDA(cudaMalloc(&o_sc_, oe * 4));
             KJ_CUDA(cudaMalloc(&o_cnt_, (oe + 1) * 4));  // nq <= oe
@@ -261,26 +261,26 @@ class ShardedIndex {
                 KJ_CUDA(cudaMalloc(&b.d_q, qe * 4));
                 b.q_cap = qe;
             }
-            if (oe > b.o_cap) {
-                if (b.d_ids) cudaFree(b.d_ids);
-                if (b.d_sc) cudaFree(b.d_sc);
-                KJ_CUDA(cudaMalloc(&b.d_ids, oe * 8));
-                KJ_CUDA(cudaMalloc(&b.d_sc, oe * 4));
-                b.o_cap = oe;
+            if (rec > b.o_cap) {
+                if (b.d_rec) cudaFree(b.d_rec);
+                KJ_CUDA(cudaMalloc(&b.d_rec, rec));
+                b.o_cap = rec;
             }
+            uint64_t* d_ids = reinterpret_cast<uint64_t*>(b.d_rec);
+            float* d_sc = reinterpret_cast<float*>(b.d_rec + oe * 8);
             cudaStream_t st = shards_[p]->stream();
             // straight from the caller's buffer, like Index::search_host: each device's thread stages its own copy concurrently
             KJ_CUDA(cudaMemcpyAsync(b.d_q, q, qe * 4, cudaMemcpyHostToDevice, st));
             // per-shard top-k, proven exact (queries the tensor-core filter cannot prove are re-run on the exact scan before this returns)
-            shards_[p]->search_device(b.d_q, nq, k, mode, b.d_ids, b.d_sc, nullptr, st, /*may_sync=*/true);
-            // candidate gather: this shard's [nq,k] lists into slot p of GPU 0's buffer (NVLink peer copy; 12 B per candidate)
-            KJ_CUDA(cudaMemcpyPeerAsync(g_ids_ + p * oe, devs_[0], b.d_ids, devs_[p], oe * 8, st));
-            KJ_CUDA(cudaMemcpyPeerAsync(g_sc_ + p * oe, devs_[0], b.d_sc, devs_[p], oe * 4, st));
+            shards_[p]->search_device(b.d_q, nq, k, mode, d_ids, d_sc, nullptr, st, /*may_sync=*/true);
+            // candidate gather: this shard's packed record into slot p of GPU 0's buffer (ONE NVLink peer copy, 12 B per candidate)
+            KJ_CUDA(cudaMemcpyPeerAsync(g_rec_ + p * rec, devs_[0], b.d_rec, devs_[p], rec, st));
             KJ_CUDA(cudaEventRecord(b.done, st));
         });
         KJ_CUDA(cudaSetDevice(devs_[0]));
         for (int p = 0; p < ns; ++p) KJ_CUDA(cudaStreamWaitEvent(stream0_, bufs_[p].done, 0));
-        merge_lists_u64(g_ids_, g_sc_, ns, nq, k, o_ids_, o_sc_, o_cnt_, stream0_);
+        merge_lists_u64(reinterpret_cast<const uint64_t*>(g_rec_), reinterpret_cast<const float*>(g_rec_ + oe * 8), ns, nq, k, o_ids_, o_sc_, o_cnt_,
+                        stream0_, rec / 8, rec / 4);
         uint8_t* h = static_cast<uint8_t*>(h_out_);
         KJ_CUDA(cudaMemcpyAsync(h, o_ids_, oe * 8, cudaMemcpyDeviceToHost, stream0_));
         KJ_CUDA(cudaMemcpyAsync(h + oe * 8, o_sc_, oe * 4, cudaMemcpyDeviceToHost, stream0_));
@@ -294,8 +294,7 @@ class ShardedIndex {
   private:
     struct Buf {
         float* d_q = nullptr;
-        uint64_t* d_ids = nullptr;
-        float* d_sc = nullptr;
+        uint8_t* d_rec = nullptr;  // [nq,k] u64 ids | [nq,k] f32 scores
         size_t q_cap = 0, o_cap = 0;
         cudaEvent_t done = nullptr;
     };
@@ -324,8 +323,9 @@ class ShardedIndex {
     std::vector<Buf> bufs_;
     std::mutex mu_;
     cudaStream_t stream0_ = nullptr;
-    uint64_t *g_ids_ = nullptr, *o_ids_ = nullptr;
-    float *g_sc_ = nullptr, *o_sc_ = nullptr;
+    uint8_t* g_rec_ = nullptr;  // n_shards packed records on device 0
+    uint64_t* o_ids_ = nullptr;
+    float* o_sc_ = nullptr;
     int32_t* o_cnt_ = nullptr;
     void* h_out_ = nullptr;
     size_t out_cap_ = 0;

@@ -96,20 +96,25 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 
 inline size_t scan_stage_bytes(int D, int rows_per_stage) { return static_cast<size_t>(rows_per_stage) * D * 4 + ((rows_per_stage * 4 + 15) & ~15); }
-inline size_t scan_list_bytes(int QT, int k) { return static_cast<size_t>(kScanConsumerWarps) * QT * k * 8; }
-inline size_t scan_smem_bytes(int D, int rows_per_stage, int nstages, int QT, int k) {
-    return 128 /*align*/ + nstages * scan_stage_bytes(D, rows_per_stage) + 2 * nstages * 8 + scan_list_bytes(QT, k);
+inline size_t scan_list_bytes(int QT, int k, int consumer_warps = kScanConsumerWarps) { return static_cast<size_t>(consumer_warps) * QT * k * 8; }
+inline size_t scan_smem_bytes(int D, int rows_per_stage, int nstages, int QT, int k, int consumer_warps = kScanConsumerWarps) {
+    return 128 /*align*/ + nstages * scan_stage_bytes(D, rows_per_stage) + 2 * nstages * 8 + scan_list_bytes(QT, k, consumer_warps);
 }
 
-// QT queries per warp (1/2/4), NCH = ceil(D/128) float4 chunks per lane.
+// QT queries per warp (1/2/4/8), NCH = ceil(D/128) float4 chunks per lane, CW consumer warps, RU rows per warp per turn.
 // One CTA per SM: a producer thread streams chunks of `rows_per_stage` consecutive rows (+ their cached norms) through
 // a ring of shared-memory stages with cp.async.bulk (~190 KB in flight per SM); 16 consumer warps in 1 or 2 groups take
 // one row each per turn from the landed stage (with 2 groups, both read every row and score different queries).
 // Dot products run on the packed FFMA2 pipe; the QT sums of a row are reduced across the warp with a transposed
 // butterfly, so the warp ends up with one finished score per 32/QT lanes and does one divide per row.
-template <int QT, int NCH>
-__global__ void __launch_bounds__(kScanCtaThreads, 1) scan_topk_kernel(ScanParams p) {
-    constexpr int LOGQ = QT == 4 ? 2 : (QT == 2 ? 1 : 0);
+//
+// The 8-query pass at dim <= 384 runs as <8, NCH, 8, 2>: ONE group of 8 warps scores all 8 queries of a row (round 1 ran two groups
+// of 4 queries, i.e. every row was fetched from shared memory and reduced twice: 232 issue slots per row, 57 % issue utilisation,
+// 43 % of HBM in ncu), the queries take 96 registers per thread (hence 8 warps, not 16), and every warp works on two rows at a
+// time so that the two dependent chains (FFMA2 -> butterfly -> divide) overlap.
+template <int QT, int NCH, int CW = kScanConsumerWarps, int RU = 1>
+__global__ void __launch_bounds__((CW + 1) * 32, 1) scan_topk_kernel(ScanParams p) {
+    constexpr int LOGQ = QT == 8 ? 3 : (QT == 4 ? 2 : (QT == 2 ? 1 : 0));
     constexpr int GROUP_SHIFT = 5 - LOGQ;  // lanes per query group = 1 << GROUP_SHIFT
     extern __shared__ uint8_t smem_scan_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_scan_raw) + 127) & ~uintptr_t(127));
@@ -122,23 +127,23 @@ __global__ void __launch_bounds__(kScanCtaThreads, 1) scan_topk_kernel(ScanParam
     uint64_t* empty_bar = full_bar + nst;
     uint8_t* lists = reinterpret_cast<uint8_t*>(empty_bar + nst);
     float* all_sc = reinterpret_cast<float*>(lists);
-    uint32_t* all_id = reinterpret_cast<uint32_t*>(lists + static_cast<size_t>(kScanConsumerWarps) * QT * k * 4);
-    __shared__ int s_cnt[kScanConsumerWarps][QT];
+    uint32_t* all_id = reinterpret_cast<uint32_t*>(lists + static_cast<size_t>(CW) * QT * k * 4);
+    __shared__ int s_cnt[CW][QT];
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < nst; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], kScanConsumerWarps);
+            mbar_init(&empty_bar[i], CW);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
     const size_t n_chunks = (p.n_rows + rps - 1) / rps;
-    const int wpg = kScanConsumerWarps / p.ngroups;  // warps per group
+    const int wpg = CW / p.ngroups;  // warps per group
     const int nq_pass = min(QT * p.ngroups, p.Q - p.q0);
 
-    if (warp == kScanConsumerWarps) {
+    if (warp == CW) {
         // ------------------------------------------------------------ producer
         if (lane == 0) {
             int it = 0;
@@ -191,54 +196,75 @@ __global__ void __launch_bounds__(kScanCtaThreads, 1) scan_topk_kernel(ScanParam
             const uint8_t* sbase = smem + stage * stage_bytes;
             const float* snorm = reinterpret_cast<const float*>(sbase + stage_rows_bytes);
             if (nq > 0) {
-                for (int r = wg; r < rows_in; r += wpg) {
-                    const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(sbase + r * row_bytes);
-                    ulonglong2 v[NCH];
+                const uint32_t sbase_u32 = smem_u32(sbase);
+                for (int r0 = wg; r0 < rows_in; r0 += RU * wpg) {
+                    // RU rows of this warp's turn: r0, r0 + wpg, ...  (a row index >= rows_in reads stale shared memory and is discarded)
+                    float sc_row[RU];
 #pragma unroll
-                    for (int cc = 0; cc < NCH; ++cc) v[cc] = (lane + 32 * cc) * 4 < D ? rp[lane + 32 * cc] : make_ulonglong2(0ull, 0ull);
-                    const float rn = snorm[r];
-                    float acc[QT];
-#pragma unroll
-                    for (int t = 0; t < QT; ++t) {
-                        uint64_t a2 = 0ull;  // (0.f, 0.f)
+                    for (int u = 0; u < RU; ++u) {
+                        const int r = r0 + u * wpg;
+                        const uint32_t raddr = sbase_u32 + static_cast<uint32_t>(min(r, rps - 1)) * static_cast<uint32_t>(row_bytes);
+                        ulonglong2 v[NCH];
 #pragma unroll
                         for (int cc = 0; cc < NCH; ++cc) {
-                            a2 = f2_fma(v[cc].x, q[t][cc][0], a2);
-                            a2 = f2_fma(v[cc].y, q[t][cc][1], a2);
-                        }
-                        float lo, hi;
-                        f2_unpack(a2, lo, hi);
-                        acc[t] = lo + hi;
-                    }
-#pragma unroll
-                    for (int step = 0; step < 5; ++step) {
-                        const int o = 16 >> step;
-                        if (step < LOGQ) {
-                            const bool upper = (lane & o) != 0;
-                            const int half = QT >> (step + 1);
-#pragma unroll
-                            for (int i = 0; i < half; ++i) {
-                                const float send = upper ? acc[i] : acc[i + half];
-                                const float keep = upper ? acc[i + half] : acc[i];
-                                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            if ((lane + 32 * cc) * 4 < D) {
+                                const uint4 t = ld_shared_v4(raddr + (lane + 32 * cc) * 16);
+                                v[cc].x = (static_cast<unsigned long long>(t.y) << 32) | t.x;
+                                v[cc].y = (static_cast<unsigned long long>(t.w) << 32) | t.z;
+                            } else {
+                                v[cc] = make_ulonglong2(0ull, 0ull);
                             }
-                        } else {
-                            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
                         }
+                        const float rn = snorm[min(r, rps - 1)];
+                        float acc[QT];
+#pragma unroll
+                        for (int t = 0; t < QT; ++t) {
+                            uint64_t a2 = 0ull;  // (0.f, 0.f)
+#pragma unroll
+                            for (int cc = 0; cc < NCH; ++cc) {
+                                a2 = f2_fma(v[cc].x, q[t][cc][0], a2);
+                                a2 = f2_fma(v[cc].y, q[t][cc][1], a2);
+                            }
+                            float lo, hi;
+                            f2_unpack(a2, lo, hi);
+                            acc[t] = lo + hi;
+                        }
+#pragma unroll
+                        for (int step = 0; step < 5; ++step) {
+                            const int o = 16 >> step;
+                            if (step < LOGQ) {
+                                const bool upper = (lane & o) != 0;
+                                const int half = QT >> (step + 1);
+#pragma unroll
+                                for (int i = 0; i < half; ++i) {
+                                    const float send = upper ? acc[i] : acc[i + half];
+                                    const float keep = upper ? acc[i + half] : acc[i];
+                                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                                }
+                            } else {
+                                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+                            }
+                        }
+                        float sres;
+                        if (p.mode == SCAN_SEGMENT) sres = rn < 1e-9f ? 0.0f : acc[0] / (qn_mine * rn);
+                        else sres = acc[0] / fmaxf(qn_mine * rn, 1e-9f);
+                        sc_row[u] = sres;
                     }
-                    float s;
-                    if (p.mode == SCAN_SEGMENT) s = rn < 1e-9f ? 0.0f : acc[0] / (qn_mine * rn);
-                    else s = acc[0] / fmaxf(qn_mine * rn, 1e-9f);
-                    uint32_t need = __ballot_sync(0xffffffffu, owner && s > thr_mine);
-                    while (need) {
-                        const int b = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int t = b >> GROUP_SHIFT;
-                        const float sb = __shfl_sync(0xffffffffu, s, b);
-                        int n = __shfl_sync(0xffffffffu, cnt_mine, b);
-                        float thr;
-                        warp_topk_insert(lsc + t * k, lid + t * k, k, n, thr, sb, static_cast<uint32_t>(row0 + r), lane);
-                        if (t_mine == t) { cnt_mine = n; thr_mine = thr; }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) {  // ascending row order: equal scores keep ascending ids in the lists
+                        const int r = r0 + u * wpg;
+                        const float s = sc_row[u];
+                        uint32_t need = __ballot_sync(0xffffffffu, owner && r < rows_in && s > thr_mine);
+                        while (need) {
+                            const int b = __ffs(need) - 1;
+                            need &= need - 1;
+                            const int t = b >> GROUP_SHIFT;
+                            const float sb = __shfl_sync(0xffffffffu, s, b);
+                            int n = __shfl_sync(0xffffffffu, cnt_mine, b);
+                            float thr;
+                            warp_topk_insert(lsc + t * k, lid + t * k, k, n, thr, sb, static_cast<uint32_t>(row0 + r), lane);
+                            if (t_mine == t) { cnt_mine = n; thr_mine = thr; }
+                        }
                     }
                 }
             }
@@ -249,7 +275,7 @@ __global__ void __launch_bounds__(kScanCtaThreads, 1) scan_topk_kernel(ScanParam
     }
     __syncthreads();
     // merge the per-warp lists of each query (the wpg warps of its group) into the CTA's output list
-    for (int tq = warp; tq < nq_pass; tq += kScanConsumerWarps + 1) {
+    for (int tq = warp; tq < nq_pass; tq += CW + 1) {
         const int grp = tq / QT, t = tq % QT;
         const int src_warp = grp * wpg + min(lane, wpg - 1);
         // lanes 0..wpg-1 each own the head of one warp's list; k rounds of a wpg-way argmax
@@ -292,6 +318,8 @@ struct MergeParams {
     uint64_t* out_ids;        // [Q, k]  kNoId64 = empty
     int* out_counts;          // [Q] or nullptr
     int L, Q, k, mode;
+    size_t ids_stride, scores_stride;  // elements between consecutive lists of in_ids / in_scores (0 = Q * k, densely packed); they
+                                       // differ for the packed per-rank record (ids | scores) of the one-collective gather
 };
 __global__ void __launch_bounds__(256) topk_merge_kernel(MergeParams p) {
     const int qi = blockIdx.x;
@@ -313,12 +341,14 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(MergeParams p) {
             for (int l = tid; l < p.L; l += 256) {
                 const int h = heads[l];
                 if (h < p.k) {
-                    const size_t off = (static_cast<size_t>(l) * p.Q + qi) * p.k + h;
+                    const size_t dense = static_cast<size_t>(p.Q) * p.k, in_list = static_cast<size_t>(qi) * p.k + h;
+                    const size_t off_i = static_cast<size_t>(l) * (p.ids_stride ? p.ids_stride : dense) + in_list;
+                    const size_t off_s = static_cast<size_t>(l) * (p.scores_stride ? p.scores_stride : dense) + in_list;
                     uint64_t id;
-                    if (p.in_ids64) id = p.in_ids64[off];
-                    else { const uint32_t i32 = p.in_ids32[off]; id = i32 == kNoId32 ? kNoId64 : p.id_base + i32; }
+                    if (p.in_ids64) id = p.in_ids64[off_i];
+                    else { const uint32_t i32 = p.in_ids32[off_i]; id = i32 == kNoId32 ? kNoId64 : p.id_base + i32; }
                     if (id != kNoId64) {
-                        const float s = p.in_scores[off];
+                        const float s = p.in_scores[off_s];
                         if (bl < 0 || s > bs || (s == bs && id < bi)) { bs = s; bi = id; bl = l; }
                     }
                 }

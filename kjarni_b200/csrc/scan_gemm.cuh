@@ -45,9 +45,11 @@ constexpr int kSgQ = 128;     // queries per tile (TMEM lanes)
 constexpr int kSgRows = 256;  // index rows per MMA tile (N)
 constexpr int kSgBK = 64;     // bf16 per k-block = one 128-byte swizzle atom
 constexpr int kSgStages = 4;
-constexpr int kSgC = 32;      // approximate candidates kept per query for the exact rescoring
+constexpr int kSgC = 32;      // approximate candidates kept per query for the exact rescoring when k <= 16 ...
+constexpr int kSgCWide = 128; // ... and when 16 < k <= 64 (a reranking Searcher fetches top_k * 5 = 50, kjarni/src/searcher/model.rs:117-121)
 constexpr int kSgCap = 2048;  // candidate buffer entries per query
-constexpr int kSgMaxD = 384;
+constexpr int kSgMaxD = 384;                                     // widest index whose 128-query tile stays resident in shared memory
+constexpr int kSgMaxDStream = 1024;                              // wider indexes (768-dim embedders) stream the query tile k-block by k-block
 constexpr int kSgMaxKB = kSgMaxD / kSgBK;                        // 6
 constexpr int kSgABlockBytes = kSgQ * kSgBK * 2;                 // 16 KB per k-block of the resident query tile
 constexpr int kSgABytes = kSgABlockBytes * kSgMaxKB;             // 96 KB
@@ -67,7 +69,11 @@ struct ScanGemmParams {
     int seed_chunks;         // seed mode: 1 = one group per 32-row chunk (group = tile*8 + chunk), 0 = one group per CTA
     int D, Q, R;             // R: row tiles per CTA per superblock
     int dbg;                 // microbenchmark switches (env KJC_SG_DBG): 1 = no epilogue work, 2 = no MMA issue, 4 = no row loads
+    int stream_a;            // D > 384: the query tile does not fit beside the row ring, so every stage carries the query k-block
+                             // (16 KB) next to the row k-block (32 KB); the query tile is re-read from L2 once per row tile
 };
+constexpr int kSgStreamStageBytes = kSgABlockBytes + kSgBBytes;  // 48 KB
+static_assert(kSgStages * kSgStreamStageBytes + 256 <= kSgSmemBytes, "streaming stages fit in the same allocation");
 
 __device__ __forceinline__ uint32_t sg_tile_of(const ScanGemmParams& p, uint32_t i) {
     return p.n_tiles == p.n_tiles_total ? i : static_cast<uint32_t>(static_cast<uint64_t>(i) * p.n_tiles_total / p.n_tiles);
@@ -92,6 +98,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int k_blocks = p.D / kSgBK;
     const int n_qt = (p.Q + kSgQ - 1) / kSgQ;
+    const bool stream_a = p.stream_a != 0;
+    // resident mode: [query tile 96 KB][4 row stages of 32 KB]; streaming mode: 4 stages of [query k-block 16 KB | row k-block 32 KB]
+    auto stage_a = [&](int stage) -> uint8_t* { return smem_sg + stage * kSgStreamStageBytes; };
+    auto stage_b = [&](int stage) -> uint8_t* { return stream_a ? smem_sg + stage * kSgStreamStageBytes + kSgABlockBytes : smem_b + stage * kSgBBytes; };
     const uint32_t tiles_per_sb = gridDim.x * static_cast<uint32_t>(p.R);
     const uint32_t n_sb = (p.n_tiles + tiles_per_sb - 1) / tiles_per_sb;
     // tiles of this CTA in superblock sb: i = sb*tiles_per_sb + r*gridDim.x + blockIdx.x, r < R, while i < n_tiles
@@ -137,9 +147,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             if (p.dbg & 4) {
                                 mbar_arrive(&full_bar[stage]);
                             } else {
-                                mbar_arrive_expect_tx(&full_bar[stage], kSgBBytes);
-                                tma_load_2d(smem_b + stage * kSgBBytes, &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0),
-                                            kEvictNormal);
+                                mbar_arrive_expect_tx(&full_bar[stage], stream_a ? kSgStreamStageBytes : kSgBBytes);
+                                if (stream_a) tma_load_2d(stage_a(stage), &tmap_q, &full_bar[stage], kb * kSgBK, qt * kSgQ, kEvictLast);
+                                tma_load_2d(stage_b(stage), &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0), kEvictNormal);
                             }
                             if (++stage == kSgStages) {
                                 stage = 0;
@@ -152,8 +162,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
         }
     } else if (warp == 3) {
-        // ------------------------------------------------ TMA producer: query tiles, k-block by k-block
-        if (lane == 0) {
+        // ------------------------------------------------ TMA producer: query tiles, k-block by k-block (resident mode only)
+        if (lane == 0 && !stream_a) {
             uint32_t ai = 0;
             for (uint32_t sb = 0; sb < n_sb; ++sb) {
                 if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;  // no tile of this CTA in the last superblock
@@ -184,17 +194,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         tc_fence_after();
                         const uint32_t tmem_d = tmem_base + acc * kSgRows;
                         for (int kb = 0; kb < k_blocks; ++kb) {
-                            if (r == 0) mbar_wait(&a_full[kb], ai & 1);
+                            if (r == 0 && !stream_a) mbar_wait(&a_full[kb], ai & 1);
                             mbar_wait(&full_bar[stage], phase);
                             tc_fence_after();
-                            const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + kb * kSgABlockBytes));
-                            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * kSgBBytes));
+                            const uint64_t da = umma_desc_k_sw128(smem_u32(stream_a ? stage_a(stage) : smem_a + kb * kSgABlockBytes));
+                            const uint64_t db = umma_desc_k_sw128(smem_u32(stage_b(stage)));
                             if (!(p.dbg & 2)) {
 #pragma unroll
                                 for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                             }
                             umma_commit(&empty_bar[stage]);
-                            if (last_r) umma_commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
+                            if (last_r && !stream_a) umma_commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
                             if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
                             if (++stage == kSgStages) {
                                 stage = 0;
@@ -316,6 +326,7 @@ struct CandSelectParams {
     float* out_scores;         // [Q, kSgC]  -inf = empty
     uint64_t* out_ids;         // [Q, kSgC]  kNoId64 = empty
     int32_t* overflow;         // [Q] 1 = the buffer overflowed (candidates were dropped)
+    int C;                     // candidates kept per query: kSgC or kSgCWide
 };
 __global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams p) {
     __shared__ float sc[kSgCap];
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams 
     }
     if (tid == 0) p.overflow[qi] = cnt > static_cast<uint32_t>(kSgCap) ? 1 : 0;
     __syncthreads();
-    for (int round = 0; round < kSgC; ++round) {
+    for (int round = 0; round < p.C; ++round) {
         float bs = -INFINITY;
         uint32_t bi = kNoId32;
         int bp = -1;
@@ -356,8 +367,8 @@ __global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams 
             int fp = -1;
             for (int w = 0; w < 8; ++w)
                 if (wp[w] >= 0 && (fp < 0 || ws[w] > fs || (ws[w] == fs && wi[w] < fi))) { fs = ws[w]; fi = wi[w]; fp = wp[w]; }
-            p.out_scores[static_cast<size_t>(qi) * kSgC + round] = fp >= 0 ? fs : -INFINITY;
-            p.out_ids[static_cast<size_t>(qi) * kSgC + round] = fp >= 0 ? p.id_base + fi : kNoId64;
+            p.out_scores[static_cast<size_t>(qi) * p.C + round] = fp >= 0 ? fs : -INFINITY;
+            p.out_ids[static_cast<size_t>(qi) * p.C + round] = fp >= 0 ? p.id_base + fi : kNoId64;
             if (fp >= 0) id[fp] = kNoId32;  // taken
         }
         __syncthreads();
@@ -401,11 +412,11 @@ row_prep_kernel(const float* __restrict__ rows, float* __restrict__ norms, __nv_
 // CTA, or 32-row chunks for small shards).  The maxima belong to distinct rows, so at least 32 rows of the shard score
 // >= that value: a valid lower bound on the 32nd best approximate score, which lets the filter drop ~99.99 % of the rows
 // with one compare.  thr0[q] is exclusive (rows must score > thr0), hence the small margin below the selected value.
-__global__ void __launch_bounds__(256) scan_seed_select_kernel(const float* __restrict__ seed_max, int L, int Q, float* __restrict__ thr0) {
+__global__ void __launch_bounds__(256) scan_seed_select_kernel(const float* __restrict__ seed_max, int L, int Q, float* __restrict__ thr0, int C) {
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (qi >= Q) return;
     const int lane = threadIdx.x & 31;
-    if (L < kSgC) {
+    if (L < C) {
         if (lane == 0) thr0[qi] = -INFINITY;
         return;
     }
@@ -414,7 +425,7 @@ __global__ void __launch_bounds__(256) scan_seed_select_kernel(const float* __re
 #pragma unroll
     for (int i = 0; i < kPer; ++i) v[i] = lane + 32 * i < L ? seed_max[static_cast<size_t>(lane + 32 * i) * Q + qi] : -INFINITY;
     float sel = -INFINITY;
-    for (int r = 0; r < kSgC; ++r) {
+    for (int r = 0; r < C; ++r) {
         float m = v[0];
         int mi = 0;
 #pragma unroll
@@ -453,20 +464,34 @@ struct RescoreParams {
     int D, Q, k, mode;
 };
 
-// One warp per query: exact fp32 cosine of the 32 candidates (arithmetic identical to scan_topk_kernel: per-lane packed
-// FMA over float4 chunks, lo + hi, xor-butterfly 16..1, one divide), final order (score desc, id asc), proof check.
+// One warp per query: exact fp32 cosine of the C candidates (arithmetic identical to scan_topk_kernel: per-lane packed FMA over
+// float4 chunks, lo + hi, xor-butterfly 16..1, one divide), final order (score desc, id asc), proof check.  Lane l owns candidates
+// l, l + 32, ... (CPL = C / 32 of them).
+template <int CPL>
 __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
+    constexpr int C = 32 * CPL;
     const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (qi >= p.Q) return;
     const int lane = threadIdx.x & 31;
     const float qn = p.qnorms[qi];
-    const uint64_t my_gid = p.cand_ids[static_cast<size_t>(qi) * kSgC + lane];
-    const float my_approx = p.cand_scores[static_cast<size_t>(qi) * kSgC + lane];
-    const int ncand = __popc(__ballot_sync(0xffffffffu, my_gid != kNoId64));
-    float my_s = -INFINITY;
+    uint64_t my_gid[CPL];
+    float my_approx[CPL], my_s[CPL];
+    int ncand = 0;
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+        my_gid[u] = p.cand_ids[static_cast<size_t>(qi) * C + u * 32 + lane];
+        my_approx[u] = p.cand_scores[static_cast<size_t>(qi) * C + u * 32 + lane];
+        my_s[u] = -INFINITY;
+        ncand += __popc(__ballot_sync(0xffffffffu, my_gid[u] != kNoId64));  // candidates are packed at the front (sorted lists)
+    }
     const float* q = p.queries + static_cast<size_t>(qi) * p.D;
     for (int c = 0; c < ncand; ++c) {
-        const uint64_t gid = __shfl_sync(0xffffffffu, my_gid, c);  // candidates are packed at the front (sorted lists)
+        uint64_t gid = 0;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) {
+            const uint64_t g = __shfl_sync(0xffffffffu, my_gid[u], c & 31);
+            if ((c >> 5) == u) gid = g;
+        }
         const size_t r = static_cast<size_t>(gid - p.id_base);
         const float* rp = p.rows + r * p.D;
         uint64_t a2 = 0ull;
@@ -485,33 +510,52 @@ __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
         float s;
         if (p.mode == SCAN_SEGMENT) s = rn < 1e-9f ? 0.0f : acc / (qn * rn);
         else s = acc / fmaxf(qn * rn, 1e-9f);
-        if (lane == c) my_s = s;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u)
+            if (lane == (c & 31) && (c >> 5) == u) my_s[u] = s;
     }
     // rank among the candidates by (score desc, id asc)
-    int rank = 0;
+    int rank[CPL];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) rank[u] = 0;
 #pragma unroll 1
-    for (int j = 0; j < kSgC; ++j) {
-        const float sj = __shfl_sync(0xffffffffu, my_s, j);
-        const uint64_t ij = __shfl_sync(0xffffffffu, my_gid, j);
-        if (j < ncand && (sj > my_s || (sj == my_s && ij < my_gid))) ++rank;
+    for (int j = 0; j < ncand; ++j) {
+        float sj = 0.f;
+        uint64_t ij = 0;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) {
+            const float ts = __shfl_sync(0xffffffffu, my_s[u], j & 31);
+            const uint64_t ti = __shfl_sync(0xffffffffu, my_gid[u], j & 31);
+            if ((j >> 5) == u) { sj = ts; ij = ti; }
+        }
+#pragma unroll
+        for (int u = 0; u < CPL; ++u)
+            if (sj > my_s[u] || (sj == my_s[u] && ij < my_gid[u])) ++rank[u];
     }
-    const bool valid = lane < ncand;
     const bool empty_query = p.mode == SCAN_SEGMENT && qn < 1e-9f;
     const int nres = empty_query ? 0 : min(p.k, ncand);
     uint64_t* oi = p.out_ids + static_cast<size_t>(qi) * p.k;
     float* os = p.out_scores + static_cast<size_t>(qi) * p.k;
-    if (valid && rank < nres) { oi[rank] = my_gid; os[rank] = my_s; }
+    float kth = 0.f;
+    bool have_kth = false;
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+        const bool valid = u * 32 + lane < ncand;
+        if (valid && rank[u] < nres) { oi[rank[u]] = my_gid[u]; os[rank[u]] = my_s[u]; }
+        const uint32_t kth_mask = __ballot_sync(0xffffffffu, valid && rank[u] == p.k - 1);
+        if (kth_mask) {
+            kth = __shfl_sync(0xffffffffu, my_s[u], __ffs(kth_mask) - 1);
+            have_kth = true;
+        }
+    }
     for (int j = nres + lane; j < p.k; j += 32) { oi[j] = kNoId64; os[j] = -INFINITY; }
     if (lane == 0 && p.out_counts) p.out_counts[qi] = nres;
-    // proof: rows outside the list have approximate cosine <= m32 (the smallest kept one) => exact <= m32 + eps
-    const uint32_t kth_mask = __ballot_sync(0xffffffffu, valid && rank == p.k - 1);
-    const int kth_lane = kth_mask ? __ffs(kth_mask) - 1 : 0;
-    const float kth = __shfl_sync(0xffffffffu, my_s, kth_lane);
-    const float m32 = __shfl_sync(0xffffffffu, my_approx, kSgC - 1);  // lists are sorted descending: last = smallest
+    // proof: rows outside the list have approximate cosine <= m_C (the smallest kept one) => exact <= m_C + eps
+    const float m_last = __shfl_sync(0xffffffffu, my_approx[CPL - 1], 31);  // lists are sorted descending: last = smallest
     if (lane == 0 && !empty_query) {
-        // fewer than 32 candidates proves the result only if nothing was filtered out (unseeded: every row is a candidate)
-        bool proven = ncand < kSgC && p.thr0[qi] == -INFINITY;
-        if (ncand == kSgC && kth_mask != 0 && qn >= 1e-9f) proven = kth > m32 / qn + p.eps;
+        // fewer than C candidates proves the result only if nothing was filtered out (unseeded: every row is a candidate)
+        bool proven = ncand < C && p.thr0[qi] == -INFINITY;
+        if (ncand == C && have_kth && qn >= 1e-9f) proven = kth > m_last / qn + p.eps;
         if (p.overflow[qi]) proven = false;
         p.flags[qi] = proven ? 0 : 1;
         if (!proven) atomicAdd(p.n_flagged, 1);

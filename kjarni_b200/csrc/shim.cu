@@ -130,7 +130,7 @@ struct TextModel {
         const std::vector<int> devs = shim_devices();
         grp.reset(new EncoderGroup(dir, devs.data(), static_cast<int>(devs.size())));
         enc = &grp->replica(0);
-        tok.reset(new Tokenizer(dir + "/tokenizer.json", enc->info().max_position_embeddings));  // truncation max_length = meta.max_seq_len
+        tok.reset(new Tokenizer(dir + "/tokenizer.json", enc->config_max_seq_len()));  // truncation max_length = meta.max_seq_len (loader.rs:108)
     }
 
     // Result rows handed over while they still sit in the encoder's pinned staging buffer: rows[i] belongs to text index[i]

@@ -53,41 +53,48 @@ class DistributedIndex:
         return cls(api.IndexShard.open_dir(root, device, rank, world), group)
 
     # -- the two device-side steps, overridable so the exchange logic can be exercised on CPU (gloo) in tests
-    def _search_local(self, queries, k: int, mode: int):
+    @staticmethod
+    def record_bytes(nq: int, k: int) -> int:
+        """One rank's packed candidate record: [nq,k] u64 ids | [nq,k] f32 scores, rounded up to 16 bytes (kjc_packed_record_bytes)."""
+        return (nq * k * 12 + 15) & ~15
+
+    def _search_local(self, queries, k: int, mode: int, rec):
+        """Per-shard exact top-k written straight into the packed record `rec` (uint8 [record_bytes])."""
+        nq = queries.shape[0]
         import torch
 
-        nq = queries.shape[0]
-        ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
         stream = torch.cuda.current_stream().cuda_stream
         # the synchronising entry: queries the tensor-core filter cannot prove are re-run on the exact scan, so the merged result is
         # the exact top-k in every case (IndexReader::search_semantic is exact)
-        N.check(N.lib().kjc_index_search_device(self.shard._h, queries.data_ptr(), nq, k, mode, ids.data_ptr(), sc.data_ptr(),
+        N.check(N.lib().kjc_index_search_device(self.shard._h, queries.data_ptr(), nq, k, mode, rec.data_ptr(), rec.data_ptr() + nq * k * 8,
                                                 None, stream if stream else None))
-        return ids, sc
 
-    def _merge(self, g_ids, g_sc, nq: int, k: int):
+    def _merge(self, gathered, nq: int, k: int):
+        """gathered: uint8 [world, record_bytes] -> (ids int64 [nq,k], scores f32 [nq,k])."""
         import torch
 
-        ids = torch.empty((nq, k), dtype=torch.int64, device=g_ids.device)
-        sc = torch.empty((nq, k), dtype=torch.float32, device=g_ids.device)
+        ids = torch.empty((nq, k), dtype=torch.int64, device=gathered.device)
+        sc = torch.empty((nq, k), dtype=torch.float32, device=gathered.device)
         stream = torch.cuda.current_stream().cuda_stream
-        N.check(N.lib().kjc_topk_merge_device_async(self.shard.device, g_ids.data_ptr(), g_sc.data_ptr(), g_ids.shape[0], nq, k,
-                                                    ids.data_ptr(), sc.data_ptr(), None, stream if stream else None))
+        N.check(N.lib().kjc_topk_merge_packed_device_async(self.shard.device, gathered.data_ptr(), gathered.shape[0], nq, k,
+                                                           ids.data_ptr(), sc.data_ptr(), None, stream if stream else None))
         return ids, sc
 
     def search(self, queries, k: int, mode: int = N.SCAN_SEGMENT):
         """queries: [Q, dim] float32 tensor on this rank's device (identical on every rank).
-        Returns (ids int64 [Q,k] global, -1 = empty; scores f32 [Q,k]) -- identical on every rank."""
+        Returns (ids int64 [Q,k] global, -1 = empty; scores f32 [Q,k]) -- identical on every rank.
+        ONE collective per search: every rank's ids and scores travel as one packed record."""
         import torch
         import torch.distributed as dist
 
         nq = queries.shape[0]
-        ids, sc = self._search_local(queries, k, mode)
+        rb = self.record_bytes(nq, k)
+        rec = torch.empty((rb,), dtype=torch.uint8, device=queries.device)
+        self._search_local(queries, k, mode, rec)
         if self.world == 1:
-            return ids, sc
-        g_ids = torch.empty((self.world * nq, k), dtype=torch.int64, device=ids.device)  # rank-major concat
-        g_sc = torch.empty((self.world * nq, k), dtype=torch.float32, device=ids.device)
-        dist.all_gather_into_tensor(g_ids, ids.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(g_sc, sc.contiguous(), group=self.group)
-        return self._merge(g_ids.view(self.world, nq, k), g_sc.view(self.world, nq, k), nq, k)
+            gathered = rec.view(1, rb)
+        else:
+            flat = torch.empty((self.world * rb,), dtype=torch.uint8, device=queries.device)  # rank-major concat
+            dist.all_gather_into_tensor(flat, rec, group=self.group)
+            gathered = flat.view(self.world, rb)
+        return self._merge(gathered, nq, k)

@@ -3,25 +3,36 @@ import ctypes as C, sys
 sys.path.insert(0, ".")
 import numpy as np
 from kjarni_b200 import _native as N
+import os
 lib = N.lib()
 M = 18944
+ITERS = int(os.environ.get("ITERS", "30"))
+RANDOM = os.environ.get("RANDOM_DATA") == "1"  # zeros draw far less power than real activations: compare both
+rng = np.random.default_rng(0)
+def data(*shape, scale=1.0):
+    if not RANDOM:
+        return np.zeros(shape, np.uint16)
+    x = (rng.standard_normal(shape) * scale).astype(np.float32)
+    return (x.view(np.uint32) >> 16).astype(np.uint16)
 def ln(K):
-    a = np.zeros((M, K), np.uint16); w = np.zeros((384, K), np.uint16); r = np.zeros((M, 384), np.uint16); o = np.empty((M, 384), np.uint16)
+    a = data(M, K); w = data(384, K, scale=K ** -0.5); r = data(M, 384); o = np.empty((M, 384), np.uint16)
     v = np.ones(384, np.float32); us = C.c_float()
-    N.check(lib.kjc_dbg_gemm_ln(a.ctypes.data, w.ctypes.data, v.ctypes.data, v.ctypes.data, v.ctypes.data, 1e-12, r.ctypes.data, M, K, o.ctypes.data, 30, C.byref(us)))
+    N.check(lib.kjc_dbg_gemm_ln(a.ctypes.data, w.ctypes.data, v.ctypes.data, v.ctypes.data, v.ctypes.data, 1e-12, r.ctypes.data, M, K, o.ctypes.data, ITERS, C.byref(us)))
     return us.value
 def gemm(Nn, epi, bn):
     us = C.c_float()
     N.check(lib.kjc_dbg_gemm_time(M, Nn, 384, epi, 0, bn, 0, 30, C.byref(us)))
     return us.value
 def chain(K1, N2, epi2):
-    a = np.zeros((M, K1), np.uint16); w = np.zeros((384, K1), np.uint16); r = np.zeros((M, 384), np.uint16); ox = np.empty((M, 384), np.uint16)
-    w2 = np.zeros((N2, 384), np.uint16); b2 = np.zeros(N2, np.float32); o2 = np.empty((M, N2), np.uint16)
+    a = data(M, K1); w = data(384, K1, scale=K1 ** -0.5); r = data(M, 384); ox = np.empty((M, 384), np.uint16)
+    w2 = data(N2, 384, scale=384 ** -0.5); b2 = np.zeros(N2, np.float32); o2 = np.empty((M, N2), np.uint16)
     v = np.ones(384, np.float32); us = C.c_float()
     N.check(lib.kjc_dbg_gemm_ln_gemm(a.ctypes.data, w.ctypes.data, v.ctypes.data, v.ctypes.data, v.ctypes.data, 1e-12, r.ctypes.data, M, K1,
-                                     w2.ctypes.data, b2.ctypes.data, N2, epi2, 0, ox.ctypes.data, o2.ctypes.data, 30, C.byref(us)))
+                                     w2.ctypes.data, b2.ctypes.data, N2, epi2, 0, ox.ctypes.data, o2.ctypes.data, ITERS, C.byref(us)))
     return us.value
 a, b, c = ln(384), gemm(1536, 1, 256), chain(384, 1536, 1)
 print(f"out-proj+LN {a:.1f} us + FFN-up {b:.1f} us = {a+b:.1f} us   |  chained {c:.1f} us")
 a, b, c = ln(1536), gemm(1152, 0, 192), chain(1536, 1152, 0)
 print(f"FFN-down+LN {a:.1f} us + QKV {b:.1f} us = {a+b:.1f} us   |  chained {c:.1f} us")
+c1, c2 = chain(384, 1536, 1 + 16), chain(1536, 1152, 0 + 16)
+print(f"CTA-pair chained (cta_group::2, half a weight tile per CTA): out-proj+LN1->FFN-up {c1:.1f} us, FFN-down+LN2->QKV {c2:.1f} us")

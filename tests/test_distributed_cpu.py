@@ -31,13 +31,20 @@ class _CpuShardIndex(kd.DistributedIndex):
         self.group = group
         self.world = dist.get_world_size(group)
 
-    def _search_local(self, queries, k, mode):
+    def _search_local(self, queries, k, mode, rec):
+        nq = queries.shape[0]
         ids, sc = ko.batched_topk(self.rows, queries.numpy(), k, row_offset=self.row0)
-        return torch.from_numpy(ids), torch.from_numpy(sc)
+        buf = rec.numpy()  # the packed record: [nq,k] ids | [nq,k] scores
+        buf[:nq * k * 8] = np.ascontiguousarray(ids, np.int64).view(np.uint8).reshape(-1)
+        buf[nq * k * 8:nq * k * 12] = np.ascontiguousarray(sc, np.float32).view(np.uint8).reshape(-1)
 
-    def _merge(self, g_ids, g_sc, nq, k):
-        ids = g_ids.numpy().transpose(1, 0, 2).reshape(nq, -1)
-        sc = g_sc.numpy().transpose(1, 0, 2).reshape(nq, -1)
+    def _merge(self, gathered, nq, k):
+        g = gathered.numpy()
+        world = g.shape[0]
+        g_ids = np.stack([g[r, :nq * k * 8].view(np.int64).reshape(nq, k) for r in range(world)])
+        g_sc = np.stack([g[r, nq * k * 8:nq * k * 12].view(np.float32).reshape(nq, k) for r in range(world)])
+        ids = g_ids.transpose(1, 0, 2).reshape(nq, -1)
+        sc = g_sc.transpose(1, 0, 2).reshape(nq, -1)
         out_i = np.full((nq, k), -1, np.int64)
         out_s = np.full((nq, k), -np.inf, np.float32)
         for q in range(nq):

@@ -241,6 +241,14 @@ def test_chained_gemm_ln_gemm(M, K1, N2, epi2):
     ref2 = np.empty((M, N2), np.uint16)
     N.check(N.lib().kjc_dbg_gemm(ptr(ref_x), ptr(to_bf16_bits(w2)), ptr(b2), None, M, N2, H, epi2, 0, 192, ptr(ref2)))
     assert np.array_equal(out2, ref2)
+    # the CTA-pair variant (epi2 + 16: two CTAs per cluster share every weight tile through tcgen05.mma.cta_group::2, odd tile counts
+    # leave one padding tile): the same bits again
+    px = np.empty((M, H), np.uint16)
+    p2 = np.empty((M, N2), np.uint16)
+    N.check(N.lib().kjc_dbg_gemm_ln_gemm(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w1)), ptr(b1), ptr(gamma), ptr(beta), 1e-12, ptr(to_bf16_bits(res)),
+                                         M, K1, ptr(to_bf16_bits(w2)), ptr(b2), N2, epi2 + 16, 0, ptr(px), ptr(p2), 0, C.byref(us)))
+    assert np.array_equal(px, out_x)
+    assert np.array_equal(p2, out2)
     # and the oracle
     y = (bf16_round(a).astype(np.float64) @ bf16_round(w1).astype(np.float64).T + b1 + bf16_round(res)).astype(np.float32)
     want_x = ko.layer_norm(y, gamma, beta, 1e-12)

@@ -145,7 +145,11 @@ def test_full_size_shard_properties():
 
 # ------------------------------------------------------------------ tensor-core filter path (scan_gemm.cuh)
 @pytest.mark.parametrize("n,dim,nq,k", [(5000, 384, 9, 10), (70000, 384, 130, 10), (40000, 128, 300, 16), (300, 64, 17, 1),
-                                        (20, 384, 12, 10), (257, 256, 128, 5), (100001, 320, 64, 10)])
+                                        (20, 384, 12, 10), (257, 256, 128, 5), (100001, 320, 64, 10),
+                                        # round 2: 16 < k <= 64 keeps 128 approximate candidates per query (a reranking Searcher fetches top_k * 5 = 50),
+                                        # dim > 384 streams the query tile k-block by k-block (768-dim embedders)
+                                        (70000, 384, 130, 50), (5000, 384, 9, 64), (12000, 64, 33, 20), (60000, 768, 40, 10), (30000, 1024, 9, 50),
+                                        (100000, 768, 200, 50), (3000, 448, 5, 17)])
 def test_gemm_filter_matches_oracle_and_exact_path(n, dim, nq, k):
     rows = ko.synth_rows(7, 0, n, dim)
     q = ko.synth_rows(11, 0, nq, dim)
@@ -155,6 +159,7 @@ def test_gemm_filter_matches_oracle_and_exact_path(n, dim, nq, k):
     sh.add_rows(np.stack([rows[n // 3], np.zeros(dim, np.float32), rows[n // 3] * 0.5]))  # duplicates (ties -> lower id) + a zero row
     allrows = np.concatenate([rows, rows[n // 3][None], np.zeros((1, dim), np.float32), rows[n // 3][None] * 0.5])
     ids, sc, cnt = sh.search_batch(q, k)  # filter path
+    assert sh.last_launch_count >= 5  # prep, (seed,) seed select, filter GEMM, candidate select, exact rescoring -- not the 3-launch exact scan
     wi, ws = ko.batched_topk(allrows, q, k, row_offset=500)
     kk = min(k, n + 3)
     assert (cnt == kk).all()
