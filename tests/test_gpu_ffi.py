@@ -382,3 +382,141 @@ def test_length_bucketed_batching_matches_batch_longest(ffi, models, monkeypatch
     want = ko.embed(ko.load_model_dir(models["tiny-bert"]), ids, mask)
     assert cosine_rows(bucketed, want).min() >= 0.9995 and np.abs(bucketed - want).max() <= 2e-2
     ffi.kjarni_embedder_free(h)
+
+
+# ------------------------------------------------------------------ indexer
+class IndexerConfig(C.Structure):
+    _fields_ = [("device", C.c_int), ("cache_dir", C.c_char_p), ("model_name", C.c_char_p), ("chunk_size", C.c_size_t),
+                ("chunk_overlap", C.c_size_t), ("batch_size", C.c_size_t), ("extensions", C.c_char_p), ("exclude_patterns", C.c_char_p),
+                ("recursive", C.c_int32), ("include_hidden", C.c_int32), ("max_file_size", C.c_size_t), ("quiet", C.c_int32)]
+
+
+class IndexStats(C.Structure):
+    _fields_ = [("documents_indexed", C.c_size_t), ("chunks_created", C.c_size_t), ("dimension", C.c_size_t), ("size_bytes", C.c_uint64),
+                ("files_processed", C.c_size_t), ("files_skipped", C.c_size_t), ("elapsed_ms", C.c_uint64)]
+
+
+class Progress(C.Structure):
+    _fields_ = [("stage", C.c_int), ("current", C.c_size_t), ("total", C.c_size_t), ("message", C.c_char_p)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(None, Progress, C.c_void_p)
+
+
+def test_indexer_builds_the_index_the_reference_would(ffi, models, tmp_path):
+    """kjarni_indexer_create / _add (Indexer::create / add, kjarni/src/indexer/model.rs:169-300,466-570): discover -> split -> embed on the
+    GPU -> segments.  Checked against the oracle's TextSplitter and BM25 restatements (pinned to the reference's unit vectors in
+    tests/test_search_cpu.py), against the embedder's own rows (vectors.bin is written from the pinned output buffer) and the fp32
+    oracle embedding, and by reading the finished directory back through IndexReader's path (searcher, keywords, index_info)."""
+    import struct
+
+    ffi.kjarni_indexer_config_default.restype = IndexerConfig
+    ffi.kjarni_indexer_free.argtypes = [C.c_void_p]
+    ffi.kjarni_indexer_create.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_int32, C.POINTER(IndexStats)]
+    ffi.kjarni_indexer_add.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.POINTER(C.c_size_t)]
+    ffi.kjarni_indexer_create_with_callback.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_size_t, C.c_int32, PROGRESS_FN, C.c_void_p,
+                                                        C.c_void_p, C.POINTER(IndexStats)]
+    ffi.kjarni_indexer_dimension.restype = C.c_size_t
+    ffi.kjarni_indexer_dimension.argtypes = [C.c_void_p]
+    ffi.kjarni_indexer_chunk_size.restype = C.c_size_t
+    ffi.kjarni_indexer_chunk_size.argtypes = [C.c_void_p]
+    ffi.kjarni_search_keywords.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(SearchResults)]
+    ffi.kjarni_cancel_token_new.restype = C.c_void_p
+    ffi.kjarni_cancel_token_cancel.argtypes = [C.c_void_p]
+    ffi.kjarni_cancel_token_free.argtypes = [C.c_void_p]
+
+    corpus = tmp_path / "corpus"
+    (corpus / "sub").mkdir(parents=True)
+    para = ["Paragraph %d talks about %s and the way %s changes retrieval quality." % (i, w, w)
+            for i, w in enumerate(["gpu kernels", "vector search", "tokenizers", "layer norm", "attention heads", "bm25 ranking", "cosine scores"])]
+    files = {"a.txt": "\n\n".join(para[:4]), "sub/b.md": "A short note about trees and rivers.", "c.txt": "\n\n".join(para[4:]) + "\n\n" + "x" * 30,
+             ".hidden.txt": "hidden files are skipped by default", "d.bin": "unsupported extension"}
+    for name, text in files.items():
+        (corpus / name).write_text(text)
+    dflt = ffi.kjarni_indexer_config_default()
+    assert (dflt.device, dflt.chunk_size, dflt.chunk_overlap, dflt.batch_size, dflt.recursive, dflt.include_hidden) == (CPU, 512, 50, 32, 1, 0)
+    cfg = ffi.kjarni_indexer_config_default()
+    cfg.device, cfg.cache_dir, cfg.chunk_size, cfg.chunk_overlap, cfg.batch_size, cfg.quiet = GPU, models["cache"].encode(), 120, 20, 3, 1
+    h = C.c_void_p()
+    assert ffi.kjarni_indexer_new(C.byref(cfg), C.byref(h)) == 0, ffi.kjarni_last_error_message()
+    assert ffi.kjarni_indexer_dimension(h) == 64 and ffi.kjarni_indexer_chunk_size(h) == 120
+    root = str(tmp_path / "built")
+    inputs = strs([str(corpus)])
+    stats = IndexStats()
+    assert ffi.kjarni_indexer_create(h, root.encode(), inputs, 1, 0, C.byref(stats)) == 0, ffi.kjarni_last_error_message()
+    # expected chunks: supported, non-hidden files in path order, split by the oracle's TextSplitter
+    order = ["a.txt", "c.txt", "sub/b.md"]
+    chunks, src = [], []
+    for name in order:
+        cs = ko.split_text(files[name], 120, 20)
+        chunks += cs
+        src += [(str(corpus / name), i, len(cs)) for i in range(len(cs))]
+    assert len(chunks) > 6
+    assert (stats.documents_indexed, stats.chunks_created, stats.dimension, stats.files_processed, stats.files_skipped) == (len(chunks), len(chunks), 64, 3, 0)
+    # the directory parses as an index; vectors.bin holds the embedder's rows in chunk order
+    info = N.KjcIndexDirInfo()
+    N.check(N.lib().kjc_index_dir_info(root.encode(), C.byref(info)))
+    assert (info.total_rows, info.dimension, info.n_segments) == (len(chunks), 64, 1)
+    seg = os.path.join(root, "segments", "seg_000000")
+    vec = np.fromfile(os.path.join(seg, "vectors.bin"), np.float32).reshape(-1, 64)
+    assert vec.shape[0] == len(chunks)
+    tok = api.Tokenizer(TOK, 64)
+    ids, mask, _ = tok.encode_batch(chunks)
+    want = ko.embed(ko.load_model_dir(models["tiny-bert"]), ids, mask)
+    cos = (vec * want).sum(1) / (np.linalg.norm(vec, axis=1) * np.linalg.norm(want, axis=1))
+    assert cos.min() >= 0.9995 and np.abs(vec - want).max() <= 2e-2
+    enc = api.EncoderModel(models["tiny-bert"])
+    assert np.abs(vec - enc.encode_batch_from_ids(ids, mask)).max() <= 2e-3  # same kernels; grouping by length only changes the padded length
+    enc.close()
+    # docs / metadata / bm25.bin as SegmentBuilder::flush leaves them
+    offs = struct.unpack("<Q%dQ" % len(chunks), open(os.path.join(seg, "docs.idx"), "rb").read())
+    assert offs[0] == len(chunks)
+    blob = open(os.path.join(seg, "docs.bin"), "rb").read()
+    bounds = list(offs[1:]) + [len(blob)]
+    assert [blob[bounds[i]:bounds[i + 1]].decode() for i in range(len(chunks))] == chunks
+    metas = [json.loads(line) for line in open(os.path.join(seg, "metadata.jsonl"))]
+    assert [(m["source"], int(m["chunk_index"]), int(m["total_chunks"])) for m in metas] == src
+    bm = ko.bm25_from_bincode(open(os.path.join(seg, "bm25.bin"), "rb").read())
+    ref = ko.Bm25()
+    for i, t in enumerate(chunks):
+        ref.add_document(i, t)
+    assert bm.total_docs == ref.total_docs and list(bm.doc_lengths) == list(ref.doc_lengths) and bm.doc_frequencies == ref.doc_frequencies
+    assert bm.search("retrieval quality of vector search", 5) == ref.search("retrieval quality of vector search", 5)
+    # read back through the searcher: a chunk's own text finds that chunk first, keyword search agrees with the oracle
+    scfg = ffi.kjarni_searcher_config_default()
+    scfg.device, scfg.cache_dir, scfg.default_mode, scfg.default_top_k = GPU, models["cache"].encode(), 1, 3
+    sh = C.c_void_p()
+    assert ffi.kjarni_searcher_new(C.byref(scfg), C.byref(sh)) == 0
+    res = SearchResults()
+    for ci in (0, len(chunks) // 2, len(chunks) - 1):
+        assert ffi.kjarni_searcher_search(sh, root.encode(), chunks[ci].encode(), C.byref(res)) == 0, ffi.kjarni_last_error_message()
+        assert res.len == 3 and res.results[0].document_id == ci and res.results[0].text.decode() == chunks[ci]
+        ffi.kjarni_search_results_free(C.byref(res))
+    assert ffi.kjarni_search_keywords(root.encode(), b"trees rivers", 5, C.byref(res)) == 0
+    assert [res.results[i].document_id for i in range(res.len)] == [d for d, _ in ko.index_search_keywords([chunks], "trees rivers", 5)]
+    ffi.kjarni_search_results_free(C.byref(res))
+    # create over an existing index needs force; add appends a new segment and the searcher sees it (fingerprint check)
+    assert ffi.kjarni_indexer_create(h, root.encode(), inputs, 1, 0, C.byref(stats)) != 0
+    extra = tmp_path / "extra.txt"
+    extra.write_text("Completely new material about submarines and lighthouses.")
+    added = C.c_size_t()
+    assert ffi.kjarni_indexer_add(h, root.encode(), strs([str(extra)]), 1, C.byref(added)) == 0, ffi.kjarni_last_error_message()
+    assert added.value == 1
+    N.check(N.lib().kjc_index_dir_info(root.encode(), C.byref(info)))
+    assert (info.total_rows, info.n_segments) == (len(chunks) + 1, 2)
+    assert ffi.kjarni_searcher_search(sh, root.encode(), b"Completely new material about submarines and lighthouses.", C.byref(res)) == 0
+    assert res.results[0].document_id == len(chunks)
+    ffi.kjarni_search_results_free(C.byref(res))
+    ffi.kjarni_searcher_free(sh)
+    assert ffi.kjarni_indexer_create(h, root.encode(), inputs, 1, 1, C.byref(stats)) == 0 and stats.documents_indexed == len(chunks)
+    # progress callback and cancellation
+    stages = []
+    cb = PROGRESS_FN(lambda p, _u: stages.append(p.stage))
+    root2 = str(tmp_path / "built2")
+    assert ffi.kjarni_indexer_create_with_callback(h, root2.encode(), inputs, 1, 0, cb, None, None, C.byref(stats)) == 0
+    assert {0, 1, 2, 4} <= set(stages)  # scanning, loading, embedding, committing
+    token = ffi.kjarni_cancel_token_new()
+    ffi.kjarni_cancel_token_cancel(token)
+    assert ffi.kjarni_indexer_create_with_callback(h, str(tmp_path / "built3").encode(), inputs, 1, 0, cb, None, token, C.byref(stats)) == 8  # Cancelled
+    ffi.kjarni_cancel_token_free(token)
+    ffi.kjarni_indexer_free(h)
