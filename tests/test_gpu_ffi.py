@@ -473,7 +473,7 @@ def test_indexer_builds_the_index_the_reference_would(ffi, models, tmp_path):
     assert offs[0] == len(chunks)
     blob = open(os.path.join(seg, "docs.bin"), "rb").read()
     bounds = list(offs[1:]) + [len(blob)]
-    assert [blob[bounds[i]:bounds[i + 1]].decode() for i in range(len(chunks))] == chunks
+    assert [blob[bounds[i]:bounds[i + 1]].decode() for i in range(len(chunks))] == [c + "\n" for c in chunks]  # text + '\n' (segment.rs:105-110)
     metas = [json.loads(line) for line in open(os.path.join(seg, "metadata.jsonl"))]
     assert [(m["source"], int(m["chunk_index"]), int(m["total_chunks"])) for m in metas] == src
     bm = ko.bm25_from_bincode(open(os.path.join(seg, "bm25.bin"), "rb").read())
