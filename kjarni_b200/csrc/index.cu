@@ -31,7 +31,9 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
     gemm_ok_ = dim % kSgBK == 0 && dim <= kSgMaxDStream && !getenv("KJC_SCAN_NO_GEMM");
     if (const char* e = getenv("KJC_SCAN_EPS")) filter_eps_ = static_cast<float>(atof(e));
     if (const char* e = getenv("KJC_SCAN_GEMM_MIN_Q")) filter_min_q_ = std::max(1, atoi(e));
-    scan_q8_ = getenv("KJC_SCAN_NO_Q8") == nullptr;
+    // exact scan: lane-per-row kernel on TMA-swizzled 32 x 32-float boxes when the dimension allows it (scan.cuh, scan_t8_kernel)
+    scan_t8_ = dim % 32 == 0 && getenv("KJC_SCAN_NO_T8") == nullptr;
+    if (scan_t8_) t_rows32_ = make_tmap_2d(rows_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, capacity, dim, kT8Rows, 32, 128);
     if (gemm_ok_) {
         const uint64_t cap16 = std::max<uint64_t>(capacity, kSgRows);  // at least one TMA box of rows
         KJ_CUDA(cudaMalloc(&rows16_, cap16 * dim * sizeof(__nv_bfloat16)));
@@ -165,19 +167,22 @@ static void launch_scan_inst(ScanParams p, int grid, cudaStream_t st) {
     kern<<<grid, (CW + 1) * 32, smem, st>>>(p);
     KJ_CUDA(cudaGetLastError());
 }
-// 8 queries per warp, one warp group; variant (KJC_SCAN_Q8_VARIANT): 0 = 8 warps x 2 rows per turn, 1 = 8 warps x 4 rows, 2 = 12 warps x 1 row
-static void launch_scan_q8(const ScanParams& p, int grid, cudaStream_t st) {
-    static const int variant = getenv("KJC_SCAN_Q8_VARIANT") ? atoi(getenv("KJC_SCAN_Q8_VARIANT")) : 0;
-    const int nch = (p.D + 127) / 128;
-    if (nch >= 3) {
-        if (variant == 1) launch_scan_inst<8, 3, 8, 4>(p, grid, st);
-        else if (variant == 2) launch_scan_inst<8, 3, 12, 1>(p, grid, st);
-        else launch_scan_inst<8, 3, 8, 2>(p, grid, st);
-    } else if (nch == 2) {
-        launch_scan_inst<8, 2, 8, 2>(p, grid, st);
-    } else {
-        launch_scan_inst<8, 1, 8, 2>(p, grid, st);
-    }
+// Lane-per-row exact scan (scan_t8_kernel, dim % 32 == 0): <= 8 queries per pass; writes kT8Teams lists per CTA and query
+constexpr int kT8Teams = 2;
+static void launch_scan_t8(const CUtensorMap& t_rows, ScanT8Params p, int grid, cudaStream_t st) {
+    static int configured[64] = {0};
+    // floats of a row per stage: the largest multiple of 32 that divides D and is <= 384 (48 KB stages at most)
+    int ds = 32;
+    for (int c = 32; c <= 384 && c <= p.D; c += 32)
+        if (p.D % c == 0) ds = c;
+    p.ds = ds;
+    const size_t fixed = scan_t8_smem_bytes(p.D, ds, 0, p.k, kT8Teams);
+    p.nstages = static_cast<int>(std::min<size_t>(4, (220 * 1024 - fixed) / (static_cast<size_t>(ds) * 128 + 16)));
+    if (p.nstages < 2) throw Error(KJC_INVALID_CONFIG, "index dimension too large for the scan pipeline");
+    const size_t smem = scan_t8_smem_bytes(p.D, ds, p.nstages, p.k, kT8Teams);
+    ensure_smem_attr(scan_t8_kernel<kT8Teams>, static_cast<int>(smem), configured);
+    scan_t8_kernel<kT8Teams><<<grid, t8_threads<kT8Teams>(), smem, st>>>(t_rows, p);
+    KJ_CUDA(cudaGetLastError());
 }
 
 template <int QT>
@@ -387,7 +392,8 @@ void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_
     int qt_max = k > 64 ? 1 : (k > 32 ? 2 : 4);
     if (dim_ > 512) qt_max = std::min(qt_max, 2);
     const int grid = std::max<int>(1, static_cast<int>(std::min<uint64_t>(num_sms_, (len_ + 31) / 32)));  // one CTA per SM
-    const size_t cand = static_cast<size_t>(grid) * nq * k;
+    const int lists_per_cta = scan_t8_ ? kT8Teams : 1;
+    const size_t cand = static_cast<size_t>(grid) * lists_per_cta * nq * k;
     if (cand > cand_cap_) {
         if (d_cand_s_) cudaFree(d_cand_s_);
         if (d_cand_i_) cudaFree(d_cand_i_);
@@ -410,9 +416,11 @@ void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_
         for (int q0 = 0; q0 < nq;) {
             p.q0 = q0;
             const int rem = nq - q0;
-            if (scan_q8_ && rem > 4 && k <= 32 && dim_ <= 384) {  // 5..8 queries: one warp group scores all of them per row
-                p.ngroups = 1;
-                launch_scan_q8(p, grid, st);
+            if (scan_t8_) {  // dim % 32 == 0: the lane-per-row kernel, 8 queries per pass
+                ScanT8Params t;
+                t.norms = norms_; t.queries = d_q; t.qnorms = d_qn_; t.out_scores = d_cand_s_; t.out_ids = d_cand_i_;
+                t.n_rows = len_; t.D = dim_; t.Q = nq; t.k = k; t.q0 = q0; t.mode = mode;
+                launch_scan_t8(t_rows32_, t, grid, st);
                 q0 += 8;
                 ++launches_;
                 continue;
@@ -429,7 +437,7 @@ void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_
     }
     MergeParams m;
     m.in_scores = d_cand_s_; m.in_ids32 = d_cand_i_; m.in_ids64 = nullptr; m.id_base = id_base_; m.qnorms = d_qn_;
-    m.out_scores = d_scores; m.out_ids = d_ids; m.out_counts = d_counts; m.L = len_ > 0 ? grid : 0; m.Q = nq; m.k = k; m.mode = mode;
+    m.out_scores = d_scores; m.out_ids = d_ids; m.out_counts = d_counts; m.L = len_ > 0 ? grid * lists_per_cta : 0; m.Q = nq; m.k = k; m.mode = mode;
     m.ids_stride = m.scores_stride = 0;
     launch_topk_merge(m, st);
     ++launches_;

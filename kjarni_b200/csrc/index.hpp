@@ -62,7 +62,8 @@ class Index {
     int64_t launches_ = 0;
     // tensor-core filter path (scan_gemm.cuh): bf16 shadow of the rows, 1/|r|, staging for query tiles and candidates
     bool gemm_ok_ = false;
-    bool scan_q8_ = true;  // exact scan: 8-query passes as one warp group (scan.cuh <8, NCH, 8, 2>); KJC_SCAN_NO_Q8 = the two-group kernel
+    bool scan_t8_ = false;  // exact scan: lane-per-row kernel (dim % 32 == 0); otherwise the warp-per-row kernels
+    CUtensorMap t_rows32_;  // fp32 rows as 32 x 32-float boxes, 128-byte swizzle
     float filter_eps_ = 0.0045f;
     int filter_min_q_ = 1;  // the filter pass reads half the bytes of the exact scan, so it wins from a single query on
     __nv_bfloat16 *rows16_ = nullptr, *d_q16_ = nullptr;

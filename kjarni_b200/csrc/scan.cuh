@@ -394,3 +394,185 @@ __global__ void synth_rows_kernel(float* __restrict__ out, uint32_t seed, uint64
 }
 
 }  // namespace kj
+
+namespace kj {
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Exact fp32 scan, round 2 (dim % 32 == 0): lane = row.
+// The kernels above reduce every row's dot products across the 32 lanes of a warp with shuffles (9 per row for 8 queries) and are
+// latency-bound on that butterfly (ncu: 41 % issue utilisation, 0.54 of the HBM copy rate).  Here a warp never reduces across lanes:
+//   * rows arrive as TMA boxes of 32 rows x 32 floats with the 128-byte swizzle, so lane r reads the 16-byte chunk c of ITS row
+//     conflict-free (physical chunk c ^ (r & 7)) while the chunk index c is the same for all lanes;
+//   * the <= 8 queries of the pass sit in shared memory and are read with warp-uniform (broadcast) 16-byte loads;
+//   * the 8 consumer warps split the dimension: warp w owns chunk w of every box (chunk j of a row belongs to group j % 8) and keeps
+//     8 packed accumulators (one per query) for its row; after the last box the 8 group partials of every (query, row) go through
+//     shared memory and warp q sums them IN GROUP ORDER, divides by the norms and maintains the CTA's top-k list of query q.
+// Fixed arithmetic order (scan_rescore_kernel reproduces it bit for bit): group partial = sequential FFMA2 over the group's chunks
+// in ascending order, (x,y) then (z,w), lo + hi; score numerator = ((((p0 + p1) + p2) + ...) + p7).
+// Issue slots per row: ~90 (was 139 + shuffle latency); shared-memory wavefronts per row: 36; HBM budget at 80 %: 83 clk per row.
+struct ScanT8Params {
+    const float* norms;     // [n_rows]
+    const float* queries;   // [Q, D]
+    const float* qnorms;    // [Q]
+    float* out_scores;      // [gridDim.x, Q, k]  per-CTA sorted candidates
+    uint32_t* out_ids;      // [gridDim.x, Q, k]  local row index, kNoId32 = empty
+    size_t n_rows;
+    int D, Q, k, q0, mode;
+    int ds;                 // floats of a row per stage (multiple of 32 dividing D, <= 384): wide rows take D / ds stages per tile
+    int nstages;
+};
+constexpr int kT8Warps = 8;         // warps of one team = chunk groups
+constexpr int kT8Rows = 32;
+template <int TEAMS>
+constexpr int t8_threads() { return (TEAMS * kT8Warps + 1) * 32; }
+
+inline size_t scan_t8_smem_bytes(int D, int ds, int nstages, int k, int teams) {
+    return 1024 /*align*/ + static_cast<size_t>(nstages) * ds * 128 + 8u * D * 4 + static_cast<size_t>(teams) * (2u * kT8Warps * 8 * kT8Rows * 4 + 8u * k * 8) +
+           2u * nstages * 8 + 64;
+}
+
+__device__ __forceinline__ void tma_load_2d_plain(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :
+                 : "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// TEAMS independent teams of 8 consumer warps share the stage ring: the CTA's i-th row tile goes to team i % TEAMS, which keeps its
+// own partial buffers, barrier and top-k lists (the CTA writes TEAMS lists per query; the merge kernel takes them all).  Two teams
+// double the warps that hide the shared-memory and barrier latencies of a tile.
+template <int TEAMS>
+__global__ void __launch_bounds__(t8_threads<TEAMS>(), 1) scan_t8_kernel(const __grid_constant__ CUtensorMap tmap_rows, ScanT8Params p) {
+    extern __shared__ uint8_t smem_t8_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_t8_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = p.D, k = p.k, ds = p.ds, nst = p.nstages;
+    const int stage_bytes = ds * 128;        // 32 rows x ds floats
+    const int boxes = ds / 32;               // TMA boxes (32 rows x 128 B) per stage
+    const int n_parts = D / ds;
+    uint8_t* stages = smem;
+    float* s_q = reinterpret_cast<float*>(stages + static_cast<size_t>(nst) * stage_bytes);  // [8][D]
+    float* s_part_all = s_q + 8 * D;                                                         // [TEAMS][2][8 groups][8 queries][32 rows]
+    float* l_sc_all = s_part_all + TEAMS * 2 * kT8Warps * 8 * kT8Rows;                       // [TEAMS][8][k]
+    uint32_t* l_id_all = reinterpret_cast<uint32_t*>(l_sc_all + TEAMS * 8 * k);              // [TEAMS][8][k]
+    // full barriers are PER TEAM: a parity wait is only exact for an observer that sees every phase of the barrier in order, and a
+    // team skips the other team's tiles (with one shared barrier per stage, team B's first wait -- parity 1 on a fresh barrier --
+    // would pass before anything had landed).  The producer alone observes the empty barriers, in order, so one per stage suffices.
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(l_id_all + TEAMS * 8 * k) + 7) & ~uintptr_t(7));  // [TEAMS][nst]
+    uint64_t* empty_bar = full_bar + TEAMS * nst;                                                                                     // [nst]
+
+    const int nq = min(8, p.Q - p.q0);  // live queries of this pass
+    for (int i = threadIdx.x; i < 8 * D; i += t8_threads<TEAMS>()) {
+        const int q = i / D, c = i - q * D;
+        s_q[i] = p.queries[static_cast<size_t>(p.q0 + min(q, nq - 1)) * D + c];  // dead query slots repeat the last live one
+    }
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_rows);
+        for (int i = 0; i < nst; ++i) mbar_init(&empty_bar[i], kT8Warps);
+        for (int i = 0; i < TEAMS * nst; ++i) mbar_init(&full_bar[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const size_t n_tiles = (p.n_rows + kT8Rows - 1) / kT8Rows;
+    if (warp == TEAMS * kT8Warps) {
+        // ------------------------------------------------------------ producer: one stage = `boxes` TMA boxes of one row tile
+        if (lane == 0) {
+            int it = 0, tile_i = 0;
+            for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+                uint64_t* fb = full_bar + (tile_i % TEAMS) * nst;  // the consuming team's barriers
+                for (int part = 0; part < n_parts; ++part, ++it) {
+                    const int stage = it % nst;
+                    mbar_wait(&empty_bar[stage], ((it / nst) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&fb[stage], static_cast<uint32_t>(stage_bytes));
+                    uint8_t* dst = stages + static_cast<size_t>(stage) * stage_bytes;
+                    for (int b = 0; b < boxes; ++b)
+                        tma_load_2d_plain(dst + b * 4096, &tmap_rows, &fb[stage], (part * boxes + b) * 32, static_cast<int32_t>(t * kT8Rows));
+                }
+            }
+        }
+    } else {
+        // ----------------------------------------------------------- consumers: team = tile parity, warp = chunk group, lane = row
+        const int team = warp / kT8Warps, w = warp % kT8Warps;
+        const uint32_t q_u32 = smem_u32(s_q);
+        const uint32_t my_chunk = (static_cast<uint32_t>(w) ^ static_cast<uint32_t>(lane & 7)) << 4;  // physical position of logical chunk `w`
+        const float qn = p.qnorms[p.q0 + min(w, nq - 1)];  // reducer role: warp q of the team owns query q
+        float* s_part = s_part_all + team * 2 * kT8Warps * 8 * kT8Rows;
+        float* my_sc = l_sc_all + (team * 8 + w) * k;
+        uint32_t* my_id = l_id_all + (team * 8 + w) * k;
+        int cnt = 0;
+        float thr = -INFINITY;
+        uint64_t* fb = full_bar + team * nst;
+        uint32_t uses = 0;       // bit s: parity of how often this team has consumed stage s = the phase parity of its barrier
+        int ti = 0, tile_i = 0;  // ti: tiles of this team so far; tile_i: tiles of the CTA so far
+        for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+            if (tile_i % TEAMS != team) continue;
+            // the reducer needs this row's norm at the very end of the tile: fetch it now, under the dot products
+            const size_t row = t * kT8Rows + lane;
+            const bool valid = row < p.n_rows;
+            const float rn = (w < nq && valid) ? __ldg(p.norms + row) : 1.0f;
+            uint64_t a2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a2[q] = 0ull;
+            for (int part = 0; part < n_parts; ++part) {
+                const int it = tile_i * n_parts + part;
+                const int stage = it % nst;
+                mbar_wait(&fb[stage], (uses >> stage) & 1);
+                uses ^= 1u << stage;
+                const uint32_t rbase = smem_u32(stages + static_cast<size_t>(stage) * stage_bytes) + lane * 128 + my_chunk;
+                const uint32_t qbase = q_u32 + static_cast<uint32_t>((part * ds + w * 4) * 4);
+#pragma unroll 2
+                for (int b = 0; b < boxes; ++b) {
+                    const uint4 rv = ld_shared_v4(rbase + b * 4096);
+                    const uint64_t rxy = (static_cast<uint64_t>(rv.y) << 32) | rv.x, rzw = (static_cast<uint64_t>(rv.w) << 32) | rv.z;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint4 qv = ld_shared_v4(qbase + static_cast<uint32_t>((q * D + b * 32) * 4));  // warp-uniform: broadcast
+                        a2[q] = f2_fma(rxy, (static_cast<uint64_t>(qv.y) << 32) | qv.x, a2[q]);
+                        a2[q] = f2_fma(rzw, (static_cast<uint64_t>(qv.w) << 32) | qv.z, a2[q]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            }
+            float* pp = s_part + ((ti & 1) * kT8Warps + w) * 8 * kT8Rows;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float lo, hi;
+                f2_unpack(a2[q], lo, hi);
+                pp[q * kT8Rows + lane] = lo + hi;
+            }
+            named_bar_sync(1 + team, kT8Warps * 32);
+            if (w < nq) {
+                const float* pr = s_part + (ti & 1) * kT8Warps * 8 * kT8Rows + w * kT8Rows + lane;
+                float acc = pr[0];
+#pragma unroll
+                for (int g = 1; g < kT8Warps; ++g) acc += pr[g * 8 * kT8Rows];
+                float s;
+                if (p.mode == SCAN_SEGMENT) s = rn < 1e-9f ? 0.0f : acc / (qn * rn);
+                else s = acc / fmaxf(qn * rn, 1e-9f);
+                uint32_t need = __ballot_sync(0xffffffffu, valid && s > thr);
+                while (need) {  // ascending rows: equal scores keep ascending ids
+                    const int b = __ffs(need) - 1;
+                    need &= need - 1;
+                    const float sb = __shfl_sync(0xffffffffu, s, b);
+                    if (sb > thr) warp_topk_insert(my_sc, my_id, k, cnt, thr, sb, static_cast<uint32_t>(t * kT8Rows + b), lane);
+                }
+            }
+            ++ti;
+        }
+        // the team's sorted list of query `w`: list index = blockIdx.x * TEAMS + team
+        if (w < nq) {
+            const size_t list = static_cast<size_t>(blockIdx.x) * TEAMS + team;
+            float* os = p.out_scores + (list * p.Q + p.q0 + w) * k;
+            uint32_t* oi = p.out_ids + (list * p.Q + p.q0 + w) * k;
+            __syncwarp();
+            for (int j = lane; j < k; j += 32) {
+                os[j] = j < cnt ? my_sc[j] : -INFINITY;
+                oi[j] = j < cnt ? my_id[j] : kNoId32;
+            }
+        }
+    }
+}
+
+}  // namespace kj

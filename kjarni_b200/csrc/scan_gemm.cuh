@@ -464,9 +464,11 @@ struct RescoreParams {
     int D, Q, k, mode;
 };
 
-// One warp per query: exact fp32 cosine of the C candidates (arithmetic identical to scan_topk_kernel: per-lane packed FMA over
-// float4 chunks, lo + hi, xor-butterfly 16..1, one divide), final order (score desc, id asc), proof check.  Lane l owns candidates
-// l, l + 32, ... (CPL = C / 32 of them).
+// One warp per query: exact fp32 cosine of the C candidates with EXACTLY the arithmetic of the exact scan (scan_t8_kernel, scan.cuh:
+// chunk j of a row belongs to group j % 8; group partial = sequential packed FMA over its chunks, (x,y) then (z,w), lo + hi;
+// numerator = ((((p0 + p1) + p2) + ...) + p7); one divide), so the filter path and the exact scan return bit-identical scores.
+// Final order (score desc, id asc), proof check.  Lane l owns candidates l, l + 32, ... (CPL = C / 32 of them) and computes the
+// whole dot product of each of them itself (dim % 32 == 0 on this path).
 template <int CPL>
 __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
     constexpr int C = 32 * CPL;
@@ -477,42 +479,39 @@ __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
     uint64_t my_gid[CPL];
     float my_approx[CPL], my_s[CPL];
     int ncand = 0;
+    const float* q = p.queries + static_cast<size_t>(qi) * p.D;
 #pragma unroll
     for (int u = 0; u < CPL; ++u) {
         my_gid[u] = p.cand_ids[static_cast<size_t>(qi) * C + u * 32 + lane];
         my_approx[u] = p.cand_scores[static_cast<size_t>(qi) * C + u * 32 + lane];
         my_s[u] = -INFINITY;
         ncand += __popc(__ballot_sync(0xffffffffu, my_gid[u] != kNoId64));  // candidates are packed at the front (sorted lists)
-    }
-    const float* q = p.queries + static_cast<size_t>(qi) * p.D;
-    for (int c = 0; c < ncand; ++c) {
-        uint64_t gid = 0;
+        if (my_gid[u] != kNoId64) {
+            const size_t r = static_cast<size_t>(my_gid[u] - p.id_base);
+            const float* rp = p.rows + r * p.D;
+            uint64_t a2[8];
 #pragma unroll
-        for (int u = 0; u < CPL; ++u) {
-            const uint64_t g = __shfl_sync(0xffffffffu, my_gid[u], c & 31);
-            if ((c >> 5) == u) gid = g;
+            for (int g = 0; g < 8; ++g) a2[g] = 0ull;
+            for (int c0 = 0; c0 < p.D; c0 += 32) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(rp + c0 + 4 * g);
+                    const ulonglong2 f = __ldg(reinterpret_cast<const ulonglong2*>(q + c0 + 4 * g));
+                    a2[g] = f2_fma(v.x, f.x, a2[g]);
+                    a2[g] = f2_fma(v.y, f.y, a2[g]);
+                }
+            }
+            float acc = 0.f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                float lo, hi;
+                f2_unpack(a2[g], lo, hi);
+                acc = g == 0 ? lo + hi : acc + (lo + hi);
+            }
+            const float rn = p.norms[r];
+            if (p.mode == SCAN_SEGMENT) my_s[u] = rn < 1e-9f ? 0.0f : acc / (qn * rn);
+            else my_s[u] = acc / fmaxf(qn * rn, 1e-9f);
         }
-        const size_t r = static_cast<size_t>(gid - p.id_base);
-        const float* rp = p.rows + r * p.D;
-        uint64_t a2 = 0ull;
-        for (int col = lane * 4; col < p.D; col += 128) {
-            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(rp + col);
-            const float4 f = *reinterpret_cast<const float4*>(q + col);
-            a2 = f2_fma(v.x, f2_pack(f.x, f.y), a2);
-            a2 = f2_fma(v.y, f2_pack(f.z, f.w), a2);
-        }
-        float lo, hi;
-        f2_unpack(a2, lo, hi);
-        float acc = lo + hi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        const float rn = p.norms[r];
-        float s;
-        if (p.mode == SCAN_SEGMENT) s = rn < 1e-9f ? 0.0f : acc / (qn * rn);
-        else s = acc / fmaxf(qn * rn, 1e-9f);
-#pragma unroll
-        for (int u = 0; u < CPL; ++u)
-            if (lane == (c & 31) && (c >> 5) == u) my_s[u] = s;
     }
     // rank among the candidates by (score desc, id asc)
     int rank[CPL];
