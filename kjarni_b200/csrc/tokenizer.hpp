@@ -43,6 +43,8 @@ inline bool is_other(uint32_t c) { return in_ranges(kUniOther, kUniOther_n, c); 
 inline bool is_mn(uint32_t c) { return in_ranges(kUniMn, kUniMn_n, c); }
 inline bool is_word(uint32_t c) { return in_ranges(kUniWord, kUniWord_n, c); }
 inline bool is_alnum(uint32_t c) { return in_ranges(kUniAlnum, kUniAlnum_n, c); }  // ~ Rust char::is_alphanumeric (see gen_unicode_tables.py)
+inline bool is_letter(uint32_t c) { return in_ranges(kUniLetter, kUniLetter_n, c); }  // regex \p{L}
+inline bool is_number(uint32_t c) { return in_ranges(kUniNumber, kUniNumber_n, c); }  // regex \p{N}
 inline bool is_ascii_punct(uint32_t c) { return (c >= 33 && c <= 47) || (c >= 58 && c <= 64) || (c >= 91 && c <= 96) || (c >= 123 && c <= 126); }
 inline bool is_punct(uint32_t c) { return is_ascii_punct(c) || in_ranges(kUniPunct, kUniPunct_n, c); }
 // BertNormalizer::is_chinese_char ranges
@@ -172,16 +174,54 @@ class Tokenizer {
             max_chars_ = static_cast<int>(model->number("max_input_chars_per_word", 100));
         } else if (mtype == "WordLevel") {
             wordpiece_ = false;
+        } else if (mtype == "BPE") {  // byte-level BPE of the RoBERTa family (tokenizers crate: models/bpe/model.rs, word.rs)
+            wordpiece_ = false;
+            bpe_ = true;
+            for (const char* k : {"dropout", "continuing_subword_prefix", "end_of_word_suffix"})
+                if (const Json* v = model->get(k))
+                    if (v->type != Json::Null) throw Error(KJC_INVALID_CONFIG, std::string("BPE option '") + k + "' is not supported");
+            if (const Json* v = model->get("byte_fallback"))
+                if (v->type == Json::Bool && v->b) throw Error(KJC_INVALID_CONFIG, "BPE byte_fallback is not supported");
         } else {
-            throw Error(KJC_INVALID_CONFIG, "tokenizer model '" + mtype + "' is not supported by the CUDA backend's tokenizer (WordPiece / WordLevel only): "
+            throw Error(KJC_INVALID_CONFIG, "tokenizer model '" + mtype + "' is not supported by the CUDA backend's tokenizer (WordPiece / WordLevel / BPE): "
                                             "pass token ids instead");
         }
         if (!vocab || vocab->type != Json::Obj) throw Error(KJC_LOAD_FAILED, "Failed to load tokenizer: model.vocab is not an object");
         vocab_.reserve(vocab->obj.size() * 2);
         for (auto& kv : vocab->obj)
             if (kv.second.type == Json::Num) vocab_[kv.first] = static_cast<uint32_t>(kv.second.num);
-        unk_ = model->string("unk_token", "[UNK]");
-        has_unk_ = lookup(unk_, unk_id_);
+        unk_ = model->string("unk_token", bpe_ ? "" : "[UNK]");
+        has_unk_ = !unk_.empty() && lookup(unk_, unk_id_);
+        if (bpe_) {
+            // merges: ["a b", ...] (older files) or [["a", "b"], ...]; rank = position; the merged token must be in the vocabulary
+            const Json* mg = model->get("merges");
+            if (!mg || mg->type != Json::Arr) throw Error(KJC_LOAD_FAILED, "Failed to load tokenizer: model.merges is not an array");
+            uint32_t rank = 0;
+            for (const Json& m : mg->arr) {
+                std::string a, b;
+                if (m.type == Json::Str) {
+                    const size_t sp = m.str.find(' ');
+                    if (sp == std::string::npos) throw Error(KJC_LOAD_FAILED, "Failed to load tokenizer: bad merge entry");
+                    a = m.str.substr(0, sp);
+                    b = m.str.substr(sp + 1);
+                } else if (m.type == Json::Arr && m.arr.size() == 2 && m.arr[0].type == Json::Str && m.arr[1].type == Json::Str) {
+                    a = m.arr[0].str;
+                    b = m.arr[1].str;
+                } else {
+                    throw Error(KJC_LOAD_FAILED, "Failed to load tokenizer: bad merge entry");
+                }
+                uint32_t ia, ib, iab;
+                if (!lookup(a, ia) || !lookup(b, ib) || !lookup(a + b, iab)) throw Error(KJC_LOAD_FAILED, "Failed to load tokenizer: merge token out of vocabulary");
+                merges_.emplace((static_cast<uint64_t>(ia) << 32) | ib, std::make_pair(rank, iab));
+                ++rank;
+            }
+            // bytes_to_unicode of the ByteLevel pre-tokenizer: printable bytes map to themselves, the rest to U+0100...
+            int n = 0;
+            for (int b = 0; b < 256; ++b) {
+                const bool keep = (b >= 33 && b <= 126) || (b >= 161 && b <= 172) || (b >= 174 && b <= 255);
+                byte_char_[b] = keep ? static_cast<uint32_t>(b) : static_cast<uint32_t>(256 + n++);
+            }
+        }
         if (const Json* n = j.get("normalizer")) parse_normalizer(*n);
         if (const Json* p = j.get("pre_tokenizer")) parse_pre(*p);
         if (const Json* at = j.get("added_tokens"))
@@ -266,7 +306,7 @@ class Tokenizer {
 
   private:
     enum NormOp { N_CLEAN, N_CJK, N_NFD, N_STRIP, N_LOWER };
-    enum PreOp { P_BERT, P_WHITESPACE, P_SPLIT };
+    enum PreOp { P_BERT, P_WHITESPACE, P_SPLIT, P_BYTELEVEL, P_BYTELEVEL_NOSPLIT };
     struct Added { std::string content; uint32_t id; };
     struct Piece { bool special; int seq; uint32_t type_id; uint32_t token_id; };
 
@@ -303,6 +343,11 @@ class Tokenizer {
         if (t == "BertPreTokenizer") pre_.push_back(P_BERT);
         else if (t == "Whitespace") pre_.push_back(P_WHITESPACE);
         else if (t == "WhitespaceSplit") pre_.push_back(P_SPLIT);
+        else if (t == "ByteLevel") {
+            auto flag = [&](const char* k, bool d) { const Json* v = p.get(k); return (v && v->type == Json::Bool) ? v->b : d; };
+            byte_prefix_space_ = flag("add_prefix_space", true);
+            pre_.push_back(flag("use_regex", true) ? P_BYTELEVEL : P_BYTELEVEL_NOSPLIT);
+        }
         else if (t == "Sequence") {
             if (const Json* l = p.get("pretokenizers"))
                 for (const Json& x : l->arr) parse_pre(x);
@@ -322,6 +367,12 @@ class Tokenizer {
             tok_pair("sep", sep);
             single_ = {{true, 0, 0, cls}, {false, 0, 0, 0}, {true, 0, 0, sep}};
             pair_ = {{true, 0, 0, cls}, {false, 0, 0, 0}, {true, 0, 0, sep}, {false, 1, 1, 0}, {true, 0, 1, sep}};
+        } else if (t == "RobertaProcessing") {  // <s> A </s>   and   <s> A </s> </s> B </s>, every type id 0 (processors/roberta.rs)
+            uint32_t cls = 0, sep = 0;
+            tok_pair("cls", cls);
+            tok_pair("sep", sep);
+            single_ = {{true, 0, 0, cls}, {false, 0, 0, 0}, {true, 0, 0, sep}};
+            pair_ = {{true, 0, 0, cls}, {false, 0, 0, 0}, {true, 0, 0, sep}, {true, 0, 0, sep}, {false, 1, 0, 0}, {true, 0, 0, sep}};
         } else if (t == "TemplateProcessing") {
             const Json* st = pp.get("special_tokens");
             auto parse_tpl = [&](const char* key, std::vector<Piece>& out) {
@@ -391,13 +442,57 @@ class Tokenizer {
         return cur;
     }
 
+    // GPT-2 / RoBERTa pattern of the ByteLevel pre-tokenizer (pre_tokenizers/byte_level.rs):
+    //   's|'t|'re|'ve|'m|'ll|'d| ?\p{L}+| ?\p{N}+| ?[^\s\p{L}\p{N}]+|\s+(?!\S)|\s+        (first matching alternative, greedy)
+    static size_t gpt2_match(const std::vector<uint32_t>& w, size_t i) {
+        const size_t n = w.size();
+        if (w[i] == '\'' && i + 1 < n) {
+            const uint32_t a = w[i + 1], b = i + 2 < n ? w[i + 2] : 0;
+            if (a == 's' || a == 't') return i + 2;
+            if ((a == 'r' && b == 'e') || (a == 'v' && b == 'e')) return i + 3;
+            if (a == 'm') return i + 2;
+            if (a == 'l' && b == 'l') return i + 3;
+            if (a == 'd') return i + 2;
+        }
+        auto cls = [&](size_t j) { return uni::is_letter(w[j]) ? 1 : (uni::is_number(w[j]) ? 2 : (uni::is_white(w[j]) ? 0 : 3)); };
+        const size_t j = (w[i] == ' ' && i + 1 < n) ? i + 1 : i;  // " ?"
+        const int c = cls(j);
+        if (c != 0) {  // alternatives 2-4: an optional space, then a run of one class
+            size_t e = j;
+            while (e < n && cls(e) == c) ++e;
+            return e;
+        }
+        size_t e = i;  // whitespace run
+        while (e < n && uni::is_white(w[e])) ++e;
+        if (e < n && e - i > 1) --e;  // \s+(?!\S): leave the last blank to the next token unless the run ends the text
+        return e;
+    }
+
     // splits [words] further according to one pre-tokenizer
-    static void pre_split(PreOp op, const std::vector<std::vector<uint32_t>>& in, std::vector<std::vector<uint32_t>>& out) {
+    void pre_split(PreOp op, const std::vector<std::vector<uint32_t>>& in, std::vector<std::vector<uint32_t>>& out) const {
         out.clear();
         for (const auto& w : in) {
             std::vector<uint32_t> cur;
             auto flush = [&] { if (!cur.empty()) { out.push_back(cur); cur.clear(); } };
-            if (op == P_BERT) {
+            if (op == P_BYTELEVEL || op == P_BYTELEVEL_NOSPLIT) {
+                std::vector<uint32_t> t;
+                if (byte_prefix_space_ && !w.empty() && w[0] != ' ') t.push_back(' ');
+                t.insert(t.end(), w.begin(), w.end());
+                auto emit = [&](size_t a, size_t b) {  // UTF-8 bytes of the piece, each mapped to its stand-in character
+                    std::string u8;
+                    for (size_t i = a; i < b; ++i) uni::encode_append(t[i], u8);
+                    std::vector<uint32_t> piece;
+                    for (unsigned char ch : u8) piece.push_back(byte_char_[ch]);
+                    if (!piece.empty()) out.push_back(std::move(piece));
+                };
+                if (op == P_BYTELEVEL_NOSPLIT) emit(0, t.size());
+                else
+                    for (size_t i = 0; i < t.size();) {
+                        const size_t e = gpt2_match(t, i);
+                        emit(i, e);
+                        i = e;
+                    }
+            } else if (op == P_BERT) {
                 for (uint32_t c : w) {
                     if (uni::is_white(c)) flush();
                     else if (uni::is_punct(c)) { flush(); out.push_back({c}); }
@@ -423,8 +518,38 @@ class Tokenizer {
         }
     }
 
+    // BPE of one pre-token (models/bpe/word.rs merge_all): symbols = characters; repeatedly apply the merge of lowest rank, leftmost
+    // first, one occurrence at a time; a character outside the vocabulary becomes unk (or is dropped when there is no unk token)
+    void bpe_tokens(const std::vector<uint32_t>& word, std::vector<uint32_t>& ids) const {
+        std::vector<uint32_t> sym;
+        std::string s;
+        for (uint32_t c : word) {
+            s.clear();
+            uni::encode_append(c, s);
+            uint32_t id;
+            if (lookup(s, id)) sym.push_back(id);
+            else if (has_unk_) sym.push_back(unk_id_);
+        }
+        while (sym.size() > 1) {
+            uint32_t best_rank = 0xFFFFFFFFu, best_id = 0;
+            size_t best_pos = 0;
+            for (size_t i = 0; i + 1 < sym.size(); ++i) {
+                auto it = merges_.find((static_cast<uint64_t>(sym[i]) << 32) | sym[i + 1]);
+                if (it != merges_.end() && it->second.first < best_rank) { best_rank = it->second.first; best_id = it->second.second; best_pos = i; }
+            }
+            if (best_rank == 0xFFFFFFFFu) break;
+            sym[best_pos] = best_id;
+            sym.erase(sym.begin() + static_cast<long>(best_pos) + 1);
+        }
+        ids.insert(ids.end(), sym.begin(), sym.end());
+    }
+
     void model_tokens(const std::vector<uint32_t>& word, std::vector<uint32_t>& ids) const {
         std::string s;
+        if (bpe_) {
+            bpe_tokens(word, ids);
+            return;
+        }
         if (!wordpiece_) {  // WordLevel: whole word or unk
             for (uint32_t c : word) uni::encode_append(c, s);
             uint32_t id;
@@ -489,7 +614,9 @@ class Tokenizer {
     }
 
     int max_length_;
-    bool wordpiece_ = true, has_unk_ = false;
+    bool wordpiece_ = true, has_unk_ = false, bpe_ = false, byte_prefix_space_ = true;
+    std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> merges_;  // (left id, right id) -> (rank, merged id)
+    uint32_t byte_char_[256] = {};
     std::string prefix_ = "##", unk_ = "[UNK]";
     uint32_t unk_id_ = 0;
     int max_chars_ = 100;

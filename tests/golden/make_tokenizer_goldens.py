@@ -9,7 +9,7 @@ Writes tests/golden/tokenizers/<name>.tokenizer.json (small synthetic vocabulari
 import json
 import os
 
-from tokenizers import Tokenizer, models, normalizers, pre_tokenizers, processors
+from tokenizers import Tokenizer, decoders, models, normalizers, pre_tokenizers, processors, trainers
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "tokenizers")
@@ -76,6 +76,18 @@ def make_tokenizers():
     t.post_processor = processors.TemplateProcessing(single="[CLS] $A [SEP]", pair="[CLS] $A [SEP] $B:1 [SEP]:1",
                                                      special_tokens=[("[CLS]", 101), ("[SEP]", 102)])
     toks["sequence"] = t
+    # byte-level BPE in the RoBERTa layout (roberta-base / distilroberta tokenizer.json): ByteLevel pre-tokenizer with the GPT-2
+    # pattern, RobertaProcessing (<s> A </s>, <s> A </s></s> B </s>), merges learned here from a small corpus
+    t = Tokenizer(models.BPE(unk_token=None))
+    t.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    t.decoder = decoders.ByteLevel()
+    corpus = [" ".join(WORDS[i:i + 9]) + "." for i in range(0, len(WORDS), 7)] + SINGLES + [a + " " + b for a, b in PAIRS] + \
+             ["It's 2019, isn't it? They've said we'll go; I'm sure he'd agree.", "Numbers 123 4567 and symbols #!$ %^& mix\twith\n\nnewlines   and   spaces "]
+    trainer = trainers.BpeTrainer(vocab_size=700, min_frequency=1, special_tokens=["<s>", "<pad>", "</s>", "<unk>", "<mask>"],
+                                  initial_alphabet=pre_tokenizers.ByteLevel.alphabet(), show_progress=False)
+    t.train_from_iterator(corpus, trainer)
+    t.post_processor = processors.RobertaProcessing(sep=("</s>", 2), cls=("<s>", 0))
+    toks["roberta_bpe"] = t
     return toks
 
 

@@ -232,6 +232,33 @@ def test_classifier_matches_oracle(ffi, models):
     assert ffi.kjarni_classifier_new(C.byref(cfg), C.byref(h)) == 7
 
 
+def test_roberta_classifier_from_text(ffi, models, tmp_path):
+    """A RoBERTa-family classifier preset end to end from TEXT: byte-level BPE tokenizer (tokenizer.hpp, pinned to the `tokenizers`
+    crate in tests/test_tokenizer_cpu.py) -> position ids offset by 2 -> roberta layout -> classifier.dense / out_proj head."""
+    cache = tmp_path / "cache"
+    d = synth.write_model_dir(str(cache / "olafuraron_emotion-english-distilroberta-base-safetensors"), "tiny-roberta")
+    bpe = os.path.join(HERE, "golden", "tokenizers", "roberta_bpe.tokenizer.json")
+    shutil.copy(bpe, os.path.join(d, "tokenizer.json"))
+    cfg = ffi.kjarni_classifier_config_default()
+    cfg.device, cfg.cache_dir, cfg.model_name = GPU, str(cache).encode(), b"distilroberta-emotion"
+    h = C.c_void_p()
+    assert ffi.kjarni_classifier_new(C.byref(cfg), C.byref(h)) == 0, ffi.kjarni_last_error_message()
+    assert ffi.kjarni_classifier_num_labels(h) == 3
+    tok = api.Tokenizer(bpe, 66)
+    m = ko.load_model_dir(d)
+    for text in TEXTS[:5] + ["It's we'll   spaced\nout, isn't it?"]:
+        res = ClassResults()
+        assert ffi.kjarni_classifier_classify(h, text.encode(), C.byref(res)) == 0 and res.len == 3
+        got = {res.results[i].label.decode(): res.results[i].score for i in range(3)}
+        ffi.kjarni_class_results_free(C.byref(res))
+        ids, mask, _ = tok.encode_batch([text])
+        assert ids[0, 0] == 0 and ids[0, int(mask.sum()) - 1] == 2  # <s> ... </s>
+        p = ko.classify_probs(ko.predict_logits(m, ids, mask))[0]
+        for i in range(3):
+            assert abs(got["LABEL_%d" % i] - p[i]) < 2e-2
+    ffi.kjarni_classifier_free(h)
+
+
 def test_reranker_matches_oracle(ffi, models):
     cfg = ffi.kjarni_reranker_config_default()
     cfg.device = GPU

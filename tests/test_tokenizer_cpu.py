@@ -1,4 +1,5 @@
-"""The C++ tokenizer (kjarni_b200/csrc/tokenizer.hpp; host-only, no GPU) against goldens produced by
+"""The C++ tokenizer (kjarni_b200/csrc/tokenizer.hpp; host-only, no GPU: WordPiece, WordLevel and the byte-level
+BPE of the RoBERTa family) against goldens produced by
 the HuggingFace `tokenizers` crate's own Python binding (tests/golden/make_tokenizer_goldens.py) with the reference's
 settings: truncation to max_length (LongestFirst), BatchLongest padding, add_special_tokens = true, texts and pairs."""
 import json
@@ -39,11 +40,15 @@ def test_token_to_id_and_errors(tmp_path):
     with pytest.raises(N.KjarniCudaError) as e:
         api.Tokenizer(str(tmp_path / "missing.json"))
     assert e.value.status == N.KJC_MODEL_NOT_FOUND
-    p = tmp_path / "bpe.json"
-    p.write_text(json.dumps({"model": {"type": "BPE", "vocab": {}, "merges": []}}))
+    p = tmp_path / "unigram.json"
+    p.write_text(json.dumps({"model": {"type": "Unigram", "vocab": []}}))
     with pytest.raises(N.KjarniCudaError) as e:
         api.Tokenizer(str(p))
-    assert e.value.status == N.KJC_INVALID_CONFIG  # byte-level BPE (RoBERTa) is driven with token ids instead
+    assert e.value.status == N.KJC_INVALID_CONFIG  # WordPiece / WordLevel / byte-level BPE are restated; SentencePiece models are not
+    p.write_text(json.dumps({"model": {"type": "BPE", "vocab": {"a": 0, "b": 1}, "merges": ["a b"]}}))
+    with pytest.raises(N.KjarniCudaError) as e:  # the merged token "ab" is not in the vocabulary
+        api.Tokenizer(str(p))
+    assert e.value.status == N.KJC_LOAD_FAILED
     p.write_text("{broken")
     with pytest.raises(N.KjarniCudaError) as e:
         api.Tokenizer(str(p))
