@@ -33,7 +33,7 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
     if (const char* e = getenv("KJC_SCAN_GEMM_MIN_Q")) filter_min_q_ = std::max(1, atoi(e));
     // exact scan: lane-per-row kernel on TMA-swizzled 32 x 32-float boxes when the dimension allows it (scan.cuh, scan_t8_kernel)
     scan_t8_ = dim % 32 == 0 && getenv("KJC_SCAN_NO_T8") == nullptr;
-    if (scan_t8_) t_rows32_ = make_tmap_2d(rows_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, capacity, dim, kT8Rows, 32, 128);
+    if (scan_t8_) t_rows32_ = make_tmap_2d(rows_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, capacity, dim, kT8Rows, 32, 128);  // 64 rows x 32 floats
     if (gemm_ok_) {
         const uint64_t cap16 = std::max<uint64_t>(capacity, kSgRows);  // at least one TMA box of rows
         KJ_CUDA(cudaMalloc(&rows16_, cap16 * dim * sizeof(__nv_bfloat16)));
@@ -171,13 +171,13 @@ static void launch_scan_inst(ScanParams p, int grid, cudaStream_t st) {
 constexpr int kT8Teams = 2;
 static void launch_scan_t8(const CUtensorMap& t_rows, ScanT8Params p, int grid, cudaStream_t st) {
     static int configured[64] = {0};
-    // floats of a row per stage: the largest multiple of 32 that divides D and is <= 384 (48 KB stages at most)
+    // floats of a row per stage: the largest multiple of 32 that divides D and is <= 192 (64 rows x 192 floats = 48 KB stages at most)
     int ds = 32;
-    for (int c = 32; c <= 384 && c <= p.D; c += 32)
+    for (int c = 32; c <= 192 && c <= p.D; c += 32)
         if (p.D % c == 0) ds = c;
     p.ds = ds;
     const size_t fixed = scan_t8_smem_bytes(p.D, ds, 0, p.k, kT8Teams);
-    p.nstages = static_cast<int>(std::min<size_t>(4, (220 * 1024 - fixed) / (static_cast<size_t>(ds) * 128 + 16)));
+    p.nstages = static_cast<int>(std::min<size_t>(4, (226 * 1024 - fixed) / (static_cast<size_t>(ds) * kT8Rows * 4)));
     if (p.nstages < 2) throw Error(KJC_INVALID_CONFIG, "index dimension too large for the scan pipeline");
     const size_t smem = scan_t8_smem_bytes(p.D, ds, p.nstages, p.k, kT8Teams);
     ensure_smem_attr(scan_t8_kernel<kT8Teams>, static_cast<int>(smem), configured);

@@ -401,8 +401,8 @@ namespace kj {
 // Exact fp32 scan, round 2 (dim % 32 == 0): lane = row.
 // The kernels above reduce every row's dot products across the 32 lanes of a warp with shuffles (9 per row for 8 queries) and are
 // latency-bound on that butterfly (ncu: 41 % issue utilisation, 0.54 of the HBM copy rate).  Here a warp never reduces across lanes:
-//   * rows arrive as TMA boxes of 32 rows x 32 floats with the 128-byte swizzle, so lane r reads the 16-byte chunk c of ITS row
-//     conflict-free (physical chunk c ^ (r & 7)) while the chunk index c is the same for all lanes;
+//   * rows arrive as TMA boxes of 64 rows x 32 floats with the 128-byte swizzle, so lane l reads the 16-byte chunk c of ITS rows
+//     (l and l + 32) conflict-free (physical chunk c ^ (row & 7)) while the chunk index c is the same for all lanes;
 //   * the <= 8 queries of the pass sit in shared memory and are read with warp-uniform (broadcast) 16-byte loads;
 //   * the 8 consumer warps split the dimension: warp w owns chunk w of every box (chunk j of a row belongs to group j % 8) and keeps
 //     8 packed accumulators (one per query) for its row; after the last box the 8 group partials of every (query, row) go through
@@ -418,17 +418,18 @@ struct ScanT8Params {
     uint32_t* out_ids;      // [gridDim.x, Q, k]  local row index, kNoId32 = empty
     size_t n_rows;
     int D, Q, k, q0, mode;
-    int ds;                 // floats of a row per stage (multiple of 32 dividing D, <= 384): wide rows take D / ds stages per tile
+    int ds;                 // floats of a row per stage (multiple of 32 dividing D, <= 192): wide rows take D / ds stages per tile
     int nstages;
 };
 constexpr int kT8Warps = 8;         // warps of one team = chunk groups
-constexpr int kT8Rows = 32;
+constexpr int kT8Rows = 64;         // rows per tile: lane l owns rows l and l + 32 (the query loads are shared by both)
+constexpr int kT8BoxBytes = kT8Rows * 128;
 template <int TEAMS>
 constexpr int t8_threads() { return (TEAMS * kT8Warps + 1) * 32; }
 
 inline size_t scan_t8_smem_bytes(int D, int ds, int nstages, int k, int teams) {
-    return 1024 /*align*/ + static_cast<size_t>(nstages) * ds * 128 + 8u * D * 4 + static_cast<size_t>(teams) * (2u * kT8Warps * 8 * kT8Rows * 4 + 8u * k * 8) +
-           2u * nstages * 8 + 64;
+    return 1024 /*align*/ + static_cast<size_t>(nstages) * ds * kT8Rows * 4 + 8u * D * 4 +
+           static_cast<size_t>(teams) * (2u * kT8Warps * 8 * kT8Rows * 4 + 8u * k * 8) + 3u * 4 * 8 + 64;
 }
 
 __device__ __forceinline__ void tma_load_2d_plain(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
@@ -436,6 +437,10 @@ __device__ __forceinline__ void tma_load_2d_plain(void* smem_dst, const void* tm
                  :
                  : "r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
+}
+// 16 bytes of shared memory as two packed fp32 pairs (no register shuffling between the load and the FFMA2s)
+__device__ __forceinline__ void ld_shared_2x64(uint32_t addr, uint64_t& lo, uint64_t& hi) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(addr));
 }
 
 // TEAMS independent teams of 8 consumer warps share the stage ring: the CTA's i-th row tile goes to team i % TEAMS, which keeps its
@@ -447,12 +452,12 @@ __global__ void __launch_bounds__(t8_threads<TEAMS>(), 1) scan_t8_kernel(const _
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_t8_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = p.D, k = p.k, ds = p.ds, nst = p.nstages;
-    const int stage_bytes = ds * 128;        // 32 rows x ds floats
-    const int boxes = ds / 32;               // TMA boxes (32 rows x 128 B) per stage
+    const int boxes = ds / 32;                    // TMA boxes (64 rows x 128 B) per stage
+    const int stage_bytes = boxes * kT8BoxBytes;  // 64 rows x ds floats
     const int n_parts = D / ds;
     uint8_t* stages = smem;
     float* s_q = reinterpret_cast<float*>(stages + static_cast<size_t>(nst) * stage_bytes);  // [8][D]
-    float* s_part_all = s_q + 8 * D;                                                         // [TEAMS][2][8 groups][8 queries][32 rows]
+    float* s_part_all = s_q + 8 * D;                                                         // [TEAMS][2][8 groups][8 queries][64 rows]
     float* l_sc_all = s_part_all + TEAMS * 2 * kT8Warps * 8 * kT8Rows;                       // [TEAMS][8][k]
     uint32_t* l_id_all = reinterpret_cast<uint32_t*>(l_sc_all + TEAMS * 8 * k);              // [TEAMS][8][k]
     // full barriers are PER TEAM: a parity wait is only exact for an observer that sees every phase of the barrier in order, and a
@@ -487,12 +492,12 @@ __global__ void __launch_bounds__(t8_threads<TEAMS>(), 1) scan_t8_kernel(const _
                     mbar_arrive_expect_tx(&fb[stage], static_cast<uint32_t>(stage_bytes));
                     uint8_t* dst = stages + static_cast<size_t>(stage) * stage_bytes;
                     for (int b = 0; b < boxes; ++b)
-                        tma_load_2d_plain(dst + b * 4096, &tmap_rows, &fb[stage], (part * boxes + b) * 32, static_cast<int32_t>(t * kT8Rows));
+                        tma_load_2d_plain(dst + b * kT8BoxBytes, &tmap_rows, &fb[stage], (part * boxes + b) * 32, static_cast<int32_t>(t * kT8Rows));
                 }
             }
         }
     } else {
-        // ----------------------------------------------------------- consumers: team = tile parity, warp = chunk group, lane = row
+        // ----------------------------------------------------------- consumers: team = tile parity, warp = chunk group, lane = 2 rows
         const int team = warp / kT8Warps, w = warp % kT8Warps;
         const uint32_t q_u32 = smem_u32(s_q);
         const uint32_t my_chunk = (static_cast<uint32_t>(w) ^ static_cast<uint32_t>(lane & 7)) << 4;  // physical position of logical chunk `w`
@@ -507,13 +512,14 @@ __global__ void __launch_bounds__(t8_threads<TEAMS>(), 1) scan_t8_kernel(const _
         int ti = 0, tile_i = 0;  // ti: tiles of this team so far; tile_i: tiles of the CTA so far
         for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
             if (tile_i % TEAMS != team) continue;
-            // the reducer needs this row's norm at the very end of the tile: fetch it now, under the dot products
-            const size_t row = t * kT8Rows + lane;
-            const bool valid = row < p.n_rows;
-            const float rn = (w < nq && valid) ? __ldg(p.norms + row) : 1.0f;
-            uint64_t a2[8];
+            // the reducer needs these rows' norms at the very end of the tile: fetch them now, under the dot products
+            const size_t row0 = t * kT8Rows + lane, row1 = row0 + 32;
+            const bool valid0 = row0 < p.n_rows, valid1 = row1 < p.n_rows;
+            const float rn0 = (w < nq && valid0) ? __ldg(p.norms + row0) : 1.0f;
+            const float rn1 = (w < nq && valid1) ? __ldg(p.norms + row1) : 1.0f;
+            uint64_t a0[8], a1[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) a2[q] = 0ull;
+            for (int q = 0; q < 8; ++q) a0[q] = a1[q] = 0ull;
             for (int part = 0; part < n_parts; ++part) {
                 const int it = tile_i * n_parts + part;
                 const int stage = it % nst;
@@ -523,40 +529,63 @@ __global__ void __launch_bounds__(t8_threads<TEAMS>(), 1) scan_t8_kernel(const _
                 const uint32_t qbase = q_u32 + static_cast<uint32_t>((part * ds + w * 4) * 4);
 #pragma unroll 2
                 for (int b = 0; b < boxes; ++b) {
-                    const uint4 rv = ld_shared_v4(rbase + b * 4096);
-                    const uint64_t rxy = (static_cast<uint64_t>(rv.y) << 32) | rv.x, rzw = (static_cast<uint64_t>(rv.w) << 32) | rv.z;
+                    uint64_t r0xy, r0zw, r1xy, r1zw;
+                    ld_shared_2x64(rbase + b * kT8BoxBytes, r0xy, r0zw);
+                    ld_shared_2x64(rbase + b * kT8BoxBytes + 32 * 128, r1xy, r1zw);  // row + 32: same swizzle phase (32 % 8 == 0)
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const uint4 qv = ld_shared_v4(qbase + static_cast<uint32_t>((q * D + b * 32) * 4));  // warp-uniform: broadcast
-                        a2[q] = f2_fma(rxy, (static_cast<uint64_t>(qv.y) << 32) | qv.x, a2[q]);
-                        a2[q] = f2_fma(rzw, (static_cast<uint64_t>(qv.w) << 32) | qv.z, a2[q]);
+                        uint64_t qxy, qzw;
+                        ld_shared_2x64(qbase + static_cast<uint32_t>((q * D + b * 32) * 4), qxy, qzw);  // warp-uniform: broadcast
+                        a0[q] = f2_fma(r0xy, qxy, a0[q]);
+                        a0[q] = f2_fma(r0zw, qzw, a0[q]);
+                        a1[q] = f2_fma(r1xy, qxy, a1[q]);
+                        a1[q] = f2_fma(r1zw, qzw, a1[q]);
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[stage]);
             }
-            float* pp = s_part + ((ti & 1) * kT8Warps + w) * 8 * kT8Rows;
+            const uint32_t pp = smem_u32(s_part + ((ti & 1) * kT8Warps + w) * 8 * kT8Rows) + lane * 4;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 float lo, hi;
-                f2_unpack(a2[q], lo, hi);
-                pp[q * kT8Rows + lane] = lo + hi;
+                f2_unpack(a0[q], lo, hi);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp + (q * kT8Rows) * 4), "f"(lo + hi) : "memory");
+                f2_unpack(a1[q], lo, hi);
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(pp + (q * kT8Rows + 32) * 4), "f"(lo + hi) : "memory");
             }
             named_bar_sync(1 + team, kT8Warps * 32);
             if (w < nq) {
-                const float* pr = s_part + (ti & 1) * kT8Warps * 8 * kT8Rows + w * kT8Rows + lane;
-                float acc = pr[0];
+                const uint32_t pr = smem_u32(s_part + (ti & 1) * kT8Warps * 8 * kT8Rows + w * kT8Rows) + lane * 4;
+                float acc0, acc1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(acc0) : "r"(pr));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(acc1) : "r"(pr + 128));
 #pragma unroll
-                for (int g = 1; g < kT8Warps; ++g) acc += pr[g * 8 * kT8Rows];
-                float s;
-                if (p.mode == SCAN_SEGMENT) s = rn < 1e-9f ? 0.0f : acc / (qn * rn);
-                else s = acc / fmaxf(qn * rn, 1e-9f);
-                uint32_t need = __ballot_sync(0xffffffffu, valid && s > thr);
-                while (need) {  // ascending rows: equal scores keep ascending ids
-                    const int b = __ffs(need) - 1;
-                    need &= need - 1;
-                    const float sb = __shfl_sync(0xffffffffu, s, b);
-                    if (sb > thr) warp_topk_insert(my_sc, my_id, k, cnt, thr, sb, static_cast<uint32_t>(t * kT8Rows + b), lane);
+                for (int g = 1; g < kT8Warps; ++g) {
+                    float x0, x1;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x0) : "r"(pr + g * 8 * kT8Rows * 4));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x1) : "r"(pr + g * 8 * kT8Rows * 4 + 128));
+                    acc0 += x0;
+                    acc1 += x1;
+                }
+                float s0, s1;
+                if (p.mode == SCAN_SEGMENT) {
+                    s0 = rn0 < 1e-9f ? 0.0f : acc0 / (qn * rn0);
+                    s1 = rn1 < 1e-9f ? 0.0f : acc1 / (qn * rn1);
+                } else {
+                    s0 = acc0 / fmaxf(qn * rn0, 1e-9f);
+                    s1 = acc1 / fmaxf(qn * rn1, 1e-9f);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {  // rows t*64 + [0, 32), then + [32, 64): ascending ids, equal scores keep ascending ids
+                    const float s = h ? s1 : s0;
+                    uint32_t need = __ballot_sync(0xffffffffu, (h ? valid1 : valid0) && s > thr);
+                    while (need) {
+                        const int b = __ffs(need) - 1;
+                        need &= need - 1;
+                        const float sb = __shfl_sync(0xffffffffu, s, b);
+                        if (sb > thr) warp_topk_insert(my_sc, my_id, k, cnt, thr, sb, static_cast<uint32_t>(t * kT8Rows + h * 32 + b), lane);
+                    }
                 }
             }
             ++ti;
