@@ -938,13 +938,16 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         KJ_CUDA(cudaGetLastError());
         ++launches_;
     } else if (o.output == KJC_OUT_POOLED) {
-        if (o.pooling == KJC_POOL_MEAN && H <= 1024 && H % 4 == 0) {
-            const size_t smem = static_cast<size_t>(kPoolWarps) * H * sizeof(float);  // <= 64 KB at H = 1024
+        if (o.pooling == KJC_POOL_MEAN && H <= 512 && H % 4 == 0) {
+            // the 16-warp kernel keeps NV float4 accumulators per lane: up to hidden 512 without spills; wider models (768, 1024: a
+            // negligible share of a 12-layer step) take the generic kernel below
+            const size_t smem = static_cast<size_t>(kPoolWarps) * H * sizeof(float);  // <= 32 KB
             dispatch_nv(H, [&](auto nv) {
-                static int configured[64] = {0};  // one per instantiation (the lambda is instantiated per NV)
-                auto kern = mean_pool_l2_kernel<decltype(nv)::value>;
-                if (smem > 40 * 1024) ensure_smem_attr(kern, static_cast<int>(smem), configured);  // static + dynamic beyond the 48 KB default
-                launch_pdl(kern, dim3(nb), dim3(kPoolThreads), smem, st, static_cast<const __nv_bfloat16*>(w.x16), d_mask, d_out, S, H, static_cast<int>(o.normalize));
+                constexpr int NV = decltype(nv)::value;
+                if constexpr (NV <= 4) {
+                    launch_pdl(mean_pool_l2_kernel<NV>, dim3(nb), dim3(kPoolThreads), smem, st, static_cast<const __nv_bfloat16*>(w.x16), d_mask, d_out, S, H,
+                               static_cast<int>(o.normalize));
+                }
             });
         } else {
             pool_l2_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(w.x16, d_mask, d_out, S, H, o.pooling, o.normalize);

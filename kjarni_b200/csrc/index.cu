@@ -32,6 +32,7 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
     if (const char* e = getenv("KJC_SCAN_EPS")) filter_eps_ = static_cast<float>(atof(e));
     if (const char* e = getenv("KJC_SCAN_GEMM_MIN_Q")) filter_min_q_ = std::max(1, atoi(e));
     // exact scan: lane-per-row kernel on TMA-swizzled 32 x 32-float boxes when the dimension allows it (scan.cuh, scan_t8_kernel)
+    escalate_ = getenv("KJC_SCAN_NO_ESCALATE") == nullptr;
     scan_t8_ = dim % 32 == 0 && getenv("KJC_SCAN_NO_T8") == nullptr;
     if (scan_t8_) t_rows32_ = make_tmap_2d(rows_, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, capacity, dim, kT8Rows, 32, 128);  // 64 rows x 32 floats
     if (gemm_ok_) {
@@ -54,7 +55,7 @@ Index::~Index() {
     for (void* p : {(void*)rows_, (void*)norms_, (void*)d_q_, (void*)d_qn_, (void*)d_cand_s_, (void*)d_cand_i_, (void*)d_out_s_,
                     (void*)d_out_i_, (void*)d_out_c_, (void*)rows16_, (void*)d_q16_, (void*)d_gc_s_, (void*)d_gc_i_,
                     (void*)d_am_s_, (void*)d_am_i_, (void*)d_fix_q_, (void*)d_fix_s_, (void*)d_fix_i_, (void*)d_fix_c_, (void*)d_flags_,
-                    (void*)d_nflag_, (void*)d_seed_})
+                    (void*)d_nflag_, (void*)d_seed_, (void*)d_esc_map_, (void*)d_esc_s_, (void*)d_esc_i_})
         if (p) cudaFree(p);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -192,9 +193,15 @@ static void launch_scan_qt(const ScanParams& p, int grid, cudaStream_t st) {
         case 1: launch_scan_inst<QT, 1>(p, grid, st); break;
         case 2: launch_scan_inst<QT, 2>(p, grid, st); break;
         case 3: launch_scan_inst<QT, 3>(p, grid, st); break;
-        case 4: launch_scan_inst<QT, 4>(p, grid, st); break;
-        case 5: case 6: launch_scan_inst<QT, 6>(p, grid, st); break;
-        default: launch_scan_inst<QT, 8>(p, grid, st); break;
+        default:
+            if constexpr (QT <= 2) {
+                if (nch == 4) launch_scan_inst<QT, 4>(p, grid, st);
+                else if (nch <= 6) launch_scan_inst<QT, 6>(p, grid, st);
+                else launch_scan_inst<QT, 8>(p, grid, st);
+            } else {
+                throw Error(KJC_INVALID_CONFIG, "internal: 4 queries per warp need dim <= 384");
+            }
+            break;
     }
 }
 
@@ -342,7 +349,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         ++launches_;
         CandSelectParams cs;
         cs.cand_scores = d_gc_s_; cs.cand_ids = d_gc_i_; cs.cand_cnt = d_cnt; cs.id_base = id_base_;
-        cs.out_scores = d_am_s_; cs.out_ids = d_am_i_; cs.overflow = d_overflow; cs.C = C;
+        cs.out_scores = d_am_s_; cs.out_ids = d_am_i_; cs.overflow = d_overflow; cs.C = C; cs.qmap = nullptr;
         scan_cand_select_kernel<<<nq, 256, 0, st>>>(cs);
         KJ_CUDA(cudaGetLastError());
         ++launches_;
@@ -350,7 +357,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         r.rows = rows_; r.norms = norms_; r.queries = d_q; r.qnorms = d_qn_; r.cand_ids = d_am_i_; r.cand_scores = d_am_s_; r.id_base = id_base_;
         r.out_ids = d_ids; r.out_scores = d_scores; r.out_counts = d_counts; r.overflow = d_overflow; r.thr0 = d_thr0;
         r.flags = d_flags_; r.n_flagged = d_nflag_;
-        r.eps = filter_eps_; r.D = dim_; r.Q = nq; r.k = k; r.mode = mode;
+        r.eps = filter_eps_; r.D = dim_; r.Q = nq; r.k = k; r.mode = mode; r.qmap = nullptr;
         if (C == kSgC) scan_rescore_kernel<1><<<(nq + 7) / 8, 256, 0, st>>>(r);
         else scan_rescore_kernel<kSgCWide / 32><<<(nq + 7) / 8, 256, 0, st>>>(r);
         KJ_CUDA(cudaGetLastError());
@@ -370,6 +377,40 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         std::vector<int> todo;
         for (int i = 0; i < nq; ++i)
             if (h_flags_[i]) todo.push_back(i);
+        // Escalation before the exact scan: the filter pass kept EVERY row above the seed bound (up to 2048 per query), so an unproven
+        // query is first re-selected with 128 instead of 32 candidates from the same buffer and re-scored -- a wider list lowers the
+        // bound on everything outside it (or, when it holds all passers, the bound becomes the seed bound itself).  Costs two small
+        // kernels over the flagged queries only; an exact pass over the shard costs ~1.5 ms per 8 queries.
+        if (escalate_ && C == kSgC && !todo.empty() && 2 * k <= kSgCWide) {
+            const size_t ns = todo.size();
+            if (ns > esc_cap_) {
+                for (void* q : {(void*)d_esc_map_, (void*)d_esc_s_, (void*)d_esc_i_}) if (q) cudaFree(q);
+                KJ_CUDA(cudaMalloc(&d_esc_map_, ns * 4));
+                KJ_CUDA(cudaMalloc(&d_esc_s_, ns * kSgCWide * 4));
+                KJ_CUDA(cudaMalloc(&d_esc_i_, ns * kSgCWide * 8));
+                esc_cap_ = ns;
+            }
+            KJ_CUDA(cudaMemcpyAsync(d_esc_map_, todo.data(), ns * 4, cudaMemcpyHostToDevice, st));
+            KJ_CUDA(cudaMemsetAsync(d_nflag_, 0, sizeof(int32_t), st));
+            CandSelectParams c2 = cs;
+            c2.out_scores = d_esc_s_; c2.out_ids = d_esc_i_; c2.C = kSgCWide; c2.qmap = d_esc_map_;
+            scan_cand_select_kernel<<<static_cast<unsigned>(ns), 256, 0, st>>>(c2);
+            KJ_CUDA(cudaGetLastError());
+            RescoreParams r2 = r;
+            r2.cand_ids = d_esc_i_; r2.cand_scores = d_esc_s_; r2.Q = static_cast<int>(ns); r2.qmap = d_esc_map_;
+            scan_rescore_kernel<kSgCWide / 32><<<static_cast<unsigned>((ns + 7) / 8), 256, 0, st>>>(r2);
+            KJ_CUDA(cudaGetLastError());
+            launches_ += 2;
+            KJ_CUDA(cudaMemcpyAsync(&nflag, d_nflag_, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            KJ_CUDA(cudaStreamSynchronize(st));
+            if (nflag == 0) continue;
+            KJ_CUDA(cudaMemcpyAsync(h_flags_.data(), d_flags_, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
+            KJ_CUDA(cudaStreamSynchronize(st));
+            std::vector<int> still;
+            for (int i : todo)
+                if (h_flags_[i]) still.push_back(i);
+            todo.swap(still);
+        }
         for (size_t b = 0; b < todo.size(); b += 8) {
             const int nb = static_cast<int>(std::min<size_t>(8, todo.size() - b));
             for (int j = 0; j < nb; ++j)
@@ -390,7 +431,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
 void Index::search_exact(const float* d_q, int nq, int k, int mode, uint64_t* d_ids, float* d_scores, int32_t* d_counts, cudaStream_t st) {
     // queries per warp: bounded by the per-warp list memory (k) and the register file (dim)
     int qt_max = k > 64 ? 1 : (k > 32 ? 2 : 4);
-    if (dim_ > 512) qt_max = std::min(qt_max, 2);
+    if (dim_ > 384) qt_max = std::min(qt_max, 2);  // 4 queries x more than 3 float4 chunks per lane would spill
     const int grid = std::max<int>(1, static_cast<int>(std::min<uint64_t>(num_sms_, (len_ + 31) / 32)));  // one CTA per SM
     const int lists_per_cta = scan_t8_ ? kT8Teams : 1;
     const size_t cand = static_cast<size_t>(grid) * lists_per_cta * nq * k;

@@ -72,6 +72,11 @@ class Index {
     uint64_t *d_am_i_ = nullptr, *d_fix_i_ = nullptr;
     int32_t *d_flags_ = nullptr, *d_nflag_ = nullptr, *d_fix_c_ = nullptr;
     float* d_seed_ = nullptr;
+    int32_t* d_esc_map_ = nullptr;  // escalation of unproven queries: their indices, 128-candidate lists
+    float* d_esc_s_ = nullptr;
+    uint64_t* d_esc_i_ = nullptr;
+    size_t esc_cap_ = 0;
+    bool escalate_ = true;  // KJC_SCAN_NO_ESCALATE: unproven queries go straight to the exact scan (test / measurement hook)
     size_t q16_cap_ = 0, gc_cap_ = 0, am_cap_ = 0, flags_cap_ = 0, seed_cap_ = 0;
     CUtensorMap t_rows16_;
     std::vector<int32_t> h_flags_;

@@ -327,6 +327,7 @@ struct CandSelectParams {
     uint64_t* out_ids;         // [Q, kSgC]  kNoId64 = empty
     int32_t* overflow;         // [Q] 1 = the buffer overflowed (candidates were dropped)
     int C;                     // candidates kept per query: kSgC or kSgCWide
+    const int32_t* qmap;       // nullptr, or [gridDim.x] query indices: block b selects for query qmap[b] and writes list b (escalation)
 };
 __global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams p) {
     __shared__ float sc[kSgCap];
@@ -334,7 +335,8 @@ __global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams 
     __shared__ float ws[8];
     __shared__ uint32_t wi[8];
     __shared__ int wp[8];
-    const int qi = blockIdx.x, tid = threadIdx.x;
+    const int qi = p.qmap ? p.qmap[blockIdx.x] : static_cast<int>(blockIdx.x), tid = threadIdx.x;
+    const int slot = blockIdx.x;  // output list
     const uint32_t cnt = p.cand_cnt[qi];
     const int n = static_cast<int>(min(cnt, static_cast<uint32_t>(kSgCap)));
     for (int j = tid; j < n; j += 256) {
@@ -367,8 +369,8 @@ __global__ void __launch_bounds__(256) scan_cand_select_kernel(CandSelectParams 
             int fp = -1;
             for (int w = 0; w < 8; ++w)
                 if (wp[w] >= 0 && (fp < 0 || ws[w] > fs || (ws[w] == fs && wi[w] < fi))) { fs = ws[w]; fi = wi[w]; fp = wp[w]; }
-            p.out_scores[static_cast<size_t>(qi) * p.C + round] = fp >= 0 ? fs : -INFINITY;
-            p.out_ids[static_cast<size_t>(qi) * p.C + round] = fp >= 0 ? p.id_base + fi : kNoId64;
+            p.out_scores[static_cast<size_t>(slot) * p.C + round] = fp >= 0 ? fs : -INFINITY;
+            p.out_ids[static_cast<size_t>(slot) * p.C + round] = fp >= 0 ? p.id_base + fi : kNoId64;
             if (fp >= 0) id[fp] = kNoId32;  // taken
         }
         __syncthreads();
@@ -462,6 +464,7 @@ struct RescoreParams {
     int32_t* n_flagged;        // running count of flagged queries
     float eps;                 // bound on |approx cosine - exact cosine|
     int D, Q, k, mode;
+    const int32_t* qmap;       // nullptr, or [Q] query indices: candidate list s belongs to query qmap[s] (escalation of unproven queries)
 };
 
 // One warp per query: exact fp32 cosine of the C candidates with EXACTLY the arithmetic of the exact scan (scan_t8_kernel, scan.cuh:
@@ -472,8 +475,9 @@ struct RescoreParams {
 template <int CPL>
 __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
     constexpr int C = 32 * CPL;
-    const int qi = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (qi >= p.Q) return;
+    const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);  // candidate list
+    if (slot >= p.Q) return;
+    const int qi = p.qmap ? p.qmap[slot] : slot;            // query
     const int lane = threadIdx.x & 31;
     const float qn = p.qnorms[qi];
     uint64_t my_gid[CPL];
@@ -482,8 +486,8 @@ __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
     const float* q = p.queries + static_cast<size_t>(qi) * p.D;
 #pragma unroll
     for (int u = 0; u < CPL; ++u) {
-        my_gid[u] = p.cand_ids[static_cast<size_t>(qi) * C + u * 32 + lane];
-        my_approx[u] = p.cand_scores[static_cast<size_t>(qi) * C + u * 32 + lane];
+        my_gid[u] = p.cand_ids[static_cast<size_t>(slot) * C + u * 32 + lane];
+        my_approx[u] = p.cand_scores[static_cast<size_t>(slot) * C + u * 32 + lane];
         my_s[u] = -INFINITY;
         ncand += __popc(__ballot_sync(0xffffffffu, my_gid[u] != kNoId64));  // candidates are packed at the front (sorted lists)
         if (my_gid[u] != kNoId64) {
@@ -552,8 +556,11 @@ __global__ void __launch_bounds__(256) scan_rescore_kernel(RescoreParams p) {
     // proof: rows outside the list have approximate cosine <= m_C (the smallest kept one) => exact <= m_C + eps
     const float m_last = __shfl_sync(0xffffffffu, my_approx[CPL - 1], 31);  // lists are sorted descending: last = smallest
     if (lane == 0 && !empty_query) {
-        // fewer than C candidates proves the result only if nothing was filtered out (unseeded: every row is a candidate)
-        bool proven = ncand < C && p.thr0[qi] == -INFINITY;
+        // fewer than C candidates: the list holds EVERY row whose approximate score beat the seed bound thr0, so the rows outside
+        // it have approximate cosine <= thr0 / |q| (thr0 = -inf, unseeded: there are no rows outside)
+        const float thr0 = p.thr0[qi];
+        bool proven = false;
+        if (ncand < C) proven = thr0 == -INFINITY || (have_kth && qn >= 1e-9f && kth > thr0 / qn + p.eps);
         if (ncand == C && have_kth && qn >= 1e-9f) proven = kth > m_last / qn + p.eps;
         if (p.overflow[qi]) proven = false;
         p.flags[qi] = proven ? 0 : 1;

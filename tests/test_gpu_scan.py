@@ -225,3 +225,30 @@ def test_gemm_filter_async_device_api_large_batch():
         better = np.nonzero(s > sc[qi, -1] + 1e-6)[0] + 500_000
         assert set(better.tolist()) <= set(ids[qi].tolist())
     sh.close()
+
+
+def test_unproven_queries_escalate_before_the_exact_scan(monkeypatch):
+    """A query whose 32-candidate proof fails is first re-selected with 128 candidates from the SAME filter buffer (it holds every row
+    above the seed bound) and re-scored; only what is still unproven goes to the exact scan.  With a deliberately wide error bound
+    many proofs fail: the answers must equal the exact scan's bit for bit, with far fewer launches than going straight to it."""
+    n, dim, nq, k = 400_000, 384, 512, 10
+    q = ko.synth_rows(11, 0, nq, dim)
+    res = {}
+    for esc in (True, False):
+        if esc:
+            monkeypatch.delenv("KJC_SCAN_NO_ESCALATE", raising=False)
+        else:
+            monkeypatch.setenv("KJC_SCAN_NO_ESCALATE", "1")
+        sh = api.IndexShard(dim, n)
+        sh.append_synthetic(7, 0, n)
+        sh.set_filter(eps=0.012, min_queries=1)
+        ids, sc, cnt = sh.search_batch(q, k)
+        res[esc] = (ids, sc, cnt, sh.last_launch_count)
+        if esc:
+            sh.set_filter(min_queries=1 << 30)
+            ids_e, sc_e, cnt_e = sh.search_batch(q[:64], k)
+            assert np.array_equal(ids[:64], ids_e) and np.array_equal(sc[:64], sc_e) and np.array_equal(cnt[:64], cnt_e)
+        sh.close()
+    assert np.array_equal(res[True][0], res[False][0]) and np.array_equal(res[True][1], res[False][1])
+    assert res[False][3] > 6 + 3 * 4, res[False][3]        # the wide bound really left several exact passes to do ...
+    assert res[True][3] < res[False][3] // 2, (res[True][3], res[False][3])  # ... and the escalation resolved most of them
