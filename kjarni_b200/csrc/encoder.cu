@@ -738,8 +738,10 @@ Encoder::~Encoder() {
         if (w.done) cudaEventDestroy(w.done);
     }
     if (ev_in_) cudaEventDestroy(ev_in_);
-    for (cudaEvent_t e : ev_chunk_)
-        if (e) cudaEventDestroy(e);
+    for (auto* v : {&ev_in_chunk_, &ev_done_chunk_, &ev_out_chunk_})
+        for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    if (s_in_) cudaStreamDestroy(s_in_);
+    if (s_out_) cudaStreamDestroy(s_out_);
     if (d_f32_) cudaFree(d_f32_);
     if (d_w16_) cudaFree(d_w16_);
     if (d_err_) cudaFree(d_err_);
@@ -1120,9 +1122,11 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
         KJ_CUDA(cudaMallocHost(&h_stage_out_, out_elems * 4));
         out_cap_ = out_elems;
     }
-    // Stage through pinned memory so the copies are true async DMA transfers, in chunks of two micro-batches: the host-side
-    // copy of chunk c+1 into the staging buffer and of chunk c-1 out of it run while the GPU works on chunk c, so only the
-    // first stage-in and the last stage-out are exposed (they were ~6 % of a 4144-sequence call when done up front).
+    // Stage through pinned memory so the copies are true async DMA transfers, in chunks of two micro-batches, and keep the copies
+    // OFF the compute stream: inputs go up on a copy-in stream (chunk c + 1 lands while chunk c computes), results come down on a
+    // copy-out stream, events order the three.  With everything on one stream every chunk paid its H2D + D2H in SM idle time
+    // (14 chunks x ~35 us of a 17 ms call).  The host-side copy of chunk c + 1 into the staging buffer and of chunk c - 1 out of it
+    // overlap the GPU work on chunk c, so only the first stage-in and the last stage-out are exposed.
     uint32_t* hs = h_stage_in_;
     const uint32_t* d_ids = d_in_;
     const float* d_mask = mask ? reinterpret_cast<const float*>(d_in_ + T) : nullptr;
@@ -1130,34 +1134,52 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
     KjcForwardOptions oc = o;  // the padding convention is decided once for the whole call, not per chunk
     oc.mask_convention = resolve_noalloc(B, S, o) ? KJC_MASK_NOALLOC : KJC_MASK_ALLOC;
     const int chunk = std::max(1, 2 * micro_batch(S));
-    if (!ev_chunk_[0]) {
-        KJ_CUDA(cudaEventCreateWithFlags(&ev_chunk_[0], cudaEventDisableTiming));
-        KJ_CUDA(cudaEventCreateWithFlags(&ev_chunk_[1], cudaEventDisableTiming));
+    const int n_chunks = (B + chunk - 1) / chunk;
+    if (!s_in_) {
+        KJ_CUDA(cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking));
+        KJ_CUDA(cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking));
     }
-    int c = 0, prev_b0 = 0, prev_nb = 0;
-    for (int b0 = 0; b0 < B; b0 += chunk, ++c) {
-        const int nb = std::min(chunk, B - b0);
+    while (static_cast<int>(ev_in_chunk_.size()) < n_chunks) {
+        cudaEvent_t e[3];
+        for (cudaEvent_t& x : e) KJ_CUDA(cudaEventCreateWithFlags(&x, cudaEventDisableTiming));
+        ev_in_chunk_.push_back(e[0]);
+        ev_done_chunk_.push_back(e[1]);
+        ev_out_chunk_.push_back(e[2]);
+    }
+    // the previous call on this handle has fully drained (it ended with a synchronise), so the staging buffers are free
+    auto stage_in = [&](int c) {
+        const int b0 = c * chunk, nb = std::min(chunk, B - b0);
         const size_t t0 = static_cast<size_t>(b0) * S, tn = static_cast<size_t>(nb) * S;
         memcpy(hs + t0, ids + t0, tn * 4);
-        KJ_CUDA(cudaMemcpyAsync(d_in_ + t0, hs + t0, tn * 4, cudaMemcpyHostToDevice, stream_));
+        KJ_CUDA(cudaMemcpyAsync(d_in_ + t0, hs + t0, tn * 4, cudaMemcpyHostToDevice, s_in_));
         if (mask) {
             memcpy(hs + T + t0, mask + t0, tn * 4);
-            KJ_CUDA(cudaMemcpyAsync(d_in_ + T + t0, hs + T + t0, tn * 4, cudaMemcpyHostToDevice, stream_));
+            KJ_CUDA(cudaMemcpyAsync(d_in_ + T + t0, hs + T + t0, tn * 4, cudaMemcpyHostToDevice, s_in_));
         }
         if (types) {
             memcpy(hs + 2 * T + t0, types + t0, tn * 4);
-            KJ_CUDA(cudaMemcpyAsync(d_in_ + 2 * T + t0, hs + 2 * T + t0, tn * 4, cudaMemcpyHostToDevice, stream_));
+            KJ_CUDA(cudaMemcpyAsync(d_in_ + 2 * T + t0, hs + 2 * T + t0, tn * 4, cudaMemcpyHostToDevice, s_in_));
         }
+        KJ_CUDA(cudaEventRecord(ev_in_chunk_[c], s_in_));
+    };
+    auto hand_over = [&](int c) {  // chunk c's rows sit in the pinned output buffer
+        const int b0 = c * chunk, nb = std::min(chunk, B - b0);
+        KJ_CUDA(cudaEventSynchronize(ev_out_chunk_[c]));
+        if (sink) (*sink)(h_stage_out_ + b0 * row, static_cast<size_t>(b0), static_cast<size_t>(nb));
+        else memcpy(out + b0 * row, h_stage_out_ + b0 * row, nb * row * 4);
+    };
+    stage_in(0);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = c * chunk, nb = std::min(chunk, B - b0);
+        const size_t t0 = static_cast<size_t>(b0) * S;
+        if (c + 1 < n_chunks) stage_in(c + 1);  // one chunk ahead of the compute stream
+        KJ_CUDA(cudaStreamWaitEvent(stream_, ev_in_chunk_[c], 0));
         forward_batches(d_ids + t0, d_mask ? d_mask + t0 : nullptr, d_types ? d_types + t0 : nullptr, nb, S, oc, d_out_ + b0 * row, stream_);
-        KJ_CUDA(cudaMemcpyAsync(h_stage_out_ + b0 * row, d_out_ + b0 * row, nb * row * 4, cudaMemcpyDeviceToHost, stream_));
-        KJ_CUDA(cudaEventRecord(ev_chunk_[c & 1], stream_));
-        if (c > 0) {
-            KJ_CUDA(cudaEventSynchronize(ev_chunk_[(c - 1) & 1]));
-            if (sink) (*sink)(h_stage_out_ + prev_b0 * row, static_cast<size_t>(prev_b0), static_cast<size_t>(prev_nb));
-            else memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);
-        }
-        prev_b0 = b0;
-        prev_nb = nb;
+        KJ_CUDA(cudaEventRecord(ev_done_chunk_[c], stream_));
+        KJ_CUDA(cudaStreamWaitEvent(s_out_, ev_done_chunk_[c], 0));
+        KJ_CUDA(cudaMemcpyAsync(h_stage_out_ + b0 * row, d_out_ + b0 * row, nb * row * 4, cudaMemcpyDeviceToHost, s_out_));
+        KJ_CUDA(cudaEventRecord(ev_out_chunk_[c], s_out_));
+        if (c > 0) hand_over(c - 1);
     }
     int err = 0;
     KJ_CUDA(cudaMemcpyAsync(&err_host_, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
@@ -1165,11 +1187,10 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
     err = err_host_;
     if (err) {
         KJ_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), stream_));
+        KJ_CUDA(cudaStreamSynchronize(s_out_));
         throw Error(KJC_INFERENCE_FAILED, "Token type ID out of range");
     }
-    // the last chunk (earlier ones were handed over in the loop)
-    if (sink) (*sink)(h_stage_out_ + prev_b0 * row, static_cast<size_t>(prev_b0), static_cast<size_t>(prev_nb));
-    else memcpy(out + prev_b0 * row, h_stage_out_ + prev_b0 * row, prev_nb * row * 4);
+    hand_over(n_chunks - 1);  // the last chunk (earlier ones were handed over in the loop)
 }
 
 // Head stage alone on caller-supplied fp32 hidden states (debug hook: the argmax stage must be

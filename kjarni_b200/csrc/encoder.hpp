@@ -196,7 +196,9 @@ class Encoder {
     size_t in_cap_ = 0, out_cap_ = 0;
     int* d_err_ = nullptr;
     int err_host_ = 0;
-    cudaEvent_t ev_chunk_[2] = {nullptr, nullptr};  // forward_host: per-chunk completion (stage-out of chunk c-1 overlaps chunk c)
+    // forward_host: copy-in / copy-out streams and per-chunk events (inputs landed, compute done, results in pinned memory)
+    cudaStream_t s_in_ = nullptr, s_out_ = nullptr;
+    std::vector<cudaEvent_t> ev_in_chunk_, ev_done_chunk_, ev_out_chunk_;
     int64_t launches_ = 0;
     // profiling
     struct ProfRec { int cls; cudaEvent_t a, b; };
