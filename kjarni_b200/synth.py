@@ -28,7 +28,8 @@ ARCHS = {
     "tiny-roberta": ("roberta", 64, 2, 4, 256, 1000, 66, 1, 3),
     "tiny-mpnet": ("mpnet", 64, 2, 4, 256, 1000, 66, 0, 0),
     # tiny shapes for CPU-speed tests
-    "tiny-bert": ("bert", 64, 2, 4, 256, 1000, 64, 2, 0),
+    "tiny-bert": ("bert", 64, 2, 4, 256, 1000, 64, 2, 0),      # head_dim 16: the mma.sync attention kernel (the tcgen05 kernels need 32 / 64)
+    "tiny-bert32": ("bert", 128, 2, 4, 512, 1000, 64, 2, 0),   # head_dim 32: the tcgen05 attention kernel at a tiny size
     "tiny-cross-encoder": ("bert_prefixed", 64, 2, 4, 256, 1000, 64, 2, 1),
     "tiny-distilbert": ("distilbert", 128, 2, 2, 512, 1000, 64, 0, 2),
     # same shape as tiny-cross-encoder with wider-initialised layer weights (ARCH_STD): the token content reaches the CLS row, so

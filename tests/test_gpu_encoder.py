@@ -21,7 +21,7 @@ COS_MIN, MAXABS = 0.9995, 2e-2
 def dirs(tmp_path_factory):
     root = tmp_path_factory.mktemp("models")
     return {a: synth.write_model_dir(str(root / a), a) for a in
-            ("tiny-bert", "tiny-cross-encoder", "tiny-reranker", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2",
+            ("tiny-bert", "tiny-bert32", "tiny-cross-encoder", "tiny-reranker", "tiny-distilbert", "minilm-l6", "minilm-l6-cross-encoder", "distilbert-sst2",
              "tiny-roberta", "tiny-mpnet", "distilroberta-emotion", "mpnet-base")}
 
 
@@ -29,7 +29,7 @@ def centred_cos(a, b):
     return cosine_rows(a - a.mean(0, keepdims=True), b - b.mean(0, keepdims=True))
 
 
-@pytest.mark.parametrize("arch,B,S", [("tiny-bert", 6, 16), ("tiny-bert", 70, 24), ("minilm-l6", 4, 32), ("minilm-l6", 32, 128),
+@pytest.mark.parametrize("arch,B,S", [("tiny-bert", 6, 16), ("tiny-bert", 70, 24), ("tiny-bert32", 9, 16), ("tiny-bert32", 33, 40), ("minilm-l6", 4, 32), ("minilm-l6", 32, 128),
                                       ("tiny-mpnet", 6, 16), ("tiny-mpnet", 5, 64), ("mpnet-base", 8, 128)])
 def test_embedding_matches_oracle(dirs, arch, B, S):
     vocab = synth.ARCHS[arch][5]
