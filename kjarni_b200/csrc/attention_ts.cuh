@@ -28,6 +28,29 @@
 
 namespace kj {
 
+// 2^x for x <= 0 on the FMA pipe, two values per call (packed fp32x2): x = n + f with n = round(x) taken from the mantissa of
+// x + 1.5 * 2^23, 2^f by a cubic on [-0.5, 0.5] (max relative error 1.9e-4, a tenth of the bf16 rounding of P), 2^n added to the
+// exponent field.  x is clamped at -125 (2^-125 is 0 for every purpose here).  Pairs of every 8 that use it: KJ_ATTN_POLY_PAIRS.
+#ifndef KJ_ATTN_POLY_PAIRS
+#define KJ_ATTN_POLY_PAIRS 0
+#endif
+constexpr int kPolyPairs = KJ_ATTN_POLY_PAIRS;
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& r0, float& r1) {
+    const uint64_t X = f2_pack(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+    const uint64_t T = f2_add(X, f2_pack(12582912.0f, 12582912.0f));
+    const uint64_t Nf = f2_add(T, f2_pack(-12582912.0f, -12582912.0f));
+    const uint64_t F = f2_fma(Nf, f2_pack(-1.0f, -1.0f), X);
+    uint64_t P = f2_fma(F, f2_pack(0.0558755f, 0.0558755f), f2_pack(0.24229444f, 0.24229444f));
+    P = f2_fma(P, F, f2_pack(0.69312727f, 0.69312727f));
+    P = f2_fma(P, F, f2_pack(0.99994824f, 0.99994824f));
+    float p0, p1, t0, t1;
+    f2_unpack(P, p0, p1);
+    f2_unpack(T, t0, t1);
+    r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+
 #ifndef KJ_ATS_MAX_STAGES
 #define KJ_ATS_MAX_STAGES 6
 #endif
@@ -368,8 +391,14 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                     if ((cfull >> c) & 1) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            const float f0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mx));
-                            const float f1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mx));
+                            float f0, f1;
+                            if (kPolyPairs > 0 && (i & 7) < kPolyPairs) {
+                                // these pairs take their 2^x from the FMA pipe (MUFU.EX2 is the busiest pipe of this pass, 4 lanes/clk/SMSP)
+                                exp2_poly2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mx), fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mx), f0, f1);
+                            } else {
+                                f0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mx));
+                                f1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mx));
+                            }
                             sum += f0 + f1;
                             pk[i] = pack_bf16(f0, f1);
                         }
