@@ -181,15 +181,17 @@ void launch_gemm_ln(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensor
     }
 }
 
+unsigned long long* g_lg_trace = nullptr;  // KJ_LG_TRACE builds: stamp buffer of the next chained launch (dbg_gemm_ln_gemm)
 // GEMM + residual + LayerNorm chained with the next projection of the same 128-row tiles (gemm_ln_gemm.cuh); one tile per CTA.
 // pair: two CTAs per cluster share every weight tile (tcgen05.mma.cta_group::2); tw / tw2 must then have 96-row boxes.
 void launch_gemm_ln_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_res, const CUtensorMap& t_x, const CUtensorMap& tw2,
                          const CUtensorMap& t_out2, int M, int K1, const float* bias1, const float* gamma, const float* beta, float eps, int N2,
-                         const float* bias2, int epi2, int act, cudaStream_t st, bool pair = false) {
+                         const float* bias2, int epi2, int act, cudaStream_t st, bool pair = false, bool ts = false, int dbg = 0) {
     static int configured_act[64] = {0}, configured_plain[64] = {0}, configured_act2[64] = {0}, configured_plain2[64] = {0};  // per instantiation
+    static int configured_act_ts[64] = {0}, configured_plain_ts[64] = {0};
     if (K1 % 8 != 0 || N2 % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs K % 8 == 0 and N % 8 == 0");
     GemmLnGemmParams p;
-    p.M = M; p.K1 = K1; p.bias1 = bias1; p.gamma = gamma; p.beta = beta; p.eps = eps; p.N2 = N2; p.bias2 = bias2; p.act = act;
+    p.M = M; p.K1 = K1; p.bias1 = bias1; p.gamma = gamma; p.beta = beta; p.eps = eps; p.N2 = N2; p.bias2 = bias2; p.act = act; p.dbg = dbg; p.trace = g_lg_trace;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
     if (pair) {
         const int ctas = 2 * ((m_tiles + 1) / 2);  // whole clusters; a tile beyond M is all padding (loads zero-filled, stores clipped)
@@ -201,6 +203,18 @@ void launch_gemm_ln_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
             auto kern = gemm_ln_gemm_kernel<EPI_BIAS_BF16, 0, true>;
             ensure_smem_attr(kern, kLg2SmemBytes, configured_plain2);
             launch_pdl_cluster(2, kern, dim3(ctas), dim3(kLnThreads), kLg2SmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
+        }
+        return;
+    }
+    if (ts) {  // x' as the phase-2 A operand in tensor memory; tw2 must have 128-row boxes
+        if (epi2 == EPI_BIAS_ACT_BF16) {
+            auto kern = gemm_ln_gemm_kernel<EPI_BIAS_ACT_BF16, 0, false, true>;
+            ensure_smem_attr(kern, kLgTSmemBytes, configured_act_ts);
+            launch_pdl(kern, dim3(m_tiles), dim3(kLnThreads), kLgTSmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
+        } else {
+            auto kern = gemm_ln_gemm_kernel<EPI_BIAS_BF16, 0, false, true>;
+            ensure_smem_attr(kern, kLgTSmemBytes, configured_plain_ts);
+            launch_pdl(kern, dim3(m_tiles), dim3(kLnThreads), kLgTSmemBytes, st, ta, tw, t_res, t_x, tw2, t_out2, p);
         }
         return;
     }
@@ -689,6 +703,8 @@ Encoder::Encoder(const std::string& dir, int device) {
         }
         ld.t_w1_192 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, kLg2BN, kGemmBlockK, 128);      // chained kernels: 192-row boxes
         ld.t_wqkv_192 = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, kLg2BN, kGemmBlockK, 128);
+        ld.t_w1_128 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, kLgTBN, kGemmBlockK, 128);      // x' in tensor memory: 128-row boxes
+        ld.t_wqkv_128 = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, kLgTBN, kGemmBlockK, 128);
         if (H == kFfH && I % kFfChunk == 0) {
             ld.t_w1_ffn = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 64, kGemmBlockK, 128);
             ld.t_w1_ffn32 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 32, kGemmBlockK, 128);
@@ -717,6 +733,10 @@ Encoder::Encoder(const std::string& dir, int device) {
     chain_embed_ = chain_ && getenv("KJC_CHAIN_EMBED") != nullptr;
     // two CTAs per cluster share the weight tiles of the chained kernels (cta_group::2): needs an even number of CTAs resident
     chain_pair_ = chain_ && num_sms_ % 2 == 0 && getenv("KJC_CHAIN_PAIR") != nullptr;
+    {
+        const char* e = getenv("KJC_CHAIN_TS");  // phase 2 reads x' from tensor memory (gemm_ln_gemm.cuh, kTS)
+        chain_ts_ = chain_ && !chain_pair_ && (e == nullptr ? KJ_CHAIN_TS_DEFAULT != 0 : atoi(e) != 0);
+    }
     if (const char* e = getenv("KJC_FP32_RESIDUAL")) set_fp32_residual(atoi(e));
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
@@ -790,6 +810,8 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
                                    : make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
     w.t_qkv16_out32 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);  // CTA-pair kernel
     w.t_h16_out32 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
+    w.t_qkv16_out64 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128);  // chained kernels: one 32 x 64 store per warp and tile
+    w.t_h16_out64 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128);
     w.t_h16_out = (gemm_wide_store(bn_i_) || (bn_i_ == 192 && pair_gemm_)) ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
                                : make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
     w.t_x16_io = make_tmap_2d(w.x16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, 32, kEpiChunkCols, 64);
@@ -828,7 +850,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         if (chain_embed) {
             // embeddings + embed LN -> layer 0's Q|K|V in one launch   (embeddings/mod.rs:181-326, qkv_projection.rs:93-138)
             prof_begin(KJC_K_GEMM_QKV, st);
-            launch_embed_ln_gemm(e, emb_g_, emb_b_, w.t_x16, layers_[0].t_wqkv_192, w.t_qkv16_out32, 3 * H, layers_[0].bqkv, st);
+            launch_embed_ln_gemm(e, emb_g_, emb_b_, w.t_x16, layers_[0].t_wqkv_192, w.t_qkv16_out64, 3 * H, layers_[0].bqkv, st);
             prof_end(st);
         } else {
             prof_begin(KJC_K_EMBED_LN, st);
@@ -862,15 +884,16 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         if (chain) {
             // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
             prof_begin(KJC_K_GEMM_FFN_UP, st);
-            launch_gemm_ln_gemm(w.t_ctx16, chain_pair_ ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, chain_pair_ ? L.t_w1_96 : L.t_w1_192, w.t_h16_out32, M, H,
-                                L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, chain_pair_);
+            launch_gemm_ln_gemm(w.t_ctx16, chain_pair_ ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, chain_pair_ ? L.t_w1_96 : (chain_ts_ ? L.t_w1_128 : L.t_w1_192),
+                                chain_ts_ ? w.t_h16_out32 : w.t_h16_out64, M, H, L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, chain_pair_, chain_ts_);
             prof_end(st);
             // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
             if (li + 1 < layers_.size()) {
                 const LayerDev& Ln = layers_[li + 1];
-                launch_gemm_ln_gemm(w.t_h16, chain_pair_ ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16, chain_pair_ ? Ln.t_wqkv_96 : Ln.t_wqkv_192, w.t_qkv16_out32,
-                                    M, I, L.b2, L.g2, L.be2, eps, 3 * H, Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, chain_pair_);
+                launch_gemm_ln_gemm(w.t_h16, chain_pair_ ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
+                                    chain_pair_ ? Ln.t_wqkv_96 : (chain_ts_ ? Ln.t_wqkv_128 : Ln.t_wqkv_192), chain_ts_ ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 3 * H,
+                                    Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, chain_pair_, chain_ts_);
             } else {
                 launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             }
@@ -1325,6 +1348,9 @@ void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const flo
     KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
     if ((M + kGemmBlockM - 1) / kGemmBlockM > prop.multiProcessorCount) throw Error(KJC_INVALID_CONFIG, "chained kernel: one 128-row tile per SM at most");
     const bool pair = (epi2 & 16) != 0;  // epi2 + 16: the CTA-pair variant (cta_group::2, each CTA loads half of every weight tile)
+    const bool ts = (epi2 & 32) != 0;    // epi2 + 32: x' as the phase-2 A operand in tensor memory (128-column phase-2 tiles)
+    if (pair && ts) throw Error(KJC_INVALID_CONFIG, "chained kernel: the CTA-pair and tensor-memory variants exclude each other");
+    const int dbg = (epi2 >> 6) & 7;     // epi2 + 64 / 128 / 256: phase-2 knock-outs (GemmLnGemmParams::dbg 1 / 2 / 4), timing only
     epi2 &= 15;
     if (N2 > kLg2BiasMax) throw Error(KJC_INVALID_CONFIG, "chained kernel: N2 too large");
     const size_t Mp = std::max(M, 128), N2p = std::max(N2, kLg2BN);
@@ -1353,11 +1379,35 @@ void dbg_gemm_ln_gemm(const uint16_t* a_bf16, const uint16_t* w1_bf16, const flo
     CUtensorMap tw = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, kLnN, K1, pair ? kLnHalfN / 2 : kLnHalfN, kGemmBlockK, 128);
     CUtensorMap tres = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, 32, kEpiChunkCols, 64);
     CUtensorMap tx = make_tmap_2d(dX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, kLnN, kGemmBlockM, kGemmBlockK, 128);
-    CUtensorMap tw2 = make_tmap_2d(dW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N2p, kLnN, pair ? kLg2BN / 2 : kLg2BN, kGemmBlockK, 128);
-    CUtensorMap to2 = make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N2, 32, kEpiChunkCols, 64);
-    auto go = [&] { launch_gemm_ln_gemm(ta, tw, tres, tx, tw2, to2, M, K1, dB, dG, dBt, eps, N2, dB2, epi2, act, nullptr, pair); };
+    CUtensorMap tw2 = make_tmap_2d(dW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N2p, kLnN, pair ? kLg2BN / 2 : (ts ? kLgTBN : kLg2BN), kGemmBlockK, 128);
+    CUtensorMap to2 = ts ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N2, 32, kEpiChunkCols, 64)
+                         : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N2, 32, 64, 128);
+    auto go = [&] { launch_gemm_ln_gemm(ta, tw, tres, tx, tw2, to2, M, K1, dB, dG, dBt, eps, N2, dB2, epi2, act, nullptr, pair, ts, dbg); };
     go();
     KJ_CUDA(cudaDeviceSynchronize());
+#if KJ_LG_TRACE
+    if (getenv("KJC_LG_TRACE")) {  // one traced launch after two warm ones: clock64 stamps of CTAs 0 and 100, in clocks since the CTA's entry
+        const int ctas = (M + kGemmBlockM - 1) / kGemmBlockM;
+        unsigned long long* dT;
+        KJ_CUDA(cudaMalloc(&dT, static_cast<size_t>(ctas + 1) * 256 * 8));
+        KJ_CUDA(cudaMemset(dT, 0, static_cast<size_t>(ctas + 1) * 256 * 8));
+        go(); go();
+        g_lg_trace = dT;
+        go();
+        g_lg_trace = nullptr;
+        KJ_CUDA(cudaDeviceSynchronize());
+        std::vector<unsigned long long> h(static_cast<size_t>(ctas) * 256);
+        KJ_CUDA(cudaMemcpy(h.data(), dT, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int cta : {0, std::min(100, ctas - 1)}) {
+            const unsigned long long* t = h.data() + static_cast<size_t>(cta) * 256;
+            fprintf(stderr, "lgtrace K1=%d N2=%d epi2=%d dbg=%d cta %d:", K1, N2, epi2, dbg, cta);
+            for (int i = 1; i < 256; ++i)
+                if (t[i] != 0) fprintf(stderr, " %d=%lld", i, static_cast<long long>(t[i] - t[0]));
+            fprintf(stderr, "\n");
+        }
+        cudaFree(dT);
+    }
+#endif
     KJ_CUDA(cudaMemcpy(out_x_bf16, dX, static_cast<size_t>(M) * kLnN * 2, cudaMemcpyDeviceToHost));
     KJ_CUDA(cudaMemcpy(out2_bf16, dO, static_cast<size_t>(M) * N2 * 2, cudaMemcpyDeviceToHost));
     if (iters > 0 && us) {  // timing (in place: the values drift, the work does not)

@@ -95,6 +95,7 @@ struct LayerDev {
     CUtensorMap t_wo_ln, t_w2_ln;        // 192-row boxes: weights of the GEMM + residual + LayerNorm kernels (hidden 384 / 768)
     CUtensorMap t_wo_96, t_w2_96, t_w1_96, t_wqkv_96;  // 96-row boxes: the CTA-pair chained kernels load half a weight tile per CTA
     CUtensorMap t_w1_192, t_wqkv_192;    // 192-row boxes: phase-2 weights of the chained GEMM+LN -> GEMM kernel
+    CUtensorMap t_w1_128, t_wqkv_128;    // 128-row boxes: the same with x' in tensor memory (kTS)
     CUtensorMap t_wqkv_half, t_w1_half;  // box of block_n/2 rows: the CTA-pair GEMM loads half a weight tile per CTA
 };
 
@@ -156,6 +157,7 @@ class Encoder {
         CUtensorMap t_x16, t_ctx16, t_h16;   // A-operand loads
         CUtensorMap t_qkv16_out, t_h16_out;  // epilogue TMA stores
         CUtensorMap t_qkv16_out32, t_h16_out32;  // 32-column store boxes (CTA-pair kernel)
+        CUtensorMap t_qkv16_out64, t_h16_out64;  // 64-column store boxes (chained kernels)
         CUtensorMap t_x16_io;                // residual load + LayerNorm output store of the fused kernel
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -184,6 +186,7 @@ class Encoder {
     int fp32_residual_ = 1;
     int cfg_max_seq_len_ = 0;
     bool chain_pair_ = false;
+    bool chain_ts_ = false;
     bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false, chain_embed_ = false;
     int lanes_ = 2;
     std::vector<Workspace> ws_;

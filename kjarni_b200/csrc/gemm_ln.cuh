@@ -177,7 +177,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (KJ_MMA_UNIFORM != 0 || lane == 0) {
             constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, kLnHalfN);
             int stage = 0;
             uint32_t phase = 0;
@@ -191,13 +191,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * kLnABytes));
                     const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes));
                     const uint64_t db1 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes + kLnHalfN * 128));
+                    if (mma_issuer_lane()) {
 #pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                        umma_f16(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
-                        umma_f16(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                            umma_f16(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                            umma_f16(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == k_blocks - 1) umma_commit(tmem_full);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == k_blocks - 1) umma_commit(tmem_full);
+                    mma_issuer_sync();
                     if (++stage == kLnStages) {
                         stage = 0;
                         phase ^= 1;

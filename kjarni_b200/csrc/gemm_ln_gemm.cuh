@@ -26,6 +26,15 @@
 // one CTA (its 128 TMEM lanes), so LayerNorm, the x' tile and both epilogues are unchanged; only the leader CTA issues MMAs, the
 // leader's barriers count both CTAs' TMA bytes, commits are multicast to both CTAs and the peer's epilogue warps release
 // accumulators / publish x' on the leader's barriers.
+//
+// kTS = true (default since round 2): phase 2 reads x' from TENSOR MEMORY instead of shared memory.  An SS-mode 128 x 192 x 16 MMA reads
+// 4 KB of A and 6 KB of B from shared memory every 96 clk while TMA writes the next 6 KB of W2 and the epilogue stages 4 KB per
+// MMA: 20 KB against the 128 B/clk the SM's shared memory delivers, i.e. >= 160 clk per MMA (measured 190-250).  The LayerNorm
+// epilogue therefore ALSO writes x' as packed bf16 into TMEM (tcgen05.st; columns [0,64) in place for column part 0, [384,512) for
+// parts 1 and 2) and phase 2 issues tcgen05.mma with the A operand in TMEM ("TS" form): the A re-reads (one per 128 output
+// columns) leave shared memory altogether.  TMEM then has room for two 128-column accumulators ([64,192), [192,320)), so phase-2
+// tiles are 128 wide (an M = 128 MMA costs N/2 clk: narrower tiles waste nothing) with five 16 KB W2 stages.  The x' tile in shared
+// memory remains only as the source of the TMA store to global memory.  Same MMA k order per output element: bit-identical.
 #pragma once
 #include <cuda.h>
 
@@ -39,9 +48,38 @@ constexpr int kLg2Stages = 3;
 constexpr int kLg2KB = kLnN / kGemmBlockK;                  // 6 k-blocks of the resident x' tile
 constexpr int kLg2BiasMax = 1536;                           // phase-2 bias columns staged in shared memory
 constexpr int kLg2RingBytes = 3 * kLnStageBytes;            // 192 KB: phase 1 always runs a 3-stage ring here
-constexpr int kLg2SmemBytes = kLg2RingBytes + kLnStatBytes + kLnVecBytes + kLg2BiasMax * 4 + 512;
-static_assert(kLg2SmemBytes <= 232448, "shared memory budget");
+constexpr int kLg2BaseBytes = kLg2RingBytes + kLnStatBytes + kLnVecBytes + kLg2BiasMax * 4 + 512;
+// Phase-2 output staging: every epilogue warp stages its whole 32 x 64 part of a 192-column tile (4 KB, 128-byte rows) and issues ONE
+// TMA store per tile.  With two 32 x 32 chunks through one 2 KB buffer the second chunk waited for the first chunk's store to
+// have read the buffer, and every chunk paid its own proxy fence + store: that chain, not the MMAs or the W2 stream, paced
+// phase 2 (knock-outs, profiles/r02_chain_knockouts.txt).  Warps 0-5 stage in [72K, 96K) (the rest of the LayerNorm staging), warp 6
+// on the LayerNorm statistics / bias1 (dead once x' is published), warps 7-11 in 20 KB behind the barriers.
+constexpr int kLg2WideBytes = 32 * 64 * 2;                  // 4 KB per warp
+constexpr int kLg2SmemBytes = kLg2BaseBytes + 5 * kLg2WideBytes;
+static_assert(kLg2BaseBytes % 1024 == 0 && kLg2SmemBytes <= 232448, "shared memory budget");
+static_assert(kLg2WBytes + 6 * kLg2WideBytes <= kLnBBytes && kLg2WideBytes <= kLnStatBytes + kLnN * 4, "wide staging aliases");
 static_assert(2 * kLg2WBytes <= 3 * kLnABytes && kLg2WBytes + kLnEpiWarps * kEpiStageBytes <= kLnBBytes, "phase-2 aliasing");
+// kTS (phase 2 takes its A operand from TENSOR MEMORY): tiles of 128 columns, five 16 KB W2 stages
+#ifndef KJ_CHAIN_TS_DEFAULT
+#define KJ_CHAIN_TS_DEFAULT 0
+#endif
+constexpr int kLgTBN = 128;
+constexpr int kLgTWBytes = kLgTBN * kGemmBlockK * 2;        // 16 KB per W2 stage
+constexpr int kLgTStages = 5;                               // stages 0-2: phase-1 A ring, 3: own region behind the tail, 4: LayerNorm staging
+constexpr int kLgTSmemBytes = kLg2BaseBytes + kLgTWBytes;
+static_assert(kLgTSmemBytes <= 232448, "kTS shared memory budget");
+static_assert(3 * kLgTWBytes <= 3 * kLnABytes && kLgTWBytes + kLnEpiWarps * kEpiStageBytes <= kLnBBytes, "kTS phase-2 aliasing");
+constexpr int kLgTAcc0 = 64;                                // TMEM: x' in [0,64) | [384,512), accumulators [64,192) and [192,320)
+__host__ __device__ constexpr int lg_phase2_bn(bool ts) { return ts ? kLgTBN : kLg2BN; }
+__host__ __device__ constexpr int lg_smem_bytes(bool ts) { return ts ? kLgTSmemBytes : kLg2SmemBytes; }
+
+// kTS: first TMEM column of the packed bf16 x' of column part `part` (128 columns of x' = 64 TMEM columns)
+__host__ __device__ constexpr uint32_t lg_x_tmem_col(int part) { return part == 0 ? 0u : 384u + 64u * static_cast<uint32_t>(part - 1); }
+
+#ifndef KJ_LG_TRACE
+#define KJ_LG_TRACE 0
+#endif
+#define KJ_LGT(slot) do { if (KJ_LG_TRACE && p.trace != nullptr) p.trace[blockIdx.x * 256 + (slot)] = clock64(); } while (0)
 
 struct GemmLnGemmParams {
     int M, K1;
@@ -52,6 +90,9 @@ struct GemmLnGemmParams {
     int N2;              // phase-2 output columns (multiple of 8; tiles of 192, the last one may be partial)
     const float* bias2;  // [N2] or nullptr
     int act;             // Activation (EPI_BIAS_ACT_BF16)
+    unsigned long long* trace;  // KJ_LG_TRACE builds: [gridDim.x][256] clock64 stamps (scripts/chain_micro.py TRACE=1)
+    int dbg;             // phase-2 knock-outs of the micro benchmark (kjc_dbg_gemm_ln_gemm): 1 = no W2 loads (barrier arrives only),
+                         // 2 = no phase-2 epilogue work (accumulator read + release only), 4 = no phase-2 MMAs
     // P1 == 1 (embedding front end): phase 1 = Embeddings::forward + embed LayerNorm instead of a GEMM (rowwise.cuh EmbedParams)
     const uint32_t* ids;       // [M]
     const uint32_t* type_ids;  // [M] or nullptr (row 0 of the type table for every token)
@@ -66,13 +107,17 @@ struct GemmLnGemmParams {
 // P1 = 1: phase 1 is the embedding front end -- word[id] (+ pos[offset + s]) (+ type[tt]) -> embed LayerNorm (reference:
 //         cpu/embeddings/mod.rs:181-326, transformer_encoder.rs:303-305), gathered by the epilogue warps (thread = token, 128
 //         columns each) straight into TMEM for the same two-pass LayerNorm; phase 2 is then layer 0's QKV projection.
-template <int EPI2, int P1 = 0, bool kPair = false>
+template <int EPI2, int P1 = 0, bool kPair = false, bool kTS = false>
 __global__ void __launch_bounds__(kLnThreads, 1)
 gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_x,
                     const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_out2, GemmLnGemmParams p) {
     static_assert(EPI2 == EPI_BIAS_BF16 || EPI2 == EPI_BIAS_ACT_BF16, "phase 2 stores bf16");
     static_assert(!(kPair && P1 == 1), "the embedding front end runs one CTA per tile");
+    static_assert(!(kTS && (kPair || P1 == 1)), "x' in tensor memory: one CTA per tile, GEMM front end");
+    constexpr int kBN2 = kTS ? kLgTBN : kLg2BN;             // phase-2 tile width
+    constexpr int kStages2 = kTS ? kLgTStages : kLg2Stages;
+    constexpr uint32_t kW2Bytes = kTS ? kLgTWBytes : kLg2WBytes;
     extern __shared__ __align__(1024) uint8_t smem_lg[];
     uint8_t* smem = smem_lg;
     if (smem_u32(smem) & 1023) __trap();
@@ -82,8 +127,11 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* smem_epi1 = smem_b;                    // LN residual staging (12 x 4 KB), aliased on W stage 0
     // phase 2 views
     uint8_t* smem_x = smem_b + kLnBBytes;           // x' tile: 6 x 16 KB
-    auto w2_stage = [&](int s) -> uint8_t* { return s < 2 ? smem + s * kLg2WBytes : smem_b; };
-    uint8_t* smem_epi2 = smem_b + kLg2WBytes;       // 12 x 2 KB
+    auto w2_stage = [&](int s) -> uint8_t* {
+        if constexpr (kTS) return s < 3 ? smem + s * kLgTWBytes : (s == 3 ? smem + kLg2BaseBytes : smem_b);
+        else return s < 2 ? smem + s * kLg2WBytes : smem_b;
+    };
+    uint8_t* smem_epi2 = smem_b + kW2Bytes;         // 12 x 2 KB
     uint8_t* tail = smem + kLg2RingBytes;
     float2* stat = reinterpret_cast<float2*>(tail);  // [3][128]
     float* s_bias = reinterpret_cast<float*>(tail + kLnStatBytes);
@@ -96,8 +144,8 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* tmem_full1 = bars + 6;      // phase-1 accumulator complete (all phase-1 MMAs retired)
     uint64_t* res_bar = bars + 7;         // [12 warps][2 buffers]
     uint64_t* x_ready = bars + 31;        // x' tile written, LN accumulator consumed, staging region free (12 arrivals)
-    uint64_t* full2 = bars + 32;          // [3]
-    uint64_t* empty2 = bars + 35;         // [3]
+    uint64_t* full2 = kTS ? bars + 44 : bars + 32;   // [3] (kTS: [5])
+    uint64_t* empty2 = kTS ? bars + 49 : bars + 35;  // [3] (kTS: [5])
     uint64_t* acc_full = bars + 38;       // [2]
     uint64_t* acc_empty = bars + 40;      // [2] (12 arrivals each; kPair: the leader's, 24 arrivals = both CTAs' epilogue warps)
     uint64_t* x_pair = bars + 42;         // kPair, leader's: both CTAs' x' tiles are written (24 arrivals)
@@ -112,7 +160,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x;  // one 128-row tile per CTA
     const int k_blocks1 = (p.K1 + kGemmBlockK - 1) / kGemmBlockK;
-    const int n2_tiles = (p.N2 + kLg2BN - 1) / kLg2BN;
+    const int n2_tiles = (p.N2 + kBN2 - 1) / kBN2;
     const bool bias2_in_smem = p.bias2 != nullptr && p.N2 <= kLg2BiasMax;
 
     // weights: independent of the predecessor kernel, staged before griddepcontrol.wait
@@ -135,6 +183,8 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int i = 0; i < 3; ++i) {
             mbar_init(&full1[i], 1);
             mbar_init(&empty1[i], 1);
+        }
+        for (int i = 0; i < kStages2; ++i) {
             mbar_init(&full2[i], 1);
             mbar_init(&empty2[i], 1);
         }
@@ -157,8 +207,10 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
+    if (threadIdx.x == 0) KJ_LGT(0);
     pdl_wait();
     pdl_launch_dependents();
+    if (threadIdx.x == 0) KJ_LGT(1);
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer
@@ -192,16 +244,19 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int it = 0;
             for (int nb = 0; nb < n2_tiles; ++nb) {
                 for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
-                    const int s = it % kLg2Stages;
-                    if (it == 2) mbar_wait(x_ready, 0);
-                    mbar_wait(&empty2[s], ((it / kLg2Stages) & 1) ^ 1);
+                    const int s = it % kStages2;
+                    if (it == kStages2 - 1) mbar_wait(x_ready, 0);  // the last stage aliases the LayerNorm staging
+                    mbar_wait(&empty2[s], ((it / kStages2) & 1) ^ 1);
+                    if (it < 48) KJ_LGT(200 + it);
                     if constexpr (kPair) {
                         if (leader) mbar_arrive_expect_tx(&full2[s], 2 * kWBoxBytes);
                         tma_load_2d_2sm(w2_stage(s), &tmap_w2, mapa_shared(smem_u32(&full2[s]), 0), kb * kGemmBlockK,
                                         nb * kLg2BN + static_cast<int>(rank) * kWRows, kEvictLast);
+                    } else if (p.dbg & 1) {
+                        mbar_arrive(&full2[s]);
                     } else {
-                        mbar_arrive_expect_tx(&full2[s], kLg2WBytes);
-                        tma_load_2d(w2_stage(s), &tmap_w2, &full2[s], kb * kGemmBlockK, nb * kLg2BN, kEvictLast);
+                        mbar_arrive_expect_tx(&full2[s], kW2Bytes);
+                        tma_load_2d(w2_stage(s), &tmap_w2, &full2[s], kb * kGemmBlockK, nb * kBN2, kEvictLast);
                     }
                 }
             }
@@ -216,49 +271,69 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if constexpr (kPair) umma_commit_2sm(bar, 3);  // the barrier at this offset in both CTAs
             else umma_commit(bar);
         };
-        if (lane == 0 && leader) {
+        if ((KJ_MMA_UNIFORM != 0 || lane == 0) && leader) {
             constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kPair ? 2 * kGemmBlockM : kGemmBlockM, kLnHalfN);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < (P1 == 0 ? k_blocks1 : 0); ++kb) {
                 mbar_wait(&full1[stage], phase);
+                if (kb == 0 && lane == 0) KJ_LGT(2);
                 tc_fence_after();
                 const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * kLnABytes));
                 const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes));
                 const uint64_t db1 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes + kLnHalfN * 128));
+                if (mma_issuer_lane()) {
 #pragma unroll
-                for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                    mma(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
-                    mma(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                        mma(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0);
+                        mma(tmem_base + kLnHalfN, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    commit(&empty1[stage]);
+                    if (kb == k_blocks1 - 1) commit(tmem_full1);
                 }
-                commit(&empty1[stage]);
-                if (kb == k_blocks1 - 1) commit(tmem_full1);
+                mma_issuer_sync();
                 if (++stage == 3) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
+            if (lane == 0) KJ_LGT(3);
             // phase 2: A = the resident x' tile, W2 streamed; accumulators [0,192) / [192,384) alternate
             if constexpr (kPair) mbar_wait_cluster(x_pair, 0);  // both CTAs' x' tiles (the peer's arrives are remote)
             else mbar_wait(x_ready, 0);
             tc_fence_after();
+            if (lane == 0) KJ_LGT(4);
             int it = 0;
             for (int nb = 0; nb < n2_tiles; ++nb) {
                 const int acc = nb & 1;
                 if constexpr (kPair) mbar_wait_cluster(&acc_empty[acc], ((nb >> 1) & 1) ^ 1);
                 else mbar_wait(&acc_empty[acc], ((nb >> 1) & 1) ^ 1);
+                if (lane == 0 && nb < 12) KJ_LGT(16 + 2 * nb);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * kLg2BN;
+                const uint32_t tmem_d = tmem_base + (kTS ? kLgTAcc0 : 0) + acc * kBN2;
                 for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
-                    const int s = it % kLg2Stages;
-                    mbar_wait(&full2[s], (it / kLg2Stages) & 1);
+                    const int s = it % kStages2;
+                    mbar_wait(&full2[s], (it / kStages2) & 1);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_x + kb * kLnABytes));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(w2_stage(s)));
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_x + kb * kLnABytes));
+                    // kTS: x' columns [64 kb, 64 kb + 64) as packed bf16 = 32 TMEM columns of column part kb / 2
+                    const uint32_t xa = tmem_base + lg_x_tmem_col((kb >> 1)) + (kb & 1) * 32;
+                    if (mma_issuer_lane()) {
+                        if (p.dbg & 4) {
+                        } else if constexpr (kTS) {
+                            constexpr uint32_t idesc_ts = umma_idesc(1 /*bf16*/, kGemmBlockM, kLgTBN);
 #pragma unroll
-                    for (int k = 0; k < kGemmBlockK / 16; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                    commit(&empty2[s]);
-                    if (kb == kLg2KB - 1) commit(&acc_full[acc]);
+                            for (int k = 0; k < kGemmBlockK / 16; ++k) umma_f16_ts(tmem_d, xa + 8 * k, db + 2 * k, idesc_ts, (kb | k) != 0);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kGemmBlockK / 16; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        commit(&empty2[s]);
+                        if (kb == kLg2KB - 1) commit(&acc_full[acc]);
+                    }
+                    mma_issuer_sync();
+                    if (kb == kLg2KB - 1 && lane == 0 && nb < 12) KJ_LGT(17 + 2 * nb);
                 }
             }
         }
@@ -364,6 +439,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float s1 = 0.0f, s2 = 0.0f;
             if constexpr (P1 == 0) {
                 mbar_wait(tmem_full1, 0);
+                if (ew == 0 && lane == 0) KJ_LGT(5);
                 tc_fence_after();
                 if (lane == 0) {
                     for (int c = 0; c < 2; ++c) {
@@ -412,8 +488,10 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             tmem_st_wait();
+            if (ew == 0 && lane == 0) KJ_LGT(6);
             stat[part * 128 + trow] = make_float2(s1, s2);
             named_bar_sync(1, kLnEpiWarps * 32);
+            if (ew == 0 && lane == 0) KJ_LGT(7);
             float t1 = 0.0f, t2 = 0.0f;
 #pragma unroll
             for (int q = 0; q < kLnParts; ++q) {
@@ -446,18 +524,25 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 const uint32_t xrow = smem_u32(smem_x) + (col0 >> 6) * kLnABytes + trow * 128;
                 const uint32_t chunk0 = static_cast<uint32_t>((col0 & 63) >> 3);  // 0 or 4
+                uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    st_shared_v4(xrow + (((chunk0 + j) ^ xsw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) st_shared_v4(xrow + (((chunk0 + j) ^ xsw) << 4), pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                if constexpr (kTS) {
+                    // the phase-2 A operand: row = lane, two bf16 per 32-bit column.  Part 0 compacts in place (columns [16c, 16c + 16)
+                    // lie inside what this warp has already read), parts 1 and 2 go to the 128 columns phase 1 never used.
+                    tmem_st_32x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + lg_x_tmem_col(part) + c * 16, pk);
                 }
             }
+            if constexpr (kTS) tmem_st_wait();
             fence_proxy_async_smem();  // x' (generic-proxy stores) -> visible to the tensor core and to the TMA store below
             tc_fence_before();         // the LayerNorm accumulator is fully read: phase-2 MMAs may overwrite it
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(x_ready);
                 if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(x_pair), 0));  // the leader's MMA warp waits for both tiles
+                if (ew == 0) KJ_LGT(8);
             }
         }
         // x' goes to global memory as well (residual of the next LayerNorm, pooling / hidden-state output): six 16 KB stores
@@ -468,20 +553,23 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             bulk_commit();
         }
         {
-            // ===== phase 2: bias (+ activation) -> bf16 -> 32 x 32 staging chunk -> TMA store, per 192-column tile
+            // ===== phase 2: bias (+ activation) -> bf16 -> 32 x 32 staging chunk -> TMA store, per 192- (kTS: 128-) column tile
             uint8_t* sbuf = smem_epi2 + ew * kEpiStageBytes;
             mbar_wait(x_ready, 0);  // the staging chunk aliases the LayerNorm staging of OTHER warps
             for (int nb = 0; nb < n2_tiles; ++nb) {
                 const int acc = nb & 1;
                 mbar_wait(&acc_full[acc], (nb >> 1) & 1);
+                const bool tr = KJ_LG_TRACE && lane == 0 && nb < 8 && (ew == 0 || ew == 7);
+                const int ts0 = (ew == 0 ? 48 : 128) + 8 * nb;
+                if (tr) KJ_LGT(ts0);
                 tc_fence_after();
-                const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kLg2BN + part * 64;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                const uint32_t tacc = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (kTS ? kLgTAcc0 : 0) + acc * kBN2;
+                // one 32-column chunk at column `cc` of the tile; `last`: this warp's last load from the accumulator
+                auto chunk = [&](int cc, bool last) {
                     uint32_t v[32];
-                    tmem_ld_32x32(taddr0 + c * 32, v);
+                    tmem_ld_32x32(tacc + cc, v);
                     tmem_ld_wait();
-                    if (c == 1) {  // last load landed: release the accumulator before the math and stores of this chunk
+                    if (last) {  // last load landed: release the accumulator before the math and stores of this chunk
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
@@ -489,8 +577,8 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             else mbar_arrive(&acc_empty[acc]);
                         }
                     }
-                    const int col0 = nb * kLg2BN + part * 64 + c * 32;
-                    if (col0 < p.N2) {
+                    const int col0 = nb * kBN2 + cc;
+                    if (col0 < p.N2 && !(p.dbg & 2)) {
                         float f[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -531,6 +619,86 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             bulk_commit();
                         }
                     }
+                };
+                if constexpr (!kTS) {
+                    // wide store: both chunks of this warp's 32 x 64 part into one 128B-swizzled 4 KB tile, one fence, one TMA store
+                    uint8_t* wbuf = ew < 6 ? smem_epi2 + ew * kLg2WideBytes : (ew == 6 ? tail : smem + kLg2BaseBytes + (ew - 7) * kLg2WideBytes);
+                    const uint32_t wbase = smem_u32(wbuf) + lane * 128;
+                    const uint32_t wsw = static_cast<uint32_t>(lane & 7);  // 128B swizzle: 16-byte chunk index ^= row & 7
+                    const int colp = nb * kBN2 + part * 64;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(tacc + part * 64 + c * 32, v);
+                        tmem_ld_wait();
+                        if (tr) KJ_LGT(ts0 + 1 + 3 * c);
+                        if (c == 1) {  // last load landed: release the accumulator before the math and stores of this chunk
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[acc]), 0));
+                                else mbar_arrive(&acc_empty[acc]);
+                            }
+                        }
+                        const int col0 = colp + c * 32;
+                        if (p.dbg & 2) continue;
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                        if (bias2_in_smem && col0 + 32 <= p.N2) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b = *reinterpret_cast<const float4*>(s_bias2 + col0 + 4 * j);
+                                f[4 * j + 0] += b.x;
+                                f[4 * j + 1] += b.y;
+                                f[4 * j + 2] += b.z;
+                                f[4 * j + 3] += b.w;
+                            }
+                        } else if (p.bias2 != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (col0 + 4 * j < p.N2) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + col0) + j);
+                                    f[4 * j + 0] += b.x;
+                                    f[4 * j + 1] += b.y;
+                                    f[4 * j + 2] += b.z;
+                                    f[4 * j + 3] += b.w;
+                                }
+                            }
+                        }
+                        if (EPI2 == EPI_BIAS_ACT_BF16) apply_act_tile(f, p.act);
+                        if (tr) KJ_LGT(ts0 + 2 + 3 * c);
+                        if (c == 0) {
+                            if (lane == 0) bulk_wait_read<0>();  // the previous tile's store (and, for warp 4, the x' stores) has read smem
+                            __syncwarp();
+                            if (tr) KJ_LGT(ts0 + 3);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            st_shared_v4(wbase + ((static_cast<uint32_t>(c * 4 + j) ^ wsw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]),
+                                         pack_bf16(f[8 * j + 2], f[8 * j + 3]), pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        }
+                    }
+                    if (!(p.dbg & 2)) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (tr) KJ_LGT(ts0 + 6);
+                        if (lane == 0 && colp < p.N2) {  // columns >= N2 are clipped by the tensor map
+                            tma_store_2d(&tmap_out2, wbuf, colp, row0);
+                            bulk_commit();
+                        }
+                        if (tr) KJ_LGT(ts0 + 7);
+                    }
+                } else if constexpr (kTS) {
+                    // the tile's four chunks are dealt round robin over the quadrant's three warps, continuing across tiles
+                    // (chunk c of tile nb belongs to part (4 nb + c) % 3): one or two chunks per warp and tile, four per three tiles
+                    const int first = (part + 3 - nb % 3) % 3;
+                    if (first == 0) {
+                        chunk(0, false);
+                        chunk(96, true);
+                    } else {
+                        chunk(first * 32, true);
+                    }
                 }
             }
             if (lane == 0) bulk_wait_read<0>();  // shared memory stays valid until the last store has read it
@@ -540,6 +708,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_before();
     if constexpr (kPair) cluster_sync_all();  // peer shared memory / barriers stay valid until both CTAs are done
     else __syncthreads();
+    if (threadIdx.x == 0) KJ_LGT(255);
     if (warp == 2) {
         tc_fence_after();
         if constexpr (kPair) tmem_dealloc_2sm<512>(tmem_base);

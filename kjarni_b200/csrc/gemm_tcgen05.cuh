@@ -223,7 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (KJ_MMA_UNIFORM != 0 || lane == 0) {
             constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -236,19 +236,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     if (!(p.dbg & 64)) mbar_wait(&full_bar[stage], phase);  // 64: raw MMA issue rate (no operand handshake)
-                    if (it == 0 && kb == 0) KJ_TRACE(3);  // first operands landed
+                    if (it == 0 && kb == 0 && lane == 0) KJ_TRACE(3);  // first operands landed
                     tc_fence_after();
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
                     const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
-                    if (!(p.dbg & 2)) {
+                    if (mma_issuer_lane()) {
+                        if (!(p.dbg & 2)) {
 #pragma unroll
-                        for (int k = 0; k < kGemmBlockK / 16; ++k) {
-                            // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-                            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            for (int k = 0; k < kGemmBlockK / 16; ++k) {
+                                // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
+                                umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            }
                         }
+                        if (!(p.dbg & 64)) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
                     }
-                    if (!(p.dbg & 64)) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                    if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                    mma_issuer_sync();
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;

@@ -31,6 +31,25 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------- mbarrier
+// MMA issue style of the GEMM kernels.  1 (default): the whole issuer warp runs the loop (waits, descriptor arithmetic on uniform
+// values) and ONE elected lane issues each group of tcgen05.mma + commits -- the descriptors stay in uniform registers and there is
+// no per-instruction elect loop; 0: everything under `if (lane == 0)` (round 1).  The issuer warp shares its scheduler with three
+// issue-bound epilogue warps, so its instruction count per MMA is what paces the tensor pipe (profiles/r02_attention_analysis.md).
+#ifndef KJ_MMA_UNIFORM
+#define KJ_MMA_UNIFORM 1
+#endif
+__device__ __forceinline__ bool mma_issuer_lane() {
+#if KJ_MMA_UNIFORM
+    return elect_one();
+#else
+    return true;
+#endif
+}
+__device__ __forceinline__ void mma_issuer_sync() {
+#if KJ_MMA_UNIFORM
+    __syncwarp();
+#endif
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -209,6 +228,28 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows = lanes, 16-bit elements packed two per 32-bit column) is read from
+// tensor memory.  Issued by ONE thread.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are
 // exactly one 128-byte swizzle atom wide (64 bf16 / 32 tf32 per row), rows

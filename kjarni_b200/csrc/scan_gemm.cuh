@@ -178,7 +178,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (KJ_MMA_UNIFORM != 0 || lane == 0) {
             constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kSgQ, kSgRows);
             int stage = 0, it = 0;
             uint32_t phase = 0, ai = 0;
@@ -199,13 +199,16 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             tc_fence_after();
                             const uint64_t da = umma_desc_k_sw128(smem_u32(stream_a ? stage_a(stage) : smem_a + kb * kSgABlockBytes));
                             const uint64_t db = umma_desc_k_sw128(smem_u32(stage_b(stage)));
-                            if (!(p.dbg & 2)) {
+                            if (mma_issuer_lane()) {
+                                if (!(p.dbg & 2)) {
 #pragma unroll
-                                for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                    for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                }
+                                umma_commit(&empty_bar[stage]);
+                                if (last_r && !stream_a) umma_commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
+                                if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
                             }
-                            umma_commit(&empty_bar[stage]);
-                            if (last_r && !stream_a) umma_commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
-                            if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                            mma_issuer_sync();
                             if (++stage == kSgStages) {
                                 stage = 0;
                                 phase ^= 1;

@@ -36,3 +36,13 @@ a, b, c = ln(1536), gemm(1152, 0, 192), chain(1536, 1152, 0)
 print(f"FFN-down+LN {a:.1f} us + QKV {b:.1f} us = {a+b:.1f} us   |  chained {c:.1f} us")
 c1, c2 = chain(384, 1536, 1 + 16), chain(1536, 1152, 0 + 16)
 print(f"CTA-pair chained (cta_group::2, half a weight tile per CTA): out-proj+LN1->FFN-up {c1:.1f} us, FFN-down+LN2->QKV {c2:.1f} us")
+c1, c2 = chain(384, 1536, 1 + 32), chain(1536, 1152, 0 + 32)
+print(f"x' in tensor memory (TS-form phase 2, 128-column tiles): out-proj+LN1->FFN-up {c1:.1f} us, FFN-down+LN2->QKV {c2:.1f} us")
+if os.environ.get("KNOCKOUT") == "1":
+    # phase-2 knock-outs (timing only): 64 = no W2 loads, 128 = no phase-2 epilogue work, 256 = no phase-2 MMAs
+    for name, K1, N2, e in (("out-proj+LN1->FFN-up", 384, 1536, 1), ("FFN-down+LN2->QKV", 1536, 1152, 0)):
+        for var, vname in ((0, "smem x'"), (32, "tmem x'")):
+            row = []
+            for ko, kname in ((0, "full"), (64, "no-W2-loads"), (128, "no-epi2"), (256, "no-mma2"), (64 + 128, "mma2-only"), (128 + 256, "loads-only"), (64 + 256, "epi2-only"), (64 + 128 + 256, "phase-1-only")):
+                row.append(f"{kname} {chain(K1, N2, e + var + ko):.1f}")
+            print(f"{name} [{vname}]: " + " | ".join(row))

@@ -303,6 +303,13 @@ def test_chained_launch_variants_agree(dirs, monkeypatch):
     c = emb.encode_batch_from_ids(ids, mask)
     emb.close()
     assert np.array_equal(a, c)  # the front end restates the embed kernel's arithmetic bit for bit
+    monkeypatch.delenv("KJC_CHAIN_EMBED")
+    for ts in ("0", "1"):  # x' of the chained launches in shared memory / in tensor memory (gemm_ln_gemm.cuh, kTS)
+        monkeypatch.setenv("KJC_CHAIN_TS", ts)
+        m = api.EncoderModel(dirs[arch])
+        d = m.encode_batch_from_ids(ids, mask)
+        m.close()
+        assert np.array_equal(a, d), ts
 
 
 def test_host_call_chunking_is_invisible(dirs):

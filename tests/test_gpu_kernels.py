@@ -249,6 +249,13 @@ def test_chained_gemm_ln_gemm(M, K1, N2, epi2):
                                          M, K1, ptr(to_bf16_bits(w2)), ptr(b2), N2, epi2 + 16, 0, ptr(px), ptr(p2), 0, C.byref(us)))
     assert np.array_equal(px, out_x)
     assert np.array_equal(p2, out2)
+    # x' as the phase-2 A operand in tensor memory (epi2 + 32: TS-form tcgen05.mma, 128-column phase-2 tiles): the same bits again
+    tx = np.empty((M, H), np.uint16)
+    t2 = np.empty((M, N2), np.uint16)
+    N.check(N.lib().kjc_dbg_gemm_ln_gemm(ptr(to_bf16_bits(a)), ptr(to_bf16_bits(w1)), ptr(b1), ptr(gamma), ptr(beta), 1e-12, ptr(to_bf16_bits(res)),
+                                         M, K1, ptr(to_bf16_bits(w2)), ptr(b2), N2, epi2 + 32, 0, ptr(tx), ptr(t2), 0, C.byref(us)))
+    assert np.array_equal(tx, out_x)
+    assert np.array_equal(t2, out2)
     # and the oracle
     y = (bf16_round(a).astype(np.float64) @ bf16_round(w1).astype(np.float64).T + b1 + bf16_round(res)).astype(np.float32)
     want_x = ko.layer_norm(y, gamma, beta, 1e-12)
