@@ -732,10 +732,16 @@ Encoder::Encoder(const std::string& dir, int device) {
     chain_ = fused_ln_ && H == kLnN && !fused_ffn_ && I <= kLg2BiasMax && 3 * H <= kLg2BiasMax && !getenv("KJC_NO_CHAIN");
     chain_embed_ = chain_ && getenv("KJC_CHAIN_EMBED") != nullptr;
     // two CTAs per cluster share the weight tiles of the chained kernels (cta_group::2): needs an even number of CTAs resident
-    chain_pair_ = chain_ && num_sms_ % 2 == 0 && getenv("KJC_CHAIN_PAIR") != nullptr;
+    {
+        // CTA-pair form of the chained launches (tcgen05.mma.cta_group::2, half a weight tile per CTA): bit 0 = FFN-down + LN2 -> QKV,
+        // bit 1 = out-proj + LN1 -> FFN-up
+        const char* e = getenv("KJC_CHAIN_PAIR");
+        chain_pair_mask_ = (chain_ && num_sms_ % 2 == 0) ? (e != nullptr ? atoi(e) : KJ_CHAIN_PAIR_DEFAULT) & 3 : 0;
+        chain_pair_ = chain_pair_mask_ != 0;
+    }
     {
         const char* e = getenv("KJC_CHAIN_TS");  // phase 2 reads x' from tensor memory (gemm_ln_gemm.cuh, kTS)
-        chain_ts_ = chain_ && !chain_pair_ && (e == nullptr ? KJ_CHAIN_TS_DEFAULT != 0 : atoi(e) != 0);
+        chain_ts_ = chain_ && (e == nullptr ? KJ_CHAIN_TS_DEFAULT != 0 : atoi(e) != 0);
     }
     if (const char* e = getenv("KJC_FP32_RESIDUAL")) set_fp32_residual(atoi(e));
     const char* env = getenv("KJC_MICRO_TOKENS");
@@ -884,16 +890,18 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         if (chain) {
             // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
             prof_begin(KJC_K_GEMM_FFN_UP, st);
-            launch_gemm_ln_gemm(w.t_ctx16, chain_pair_ ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, chain_pair_ ? L.t_w1_96 : (chain_ts_ ? L.t_w1_128 : L.t_w1_192),
-                                chain_ts_ ? w.t_h16_out32 : w.t_h16_out64, M, H, L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, chain_pair_, chain_ts_);
+            const bool pair_up = (chain_pair_mask_ & 2) != 0, ts_up = chain_ts_ && !pair_up;
+            launch_gemm_ln_gemm(w.t_ctx16, pair_up ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, pair_up ? L.t_w1_96 : (ts_up ? L.t_w1_128 : L.t_w1_192),
+                                ts_up ? w.t_h16_out32 : w.t_h16_out64, M, H, L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, pair_up, ts_up);
             prof_end(st);
             // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
             prof_begin(KJC_K_GEMM_FFN_DOWN, st);
             if (li + 1 < layers_.size()) {
                 const LayerDev& Ln = layers_[li + 1];
-                launch_gemm_ln_gemm(w.t_h16, chain_pair_ ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
-                                    chain_pair_ ? Ln.t_wqkv_96 : (chain_ts_ ? Ln.t_wqkv_128 : Ln.t_wqkv_192), chain_ts_ ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 3 * H,
-                                    Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, chain_pair_, chain_ts_);
+                const bool pair_dn = (chain_pair_mask_ & 1) != 0, ts_dn = chain_ts_ && !pair_dn;
+                launch_gemm_ln_gemm(w.t_h16, pair_dn ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
+                                    pair_dn ? Ln.t_wqkv_96 : (ts_dn ? Ln.t_wqkv_128 : Ln.t_wqkv_192), ts_dn ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 3 * H,
+                                    Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, pair_dn, ts_dn);
             } else {
                 launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             }

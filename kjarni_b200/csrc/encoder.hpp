@@ -186,6 +186,7 @@ class Encoder {
     int fp32_residual_ = 1;
     int cfg_max_seq_len_ = 0;
     bool chain_pair_ = false;
+    int chain_pair_mask_ = 0;
     bool chain_ts_ = false;
     bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false, chain_embed_ = false;
     int lanes_ = 2;

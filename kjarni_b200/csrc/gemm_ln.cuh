@@ -54,6 +54,45 @@ constexpr int kLnSmemBytes = kLnStages * kLnStageBytes + (kLnAliasEpi ? 0 : kLnE
 static_assert(kLnEpiWarps * kLnEpiBytesPerWarp <= kLnStageBytes, "aliased epilogue staging must fit in one ring stage");
 static_assert(kLnSmemBytes <= 232448, "shared memory budget");
 
+// The LayerNorm epilogue is issue-bound (12 warps x 128 columns per row tile, scripts/chain_trace.py): its arithmetic runs on the
+// packed fp32x2 pipe.  Shared by gemm_ln_kernel and gemm_ln_gemm_kernel so that both produce the same bits.
+// Pass A, one 32-column chunk: v = acc + residual + bias (per element exactly as in round 1: (acc + res) + bias), row sum and sum of
+// squares accumulated as (even columns, odd columns) pairs -- the caller adds the two halves at the end.
+__device__ __forceinline__ void ln_pass_a_chunk(uint32_t (&v)[32], const uint4 (&r4)[4], const float* bs, uint64_t& sum2, uint64_t& sq2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
+        const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
+        const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
+        const uint64_t bb[4] = {f2_pack(b0.x, b0.y), f2_pack(b0.z, b0.w), f2_pack(b1.x, b1.y), f2_pack(b1.z, b1.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint64_t res = f2_pack(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));  // two bf16 -> two fp32
+            const uint64_t a = f2_add(f2_add(f2_pack(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])), res), bb[e]);
+            sum2 = f2_add(sum2, a);
+            sq2 = f2_fma(a, a, sq2);
+            float a0, a1;
+            f2_unpack(a, a0, a1);
+            v[8 * j + 2 * e] = __float_as_uint(a0);
+            v[8 * j + 2 * e + 1] = __float_as_uint(a1);
+        }
+    }
+}
+// Pass B, one 32-column chunk: ((v * rstd + nmr) * gamma + beta) -> 16 packed bf16 pairs (per element the same two fmas as round 1)
+__device__ __forceinline__ void ln_pass_b_chunk(const uint32_t (&v)[32], float rstd, float nmr, const float* g, const float* bt, uint32_t (&pk)[16]) {
+    const uint64_t r2 = f2_pack(rstd, rstd), n2 = f2_pack(nmr, nmr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + 4 * j);
+        const float4 b4 = *reinterpret_cast<const float4*>(bt + 4 * j);
+        float y0, y1, y2, y3;
+        f2_unpack(f2_fma(f2_fma(f2_pack(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1])), r2, n2), f2_pack(g4.x, g4.y), f2_pack(b4.x, b4.y)), y0, y1);
+        f2_unpack(f2_fma(f2_fma(f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), r2, n2), f2_pack(g4.z, g4.w), f2_pack(b4.z, b4.w)), y2, y3);
+        pk[2 * j] = pack_bf16(y0, y1);
+        pk[2 * j + 1] = pack_bf16(y2, y3);
+    }
+}
+
 struct GemmLnParams {
     int M, K;
     const float* bias;   // [H] or nullptr
@@ -243,7 +282,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
 
             // ---- pass A: v = acc + bias + residual ; row sum and sum of squares ; v -> TMEM
-            float s1 = 0.0f, s2 = 0.0f;
+            uint64_t sum2 = f2_pack(0.0f, 0.0f), sq2 = f2_pack(0.0f, 0.0f);
 #pragma unroll 1
             for (int c = 0; c < kChunks; ++c) {
                 const int b = c & 1;
@@ -256,25 +295,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 4; ++j) r4[j] = ld_shared_v4(rbase + ((j ^ sw) << 4));
                 tmem_ld_wait();
-                const float* bs = s_bias + col_base + c * kEpiChunkCols;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
-                    const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
-                    const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-                        const float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo + bb[2 * e];
-                        const float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi + bb[2 * e + 1];
-                        s1 += a0 + a1;
-                        s2 = fmaf(a0, a0, s2);
-                        s2 = fmaf(a1, a1, s2);
-                        v[8 * j + 2 * e] = __float_as_uint(a0);
-                        v[8 * j + 2 * e + 1] = __float_as_uint(a1);
-                    }
-                }
+                ln_pass_a_chunk(v, r4, s_bias + col_base + c * kEpiChunkCols, sum2, sq2);
                 tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
                 __syncwarp();  // every lane has read residual buffer b
                 if (lane == 0 && c + 2 < kChunks) {
@@ -283,6 +304,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
             }
             tmem_st_wait();
+            float s1, s2;
+            {
+                float e0, e1, q0, q1;
+                f2_unpack(sum2, e0, e1);
+                f2_unpack(sq2, q0, q1);
+                s1 = e0 + e1;
+                s2 = q0 + q1;
+            }
             stat[part * 128 + trow] = make_float2(s1, s2);
             if (kCluster > 1) {  // the same partial sums into the peer's buffer for this tile parity, then a releasing remote arrive
                 const uint32_t peer = rank ^ 1u;
@@ -329,25 +358,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     if (lane == 0) mbar_arrive(tmem_empty);
                 }
                 const int col0 = col_base + c * kEpiChunkCols;  // within this CTA's 384 columns
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 g = *reinterpret_cast<const float4*>(s_gamma + col0 + 4 * j);
-                    const float4 bt = *reinterpret_cast<const float4*>(s_beta + col0 + 4 * j);
-                    f[4 * j + 0] = fmaf(fmaf(__uint_as_float(v[4 * j + 0]), rstd, nmr), g.x, bt.x);
-                    f[4 * j + 1] = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr), g.y, bt.y);
-                    f[4 * j + 2] = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr), g.z, bt.z);
-                    f[4 * j + 3] = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr), g.w, bt.w);
-                }
+                uint32_t pk[16];
+                ln_pass_b_chunk(v, rstd, nmr, s_gamma + col0, s_beta + col0, pk);
                 if (lane == 0) bulk_wait_read<1>();
                 __syncwarp();
                 uint8_t* buf = ebuf + sbuf * kEpiStageBytes;
                 const uint32_t obase = smem_u32(buf) + lane * 64;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    st_shared_v4(obase + ((j ^ sw) << 4), pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                 pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-                }
+                for (int j = 0; j < 4; ++j) st_shared_v4(obase + ((j ^ sw) << 4), pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {

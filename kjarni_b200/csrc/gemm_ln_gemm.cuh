@@ -60,6 +60,12 @@ static_assert(kLg2BaseBytes % 1024 == 0 && kLg2SmemBytes <= 232448, "shared memo
 static_assert(kLg2WBytes + 6 * kLg2WideBytes <= kLnBBytes && kLg2WideBytes <= kLnStatBytes + kLnN * 4, "wide staging aliases");
 static_assert(2 * kLg2WBytes <= 3 * kLnABytes && kLg2WBytes + kLnEpiWarps * kEpiStageBytes <= kLnBBytes, "phase-2 aliasing");
 // kTS (phase 2 takes its A operand from TENSOR MEMORY): tiles of 128 columns, five 16 KB W2 stages
+#ifndef KJ_LG_EARLY
+#define KJ_LG_EARLY 0  // kPair: weight halves of the first stages before griddepcontrol.wait, residual chunks before the accumulator is complete
+#endif
+#ifndef KJ_CHAIN_PAIR_DEFAULT
+#define KJ_CHAIN_PAIR_DEFAULT 3
+#endif
 #ifndef KJ_CHAIN_TS_DEFAULT
 #define KJ_CHAIN_TS_DEFAULT 0
 #endif
@@ -116,7 +122,11 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     static_assert(!(kPair && P1 == 1), "the embedding front end runs one CTA per tile");
     static_assert(!(kTS && (kPair || P1 == 1)), "x' in tensor memory: one CTA per tile, GEMM front end");
     constexpr int kBN2 = kTS ? kLgTBN : kLg2BN;             // phase-2 tile width
-    constexpr int kStages2 = kTS ? kLgTStages : kLg2Stages;
+    // kPair: every CTA holds HALF of each weight tile, so the same shared memory holds rings twice as deep in MMA time: four phase-1
+    // stages of 40 KB (A 16 KB | two 12 KB weight halves) and six 12 KB W2 stages.  A TMA round trip under load is ~1500 clk
+    // (scripts/chain_trace.py) against 384 clk of MMAs per stage: three stages left both phases latency-bound.
+    constexpr int kStages1 = kPair ? 4 : 3;
+    constexpr int kStages2 = kTS ? kLgTStages : (kPair ? 6 : kLg2Stages);
     constexpr uint32_t kW2Bytes = kTS ? kLgTWBytes : kLg2WBytes;
     extern __shared__ __align__(1024) uint8_t smem_lg[];
     uint8_t* smem = smem_lg;
@@ -124,13 +134,20 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // phase 1 views
     uint8_t* smem_a = smem;                         // 3 x 16 KB
     uint8_t* smem_b = smem + 3 * kLnABytes;         // 3 x 48 KB
-    uint8_t* smem_epi1 = smem_b;                    // LN residual staging (12 x 4 KB), aliased on W stage 0
+    uint8_t* smem_epi1 = smem_b;                    // LN residual staging (12 x 4 KB), aliased on W stage 0 (kPair: see ln_stage)
     // phase 2 views
     uint8_t* smem_x = smem_b + kLnBBytes;           // x' tile: 6 x 16 KB
     auto w2_stage = [&](int s) -> uint8_t* {
         if constexpr (kTS) return s < 3 ? smem + s * kLgTWBytes : (s == 3 ? smem + kLg2BaseBytes : smem_b);
+        else if constexpr (kPair) return smem + s * (kLg2WBytes / 2);  // [0, 72K): stages 0-3 over the phase-1 A ring, 4-5 over the LayerNorm staging
         else return s < 2 ? smem + s * kLg2WBytes : smem_b;
     };
+    // phase-1 stage views (kPair: packed 40 KB stages)
+    constexpr int kP1PairStage = kLnABytes + kLnBBytes / 2;
+    static_assert(4 * kP1PairStage + 8 * kLnEpiBytesPerWarp <= kLg2RingBytes && 4 * kLnEpiBytesPerWarp <= 5 * kLg2WideBytes, "kPair phase-1 ring + residual staging");
+    auto p1_a = [&](int st) -> uint8_t* { return kPair ? smem + st * kP1PairStage : smem_a + st * kLnABytes; };
+    auto p1_w0 = [&](int st) -> uint8_t* { return kPair ? smem + st * kP1PairStage + kLnABytes : smem_b + st * kLnBBytes; };
+    auto p1_w1 = [&](int st) -> uint8_t* { return kPair ? smem + st * kP1PairStage + kLnABytes + kLnBBytes / 4 : smem_b + st * kLnBBytes + kLnHalfN * 128; };
     uint8_t* smem_epi2 = smem_b + kW2Bytes;         // 12 x 2 KB
     uint8_t* tail = smem + kLg2RingBytes;
     float2* stat = reinterpret_cast<float2*>(tail);  // [3][128]
@@ -139,13 +156,13 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* s_beta = s_gamma + kLnN;
     float* s_bias2 = s_beta + kLnN;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias2 + kLg2BiasMax);
-    uint64_t* full1 = bars;               // [3]
-    uint64_t* empty1 = bars + 3;          // [3]
+    uint64_t* full1 = kPair ? bars + 56 : bars;        // [3] (kPair: [4])
+    uint64_t* empty1 = kPair ? bars + 60 : bars + 3;   // [3] (kPair: [4])
     uint64_t* tmem_full1 = bars + 6;      // phase-1 accumulator complete (all phase-1 MMAs retired)
     uint64_t* res_bar = bars + 7;         // [12 warps][2 buffers]
     uint64_t* x_ready = bars + 31;        // x' tile written, LN accumulator consumed, staging region free (12 arrivals)
-    uint64_t* full2 = kTS ? bars + 44 : bars + 32;   // [3] (kTS: [5])
-    uint64_t* empty2 = kTS ? bars + 49 : bars + 35;  // [3] (kTS: [5])
+    uint64_t* full2 = (kTS || kPair) ? bars + 44 : bars + 32;                   // [3] (kTS: [5], kPair: [6])
+    uint64_t* empty2 = kTS ? bars + 49 : (kPair ? bars + 50 : bars + 35);       // [3] (kTS: [5], kPair: [6])
     uint64_t* acc_full = bars + 38;       // [2]
     uint64_t* acc_empty = bars + 40;      // [2] (12 arrivals each; kPair: the leader's, 24 arrivals = both CTAs' epilogue warps)
     uint64_t* x_pair = bars + 42;         // kPair, leader's: both CTAs' x' tiles are written (24 arrivals)
@@ -180,7 +197,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tma_prefetch_desc(&tmap_out2);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < kStages1; ++i) {
             mbar_init(&full1[i], 1);
             mbar_init(&empty1[i], 1);
         }
@@ -208,6 +225,18 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     if (threadIdx.x == 0) KJ_LGT(0);
+    // kPair: the producer thread requests the WEIGHT halves of the first phase-1 stages before it waits for the predecessor grid (they
+    // do not depend on it; the activations of the same stages follow after the wait and complete the same barriers)
+    constexpr bool kEarlyW = kPair && P1 == 0 && KJ_LG_EARLY != 0;
+    const int early_w = kEarlyW ? (k_blocks1 < kStages1 ? k_blocks1 : kStages1) : 0;
+    if (kEarlyW && threadIdx.x == 0) {
+        for (int st = 0; st < early_w; ++st) {
+            const uint32_t lbar = mapa_shared(smem_u32(&full1[st]), 0);
+            if (leader) mbar_arrive_expect_tx(&full1[st], 2 * (kLnABytes + 2 * kWBoxBytes));
+            tma_load_2d_2sm(p1_w0(st), &tmap_w, lbar, st * kGemmBlockK, static_cast<int>(rank) * kWRows, kEvictLast);
+            tma_load_2d_2sm(p1_w1(st), &tmap_w, lbar, st * kGemmBlockK, kLnHalfN + static_cast<int>(rank) * kWRows, kEvictLast);
+        }
+    }
     pdl_wait();
     pdl_launch_dependents();
     if (threadIdx.x == 0) KJ_LGT(1);
@@ -222,18 +251,20 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if constexpr (kPair) {
                     // this CTA's A rows and its 96-row half of each 192-row weight tile; all bytes are counted on the LEADER's barrier
                     const uint32_t lbar = mapa_shared(smem_u32(&full1[stage]), 0);
-                    if (leader) mbar_arrive_expect_tx(&full1[stage], 2 * (kLnABytes + 2 * kWBoxBytes));
-                    tma_load_2d_2sm(smem_a + stage * kLnABytes, &tmap_a, lbar, kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
-                    tma_load_2d_2sm(smem_b + stage * kLnBBytes, &tmap_w, lbar, kb * kGemmBlockK, static_cast<int>(rank) * kWRows, kEvictLast);
-                    tma_load_2d_2sm(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, lbar, kb * kGemmBlockK,
-                                    kLnHalfN + static_cast<int>(rank) * kWRows, kEvictLast);
+                    const bool w_requested = kb < early_w;  // weight halves (and the expected byte count) already issued above
+                    if (leader && !w_requested) mbar_arrive_expect_tx(&full1[stage], 2 * (kLnABytes + 2 * kWBoxBytes));
+                    tma_load_2d_2sm(p1_a(stage), &tmap_a, lbar, kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
+                    if (!w_requested) {
+                        tma_load_2d_2sm(p1_w0(stage), &tmap_w, lbar, kb * kGemmBlockK, static_cast<int>(rank) * kWRows, kEvictLast);
+                        tma_load_2d_2sm(p1_w1(stage), &tmap_w, lbar, kb * kGemmBlockK, kLnHalfN + static_cast<int>(rank) * kWRows, kEvictLast);
+                    }
                 } else {
                     mbar_arrive_expect_tx(&full1[stage], kLnStageBytes);
                     tma_load_2d(smem_a + stage * kLnABytes, &tmap_a, &full1[stage], kb * kGemmBlockK, tile * kGemmBlockM, kEvictFirst);
                     tma_load_2d(smem_b + stage * kLnBBytes, &tmap_w, &full1[stage], kb * kGemmBlockK, 0, kEvictLast);
                     tma_load_2d(smem_b + stage * kLnBBytes + kLnHalfN * 128, &tmap_w, &full1[stage], kb * kGemmBlockK, kLnHalfN, kEvictLast);
                 }
-                if (++stage == 3) {
+                if (++stage == kStages1) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -245,7 +276,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int nb = 0; nb < n2_tiles; ++nb) {
                 for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
                     const int s = it % kStages2;
-                    if (it == kStages2 - 1) mbar_wait(x_ready, 0);  // the last stage aliases the LayerNorm staging
+                    if (!kPair && it == kStages2 - 1) mbar_wait(x_ready, 0);  // the last stage aliases the LayerNorm staging (kPair: it has memory of its own)
                     mbar_wait(&empty2[s], ((it / kStages2) & 1) ^ 1);
                     if (it < 48) KJ_LGT(200 + it);
                     if constexpr (kPair) {
@@ -279,9 +310,9 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 mbar_wait(&full1[stage], phase);
                 if (kb == 0 && lane == 0) KJ_LGT(2);
                 tc_fence_after();
-                const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * kLnABytes));
-                const uint64_t db0 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes));
-                const uint64_t db1 = umma_desc_k_sw128(smem_u32(smem_b + stage * kLnBBytes + kLnHalfN * 128));
+                const uint64_t da = umma_desc_k_sw128(smem_u32(p1_a(stage)));
+                const uint64_t db0 = umma_desc_k_sw128(smem_u32(p1_w0(stage)));
+                const uint64_t db1 = umma_desc_k_sw128(smem_u32(p1_w1(stage)));
                 if (mma_issuer_lane()) {
 #pragma unroll
                     for (int k = 0; k < kGemmBlockK / 16; ++k) {
@@ -292,7 +323,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (kb == k_blocks1 - 1) commit(tmem_full1);
                 }
                 mma_issuer_sync();
-                if (++stage == 3) {
+                if (++stage == kStages1) {
                     stage = 0;
                     phase ^= 1;
                 }
@@ -343,7 +374,11 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int quad = warp & 3;
         const int part = ew >> 2;
         constexpr int kChunks = kLnPartCols / kEpiChunkCols;  // 4
-        uint8_t* ebuf = smem_epi1 + ew * kLnEpiBytesPerWarp;
+        // kPair: the packed phase-1 ring ends at 160 KB, so the residual staging has memory of its own -- 8 warps in [160K, 192K) (x' k-blocks 4
+        // and 5, written only in pass B, after the statistics barrier that ends every warp's residual reads), 4 warps in the wide-store
+        // tiles behind the barriers (phase 2) -- and the first two residual chunks are requested before the accumulator is complete
+        uint8_t* ebuf = !kPair ? smem_epi1 + ew * kLnEpiBytesPerWarp
+                               : (ew < 8 ? smem + 4 * kP1PairStage + ew * kLnEpiBytesPerWarp : smem + kLg2BaseBytes + (ew - 8) * kLnEpiBytesPerWarp);
         uint64_t* rbar = res_bar + 2 * ew;
         const uint32_t sw = (lane >> 1) & 3;  // 64B swizzle of this lane's row (residual / phase-2 staging tiles)
         const int trow = quad * 32 + lane;    // row inside the tile
@@ -436,18 +471,22 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // ===== phase 1: bias + residual + LayerNorm, output into the resident x' tile
             const int col_base = part * kLnPartCols;
             const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + col_base;
-            float s1 = 0.0f, s2 = 0.0f;
+            uint64_t sum2 = f2_pack(0.0f, 0.0f), sq2 = f2_pack(0.0f, 0.0f);
             if constexpr (P1 == 0) {
+                auto request_residual = [&] {
+                    if (lane == 0) {
+                        for (int c = 0; c < 2; ++c) {
+                            mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
+                            tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
+                        }
+                    }
+                    __syncwarp();
+                };
+                if constexpr (kPair && KJ_LG_EARLY != 0) request_residual();  // staging of its own: in flight while phase 1 runs
                 mbar_wait(tmem_full1, 0);
                 if (ew == 0 && lane == 0) KJ_LGT(5);
                 tc_fence_after();
-                if (lane == 0) {
-                    for (int c = 0; c < 2; ++c) {
-                        mbar_arrive_expect_tx(&rbar[c], kEpiStageBytes);
-                        tma_load_2d(ebuf + c * kEpiStageBytes, &tmap_res, &rbar[c], col_base + c * kEpiChunkCols, row0, kEvictFirst);
-                    }
-                }
-                __syncwarp();
+                if constexpr (!(kPair && KJ_LG_EARLY != 0)) request_residual();  // staging aliased on the ring: free once every phase-1 MMA has retired
 #pragma unroll 1
                 for (int c = 0; c < kChunks; ++c) {
                     const int b = c & 1;
@@ -460,25 +499,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) r4[j] = ld_shared_v4(rbase + ((j ^ sw) << 4));
                     tmem_ld_wait();
-                    const float* bs = s_bias + col_base + c * kEpiChunkCols;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t w[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w};
-                        const float4 b0 = *reinterpret_cast<const float4*>(bs + 8 * j);
-                        const float4 b1 = *reinterpret_cast<const float4*>(bs + 8 * j + 4);
-                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
-                            const float a0 = __uint_as_float(v[8 * j + 2 * e]) + lo + bb[2 * e];
-                            const float a1 = __uint_as_float(v[8 * j + 2 * e + 1]) + hi + bb[2 * e + 1];
-                            s1 += a0 + a1;
-                            s2 = fmaf(a0, a0, s2);
-                            s2 = fmaf(a1, a1, s2);
-                            v[8 * j + 2 * e] = __float_as_uint(a0);
-                            v[8 * j + 2 * e + 1] = __float_as_uint(a1);
-                        }
-                    }
+                    ln_pass_a_chunk(v, r4, s_bias + col_base + c * kEpiChunkCols, sum2, sq2);
                     tmem_st_32x32(taddr0 + c * kEpiChunkCols, v);
                     __syncwarp();
                     if (lane == 0 && c + 2 < kChunks) {
@@ -489,6 +510,14 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             tmem_st_wait();
             if (ew == 0 && lane == 0) KJ_LGT(6);
+            float s1, s2;
+            {
+                float e0, e1, q0, q1;
+                f2_unpack(sum2, e0, e1);
+                f2_unpack(sq2, q0, q1);
+                s1 = e0 + e1;
+                s2 = q0 + q1;
+            }
             stat[part * 128 + trow] = make_float2(s1, s2);
             named_bar_sync(1, kLnEpiWarps * 32);
             if (ew == 0 && lane == 0) KJ_LGT(7);
@@ -512,21 +541,10 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 tmem_ld_32x32(taddr0 + c * kEpiChunkCols, v);
                 tmem_ld_wait();
                 const int col0 = col_base + c * kEpiChunkCols;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 g = *reinterpret_cast<const float4*>(s_gamma + col0 + 4 * j);
-                    const float4 bt = *reinterpret_cast<const float4*>(s_beta + col0 + 4 * j);
-                    f[4 * j + 0] = fmaf(fmaf(__uint_as_float(v[4 * j + 0]), rstd, nmr), g.x, bt.x);
-                    f[4 * j + 1] = fmaf(fmaf(__uint_as_float(v[4 * j + 1]), rstd, nmr), g.y, bt.y);
-                    f[4 * j + 2] = fmaf(fmaf(__uint_as_float(v[4 * j + 2]), rstd, nmr), g.z, bt.z);
-                    f[4 * j + 3] = fmaf(fmaf(__uint_as_float(v[4 * j + 3]), rstd, nmr), g.w, bt.w);
-                }
+                uint32_t pk[16];
+                ln_pass_b_chunk(v, rstd, nmr, s_gamma + col0, s_beta + col0, pk);
                 const uint32_t xrow = smem_u32(smem_x) + (col0 >> 6) * kLnABytes + trow * 128;
                 const uint32_t chunk0 = static_cast<uint32_t>((col0 & 63) >> 3);  // 0 or 4
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) st_shared_v4(xrow + (((chunk0 + j) ^ xsw) << 4), pk[4 * j + 0], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                 if constexpr (kTS) {
@@ -573,7 +591,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[acc]), 0));
+                            if constexpr (kPair) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&acc_empty[acc]), 0));
                             else mbar_arrive(&acc_empty[acc]);
                         }
                     }
@@ -636,7 +654,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) {
-                                if constexpr (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[acc]), 0));
+                                if constexpr (kPair) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&acc_empty[acc]), 0));
                                 else mbar_arrive(&acc_empty[acc]);
                             }
                         }

@@ -316,6 +316,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t ran
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Arrive without the cluster-scope release: for "this warp has finished READING" signals (tcgen05.wait::ld has already completed the
+// reads), where nothing written by this thread has to become visible to the waiter.  The release form made every epilogue warp of
+// the CTA-pair kernels wait ~1400 clk per tile for its earlier st.shared / TMA traffic to drain (scripts/chain_trace.py).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load into THIS CTA's shared memory whose completion bytes are counted on an mbarrier that may live in the peer CTA of
 // the pair (`bar_cluster_addr` is a shared::cluster address, e.g. mapa_shared(bar, 0) for the leader's barrier).
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int32_t c0, int32_t c1,

@@ -19,6 +19,7 @@ def chain(K1, N2, epi2):
     v = np.ones(384, np.float32); us = C.c_float()
     N.check(lib.kjc_dbg_gemm_ln_gemm(a.ctypes.data, w.ctypes.data, v.ctypes.data, v.ctypes.data, v.ctypes.data, 1e-12, r.ctypes.data, M, K1,
                                      w2.ctypes.data, b2.ctypes.data, N2, epi2, 0, ox.ctypes.data, o2.ctypes.data, 0, C.byref(us)))
-for ko in (0, 64, 128, 256):
-    chain(384, 1536, 1 + ko)
-    chain(1536, 1152, 0 + ko)
+for var in [int(x) for x in os.environ.get("VARIANTS", "0").split(",")]:
+    for ko in [int(x) for x in os.environ.get("KOS", "0,64,128,256").split(",")]:
+        chain(384, 1536, 1 + var + ko)
+        chain(1536, 1152, 0 + var + ko)

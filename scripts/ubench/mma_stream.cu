@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128, 1) probe(unsigned long long* cyc) {
             const uint32_t d = TS ? tb + 192 + (t & 1) * 0 : tb + (t & 1) * 256;  // TS: x' in [0,192), one accumulator region behind it (N <= 256 only with one buffer)
 #pragma unroll 1
             for (int kb = 0; kb < 6; ++kb, ++it) {
-                if (HS) {
+                if (HS == 1) {
                     uint32_t ok = 0;
                     while (!ok) asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(&bar_ready)), "r"(1) : "memory");
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -89,18 +89,36 @@ __global__ void __launch_bounds__(128, 1) probe(unsigned long long* cyc) {
                 const uint64_t da = desc_sw128(a0 + (VARY ? kb * 16384 : 0));
                 const uint64_t db = desc_sw128(b0 + (VARY ? (it % kStages) * kBStage : 0));
                 const uint32_t ta = tb + (VARY ? kb * 32 : 0);
+                constexpr int kFirst = HS >= 2 ? HS : 4;  // HS = 2 / 3: the NEXT k-block's wait sits behind the first 2 / 3 MMAs of this one
                 if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < kFirst; ++k) {
                         if (TS) umma_ts(d, ta + 8 * k, db + 2 * k, idesc, (kb | k) != 0);
                         else umma(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
-                    if (CMT) {
+                    if (HS < 2 && CMT) {
                         commit(&bar_sink);
                         if (kb == 5) commit(&bar_sink);
                     }
                 }
                 __syncwarp();
+                if (HS >= 2) {
+                    uint32_t ok = 0;
+                    while (!ok) asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(ok) : "r"(smem_u32(&bar_ready)), "r"(1) : "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = kFirst; k < 4; ++k) {
+                            if (TS) umma_ts(d, ta + 8 * k, db + 2 * k, idesc, 1);
+                            else umma(d, da + 2 * k, db + 2 * k, idesc, 1);
+                        }
+                        if (CMT) {
+                            commit(&bar_sink);
+                            if (kb == 5) commit(&bar_sink);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
         if (elect_one()) commit(&bar_done);
@@ -140,6 +158,8 @@ void sweep() {
     run<N, 1, 1, 0, 0, 0>();
     run<N, 1, 1, 1, 0, 0>();
     run<N, 1, 1, 1, 1, 0>();
+    run<N, 1, 1, 1, 2, 0>();
+    run<N, 1, 1, 1, 3, 0>();
     run<N, 0, 1, 0, 0, 0>();
 }
 

@@ -304,12 +304,15 @@ def test_chained_launch_variants_agree(dirs, monkeypatch):
     emb.close()
     assert np.array_equal(a, c)  # the front end restates the embed kernel's arithmetic bit for bit
     monkeypatch.delenv("KJC_CHAIN_EMBED")
-    for ts in ("0", "1"):  # x' of the chained launches in shared memory / in tensor memory (gemm_ln_gemm.cuh, kTS)
+    # the default pairs both chained launches (tcgen05.mma.cta_group::2, KJC_CHAIN_PAIR=3); one CTA per tile for either or both
+    # launches, and x' of the one-CTA launches in tensor memory (KJC_CHAIN_TS, gemm_ln_gemm.cuh kTS), must give the same bits
+    for pair, ts in (("0", "0"), ("1", "0"), ("2", "0"), ("0", "1"), ("1", "1")):
+        monkeypatch.setenv("KJC_CHAIN_PAIR", pair)
         monkeypatch.setenv("KJC_CHAIN_TS", ts)
         m = api.EncoderModel(dirs[arch])
         d = m.encode_batch_from_ids(ids, mask)
         m.close()
-        assert np.array_equal(a, d), ts
+        assert np.array_equal(a, d), (pair, ts)
 
 
 def test_host_call_chunking_is_invisible(dirs):
