@@ -35,6 +35,9 @@ namespace kj {
 #define KJ_ATTN_POLY_PAIRS 0
 #endif
 constexpr int kPolyPairs = KJ_ATTN_POLY_PAIRS;
+#ifndef KJ_ATTN_TWO_ISSUERS
+#define KJ_ATTN_TWO_ISSUERS 1
+#endif
 #ifndef KJ_ATTN_PACKED_SOFTMAX
 #define KJ_ATTN_PACKED_SOFTMAX 1
 #endif
@@ -98,6 +101,7 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
     using Cfg = AtsCfg<D, NKB>;
     constexpr int NIN = Cfg::kInStages;
     constexpr int NSL = Cfg::kSlots;
+    constexpr bool kTwoIssuers = KJ_ATTN_TWO_ISSUERS != 0 && NKB == 1;  // S <= 128 only: measured slower at S = 256 (32.4 vs 30.9 us)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_in = smem;
@@ -195,8 +199,11 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
                 for (int k = 0; k < nkb; ++k) tma_load_3d(stage_v(stage, k), &tmap_qkv, &full_v[stage], 2 * p.H + h * D, k * 128, b);
             }
         }
-    } else if (warp == 1) {
-        // -------------------------------------------------------------- MMA issuer (whole warp, warp-uniform code)
+    } else if (warp == 1 || (kTwoIssuers && warp == 2)) {
+        // -------------------------------------------------------------- MMA issuers (whole warps, warp-uniform code)
+        // kTwoIssuers (S <= 128): warp 1 issues every Q.K^T, warp 2 (idle after the TMEM allocation) every P.V, each in unit order with
+        // blocking waits -- a P.V no longer queues behind the polling and the Q.K^T issue of other slots (the softmax warps waited
+        // 0.9 us per unit for O, profiles/r02_attention_analysis.md).  Otherwise warp 1 issues both from one greedy polling loop.
         constexpr uint32_t idesc_qk = umma_idesc(1, 128, 128);
         constexpr uint32_t idesc_pv = umma_idesc(1, 128, D) | (1u << 16);  // B (= V) is MN-major; A (= P) comes from TMEM
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -206,7 +213,8 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
             int b, h;
             while (get_unit(n_mine, b, h)) ++n_mine;
         }
-        if (p.dbg & 1) {  // probe: consume the input stages without any tensor or softmax work
+        if ((p.dbg & 1) && warp == 2) n_mine = 0;
+        if ((p.dbg & 1) && warp == 1) {  // probe: consume the input stages without any tensor or softmax work
             for (int i = 0; i < n_mine; ++i) {
                 mbar_wait(&full_qk[i % NIN], (i / NIN) & 1);
                 mbar_wait(&full_v[i % NIN], (i / NIN) & 1);
@@ -267,6 +275,28 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_c
         // Greedy issue: Q.K^T of query block q as soon as its inputs landed and its slot is free (O of the previous occupant read),
         // P.V of query block v as soon as every warpgroup of its slot has published its P block.
         int qk_next = 0, pv_next = 0;
+        if (kTwoIssuers) {
+            if (warp == 1) {
+                for (int g = 0; g < total; ++g) {
+                    const int iu = g / nkb;
+                    const int stage = iu % NIN, slot = g % NSL, use = g / NSL;
+                    mbar_wait(&full_qk[stage], (iu / NIN) & 1);
+                    if (use > 0) mbar_wait(&o_empty[slot], (use - 1) & 1);
+                    issue_qk(g);
+                }
+            } else {
+                for (int g = 0; g < total; ++g) {
+                    const int iu = g / nkb;
+                    const int stage = iu % NIN, slot = g % NSL;
+                    const uint32_t par = (g / NSL) & 1;
+                    mbar_wait(&full_v[stage], (iu / NIN) & 1);
+#pragma unroll
+                    for (int j = 0; j < NKB; ++j) mbar_wait(&p_full[slot * NKB + j], par);
+                    issue_pv(g);
+                }
+            }
+            pv_next = total;
+        }
         while (pv_next < total) {
             if (qk_next < total && qk_next < pv_next + NSL) {
                 const int iu = qk_next / nkb;

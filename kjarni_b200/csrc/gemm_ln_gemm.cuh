@@ -6,35 +6,41 @@
 //
 // Why: every op of the layer is local to a 128-token tile, so the CTA that produced tile b of x' can run the next projection of
 // tile b straight away.  Against two launches this removes one launch's fill and drain bubbles (~5 us of a ~20 us launch,
-// DESIGN.md section 5), the re-load of x' as the A operand (it never leaves shared memory: 6 k-blocks of 16 KB written by the
-// LayerNorm epilogue directly in the 128B-swizzled K-major layout the tensor core reads) and one third of the TMA writes into
-// shared memory during phase 2 -- shared-memory bandwidth is what bounds these K = 384 GEMMs.
+// DESIGN.md section 5) and the re-load of x' as the A operand (it never leaves shared memory: 6 k-blocks of 16 KB written by the
+// LayerNorm epilogue directly in the 128B-swizzled K-major layout the tensor core reads).
 //
 // One tile per CTA (the host falls back to the two separate kernels when there are more 128-row tiles than SMs).
-// Shared memory (bytes) -- phase 2 lives entirely inside phase 1's operand ring:
+// Shared memory (bytes), one CTA per tile -- phase 2 lives entirely inside phase 1's operand ring:
 //     [0, 48K)       phase 1: A ring, 3 x 16 KB               | phase 2: W2 stages 0, 1 (2 x 24 KB)
-//     [48K, 96K)     phase 1: W ring stage 0 (= LN staging)   | phase 2: W2 stage 2 (24 KB) + output staging (12 x 2 KB)
+//     [48K, 96K)     phase 1: W ring stage 0 (= LN staging)   | phase 2: W2 stage 2 (24 KB) + output staging of warps 0-5 (6 x 4 KB)
 //     [96K, 192K)    phase 1: W ring stages 1, 2              | phase 2: x' tile, 6 x 16 KB (A operand, resident)
+//     [192K, 206K)   LayerNorm statistics, bias / gamma / beta, phase-2 bias, barriers (warp 6 stages its output on the dead statistics)
+//     [206K, 226K)   output staging of warps 7-11
 // TMEM: phase 1 accumulates the full 128 x 384 rows in columns [0, 384); phase 2 double-buffers 128 x 192 accumulators in
 // [0, 192) and [192, 384).  Warp roles as in gemm_ln.cuh (warp 0 TMA, warp 1 MMA, warp 2 TMEM, warps 4-15 epilogue).
 // Results are bit-identical to gemm_ln384_kernel followed by gemm_tcgen05_kernel<192, EPI>: same MMA shapes, same k order.
 //
-// kPair = true: two CTAs of a cluster (one TPC) run their two row tiles together with tcgen05.mma.cta_group::2 (M = 256: 128 rows
-// per CTA).  Each CTA loads only HALF of every weight tile (96 of the 192 rows of W1 / W2 per MMA) and the tensor core reads both
-// halves, so the weight bytes written into and read out of each SM's shared memory halve -- shared-memory bandwidth (TMA writes +
-// operand reads + epilogue staging against 128 B/clk) is what bounds these kernels.  Rows are still owned by
-// one CTA (its 128 TMEM lanes), so LayerNorm, the x' tile and both epilogues are unchanged; only the leader CTA issues MMAs, the
+// kPair = true (the default of the encoder, KJC_CHAIN_PAIR): two CTAs of a cluster (one TPC) run their two row tiles together with
+// tcgen05.mma.cta_group::2 (M = 256: 128 rows per CTA).  Each CTA loads only HALF of every weight tile (96 of the 192 rows of
+// W1 / W2 per MMA) and the tensor core reads both halves.  What this buys (scripts/chain_trace.py, profiles/r02_chain_*): with one
+// CTA per tile every SM streams the whole weight matrix out of L2 (148 x 1.2 MB per launch, ~18-24 TB/s at the MMA rate against
+// the ~10 TB/s L2 delivers), a TMA round trip takes ~1500 clk under that load, and a three-stage ring holds 384-768 clk of MMAs
+// per stage: phase 2 and FFN-down's phase 1 ran latency-bound at 180 clk per MMA.  Half-size weight stages make the same shared
+// memory a ring twice as deep in MMA time -- four 40 KB phase-1 stages (A 16 KB | two 12 KB weight halves) and six 12 KB W2 stages
+// -- and halve the L2 traffic: FFN-down's phase 1 now runs at 98 clk per MMA (floor 96), phase 2 at ~120.  Rows are still owned
+// by one CTA (its 128 TMEM lanes), so LayerNorm, the x' tile and both epilogues are unchanged; only the leader CTA issues MMAs, the
 // leader's barriers count both CTAs' TMA bytes, commits are multicast to both CTAs and the peer's epilogue warps release
-// accumulators / publish x' on the leader's barriers.
+// accumulators / publish x' on the leader's barriers.  The accumulator release is a RELAXED cluster arrive: the release form cost
+// every epilogue warp ~1400 clk per tile (it waits for the warp's earlier shared-memory / TMA traffic to drain), which is what made
+// the first pair variant of this kernel slower than the one-CTA form.  The residual staging has memory of its own behind the
+// 160 KB ring ([160K, 192K) + 16 KB of the output staging), so all six W2 stages are prefetched under the LayerNorm epilogue.
 //
-// kTS = true (default since round 2): phase 2 reads x' from TENSOR MEMORY instead of shared memory.  An SS-mode 128 x 192 x 16 MMA reads
-// 4 KB of A and 6 KB of B from shared memory every 96 clk while TMA writes the next 6 KB of W2 and the epilogue stages 4 KB per
-// MMA: 20 KB against the 128 B/clk the SM's shared memory delivers, i.e. >= 160 clk per MMA (measured 190-250).  The LayerNorm
-// epilogue therefore ALSO writes x' as packed bf16 into TMEM (tcgen05.st; columns [0,64) in place for column part 0, [384,512) for
-// parts 1 and 2) and phase 2 issues tcgen05.mma with the A operand in TMEM ("TS" form): the A re-reads (one per 128 output
-// columns) leave shared memory altogether.  TMEM then has room for two 128-column accumulators ([64,192), [192,320)), so phase-2
-// tiles are 128 wide (an M = 128 MMA costs N/2 clk: narrower tiles waste nothing) with five 16 KB W2 stages.  The x' tile in shared
-// memory remains only as the source of the TMA store to global memory.  Same MMA k order per output element: bit-identical.
+// kTS = true (opt-in, KJC_CHAIN_TS, one CTA per tile): phase 2 reads x' from TENSOR MEMORY instead of shared memory.  The LayerNorm
+// epilogue ALSO writes x' as packed bf16 into TMEM (tcgen05.st; columns [0,64) in place for column part 0, [384,512) for parts 1
+// and 2) and phase 2 issues tcgen05.mma with the A operand in TMEM ("TS" form).  TMEM then has room for two 128-column accumulators
+// ([64,192), [192,320)), so phase-2 tiles are 128 wide with five 16 KB W2 stages; the x' tile in shared memory remains only as the
+// source of the TMA store to global memory.  Bit-identical.  Measured equal to the shared-memory form (33.1 vs 33.0 us): the A
+// operand reads were not what bounded phase 2 (the W2 stream was), so it is not the default.
 #pragma once
 #include <cuda.h>
 
@@ -50,10 +56,10 @@ constexpr int kLg2BiasMax = 1536;                           // phase-2 bias colu
 constexpr int kLg2RingBytes = 3 * kLnStageBytes;            // 192 KB: phase 1 always runs a 3-stage ring here
 constexpr int kLg2BaseBytes = kLg2RingBytes + kLnStatBytes + kLnVecBytes + kLg2BiasMax * 4 + 512;
 // Phase-2 output staging: every epilogue warp stages its whole 32 x 64 part of a 192-column tile (4 KB, 128-byte rows) and issues ONE
-// TMA store per tile.  With two 32 x 32 chunks through one 2 KB buffer the second chunk waited for the first chunk's store to
-// have read the buffer, and every chunk paid its own proxy fence + store: that chain, not the MMAs or the W2 stream, paced
-// phase 2 (knock-outs, profiles/r02_chain_knockouts.txt).  Warps 0-5 stage in [72K, 96K) (the rest of the LayerNorm staging), warp 6
-// on the LayerNorm statistics / bias1 (dead once x' is published), warps 7-11 in 20 KB behind the barriers.
+// TMA store per tile (one proxy fence, one store, no wait for the first chunk's store inside the tile) -- the same form as the
+// stand-alone GEMM's 192-column tiles.  Measured neutral against two 32 x 32 chunks through one 2 KB buffer (35.1 vs 34.6 us): the
+// store chain was not what paced phase 2 either.  Warps 0-5 stage in [72K, 96K) (the rest of the LayerNorm staging), warp 6 on the
+// LayerNorm statistics / bias1 (dead once x' is published), warps 7-11 in 20 KB behind the barriers.
 constexpr int kLg2WideBytes = 32 * 64 * 2;                  // 4 KB per warp
 constexpr int kLg2SmemBytes = kLg2BaseBytes + 5 * kLg2WideBytes;
 static_assert(kLg2BaseBytes % 1024 == 0 && kLg2SmemBytes <= 232448, "shared memory budget");
@@ -61,7 +67,9 @@ static_assert(kLg2WBytes + 6 * kLg2WideBytes <= kLnBBytes && kLg2WideBytes <= kL
 static_assert(2 * kLg2WBytes <= 3 * kLnABytes && kLg2WBytes + kLnEpiWarps * kEpiStageBytes <= kLnBBytes, "phase-2 aliasing");
 // kTS (phase 2 takes its A operand from TENSOR MEMORY): tiles of 128 columns, five 16 KB W2 stages
 #ifndef KJ_LG_EARLY
-#define KJ_LG_EARLY 0  // kPair: weight halves of the first stages before griddepcontrol.wait, residual chunks before the accumulator is complete
+#define KJ_LG_EARLY 0  // kPair: weight halves of the first stages before griddepcontrol.wait, residual chunks before the accumulator is
+                       // complete.  Measured 1.2 % SLOWER in the whole step (262-263 vs 266 k emb/s): the early loads compete with the
+                       // predecessor's tail and with phase 1 for the same L2 bandwidth.  Compiled out.
 #endif
 #ifndef KJ_CHAIN_PAIR_DEFAULT
 #define KJ_CHAIN_PAIR_DEFAULT 3
