@@ -118,6 +118,30 @@ static void launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb
     }
 }
 
+// CTA-pair form of the GEMM (gemm_tcgen05_kernel<BN, EPI, true>: tcgen05.mma.cta_group::2 over two row tiles, half a weight tile per CTA):
+// bf16 outputs, 192- and 256-column tiles; `tb_half` has a box of block_n / 2 weight rows.
+template <int BN, int EPI>
+static void launch_gemm_cta_pair_inst(const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p, int num_sms,
+                                      cudaStream_t st) {
+    using Cfg = GemmCfg<BN, true>;
+    static int configured[64] = {0};
+    auto kern = gemm_tcgen05_kernel<BN, EPI, true>;
+    ensure_smem_attr(kern, Cfg::kSmemBytes, configured);
+    const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int grid = 2 * std::min(((m_tiles + 1) / 2) * n_tiles, std::max(1, num_sms / 2));
+    launch_pdl_cluster(2, kern, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, ta, tb_half, tc, p);
+}
+bool gemm_cta_pair_supported(int block_n, int epi) { return (block_n == 192 || block_n == 256) && (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_ACT_BF16); }
+void launch_gemm_cta_pair(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb_half, const CUtensorMap& tc, const GemmParams& p,
+                          int num_sms, cudaStream_t st) {
+    if (p.N % 16 != 0 || p.K % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs N % 16 == 0 and K % 8 == 0");
+    if (!gemm_cta_pair_supported(block_n, epi)) throw Error(KJC_INVALID_CONFIG, "CTA-pair GEMM: 192- or 256-column tiles, bf16 output");
+    const bool act = epi == EPI_BIAS_ACT_BF16;
+    if (block_n == 192) act ? launch_gemm_cta_pair_inst<192, EPI_BIAS_ACT_BF16>(ta, tb_half, tc, p, num_sms, st) : launch_gemm_cta_pair_inst<192, EPI_BIAS_BF16>(ta, tb_half, tc, p, num_sms, st);
+    else act ? launch_gemm_cta_pair_inst<256, EPI_BIAS_ACT_BF16>(ta, tb_half, tc, p, num_sms, st) : launch_gemm_cta_pair_inst<256, EPI_BIAS_BF16>(ta, tb_half, tc, p, num_sms, st);
+}
+
 void launch_gemm(int block_n, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p, int num_sms,
                  cudaStream_t st) {
     if (p.N % 16 != 0 || p.K % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs N % 16 == 0 and K % 8 == 0");
@@ -710,10 +734,16 @@ Encoder::Encoder(const std::string& dir, int device) {
             ld.t_w1_ffn32 = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, 32, kGemmBlockK, 128);
             ld.t_w2_ffn = make_tmap_2d(ld.w2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, I, 64, kGemmBlockK, 128);
         }
-        if (H <= kPairMaxKB * kGemmBlockK && bn_qkv_ >= 128 && bn_i_ >= 128) {  // CTA-pair kernel: each CTA loads half of a weight tile
+        if (bn_qkv_ >= 128 && bn_i_ >= 128) {  // CTA-pair kernels: each CTA loads half of a weight tile
             ld.t_wqkv_half = make_tmap_2d(ld.wqkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 3 * H, H, bn_qkv_ / 2, kGemmBlockK, 128);
             ld.t_w1_half = make_tmap_2d(ld.w1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, I, H, bn_i_ / 2, kGemmBlockK, 128);
         }
+    }
+    {
+        // QKV and FFN-up as CTA pairs (gemm_tcgen05_kernel<BN, EPI, true>): bit 0 = QKV, bit 1 = FFN-up; KJC_GEMM_PAIR overrides
+        const char* e = getenv("KJC_GEMM_PAIR");
+        const int want = e != nullptr ? atoi(e) : KJ_GEMM_PAIR_DEFAULT;
+        gemm_pair_mask_ = num_sms_ % 2 == 0 ? ((gemm_cta_pair_supported(bn_qkv_, EPI_BIAS_BF16) ? want & 1 : 0) | (gemm_cta_pair_supported(bn_i_, EPI_BIAS_ACT_BF16) ? want & 2 : 0)) : 0;
     }
     pair_gemm_ = H <= kPairMaxKB * kGemmBlockK && H % kGemmBlockK == 0 && bn_qkv_ >= 128 && bn_i_ >= 128 && experimental_kernels_built() && getenv("KJC_PAIR_GEMM") != nullptr;  // slower than the 1-CTA kernel at one 256-row tile per pair (launch-bound regime): opt-in
     if (info_.head_kind != KJC_HEAD_ABSENT) {
@@ -874,6 +904,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
             g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = 3 * H; g.act = ACT_NONE;
             prof_begin(KJC_K_GEMM_QKV, st);
             if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, (bn_qkv_ == 192 ? w.t_qkv16_out : w.t_qkv16_out32), g, sms, st);
+            else if ((gemm_pair_mask_ & 1) && M > kGemmBlockM) launch_gemm_cta_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, w.t_qkv16_out, g, sms, st);
             else launch_gemm(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv, w.t_qkv16_out, g, sms, st);
             prof_end(st);
             ++launches_;
@@ -902,6 +933,11 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
                 launch_gemm_ln_gemm(w.t_h16, pair_dn ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
                                     pair_dn ? Ln.t_wqkv_96 : (ts_dn ? Ln.t_wqkv_128 : Ln.t_wqkv_192), ts_dn ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 3 * H,
                                     Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, pair_dn, ts_dn);
+            } else if ((chain_pair_mask_ & 1) != 0 && !getenv("KJC_LAST_LN_ONE_CTA")) {
+                // last layer: the same CTA-pair launch with an empty second projection (N2 = 0: no phase-2 tiles) -- its phase 1 streams half
+                // the weight bytes per SM through a ring twice as deep as gemm_ln_kernel<1>'s
+                launch_gemm_ln_gemm(w.t_h16, L.t_w2_96, w.t_x16_io, w.t_x16, L.t_wqkv_96, w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 0, nullptr, EPI_BIAS_BF16,
+                                    ACT_NONE, st, true, false);
             } else {
                 launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
             }
@@ -938,6 +974,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         g.M = M; g.N = I; g.K = H; g.bias = L.b1; g.out = w.h16; g.ldo = I; g.act = act_;
         prof_begin(KJC_K_GEMM_FFN_UP, st);
         if (pair_gemm_) launch_gemm_pair(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1_half, (bn_i_ == 192 ? w.t_h16_out : w.t_h16_out32), g, sms, st);
+        else if ((gemm_pair_mask_ & 2) && M > kGemmBlockM) launch_gemm_cta_pair(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1_half, w.t_h16_out, g, sms, st);
         else launch_gemm(bn_i_, EPI_BIAS_ACT_BF16, w.t_x16, L.t_w1, w.t_h16_out, g, sms, st);
         prof_end(st);
         // y = x + t W2^T + b2 ; x = LN2(y)                         (standard_new.rs:76-79, encoder_layer.rs:150-176)
@@ -1259,7 +1296,9 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         int dev = 0;
         KJ_CUDA(cudaGetDevice(&dev));
         KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
-        const bool pair = block_n >= 1000;
+        const bool pair2 = block_n >= 2000;  // + 2000: the CTA-pair form of gemm_tcgen05_kernel
+        if (pair2) block_n -= 2000;
+        const bool pair = block_n >= 1000;   // + 1000: the experimental A-resident pair kernel (gemm_pair.cuh)
         if (pair) block_n -= 1000;
         const int bn = block_n > 0 ? block_n : pick_block_n(N);
         const size_t Mp = std::max(M, 128), Np = std::max(N, bn);
@@ -1289,7 +1328,10 @@ void dbg_gemm(const uint16_t* a_bf16, const uint16_t* w_bf16, const float* bias,
         CUtensorMap tc = ta;
         if (!f32out) tc = ((!pair && gemm_wide_store(bn)) || (bn == 192 && pair)) ? make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, 64, 128)
                                                : make_tmap_2d(dO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, N, 32, kEpiChunkCols, 64);
-        if (pair) {
+        if (pair2) {
+            CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
+            launch_gemm_cta_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
+        } else if (pair) {
             CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
             launch_gemm_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
         } else
@@ -1485,6 +1527,8 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     int dev = 0;
     KJ_CUDA(cudaGetDevice(&dev));
     KJ_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const bool pair2 = block_n >= 2000;
+    if (pair2) block_n -= 2000;
     const bool pair = block_n >= 1000;
     if (pair) block_n -= 1000;
     const int bn = block_n > 0 ? block_n : pick_block_n(N);
@@ -1515,7 +1559,8 @@ float dbg_gemm_time(int M, int N, int K, int epi, int act, int block_n, int flag
     KJ_CUDA(cudaEventCreate(&e1));
     CUtensorMap tbh = make_tmap_2d(dW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Np, K, bn / 2, kGemmBlockK, 128);
     auto go = [&] {
-        if (pair) launch_gemm_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
+        if (pair2) launch_gemm_cta_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
+        else if (pair) launch_gemm_pair(bn, epi, ta, tbh, tc, p, prop.multiProcessorCount, nullptr);
         else launch_gemm(bn, epi, ta, tb, tc, p, prop.multiProcessorCount, nullptr);
     };
     for (int i = 0; i < 5; ++i) go();

@@ -101,23 +101,6 @@ struct GemmLnParams {
     float eps;
 };
 
-// acquire at cluster scope: pairs with the peer's mbarrier.arrive.release.cluster after its st.shared::cluster
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0, ok = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P;\n\t"
-            "}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (ok) break;
-        if (++spins > KJ_MBAR_SPIN_LIMIT) __trap();
-    }
-}
 __device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
 }

@@ -55,6 +55,9 @@ constexpr int kEpiChunkCols = 32;                         // columns per tcgen05
 constexpr int kEpiStageBytes = 32 * kEpiChunkCols * 2;    // one warp's bf16 staging tile: 32 rows x 64 B (64B swizzle)
 constexpr int kEpiBiasMax = 3072;                         // bias columns staged in shared memory (BN <= 192 configurations)
 
+#ifndef KJ_GEMM_PAIR_DEFAULT
+#define KJ_GEMM_PAIR_DEFAULT 3  // encoder: QKV (bit 0) and FFN-up (bit 1) as CTA pairs when their tiles are 192 / 256 columns wide
+#endif
 #ifndef KJ_GEMM_PARTS192
 #define KJ_GEMM_PARTS192 3
 #endif
@@ -66,14 +69,18 @@ constexpr bool kGemm192WideStore = KJ_GEMM_PARTS192 == 3;
 // output tensor map with a 32 x 64 box for these widths.
 constexpr bool gemm_wide_store(int bn) { return (bn == 192 && kGemm192WideStore) || (bn == 256 && KJ_GEMM_WIDE256 != 0); }
 
-template <int BN>
+// kPair (gemm_tcgen05_kernel<BN, EPI, true>): two CTAs of a cluster run two row tiles against the same weight tile as one
+// tcgen05.mma.cta_group::2 (M = 256), each CTA loading its own A rows and HALF of the weight rows.  A K-streaming 128 x BN tile
+// needs (16 + BN / 8) KB from L2 per k-block of BN / 2 clk x 4 MMAs -- 87 flop/B at BN = 256, and L2 delivers ~10 TB/s to 148 SMs
+// streaming at once: ~870 TFLOP/s, which is what the one-CTA kernel measures on the hidden-768 projections (0.63-0.65 of the
+// sustained roof).  Half the weight bytes per SM is 131 flop/B, and the smaller stages make the ring deeper in MMA time.
+template <int BN, bool kPair = false>
 struct GemmCfg {
     static constexpr bool kWide = gemm_wide_store(BN);
     // 256-column tiles: a tcgen05.mma of M = 128 costs ~128 clk whatever N <= 256 is (measured, scripts/mma_rate.py), so the widest
     // tile wastes no tensor time; its 16 epilogue warps need 64 KB of staging, hence 3 operand stages of 48 KB
-    static constexpr int kStages = (BN <= 64) ? 6 : ((BN <= 128) ? 5 : ((BN == 256 && kWide) ? 3 : 4));
     static constexpr int kABytes = kGemmBlockM * kGemmBlockK * 2;
-    static constexpr int kBBytes = BN * kGemmBlockK * 2;
+    static constexpr int kBBytes = (kPair ? BN / 2 : BN) * kGemmBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
     // epilogue warps: 4 TMEM lane quadrants x kParts column parts.  Wide-store tiles use parts of 64 columns (12 / 16 warps, 3 / 4 per
@@ -89,6 +96,8 @@ struct GemmCfg {
     static constexpr int kEpiBufBytes = 32 * kStoreCols * 2;
     static constexpr int kEpiBytes = kEpiWarpsN * kEpiBufs * kEpiBufBytes;
     static constexpr int kBiasBytes = (BN <= 192 || kWide) ? kEpiBiasMax * 4 : 0;  // bias staged in smem where it fits
+    static constexpr int kPairStages = (232448 - 1024 - 256 - kBiasBytes - kEpiBytes) / kStageBytes;  // as many as fit (BN 256: 4 x 32 KB, 192: 5 x 28 KB)
+    static constexpr int kStages = kPair ? (kPairStages > 8 ? 8 : kPairStages) : ((BN <= 64) ? 6 : ((BN <= 128) ? 5 : ((BN == 256 && kWide) ? 3 : 4)));
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -137,11 +146,12 @@ __device__ __forceinline__ void apply_act_tile(float (&f)[NELEM], int act) {
     }
 }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
+template <int BN, int EPI, bool kPair = false>
+__global__ void __launch_bounds__(GemmCfg<BN, kPair>::kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, GemmParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, kPair>;
+    static_assert(!kPair || (BN % 32 == 0 && BN >= 128 && 2 * Cfg::kStages + 5 <= 32), "pair tiles: 128-256 columns");
     constexpr int kStages = Cfg::kStages;
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
 
@@ -168,8 +178,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int m_tiles = (p.M + kGemmBlockM - 1) / kGemmBlockM;
     const int n_tiles = (p.N + BN - 1) / BN;
-    const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (p.K + kGemmBlockK - 1) / kGemmBlockK;
+    // work units: (row tile, column tile), or for pairs (two consecutive row tiles, column tile) with this CTA on row tile 2 u + rank
+    // (a row tile beyond M is all padding: loads zero-filled, stores clipped)
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int num_tiles = (kPair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+    auto row_tile_of = [&](int tile) { return kPair ? 2 * (tile / n_tiles) + static_cast<int>(rank) : tile / n_tiles; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -183,13 +200,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], Cfg::kEpiWarpsN);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], (kPair ? 2 : 1) * Cfg::kEpiWarpsN);  // one arrive per epilogue warp (pairs: of both CTAs, on the leader's)
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_base_smem);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_base_smem);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / TMA completion
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
     if (threadIdx.x == 0) KJ_TRACE(1);  // prologue done
@@ -202,11 +223,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles && !(p.dbg & 64); tile += gridDim.x) {
-                const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+            for (int tile = worker; tile < num_tiles && !(p.dbg & 64); tile += n_workers) {
+                const int m_blk = row_tile_of(tile), n_blk = tile % n_tiles;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (p.dbg & 4) {
+                    if constexpr (kPair) {
+                        // this CTA's A rows and its half of the weight tile; all bytes are counted on the LEADER's barrier
+                        const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        tma_load_2d_2sm(smem_a + stage * Cfg::kABytes, &tmap_a, lbar, kb * kGemmBlockK, m_blk * kGemmBlockM, kEvictFirst);
+                        tma_load_2d_2sm(smem_b + stage * Cfg::kBBytes, &tmap_b, lbar, kb * kGemmBlockK, n_blk * BN + static_cast<int>(rank) * (BN / 2), kEvictLast);
+                    } else if (p.dbg & 4) {
                         mbar_arrive(&full_bar[stage]);
                     } else {
                         mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -223,15 +250,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (KJ_MMA_UNIFORM != 0 || lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kGemmBlockM, BN);
+        if ((KJ_MMA_UNIFORM != 0 || lane == 0) && leader) {  // pairs: the leader issues for both CTAs
+            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kPair ? 2 * kGemmBlockM : kGemmBlockM, BN);
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (kPair) umma_commit_2sm(bar, 3);  // the barrier at this offset in both CTAs
+                else umma_commit(bar);
+            };
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                if constexpr (kPair) mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);  // the peer's arrives are remote
+                else mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -245,11 +277,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                             for (int k = 0; k < kGemmBlockK / 16; ++k) {
                                 // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in (addr >> 4) units
-                                umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                if constexpr (kPair) umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                else umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                             }
                         }
-                        if (!(p.dbg & 64)) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-                        if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                        if (!(p.dbg & 64)) commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                        if (kb == k_blocks - 1) commit(&tmem_full[acc]);
                     }
                     mma_issuer_sync();
                     if (++stage == kStages) {
@@ -269,8 +302,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint8_t* stage_buf = smem_epi + ew * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
         int sbuf = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        // "this warp has read the accumulator": pairs arrive on the leader's barrier, without the cluster-scope release (the reads are
+        // complete; the release form waits for the warp's earlier shared-memory / TMA traffic, ~1400 clk per tile in the chained kernels)
+        auto release_acc = [&](int a) {
+            if constexpr (kPair) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tmem_empty[a]), 0));
+            else mbar_arrive(&tmem_empty[a]);
+        };
+        for (int tile = worker; tile < num_tiles; tile += n_workers, ++it) {
+            const int m_blk = row_tile_of(tile), n_blk = tile % n_tiles;
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -309,7 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (c == 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        if (lane == 0) release_acc(acc);
                     }
                     const int col0 = colp + c * 32;
                     float f[32];
@@ -369,7 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (c + 1 == kChunks) {  // last load landed: release the accumulator before the math and stores of this chunk
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                        if (lane == 0) release_acc(acc);
                     }
                     const int col0 = n_blk * BN + half * kColsPerHalf + c * kEpiChunkCols;
                     if (col0 < p.N) {
@@ -470,7 +509,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (!kStaged || (p.dbg & 1)) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) release_acc(acc);
             }
             if (ew == 0 && lane == 0 && it < 6) KJ_TRACE(5 + 2 * it);  // epilogue of tile `it` done (stores issued)
         }
@@ -479,10 +518,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // peer shared memory / barriers stay valid until both CTAs are done
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
     if (threadIdx.x == 64) KJ_TRACE(17);  // exit
 }

@@ -63,6 +63,25 @@ def test_gemm_every_block_n_and_tails(block_n):
     assert np.abs(got - want).max() < 1e-3
 
 
+@pytest.mark.parametrize("M,Nn,K", [(256, 768, 768), (300, 1152, 384), (1000, 2304, 768), (4096, 3072, 768), (18944, 1152, 384), (130, 416, 200),
+                                    (128, 512, 64)])
+@pytest.mark.parametrize("block_n", [192, 256])
+@pytest.mark.parametrize("epi", [0, 1])
+def test_gemm_cta_pair_matches_one_cta(M, Nn, K, block_n, epi):
+    """The CTA-pair form of the GEMM (block_n + 2000: tcgen05.mma.cta_group::2 over two row tiles, half a weight tile per CTA, deeper
+    ring) issues the same MMA shapes in the same k order as the one-CTA kernel: same bits, for odd row-tile counts (one padding tile),
+    N and K tails, a single row tile, and against the fp32 oracle."""
+    rng = np.random.default_rng(M + Nn + K + block_n + epi)
+    a = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((Nn, K)) / math.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(Nn).astype(np.float32)
+    one = run_gemm(a, w, bias, None, epi, act=0, block_n=block_n)
+    pair = run_gemm(a, w, bias, None, epi, act=0, block_n=block_n + 2000)
+    assert np.array_equal(one, pair)
+    want = ref_gemm(a, w, bias, None, epi, 0)
+    assert (np.abs(pair - want) / (1.0 + np.abs(want))).max() < 2.0 ** -8
+
+
 @pytest.mark.parametrize("block_n", [128, 192, 256])
 @pytest.mark.parametrize("Nn", [1152, 416, 1536])
 @pytest.mark.parametrize("epi", [0, 1])
