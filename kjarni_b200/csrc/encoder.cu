@@ -768,6 +768,7 @@ Encoder::Encoder(const std::string& dir, int device) {
         const char* e = getenv("KJC_CHAIN_PAIR");
         chain_pair_mask_ = (chain_ && num_sms_ % 2 == 0) ? (e != nullptr ? atoi(e) : KJ_CHAIN_PAIR_DEFAULT) & 3 : 0;
         chain_pair_ = chain_pair_mask_ != 0;
+        last_ln_pair_ = getenv("KJC_LAST_LN_PAIR") != nullptr;
     }
     {
         const char* e = getenv("KJC_CHAIN_TS");  // phase 2 reads x' from tensor memory (gemm_ln_gemm.cuh, kTS)
@@ -933,9 +934,9 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
                 launch_gemm_ln_gemm(w.t_h16, pair_dn ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
                                     pair_dn ? Ln.t_wqkv_96 : (ts_dn ? Ln.t_wqkv_128 : Ln.t_wqkv_192), ts_dn ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 3 * H,
                                     Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, pair_dn, ts_dn);
-            } else if ((chain_pair_mask_ & 1) != 0 && !getenv("KJC_LAST_LN_ONE_CTA")) {
-                // last layer: the same CTA-pair launch with an empty second projection (N2 = 0: no phase-2 tiles) -- its phase 1 streams half
-                // the weight bytes per SM through a ring twice as deep as gemm_ln_kernel<1>'s
+            } else if ((chain_pair_mask_ & 1) != 0 && last_ln_pair_) {
+                // last layer, opt-in (KJC_LAST_LN_PAIR): the same CTA-pair launch with an empty second projection (N2 = 0: no phase-2 tiles).
+                // Bit-identical; measured 0.5 % slower in the whole step than gemm_ln_kernel<1> (268.9 vs 270.2 k emb/s), so not the default
                 launch_gemm_ln_gemm(w.t_h16, L.t_w2_96, w.t_x16_io, w.t_x16, L.t_wqkv_96, w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 0, nullptr, EPI_BIAS_BF16,
                                     ACT_NONE, st, true, false);
             } else {

@@ -187,6 +187,7 @@ class Encoder {
     int cfg_max_seq_len_ = 0;
     bool chain_pair_ = false;
     int chain_pair_mask_ = 0;
+    bool last_ln_pair_ = false;
     int gemm_pair_mask_ = 0;  // bit 0: QKV, bit 1: FFN-up run as CTA pairs (gemm_tcgen05_kernel<BN, EPI, true>)
     bool chain_ts_ = false;
     bool fused_ln_ = false, pair_gemm_ = false, fused_ffn_ = false, chain_ = false, chain_embed_ = false;

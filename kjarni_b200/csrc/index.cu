@@ -47,6 +47,7 @@ Index::Index(int dim, uint64_t capacity, uint64_t id_base, int device) : dim_(di
         KJ_CUDA(cudaMalloc(&d_fix_c_, 8 * sizeof(int32_t)));
         KJ_CUDA(cudaStreamSynchronize(stream_));
         t_rows16_ = make_tmap_2d(rows16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cap16, dim, kSgRows, kSgBK, 128);
+        t_rows16_half_ = make_tmap_2d(rows16_, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, cap16, dim, kSgRows / 2, kSgBK, 128);  // CTA-pair filter pass: half a row tile per CTA
     }
 }
 
@@ -248,11 +249,14 @@ static __global__ void add_counter_kernel(const int32_t* src, int32_t* dst) { at
 // proof check -> (sync callers) exact re-run of the queries that could not be proven.
 void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint64_t* d_ids_all, float* d_scores_all, int32_t* d_counts_all,
                         cudaStream_t st, bool may_sync) {
-    static int configured[64] = {0};
+    static int configured[64] = {0}, configured_pair[64] = {0};
+    // filter pass as CTA pairs (scan_gemm_kernel<true>): two query tiles against the same row tiles, half a row tile per CTA
+    static const bool env_pair = getenv("KJC_SG_PAIR") ? atoi(getenv("KJC_SG_PAIR")) != 0 : true;
     static const int env_R = getenv("KJC_SG_R") ? std::max(1, atoi(getenv("KJC_SG_R"))) : 3;
     static const int env_dbg = getenv("KJC_SG_DBG") ? atoi(getenv("KJC_SG_DBG")) : 0;
     static const bool env_no_seed = getenv("KJC_SG_NO_SEED") != nullptr;
-    ensure_smem_attr(scan_gemm_kernel, kSgSmemBytes, configured);
+    ensure_smem_attr(scan_gemm_kernel<false>, kSgSmemBytes, configured);
+    ensure_smem_attr(scan_gemm_kernel<true>, kSgSmemBytes, configured_pair);
     const uint32_t n_tiles = static_cast<uint32_t>((len_ + kSgRows - 1) / kSgRows);
     const int grid = static_cast<int>(std::min<uint32_t>(num_sms_, n_tiles));
     const int qb_max = std::min(nq_all, 4096);  // queries per pass over the shard (bounds the candidate buffers)
@@ -335,7 +339,7 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
                 ss.n_tiles = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(sgrid) * 8);
                 seed_groups = 2 * sgrid;  // per CTA and column half
             }
-            scan_gemm_kernel<<<sgrid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, ss);
+            scan_gemm_kernel<false><<<sgrid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, ss);
             KJ_CUDA(cudaGetLastError());
             ++launches_;
         }
@@ -344,7 +348,28 @@ void Index::search_gemm(const float* d_q_all, int nq_all, int k, int mode, uint6
         ++launches_;
         // ---- filter pass
         sp.thr0 = d_thr0;
-        scan_gemm_kernel<<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, sp);
+        if (env_pair && !sp.stream_a && nq > kSgQ && num_sms_ >= 2) {
+            // more than one query tile, resident query tiles: pairs of CTAs share every row tile (superblocks of half as many tiles,
+            // twice as many per worker, so the L2-resident footprint per superblock is unchanged)
+            ScanGemmParams pp = sp;
+            pp.R = 2 * sp.R;
+            const unsigned clusters = std::min<uint32_t>(static_cast<uint32_t>(num_sms_ / 2), n_tiles);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * clusters);
+            cfg.blockDim = dim3(kSgThreads);
+            cfg.dynamicSmemBytes = kSgSmemBytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            KJ_CUDA(cudaLaunchKernelEx(&cfg, scan_gemm_kernel<true>, t_q, t_rows16_half_, pp));
+        } else {
+            scan_gemm_kernel<false><<<grid, kSgThreads, kSgSmemBytes, st>>>(t_q, t_rows16_, sp);
+        }
         KJ_CUDA(cudaGetLastError());
         ++launches_;
         CandSelectParams cs;

@@ -78,7 +78,7 @@ class Index {
     size_t esc_cap_ = 0;
     bool escalate_ = true;  // KJC_SCAN_NO_ESCALATE: unproven queries go straight to the exact scan (test / measurement hook)
     size_t q16_cap_ = 0, gc_cap_ = 0, am_cap_ = 0, flags_cap_ = 0, seed_cap_ = 0;
-    CUtensorMap t_rows16_;
+    CUtensorMap t_rows16_, t_rows16_half_;
     std::vector<int32_t> h_flags_;
 };
 

@@ -54,7 +54,8 @@ constexpr int kSgMaxKB = kSgMaxD / kSgBK;                        // 6
 constexpr int kSgABlockBytes = kSgQ * kSgBK * 2;                 // 16 KB per k-block of the resident query tile
 constexpr int kSgABytes = kSgABlockBytes * kSgMaxKB;             // 96 KB
 constexpr int kSgBBytes = kSgRows * kSgBK * 2;                   // 32 KB per stage
-constexpr int kSgSmemBytes = kSgABytes + kSgStages * kSgBBytes + 256;  // 229,632 B
+constexpr int kSgPairStages = 8;                                 // kPair: the same 128 KB as a ring of eight half tiles
+constexpr int kSgSmemBytes = kSgABytes + kSgStages * kSgBBytes + 512;  // 229,888 B
 constexpr int kSgSeedGroupsMax = 320;                            // seed maxima per query (select kernel: 10 per lane)
 
 struct ScanGemmParams {
@@ -73,12 +74,21 @@ struct ScanGemmParams {
                              // (16 KB) next to the row k-block (32 KB); the query tile is re-read from L2 once per row tile
 };
 constexpr int kSgStreamStageBytes = kSgABlockBytes + kSgBBytes;  // 48 KB
-static_assert(kSgStages * kSgStreamStageBytes + 256 <= kSgSmemBytes, "streaming stages fit in the same allocation");
+static_assert(kSgStages * kSgStreamStageBytes + 512 <= kSgSmemBytes, "streaming stages fit in the same allocation");
 
 __device__ __forceinline__ uint32_t sg_tile_of(const ScanGemmParams& p, uint32_t i) {
     return p.n_tiles == p.n_tiles_total ? i : static_cast<uint32_t>(static_cast<uint64_t>(i) * p.n_tiles_total / p.n_tiles);
 }
 
+// kPair: two CTAs of a cluster work on the SAME row tiles for two DIFFERENT query tiles (tcgen05.mma.cta_group::2, M = 256: 128 queries
+// per CTA).  Each CTA loads only half of every row tile (128 of its 256 rows) and the tensor core reads both halves.  With the query
+// tile resident, a 128 x 256 x 64 k-block needs 32 KB of rows per 512 clk of MMAs: 64 B/clk per SM, 18 TB/s for 148 SMs streaming out
+// of the L2-resident superblock against the ~10 TB/s L2 delivers -- the one-CTA filter pass measures 0.65 of the tensor roof, and the
+// chained encoder kernels had the same bound.  Half the row bytes per SM, and the same 128 KB as a ring of eight
+// half tiles instead of four whole ones.  Queries stay owned by one CTA (its TMEM lanes): the filter epilogue is unchanged, it only
+// releases accumulators on the leader's barrier (relaxed cluster arrive).  `tmap_rows` has 128-row boxes in this mode; query tile of
+// iteration j = 2j + rank (a tile beyond the batch is all padding); filter pass with a resident query tile only (dim <= 384).
+template <bool kPair>
 __global__ void __launch_bounds__(kSgThreads, 1)
 scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_rows, ScanGemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_sg[];
@@ -87,8 +97,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     uint8_t* smem_b = smem_a + kSgABytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kSgStages * kSgBBytes);
     uint64_t* full_bar = bars;                       // [stages]
-    uint64_t* empty_bar = full_bar + kSgStages;      // [stages]
-    uint64_t* a_full = empty_bar + kSgStages;        // [6]
+    constexpr int kNS = kPair ? kSgPairStages : kSgStages;  // row stages (kPair: half tiles, resident query tile only)
+    constexpr int kBStride = kPair ? kSgBBytes / 2 : kSgBBytes;
+    uint64_t* empty_bar = full_bar + kNS;            // [stages]
+    uint64_t* a_full = empty_bar + kNS;              // [6]
     uint64_t* a_empty = a_full + kSgMaxKB;           // [6]
     uint64_t* tmem_full = a_empty + kSgMaxKB;        // [2]
     uint64_t* tmem_empty = tmem_full + 2;            // [2]
@@ -97,21 +109,29 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int k_blocks = p.D / kSgBK;
-    const int n_qt = (p.Q + kSgQ - 1) / kSgQ;
+    const int n_qt_all = (p.Q + kSgQ - 1) / kSgQ;
     const bool stream_a = p.stream_a != 0;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const uint32_t widx = kPair ? cluster_id_x() : blockIdx.x;          // worker (CTA or CTA pair) index / count: row tiles are dealt to workers
+    const uint32_t nworkers = kPair ? cluster_nctaid_x() : gridDim.x;
+    const int n_qt = kPair ? (n_qt_all + 1) / 2 : n_qt_all;              // query-tile iterations; this CTA's tile of iteration j:
+    auto my_qt = [&](int j) { return kPair ? 2 * j + static_cast<int>(rank) : j; };
+    constexpr uint32_t kBLoadBytes = kPair ? kSgBBytes / 2 : kSgBBytes;  // row bytes this CTA loads per stage
+    constexpr int kRowsLoaded = kPair ? kSgRows / 2 : kSgRows;
     // resident mode: [query tile 96 KB][4 row stages of 32 KB]; streaming mode: 4 stages of [query k-block 16 KB | row k-block 32 KB]
     auto stage_a = [&](int stage) -> uint8_t* { return smem_sg + stage * kSgStreamStageBytes; };
-    auto stage_b = [&](int stage) -> uint8_t* { return stream_a ? smem_sg + stage * kSgStreamStageBytes + kSgABlockBytes : smem_b + stage * kSgBBytes; };
-    const uint32_t tiles_per_sb = gridDim.x * static_cast<uint32_t>(p.R);
+    auto stage_b = [&](int stage) -> uint8_t* { return stream_a ? smem_sg + stage * kSgStreamStageBytes + kSgABlockBytes : smem_b + stage * kBStride; };
+    const uint32_t tiles_per_sb = nworkers * static_cast<uint32_t>(p.R);
     const uint32_t n_sb = (p.n_tiles + tiles_per_sb - 1) / tiles_per_sb;
-    // tiles of this CTA in superblock sb: i = sb*tiles_per_sb + r*gridDim.x + blockIdx.x, r < R, while i < n_tiles
+    // tiles of this worker in superblock sb: i = sb*tiles_per_sb + r*nworkers + widx, r < R, while i < n_tiles
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_rows);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kSgStages; ++i) {
+        for (int i = 0; i < kNS; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
@@ -121,13 +141,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kSgEpiWarps);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty[i], kPair ? 2 * kSgEpiWarps : kSgEpiWarps);  // one arrive per epilogue warp (kPair: of both CTAs, on the leader's)
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_base_smem);
+    if (warp == 2) {
+        if constexpr (kPair) tmem_alloc_2sm<512>(tmem_base_smem);
+        else tmem_alloc<512>(tmem_base_smem);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / TMA completion
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_smem;
 
@@ -139,19 +163,24 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (uint32_t sb = 0; sb < n_sb; ++sb) {
                 for (int qt = 0; qt < n_qt; ++qt) {
                     for (int r = 0; r < p.R; ++r) {
-                        const uint32_t i = sb * tiles_per_sb + r * gridDim.x + blockIdx.x;
+                        const uint32_t i = sb * tiles_per_sb + r * nworkers + widx;
                         if (i >= p.n_tiles) break;
-                        const uint32_t row0 = sg_tile_of(p, i) * kSgRows;
+                        const uint32_t row0 = sg_tile_of(p, i) * kSgRows + rank * kRowsLoaded;  // kPair: this CTA's half of the row tile
                         for (int kb = 0; kb < k_blocks; ++kb) {
                             mbar_wait(&empty_bar[stage], phase ^ 1);
                             if (p.dbg & 4) {
-                                mbar_arrive(&full_bar[stage]);
+                                if (leader) mbar_arrive(&full_bar[stage]);
+                            } else if constexpr (kPair) {
+                                const uint32_t lbar = mapa_shared(smem_u32(&full_bar[stage]), 0);  // all bytes are counted on the leader's barrier
+                                if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kBLoadBytes + (stream_a ? kSgABlockBytes : 0)));
+                                if (stream_a) tma_load_2d_2sm(stage_a(stage), &tmap_q, lbar, kb * kSgBK, my_qt(qt) * kSgQ, kEvictLast);
+                                tma_load_2d_2sm(stage_b(stage), &tmap_rows, lbar, kb * kSgBK, static_cast<int32_t>(row0), kEvictNormal);
                             } else {
                                 mbar_arrive_expect_tx(&full_bar[stage], stream_a ? kSgStreamStageBytes : kSgBBytes);
                                 if (stream_a) tma_load_2d(stage_a(stage), &tmap_q, &full_bar[stage], kb * kSgBK, qt * kSgQ, kEvictLast);
                                 tma_load_2d(stage_b(stage), &tmap_rows, &full_bar[stage], kb * kSgBK, static_cast<int32_t>(row0), kEvictNormal);
                             }
-                            if (++stage == kSgStages) {
+                            if (++stage == kNS) {
                                 stage = 0;
                                 phase ^= 1;
                             }
@@ -166,31 +195,42 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (lane == 0 && !stream_a) {
             uint32_t ai = 0;
             for (uint32_t sb = 0; sb < n_sb; ++sb) {
-                if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;  // no tile of this CTA in the last superblock
+                if (sb * tiles_per_sb + widx >= p.n_tiles) break;  // no tile of this worker in the last superblock
                 for (int qt = 0; qt < n_qt; ++qt, ++ai) {
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         mbar_wait(&a_empty[kb], (ai & 1) ^ 1);
-                        mbar_arrive_expect_tx(&a_full[kb], kSgABlockBytes);
-                        tma_load_2d(smem_a + kb * kSgABlockBytes, &tmap_q, &a_full[kb], kb * kSgBK, qt * kSgQ, kEvictLast);
+                        if constexpr (kPair) {
+                            if (leader) mbar_arrive_expect_tx(&a_full[kb], 2 * kSgABlockBytes);
+                            tma_load_2d_2sm(smem_a + kb * kSgABlockBytes, &tmap_q, mapa_shared(smem_u32(&a_full[kb]), 0), kb * kSgBK, my_qt(qt) * kSgQ,
+                                            kEvictLast);
+                        } else {
+                            mbar_arrive_expect_tx(&a_full[kb], kSgABlockBytes);
+                            tma_load_2d(smem_a + kb * kSgABlockBytes, &tmap_q, &a_full[kb], kb * kSgBK, qt * kSgQ, kEvictLast);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer
-        if (KJ_MMA_UNIFORM != 0 || lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kSgQ, kSgRows);
+        if ((KJ_MMA_UNIFORM != 0 || lane == 0) && leader) {  // kPair: the leader issues for both CTAs
+            constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kPair ? 2 * kSgQ : kSgQ, kSgRows);
+            auto commit = [&](uint64_t* bar) {
+                if constexpr (kPair) umma_commit_2sm(bar, 3);  // the barrier at this offset in both CTAs
+                else umma_commit(bar);
+            };
             int stage = 0, it = 0;
             uint32_t phase = 0, ai = 0;
             for (uint32_t sb = 0; sb < n_sb; ++sb) {
-                if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;
+                if (sb * tiles_per_sb + widx >= p.n_tiles) break;
                 for (int qt = 0; qt < n_qt; ++qt, ++ai) {
                     for (int r = 0; r < p.R; ++r) {
-                        const uint32_t i = sb * tiles_per_sb + r * gridDim.x + blockIdx.x;
+                        const uint32_t i = sb * tiles_per_sb + r * nworkers + widx;
                         if (i >= p.n_tiles) break;
-                        const bool last_r = (r + 1 == p.R) || (i + gridDim.x >= p.n_tiles);
+                        const bool last_r = (r + 1 == p.R) || (i + nworkers >= p.n_tiles);
                         const int acc = it & 1;
-                        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                        if constexpr (kPair) mbar_wait_cluster(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // the peer's arrives are remote
+                        else mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t tmem_d = tmem_base + acc * kSgRows;
                         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -202,14 +242,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                             if (mma_issuer_lane()) {
                                 if (!(p.dbg & 2)) {
 #pragma unroll
-                                    for (int k = 0; k < kSgBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                    for (int k = 0; k < kSgBK / 16; ++k) {
+                                        if constexpr (kPair) umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                        else umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                                    }
                                 }
-                                umma_commit(&empty_bar[stage]);
-                                if (last_r && !stream_a) umma_commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
-                                if (kb == k_blocks - 1) umma_commit(&tmem_full[acc]);
+                                commit(&empty_bar[stage]);
+                                if (last_r && !stream_a) commit(&a_empty[kb]);  // this k-block of the query tile may be replaced
+                                if (kb == k_blocks - 1) commit(&tmem_full[acc]);
                             }
                             mma_issuer_sync();
-                            if (++stage == kSgStages) {
+                            if (++stage == kNS) {
                                 stage = 0;
                                 phase ^= 1;
                             }
@@ -227,16 +270,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const bool seed_mode = p.seed_max != nullptr;
         constexpr int kHalfCols = kSgRows / 2;  // 128
         int it = 0;
+        const uint32_t leader_empty[2] = {kPair ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u, kPair ? mapa_shared(smem_u32(&tmem_empty[1]), 0) : 0u};
         for (uint32_t sb = 0; sb < n_sb; ++sb) {
-            if (sb * tiles_per_sb + blockIdx.x >= p.n_tiles) break;
+            if (sb * tiles_per_sb + widx >= p.n_tiles) break;
             for (int qt = 0; qt < n_qt; ++qt) {
-                const int qi = qt * kSgQ + tq;
+                const int qi = my_qt(qt) * kSgQ + tq;
                 const bool live = qi < p.Q;
                 // rows must beat thr; padded lanes never pass
                 const float thr = live ? (p.thr0 != nullptr ? p.thr0[qi] : -INFINITY) : INFINITY;
                 float best = -INFINITY;  // seed mode, one group per CTA: running maximum over this CTA's sample tiles
                 for (int r = 0; r < p.R; ++r) {
-                    const uint32_t i = sb * tiles_per_sb + r * gridDim.x + blockIdx.x;
+                    const uint32_t i = sb * tiles_per_sb + r * nworkers + widx;
                     if (i >= p.n_tiles) break;
                     const int acc = it & 1;
                     const uint32_t ph = (it >> 1) & 1;
@@ -299,12 +343,15 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) {
+                        if constexpr (kPair) mbar_arrive_cluster_relaxed(leader_empty[acc]);  // "finished reading": no release needed (ptx.cuh)
+                        else mbar_arrive(&tmem_empty[acc]);
+                    }
                     ++it;
                 }
-                // one group per CTA and column half (2 * gridDim.x groups)
+                // one group per worker and column half (2 * nworkers groups)
                 if (seed_mode && !p.seed_chunks && live) {
-                    float* g = p.seed_max + static_cast<size_t>(blockIdx.x * 2 + half) * p.Q + qi;  // only this thread touches it
+                    float* g = p.seed_max + static_cast<size_t>(widx * 2 + half) * p.Q + qi;  // only this thread touches it
                     *g = sb == 0 ? best : fmaxf(*g, best);
                 }
             }
@@ -312,10 +359,12 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();  // peer shared memory / barriers stay valid until both CTAs are done
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        if constexpr (kPair) tmem_dealloc_2sm<512>(tmem_base);
+        else tmem_dealloc<512>(tmem_base);
     }
 }
 
