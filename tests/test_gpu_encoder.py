@@ -315,6 +315,28 @@ def test_chained_launch_variants_agree(dirs, monkeypatch):
         assert np.array_equal(a, d), (pair, ts)
 
 
+def test_gemm_cta_pair_variants_agree(dirs, monkeypatch):
+    """The stand-alone QKV / FFN-up projections run as CTA pairs by default (gemm_tcgen05_kernel<BN, EPI, true>, KJC_GEMM_PAIR = 3); one CTA
+    per tile for either or both must give the same logits bit for bit on a hidden-768 model (every projection of every layer), and
+    the same embeddings on MiniLM-L6 (layer 0's QKV)."""
+    for arch, B, S in (("distilbert-sst2", 20, 128), ("minilm-l6", 24, 128)):
+        if arch not in dirs:
+            pytest.skip(f"{arch} fixture not built")
+        ids, mask, _ = synth.synth_tokens(B, S, synth.ARCHS[arch][5], regime="P", seed=41)
+        outs = []
+        for pair in (None, "0", "1", "2"):
+            if pair is None:
+                monkeypatch.delenv("KJC_GEMM_PAIR", raising=False)
+            else:
+                monkeypatch.setenv("KJC_GEMM_PAIR", pair)
+            m = api.EncoderModel(dirs[arch])
+            outs.append(m.predict_logits(ids, mask) if synth.ARCHS[arch][8] > 0 else m.encode_batch_from_ids(ids, mask))
+            m.close()
+        for o in outs[1:]:
+            assert np.array_equal(outs[0], o)
+        assert np.isfinite(outs[0]).all()
+
+
 def test_host_call_chunking_is_invisible(dirs):
     """kjc_encoder_forward stages large batches through pinned memory in chunks of two micro-batches overlapped with the GPU
     work; the rows must equal those of small calls bit for bit, in order, including the last partial chunk."""
