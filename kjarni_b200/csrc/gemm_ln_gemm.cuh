@@ -67,7 +67,7 @@ static_assert(kLg2WBytes + 6 * kLg2WideBytes <= kLnBBytes && kLg2WideBytes <= kL
 static_assert(2 * kLg2WBytes <= 3 * kLnABytes && kLg2WBytes + kLnEpiWarps * kEpiStageBytes <= kLnBBytes, "phase-2 aliasing");
 // kTS (phase 2 takes its A operand from TENSOR MEMORY): tiles of 128 columns, five 16 KB W2 stages
 #ifndef KJ_LG_EARLY
-#define KJ_LG_EARLY 0  // kPair: weight halves of the first stages before griddepcontrol.wait, residual chunks before the accumulator is
+#define KJ_LG_EARLY 0  // kPair: bit 0 = weight halves of the first stages before griddepcontrol.wait, bit 1 = residual chunks before the accumulator is
                        // complete.  Measured 1.2 % SLOWER in the whole step (262-263 vs 266 k emb/s): the early loads compete with the
                        // predecessor's tail and with phase 1 for the same L2 bandwidth.  Compiled out.
 #endif
@@ -235,7 +235,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (threadIdx.x == 0) KJ_LGT(0);
     // kPair: the producer thread requests the WEIGHT halves of the first phase-1 stages before it waits for the predecessor grid (they
     // do not depend on it; the activations of the same stages follow after the wait and complete the same barriers)
-    constexpr bool kEarlyW = kPair && P1 == 0 && KJ_LG_EARLY != 0;
+    constexpr bool kEarlyW = kPair && P1 == 0 && (KJ_LG_EARLY & 1) != 0;
     const int early_w = kEarlyW ? (k_blocks1 < kStages1 ? k_blocks1 : kStages1) : 0;
     if (kEarlyW && threadIdx.x == 0) {
         for (int st = 0; st < early_w; ++st) {
@@ -490,11 +490,11 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     __syncwarp();
                 };
-                if constexpr (kPair && KJ_LG_EARLY != 0) request_residual();  // staging of its own: in flight while phase 1 runs
+                if constexpr (kPair && (KJ_LG_EARLY & 2) != 0) request_residual();  // staging of its own: in flight while phase 1 runs
                 mbar_wait(tmem_full1, 0);
                 if (ew == 0 && lane == 0) KJ_LGT(5);
                 tc_fence_after();
-                if constexpr (!(kPair && KJ_LG_EARLY != 0)) request_residual();  // staging aliased on the ring: free once every phase-1 MMA has retired
+                if constexpr (!(kPair && (KJ_LG_EARLY & 2) != 0)) request_residual();  // staging aliased on the ring: free once every phase-1 MMA has retired
 #pragma unroll 1
                 for (int c = 0; c < kChunks; ++c) {
                     const int b = c & 1;
