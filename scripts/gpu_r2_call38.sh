@@ -10,6 +10,6 @@ python -c "
 import json
 d=json.load(open('gpurun_out/r2c38_bench_2gpu.json'))
 print('2gpu', d['value'], d['e2e']['value'], d['n_gpus'], d.get('index_topk',{}).get('value'))" >> $O 2>&1
-timeout 600 python scripts/inproc_bench.py 2 > gpurun_out/r2c38_inproc_2gpu.json 2> gpurun_out/r2c38_inproc.err
+timeout 600 python scripts/inproc_bench.py --gpus 2 > gpurun_out/r2c38_inproc_2gpu.json 2> gpurun_out/r2c38_inproc.err
 tail -c 800 gpurun_out/r2c38_inproc_2gpu.json >> $O
 cat $O
