@@ -350,9 +350,12 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (lane == 0 && nb < 12) KJ_LGT(16 + 2 * nb);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (kTS ? kLgTAcc0 : 0) + acc * kBN2;
+                [[maybe_unused]] long long tw_wait = 0;  // KJ_LG_TRACE: clocks this tile spent waiting for W2 stages
                 for (int kb = 0; kb < kLg2KB; ++kb, ++it) {
                     const int s = it % kStages2;
+                    [[maybe_unused]] const long long tw0 = KJ_LG_TRACE ? clock64() : 0;
                     mbar_wait(&full2[s], (it / kStages2) & 1);
+                    if (KJ_LG_TRACE) tw_wait += clock64() - tw0;
                     tc_fence_after();
                     const uint64_t db = umma_desc_k_sw128(smem_u32(w2_stage(s)));
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_x + kb * kLnABytes));
@@ -372,7 +375,10 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (kb == kLg2KB - 1) commit(&acc_full[acc]);
                     }
                     mma_issuer_sync();
-                    if (kb == kLg2KB - 1 && lane == 0 && nb < 12) KJ_LGT(17 + 2 * nb);
+                    if (kb == kLg2KB - 1 && lane == 0 && nb < 12) {
+                        KJ_LGT(17 + 2 * nb);
+                        if (KJ_LG_TRACE && p.trace != nullptr) p.trace[blockIdx.x * 256 + 112 + nb] = p.trace[blockIdx.x * 256] + static_cast<unsigned long long>(tw_wait);  // printed relative to slot 0
+                    }
                 }
             }
         }

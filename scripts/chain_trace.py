@@ -2,7 +2,7 @@
 Slots: 1 pdl_wait done | 2 first phase-1 operands | 3 phase-1 MMAs issued | 5 accumulator complete | 6 LN pass A | 7 statistics barrier |
 8 x' published | 4 MMA warp sees x' | 16+2nb / 17+2nb MMA warp: accumulator free / tile nb issued | 48+8nb.. (warp 4) and 128+8nb.. (warp 11):
 +0 accumulator full, +1 chunk 0 loaded, +2 chunk 0 math, +3 staging free, +4 chunk 1 loaded, +5 chunk 1 math, +6 fence, +7 store issued |
-200+it producer: stage free, W2 load issued | 255 exit."""
+200+it producer: stage free, W2 load issued | 112+nb clocks the MMA warp waited for W2 stages in tile nb | 255 exit."""
 import ctypes as C, os, sys
 sys.path.insert(0, ".")
 import numpy as np
