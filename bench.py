@@ -52,7 +52,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md).  The poller is started BEFORE the warm-up
+    steps -- nvidia-smi's start-up (NVML initialisation, first query) stalls kernel launches for milliseconds, which belongs into the
+    warm-up, not into a 50-150 ms timed region -- and `stop(t0, t1)` keeps the samples whose arrival time lies inside the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -65,14 +67,17 @@ class ClockSampler:
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_wait = time.time() + 3.0  # the first sample has arrived = the poller's start-up is over
+            while not self.rows and time.time() < t_wait and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +87,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if t0 is None or (t0 <= t <= t1 + 0.15)]  # a sample is reported up to one period after it was taken
+        if not rows:  # timed region shorter than one sampling period: the samples closest to it (taken under the same load, in the warm-up)
+            rows = [r for _, r in self.rows[-2:]]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -287,19 +295,21 @@ def main():
                                                      out_d.data_ptr(), stream))
 
     # ---------------------------------------------------------------- value: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step_dev()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     barrier()
     ms = max_over_ranks(ms)
     launches_per_step = enc.last_launch_count
