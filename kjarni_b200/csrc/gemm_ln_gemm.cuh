@@ -617,11 +617,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (bias2_in_smem && col0 + 32 <= p.N2) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 b = *reinterpret_cast<const float4*>(s_bias2 + col0 + 4 * j);
-                                f[4 * j + 0] += b.x;
-                                f[4 * j + 1] += b.y;
-                                f[4 * j + 2] += b.z;
-                                f[4 * j + 3] += b.w;
+                                add_bias4(f + 4 * j, *reinterpret_cast<const float4*>(s_bias2 + col0 + 4 * j));
                             }
                         } else if (p.bias2 != nullptr) {
 #pragma unroll
@@ -680,11 +676,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (bias2_in_smem && col0 + 32 <= p.N2) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 b = *reinterpret_cast<const float4*>(s_bias2 + col0 + 4 * j);
-                                f[4 * j + 0] += b.x;
-                                f[4 * j + 1] += b.y;
-                                f[4 * j + 2] += b.z;
-                                f[4 * j + 3] += b.w;
+                                add_bias4(f + 4 * j, *reinterpret_cast<const float4*>(s_bias2 + col0 + 4 * j));
                             }
                         } else if (p.bias2 != nullptr) {
 #pragma unroll
