@@ -210,13 +210,15 @@ unsigned long long* g_lg_trace = nullptr;  // KJ_LG_TRACE builds: stamp buffer o
 // pair: two CTAs per cluster share every weight tile (tcgen05.mma.cta_group::2); tw / tw2 must then have 96-row boxes.
 void launch_gemm_ln_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& t_res, const CUtensorMap& t_x, const CUtensorMap& tw2,
                          const CUtensorMap& t_out2, int M, int K1, const float* bias1, const float* gamma, const float* beta, float eps, int N2,
-                         const float* bias2, int epi2, int act, cudaStream_t st, bool pair = false, bool ts = false, int dbg = 0) {
+                         const float* bias2, int epi2, int act, cudaStream_t st, bool pair = false, bool ts = false, int dbg = 0, int tile_base = 0,
+                         int tile_count = -1) {
     static int configured_act[64] = {0}, configured_plain[64] = {0}, configured_act2[64] = {0}, configured_plain2[64] = {0};  // per instantiation
     static int configured_act_ts[64] = {0}, configured_plain_ts[64] = {0};
     if (K1 % 8 != 0 || N2 % 8 != 0) throw Error(KJC_INVALID_CONFIG, "GEMM needs K % 8 == 0 and N % 8 == 0");
-    GemmLnGemmParams p;
+    GemmLnGemmParams p{};
     p.M = M; p.K1 = K1; p.bias1 = bias1; p.gamma = gamma; p.beta = beta; p.eps = eps; p.N2 = N2; p.bias2 = bias2; p.act = act; p.dbg = dbg; p.trace = g_lg_trace;
-    const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    p.tile_base = tile_base;
+    const int m_tiles = tile_count >= 0 ? tile_count : (M + kGemmBlockM - 1) / kGemmBlockM;  // tiles of this launch
     if (pair) {
         const int ctas = 2 * ((m_tiles + 1) / 2);  // whole clusters; a tile beyond M is all padding (loads zero-filled, stores clipped)
         if (epi2 == EPI_BIAS_ACT_BF16) {
@@ -872,11 +874,14 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
     const bool precise = fp32_residual_for(o);
     if (precise) ensure_fp32_stream(w);
     const bool fused_ln = fused_ln_ && !precise;
-    // chained launches need one 128-row tile per CTA
-    const bool chain = chain_ && !precise && !pair_gemm_ && (M + kGemmBlockM - 1) / kGemmBlockM <= sms;
+    // chained launches run one 128-row tile per CTA: a micro-batch of more tiles than SMs takes them in row chunks of `chunk_tiles`
+    // (attention, the embedding and the output kernel still cover the whole micro-batch in one launch each)
+    const bool chain = chain_ && !precise && !pair_gemm_;
+    const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    const int chunk_tiles = std::max(2, sms & ~1);
     // the embedding front end of the chained kernel is bit-identical but measured slower than the two launches (12 gathering warps
     // per SM are latency-bound: 50 us against 17 + 27 us), so it stays opt-in (KJC_CHAIN_EMBED)
-    const bool chain_embed = chain && chain_embed_ && !layers_.empty();
+    const bool chain_embed = chain && chain_embed_ && !layers_.empty() && m_tiles <= sms;
     {
         EmbedParams e;
         e.ids = d_ids; e.type_ids = d_types; e.word = word_; e.pos = pos_; e.type = type_; e.gamma = emb_g_; e.beta = emb_b_;
@@ -920,30 +925,43 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         launch_attention(a, d, st);
         prof_end(st);
         if (chain) {
-            // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
-            prof_begin(KJC_K_GEMM_FFN_UP, st);
+            const bool last = li + 1 == layers_.size();
             const bool pair_up = (chain_pair_mask_ & 2) != 0, ts_up = chain_ts_ && !pair_up;
-            launch_gemm_ln_gemm(w.t_ctx16, pair_up ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, pair_up ? L.t_w1_96 : (ts_up ? L.t_w1_128 : L.t_w1_192),
-                                ts_up ? w.t_h16_out32 : w.t_h16_out64, M, H, L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, pair_up, ts_up);
-            prof_end(st);
-            // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
-            prof_begin(KJC_K_GEMM_FFN_DOWN, st);
-            if (li + 1 < layers_.size()) {
-                const LayerDev& Ln = layers_[li + 1];
-                const bool pair_dn = (chain_pair_mask_ & 1) != 0, ts_dn = chain_ts_ && !pair_dn;
-                launch_gemm_ln_gemm(w.t_h16, pair_dn ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
-                                    pair_dn ? Ln.t_wqkv_96 : (ts_dn ? Ln.t_wqkv_128 : Ln.t_wqkv_192), ts_dn ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 3 * H,
-                                    Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, pair_dn, ts_dn);
-            } else if ((chain_pair_mask_ & 1) != 0 && last_ln_pair_) {
-                // last layer, opt-in (KJC_LAST_LN_PAIR): the same CTA-pair launch with an empty second projection (N2 = 0: no phase-2 tiles).
-                // Bit-identical; measured 0.5 % slower in the whole step than gemm_ln_kernel<1> (268.9 vs 270.2 k emb/s), so not the default
-                launch_gemm_ln_gemm(w.t_h16, L.t_w2_96, w.t_x16_io, w.t_x16, L.t_wqkv_96, w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 0, nullptr, EPI_BIAS_BF16,
-                                    ACT_NONE, st, true, false);
-            } else {
-                launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
+            const bool pair_dn = (chain_pair_mask_ & 1) != 0, ts_dn = chain_ts_ && !pair_dn;
+            for (int t0 = 0; t0 < m_tiles; t0 += chunk_tiles) {
+                const int tn = std::min(chunk_tiles, m_tiles - t0);
+                // x = LN1(x + ctx Wo^T + bo) ; t = act(x W1^T + b1)          (encoder_layer.rs:120-147, standard_new.rs:47-73)
+                prof_begin(KJC_K_GEMM_FFN_UP, st);
+                launch_gemm_ln_gemm(w.t_ctx16, pair_up ? L.t_wo_96 : L.t_wo_ln, w.t_x16_io, w.t_x16, pair_up ? L.t_w1_96 : (ts_up ? L.t_w1_128 : L.t_w1_192),
+                                    ts_up ? w.t_h16_out32 : w.t_h16_out64, M, H, L.bo, L.g1, L.be1, eps, I, L.b1, EPI_BIAS_ACT_BF16, act_, st, pair_up, ts_up, 0, t0, tn);
+                prof_end(st);
+                ++launches_;
+                // x = LN2(x + t W2^T + b2) ; next layer's Q|K|V              (standard_new.rs:76-79, encoder_layer.rs:150-176, qkv_projection.rs:93-138)
+                if (!last) {
+                    const LayerDev& Ln = layers_[li + 1];
+                    prof_begin(KJC_K_GEMM_FFN_DOWN, st);
+                    launch_gemm_ln_gemm(w.t_h16, pair_dn ? L.t_w2_96 : L.t_w2_ln, w.t_x16_io, w.t_x16,
+                                        pair_dn ? Ln.t_wqkv_96 : (ts_dn ? Ln.t_wqkv_128 : Ln.t_wqkv_192), ts_dn ? w.t_qkv16_out32 : w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps,
+                                        3 * H, Ln.bqkv, EPI_BIAS_BF16, ACT_NONE, st, pair_dn, ts_dn, 0, t0, tn);
+                    prof_end(st);
+                    ++launches_;
+                } else if (pair_dn && last_ln_pair_) {
+                    // last layer, opt-in (KJC_LAST_LN_PAIR): the same CTA-pair launch with an empty second projection (N2 = 0: no phase-2 tiles).
+                    // Bit-identical; measured 0.5 % slower in the whole step than gemm_ln_kernel<1> (268.9 vs 270.2 k emb/s), so not the default
+                    prof_begin(KJC_K_GEMM_FFN_DOWN, st);
+                    launch_gemm_ln_gemm(w.t_h16, L.t_w2_96, w.t_x16_io, w.t_x16, L.t_wqkv_96, w.t_qkv16_out64, M, I, L.b2, L.g2, L.be2, eps, 0, nullptr, EPI_BIAS_BF16,
+                                        ACT_NONE, st, true, false, 0, t0, tn);
+                    prof_end(st);
+                    ++launches_;
+                }
             }
-            prof_end(st);
-            launches_ += 3;
+            if (last && !(pair_dn && last_ln_pair_)) {
+                prof_begin(KJC_K_GEMM_FFN_DOWN, st);
+                launch_gemm_ln(w.t_h16, L.t_w2_ln, w.t_x16_io, M, H, I, L.b2, L.g2, L.be2, eps, sms, st);
+                prof_end(st);
+                ++launches_;
+            }
+            ++launches_;  // attention
             continue;
         }
         // y = x + ctx Wo^T + bo ; x = LN1(y)                       (encoder_layer.rs:120-147)

@@ -97,6 +97,8 @@ __host__ __device__ constexpr uint32_t lg_x_tmem_col(int part) { return part == 
 
 struct GemmLnGemmParams {
     int M, K1;
+    int tile_base;       // first 128-row tile of this launch (even for CTA pairs): a micro-batch wider than one tile per SM runs as
+                         // several launches over consecutive row chunks of the same tensors
     const float* bias1;  // [384] or nullptr
     const float* gamma;  // [384]
     const float* beta;   // [384]
@@ -183,7 +185,7 @@ gemm_ln_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;  // one 128-row tile per CTA
+    const int tile = p.tile_base + blockIdx.x;  // one 128-row tile per CTA; a launch covers tiles [tile_base, tile_base + gridDim.x)
     const int k_blocks1 = (p.K1 + kGemmBlockK - 1) / kGemmBlockK;
     const int n2_tiles = (p.N2 + kBN2 - 1) / kBN2;
     const bool bias2_in_smem = p.bias2 != nullptr && p.N2 <= kLg2BiasMax;

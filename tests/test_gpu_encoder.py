@@ -315,6 +315,32 @@ def test_chained_launch_variants_agree(dirs, monkeypatch):
         assert np.array_equal(a, d), (pair, ts)
 
 
+def test_micro_batch_wider_than_one_tile_per_sm(dirs, monkeypatch):
+    """A micro-batch of more 128-row tiles than SMs runs its chained launches over consecutive row chunks (tile_base) while attention,
+    the embedding and the pooling kernel cover the whole micro-batch at once: every op is local to a sequence, so the embeddings must be
+    the same bits whatever KJC_MICRO_TOKENS is (one tile per SM, two and a half, four)."""
+    import torch
+    arch = "minilm-l6"
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 2 * sms + 37  # ragged: the last chunk holds an odd number of tiles
+    ids, mask, _ = synth.synth_tokens(B, 128, synth.ARCHS[arch][5], regime="P", seed=53)
+    outs = {}
+    for tokens in (None, str(sms * 128 * 5 // 2), str(sms * 128 * 4)):
+        if tokens is None:
+            monkeypatch.setenv("KJC_MICRO_TOKENS", str(sms * 128))
+        else:
+            monkeypatch.setenv("KJC_MICRO_TOKENS", tokens)
+        m = api.EncoderModel(dirs[arch])
+        assert N.lib().kjc_encoder_chained(m._h) == 1
+        outs[tokens] = m.encode_batch_from_ids(ids, mask)
+        m.close()
+    monkeypatch.delenv("KJC_MICRO_TOKENS")
+    for k, v in outs.items():
+        assert np.array_equal(outs[None], v), k
+    want = ko.embed(ko.load_model_dir(dirs[arch]), ids[-2:], mask[-2:])
+    assert cosine_rows(outs[None][-2:], want).min() >= COS_MIN
+
+
 def test_gemm_cta_pair_variants_agree(dirs, monkeypatch):
     """The stand-alone QKV / FFN-up projections run as CTA pairs by default (gemm_tcgen05_kernel<BN, EPI, true>, KJC_GEMM_PAIR = 3); one CTA
     per tile for either or both must give the same logits bit for bit on a hidden-768 model (every projection of every layer), and
