@@ -777,6 +777,8 @@ Encoder::Encoder(const std::string& dir, int device) {
         chain_ts_ = chain_ && (e == nullptr ? KJ_CHAIN_TS_DEFAULT != 0 : atoi(e) != 0);
     }
     if (const char* e = getenv("KJC_FP32_RESIDUAL")) set_fp32_residual(atoi(e));
+    chain_min_tiles_ = num_sms_ / 2 + 1;
+    if (const char* e = getenv("KJC_CHAIN_MIN_TILES")) chain_min_tiles_ = atoi(e);
     const char* env = getenv("KJC_MICRO_TOKENS");
     micro_tokens_ = env ? std::max(128, atoi(env)) : num_sms_ * 128;
     lanes_ = 1;  // measured: no gain from concurrent lanes (the kernels are epilogue-issue-bound, not launch-latency-bound)
@@ -876,8 +878,11 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
     const bool fused_ln = fused_ln_ && !precise;
     // chained launches run one 128-row tile per CTA: a micro-batch of more tiles than SMs takes them in row chunks of `chunk_tiles`
     // (attention, the embedding and the output kernel still cover the whole micro-batch in one launch each)
-    const bool chain = chain_ && !precise && !pair_gemm_;
     const int m_tiles = (M + kGemmBlockM - 1) / kGemmBlockM;
+    // ... and pay off only when most SMs own a tile: a chained launch keeps a tile's two projections on ONE SM (or CTA pair), so a batch
+    // of 32 x 128 tokens occupies 32 SMs for the whole layer, while the stand-alone QKV / FFN-up GEMMs spread their column tiles over
+    // every SM.  Measured (scripts/c1_latency_ab.py): 32 tiles 366 -> 327 us per forward, 8 tiles 342 -> 284 us, 64 tiles 397 -> 390 us
+    const bool chain = chain_ && !precise && !pair_gemm_ && m_tiles >= chain_min_tiles_;
     const int chunk_tiles = std::max(2, sms & ~1);
     // the embedding front end of the chained kernel is bit-identical but measured slower than the two launches (12 gathering warps
     // per SM are latency-bound: 50 us against 17 + 27 us), so it stays opt-in (KJC_CHAIN_EMBED)

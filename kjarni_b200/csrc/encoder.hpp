@@ -174,6 +174,7 @@ class Encoder {
     KjcEncoderInfo info_{};
     std::vector<std::string> labels_;
     int num_sms_ = 0, act_ = 0, micro_tokens_ = 0;
+    int chain_min_tiles_ = 0;  // micro-batches of fewer 128-row tiles take one kernel per op (KJC_CHAIN_MIN_TILES)
     int bn_qkv_ = 0, bn_h_ = 0, bn_i_ = 0;
     std::mutex mu_;
     cudaStream_t stream_ = nullptr;

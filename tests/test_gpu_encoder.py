@@ -341,6 +341,31 @@ def test_micro_batch_wider_than_one_tile_per_sm(dirs, monkeypatch):
     assert cosine_rows(outs[None][-2:], want).min() >= COS_MIN
 
 
+def test_small_batches_take_one_kernel_per_op(dirs, monkeypatch):
+    """Default dispatch (no KJC_CHAIN_MIN_TILES): a batch of 32 x 128 tokens (32 tiles, the latency case of BASELINE configs[0]) runs one
+    kernel per op -- 5 launches per layer instead of 3 -- and a full micro-batch runs the chained launches; both give the bits of the
+    forced-chained form."""
+    import torch
+    arch = "minilm-l6"
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for B in (32, sms):
+        ids, mask, _ = synth.synth_tokens(B, 128, synth.ARCHS[arch][5], regime="P", seed=59)
+        monkeypatch.setenv("KJC_CHAIN_MIN_TILES", "0")
+        m = api.EncoderModel(dirs[arch])
+        forced = m.encode_batch_from_ids(ids, mask)
+        n_forced = m.last_launch_count
+        m.close()
+        monkeypatch.delenv("KJC_CHAIN_MIN_TILES")
+        m = api.EncoderModel(dirs[arch])
+        layers = m.info.num_layers
+        default = m.encode_batch_from_ids(ids, mask)
+        n_default = m.last_launch_count
+        m.close()
+        assert np.array_equal(forced, default), B
+        assert n_forced == 3 + 3 * layers, (B, n_forced)  # embed, layer-0 QKV, pool + (attention, two chained launches) per layer
+        assert n_default == (2 + 5 * layers if B == 32 else n_forced), (B, n_default)
+
+
 def test_gemm_cta_pair_variants_agree(dirs, monkeypatch):
     """The stand-alone QKV / FFN-up projections run as CTA pairs by default (gemm_tcgen05_kernel<BN, EPI, true>, KJC_GEMM_PAIR = 3); one CTA
     per tile for either or both must give the same logits bit for bit on a hidden-768 model (every projection of every layer), and
