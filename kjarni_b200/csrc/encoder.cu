@@ -1227,6 +1227,28 @@ void Encoder::forward_host(const uint32_t* ids, const float* mask, const uint32_
     oc.mask_convention = resolve_noalloc(B, S, o) ? KJC_MASK_NOALLOC : KJC_MASK_ALLOC;
     const int chunk = std::max(1, 2 * micro_batch(S));
     const int n_chunks = (B + chunk - 1) / chunk;
+    if (n_chunks == 1) {
+        // One chunk (the latency case): nothing to overlap, so everything goes on the compute stream -- one H2D of the contiguous
+        // ids | mask | types span, the kernels, the D2H of the rows and of the error flag, one synchronise -- instead of three streams
+        // and four event hops (~35 us of a 0.38 ms call at 32 x 128 tokens).
+        memcpy(hs, ids, T * 4);
+        if (mask) memcpy(hs + T, mask, T * 4);
+        if (types) memcpy(hs + 2 * T, types, T * 4);
+        const size_t span = types ? 3 * T : (mask ? 2 * T : T);
+        KJ_CUDA(cudaMemcpyAsync(d_in_, hs, span * 4, cudaMemcpyHostToDevice, stream_));
+        forward_batches(d_ids, d_mask, d_types, B, S, oc, d_out_, stream_);
+        KJ_CUDA(cudaMemcpyAsync(h_stage_out_, d_out_, out_elems * 4, cudaMemcpyDeviceToHost, stream_));
+        KJ_CUDA(cudaMemcpyAsync(&err_host_, d_err_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+        KJ_CUDA(cudaStreamSynchronize(stream_));
+        if (err_host_) {
+            KJ_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), stream_));
+            KJ_CUDA(cudaStreamSynchronize(stream_));
+            throw Error(KJC_INFERENCE_FAILED, "Token type ID out of range");
+        }
+        if (sink) (*sink)(h_stage_out_, 0, static_cast<size_t>(B));
+        else memcpy(out, h_stage_out_, out_elems * 4);
+        return;
+    }
     if (!s_in_) {
         KJ_CUDA(cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking));
         KJ_CUDA(cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking));
