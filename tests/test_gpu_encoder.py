@@ -226,6 +226,9 @@ def test_edge_cases(dirs):
     with pytest.raises(N.KjarniCudaError) as e:
         enc.forward_tokens(ids, mask, np.full_like(ids, 9))  # token-type id out of range: the reference panics
     assert e.value.status == 5
+    # the device-side error flag is cleared by the failing call: the handle keeps working
+    again = enc._forward(ids, mask, None, N.OUT_POOLED, N.POOL_MEAN, True, N.MASK_ALLOC)
+    assert cosine_rows(again, want).min() >= COS_MIN
     enc.close()
     with pytest.raises(N.KjarniCudaError) as e:
         api.EncoderModel("/nonexistent/dir")
