@@ -24,6 +24,7 @@ struct AttnParams {
     int max_ctas = 0;          // persistent tcgen05 kernel: CTAs to launch (0 = one per SM)
     int dbg = 0;               // probes (KJC_ATTN_DBG through kjc_dbg_attention): 1 = TMA loads only (no MMA, no softmax)
     unsigned long long* trace = nullptr;  // optional [gridDim.x][64] %globaltimer stamps (KJC_ATTN_TRACE, dbg_attention)
+    int ld_qkv = 0;            // row pitch of qkv in elements (0 = 3H); attention_ts only: the encoder lays qkv rows over the FFN rows (pitch I)
 };
 
 constexpr int kAttnThreads = 256;

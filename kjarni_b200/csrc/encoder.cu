@@ -354,13 +354,14 @@ template <int D, int NKB>
 static void launch_attention_ts(const AttnParams& p, cudaStream_t st) {
     using Cfg = AtsCfg<D, NKB>;
     static int configured[64] = {0};
-    struct Key { const void *q, *c; int B, S, H; };
-    static thread_local Key key{nullptr, nullptr, 0, 0, 0};
+    struct Key { const void *q, *c; int B, S, H, ld; };
+    static thread_local Key key{nullptr, nullptr, 0, 0, 0, 0};
     static thread_local CUtensorMap t_qkv, t_ctx;
-    if (key.q != p.qkv || key.c != p.ctx || key.B != p.B || key.S != p.S || key.H != p.H) {
-        t_qkv = make_tmap_3d(p.qkv, 2, 3 * static_cast<uint64_t>(p.H), p.S, p.B, D, 128, D * 2);
+    const int ld = p.ld_qkv > 0 ? p.ld_qkv : 3 * p.H;
+    if (key.q != p.qkv || key.c != p.ctx || key.B != p.B || key.S != p.S || key.H != p.H || key.ld != ld) {
+        t_qkv = make_tmap_3d(p.qkv, 2, static_cast<uint64_t>(ld), p.S, p.B, D, 128, D * 2);
         t_ctx = make_tmap_3d(p.ctx, 2, p.H, p.S, p.B, D, 32, D * 2);
-        key = Key{p.qkv, p.ctx, p.B, p.S, p.H};
+        key = Key{p.qkv, p.ctx, p.B, p.S, p.H, ld};
     }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -395,6 +396,7 @@ void launch_attention(const AttnParams& p, int D, cudaStream_t st) {
         KJ_CUDA(cudaGetLastError());
         return;
     }
+    if (p.ld_qkv > 0 && p.ld_qkv != 3 * p.H) throw Error(KJC_INVALID_CONFIG, "only attention_ts takes a pitched qkv");
     if (variant <= 1 && p.S <= kAtcS && (D == 32 || D == 64) && (p.H % 8 == 0)) {
         if (D == 32) launch_attention_tc<32>(p, st);
         else launch_attention_tc<64>(p, st);
@@ -777,6 +779,7 @@ Encoder::Encoder(const std::string& dir, int device) {
         chain_ts_ = chain_ && (e == nullptr ? KJ_CHAIN_TS_DEFAULT != 0 : atoi(e) != 0);
     }
     if (const char* e = getenv("KJC_FP32_RESIDUAL")) set_fp32_residual(atoi(e));
+    alias_qkv_ = getenv("KJC_NO_ALIAS_QKV") == nullptr;
     chain_min_tiles_ = num_sms_ / 2 + 1;
     if (const char* e = getenv("KJC_CHAIN_MIN_TILES")) chain_min_tiles_ = atoi(e);
     const char* env = getenv("KJC_MICRO_TOKENS");
@@ -816,6 +819,7 @@ Encoder::~Encoder() {
 }
 
 void Encoder::free_workspace(Workspace& w) {
+    if (w.qkv16 == w.h16) w.qkv16 = nullptr;  // aliased (ensure_workspace)
     for (void* p : {(void*)w.y32, (void*)w.x32, (void*)w.x16, (void*)w.qkv16, (void*)w.ctx16, (void*)w.h16, (void*)w.head32})
         if (p) cudaFree(p);
     w.y32 = w.x32 = nullptr; w.x16 = w.qkv16 = w.ctx16 = w.h16 = nullptr;
@@ -834,9 +838,24 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     const int H = info_.hidden_size, I = info_.intermediate_size;
     if (!fused_ln_) KJ_CUDA(cudaMalloc(&w.y32, T * H * 4));  // pre-LayerNorm sums of the unfused path (fp32-residual mode allocates lazily)
     KJ_CUDA(cudaMalloc(&w.x16, T * H * 2));
-    KJ_CUDA(cudaMalloc(&w.qkv16, T * 3 * H * 2));
     KJ_CUDA(cudaMalloc(&w.ctx16, T * H * 2));
     KJ_CUDA(cudaMalloc(&w.h16, T * I * 2));
+    // Q|K|V of a row are dead once attention has run and the FFN activations of a row are dead once FFN-down has read them, and every
+    // kernel that writes one of them for a row tile has finished reading the other for that tile (the chained FFN-down launch stores QKV
+    // only after all phase-1 MMAs -- the readers of h -- have retired).  So row r of qkv lives in the first 3H elements of row r of h
+    // (pitch I): a layer's working set drops from 131 MB to 87 MB per 148 sequences and the dead tensor is overwritten in L2 instead of
+    // being written back to HBM (ncu --cache-control none: 138 MB of DRAM writes per layer before).  Needs the pitched attention_ts.
+    {
+        const int d = H / std::max(1, info_.num_heads);
+        const bool ts_attention = attention_variant() == 0 && (d == 32 || d == 64) && H % 8 == 0;
+        if (alias_qkv_ && ts_attention && I >= 3 * H) {
+            w.qkv16 = w.h16;
+            w.qkv_ld = I;
+        } else {
+            KJ_CUDA(cudaMalloc(&w.qkv16, T * 3 * H * 2));
+            w.qkv_ld = 3 * H;
+        }
+    }
     if (w_pre_) KJ_CUDA(cudaMalloc(&w.head32, T * H * 4));  // pre-classifier output, at most one sequence per token
     // stale rows beyond the live token count are read by TMA (results discarded): keep them finite
     KJ_CUDA(cudaMemsetAsync(w.x16, 0, T * H * 2, w.stream));
@@ -847,11 +866,11 @@ void Encoder::ensure_workspace(Workspace& w, int tokens) {
     w.t_ctx16 = make_tmap_2d(w.ctx16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, H, kGemmBlockM, kGemmBlockK, 128);
     w.t_h16 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, kGemmBlockM, kGemmBlockK, 128);
     // store boxes: 192-column tiles store 32 x 64 parts (128B swizzle), the other widths 32 x 32 chunks (64B swizzle)
-    w.t_qkv16_out = (gemm_wide_store(bn_qkv_) || (bn_qkv_ == 192 && pair_gemm_)) ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128)
-                                   : make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);
-    w.t_qkv16_out32 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, kEpiChunkCols, 64);  // CTA-pair kernel
+    w.t_qkv16_out = (gemm_wide_store(bn_qkv_) || (bn_qkv_ == 192 && pair_gemm_)) ? make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, w.qkv_ld, 32, 64, 128)
+                                   : make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, w.qkv_ld, 32, kEpiChunkCols, 64);
+    w.t_qkv16_out32 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, w.qkv_ld, 32, kEpiChunkCols, 64);  // CTA-pair kernel
     w.t_h16_out32 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
-    w.t_qkv16_out64 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, 3 * H, 32, 64, 128);  // chained kernels: one 32 x 64 store per warp and tile
+    w.t_qkv16_out64 = make_tmap_2d(w.qkv16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, w.qkv_ld, 32, 64, 128);  // chained kernels: one 32 x 64 store per warp and tile
     w.t_h16_out64 = make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128);
     w.t_h16_out = (gemm_wide_store(bn_i_) || (bn_i_ == 192 && pair_gemm_)) ? make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, 64, 128)
                                : make_tmap_2d(w.h16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, T, I, 32, kEpiChunkCols, 64);
@@ -912,7 +931,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         GemmParams g{};
         // Q|K|V = x Wqkv^T + b                                   (qkv_projection.rs:93-138)
         if (!chain || (li == 0 && !chain_embed)) {  // chained: QKV comes from the embedding launch / the previous layer's FFN-down + LN2 launch
-            g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = 3 * H; g.act = ACT_NONE;
+            g.M = M; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out = w.qkv16; g.ldo = w.qkv_ld; g.act = ACT_NONE;
             prof_begin(KJC_K_GEMM_QKV, st);
             if (pair_gemm_) launch_gemm_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, (bn_qkv_ == 192 ? w.t_qkv16_out : w.t_qkv16_out32), g, sms, st);
             else if ((gemm_pair_mask_ & 1) && M > kGemmBlockM) launch_gemm_cta_pair(bn_qkv_, EPI_BIAS_BF16, w.t_x16, L.t_wqkv_half, w.t_qkv16_out, g, sms, st);
@@ -923,6 +942,7 @@ void Encoder::forward_micro(Workspace& w, int sms, const uint32_t* d_ids, const 
         // softmax(QK^T/sqrt(d) + mask) V, heads merged             (encoder_self_attention.rs:213-298)
         AttnParams a;
         a.qkv = w.qkv16; a.mask = d_mask; a.ctx = w.ctx16; a.B = nb; a.S = S; a.H = H; a.heads = info_.num_heads;
+        a.ld_qkv = w.qkv_ld;
         a.scale_log2e = (1.0f / sqrtf(static_cast<float>(d))) * 1.4426950408889634f;
         a.nan_if_all_masked = noalloc_convention ? 1 : 0;
         a.max_ctas = sms;

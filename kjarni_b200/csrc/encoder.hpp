@@ -154,6 +154,7 @@ class Encoder {
         float* x32 = nullptr;  // fp32-residual mode: the residual stream in fp32 (x16 is its bf16 copy for the tensor-core operands)
         float* head32 = nullptr;  // classification head: pre-classifier output [sequences, H]
         __nv_bfloat16 *x16 = nullptr, *qkv16 = nullptr, *ctx16 = nullptr, *h16 = nullptr;
+        int qkv_ld = 0;        // row pitch of qkv16 in elements: 3H, or I when qkv16 aliases h16 (see ensure_workspace)
         CUtensorMap t_x16, t_ctx16, t_h16;   // A-operand loads
         CUtensorMap t_qkv16_out, t_h16_out;  // epilogue TMA stores
         CUtensorMap t_qkv16_out32, t_h16_out32;  // 32-column store boxes (CTA-pair kernel)
@@ -174,6 +175,7 @@ class Encoder {
     KjcEncoderInfo info_{};
     std::vector<std::string> labels_;
     int num_sms_ = 0, act_ = 0, micro_tokens_ = 0;
+    bool alias_qkv_ = true;    // qkv rows laid over the FFN activation rows (KJC_NO_ALIAS_QKV)
     int chain_min_tiles_ = 0;  // micro-batches of fewer 128-row tiles take one kernel per op (KJC_CHAIN_MIN_TILES)
     int bn_qkv_ = 0, bn_h_ = 0, bn_i_ = 0;
     std::mutex mu_;
