@@ -373,15 +373,17 @@ def main():
             k["contains"] = contains[name]
         kernels[name] = k
     dom = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
-    traffic = None
+    traffic = traffic_in_step = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(dom)
+            tj = json.load(open(tp))
+            traffic = tj.get(dom)                               # cold-cache: one ncu --set full capture
+            traffic_in_step = (tj.get("in_step") or {}).get(dom)  # ncu --cache-control none: what the launch moves inside a step
         except Exception:
-            traffic = None
+            traffic = traffic_in_step = None
     roofline = {"kernel": dom, "bound": kernels[dom]["bound"], "achieved": kernels[dom]["achieved"], "peak": kernels[dom]["peak"],
-                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic,
+                "unit": kernels[dom]["unit"], "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_in_step": traffic_in_step,
                 "peak_source": peaks["src"] + (" bf16_tflops_sustained" if kernels[dom]["bound"] == "tensor" else " hbm_gbs"),
                 "how": f"CUDA events around every launch, {prof_steps} extra steps after the timed region",
                 "whole_step": {"achieved": round(value / world * flops_per_seq(H, L, I, SEQ) / 1e12, 2), "unit": "TFLOP/s",
